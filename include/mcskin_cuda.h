@@ -1,0 +1,245 @@
+/*
+ * mcskin_cuda.h — C ABI of the B200-native render hot path.
+ *
+ * This is the drop-in boundary for MCSkin RaytraceRenderer's
+ *     Image TileRenderer::render(const Scene&, const RayTracer::Config&, progress)
+ * (reference: src/raytracer/tile_renderer.h:26-28, tile_renderer.cpp:129-189).
+ * The reference has no FFI of its own (it is one C++ process); the C++ wrapper in
+ * include/mcskin/raytracer/tile_renderer.h keeps the reference's signature and
+ * flattens Scene/Config into the PODs below before calling these entry points.
+ * INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Rules of the ABI: plain pointers and sizes, fixed-width PODs, no STL, no torch
+ * types, no exceptions.  Every function returns 0 on success or a negative
+ * MC_ERR_* code; mcskin_cuda_last_error() returns the thread-local message.
+ * There is no CPU fallback: without a CUDA device every compute call fails with
+ * MC_ERR_NO_DEVICE.
+ */
+#ifndef MCSKIN_CUDA_H
+#define MCSKIN_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCSKIN_ABI_VERSION 1
+
+enum {
+    MC_OK = 0,
+    MC_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, bad texture window) */
+    MC_ERR_NO_DEVICE = -2, /* no CUDA device / driver */
+    MC_ERR_CUDA = -3,      /* a CUDA runtime call or kernel failed */
+    MC_ERR_LIMIT = -4      /* scene exceeds a documented limit */
+};
+
+/* One face texture = a window of `width*height` RGBA float texels in the scene's
+ * texel pool (row-major).  Mirrors TextureRegion (src/skin/texture_region.h:7-27).
+ *   texel_offset <  0              : null Triangle::texture  -> opaque magenta (intersection.cpp:303-306)
+ *   width <= 0 || height <= 0      : empty region            -> (0,0,0,1)      (texture_region.h:20-22) */
+typedef struct McFaceTex {
+    int32_t texel_offset;
+    int32_t width;
+    int32_t height;
+} McFaceTex;
+
+/* One Mesh, which the reference intersects as ONE axis-aligned box
+ * (src/raytracer/intersection.cpp:200-406, src/scene/mesh.h:12-30).
+ * bounds_* are the min/max over the vertices of the triangle list the reference
+ * uses for that mesh: Mesh::localTriangles when has_rotation, else Mesh::triangles
+ * (intersection.cpp:45-64,374-395).  face[f] is the texture of
+ * Mesh::triangles[2*f] for the reference face index f = 0..5
+ * (-Z,+Z,+X,-X,+Y,-Y; intersection.cpp:86-129). */
+typedef struct McBox {
+    float bounds_min[3];
+    float bounds_max[3];
+    float pivot[3];        /* Mesh::pivot */
+    float rot_x_deg;       /* Mesh::rotX */
+    float rot_z_deg;       /* Mesh::rotZ */
+    int32_t has_rotation;  /* Mesh::hasRotation */
+    int32_t is_outer_layer;/* Mesh::isOuterLayer */
+    int32_t n_triangles;   /* size of the list the bounds came from; 0 -> never hit (intersection.cpp:205) */
+    McFaceTex face[6];
+} McBox;
+
+/* Scene (src/scene/scene.h:10-34).  Light::intensity is never read by the
+ * reference and is not carried. */
+typedef struct McScene {
+    int32_t n_boxes;
+    const McBox* boxes;
+    int32_t n_texels;
+    const float* texels_rgba; /* n_texels * 4 floats */
+    float light_pos[3];
+    float light_color[4];
+    float light_radius;
+    float cam_pos[3];
+    float cam_target[3];
+    float cam_up[3];
+    float cam_fov_deg;
+    float background[4];
+} McScene;
+
+/* RayTracer::Config (src/raytracer/raytracer.h:10-38) + ShadingParams
+ * (src/raytracer/shading.h:9-14).  thread_count is accepted and ignored. */
+typedef struct McConfig {
+    int32_t width, height;
+    int32_t max_bounces;
+    int32_t samples_per_pixel;
+    int32_t tile_size;
+    int32_t thread_count;
+    int32_t soft_shadows;
+    int32_t shadow_samples;
+    int32_t ao_enabled;
+    int32_t ao_samples;
+    float ao_radius;
+    float ao_intensity;
+    int32_t dof_enabled;
+    float aperture;
+    float focus_distance;
+    int32_t gradient_bg;
+    float gradient_scale;
+    float bg_center[4];
+    float bg_edge[4];
+    float kd, ks, ambient, shininess;
+} McConfig;
+
+/* Fills *cfg with the reference defaults (raytracer.h:10-38, shading.h:9-14). */
+void mcskin_config_defaults(McConfig* cfg);
+
+/* Tile = {x, y, width, height} (tile_renderer.h:11-14). */
+typedef struct McTile {
+    int32_t x, y, width, height;
+} McTile;
+
+/* TileRenderer::generateTiles (tile_renderer.cpp:18-39).  Returns the tile count
+ * (0 for non-positive arguments); writes at most `capacity` tiles when out != NULL. */
+int32_t mcskin_generate_tiles(int32_t image_width, int32_t image_height, int32_t tile_size,
+                              McTile* out, int32_t capacity);
+
+/* progress(done, total, user): called on the calling thread, exactly `total`
+ * (= tile count) times with done = 1..total (tile_renderer.cpp:168-172). */
+typedef void (*McProgressFn)(int32_t done, int32_t total, void* user);
+
+/* Per-frame counters written by the device (all optional). */
+typedef struct McRenderStats {
+    int32_t n_tiles;
+    int32_t n_active_pixels;   /* pixels with at least one primary sample hitting geometry */
+    int64_t n_samples;         /* width*height*spp */
+    float ms_device;           /* CUDA-event time of the kernels of this call */
+    int32_t n_kernel_launches; /* kernels launched by this call */
+} McRenderStats;
+
+int32_t mcskin_cuda_device_count(void);
+const char* mcskin_cuda_last_error(void);
+int32_t mcskin_cuda_abi_version(void);
+
+/* TileRenderer::render: host scene in, host image out (row-major, width*height pixels).
+ * out_rgba_f32 : width*height*4 floats (Image::pixels), may be NULL
+ * out_rgba_u8  : width*height*4 bytes, uint8(clamp(c)*255+0.5) (image_writer.cpp:18-22), may be NULL
+ * Renders on the current thread's CUDA device `device` (>= 0). */
+int32_t mcskin_cuda_render(const McScene* scene, const McConfig* cfg, int32_t device,
+                           float* out_rgba_f32, uint8_t* out_rgba_u8,
+                           McProgressFn progress, void* user, McRenderStats* stats);
+
+/* TileRenderer::renderTile (tile_renderer.cpp:71-127): renders one tile into the
+ * caller's full-size image buffers (only the tile's pixels are written). */
+int32_t mcskin_cuda_render_tile(const McScene* scene, const McConfig* cfg, int32_t device,
+                                const McTile* tile, float* image_rgba_f32, uint8_t* image_rgba_u8);
+
+/* Same frame split over devices 0..n_devices-1 of this process by interleaved
+ * tile rows (tile row j -> device j % n_devices) and gathered on the host. */
+int32_t mcskin_cuda_render_multi(const McScene* scene, const McConfig* cfg, int32_t n_devices,
+                                 float* out_rgba_f32, uint8_t* out_rgba_u8, McRenderStats* stats);
+
+/* ---- device-resident interface (bench `value`, torch.distributed band gather) ---- */
+typedef struct McContext McContext;
+
+int32_t mcskin_cuda_context_create(int32_t device, McContext** out);
+void mcskin_cuda_context_destroy(McContext* ctx);
+/* Uploads and pre-processes scene+config (host trig, camera basis, texel pool). */
+int32_t mcskin_cuda_context_set_scene(McContext* ctx, const McScene* scene, const McConfig* cfg);
+/* Renders tile rows {first_tile_row + k*tile_row_stride} into device buffers laid
+ * out as a compact band image: the local tile rows in increasing order, each
+ * tile_size pixel rows (last one clipped), width*4 channels per row.
+ * d_out_f32 / d_out_u8 are DEVICE pointers (either may be 0).  stream is a
+ * cudaStream_t passed as void* (0 = default stream).  Asynchronous. */
+int32_t mcskin_cuda_context_render_bands(McContext* ctx, int32_t first_tile_row, int32_t tile_row_stride,
+                                         void* d_out_f32, void* d_out_u8, void* stream);
+/* Number of pixel rows the call above writes for that partition. */
+int32_t mcskin_cuda_band_rows(const McConfig* cfg, int32_t first_tile_row, int32_t tile_row_stride);
+/* Blocks until the context's work is done, fills stats of the last render. */
+int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats);
+
+/* Batched renders (one skin per scene, same config), scene i -> image i.
+ * d_out_* are device pointers to n_scenes consecutive images. */
+int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, int32_t n_scenes,
+                                         const McConfig* cfg, void* d_out_f32, void* d_out_u8, void* stream);
+
+/* ---- single-ray entry points: the reference's free functions, exercised through
+ *      the same device code (no CPU fallback).  All arrays are HOST memory. ---- */
+typedef struct McRay {
+    float origin[3];
+    float dir[3];
+} McRay;
+
+/* HitResult (src/scene/triangle.h:19-26) + the (box, face) id the reference does
+ * not expose; tri_id = box*12 + face*2, -1 on miss. */
+typedef struct McHit {
+    int32_t hit;
+    float t;
+    float point[3];
+    float normal[3];
+    float tex_color[4];
+    int32_t is_outer_layer;
+    int32_t box;
+    int32_t face;
+} McHit;
+
+/* intersectScene (intersection.cpp:408-421); box >= 0 restricts to intersectMesh of that box. */
+int32_t mcskin_cuda_intersect(const McScene* scene, int32_t device, int32_t box,
+                              const McRay* rays, int32_t n, McHit* out);
+/* RayTracer::traceRay(ray, scene, depth, cfg->max_bounces, params, use_config ? &config : nullptr)
+ * (raytracer.cpp:82-148). out_rgba: n*4 floats. */
+int32_t mcskin_cuda_trace(const McScene* scene, const McConfig* cfg, int32_t device, int32_t use_config,
+                          int32_t depth, const McRay* rays, int32_t n, float* out_rgba);
+/* shade(hit, viewDir, light, scene, params, shadowFactor) (shading.cpp:62-96). */
+int32_t mcskin_cuda_shade(const McScene* scene, const McConfig* cfg, int32_t device,
+                          const McHit* hits, const float* view_dirs /* n*3 */, const float* shadow_factors /* n */,
+                          int32_t n, float* out_rgba);
+/* isInShadow(point, normal, lightPos, scene) (shading.cpp:14-26): out[i] = 0/1. */
+int32_t mcskin_cuda_in_shadow(const McScene* scene, int32_t device, const float* points, const float* normals,
+                              const float* light_positions, int32_t n, int32_t* out);
+/* computeSoftShadow(point, normal, scene.light, scene, samples, seed) (shading.cpp:28-60). */
+int32_t mcskin_cuda_soft_shadow(const McScene* scene, int32_t device, const float* points, const float* normals,
+                                const uint32_t* seeds, int32_t samples, int32_t n, float* out);
+/* RayTracer::computeAO(point, normal, scene, samples, radius, seed) (raytracer.cpp:38-78). */
+int32_t mcskin_cuda_ambient_occlusion(const McScene* scene, int32_t device, const float* points,
+                                      const float* normals, const uint32_t* seeds, int32_t samples,
+                                      float radius, int32_t n, float* out);
+/* Camera::generateRay(u, v, aspect) (camera.cpp:8-26). uv: n*2 floats. */
+int32_t mcskin_cuda_generate_rays(const McScene* scene, int32_t device, float aspect, const float* uv,
+                                  int32_t n, McRay* out);
+/* RayTracer::backgroundColor(scene, u, v, use_config ? &config : nullptr) (raytracer.cpp:16-34). */
+int32_t mcskin_cuda_background(const McScene* scene, const McConfig* cfg, int32_t device, int32_t use_config,
+                               const float* uv, int32_t n, float* out_rgba);
+/* Hit mask + triangle id of the pinhole ray through each pixel centre
+ * (u=(px+.5)/W, v=(py+.5)/H): out_tri_id[py*W+px] = box*12+face*2, or -1. */
+int32_t mcskin_cuda_aov(const McScene* scene, const McConfig* cfg, int32_t device, int32_t* out_tri_id);
+
+/* ---- callers either side of the path: skin atlas -> scene ---- */
+/* Builds the flat scene the reference's SkinParser::parse + MeshBuilder::buildScene
+ * produce for an RGBA8 atlas (64x64 or 64x32) and a pose (12 floats: rotX,rotZ for
+ * head, body, rightArm, leftArm, rightLeg, leftLeg; NULL = standing).
+ * (skin_parser.cpp:11-132, mesh_builder.cpp:66-202.)  Host-side, no GPU needed.
+ * boxes_out: capacity 12; texels_out: capacity MCSKIN_MAX_SKIN_TEXELS*4 floats. */
+#define MCSKIN_MAX_SKIN_BOXES 12
+#define MCSKIN_MAX_SKIN_TEXELS 4096
+int32_t mcskin_build_skin_scene(const uint8_t* atlas_rgba8, int32_t atlas_w, int32_t atlas_h,
+                                const float* pose12, McBox* boxes_out, float* texels_out,
+                                McScene* scene_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCSKIN_CUDA_H */
