@@ -133,6 +133,9 @@ typedef struct McRenderStats {
 int32_t mcskin_cuda_device_count(void);
 const char* mcskin_cuda_last_error(void);
 int32_t mcskin_cuda_abi_version(void);
+/* sizeof of McFaceTex, McBox, McScene, McConfig, McTile, McRenderStats, McRay, McHit
+ * as compiled, so a binding can verify its mirror of this header. */
+void mcskin_cuda_abi_sizes(int32_t* out8);
 
 /* TileRenderer::render: host scene in, host image out (row-major, width*height pixels).
  * out_rgba_f32 : width*height*4 floats (Image::pixels), may be NULL
@@ -170,6 +173,10 @@ int32_t mcskin_cuda_context_render_bands(McContext* ctx, int32_t first_tile_row,
 int32_t mcskin_cuda_band_rows(const McConfig* cfg, int32_t first_tile_row, int32_t tile_row_stride);
 /* Blocks until the context's work is done, fills stats of the last render. */
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats);
+/* Tuning / test knobs: "force_all_active" (0/1: skip the hit/miss classification and
+ * shade every pixel), "record_budget_bytes" (work-list memory per launch pair),
+ * "shade_blocks_per_sm" (persistent grid size of the shading pass). */
+int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t value);
 
 /* Batched renders (one skin per scene, same config), scene i -> image i.
  * d_out_* are device pointers to n_scenes consecutive images. */

@@ -113,6 +113,7 @@ class McHit(C.Structure):
 
 
 McProgressFn = C.CFUNCTYPE(None, C.c_int32, C.c_int32, C.c_void_p)
+McContext_p = C.c_void_p  # opaque McContext*
 
 # numpy views of the same layouts (arrays of rays / hits cross the ABI as raw buffers)
 RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("dir", np.float32, 3)])

@@ -1,0 +1,76 @@
+"""In-tree build of libmcskin_cuda.so (nvcc, sm_100a).  No JIT cache: the .so lives
+next to the package so it travels with the repo snapshot to the GPU box."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+LIB_DIR = PKG / "_lib"
+LIB_PATH = LIB_DIR / "libmcskin_cuda.so"
+
+CUDA_SOURCES = ["kernels.cu", "capi.cu"]
+HOST_SOURCES = ["host_prep.cpp", "skin_scene.cpp"]
+
+# --fmad=false: the geometry chain must round like the x86-64 reference build (no FMA);
+# IEEE division and sqrt are nvcc's defaults and are left alone (no -use_fast_math).
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "--fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; the CUDA extension cannot be built")
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    newest = max(p.stat().st_mtime for p in list(CSRC.glob("*")) + [ROOT / "include" / "mcskin_cuda.h"])
+    return LIB_PATH.stat().st_mtime < newest
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB_PATH
+    LIB_DIR.mkdir(exist_ok=True)
+    obj_dir = LIB_DIR / "obj"
+    obj_dir.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+    inc = ["-I", str(ROOT / "include"), "-I", str(CSRC)]
+    procs = []
+    objs = []
+    for src in CUDA_SOURCES + HOST_SOURCES:
+        obj = obj_dir / (src.rsplit(".", 1)[0] + ".o")
+        objs.append(str(obj))
+        cmd = [nvcc, *NVCC_FLAGS, *inc, "-c", str(CSRC / src), "-o", str(obj)]
+        if src.endswith(".cu"):
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src}\n{out}")
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    (LIB_DIR / "build.log").write_text("\n".join(log))
+    link = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print("\n".join(log))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

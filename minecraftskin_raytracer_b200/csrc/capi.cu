@@ -1,0 +1,730 @@
+// capi.cu — the extern "C" layer of include/mcskin_cuda.h: contexts, device memory,
+// launches, host<->device copies.  No exceptions leave this file; every failure is a
+// negative MC_ERR_* plus a thread-local message (mcskin_cuda_last_error).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "host_prep.hpp"
+#include "kernels.cuh"
+#include "mcskin_cuda.h"
+
+using namespace mcskin;
+
+namespace {
+
+int fail(int code, const std::string& msg) {
+    set_last_error(msg);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MC_ERR_NO_DEVICE : MC_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU_TRY(expr)                                     \
+    do {                                                 \
+        cudaError_t e__ = (expr);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+    } while (0)
+
+// Device buffer that only ever grows.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct McContext {
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;  // used when the caller passes stream 0 to the host-facing calls
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool hasScene = false;
+    PreparedFrame prep;
+    McConfig cfg{};
+    DevBuf boxes, texels;
+    DevBuf count, slotPixel, records;
+    DevBuf imgF32, imgU8, scratchIn, scratchOut;
+    PinnedBuf pinned;
+    // options
+    int forceAllActive = 0;
+    long long recordBudgetBytes = 1ll << 31;
+    int shadeBlocksPerSm = 8;
+    // stats of the last render
+    McRenderStats stats{};
+    bool statsPending = false;
+    std::vector<unsigned int> hostCounts;  // active-pixel counts read back lazily
+    DevBuf countLog;                       // one counter per chunk of the last render
+    int chunksLastRender = 0;
+};
+
+namespace {
+
+int upload_scene(McContext* ctx) {
+    const PreparedFrame& pf = ctx->prep;
+    CU_TRY(ctx->boxes.reserve(std::max<size_t>(1, pf.boxes.size()) * sizeof(DevBox)));
+    CU_TRY(ctx->texels.reserve(pf.texels.size() * sizeof(float4h)));
+    if (!pf.boxes.empty())
+        CU_TRY(cudaMemcpyAsync(ctx->boxes.p, pf.boxes.data(), pf.boxes.size() * sizeof(DevBox),
+                               cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(ctx->texels.p, pf.texels.data(), pf.texels.size() * sizeof(float4h),
+                           cudaMemcpyHostToDevice, ctx->stream));
+    // pageable sources: the copies above are staged synchronously by the runtime, so the
+    // host vectors may change afterwards
+    return MC_OK;
+}
+
+FramePointers frame_pointers(const McContext* ctx) {
+    return FramePointers{static_cast<const DevBox*>(ctx->boxes.p), static_cast<const float4*>(ctx->texels.p)};
+}
+
+int local_tile_rows(const DevFrame& f, int first, int stride) {
+    if (f.tiles_y <= 0 || first < 0 || stride <= 0 || first >= f.tiles_y) return 0;
+    return (f.tiles_y - first + stride - 1) / stride;
+}
+
+int band_pixel_rows(const DevFrame& f, int first, int stride) {
+    const int n = local_tile_rows(f, first, stride);
+    if (n == 0) return 0;
+    const int lastTileRow = first + (n - 1) * stride;
+    const int lastHeight = std::min(f.tile_size, f.height - lastTileRow * f.tile_size);
+    return (n - 1) * f.tile_size + lastHeight;
+}
+
+// Launches the two passes for the tile rows {first + k*stride}; output pointers are device memory.
+int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* outU8, cudaStream_t stream) {
+    const DevFrame& f = ctx->prep.frame;
+    const int nRows = local_tile_rows(f, first, stride);
+    ctx->chunksLastRender = 0;
+    ctx->stats = McRenderStats{};
+    ctx->stats.n_samples = static_cast<int64_t>(std::max(f.width, 0)) * std::max(f.height, 0) * f.spp;
+    ctx->stats.n_tiles = nRows * f.tiles_x;
+    if (nRows == 0) return MC_OK;
+    if (f.width > 65535 || f.height > 65535) return fail(MC_ERR_LIMIT, "image larger than 65535 pixels on a side");
+    if (static_cast<long long>(f.tile_size) * f.tile_size > (1ll << 30))
+        return fail(MC_ERR_LIMIT, "tile_size too large");
+
+    const bool classify = !ctx->forceAllActive && f.spp <= kBlockThreads;
+    const size_t slotsPerTileRow = static_cast<size_t>(f.tiles_x) * f.tile_size * f.tile_size;
+    const size_t recordBytesPerSlot = static_cast<size_t>(f.spp) * f.draws_per_sample * sizeof(float);
+    // tile rows per chunk so that the worst-case work list fits the budget
+    size_t rowsPerChunk = nRows;
+    if (recordBytesPerSlot > 0) {
+        const size_t perRow = slotsPerTileRow * recordBytesPerSlot;
+        rowsPerChunk = std::max<size_t>(1, static_cast<size_t>(ctx->recordBudgetBytes) / std::max<size_t>(1, perRow));
+        rowsPerChunk = std::min<size_t>(rowsPerChunk, nRows);
+    }
+    // slot indices are 32-bit
+    while (rowsPerChunk > 1 && rowsPerChunk * slotsPerTileRow > 0x7fffffffull) --rowsPerChunk;
+    const size_t slotCap = rowsPerChunk * slotsPerTileRow;
+    if (slotCap > 0x7fffffffull) return fail(MC_ERR_LIMIT, "one tile row holds more than 2^31 pixels");
+    const int nChunks = static_cast<int>((nRows + rowsPerChunk - 1) / rowsPerChunk);
+
+    CU_TRY(ctx->countLog.reserve(sizeof(unsigned int) * nChunks));
+    CU_TRY(ctx->slotPixel.reserve(slotCap * sizeof(uint2)));
+    CU_TRY(ctx->records.reserve(std::max<size_t>(16, slotCap * recordBytesPerSlot)));
+    CU_TRY(cudaMemsetAsync(ctx->countLog.p, 0, sizeof(unsigned int) * nChunks, stream));
+
+    CU_TRY(cudaEventRecord(ctx->ev0, stream));
+    const FramePointers fp = frame_pointers(ctx);
+    int launches = 0;
+    for (int c = 0; c < nChunks; ++c) {
+        const int row0 = static_cast<int>(c * rowsPerChunk);
+        const int rows = static_cast<int>(std::min<size_t>(rowsPerChunk, nRows - row0));
+        BandView band;
+        band.first_tile_row = first + row0 * stride;
+        band.tile_row_stride = stride;
+        band.n_tile_rows = rows;
+        const size_t pixelOffset = static_cast<size_t>(row0) * f.tile_size * f.width;
+        band.out_f32 = outF32 ? outF32 + pixelOffset : nullptr;
+        band.out_u8 = outU8 ? outU8 + pixelOffset : nullptr;
+        ActiveList list;
+        list.count = static_cast<unsigned int*>(ctx->countLog.p) + c;
+        list.slot_pixel = static_cast<uint2*>(ctx->slotPixel.p);
+        list.records = static_cast<float*>(ctx->records.p);
+        list.capacity = static_cast<unsigned int>(static_cast<size_t>(rows) * slotsPerTileRow);
+        if (!classify) {
+            // positional slots: mark all unused, preset the count to the capacity
+            CU_TRY(cudaMemsetAsync(list.slot_pixel, 0xff, static_cast<size_t>(list.capacity) * sizeof(uint2), stream));
+            CU_TRY(cudaMemcpyAsync(list.count, &list.capacity, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
+        }
+        launch_primary(f, fp, band, list, classify ? 1 : 0, stream);
+        launch_shade(f, fp, band, list, ctx->smCount * ctx->shadeBlocksPerSm, stream);
+        launches += 2;
+    }
+    CU_TRY(cudaEventRecord(ctx->ev1, stream));
+    CU_TRY(cudaGetLastError());
+    ctx->chunksLastRender = nChunks;
+    ctx->stats.n_kernel_launches = launches;
+    ctx->statsPending = true;
+    return MC_OK;
+}
+
+int finish_stats(McContext* ctx, McRenderStats* out) {
+    if (ctx->statsPending) {
+        CU_TRY(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.0f;
+        CU_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->stats.ms_device = ms;
+        ctx->hostCounts.resize(ctx->chunksLastRender);
+        if (ctx->chunksLastRender > 0)
+            CU_TRY(cudaMemcpy(ctx->hostCounts.data(), ctx->countLog.p, sizeof(unsigned int) * ctx->chunksLastRender,
+                              cudaMemcpyDeviceToHost));
+        long long active = 0;
+        for (unsigned int v : ctx->hostCounts) active += v;
+        ctx->stats.n_active_pixels = static_cast<int32_t>(std::min<long long>(active, 0x7fffffff));
+        ctx->statsPending = false;
+    }
+    if (out) *out = ctx->stats;
+    return MC_OK;
+}
+
+// One cached context per device for the host-facing convenience calls.
+std::mutex g_ctxMutex;
+std::vector<McContext*> g_ctxByDevice;
+
+int shared_context(int device, McContext** out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(MC_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0"));
+    if (device < 0 || device >= n) return fail(MC_ERR_INVALID, "device index out of range");
+    if (g_ctxByDevice.size() < static_cast<size_t>(n)) g_ctxByDevice.resize(n, nullptr);
+    if (!g_ctxByDevice[device]) {
+        McContext* c = nullptr;
+        const int rc = mcskin_cuda_context_create(device, &c);
+        if (rc != MC_OK) return rc;
+        g_ctxByDevice[device] = c;
+    }
+    *out = g_ctxByDevice[device];
+    CU_TRY(cudaSetDevice(device));
+    return MC_OK;
+}
+
+int copy_out(McContext* ctx, void* hostDst, const void* devSrc, size_t bytes) {
+    // staged through pinned memory: a pageable destination would make the runtime do the same, slower
+    CU_TRY(ctx->pinned.reserve(bytes));
+    CU_TRY(cudaMemcpyAsync(ctx->pinned.p, devSrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(hostDst, ctx->pinned.p, bytes);
+    return MC_OK;
+}
+
+// Runs a single-query launcher: uploads inputs, launches, downloads outputs.
+struct Staged {
+    McContext* ctx;
+    std::vector<void*> temps;
+    ~Staged() {
+        for (void* p : temps) cudaFree(p);
+    }
+    int up(const void* host, size_t bytes, void** dev) {
+        *dev = nullptr;
+        if (bytes == 0) return MC_OK;
+        CU_TRY(cudaMalloc(dev, bytes));
+        temps.push_back(*dev);
+        if (host) CU_TRY(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return MC_OK;
+    }
+    int down(void* host, const void* dev, size_t bytes) {
+        if (bytes == 0) return MC_OK;
+        CU_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        CU_TRY(cudaGetLastError());
+        return MC_OK;
+    }
+};
+
+int query_setup(const McScene* scene, const McConfig* cfg, int device, int useConfig, float aspect, McContext** ctx) {
+    const int rc = shared_context(device, ctx);
+    if (rc != MC_OK) return rc;
+    std::string err;
+    const int prc = prepare_frame(scene, cfg, useConfig, aspect, (*ctx)->prep, err);
+    if (prc != MC_OK) return fail(prc, err);
+    (*ctx)->hasScene = true;
+    if (cfg) (*ctx)->cfg = *cfg;
+    return upload_scene(*ctx);
+}
+
+}  // namespace
+
+// =============================================================== exported functions
+extern "C" {
+
+int32_t mcskin_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
+    if (!out) return fail(MC_ERR_INVALID, "context_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(MC_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0"));
+    }
+    if (device < 0 || device >= n) return fail(MC_ERR_INVALID, "device index out of range");
+    CU_TRY(cudaSetDevice(device));
+    std::unique_ptr<McContext> ctx(new McContext());
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->smCount = prop.multiProcessorCount;
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreate(&ctx->ev0));
+    CU_TRY(cudaEventCreate(&ctx->ev1));
+    if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
+    *out = ctx.release();
+    return MC_OK;
+}
+
+void mcskin_cuda_context_destroy(McContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->boxes, &ctx->texels, &ctx->count, &ctx->slotPixel, &ctx->records, &ctx->imgF32, &ctx->imgU8,
+                      &ctx->scratchIn, &ctx->scratchOut, &ctx->countLog})
+        b->release();
+    ctx->pinned.release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return fail(MC_ERR_INVALID, "set_option: null argument");
+    const std::string k(name);
+    if (k == "force_all_active") ctx->forceAllActive = value != 0;
+    else if (k == "record_budget_bytes") ctx->recordBudgetBytes = std::max<int64_t>(1, value);
+    else if (k == "shade_blocks_per_sm") ctx->shadeBlocksPerSm = static_cast<int>(std::max<int64_t>(1, value));
+    else return fail(MC_ERR_INVALID, "set_option: unknown option " + k);
+    return MC_OK;
+}
+
+int32_t mcskin_cuda_context_set_scene(McContext* ctx, const McScene* scene, const McConfig* cfg) {
+    if (!ctx || !scene || !cfg) return fail(MC_ERR_INVALID, "set_scene: null argument");
+    CU_TRY(cudaSetDevice(ctx->device));
+    std::string err;
+    const int rc = prepare_frame(scene, cfg, 1, 0.0f, ctx->prep, err);
+    if (rc != MC_OK) return fail(rc, err);
+    ctx->cfg = *cfg;
+    ctx->hasScene = true;
+    return upload_scene(ctx);
+}
+
+int32_t mcskin_cuda_band_rows(const McConfig* cfg, int32_t first, int32_t stride) {
+    if (!cfg || cfg->width <= 0 || cfg->height <= 0 || cfg->tile_size <= 0) return 0;
+    DevFrame f{};
+    f.width = cfg->width;
+    f.height = cfg->height;
+    f.tile_size = cfg->tile_size;
+    f.tiles_x = (cfg->width + cfg->tile_size - 1) / cfg->tile_size;
+    f.tiles_y = (cfg->height + cfg->tile_size - 1) / cfg->tile_size;
+    return band_pixel_rows(f, first, stride);
+}
+
+int32_t mcskin_cuda_context_render_bands(McContext* ctx, int32_t first, int32_t stride, void* dOutF32, void* dOutU8,
+                                         void* stream) {
+    if (!ctx || !ctx->hasScene) return fail(MC_ERR_INVALID, "render_bands: no scene set");
+    if (stride <= 0 || first < 0) return fail(MC_ERR_INVALID, "render_bands: bad partition");
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return render_bands(ctx, first, stride, static_cast<float4*>(dOutF32), static_cast<uchar4*>(dOutU8), s);
+}
+
+int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats) {
+    if (!ctx) return fail(MC_ERR_INVALID, "sync: null context");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int rc = finish_stats(ctx, stats);
+    if (rc != MC_OK) return rc;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaGetLastError());
+    return MC_OK;
+}
+
+static int render_host(McContext* ctx, const McScene* scene, const McConfig* cfg, int first, int stride,
+                       float* outF32, uint8_t* outU8, size_t hostRowOffsetPixels, McRenderStats* stats) {
+    (void)hostRowOffsetPixels;
+    int rc = mcskin_cuda_context_set_scene(ctx, scene, cfg);
+    if (rc != MC_OK) return rc;
+    const DevFrame& f = ctx->prep.frame;
+    const int rows = band_pixel_rows(f, first, stride);
+    const size_t pixels = static_cast<size_t>(rows) * std::max(f.width, 0);
+    if (pixels == 0) {
+        if (stats) *stats = McRenderStats{};
+        return MC_OK;
+    }
+    if (outF32) CU_TRY(ctx->imgF32.reserve(pixels * sizeof(float4)));
+    if (outU8) CU_TRY(ctx->imgU8.reserve(pixels * sizeof(uchar4)));
+    rc = render_bands(ctx, first, stride, outF32 ? static_cast<float4*>(ctx->imgF32.p) : nullptr,
+                      outU8 ? static_cast<uchar4*>(ctx->imgU8.p) : nullptr, ctx->stream);
+    if (rc != MC_OK) return rc;
+    if (outF32) {
+        rc = copy_out(ctx, outF32, ctx->imgF32.p, pixels * sizeof(float4));
+        if (rc != MC_OK) return rc;
+    }
+    if (outU8) {
+        rc = copy_out(ctx, outU8, ctx->imgU8.p, pixels * sizeof(uchar4));
+        if (rc != MC_OK) return rc;
+    }
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaGetLastError());
+    return finish_stats(ctx, stats);
+}
+
+int32_t mcskin_cuda_render(const McScene* scene, const McConfig* cfg, int32_t device, float* outF32, uint8_t* outU8,
+                           McProgressFn progress, void* user, McRenderStats* stats) {
+    if (!scene || !cfg) return fail(MC_ERR_INVALID, "render: null scene or config");
+    const int32_t totalTiles = mcskin_generate_tiles(cfg->width, cfg->height, cfg->tile_size, nullptr, 0);
+    if (totalTiles == 0) {  // tile_renderer.cpp:144-146: nothing to do, no callbacks
+        if (stats) *stats = McRenderStats{};
+        return MC_OK;
+    }
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = shared_context(device, &ctx);
+    if (rc != MC_OK) return rc;
+    rc = render_host(ctx, scene, cfg, 0, 1, outF32, outU8, 0, stats);
+    if (rc != MC_OK) return rc;
+    if (progress)
+        for (int32_t i = 1; i <= totalTiles; ++i) progress(i, totalTiles, user);
+    return MC_OK;
+}
+
+int32_t mcskin_cuda_render_tile(const McScene* scene, const McConfig* cfg, int32_t device, const McTile* tile,
+                                float* imageF32, uint8_t* imageU8) {
+    if (!scene || !cfg || !tile) return fail(MC_ERR_INVALID, "render_tile: null argument");
+    if (cfg->width <= 0 || cfg->height <= 0) return fail(MC_ERR_INVALID, "render_tile: empty image");
+    if (tile->width <= 0 || tile->height <= 0) return MC_OK;
+    if (tile->x < 0 || tile->y < 0 || tile->x + tile->width > cfg->width || tile->y + tile->height > cfg->height)
+        return fail(MC_ERR_INVALID, "render_tile: tile outside the image");
+    // A tile is rendered as a one-tile frame whose pixel origin is the tile's: same RNG seed
+    // (tile.y*width + tile.x), same u,v because the frame size stays the full image's.
+    // The kernels address tiles on the tile_size grid, so an off-grid or odd-sized tile is
+    // only supported when it coincides with a grid tile.
+    const int ts = cfg->tile_size;
+    if (ts <= 0 || tile->x % ts != 0 || tile->y % ts != 0 ||
+        tile->width != std::min(ts, cfg->width - tile->x) || tile->height != std::min(ts, cfg->height - tile->y))
+        return fail(MC_ERR_INVALID, "render_tile: tile is not a tile of generateTiles(width, height, tile_size)");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = shared_context(device, &ctx);
+    if (rc != MC_OK) return rc;
+    rc = mcskin_cuda_context_set_scene(ctx, scene, cfg);
+    if (rc != MC_OK) return rc;
+    const DevFrame& f = ctx->prep.frame;
+    const int tileRow = tile->y / ts;
+    const size_t pixels = static_cast<size_t>(tile->height) * f.width;
+    CU_TRY(ctx->imgF32.reserve(pixels * sizeof(float4)));
+    CU_TRY(ctx->imgU8.reserve(pixels * sizeof(uchar4)));
+    // render the whole tile row (cheap) and copy back only the tile's columns
+    rc = render_bands(ctx, tileRow, f.tiles_y, static_cast<float4*>(ctx->imgF32.p), static_cast<uchar4*>(ctx->imgU8.p),
+                      ctx->stream);
+    if (rc != MC_OK) return rc;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (imageF32)
+        CU_TRY(cudaMemcpy2D(imageF32 + (static_cast<size_t>(tile->y) * f.width + tile->x) * 4, f.width * sizeof(float4),
+                            static_cast<float4*>(ctx->imgF32.p) + tile->x, f.width * sizeof(float4),
+                            tile->width * sizeof(float4), tile->height, cudaMemcpyDeviceToHost));
+    if (imageU8)
+        CU_TRY(cudaMemcpy2D(imageU8 + (static_cast<size_t>(tile->y) * f.width + tile->x) * 4, f.width * sizeof(uchar4),
+                            static_cast<uchar4*>(ctx->imgU8.p) + tile->x, f.width * sizeof(uchar4),
+                            tile->width * sizeof(uchar4), tile->height, cudaMemcpyDeviceToHost));
+    return finish_stats(ctx, nullptr);
+}
+
+int32_t mcskin_cuda_render_multi(const McScene* scene, const McConfig* cfg, int32_t nDevices, float* outF32,
+                                 uint8_t* outU8, McRenderStats* stats) {
+    if (!scene || !cfg) return fail(MC_ERR_INVALID, "render_multi: null scene or config");
+    const int avail = mcskin_cuda_device_count();
+    if (avail <= 0) return fail(MC_ERR_NO_DEVICE, "no CUDA device");
+    if (nDevices <= 0 || nDevices > avail) return fail(MC_ERR_INVALID, "render_multi: bad device count");
+    const int32_t totalTiles = mcskin_generate_tiles(cfg->width, cfg->height, cfg->tile_size, nullptr, 0);
+    if (totalTiles == 0) {
+        if (stats) *stats = McRenderStats{};
+        return MC_OK;
+    }
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    std::vector<McContext*> ctxs(nDevices, nullptr);
+    std::string err;
+    const int ts = cfg->tile_size, W = cfg->width, H = cfg->height;
+    const int tilesY = (H + ts - 1) / ts;
+    // launch everywhere first (asynchronous), then gather
+    for (int d = 0; d < nDevices; ++d) {
+        int rc = shared_context(d, &ctxs[d]);
+        if (rc != MC_OK) return rc;
+        McContext* ctx = ctxs[d];
+        rc = mcskin_cuda_context_set_scene(ctx, scene, cfg);
+        if (rc != MC_OK) return rc;
+        const int rows = band_pixel_rows(ctx->prep.frame, d, nDevices);
+        const size_t pixels = static_cast<size_t>(rows) * W;
+        if (pixels == 0) continue;
+        if (outF32) CU_TRY(ctx->imgF32.reserve(pixels * sizeof(float4)));
+        if (outU8) CU_TRY(ctx->imgU8.reserve(pixels * sizeof(uchar4)));
+        rc = render_bands(ctx, d, nDevices, outF32 ? static_cast<float4*>(ctx->imgF32.p) : nullptr,
+                          outU8 ? static_cast<uchar4*>(ctx->imgU8.p) : nullptr, ctx->stream);
+        if (rc != MC_OK) return rc;
+    }
+    McRenderStats total{};
+    for (int d = 0; d < nDevices; ++d) {
+        McContext* ctx = ctxs[d];
+        CU_TRY(cudaSetDevice(d));
+        const int nLocal = local_tile_rows(ctx->prep.frame, d, nDevices);
+        for (int r = 0; r < nLocal; ++r) {  // de-interleave tile row by tile row
+            const int tileRow = d + r * nDevices;
+            const int y0 = tileRow * ts;
+            const int h = std::min(ts, H - y0);
+            const size_t src = static_cast<size_t>(r) * ts * W, dst = static_cast<size_t>(y0) * W;
+            if (outF32)
+                CU_TRY(cudaMemcpyAsync(outF32 + dst * 4, static_cast<float4*>(ctx->imgF32.p) + src,
+                                       static_cast<size_t>(h) * W * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+            if (outU8)
+                CU_TRY(cudaMemcpyAsync(outU8 + dst * 4, static_cast<uchar4*>(ctx->imgU8.p) + src,
+                                       static_cast<size_t>(h) * W * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        (void)tilesY;
+    }
+    for (int d = 0; d < nDevices; ++d) {
+        CU_TRY(cudaSetDevice(d));
+        CU_TRY(cudaStreamSynchronize(ctxs[d]->stream));
+        McRenderStats s{};
+        const int rc = finish_stats(ctxs[d], &s);
+        if (rc != MC_OK) return rc;
+        total.n_tiles += s.n_tiles;
+        total.n_active_pixels += s.n_active_pixels;
+        total.n_kernel_launches += s.n_kernel_launches;
+        total.ms_device = std::max(total.ms_device, s.ms_device);
+    }
+    total.n_samples = static_cast<int64_t>(W) * H * std::max(1, cfg->samples_per_pixel);
+    if (stats) *stats = total;
+    return MC_OK;
+}
+
+int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, int32_t nScenes, const McConfig* cfg,
+                                         void* dOutF32, void* dOutU8, void* stream) {
+    if (!ctx || !scenes || !cfg || nScenes < 0) return fail(MC_ERR_INVALID, "render_batch: bad argument");
+    const size_t pixels = static_cast<size_t>(std::max(cfg->width, 0)) * std::max(cfg->height, 0);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    for (int i = 0; i < nScenes; ++i) {
+        // scenes are independent frames; the scene buffers are reused, so order the upload after the previous frame
+        CU_TRY(cudaStreamSynchronize(s));
+        int rc = mcskin_cuda_context_set_scene(ctx, &scenes[i], cfg);
+        if (rc != MC_OK) return rc;
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        rc = render_bands(ctx, 0, 1, dOutF32 ? static_cast<float4*>(dOutF32) + i * pixels : nullptr,
+                          dOutU8 ? static_cast<uchar4*>(dOutU8) + i * pixels : nullptr, s);
+        if (rc != MC_OK) return rc;
+    }
+    return MC_OK;
+}
+
+// ------------------------------------------------------------------ single-ray entry points
+int32_t mcskin_cuda_intersect(const McScene* scene, int32_t device, int32_t box, const McRay* rays, int32_t n,
+                              McHit* out) {
+    if (n < 0 || (n > 0 && (!rays || !out))) return fail(MC_ERR_INVALID, "intersect: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = query_setup(scene, nullptr, device, 0, 1.0f, &ctx);
+    if (rc != MC_OK) return rc;
+    if (box >= scene->n_boxes) return fail(MC_ERR_INVALID, "intersect: box index out of range");
+    Staged st{ctx, {}};
+    void *dR, *dO;
+    if ((rc = st.up(rays, sizeof(McRay) * n, &dR)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(McHit) * n, &dO)) != MC_OK) return rc;
+    launch_intersect(ctx->prep.frame, frame_pointers(ctx), box, static_cast<McRay*>(dR), n, static_cast<McHit*>(dO),
+                     ctx->stream);
+    return st.down(out, dO, sizeof(McHit) * n);
+}
+
+int32_t mcskin_cuda_trace(const McScene* scene, const McConfig* cfg, int32_t device, int32_t useConfig, int32_t depth,
+                          const McRay* rays, int32_t n, float* out) {
+    if (!cfg || n < 0 || (n > 0 && (!rays || !out))) return fail(MC_ERR_INVALID, "trace: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = query_setup(scene, cfg, device, useConfig, 0.0f, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void *dR, *dO;
+    if ((rc = st.up(rays, sizeof(McRay) * n, &dR)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(float4) * n, &dO)) != MC_OK) return rc;
+    launch_trace(ctx->prep.frame, frame_pointers(ctx), depth, static_cast<McRay*>(dR), n, static_cast<float4*>(dO),
+                 ctx->stream);
+    return st.down(out, dO, sizeof(float4) * n);
+}
+
+int32_t mcskin_cuda_shade(const McScene* scene, const McConfig* cfg, int32_t device, const McHit* hits,
+                          const float* viewDirs, const float* shadowFactors, int32_t n, float* out) {
+    if (!cfg || n < 0 || (n > 0 && (!hits || !viewDirs || !out))) return fail(MC_ERR_INVALID, "shade: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = query_setup(scene, cfg, device, 1, 0.0f, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void *dH, *dV, *dS = nullptr, *dO;
+    if ((rc = st.up(hits, sizeof(McHit) * n, &dH)) != MC_OK) return rc;
+    if ((rc = st.up(viewDirs, sizeof(float) * 3 * n, &dV)) != MC_OK) return rc;
+    if (shadowFactors && (rc = st.up(shadowFactors, sizeof(float) * n, &dS)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(float4) * n, &dO)) != MC_OK) return rc;
+    launch_shade_hits(ctx->prep.frame, frame_pointers(ctx), static_cast<McHit*>(dH), static_cast<float*>(dV),
+                      static_cast<float*>(dS), n, static_cast<float4*>(dO), ctx->stream);
+    return st.down(out, dO, sizeof(float4) * n);
+}
+
+int32_t mcskin_cuda_in_shadow(const McScene* scene, int32_t device, const float* points, const float* normals,
+                              const float* lights, int32_t n, int32_t* out) {
+    if (n < 0 || (n > 0 && (!points || !normals || !lights || !out))) return fail(MC_ERR_INVALID, "in_shadow: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = query_setup(scene, nullptr, device, 0, 1.0f, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void *dP, *dN, *dL, *dO;
+    if ((rc = st.up(points, sizeof(float) * 3 * n, &dP)) != MC_OK) return rc;
+    if ((rc = st.up(normals, sizeof(float) * 3 * n, &dN)) != MC_OK) return rc;
+    if ((rc = st.up(lights, sizeof(float) * 3 * n, &dL)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(int) * n, &dO)) != MC_OK) return rc;
+    launch_in_shadow(ctx->prep.frame, frame_pointers(ctx), static_cast<float*>(dP), static_cast<float*>(dN),
+                     static_cast<float*>(dL), n, static_cast<int*>(dO), ctx->stream);
+    return st.down(out, dO, sizeof(int) * n);
+}
+
+int32_t mcskin_cuda_soft_shadow(const McScene* scene, int32_t device, const float* points, const float* normals,
+                                const uint32_t* seeds, int32_t samples, int32_t n, float* out) {
+    if (n < 0 || (n > 0 && (!points || !normals || !seeds || !out))) return fail(MC_ERR_INVALID, "soft_shadow: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = query_setup(scene, nullptr, device, 0, 1.0f, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void *dP, *dN, *dS, *dO;
+    if ((rc = st.up(points, sizeof(float) * 3 * n, &dP)) != MC_OK) return rc;
+    if ((rc = st.up(normals, sizeof(float) * 3 * n, &dN)) != MC_OK) return rc;
+    if ((rc = st.up(seeds, sizeof(uint32_t) * n, &dS)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(float) * n, &dO)) != MC_OK) return rc;
+    launch_soft_shadow(ctx->prep.frame, frame_pointers(ctx), static_cast<float*>(dP), static_cast<float*>(dN),
+                       static_cast<uint32_t*>(dS), samples, n, static_cast<float*>(dO), ctx->stream);
+    return st.down(out, dO, sizeof(float) * n);
+}
+
+int32_t mcskin_cuda_ambient_occlusion(const McScene* scene, int32_t device, const float* points, const float* normals,
+                                      const uint32_t* seeds, int32_t samples, float radius, int32_t n, float* out) {
+    if (n < 0 || (n > 0 && (!points || !normals || !seeds || !out))) return fail(MC_ERR_INVALID, "ambient_occlusion: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = query_setup(scene, nullptr, device, 0, 1.0f, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void *dP, *dN, *dS, *dO;
+    if ((rc = st.up(points, sizeof(float) * 3 * n, &dP)) != MC_OK) return rc;
+    if ((rc = st.up(normals, sizeof(float) * 3 * n, &dN)) != MC_OK) return rc;
+    if ((rc = st.up(seeds, sizeof(uint32_t) * n, &dS)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(float) * n, &dO)) != MC_OK) return rc;
+    launch_ambient_occlusion(ctx->prep.frame, frame_pointers(ctx), static_cast<float*>(dP), static_cast<float*>(dN),
+                             static_cast<uint32_t*>(dS), samples, radius, n, static_cast<float*>(dO), ctx->stream);
+    return st.down(out, dO, sizeof(float) * n);
+}
+
+int32_t mcskin_cuda_generate_rays(const McScene* scene, int32_t device, float aspect, const float* uv, int32_t n,
+                                  McRay* out) {
+    if (n < 0 || (n > 0 && (!uv || !out))) return fail(MC_ERR_INVALID, "generate_rays: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = query_setup(scene, nullptr, device, 0, aspect, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void *dU, *dO;
+    if ((rc = st.up(uv, sizeof(float) * 2 * n, &dU)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(McRay) * n, &dO)) != MC_OK) return rc;
+    launch_generate_rays(ctx->prep.frame, static_cast<float*>(dU), n, static_cast<McRay*>(dO), ctx->stream);
+    return st.down(out, dO, sizeof(McRay) * n);
+}
+
+int32_t mcskin_cuda_background(const McScene* scene, const McConfig* cfg, int32_t device, int32_t useConfig,
+                               const float* uv, int32_t n, float* out) {
+    if (!cfg || n < 0 || (n > 0 && (!uv || !out))) return fail(MC_ERR_INVALID, "background: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = query_setup(scene, cfg, device, useConfig, 0.0f, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void *dU, *dO;
+    if ((rc = st.up(uv, sizeof(float) * 2 * n, &dU)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(float4) * n, &dO)) != MC_OK) return rc;
+    launch_background(ctx->prep.frame, static_cast<float*>(dU), n, static_cast<float4*>(dO), ctx->stream);
+    return st.down(out, dO, sizeof(float4) * n);
+}
+
+int32_t mcskin_cuda_aov(const McScene* scene, const McConfig* cfg, int32_t device, int32_t* outTriId) {
+    if (!cfg || !outTriId) return fail(MC_ERR_INVALID, "aov: bad argument");
+    if (cfg->width <= 0 || cfg->height <= 0) return MC_OK;
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = query_setup(scene, cfg, device, 1, 0.0f, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void* dO;
+    const size_t bytes = sizeof(int32_t) * static_cast<size_t>(cfg->width) * cfg->height;
+    if ((rc = st.up(nullptr, bytes, &dO)) != MC_OK) return rc;
+    launch_aov(ctx->prep.frame, frame_pointers(ctx), static_cast<int*>(dO), ctx->stream);
+    return st.down(outTriId, dO, bytes);
+}
+
+// struct sizes, so bindings can check their mirror of the header
+void mcskin_cuda_abi_sizes(int32_t* out8) {
+    if (!out8) return;
+    out8[0] = sizeof(McFaceTex);
+    out8[1] = sizeof(McBox);
+    out8[2] = sizeof(McScene);
+    out8[3] = sizeof(McConfig);
+    out8[4] = sizeof(McTile);
+    out8[5] = sizeof(McRenderStats);
+    out8[6] = sizeof(McRay);
+    out8[7] = sizeof(McHit);
+}
+
+}  // extern "C"

@@ -1,0 +1,314 @@
+// dev_intersect.cuh — ray vs. the scene's boxes: intersectScene / intersectMesh /
+// intersectAABB of the reference (src/raytracer/intersection.cpp:200-421) as one
+// loop over pre-digested DevBox records.
+//
+// What is kept bit-for-bit: slab order x,y,z; the 1e-8
+// parallel test; strict comparisons so ties go to the lowest axis; the
+// origin-inside case taking the exit face with its OUTWARD normal; face table, UV
+// orientation and clamping; truncating nearest-texel lookup; alpha == 0 pass-through
+// for inner boxes and the exit-face fallback (flipped normal) for outer boxes;
+// world->local = undo rotZ then undo rotX about the pivot with the pivot subtracted
+// and re-added around EACH step; renormalised local direction; t recomputed as
+// dot(p_world - o, d) for posed boxes; closest hit on strict t < best in box order.
+//
+// What is restructured: bounds, pose sines/cosines and face windows are read from the
+// DevBox instead of being recomputed per ray (the reference's computeAABB alone was
+// ~6x the slab test); the entry and exit faces come out of one pass over the axes; the
+// winner's normal and texel colour are materialised once after the loop; shadow rays
+// stop at the first occluder (same boolean as "closest hit closer than the light").
+#pragma once
+#include "dev_math.cuh"
+#include "dev_types.cuh"
+
+namespace mcskin {
+
+struct Ray {
+    V3 o, d;
+};
+
+// Result of the closest-hit query (HitResult, src/scene/triangle.h:19-26, plus ids).
+struct Hit {
+    float t;
+    V3 p;       // world-space hit point
+    int box;    // -1 = miss
+    int face;   // reference face index 0..5
+    int texel;  // index into the texel pool
+    bool flip;  // outer-layer exit-face hit: normal = -faceNormal, isOuterLayer forced true
+};
+
+struct SceneView {
+    const DevBox* __restrict__ boxes;
+    const float4* __restrict__ texels;
+    int n_boxes;
+};
+
+__device__ __forceinline__ V3 face_normal(int face) {
+    // intersection.cpp:86-122
+    switch (face) {
+        case 0: return mk3(0.0f, 0.0f, -1.0f);
+        case 1: return mk3(0.0f, 0.0f, 1.0f);
+        case 2: return mk3(1.0f, 0.0f, 0.0f);
+        case 3: return mk3(-1.0f, 0.0f, 0.0f);
+        case 4: return mk3(0.0f, 1.0f, 0.0f);
+        default: return mk3(0.0f, -1.0f, 0.0f);
+    }
+}
+__device__ __forceinline__ int face_index(int axis, bool negSide) {
+    if (axis == 2) return negSide ? 0 : 1;
+    if (axis == 0) return negSide ? 3 : 2;
+    return negSide ? 5 : 4;
+}
+
+// rotatePoint (intersection.cpp:12-37) with host-evaluated cos/sin.
+__device__ __forceinline__ V3 rotate_about(V3 point, V3 pivot, bool doX, float cX, float sX, bool doZ, float cZ,
+                                           float sZ) {
+    V3 p = point - pivot;
+    if (doX) {
+        const float ny = p.y * cX - p.z * sX;
+        const float nz = p.y * sX + p.z * cX;
+        p.y = ny;
+        p.z = nz;
+    }
+    if (doZ) {
+        const float nx = p.x * cZ - p.y * sZ;
+        const float ny = p.x * sZ + p.y * cZ;
+        p.x = nx;
+        p.y = ny;
+    }
+    return p + pivot;
+}
+
+// One slab axis (intersection.cpp:221-250 and the exit-face recomputation :265-285).
+struct Slab {
+    float tmin, tmax;
+    int axis, exitAxis;
+    bool neg, exitNeg;
+};
+template <int AXIS>
+__device__ __forceinline__ bool slab_axis(Slab& s, float o, float d, float lo, float hi) {
+    if (fabsf(d) < 1e-8f) return !(o < lo || o > hi);
+    const float inv = 1.0f / d;
+    const float t0 = (lo - o) * inv;
+    const float t1 = (hi - o) * inv;
+    const bool swapped = t0 > t1;
+    const float tn = swapped ? t1 : t0;
+    const float tf = swapped ? t0 : t1;
+    if (tn > s.tmin) {
+        s.tmin = tn;
+        s.axis = AXIS;
+        s.neg = !swapped;
+    }
+    if (tf < s.tmax) {  // std::min(tmax, t1) and the strict '<' of the exit-face loops
+        s.tmax = tf;
+        s.exitAxis = AXIS;
+        s.exitNeg = swapped;
+    }
+    return true;
+}
+
+// computeFaceUV + TextureRegion::sample addressing (intersection.cpp:136-196,
+// texture_region.h:19-26) -> texel pool index.
+__device__ __forceinline__ int face_texel(const DevBox& bx, V3 p, int axis, bool negSide, int face) {
+    float u, v;
+    if (axis == 2) {
+        const float lx = (p.x - bx.lo[0]) / bx.size[0];
+        const float ly = (p.y - bx.lo[1]) / bx.size[1];
+        u = negSide ? 1.0f - lx : lx;
+        v = 1.0f - ly;
+    } else if (axis == 0) {
+        const float lz = (p.z - bx.lo[2]) / bx.size[2];
+        const float ly = (p.y - bx.lo[1]) / bx.size[1];
+        u = !negSide ? 1.0f - lz : lz;
+        v = 1.0f - ly;
+    } else {
+        const float lx = (p.x - bx.lo[0]) / bx.size[0];
+        const float lz = (p.z - bx.lo[2]) / bx.size[2];
+        u = lx;
+        v = !negSide ? lz : 1.0f - lz;
+    }
+    u = clamp01(u);
+    v = clamp01(v);
+    const int2 ft = bx.face[face];
+    const int w = ft.y & 0xffff;
+    const int h = ft.y >> 16;
+    int x = __float2int_rz(u * static_cast<float>(w));
+    int y = __float2int_rz(v * static_cast<float>(h));
+    x = max(0, min(x, w - 1));
+    y = max(0, min(y, h - 1));
+    return ft.x + y * w + x;
+}
+
+struct BoxHit {
+    float t;
+    V3 p;  // in the space of the ray handed to box_test
+    int face, texel;
+    bool flip;
+};
+
+// intersectAABB (intersection.cpp:200-371) against one box, ray already in box space.
+__device__ __forceinline__ bool box_test(const SceneView& sc, const DevBox& bx, V3 o, V3 d, BoxHit& out) {
+    Slab s;
+    s.tmin = -FLT_MAX;
+    s.tmax = FLT_MAX;
+    s.axis = 0;
+    s.exitAxis = 0;
+    s.neg = false;
+    s.exitNeg = false;
+    if (!slab_axis<0>(s, o.x, d.x, bx.lo[0], bx.hi[0])) return false;
+    if (!slab_axis<1>(s, o.y, d.y, bx.lo[1], bx.hi[1])) return false;
+    if (!slab_axis<2>(s, o.z, d.z, bx.lo[2], bx.hi[2])) return false;
+    // the reference tests this after every axis; tmin only grows and tmax only shrinks,
+    // so testing once at the end rejects exactly the same rays
+    if (s.tmin > s.tmax || s.tmax < 0.0f) return false;
+
+    float tHit = s.tmin;
+    int axis = s.axis;
+    bool negSide = s.neg;
+    if (tHit < 0.0f) {  // origin inside: leave through the exit face (intersection.cpp:254-288)
+        tHit = s.tmax;
+        axis = s.exitAxis;
+        negSide = s.exitNeg;
+    }
+    const V3 p = o + d * tHit;
+    const int face = face_index(axis, negSide);
+    const int texel = face_texel(bx, p, axis, negSide, face);
+    const float alpha = __ldg(&sc.texels[texel].w);
+    if (alpha == 0.0f) {  // intersection.cpp:311-361
+        if (!(bx.flags & kBoxOuter)) return false;
+        if (!(s.tmax > tHit)) return false;
+        const V3 bp = o + d * s.tmax;
+        const int bface = face_index(s.exitAxis, s.exitNeg);
+        const int btexel = face_texel(bx, bp, s.exitAxis, s.exitNeg, bface);
+        const float balpha = __ldg(&sc.texels[btexel].w);
+        if (!(balpha > 0.0f)) return false;
+        out.t = s.tmax;
+        out.p = bp;
+        out.face = bface;
+        out.texel = btexel;
+        out.flip = true;
+        return true;
+    }
+    out.t = tHit;
+    out.p = p;
+    out.face = face;
+    out.texel = texel;
+    out.flip = false;
+    return true;
+}
+
+// intersectMesh (intersection.cpp:373-406): hit distance and point in WORLD space.
+__device__ __forceinline__ bool mesh_test(const SceneView& sc, const DevBox& bx, const Ray& ray, BoxHit& out) {
+    const uint32_t flags = bx.flags;
+    if (flags & kBoxEmpty) return false;
+    if (!(flags & kBoxRotated)) return box_test(sc, bx, ray.o, ray.d, out);
+
+    const V3 pivot = ld3(bx.pivot);
+    const V3 zero = mk3(0.0f, 0.0f, 0.0f);
+    const bool doX = flags & kBoxRotX, doZ = flags & kBoxRotZ;
+    // rotatePoint(o, pivot, 0, -rotZ) then rotatePoint(., pivot, -rotX, 0); same for the direction about 0
+    V3 lo = rotate_about(ray.o, pivot, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
+    lo = rotate_about(lo, pivot, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
+    V3 ld = rotate_about(ray.d, zero, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
+    ld = rotate_about(ld, zero, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
+    ld = normalize3(ld);
+    if (!box_test(sc, bx, lo, ld, out)) return false;
+    out.p = rotate_about(out.p, pivot, doX, bx.fwd_cx, bx.fwd_sx, doZ, bx.fwd_cz, bx.fwd_sz);
+    out.t = dot3(out.p - ray.o, ray.d);
+    return true;
+}
+
+// Conservative reject against the inflated bounds of the whole figure.
+__device__ __forceinline__ bool misses_cull_box(const DevFrame& fr, const Ray& ray) {
+    if (!fr.cull_valid) return false;
+    Slab s;
+    s.tmin = -FLT_MAX;
+    s.tmax = FLT_MAX;
+    s.axis = s.exitAxis = 0;
+    s.neg = s.exitNeg = false;
+    if (!slab_axis<0>(s, ray.o.x, ray.d.x, fr.cull_lo[0], fr.cull_hi[0])) return true;
+    if (!slab_axis<1>(s, ray.o.y, ray.d.y, fr.cull_lo[1], fr.cull_hi[1])) return true;
+    if (!slab_axis<2>(s, ray.o.z, ray.d.z, fr.cull_lo[2], fr.cull_hi[2])) return true;
+    return s.tmin > s.tmax || s.tmax < 0.0f;
+}
+
+// intersectScene (intersection.cpp:408-421).
+__device__ __forceinline__ Hit closest_hit(const SceneView& sc, const Ray& ray) {
+    Hit best;
+    best.t = FLT_MAX;
+    best.box = -1;
+    best.face = 0;
+    best.texel = 0;
+    best.flip = false;
+    best.p = mk3(0.0f, 0.0f, 0.0f);
+    for (int b = 0; b < sc.n_boxes; ++b) {
+        BoxHit h;
+        if (mesh_test(sc, sc.boxes[b], ray, h) && h.t < best.t) {
+            best.t = h.t;
+            best.p = h.p;
+            best.box = b;
+            best.face = h.face;
+            best.texel = h.texel;
+            best.flip = h.flip;
+        }
+    }
+    return best;
+}
+
+// intersectMesh of one box (the reference's unit tests call it directly).
+__device__ __forceinline__ Hit single_box_hit(const SceneView& sc, int b, const Ray& ray) {
+    Hit best;
+    best.t = 0.0f;
+    best.box = -1;
+    best.face = 0;
+    best.texel = 0;
+    best.flip = false;
+    best.p = mk3(0.0f, 0.0f, 0.0f);
+    BoxHit h;
+    if (b >= 0 && b < sc.n_boxes && mesh_test(sc, sc.boxes[b], ray, h)) {
+        best.t = h.t;
+        best.p = h.p;
+        best.box = b;
+        best.face = h.face;
+        best.texel = h.texel;
+        best.flip = h.flip;
+    }
+    return best;
+}
+
+// hit.hit of intersectScene, stopping at the first box that reports a hit.
+__device__ __forceinline__ bool any_hit(const SceneView& sc, const Ray& ray) {
+    for (int b = 0; b < sc.n_boxes; ++b) {
+        BoxHit h;
+        if (mesh_test(sc, sc.boxes[b], ray, h)) return true;
+    }
+    return false;
+}
+
+// isInShadow's `hit.hit && hit.t < distToLight` (shading.cpp:23-25): the closest hit is
+// nearer than the light iff some box reports a hit nearer than the light.
+__device__ __forceinline__ bool occluded(const SceneView& sc, const Ray& ray, float dist) {
+    for (int b = 0; b < sc.n_boxes; ++b) {
+        BoxHit h;
+        if (mesh_test(sc, sc.boxes[b], ray, h) && h.t < dist) return true;
+    }
+    return false;
+}
+
+// Normal of the winning hit (intersection.cpp:355,366,399-401).
+__device__ __forceinline__ V3 hit_normal(const SceneView& sc, const Hit& h) {
+    V3 n = face_normal(h.face);
+    if (h.flip) n = n * -1.0f;
+    const DevBox& bx = sc.boxes[h.box];
+    if (bx.flags & kBoxRotated) {
+        n = rotate_about(n, mk3(0.0f, 0.0f, 0.0f), bx.flags & kBoxRotX, bx.fwd_cx, bx.fwd_sx, bx.flags & kBoxRotZ,
+                         bx.fwd_cz, bx.fwd_sz);
+        n = normalize3(n);
+    }
+    return n;
+}
+__device__ __forceinline__ float4 hit_texel(const SceneView& sc, const Hit& h) { return __ldg(&sc.texels[h.texel]); }
+__device__ __forceinline__ bool hit_is_outer(const SceneView& sc, const Hit& h) {
+    return h.flip || (sc.boxes[h.box].flags & kBoxOuter);
+}
+
+}  // namespace mcskin

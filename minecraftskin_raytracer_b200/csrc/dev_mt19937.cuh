@@ -1,0 +1,164 @@
+// dev_mt19937.cuh — std::mt19937 + libstdc++'s uniform_real_distribution<float>(0,1)
+// on the device, in the two access patterns the reference has:
+//
+//  (a) one engine per TILE, seeded tile.y*width + tile.x, consumed sequentially in
+//      pixel-row-major, sample-minor order (tile_renderer.cpp:78-104).  A CTA owns a
+//      tile and regenerates the stream 624 words at a time with a three-phase
+//      parallel twist, dropping canonical floats into a shared-memory ring in step
+//      with the sample loop (TileStream).
+//  (b) a FRESH engine per shaded hit / AO query whose first 2N outputs are used
+//      (shading.cpp:43-50, raytracer.cpp:50-56).  Output j < 227 of a fresh engine
+//      only needs words j, j+1 and j+397 of the Knuth-LCG seeding sequence, so two
+//      LCG cursors 397 words apart stream them out of registers with no state array
+//      (FreshStream); more than 227 outputs fall back to a full state in local memory.
+//
+// Float mapping (libstdc++ 13 bits/random.tcc:3349-3381, generate_canonical<float,24>
+// with a 32-bit engine): one engine call, float(u32) * 2^-32 with the conversion
+// rounded to nearest, and a result >= 1 replaced by nextafterf(1,0) = 0x3f7fffff.
+#pragma once
+#include "dev_math.cuh"
+
+namespace mcskin {
+
+constexpr int kMtN = 624;
+constexpr int kMtM = 397;
+
+__device__ __forceinline__ uint32_t mt_lcg(uint32_t prev, uint32_t i) {
+    return 1812433253u * (prev ^ (prev >> 30)) + i;
+}
+__device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t next, uint32_t far) {
+    const uint32_t y = (cur & 0x80000000u) | (next & 0x7fffffffu);
+    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+__device__ __forceinline__ float mt_canonical(uint32_t u) {
+    const float r = __uint2float_rn(u) * 2.3283064365386963e-10f;  // exact scaling by 2^-32
+    return (r >= 1.0f) ? __uint_as_float(0x3f7fffffu) : r;
+}
+
+// ---- (b) fresh engine, first outputs only -------------------------------------
+struct FreshStream {
+    uint32_t cur, nxt, far;
+    uint32_t j;
+
+    __device__ __forceinline__ void seed(uint32_t s) {
+        cur = s;
+        nxt = mt_lcg(s, 1u);
+        uint32_t x = nxt;
+#pragma unroll 4
+        for (uint32_t i = 2u; i <= static_cast<uint32_t>(kMtM); ++i) x = mt_lcg(x, i);
+        far = x;
+        j = 0u;
+    }
+    // valid for the first kMtN - kMtM = 227 calls
+    __device__ __forceinline__ float next() {
+        const uint32_t v = mt_mix(cur, nxt, far);
+        cur = nxt;
+        nxt = mt_lcg(nxt, j + 2u);
+        far = mt_lcg(far, j + static_cast<uint32_t>(kMtM) + 1u);
+        ++j;
+        return mt_canonical(mt_temper(v));
+    }
+};
+constexpr int kFreshStreamMaxDraws = kMtN - kMtM;
+
+// Full engine in local memory: only for shadowSamples/aoSamples > 113.
+struct LocalEngine {
+    uint32_t s[kMtN];
+    int idx;
+    __device__ void seed(uint32_t v) {
+        s[0] = v;
+        for (int i = 1; i < kMtN; ++i) s[i] = mt_lcg(s[i - 1], static_cast<uint32_t>(i));
+        idx = kMtN;
+    }
+    __device__ float next() {
+        if (idx >= kMtN) {
+            for (int i = 0; i < kMtN; ++i) {
+                const int i1 = (i + 1 == kMtN) ? 0 : i + 1;
+                const int im = (i + kMtM >= kMtN) ? i + kMtM - kMtN : i + kMtM;
+                s[i] = mt_mix(s[i], s[i1], s[im]);
+            }
+            idx = 0;
+        }
+        return mt_canonical(mt_temper(s[idx++]));
+    }
+};
+
+// ---- (a) per-tile stream, CTA-cooperative ----------------------------------------
+constexpr int kRingSize = 2048;  // floats; >= 4 draws * 256 samples + one 624-word block
+constexpr int kRingMask = kRingSize - 1;
+
+struct TileStreamSmem {
+    uint32_t state[2][kMtN];  // ping-pong so a phase never overwrites a word another thread still reads
+    float ring[kRingSize];    // canonical floats, absolute stream index & kRingMask
+};
+
+struct TileStream {
+    TileStreamSmem* sm;
+    int which;               // state[which] is the current block
+    long long produced;      // stream words generated so far (multiple of 624)
+
+    // All threads call; thread 0 runs the 623-step seeding recurrence.
+    __device__ void seed(TileStreamSmem* smem, uint32_t seedValue) {
+        sm = smem;
+        which = 0;
+        produced = 0;
+        if (threadIdx.x == 0) {
+            uint32_t x = seedValue;
+            sm->state[0][0] = x;
+            for (uint32_t i = 1u; i < static_cast<uint32_t>(kMtN); ++i) {
+                x = mt_lcg(x, i);
+                sm->state[0][i] = x;
+            }
+        }
+        __syncthreads();
+    }
+
+    // Generates the next 624 words into the ring.  Uniform call; ends with a barrier.
+    __device__ void produce_block() {
+        const uint32_t* a = sm->state[which];
+        uint32_t* b = sm->state[which ^ 1];
+        const int base = static_cast<int>(produced & kRingMask);
+        // phase 1: words [0, 227) depend on the old block only
+        for (int i = threadIdx.x; i < kMtN - kMtM; i += blockDim.x) {
+            const uint32_t v = mt_mix(a[i], a[i + 1], a[i + kMtM]);
+            b[i] = v;
+            sm->ring[(base + i) & kRingMask] = mt_canonical(mt_temper(v));
+        }
+        __syncthreads();
+        // phase 2: words [227, 454) use new words [0, 227)
+        for (int i = (kMtN - kMtM) + threadIdx.x; i < 2 * (kMtN - kMtM); i += blockDim.x) {
+            const uint32_t v = mt_mix(a[i], a[i + 1], b[i - (kMtN - kMtM)]);
+            b[i] = v;
+            sm->ring[(base + i) & kRingMask] = mt_canonical(mt_temper(v));
+        }
+        __syncthreads();
+        // phase 3: words [454, 624) use new words [227, 397); the last one wraps to new word 0
+        for (int i = 2 * (kMtN - kMtM) + threadIdx.x; i < kMtN; i += blockDim.x) {
+            const uint32_t nextWord = (i + 1 == kMtN) ? b[0] : a[i + 1];
+            const uint32_t v = mt_mix(a[i], nextWord, b[i - (kMtN - kMtM)]);
+            b[i] = v;
+            sm->ring[(base + i) & kRingMask] = mt_canonical(mt_temper(v));
+        }
+        __syncthreads();
+        which ^= 1;
+        produced += kMtN;
+    }
+
+    // Makes every stream word below `end` available (words older than
+    // kRingSize - 624 behind `end` may already be overwritten).
+    __device__ void ensure(long long end) {
+        while (produced < end) produce_block();
+    }
+    __device__ __forceinline__ float at(long long index) const {
+        return sm->ring[static_cast<int>(index & kRingMask)];
+    }
+};
+
+}  // namespace mcskin

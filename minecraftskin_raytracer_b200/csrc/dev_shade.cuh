@@ -1,0 +1,272 @@
+// dev_shade.cuh — camera rays, background, shadows, Blinn-Phong, AO and the bounce
+// loop: Camera::generateRay (camera.cpp:8-26), generateDOFRay (tile_renderer.cpp:42-69),
+// RayTracer::backgroundColor / computeAO / traceRay (raytracer.cpp:16-148),
+// isInShadow / computeSoftShadow / shade (shading.cpp:14-96).
+//
+// The recursion of traceRay is flattened: the loop walks down the bounce chain
+// keeping each level's shaded colour on a small per-thread stack, then folds the
+// chain back-to-front with the reference's own mix (c*0.9f + r*0.1f, alpha restored,
+// clamp) so every level rounds exactly as the recursive code does.
+#pragma once
+#include "dev_intersect.cuh"
+#include "dev_mt19937.cuh"
+
+namespace mcskin {
+
+constexpr float kShadowEpsilon = 1e-3f;    // shading.cpp:12
+constexpr float kReflectEpsilon = 1e-3f;   // raytracer.cpp:12
+constexpr float kReflectivity = 0.1f;      // raytracer.cpp:11
+constexpr int kMaxStackDepth = 64;         // deeper levels weigh < 1e-64: invisible in float
+// 2.0f * static_cast<float>(M_PI), evaluated in float like the reference (shading.cpp:49)
+#define MCSKIN_TWO_PI_F (2.0f * 3.14159274101257324219f)
+
+// Camera::generateRay with the look-at basis and tan(fov/2) hoisted to the host.
+__device__ __forceinline__ Ray camera_ray(const DevFrame& fr, float u, float v) {
+    const float su = (2.0f * u - 1.0f) * fr.half_w;
+    const float sv = (2.0f * (1.0f - v) - 1.0f) * fr.half_h;
+    const V3 fwd = ld3(fr.cam_fwd), right = ld3(fr.cam_right), up = ld3(fr.cam_up);
+    Ray r;
+    r.o = ld3(fr.cam_pos);
+    r.d = normalize3((fwd + right * su) + up * sv);
+    return r;
+}
+
+// sinf/cosf of a float angle.  TODO(parity): glibc-exact double-precision evaluation.
+__device__ __forceinline__ void sincos_ref(float a, float* s, float* c) {
+    *s = sinf(a);
+    *c = cosf(a);
+}
+
+// generateDOFRay; r1, r2 are the two lens draws that follow the jitter draws.
+__device__ __forceinline__ Ray dof_ray(const DevFrame& fr, float u, float v, float r1, float r2) {
+    const Ray pin = camera_ray(fr, u, v);
+    const V3 focus = pin.o + pin.d * fr.focus_dist;
+    const float angle = MCSKIN_TWO_PI_F * r1;
+    const float radius = fr.aperture * sqrtf(r2);
+    float sn, cs;
+    sincos_ref(angle, &sn, &cs);
+    const float lensX = radius * cs;
+    const float lensY = radius * sn;
+    const V3 lens = ld3(fr.cam_right) * lensX + ld3(fr.cam_up) * lensY;
+    Ray r;
+    r.o = ld3(fr.cam_pos) + lens;
+    r.d = normalize3(focus - r.o);
+    return r;
+}
+
+__device__ __forceinline__ float4 flat_background(const DevFrame& fr) {
+    return make_float4(fr.background[0], fr.background[1], fr.background[2], fr.background[3]);
+}
+// RayTracer::backgroundColor with a config
+__device__ __forceinline__ float4 config_background(const DevFrame& fr, float u, float v) {
+    if (!fr.gradient_bg) return flat_background(fr);
+    const float cx = u - 0.5f, cy = v - 0.5f;
+    float dist = sqrtf(cx * cx + cy * cy) * 2.0f * fr.gradient_scale;
+    dist = clamp01(dist);
+    const float t = dist * dist;
+    const float k = 1.0f - t;
+    return make_float4(fr.bg_center[0] * k + fr.bg_edge[0] * t, fr.bg_center[1] * k + fr.bg_edge[1] * t,
+                       fr.bg_center[2] * k + fr.bg_edge[2] * t, 1.0f);
+}
+
+// isInShadow
+__device__ __forceinline__ bool in_shadow(const SceneView& sc, V3 point, V3 normal, V3 lightPos) {
+    Ray r;
+    r.o = point + normal * kShadowEpsilon;
+    const V3 toLight = lightPos - r.o;
+    const float dist = len3(toLight);
+    if (dist < 1e-6f) return false;
+    r.d = div3(toLight, dist);
+    return occluded(sc, r, dist);
+}
+
+// Orthonormal frame of computeSoftShadow / computeAO: t = normalize(e x n), b = n x t
+__device__ __forceinline__ void frame_about(V3 n, V3* t, V3* b) {
+    if (fabsf(n.x) < 0.9f) *t = normalize3(cross3(mk3(1.0f, 0.0f, 0.0f), n));
+    else *t = normalize3(cross3(mk3(0.0f, 1.0f, 0.0f), n));
+    *b = cross3(n, *t);
+}
+
+template <class Engine>
+__device__ __forceinline__ int soft_shadow_count(const SceneView& sc, const DevFrame& fr, V3 point, V3 normal,
+                                                 int samples, Engine& rng) {
+    const V3 lp = ld3(fr.light_pos);
+    const V3 toPoint = normalize3(point - lp);
+    V3 tangent, bitangent;
+    frame_about(toPoint, &tangent, &bitangent);
+    int lit = 0;
+    for (int i = 0; i < samples; ++i) {
+        const float angle = MCSKIN_TWO_PI_F * rng.next();
+        const float r = fr.light_radius * sqrtf(rng.next());
+        float sn, cs;
+        sincos_ref(angle, &sn, &cs);
+        const V3 offset = tangent * (r * cs) + bitangent * (r * sn);
+        const V3 samplePos = lp + offset;
+        if (!in_shadow(sc, point, normal, samplePos)) ++lit;
+    }
+    return lit;
+}
+
+// computeSoftShadow
+__device__ __noinline__ float soft_shadow_large(const SceneView& sc, const DevFrame& fr, V3 point, V3 normal,
+                                                int samples, uint32_t seed) {
+    LocalEngine rng;
+    rng.seed(seed);
+    return static_cast<float>(soft_shadow_count(sc, fr, point, normal, samples, rng)) / static_cast<float>(samples);
+}
+__device__ __forceinline__ float soft_shadow(const SceneView& sc, const DevFrame& fr, V3 point, V3 normal,
+                                             int samples, uint32_t seed) {
+    if (samples <= 1 || fr.light_radius < 1e-4f) return in_shadow(sc, point, normal, ld3(fr.light_pos)) ? 0.0f : 1.0f;
+    if (2 * samples > kFreshStreamMaxDraws) return soft_shadow_large(sc, fr, point, normal, samples, seed);
+    FreshStream rng;
+    rng.seed(seed);
+    return static_cast<float>(soft_shadow_count(sc, fr, point, normal, samples, rng)) / static_cast<float>(samples);
+}
+
+template <class Engine>
+__device__ __forceinline__ int ao_count(const SceneView& sc, V3 point, V3 normal, int samples, float radius,
+                                        Engine& rng) {
+    const V3 N = normalize3(normal);
+    V3 T, B;
+    frame_about(N, &T, &B);
+    Ray r;
+    r.o = point + N * 1e-3f;
+    int occludedCount = 0;
+    for (int i = 0; i < samples; ++i) {
+        const float r1 = rng.next();
+        const float r2 = rng.next();
+        const float sinT = sqrtf(1.0f - r1);
+        const float cosT = sqrtf(r1);
+        const float phi = MCSKIN_TWO_PI_F * r2;
+        float sn, cs;
+        sincos_ref(phi, &sn, &cs);
+        const V3 l = mk3(sinT * cs, cosT, sinT * sn);
+        r.d = normalize3((T * l.x + N * l.y) + B * l.z);
+        if (occluded(sc, r, radius)) ++occludedCount;  // hit.hit && hit.t < radius
+    }
+    return occludedCount;
+}
+__device__ __noinline__ float ambient_occlusion_large(const SceneView& sc, V3 point, V3 normal, int samples,
+                                                      float radius, uint32_t seed) {
+    LocalEngine rng;
+    rng.seed(seed);
+    return 1.0f - static_cast<float>(ao_count(sc, point, normal, samples, radius, rng)) / static_cast<float>(samples);
+}
+// RayTracer::computeAO
+__device__ __forceinline__ float ambient_occlusion(const SceneView& sc, V3 point, V3 normal, int samples,
+                                                   float radius, uint32_t seed) {
+    if (2 * samples > kFreshStreamMaxDraws) return ambient_occlusion_large(sc, point, normal, samples, radius, seed);
+    FreshStream rng;
+    rng.seed(seed);
+    return 1.0f - static_cast<float>(ao_count(sc, point, normal, samples, radius, rng)) / static_cast<float>(samples);
+}
+
+// shade(): Blinn-Phong with the visibility factor (negative = hard shadow test inside)
+__device__ __forceinline__ float4 shade_hit(const SceneView& sc, const DevFrame& fr, V3 P, V3 normal, float4 tex,
+                                            V3 viewDir, float shadowFactor) {
+    const V3 lp = ld3(fr.light_pos);
+    const V3 L = normalize3(lp - P);
+    const V3 N = normalize3(normal);
+    const V3 V = normalize3(viewDir);
+    float vis = shadowFactor;
+    if (vis < 0.0f) vis = in_shadow(sc, P, N, lp) ? 0.0f : 1.0f;
+    const float ndl = fmaxf(0.0f, dot3(N, L));
+    const float kdiff = fr.kd * ndl * vis;
+    const V3 H = normalize3(L + V);
+    const float ndh = fmaxf(0.0f, dot3(N, H));
+    const float spec = powf(ndh, fr.shininess);
+    const float kspec = fr.ks * spec * vis;
+    float4 out;
+    out.x = (tex.x * fr.ambient + tex.x * fr.light_color[0] * kdiff) + fr.light_color[0] * kspec;
+    out.y = (tex.y * fr.ambient + tex.y * fr.light_color[1] * kdiff) + fr.light_color[1] * kspec;
+    out.z = (tex.z * fr.ambient + tex.z * fr.light_color[2] * kdiff) + fr.light_color[2] * kspec;
+    out.w = tex.w;
+    return clamp4(out);
+}
+
+// traceRay(ray, scene, startDepth, maxBounces, params, config) including the
+// tile renderer's primary-miss override when (u, v) are supplied (tile_renderer.cpp:106-114).
+struct TraceOptions {
+    int start_depth;     // 0 for camera rays
+    bool primary_uv;     // true: a depth-0 miss resolves to backgroundColor(u, v)
+    float u, v;
+};
+
+__device__ __forceinline__ float4 trace_path(const SceneView& sc, const DevFrame& fr, Ray ray,
+                                             const TraceOptions& opt) {
+    const bool cfg = fr.use_config != 0;
+    const int maxB = fr.max_bounces;
+    int depth = opt.start_depth;
+
+    if (depth > maxB) {  // raytracer.cpp:86-90
+        float4 c = cfg ? config_background(fr, 0.5f, 0.5f) : flat_background(fr);
+        if (opt.primary_uv && closest_hit(sc, ray).box < 0) c = config_background(fr, opt.u, opt.v);
+        return c;
+    }
+
+    float stack[kMaxStackDepth][3];  // shaded rgb of every level that spawned a reflection
+    float alpha0 = 1.0f;             // only the outermost level's alpha survives the fold
+    int top = 0;
+    float4 tail;                     // colour returned by the deepest call
+    for (;;) {
+        const Hit hit = closest_hit(sc, ray);
+        if (hit.box < 0) {  // raytracer.cpp:94-102
+            if (depth == 0 && opt.primary_uv) tail = config_background(fr, opt.u, opt.v);
+            else if (depth == 0 && cfg) tail = config_background(fr, 0.5f, 0.5f);
+            else tail = flat_background(fr);
+            break;
+        }
+        const V3 P = hit.p;
+        const V3 nrm = hit_normal(sc, hit);
+        const float4 tex = hit_texel(sc, hit);
+        const V3 viewDir = normalize3(ray.o - P);
+        float shadowFactor = -1.0f;
+        if (cfg && fr.soft_on) {
+            const uint32_t seed = seed_cast(P.x * 12345.0f + P.y * 67890.0f + P.z * 11111.0f +
+                                            static_cast<float>(depth) * 99999.0f);
+            shadowFactor = soft_shadow(sc, fr, P, nrm, fr.shadow_samples, seed);
+        }
+        float4 shaded = shade_hit(sc, fr, P, nrm, tex, viewDir, shadowFactor);
+        const float alpha = shaded.w;
+        if (cfg && fr.ao_on && depth == 0) {
+            const uint32_t seed = seed_cast(P.x * 73856093.0f + P.y * 19349663.0f + P.z * 83492791.0f);
+            const float ao = ambient_occlusion(sc, P, nrm, fr.ao_samples, fr.ao_radius, seed);
+            const float f = 1.0f - fr.ao_intensity * (1.0f - ao);
+            shaded.x *= f;
+            shaded.y *= f;
+            shaded.z *= f;
+        }
+        if (depth < maxB && top < kMaxStackDepth) {
+            stack[top][0] = shaded.x;
+            stack[top][1] = shaded.y;
+            stack[top][2] = shaded.z;
+            if (top == 0) alpha0 = alpha;
+            ++top;
+            const V3 N = normalize3(nrm);
+            const V3 D = normalize3(ray.d);
+            V3 R = D - N * (2.0f * dot3(D, N));
+            R = normalize3(R);
+            ray.o = P + N * kReflectEpsilon;
+            ray.d = R;
+            ++depth;
+            continue;
+        }
+        shaded.w = alpha;
+        tail = clamp4(shaded);
+        break;
+    }
+    // fold back: shaded*(1-0.1f) + reflected*0.1f, alpha restored, clamp (raytracer.cpp:143-147)
+    const float keep = 1.0f - kReflectivity;
+    while (top > 0) {
+        --top;
+        float4 c;
+        c.x = stack[top][0] * keep + tail.x * kReflectivity;
+        c.y = stack[top][1] * keep + tail.y * kReflectivity;
+        c.z = stack[top][2] * keep + tail.z * kReflectivity;
+        c.w = alpha0;  // deeper levels' alpha is overwritten by the caller's (raytracer.cpp:146)
+        tail = clamp4(c);
+    }
+    return tail;
+}
+
+}  // namespace mcskin

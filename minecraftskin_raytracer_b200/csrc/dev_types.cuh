@@ -1,0 +1,74 @@
+// dev_types.cuh — device-side layout of one frame's read-only inputs.
+//
+// Everything the kernels read per frame, pre-digested on the host by
+// scene_prep.cpp with the host's glibc so that every libm call the reference makes
+// per ray with frame-constant arguments (tanf of the fov, cosf/sinf of pose
+// angles; camera.cpp:15, intersection.cpp:17-19,27-29) yields the bit-identical
+// value on the device.
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>  // int2, __align__
+
+namespace mcskin {
+
+constexpr int kFaceCount = 6;
+
+// One Mesh == one box (intersection.cpp:200-406).  144 bytes, 16-byte aligned so a
+// warp-uniform read is a handful of broadcast LDG.128s.
+struct __align__(16) DevBox {
+    float lo[3];      // bounds_min
+    uint32_t flags;   // kBox* bits
+    float hi[3];      // bounds_max
+    float pad0;
+    float size[3];    // hi-lo per axis, replaced by 1 where <= 1e-8 (intersection.cpp:141-143)
+    float pad1;
+    float pivot[3];
+    float pad2;
+    float inv_cx, inv_sx, inv_cz, inv_sz;  // cosf/sinf of rad(-rotX), rad(-rotZ): world -> local
+    float fwd_cx, fwd_sx, fwd_cz, fwd_sz;  // cosf/sinf of rad(+rotX), rad(+rotZ): local -> world
+    // face f: x = first texel in the pool, y = width | (height << 16)
+    int2 face[kFaceCount];
+};
+
+enum : uint32_t {
+    kBoxOuter = 1u,      // Mesh::isOuterLayer
+    kBoxRotated = 2u,    // Mesh::hasRotation
+    kBoxRotX = 4u,       // |rotX| > 0.01 (intersection.cpp:16)
+    kBoxRotZ = 8u,       // |rotZ| > 0.01 (intersection.cpp:26)
+    kBoxEmpty = 16u      // no triangles: never hit (intersection.cpp:205)
+};
+
+// Frame constants, passed by value as a kernel parameter (constant bank).
+struct DevFrame {
+    // image / sampling
+    int width, height, spp, max_bounces;
+    int tile_size, tiles_x, tiles_y;
+    int draws_per_sample;     // 0 (spp==1, no DOF), 2 (jitter or lens), 4 (jitter + lens)
+    float inv_spp;            // 1.0f / float(spp) (tile_renderer.cpp:122)
+    float width_f, height_f, aspect;
+    // camera (camera.cpp:10-16 evaluated once on the host)
+    float cam_pos[3], cam_fwd[3], cam_right[3], cam_up[3];
+    float half_w, half_h;
+    int dof_on;               // dofEnabled && aperture > 1e-6f (tile_renderer.cpp:99)
+    float aperture, focus_dist;
+    // scene
+    int n_boxes;
+    float light_pos[3], light_color[4], light_radius;
+    float background[4];
+    // integrator
+    int use_config;           // traceRay's config pointer non-null (always 1 for render())
+    int soft_on;              // softShadows && shadowSamples > 1 (raytracer.cpp:109)
+    int shadow_samples;
+    int ao_on, ao_samples;
+    float ao_radius, ao_intensity;
+    int gradient_bg;
+    float gradient_scale;
+    float bg_center[4], bg_edge[4];
+    float kd, ks, ambient, shininess;
+    // conservative bounds of everything hittable (world space, slightly inflated): rays
+    // that miss it cannot hit any box
+    float cull_lo[3], cull_hi[3];
+    int cull_valid;
+};
+
+}  // namespace mcskin

@@ -1,0 +1,282 @@
+// host_prep.cpp — frame preparation on the host (no CUDA calls).
+//
+// Everything here is evaluated with the host's float arithmetic and glibc libm in
+// the reference's own operation order, so that values the reference recomputes per
+// ray from frame constants come out bit-identical:
+//   * camera look-at basis and tan(fov/2)          camera.cpp:10-16
+//   * thin-lens focus distance                     tile_renderer.cpp:82-85
+//   * pose sines / cosines, rad = deg*PI_f/180     intersection.cpp:16-19,26-29
+//   * UV axis sizes with the 1e-8 guard            intersection.cpp:138-143
+// Compiled with -ffp-contract=off; x86-64 baseline has no FMA to contract anyway.
+#include "host_prep.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace mcskin {
+
+namespace {
+
+thread_local std::string g_lastError;
+
+struct H3 {
+    float x, y, z;
+};
+H3 sub(H3 a, H3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+H3 crossh(H3 a, H3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+float lenh(H3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+H3 normh(H3 a) {  // vec3.h:46-50
+    const float l = lenh(a);
+    if (l < 1e-8f) return {0.0f, 0.0f, 0.0f};
+    const float inv = 1.0f / l;
+    return {a.x * inv, a.y * inv, a.z * inv};
+}
+float radians(float deg) { return deg * static_cast<float>(M_PI) / 180.0f; }
+
+}  // namespace
+
+void set_last_error(const std::string& message) { g_lastError = message; }
+
+extern "C" const char* mcskin_cuda_last_error(void) { return g_lastError.c_str(); }
+extern "C" int32_t mcskin_cuda_abi_version(void) { return MCSKIN_ABI_VERSION; }
+
+extern "C" void mcskin_config_defaults(McConfig* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    // raytracer.h:10-38
+    c->width = 256;
+    c->height = 256;
+    c->max_bounces = 3;
+    c->samples_per_pixel = 1;
+    c->tile_size = 32;
+    c->thread_count = 0;
+    c->soft_shadows = 1;
+    c->shadow_samples = 8;
+    c->ao_enabled = 0;
+    c->ao_samples = 8;
+    c->ao_radius = 3.0f;
+    c->ao_intensity = 0.5f;
+    c->dof_enabled = 0;
+    c->aperture = 0.5f;
+    c->focus_distance = 0.0f;
+    c->gradient_bg = 1;
+    c->gradient_scale = 1.0f;
+    const float center[4] = {0.91f, 0.89f, 0.86f, 1.0f}, edge[4] = {0.56f, 0.63f, 0.71f, 1.0f};
+    std::memcpy(c->bg_center, center, sizeof(center));
+    std::memcpy(c->bg_edge, edge, sizeof(edge));
+    // shading.h:9-14
+    c->kd = 0.75f;
+    c->ks = 0.15f;
+    c->ambient = 0.20f;
+    c->shininess = 16.0f;
+}
+
+extern "C" int32_t mcskin_generate_tiles(int32_t w, int32_t h, int32_t ts, McTile* out, int32_t capacity) {
+    if (w <= 0 || h <= 0 || ts <= 0) return 0;  // tile_renderer.cpp:19-21
+    const long long cols = (static_cast<long long>(w) + ts - 1) / ts, rows = (static_cast<long long>(h) + ts - 1) / ts;
+    const long long total = cols * rows;
+    if (total > std::numeric_limits<int32_t>::max()) return 0;
+    if (out) {
+        long long n = 0;
+        for (long long ty = 0; ty < rows && n < capacity; ++ty)
+            for (long long tx = 0; tx < cols && n < capacity; ++tx, ++n) {
+                McTile t;
+                t.x = static_cast<int32_t>(tx * ts);
+                t.y = static_cast<int32_t>(ty * ts);
+                t.width = ts < w - t.x ? ts : w - t.x;
+                t.height = ts < h - t.y ? ts : h - t.y;
+                out[n] = t;
+            }
+    }
+    return static_cast<int32_t>(total);
+}
+
+int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, float aspectOverride,
+                  PreparedFrame& out, std::string& error) {
+    if (!scene) {
+        error = "scene is null";
+        return MC_ERR_INVALID;
+    }
+    if (scene->n_boxes < 0 || scene->n_texels < 0 || (scene->n_boxes > 0 && !scene->boxes) ||
+        (scene->n_texels > 0 && !scene->texels_rgba)) {
+        error = "scene has negative counts or null arrays";
+        return MC_ERR_INVALID;
+    }
+    McConfig cfg;
+    if (cfgIn) cfg = *cfgIn;
+    else mcskin_config_defaults(&cfg);
+
+    DevFrame& f = out.frame;
+    std::memset(&f, 0, sizeof(f));
+    f.width = cfg.width;
+    f.height = cfg.height;
+    f.spp = cfg.samples_per_pixel > 1 ? cfg.samples_per_pixel : 1;  // tile_renderer.cpp:76
+    f.max_bounces = cfg.max_bounces;
+    f.tile_size = cfg.tile_size;
+    if (cfg.width > 0 && cfg.height > 0 && cfg.tile_size > 0) {
+        f.tiles_x = (cfg.width + cfg.tile_size - 1) / cfg.tile_size;
+        f.tiles_y = (cfg.height + cfg.tile_size - 1) / cfg.tile_size;
+    }
+    f.inv_spp = 1.0f / static_cast<float>(f.spp);
+    f.width_f = static_cast<float>(cfg.width);
+    f.height_f = static_cast<float>(cfg.height);
+    f.aspect = aspectOverride > 0.0f ? aspectOverride
+                                     : static_cast<float>(cfg.width) / static_cast<float>(cfg.height);
+
+    // camera.cpp:10-16
+    const H3 pos{scene->cam_pos[0], scene->cam_pos[1], scene->cam_pos[2]};
+    const H3 tgt{scene->cam_target[0], scene->cam_target[1], scene->cam_target[2]};
+    const H3 upv{scene->cam_up[0], scene->cam_up[1], scene->cam_up[2]};
+    const H3 fwd = normh(sub(tgt, pos));
+    const H3 right = normh(crossh(fwd, upv));
+    const H3 trueUp = crossh(right, fwd);
+    const float halfH = std::tan(scene->cam_fov_deg * 0.5f * static_cast<float>(M_PI) / 180.0f);
+    const float halfW = halfH * f.aspect;
+    f.cam_pos[0] = pos.x; f.cam_pos[1] = pos.y; f.cam_pos[2] = pos.z;
+    f.cam_fwd[0] = fwd.x; f.cam_fwd[1] = fwd.y; f.cam_fwd[2] = fwd.z;
+    f.cam_right[0] = right.x; f.cam_right[1] = right.y; f.cam_right[2] = right.z;
+    f.cam_up[0] = trueUp.x; f.cam_up[1] = trueUp.y; f.cam_up[2] = trueUp.z;
+    f.half_w = halfW;
+    f.half_h = halfH;
+
+    // tile_renderer.cpp:82-85, :99
+    f.dof_on = (cfg.dof_enabled && cfg.aperture > 1e-6f) ? 1 : 0;
+    f.aperture = cfg.aperture;
+    f.focus_dist = cfg.focus_distance;
+    if (f.focus_dist <= 0.0f) f.focus_dist = lenh(sub(tgt, pos));
+    f.draws_per_sample = (f.spp > 1 ? 2 : 0) + (f.dof_on ? 2 : 0);
+
+    f.n_boxes = scene->n_boxes;
+    std::memcpy(f.light_pos, scene->light_pos, sizeof(f.light_pos));
+    std::memcpy(f.light_color, scene->light_color, sizeof(f.light_color));
+    f.light_radius = scene->light_radius;
+    std::memcpy(f.background, scene->background, sizeof(f.background));
+
+    f.use_config = useConfig ? 1 : 0;
+    f.soft_on = (cfg.soft_shadows && cfg.shadow_samples > 1) ? 1 : 0;  // raytracer.cpp:109
+    f.shadow_samples = cfg.shadow_samples;
+    f.ao_on = cfg.ao_enabled ? 1 : 0;
+    f.ao_samples = cfg.ao_samples;
+    f.ao_radius = cfg.ao_radius;
+    f.ao_intensity = cfg.ao_intensity;
+    f.gradient_bg = cfg.gradient_bg ? 1 : 0;
+    f.gradient_scale = cfg.gradient_scale;
+    std::memcpy(f.bg_center, cfg.bg_center, sizeof(f.bg_center));
+    std::memcpy(f.bg_edge, cfg.bg_edge, sizeof(f.bg_edge));
+    f.kd = cfg.kd;
+    f.ks = cfg.ks;
+    f.ambient = cfg.ambient;
+    f.shininess = cfg.shininess;
+
+    // texel pool + the two synthetic 1x1 textures
+    out.texels.resize(static_cast<size_t>(scene->n_texels) + 2);
+    if (scene->n_texels > 0) std::memcpy(out.texels.data(), scene->texels_rgba, sizeof(float4h) * scene->n_texels);
+    const int magentaTexel = scene->n_texels;      // null Triangle::texture (intersection.cpp:303-306)
+    const int blankTexel = scene->n_texels + 1;    // empty TextureRegion -> Color() (texture_region.h:20-22)
+    out.texels[magentaTexel] = {1.0f, 0.0f, 1.0f, 1.0f};
+    out.texels[blankTexel] = {0.0f, 0.0f, 0.0f, 1.0f};
+
+    out.boxes.resize(scene->n_boxes);
+    double cullLo[3] = {1e300, 1e300, 1e300}, cullHi[3] = {-1e300, -1e300, -1e300};
+    bool anyBox = false;
+    for (int b = 0; b < scene->n_boxes; ++b) {
+        const McBox& src = scene->boxes[b];
+        DevBox& d = out.boxes[b];
+        std::memset(&d, 0, sizeof(d));
+        uint32_t flags = 0;
+        if (src.is_outer_layer) flags |= kBoxOuter;
+        if (src.n_triangles <= 0) flags |= kBoxEmpty;
+        for (int k = 0; k < 3; ++k) {
+            d.lo[k] = src.bounds_min[k];
+            d.hi[k] = src.bounds_max[k];
+            const float s = src.bounds_max[k] - src.bounds_min[k];
+            d.size[k] = (s > 1e-8f) ? s : 1.0f;
+            d.pivot[k] = src.pivot[k];
+        }
+        d.inv_cx = d.inv_cz = d.fwd_cx = d.fwd_cz = 1.0f;
+        if (src.has_rotation) {
+            flags |= kBoxRotated;
+            // the inverse passes -rot (intersection.cpp:388-391); |−x| > 0.01 is the same test
+            if (std::fabs(src.rot_x_deg) > 0.01f) flags |= kBoxRotX;
+            if (std::fabs(src.rot_z_deg) > 0.01f) flags |= kBoxRotZ;
+            const float ix = radians(-src.rot_x_deg), iz = radians(-src.rot_z_deg);
+            const float fx = radians(src.rot_x_deg), fz = radians(src.rot_z_deg);
+            d.inv_cx = std::cos(ix); d.inv_sx = std::sin(ix);
+            d.inv_cz = std::cos(iz); d.inv_sz = std::sin(iz);
+            d.fwd_cx = std::cos(fx); d.fwd_sx = std::sin(fx);
+            d.fwd_cz = std::cos(fz); d.fwd_sz = std::sin(fz);
+        }
+        d.flags = flags;
+        for (int k = 0; k < kFaceCount; ++k) {
+            const McFaceTex& ft = src.face[k];
+            int offset, w, h;
+            if (ft.texel_offset < 0) {
+                offset = magentaTexel; w = 1; h = 1;
+            } else if (ft.width <= 0 || ft.height <= 0) {
+                offset = blankTexel; w = 1; h = 1;
+            } else {
+                offset = ft.texel_offset; w = ft.width; h = ft.height;
+                if (w > 32767 || h > 32767) {
+                    error = "face texture larger than 32767 texels on a side";
+                    return MC_ERR_LIMIT;
+                }
+                if (static_cast<long long>(offset) + static_cast<long long>(w) * h > scene->n_texels) {
+                    error = "face texture window runs past the texel pool";
+                    return MC_ERR_INVALID;
+                }
+            }
+            d.face[k].x = offset;
+            d.face[k].y = w | (h << 16);
+        }
+        // conservative world bounds of this box (posed boxes: rotate the 8 corners in double)
+        if (!(flags & kBoxEmpty)) {
+            anyBox = true;
+            for (int corner = 0; corner < 8; ++corner) {
+                double p[3] = {(corner & 1) ? d.hi[0] : d.lo[0], (corner & 2) ? d.hi[1] : d.lo[1],
+                               (corner & 4) ? d.hi[2] : d.lo[2]};
+                if (src.has_rotation) {
+                    double x = p[0] - d.pivot[0], y = p[1] - d.pivot[1], z = p[2] - d.pivot[2];
+                    if (flags & kBoxRotX) {
+                        const double a = static_cast<double>(src.rot_x_deg) * M_PI / 180.0, c = std::cos(a), s = std::sin(a);
+                        const double ny = y * c - z * s, nz = y * s + z * c;
+                        y = ny; z = nz;
+                    }
+                    if (flags & kBoxRotZ) {
+                        const double a = static_cast<double>(src.rot_z_deg) * M_PI / 180.0, c = std::cos(a), s = std::sin(a);
+                        const double nx = x * c - y * s, ny = x * s + y * c;
+                        x = nx; y = ny;
+                    }
+                    p[0] = x + d.pivot[0]; p[1] = y + d.pivot[1]; p[2] = z + d.pivot[2];
+                }
+                for (int k = 0; k < 3; ++k) {
+                    if (p[k] < cullLo[k]) cullLo[k] = p[k];
+                    if (p[k] > cullHi[k]) cullHi[k] = p[k];
+                }
+            }
+        }
+    }
+    f.cull_valid = 0;
+    if (anyBox) {
+        bool finite = true;
+        for (int k = 0; k < 3; ++k) {
+            const double ext = cullHi[k] - cullLo[k];
+            const double margin = 1e-3 * (std::fabs(cullLo[k]) + std::fabs(cullHi[k]) + ext) + 1e-2;
+            f.cull_lo[k] = static_cast<float>(cullLo[k] - margin);
+            f.cull_hi[k] = static_cast<float>(cullHi[k] + margin);
+            if (!std::isfinite(f.cull_lo[k]) || !std::isfinite(f.cull_hi[k])) finite = false;
+        }
+        f.cull_valid = finite ? 1 : 0;
+    } else {
+        // nothing hittable: an empty box rejects every ray
+        for (int k = 0; k < 3; ++k) { f.cull_lo[k] = 1.0f; f.cull_hi[k] = -1.0f; }
+        f.cull_valid = 1;
+    }
+    return MC_OK;
+}
+
+}  // namespace mcskin

@@ -1,0 +1,420 @@
+// kernels.cu — the CUDA kernels of the render hot path (sm_100a).
+//
+//   k_primary : TileRenderer::renderTile's sample loop up to "did anything get hit"
+//               (tile_renderer.cpp:71-127): one CTA per reference tile regenerates that
+//               tile's std::mt19937 jitter stream, shoots the camera / thin-lens rays,
+//               resolves every pixel whose samples all miss to the averaged gradient
+//               background, and appends the others — with their jitter draws — to a
+//               compact work list.
+//   k_shade   : RayTracer::traceRay for every sample of every listed pixel (closest hit,
+//               soft/hard shadows, Blinn-Phong, AO, mirror bounces), then the ordered
+//               per-pixel average.  One thread per pixel-sample over a persistent grid, so
+//               the ~7 % of the frame that carries ~95 % of the work is spread evenly over
+//               all SMs instead of being pinned to the tiles that contain the figure.
+//
+// Both passes sum a pixel's samples in sample order, like the reference, so pixels are
+// reproducible bit-for-bit run to run and background pixels match the CPU result exactly.
+#include "kernels.cuh"
+
+#include "dev_shade.cuh"
+
+namespace mcskin {
+
+namespace {
+
+constexpr unsigned int kUnusedSlot = 0xffffffffu;
+
+struct TileGeom {
+    int x, y, w, h;   // frame pixels
+    int bandRow0;     // first pixel row of this tile inside the band image
+    int localIndex;   // tile index inside the band
+};
+
+__device__ __forceinline__ TileGeom tile_geom(const DevFrame& fr, const BandView& band, int localTile) {
+    TileGeom g;
+    const int localRow = localTile / fr.tiles_x;
+    const int tx = localTile - localRow * fr.tiles_x;
+    const int ty = band.first_tile_row + localRow * band.tile_row_stride;
+    g.x = tx * fr.tile_size;
+    g.y = ty * fr.tile_size;
+    g.w = min(fr.tile_size, fr.width - g.x);
+    g.h = min(fr.tile_size, fr.height - g.y);
+    g.bandRow0 = localRow * fr.tile_size;
+    g.localIndex = localTile;
+    return g;
+}
+
+struct SampleDraws {
+    float jx, jy, r1, r2;
+};
+
+// Order of the draws of one sample in the tile stream: jitter x, y (spp > 1 only), then
+// lens angle, radius (DOF only) — tile_renderer.cpp:92-93 and :58-60.
+__device__ __forceinline__ SampleDraws unpack_draws(const DevFrame& fr, const float* d) {
+    SampleDraws s;
+    s.jx = 0.5f;
+    s.jy = 0.5f;
+    s.r1 = 0.0f;
+    s.r2 = 0.0f;
+    int i = 0;
+    if (fr.spp > 1) {
+        s.jx = d[0];
+        s.jy = d[1];
+        i = 2;
+    }
+    if (fr.dof_on) {
+        s.r1 = d[i];
+        s.r2 = d[i + 1];
+    }
+    return s;
+}
+
+__device__ __forceinline__ Ray primary_ray(const DevFrame& fr, int px, int py, const SampleDraws& s, float* u,
+                                           float* v) {
+    *u = (static_cast<float>(px) + s.jx) / fr.width_f;   // tile_renderer.cpp:95-96
+    *v = (static_cast<float>(py) + s.jy) / fr.height_f;
+    return fr.dof_on ? dof_ray(fr, *u, *v, s.r1, s.r2) : camera_ray(fr, *u, *v);
+}
+
+__device__ __forceinline__ void store_pixel(const BandView& band, unsigned int index, float4 c) {
+    if (band.out_f32) band.out_f32[index] = c;
+    if (band.out_u8) band.out_u8[index] = quantize4(c);
+}
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_primary(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list, const int classify) {
+    __shared__ TileStreamSmem mt;
+    __shared__ float4 stage[kBlockThreads];
+    __shared__ int pixHit[kBlockThreads];
+    __shared__ unsigned int pixSlot[kBlockThreads];
+
+    const int tid = threadIdx.x;
+    const TileGeom tg = tile_geom(fr, band, blockIdx.x);
+    const int spp = fr.spp, dps = fr.draws_per_sample;
+    const int nPix = tg.w * tg.h;
+    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+
+    TileStream stream;
+    stream.sm = &mt;
+    stream.which = 0;
+    stream.produced = 0;
+    if (dps > 0) stream.seed(&mt, static_cast<uint32_t>(tg.y * fr.width + tg.x));  // tile_renderer.cpp:78
+
+    if (classify && spp <= kBlockThreads) {
+        const int pixPerPass = kBlockThreads / spp;
+        const int lanePix = tid / spp;
+        const int s = tid - lanePix * spp;
+        const bool laneOn = lanePix < pixPerPass;
+        for (int q0 = 0; q0 < nPix; q0 += pixPerPass) {
+            if (tid < pixPerPass) pixHit[tid] = 0;
+            if (dps > 0) stream.ensure(static_cast<long long>(min(q0 + pixPerPass, nPix)) * spp * dps);
+            __syncthreads();
+
+            const int q = q0 + lanePix;
+            const bool valid = laneOn && q < nPix;
+            float draws[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            int px = 0, py = 0;
+            if (valid) {
+                const int ly = q / tg.w;
+                px = tg.x + (q - ly * tg.w);
+                py = tg.y + ly;
+                const long long base = (static_cast<long long>(q) * spp + s) * dps;
+                for (int i = 0; i < dps; ++i) draws[i] = stream.at(base + i);
+                const SampleDraws sd = unpack_draws(fr, draws);
+                float u, v;
+                const Ray ray = primary_ray(fr, px, py, sd, &u, &v);
+                const bool hit = !misses_cull_box(fr, ray) && any_hit(sc, ray);
+                stage[tid] = config_background(fr, u, v);  // tile_renderer.cpp:111-114
+                if (hit) pixHit[lanePix] = 1;
+            }
+            __syncthreads();
+
+            if (tid < pixPerPass && q0 + tid < nPix) {
+                const int qq = q0 + tid;
+                const int ly = qq / tg.w;
+                const int lx = qq - ly * tg.w;
+                const unsigned int outIndex =
+                    static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + (tg.x + lx);
+                if (pixHit[tid]) {
+                    const unsigned int slot = atomicAdd(list.count, 1u);
+                    pixSlot[tid] = slot;
+                    if (slot < list.capacity)
+                        list.slot_pixel[slot] =
+                            make_uint2(outIndex, static_cast<unsigned int>(tg.x + lx) |
+                                                     (static_cast<unsigned int>(tg.y + ly) << 16));
+                } else {
+                    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    for (int i = 0; i < spp; ++i) acc = add4(acc, stage[tid * spp + i]);
+                    store_pixel(band, outIndex, scale4(acc, fr.inv_spp));
+                }
+            }
+            __syncthreads();
+
+            if (valid && pixHit[lanePix] && dps > 0) {
+                const unsigned int slot = pixSlot[lanePix];
+                if (slot < list.capacity) {
+                    float* rec = list.records + (static_cast<size_t>(slot) * spp + s) * dps;
+                    for (int i = 0; i < dps; ++i) rec[i] = draws[i];
+                }
+            }
+            __syncthreads();
+        }
+        return;
+    }
+
+    // Every pixel goes on the work list; slots are positional (tile-major), so no counter.
+    const long long nSamples = static_cast<long long>(nPix) * spp;
+    const unsigned int slot0 = static_cast<unsigned int>(tg.localIndex) * fr.tile_size * fr.tile_size;
+    for (long long k0 = 0; k0 < nSamples; k0 += kBlockThreads) {
+        const long long kEnd = (k0 + kBlockThreads < nSamples) ? k0 + kBlockThreads : nSamples;
+        if (dps > 0) stream.ensure(kEnd * dps);
+        __syncthreads();
+        const long long k = k0 + tid;
+        if (k < nSamples) {
+            const int q = static_cast<int>(k / spp);
+            const int s = static_cast<int>(k - static_cast<long long>(q) * spp);
+            const unsigned int slot = slot0 + q;
+            if (slot < list.capacity) {
+                if (s == 0) {
+                    const int ly = q / tg.w;
+                    const int lx = q - ly * tg.w;
+                    const unsigned int outIndex =
+                        static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + (tg.x + lx);
+                    list.slot_pixel[slot] = make_uint2(
+                        outIndex, static_cast<unsigned int>(tg.x + lx) | (static_cast<unsigned int>(tg.y + ly) << 16));
+                }
+                float* rec = list.records + (static_cast<size_t>(slot) * spp + s) * dps;
+                for (int i = 0; i < dps; ++i) rec[i] = stream.at(k * dps + i);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_shade(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list) {
+    __shared__ float4 stage[kBlockThreads];
+
+    const int tid = threadIdx.x;
+    const int spp = fr.spp, dps = fr.draws_per_sample;
+    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    unsigned int count = *list.count;
+    if (count > list.capacity) count = list.capacity;
+
+    const bool small = spp <= kBlockThreads;
+    const int pixPerGroup = small ? kBlockThreads / spp : 1;
+    const int chunks = small ? 1 : (spp + kBlockThreads - 1) / kBlockThreads;
+    const int lanePix = small ? tid / spp : 0;
+    const int laneSample = small ? tid - lanePix * spp : tid;
+    const bool laneOn = lanePix < pixPerGroup;
+
+    for (unsigned int g = blockIdx.x; static_cast<unsigned long long>(g) * pixPerGroup < count; g += gridDim.x) {
+        const unsigned int slot = g * pixPerGroup + lanePix;
+        uint2 sp = make_uint2(kUnusedSlot, 0u);
+        if (laneOn && slot < count) sp = list.slot_pixel[slot];
+        const bool slotOn = sp.x != kUnusedSlot;
+        const int px = static_cast<int>(sp.y & 0xffffu), py = static_cast<int>(sp.y >> 16);
+
+        // the summing thread of pixel i of this group is thread i
+        const unsigned int sumSlot = g * pixPerGroup + tid;
+        uint2 sumSp = make_uint2(kUnusedSlot, 0u);
+        if (tid < pixPerGroup && sumSlot < count) sumSp = list.slot_pixel[sumSlot];
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+
+        for (int c = 0; c < chunks; ++c) {
+            const int s = laneSample + c * kBlockThreads;
+            if (slotOn && s < spp) {
+                float draws[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                const float* rec = list.records + (static_cast<size_t>(slot) * spp + s) * dps;
+                for (int i = 0; i < dps; ++i) draws[i] = rec[i];
+                const SampleDraws sd = unpack_draws(fr, draws);
+                TraceOptions opt;
+                opt.start_depth = 0;
+                opt.primary_uv = true;
+                const Ray ray = primary_ray(fr, px, py, sd, &opt.u, &opt.v);
+                stage[tid] = trace_path(sc, fr, ray, opt);
+            }
+            __syncthreads();
+            if (sumSp.x != kUnusedSlot) {
+                const int n = small ? spp : min(kBlockThreads, spp - c * kBlockThreads);
+                const int first = small ? tid * spp : 0;
+                for (int i = 0; i < n; ++i) acc = add4(acc, stage[first + i]);  // tile_renderer.cpp:116-119
+            }
+            __syncthreads();
+        }
+        if (sumSp.x != kUnusedSlot) store_pixel(band, sumSp.x, scale4(acc, fr.inv_spp));
+    }
+}
+
+// ------------------------------------------------------------------ single-query kernels
+__device__ __forceinline__ void write_hit(const SceneView& sc, const Hit& h, McHit* o) {
+    McHit r;
+    r.hit = h.box >= 0 ? 1 : 0;
+    r.t = 0.0f;
+    r.point[0] = r.point[1] = r.point[2] = 0.0f;
+    r.normal[0] = r.normal[1] = r.normal[2] = 0.0f;
+    r.tex_color[0] = r.tex_color[1] = r.tex_color[2] = r.tex_color[3] = 0.0f;
+    r.is_outer_layer = 0;
+    r.box = -1;
+    r.face = -1;
+    if (h.box >= 0) {
+        const V3 n = hit_normal(sc, h);
+        const float4 t = hit_texel(sc, h);
+        r.t = h.t;
+        r.point[0] = h.p.x; r.point[1] = h.p.y; r.point[2] = h.p.z;
+        r.normal[0] = n.x; r.normal[1] = n.y; r.normal[2] = n.z;
+        r.tex_color[0] = t.x; r.tex_color[1] = t.y; r.tex_color[2] = t.z; r.tex_color[3] = t.w;
+        r.is_outer_layer = hit_is_outer(sc, h) ? 1 : 0;
+        r.box = h.box;
+        r.face = h.face;
+    }
+    *o = r;
+}
+
+__global__ void k_intersect(const DevFrame fr, const FramePointers fp, int box, const McRay* rays, int n, McHit* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    Ray r{ld3(rays[i].origin), ld3(rays[i].dir)};
+    const Hit h = box >= 0 ? single_box_hit(sc, box, r) : closest_hit(sc, r);
+    write_hit(sc, h, &out[i]);
+}
+
+__global__ void k_trace(const DevFrame fr, const FramePointers fp, int depth, const McRay* rays, int n, float4* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    Ray r{ld3(rays[i].origin), ld3(rays[i].dir)};
+    TraceOptions opt;
+    opt.start_depth = depth;
+    opt.primary_uv = false;
+    opt.u = opt.v = 0.5f;
+    out[i] = trace_path(sc, fr, r, opt);
+}
+
+__global__ void k_shade_hits(const DevFrame fr, const FramePointers fp, const McHit* hits, const float* viewDirs,
+                             const float* shadowFactors, int n, float4* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    const McHit h = hits[i];
+    out[i] = shade_hit(sc, fr, ld3(h.point), ld3(h.normal),
+                       make_float4(h.tex_color[0], h.tex_color[1], h.tex_color[2], h.tex_color[3]),
+                       ld3(viewDirs + 3 * i), shadowFactors ? shadowFactors[i] : -1.0f);
+}
+
+__global__ void k_in_shadow(const DevFrame fr, const FramePointers fp, const float* points, const float* normals,
+                            const float* lights, int n, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    out[i] = in_shadow(sc, ld3(points + 3 * i), ld3(normals + 3 * i), ld3(lights + 3 * i)) ? 1 : 0;
+}
+
+__global__ void k_soft_shadow(const DevFrame fr, const FramePointers fp, const float* points, const float* normals,
+                              const uint32_t* seeds, int samples, int n, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    out[i] = soft_shadow(sc, fr, ld3(points + 3 * i), ld3(normals + 3 * i), samples, seeds[i]);
+}
+
+__global__ void k_ambient_occlusion(const DevFrame fr, const FramePointers fp, const float* points,
+                                    const float* normals, const uint32_t* seeds, int samples, float radius, int n,
+                                    float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    out[i] = ambient_occlusion(sc, ld3(points + 3 * i), ld3(normals + 3 * i), samples, radius, seeds[i]);
+}
+
+__global__ void k_generate_rays(const DevFrame fr, const float* uv, int n, McRay* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Ray r = camera_ray(fr, uv[2 * i], uv[2 * i + 1]);
+    out[i].origin[0] = r.o.x; out[i].origin[1] = r.o.y; out[i].origin[2] = r.o.z;
+    out[i].dir[0] = r.d.x; out[i].dir[1] = r.d.y; out[i].dir[2] = r.d.z;
+}
+
+__global__ void k_background(const DevFrame fr, const float* uv, int n, float4* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fr.use_config ? config_background(fr, uv[2 * i], uv[2 * i + 1]) : flat_background(fr);
+}
+
+// hit mask + (box, face) id of the pinhole ray through each pixel centre
+__global__ void k_aov(const DevFrame fr, const FramePointers fp, int* outTriId) {
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= fr.width || py >= fr.height) return;
+    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    const float u = (static_cast<float>(px) + 0.5f) / fr.width_f;
+    const float v = (static_cast<float>(py) + 0.5f) / fr.height_f;
+    const Hit h = closest_hit(sc, camera_ray(fr, u, v));
+    outTriId[py * fr.width + px] = h.box >= 0 ? h.box * 12 + h.face * 2 : -1;
+}
+
+inline int blocks_for(int n) { return (n + kBlockThreads - 1) / kBlockThreads; }
+
+}  // namespace
+
+void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
+                    int classify, cudaStream_t stream) {
+    const int nTiles = band.n_tile_rows * fr.tiles_x;
+    if (nTiles <= 0) return;
+    k_primary<<<nTiles, kBlockThreads, 0, stream>>>(fr, fp, band, list, classify);
+}
+
+void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
+                  int gridBlocks, cudaStream_t stream) {
+    if (gridBlocks <= 0) return;
+    k_shade<<<gridBlocks, kBlockThreads, 0, stream>>>(fr, fp, band, list);
+}
+
+void launch_intersect(const DevFrame& fr, const FramePointers& fp, int box, const McRay* rays, int n, McHit* out,
+                      cudaStream_t stream) {
+    if (n > 0) k_intersect<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, fp, box, rays, n, out);
+}
+void launch_trace(const DevFrame& fr, const FramePointers& fp, int depth, const McRay* rays, int n, float4* out,
+                  cudaStream_t stream) {
+    if (n > 0) k_trace<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, fp, depth, rays, n, out);
+}
+void launch_shade_hits(const DevFrame& fr, const FramePointers& fp, const McHit* hits, const float* viewDirs,
+                       const float* shadowFactors, int n, float4* out, cudaStream_t stream) {
+    if (n > 0) k_shade_hits<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, fp, hits, viewDirs, shadowFactors, n, out);
+}
+void launch_in_shadow(const DevFrame& fr, const FramePointers& fp, const float* points, const float* normals,
+                      const float* lights, int n, int* out, cudaStream_t stream) {
+    if (n > 0) k_in_shadow<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, fp, points, normals, lights, n, out);
+}
+void launch_soft_shadow(const DevFrame& fr, const FramePointers& fp, const float* points, const float* normals,
+                        const uint32_t* seeds, int samples, int n, float* out, cudaStream_t stream) {
+    if (n > 0)
+        k_soft_shadow<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, fp, points, normals, seeds, samples, n, out);
+}
+void launch_ambient_occlusion(const DevFrame& fr, const FramePointers& fp, const float* points, const float* normals,
+                              const uint32_t* seeds, int samples, float radius, int n, float* out,
+                              cudaStream_t stream) {
+    if (n > 0)
+        k_ambient_occlusion<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, fp, points, normals, seeds, samples,
+                                                                         radius, n, out);
+}
+void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out, cudaStream_t stream) {
+    if (n > 0) k_generate_rays<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, uv, n, out);
+}
+void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream) {
+    if (n > 0) k_background<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, uv, n, out);
+}
+void launch_aov(const DevFrame& fr, const FramePointers& fp, int* outTriId, cudaStream_t stream) {
+    if (fr.width <= 0 || fr.height <= 0) return;
+    dim3 block(32, 8);
+    dim3 grid((fr.width + 31) / 32, (fr.height + 7) / 8);
+    k_aov<<<grid, block, 0, stream>>>(fr, fp, outTriId);
+}
+
+}  // namespace mcskin

@@ -1,0 +1,62 @@
+// kernels.cuh — launch-side declarations shared by kernels.cu and the C-ABI host code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev_types.cuh"
+#include "mcskin_cuda.h"
+
+namespace mcskin {
+
+constexpr int kBlockThreads = 256;
+
+// Which tile rows of the frame a launch covers, and where its pixels land.
+// Local tile row r is frame tile row first_tile_row + r*tile_row_stride; the output
+// image is the compact band of those rows (tile_size pixel rows each, last clipped).
+struct BandView {
+    int first_tile_row, tile_row_stride, n_tile_rows;
+    float4* out_f32;  // may be null
+    uchar4* out_u8;   // may be null
+};
+
+// Work list produced by the primary pass for the shading pass.
+struct ActiveList {
+    unsigned int* count;  // number of slots in use (device counter)
+    uint2* slot_pixel;    // x = index into the band image, y = px | (py << 16); x = 0xffffffff: unused slot
+    float* records;       // slot-major, spp * draws_per_sample floats per slot: jx, jy [, lens r1, r2]
+    unsigned int capacity;
+};
+
+struct FramePointers {
+    const DevBox* boxes;
+    const float4* texels;
+};
+
+// Primary pass: per-tile jitter stream, camera rays, hit/miss classification, background
+// resolve of pixels no sample of which hits, work records for the rest.
+// classify == 0 puts every pixel on the work list (used for spp > 256 and for tests).
+void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
+                    int classify, cudaStream_t stream);
+// Shading pass: full integrator for every sample of every listed pixel, ordered resolve.
+void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
+                  int gridBlocks, cudaStream_t stream);
+
+// Single-query views of the same device code (all pointers are device memory).
+void launch_intersect(const DevFrame& fr, const FramePointers& fp, int box, const McRay* rays, int n, McHit* out,
+                      cudaStream_t stream);
+void launch_trace(const DevFrame& fr, const FramePointers& fp, int depth, const McRay* rays, int n, float4* out,
+                  cudaStream_t stream);
+void launch_shade_hits(const DevFrame& fr, const FramePointers& fp, const McHit* hits, const float* viewDirs,
+                       const float* shadowFactors, int n, float4* out, cudaStream_t stream);
+void launch_in_shadow(const DevFrame& fr, const FramePointers& fp, const float* points, const float* normals,
+                      const float* lights, int n, int* out, cudaStream_t stream);
+void launch_soft_shadow(const DevFrame& fr, const FramePointers& fp, const float* points, const float* normals,
+                        const uint32_t* seeds, int samples, int n, float* out, cudaStream_t stream);
+void launch_ambient_occlusion(const DevFrame& fr, const FramePointers& fp, const float* points, const float* normals,
+                              const uint32_t* seeds, int samples, float radius, int n, float* out,
+                              cudaStream_t stream);
+void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out, cudaStream_t stream);
+void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream);
+void launch_aov(const DevFrame& fr, const FramePointers& fp, int* outTriId, cudaStream_t stream);
+
+}  // namespace mcskin

@@ -1,0 +1,288 @@
+"""Loader and typed front-end of libmcskin_cuda.so (the C ABI of include/mcskin_cuda.h).
+
+The CUDA extension is the product: there is no CPU fallback here.  If the shared
+library is missing the import of this module raises; if no CUDA device is present,
+every compute call raises McSkinError(MC_ERR_NO_DEVICE).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import _abi
+from ._abi import McConfig, McContext_p, McHit, McRay, McRenderStats, McScene, McTile  # noqa: F401
+from .scene import FlatScene, pose_array
+
+LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmcskin_cuda.so"
+
+# every symbol include/mcskin_cuda.h declares
+EXPORTS = [
+    "mcskin_config_defaults", "mcskin_generate_tiles", "mcskin_cuda_device_count", "mcskin_cuda_last_error",
+    "mcskin_cuda_abi_version", "mcskin_cuda_abi_sizes", "mcskin_cuda_render", "mcskin_cuda_render_tile",
+    "mcskin_cuda_render_multi", "mcskin_cuda_context_create", "mcskin_cuda_context_destroy",
+    "mcskin_cuda_context_set_scene", "mcskin_cuda_context_render_bands", "mcskin_cuda_band_rows",
+    "mcskin_cuda_context_sync", "mcskin_cuda_context_set_option", "mcskin_cuda_context_render_batch",
+    "mcskin_cuda_intersect", "mcskin_cuda_trace", "mcskin_cuda_shade", "mcskin_cuda_in_shadow",
+    "mcskin_cuda_soft_shadow", "mcskin_cuda_ambient_occlusion", "mcskin_cuda_generate_rays",
+    "mcskin_cuda_background", "mcskin_cuda_aov", "mcskin_build_skin_scene",
+]
+
+
+class McSkinError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"mcskin_cuda error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()').  There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.mcskin_cuda_last_error.restype = C.c_char_p
+    for name in EXPORTS:
+        fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
+        if name not in ("mcskin_cuda_last_error", "mcskin_config_defaults", "mcskin_cuda_context_destroy",
+                        "mcskin_cuda_abi_sizes"):
+            fn.restype = C.c_int32
+    lib.mcskin_config_defaults.restype = None
+    lib.mcskin_cuda_context_destroy.restype = None
+    lib.mcskin_cuda_abi_sizes.restype = None
+    return lib
+
+
+_lib = _load()
+
+
+def raw() -> C.CDLL:
+    return _lib
+
+
+def last_error() -> str:
+    return (_lib.mcskin_cuda_last_error() or b"").decode("utf-8", "replace")
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise McSkinError(rc, last_error())
+
+
+def _ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a.reshape(shape) if shape is not None else a
+
+
+def device_count() -> int:
+    return int(_lib.mcskin_cuda_device_count())
+
+
+def abi_sizes() -> list[int]:
+    out = (C.c_int32 * 8)()
+    _lib.mcskin_cuda_abi_sizes(out)
+    return list(out)
+
+
+def config_defaults() -> McConfig:
+    cfg = McConfig()
+    _lib.mcskin_config_defaults(C.byref(cfg))
+    return cfg
+
+
+def generate_tiles(width: int, height: int, tile_size: int) -> np.ndarray:
+    """TileRenderer::generateTiles (tile_renderer.cpp:18-39) as a structured array."""
+    n = _lib.mcskin_generate_tiles(C.c_int32(width), C.c_int32(height), C.c_int32(tile_size), None, C.c_int32(0))
+    out = np.zeros(n, dtype=_abi.TILE_DTYPE)
+    if n:
+        _lib.mcskin_generate_tiles(C.c_int32(width), C.c_int32(height), C.c_int32(tile_size),
+                                   _ptr(out, McTile), C.c_int32(n))
+    return out
+
+
+def build_skin_scene(atlas: np.ndarray, pose=None) -> FlatScene:
+    """SkinParser::parse + MeshBuilder::buildScene for an RGBA8 atlas [H,64,4] (host-side C++)."""
+    atlas = np.ascontiguousarray(atlas, dtype=np.uint8)
+    if atlas.ndim != 3 or atlas.shape[2] != 4:
+        raise ValueError("atlas must be uint8 [H, W, 4]")
+    p = pose_array(pose)
+    boxes = np.zeros(12, dtype=_abi.BOX_DTYPE)
+    texels = np.zeros((4096, 4), dtype=np.float32)
+    cs = McScene()
+    _check(_lib.mcskin_build_skin_scene(_ptr(atlas, C.c_uint8), C.c_int32(atlas.shape[1]), C.c_int32(atlas.shape[0]),
+                                        None if p is None else _ptr(p, C.c_float), _ptr(boxes, _abi.McBox),
+                                        _ptr(texels, C.c_float), C.byref(cs)))
+    return FlatScene.from_c(cs)
+
+
+# ---------------------------------------------------------------- whole-frame calls
+def render(scene: FlatScene, cfg: McConfig, device: int = 0, want_f32: bool = True, want_u8: bool = False,
+           progress=None, multi_devices: int = 0):
+    """mcskin_cuda_render: host scene in, host image(s) out.  Returns (f32|None, u8|None, stats dict)."""
+    h, w = max(cfg.height, 0), max(cfg.width, 0)
+    f32 = np.zeros((h, w, 4), dtype=np.float32) if want_f32 else None
+    if f32 is not None:
+        f32[..., 3] = 1.0  # Image(w,h) default-constructs pixels to (0,0,0,1) (image.h:15, color.h:8)
+    u8 = np.zeros((h, w, 4), dtype=np.uint8) if want_u8 else None
+    if u8 is not None:
+        u8[..., 3] = 255
+    stats = McRenderStats()
+    cs = scene.as_c()
+    if multi_devices and multi_devices > 0:
+        _check(_lib.mcskin_cuda_render_multi(C.byref(cs), C.byref(cfg), C.c_int32(multi_devices),
+                                             None if f32 is None else _ptr(f32, C.c_float),
+                                             None if u8 is None else _ptr(u8, C.c_uint8), C.byref(stats)))
+    else:
+        cb = _abi.McProgressFn(lambda d, t, _u: progress(d, t)) if progress else C.cast(None, _abi.McProgressFn)
+        _check(_lib.mcskin_cuda_render(C.byref(cs), C.byref(cfg), C.c_int32(device),
+                                       None if f32 is None else _ptr(f32, C.c_float),
+                                       None if u8 is None else _ptr(u8, C.c_uint8), cb, None, C.byref(stats)))
+    return f32, u8, {k: getattr(stats, k) for k, _ in McRenderStats._fields_}
+
+
+def render_tile(scene: FlatScene, cfg: McConfig, tile, image_f32: np.ndarray, device: int = 0) -> np.ndarray:
+    image_f32 = np.ascontiguousarray(image_f32, dtype=np.float32)
+    t = McTile(*[int(v) for v in tile])
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_render_tile(C.byref(cs), C.byref(cfg), C.c_int32(device), C.byref(t),
+                                        _ptr(image_f32, C.c_float), None))
+    return image_f32
+
+
+class Context:
+    """Device-resident renderer (McContext): scene uploaded once, output in caller-owned device memory."""
+
+    def __init__(self, device: int = 0):
+        self._h = McContext_p()
+        _check(_lib.mcskin_cuda_context_create(C.c_int32(device), C.byref(self._h)))
+        self.device = device
+        self.cfg: McConfig | None = None
+
+    def close(self):
+        if self._h:
+            _lib.mcskin_cuda_context_destroy(self._h)
+            self._h = McContext_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def set_option(self, name: str, value: int):
+        _check(_lib.mcskin_cuda_context_set_option(self._h, name.encode(), C.c_int64(value)))
+
+    def set_scene(self, scene: FlatScene, cfg: McConfig):
+        cs = scene.as_c()
+        _check(_lib.mcskin_cuda_context_set_scene(self._h, C.byref(cs), C.byref(cfg)))
+        self.cfg = _abi.copy_config(cfg)
+
+    def band_rows(self, first_tile_row: int = 0, stride: int = 1) -> int:
+        return int(_lib.mcskin_cuda_band_rows(C.byref(self.cfg), C.c_int32(first_tile_row), C.c_int32(stride)))
+
+    def render_bands(self, first_tile_row: int, stride: int, d_out_f32: int = 0, d_out_u8: int = 0, stream: int = 0):
+        """Asynchronous. d_out_* are raw device addresses (e.g. torch.Tensor.data_ptr())."""
+        _check(_lib.mcskin_cuda_context_render_bands(self._h, C.c_int32(first_tile_row), C.c_int32(stride),
+                                                     C.c_void_p(d_out_f32 or None), C.c_void_p(d_out_u8 or None),
+                                                     C.c_void_p(stream or None)))
+
+    def sync(self) -> dict:
+        stats = McRenderStats()
+        _check(_lib.mcskin_cuda_context_sync(self._h, C.byref(stats)))
+        return {k: getattr(stats, k) for k, _ in McRenderStats._fields_}
+
+
+# ---------------------------------------------------------------- single-ray views
+def intersect(scene: FlatScene, rays: np.ndarray, box: int = -1, device: int = 0) -> np.ndarray:
+    rays = np.ascontiguousarray(rays, dtype=_abi.RAY_DTYPE)
+    out = np.zeros(len(rays), dtype=_abi.HIT_DTYPE)
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_intersect(C.byref(cs), C.c_int32(device), C.c_int32(box), _ptr(rays, McRay),
+                                      C.c_int32(len(rays)), _ptr(out, McHit)))
+    return out
+
+
+def trace(scene: FlatScene, cfg: McConfig, rays: np.ndarray, depth: int = 0, use_config: bool = True,
+          device: int = 0) -> np.ndarray:
+    rays = np.ascontiguousarray(rays, dtype=_abi.RAY_DTYPE)
+    out = np.zeros((len(rays), 4), dtype=np.float32)
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_trace(C.byref(cs), C.byref(cfg), C.c_int32(device), C.c_int32(int(use_config)),
+                                  C.c_int32(depth), _ptr(rays, McRay), C.c_int32(len(rays)), _ptr(out, C.c_float)))
+    return out
+
+
+def shade(scene: FlatScene, cfg: McConfig, hits: np.ndarray, view_dirs, shadow_factors=None,
+          device: int = 0) -> np.ndarray:
+    hits = np.ascontiguousarray(hits, dtype=_abi.HIT_DTYPE)
+    vd = _f32(view_dirs, (-1, 3))
+    sf = None if shadow_factors is None else _f32(shadow_factors)
+    out = np.zeros((len(hits), 4), dtype=np.float32)
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_shade(C.byref(cs), C.byref(cfg), C.c_int32(device), _ptr(hits, McHit), _ptr(vd, C.c_float),
+                                  None if sf is None else _ptr(sf, C.c_float), C.c_int32(len(hits)),
+                                  _ptr(out, C.c_float)))
+    return out
+
+
+def in_shadow(scene: FlatScene, points, normals, lights, device: int = 0) -> np.ndarray:
+    p, n, l = _f32(points, (-1, 3)), _f32(normals, (-1, 3)), _f32(lights, (-1, 3))
+    out = np.zeros(len(p), dtype=np.int32)
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_in_shadow(C.byref(cs), C.c_int32(device), _ptr(p, C.c_float), _ptr(n, C.c_float),
+                                      _ptr(l, C.c_float), C.c_int32(len(p)), _ptr(out, C.c_int32)))
+    return out
+
+
+def soft_shadow(scene: FlatScene, points, normals, seeds, samples: int, device: int = 0) -> np.ndarray:
+    p, n = _f32(points, (-1, 3)), _f32(normals, (-1, 3))
+    s = np.ascontiguousarray(seeds, dtype=np.uint32)
+    out = np.zeros(len(p), dtype=np.float32)
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_soft_shadow(C.byref(cs), C.c_int32(device), _ptr(p, C.c_float), _ptr(n, C.c_float),
+                                        _ptr(s, C.c_uint32), C.c_int32(samples), C.c_int32(len(p)),
+                                        _ptr(out, C.c_float)))
+    return out
+
+
+def ambient_occlusion(scene: FlatScene, points, normals, seeds, samples: int, radius: float,
+                      device: int = 0) -> np.ndarray:
+    p, n = _f32(points, (-1, 3)), _f32(normals, (-1, 3))
+    s = np.ascontiguousarray(seeds, dtype=np.uint32)
+    out = np.zeros(len(p), dtype=np.float32)
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_ambient_occlusion(C.byref(cs), C.c_int32(device), _ptr(p, C.c_float), _ptr(n, C.c_float),
+                                              _ptr(s, C.c_uint32), C.c_int32(samples), C.c_float(radius),
+                                              C.c_int32(len(p)), _ptr(out, C.c_float)))
+    return out
+
+
+def generate_rays(scene: FlatScene, aspect: float, uv, device: int = 0) -> np.ndarray:
+    uv = _f32(uv, (-1, 2))
+    out = np.zeros(len(uv), dtype=_abi.RAY_DTYPE)
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_generate_rays(C.byref(cs), C.c_int32(device), C.c_float(aspect), _ptr(uv, C.c_float),
+                                          C.c_int32(len(uv)), _ptr(out, McRay)))
+    return out
+
+
+def background(scene: FlatScene, cfg: McConfig, uv, use_config: bool = True, device: int = 0) -> np.ndarray:
+    uv = _f32(uv, (-1, 2))
+    out = np.zeros((len(uv), 4), dtype=np.float32)
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_background(C.byref(cs), C.byref(cfg), C.c_int32(device), C.c_int32(int(use_config)),
+                                       _ptr(uv, C.c_float), C.c_int32(len(uv)), _ptr(out, C.c_float)))
+    return out
+
+
+def aov(scene: FlatScene, cfg: McConfig, device: int = 0) -> np.ndarray:
+    out = np.full((max(cfg.height, 0), max(cfg.width, 0)), -1, dtype=np.int32)
+    cs = scene.as_c()
+    _check(_lib.mcskin_cuda_aov(C.byref(cs), C.byref(cfg), C.c_int32(device), _ptr(out, C.c_int32)))
+    return out

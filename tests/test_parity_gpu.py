@@ -1,0 +1,225 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): hit mask and (box, face) id bit-exact; geometry
+(t, point, normal, texel) bit-exact; 8-bit RGBA within +-1 LSB on >= 99.9 % of pixels;
+background pixels bit-exact as floats.
+"""
+import numpy as np
+import pytest
+
+from minecraftskin_raytracer_b200 import _abi
+from tests.conftest import pixel_report
+from tests.scenes import RENDER_CASES, make_config, random_rays, synth_skin
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(mclib, seed=1, kind="64x64", pose=None):
+    return mclib.build_skin_scene(synth_skin(seed, kind), pose)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("pose", [None, "walking", "dab"])
+def test_intersect_bit_exact(gpu, oracle, pose):
+    scene = _scene(gpu, 1, "64x64", pose)
+    rays = random_rays(np.random.default_rng(7), 20000)
+    want = oracle.intersect(scene, rays)
+    got = gpu.intersect(scene, rays)
+    assert want["hit"].mean() > 0.2
+    assert np.array_equal(got["hit"], want["hit"])
+    for f in ("box", "face", "is_outer_layer"):
+        assert np.array_equal(got[f], want[f]), f
+    for f in ("t", "point", "normal", "tex_color"):
+        assert np.array_equal(_bits(got[f]), _bits(want[f])), f
+
+
+def test_intersect_single_box(gpu, oracle):
+    scene = _scene(gpu, 3, "64x64", "waving")
+    rays = random_rays(np.random.default_rng(11), 4000)
+    for box in (0, 1, 4, 5):
+        want = oracle.intersect(scene, rays, box=box)
+        got = gpu.intersect(scene, rays, box=box)
+        assert np.array_equal(got["hit"], want["hit"])
+        assert np.array_equal(_bits(got["t"]), _bits(want["t"]))
+        assert np.array_equal(got["face"], want["face"])
+
+
+def test_generate_rays_and_background_bit_exact(gpu, oracle):
+    scene = _scene(gpu)
+    uv = np.random.default_rng(3).random((5000, 2)).astype(np.float32)
+    for aspect in (1.0, 16.0 / 9.0, 0.5):
+        want = oracle.generate_rays(scene, aspect, uv)
+        got = gpu.generate_rays(scene, aspect, uv)
+        assert np.array_equal(_bits(got["dir"]), _bits(want["dir"]))
+        assert np.array_equal(_bits(got["origin"]), _bits(want["origin"]))
+    for kw in (dict(), dict(gradient_bg=0), dict(gradient_scale=2.5)):
+        cfg = make_config(**kw)
+        assert np.array_equal(_bits(gpu.background(scene, cfg, uv)), _bits(oracle.background(scene, cfg, uv)))
+    cfg = make_config()
+    assert np.array_equal(_bits(gpu.background(scene, cfg, uv, use_config=False)),
+                          _bits(oracle.background(scene, cfg, uv, use_config=False)))
+
+
+def _surface_points(oracle, scene, n, seed):
+    rays = random_rays(np.random.default_rng(seed), n)
+    hits = oracle.intersect(scene, rays)
+    keep = hits["hit"] == 1
+    return rays[keep], hits[keep]
+
+
+def test_in_shadow_exact(gpu, oracle):
+    scene = _scene(gpu, 1, "64x64", "walking")
+    rays, hits = _surface_points(oracle, scene, 12000, 5)
+    lights = np.tile(np.float32(scene.light_pos), (len(hits), 1))
+    lights += np.random.default_rng(1).normal(scale=4.0, size=lights.shape).astype(np.float32)
+    want = oracle.in_shadow(scene, hits["point"], hits["normal"], lights)
+    got = gpu.in_shadow(scene, hits["point"], hits["normal"], lights)
+    assert 0.02 < want.mean() < 0.98
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("samples", [2, 8, 64, 120])
+def test_soft_shadow(gpu, oracle, samples):
+    scene = _scene(gpu, 1, "64x64", None)
+    rays, hits = _surface_points(oracle, scene, 3000 if samples < 100 else 600, 9)
+    seeds = np.random.default_rng(2).integers(0, 2**32, size=len(hits), dtype=np.uint32)
+    want = oracle.soft_shadow(scene, hits["point"], hits["normal"], seeds, samples)
+    got = gpu.soft_shadow(scene, hits["point"], hits["normal"], seeds, samples)
+    # identical RNG stream; device sinf/cosf may differ from glibc in the last ulp, which can
+    # move a shadow ray across an edge: allow a vanishing fraction of single-sample flips
+    differ = got != want
+    assert differ.mean() <= 2e-3, differ.mean()
+    assert np.abs(got - want).max() <= 1.0 / samples + 1e-6
+
+
+def test_ambient_occlusion(gpu, oracle):
+    scene = _scene(gpu, 4, "64x64", "waving")
+    rays, hits = _surface_points(oracle, scene, 3000, 13)
+    seeds = np.random.default_rng(4).integers(0, 2**32, size=len(hits), dtype=np.uint32)
+    for samples in (8, 16):
+        want = oracle.ambient_occlusion(scene, hits["point"], hits["normal"], seeds, samples, 3.0)
+        got = gpu.ambient_occlusion(scene, hits["point"], hits["normal"], seeds, samples, 3.0)
+        differ = got != want
+        assert differ.mean() <= 2e-3, differ.mean()
+
+
+def test_shade_matches(gpu, oracle):
+    scene = _scene(gpu, 1, "64x64", None)
+    rays, hits = _surface_points(oracle, scene, 6000, 17)
+    view = -rays["dir"]
+    cfg = make_config()
+    for sf in (None, np.random.default_rng(0).random(len(hits)).astype(np.float32)):
+        want = oracle.shade(scene, cfg, hits, view, sf)
+        got = gpu.shade(scene, cfg, hits, view, sf)
+        # colour math only (device powf vs glibc powf): tolerance 2e-6 absolute, far below 1/255
+        assert np.abs(got - want).max() <= 2e-6
+
+
+@pytest.mark.parametrize("use_config,depth", [(True, 0), (False, 0), (True, 2), (True, 9)])
+def test_trace_matches(gpu, oracle, use_config, depth):
+    scene = _scene(gpu, 5, "64x64", "fighting")
+    rays = random_rays(np.random.default_rng(23), 3000)
+    cfg = make_config(max_bounces=4)
+    want = oracle.trace(scene, cfg, rays, depth=depth, use_config=use_config)
+    got = gpu.trace(scene, cfg, rays, depth=depth, use_config=use_config)
+    close = np.abs(got - want).max(axis=1) <= 1e-5
+    assert close.mean() >= 0.998, close.mean()
+
+
+@pytest.mark.parametrize("case", RENDER_CASES, ids=[c[0] for c in RENDER_CASES])
+@pytest.mark.parametrize("all_active", [False, True], ids=["classified", "all_active"])
+def test_render_parity(gpu, oracle, case, all_active, monkeypatch):
+    name, seed, kind, pose, over = case
+    scene = _scene(gpu, seed, kind, pose)
+    cfg = make_config(**over)
+    want = oracle.render(scene, cfg)
+    if all_active:
+        ctx_opts = {"force_all_active": 1}
+    else:
+        ctx_opts = {}
+    got = _render_with_options(gpu, scene, cfg, ctx_opts)
+    rep = pixel_report(got, want, oracle.quantize)
+    # hit mask / triangle id at pixel centres
+    tri_want = oracle.aov(scene, cfg)
+    tri_got = gpu.aov(scene, cfg)
+    assert np.array_equal(tri_got, tri_want)
+    assert rep["within1"] >= 0.999, rep
+    # pixels none of whose samples can hit anything: exact float equality
+    bg = _background_pixels(oracle, scene, cfg, want)
+    assert np.array_equal(_bits(got[bg]), _bits(want[bg]))
+    assert bg.mean() > 0.3
+
+
+def _background_pixels(oracle, scene, cfg, want):
+    """Pixels whose colour equals the pure-background render (an empty scene) bit for bit."""
+    from minecraftskin_raytracer_b200.scene import FlatScene
+    empty = FlatScene(light_pos=scene.light_pos, cam_pos=scene.cam_pos, cam_target=scene.cam_target,
+                      cam_up=scene.cam_up, cam_fov_deg=scene.cam_fov_deg, background=scene.background)
+    pure = oracle.render(empty, cfg)
+    return (pure.view(np.uint32) == want.view(np.uint32)).all(axis=-1)
+
+
+def _render_with_options(gpu, scene, cfg, opts):
+    """Render through the device-resident context (so options can be set) and fetch with torch-free cudaMemcpy."""
+    import ctypes as C
+    if not opts:
+        f32, _, _ = gpu.render(scene, cfg)
+        return f32
+    import torch
+    ctx = gpu.Context(0)
+    try:
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        ctx.set_scene(scene, cfg)
+        out = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        ctx.render_bands(0, 1, out.data_ptr(), 0, 0)
+        ctx.sync()
+        return out.cpu().numpy()
+    finally:
+        ctx.close()
+
+
+def test_u8_output_and_progress(gpu, oracle):
+    scene = _scene(gpu, 1)
+    cfg = make_config(width=100, height=70, samples_per_pixel=2, max_bounces=2)
+    calls = []
+    f32, u8, stats = gpu.render(scene, cfg, want_u8=True, progress=lambda d, t: calls.append((d, t)))
+    total = len(gpu.generate_tiles(100, 70, 32))
+    assert calls == [(i, total) for i in range(1, total + 1)]  # tests/test_tile_renderer.cpp:85-104
+    assert np.array_equal(u8, oracle.quantize(f32))             # image_writer.cpp:18-22
+    assert stats["n_kernel_launches"] >= 2 and stats["n_tiles"] == total
+
+
+def test_render_tile_matches_full_frame(gpu, oracle):
+    scene = _scene(gpu, 2, "64x64", "walking")
+    cfg = make_config(width=80, height=72, samples_per_pixel=3, max_bounces=2)
+    full, _, _ = gpu.render(scene, cfg)
+    img = np.zeros((72, 80, 4), dtype=np.float32)
+    img[..., 3] = 1
+    for t in gpu.generate_tiles(80, 72, 32):
+        img = gpu.render_tile(scene, cfg, tuple(t), img)
+    assert np.array_equal(_bits(img), _bits(full))
+
+
+def test_deterministic_run_to_run(gpu):
+    scene = _scene(gpu, 1, "64x64", "dab")
+    cfg = make_config(width=96, height=96, samples_per_pixel=4)
+    a, _, _ = gpu.render(scene, cfg)
+    b, _, _ = gpu.render(scene, cfg)
+    assert np.array_equal(_bits(a), _bits(b))  # tests/test_tile_renderer_props.cpp:89-134
+
+
+def test_empty_scene_and_degenerate_sizes(gpu, oracle):
+    from minecraftskin_raytracer_b200.scene import FlatScene
+    empty = FlatScene()
+    cfg = make_config(width=64, height=48, samples_per_pixel=2)
+    got, _, _ = gpu.render(empty, cfg)
+    assert np.array_equal(_bits(got), _bits(oracle.render(empty, cfg)))
+    for w, h, ts in ((0, 10, 32), (10, 0, 32), (10, 10, 0), (-5, 10, 32)):
+        cfg = make_config(width=w, height=h, tile_size=ts)
+        f32, _, stats = gpu.render(empty, cfg)   # tile_renderer.cpp:144-146: empty image, no error
+        assert f32.size == max(w, 0) * max(h, 0) * 4
