@@ -128,6 +128,8 @@ typedef struct McRenderStats {
     int64_t n_samples;         /* width*height*spp */
     float ms_device;           /* CUDA-event time of the kernels of this call */
     int32_t n_kernel_launches; /* kernels launched by this call */
+    float ms_primary;          /* of which: primary (classification + background) pass */
+    float ms_shade;            /* of which: shading pass */
 } McRenderStats;
 
 int32_t mcskin_cuda_device_count(void);

@@ -92,6 +92,8 @@ class McRenderStats(C.Structure):
         ("n_samples", C.c_int64),
         ("ms_device", C.c_float),
         ("n_kernel_launches", C.c_int32),
+        ("ms_primary", C.c_float),
+        ("ms_shade", C.c_float),
     ]
 
 

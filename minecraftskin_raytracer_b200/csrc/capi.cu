@@ -78,6 +78,7 @@ struct McContext {
     int smCount = 148;
     cudaStream_t stream = nullptr;  // used when the caller passes stream 0 to the host-facing calls
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> passEvents;  // 3 per chunk: before primary, between, after shade
     bool hasScene = false;
     PreparedFrame prep;
     McConfig cfg{};
@@ -164,6 +165,11 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
     CU_TRY(ctx->records.reserve(std::max<size_t>(16, slotCap * recordBytesPerSlot)));
     CU_TRY(cudaMemsetAsync(ctx->countLog.p, 0, sizeof(unsigned int) * nChunks, stream));
 
+    while (ctx->passEvents.size() < static_cast<size_t>(3 * nChunks)) {
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreate(&e));
+        ctx->passEvents.push_back(e);
+    }
     CU_TRY(cudaEventRecord(ctx->ev0, stream));
     const FramePointers fp = frame_pointers(ctx);
     int launches = 0;
@@ -187,8 +193,11 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
             CU_TRY(cudaMemsetAsync(list.slot_pixel, 0xff, static_cast<size_t>(list.capacity) * sizeof(uint2), stream));
             CU_TRY(cudaMemcpyAsync(list.count, &list.capacity, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
         }
+        CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
         launch_primary(f, fp, band, list, classify ? 1 : 0, stream);
+        CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 1], stream));
         launch_shade(f, fp, band, list, ctx->smCount * ctx->shadeBlocksPerSm, stream);
+        CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 2], stream));
         launches += 2;
     }
     CU_TRY(cudaEventRecord(ctx->ev1, stream));
@@ -205,6 +214,14 @@ int finish_stats(McContext* ctx, McRenderStats* out) {
         float ms = 0.0f;
         CU_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->stats.ms_device = ms;
+        ctx->stats.ms_primary = ctx->stats.ms_shade = 0.0f;
+        for (int c = 0; c < ctx->chunksLastRender; ++c) {
+            float a = 0.0f, b = 0.0f;
+            CU_TRY(cudaEventElapsedTime(&a, ctx->passEvents[3 * c], ctx->passEvents[3 * c + 1]));
+            CU_TRY(cudaEventElapsedTime(&b, ctx->passEvents[3 * c + 1], ctx->passEvents[3 * c + 2]));
+            ctx->stats.ms_primary += a;
+            ctx->stats.ms_shade += b;
+        }
         ctx->hostCounts.resize(ctx->chunksLastRender);
         if (ctx->chunksLastRender > 0)
             CU_TRY(cudaMemcpy(ctx->hostCounts.data(), ctx->countLog.p, sizeof(unsigned int) * ctx->chunksLastRender,
@@ -332,6 +349,7 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     ctx->pinned.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->passEvents) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -539,6 +557,8 @@ int32_t mcskin_cuda_render_multi(const McScene* scene, const McConfig* cfg, int3
         total.n_active_pixels += s.n_active_pixels;
         total.n_kernel_launches += s.n_kernel_launches;
         total.ms_device = std::max(total.ms_device, s.ms_device);
+        total.ms_primary = std::max(total.ms_primary, s.ms_primary);
+        total.ms_shade = std::max(total.ms_shade, s.ms_shade);
     }
     total.n_samples = static_cast<int64_t>(W) * H * std::max(1, cfg->samples_per_pixel);
     if (stats) *stats = total;

@@ -101,7 +101,12 @@ typedef struct Ctx {
     const McScene* sc;
     const McConfig* cfg; /* may be NULL (traceRay without config) */
     McOracleCounters cnt;
+    McOracleCounters scratch; /* receives the inner-work counts of the redundant re-test */
+    int in_retest;
 } Ctx;
+/* inner-work counters describe UNIQUE rays only: the re-test of tile_renderer.cpp:111
+ * repeats the primary ray exactly, so its box tests are counted into `scratch` */
+#define CNT(cx) ((cx)->in_retest ? &(cx)->scratch : &(cx)->cnt)
 
 /* ------------------------------------------------ intersection.cpp:12-42 rotatePoint */
 static V3 rotate_point(V3 point, V3 pivot, float rotXDeg, float rotZDeg) {
@@ -213,7 +218,7 @@ static McHit intersect_box(Ctx* cx, V3 ro, V3 rd, const McBox* box, int boxIndex
         if (tHit < 0.0f) return res;
         exit_face(o, d, lo, hi, &axis, &neg);
     }
-    cx->cnt.n_slab_pass++;
+    CNT(cx)->n_slab_pass++;
     V3 p = vadd(ro, vmul(rd, tHit)); /* ray.h:14 */
     V3 n;
     int f = face_of(axis, neg, &n);
@@ -226,7 +231,7 @@ static McHit intersect_box(Ctx* cx, V3 ro, V3 rd, const McBox* box, int boxIndex
         if (tmax > tHit) {
             int ea, en;
             exit_face(o, d, lo, hi, &ea, &en);
-            cx->cnt.n_backface_eval++;
+            CNT(cx)->n_backface_eval++;
             V3 bp = vadd(ro, vmul(rd, tmax));
             V3 bn;
             int bf = face_of(ea, en, &bn);
@@ -259,10 +264,10 @@ static McHit intersect_box(Ctx* cx, V3 ro, V3 rd, const McBox* box, int boxIndex
 static McHit intersect_mesh(Ctx* cx, V3 ro, V3 rd, int b) {
     const McBox* box = &cx->sc->boxes[b];
     if (!box->has_rotation) {
-        cx->cnt.n_box_tests_plain++;
+        CNT(cx)->n_box_tests_plain++;
         return intersect_box(cx, ro, rd, box, b);
     }
-    cx->cnt.n_box_tests_rotated++;
+    CNT(cx)->n_box_tests_rotated++;
     V3 pivot = v3(box->pivot[0], box->pivot[1], box->pivot[2]);
     V3 lo = rotate_point(ro, pivot, 0, -box->rot_z_deg);
     lo = rotate_point(lo, pivot, -box->rot_x_deg, 0);
@@ -270,7 +275,7 @@ static McHit intersect_mesh(Ctx* cx, V3 ro, V3 rd, int b) {
     ld = rotate_dir(ld, -box->rot_x_deg, 0);
     McHit h = intersect_box(cx, lo, vnorm(ld), box, b);
     if (h.hit) {
-        cx->cnt.n_rotated_hits++;
+        CNT(cx)->n_rotated_hits++;
         V3 p = rotate_point(v3(h.point[0], h.point[1], h.point[2]), pivot, box->rot_x_deg, box->rot_z_deg);
         V3 n = vnorm(rotate_dir(v3(h.normal[0], h.normal[1], h.normal[2]), box->rot_x_deg, box->rot_z_deg));
         h.point[0] = p.x; h.point[1] = p.y; h.point[2] = p.z;
@@ -541,7 +546,9 @@ static void render_tile(Ctx* cx, const McTile* tile, float* image) {
                 /* tile_renderer.cpp:106 always passes ShadingParams{}; McConfig carries the same defaults */
                 Col c = trace_ray(cx, ro, rd, 0, cfg->max_bounces, cfg->kd, cfg->ks, cfg->ambient, cfg->shininess);
                 cx->cnt.n_retests++;
+                cx->in_retest = 1;
                 McHit again = intersect_scene(cx, ro, rd); /* tile_renderer.cpp:111 */
+                cx->in_retest = 0;
                 if (!again.hit) { c = background(sc, u, v, cfg); cx->cnt.n_background_primary++; }
                 acc.r += c.r; acc.g += c.g; acc.b += c.b; acc.a += c.a;
             }

@@ -10,7 +10,10 @@ extern "C" {
 #endif
 
 /* Exact event counts of one render; the inputs of the algorithmic work model
- * (DESIGN.md "Work model").  All int64, summed over threads. */
+ * (DESIGN.md "Work model").  All int64, summed over threads.
+ * n_intersect_scene counts every invocation (what ld --wrap sees on the reference);
+ * the box-level counters below it cover UNIQUE rays only, i.e. they exclude the
+ * redundant re-test of each primary ray (tile_renderer.cpp:111). */
 typedef struct McOracleCounters {
     int64_t n_intersect_scene;   /* intersectScene invocations (incl. the redundant re-test) */
     int64_t n_primary_rays;      /* pixel-samples */
