@@ -102,11 +102,12 @@ namespace {
 
 int upload_scene(McContext* ctx) {
     const PreparedFrame& pf = ctx->prep;
-    CU_TRY(ctx->boxes.reserve(std::max<size_t>(1, pf.boxes.size()) * sizeof(DevBox)));
+    if (pf.blob.size() > kMaxSceneSmemBytes)
+        return fail(MC_ERR_LIMIT, "scene has too many meshes for the shared-memory staging area (" +
+                                      std::to_string(pf.boxes.size()) + " boxes)");
+    CU_TRY(ctx->boxes.reserve(pf.blob.size()));
     CU_TRY(ctx->texels.reserve(pf.texels.size() * sizeof(float4h)));
-    if (!pf.boxes.empty())
-        CU_TRY(cudaMemcpyAsync(ctx->boxes.p, pf.boxes.data(), pf.boxes.size() * sizeof(DevBox),
-                               cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(ctx->boxes.p, pf.blob.data(), pf.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaMemcpyAsync(ctx->texels.p, pf.texels.data(), pf.texels.size() * sizeof(float4h),
                            cudaMemcpyHostToDevice, ctx->stream));
     // pageable sources: the copies above are staged synchronously by the runtime, so the
@@ -115,7 +116,8 @@ int upload_scene(McContext* ctx) {
 }
 
 FramePointers frame_pointers(const McContext* ctx) {
-    return FramePointers{static_cast<const DevBox*>(ctx->boxes.p), static_cast<const float4*>(ctx->texels.p)};
+    return FramePointers{static_cast<const unsigned char*>(ctx->boxes.p), static_cast<const float4*>(ctx->texels.p),
+                         static_cast<unsigned int>(ctx->prep.blob.size())};
 }
 
 int local_tile_rows(const DevFrame& f, int first, int stride) {

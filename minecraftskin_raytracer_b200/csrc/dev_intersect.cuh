@@ -1,6 +1,6 @@
 // dev_intersect.cuh — ray vs. the scene's boxes: intersectScene / intersectMesh /
-// intersectAABB of the reference (src/raytracer/intersection.cpp:200-421) as one
-// loop over pre-digested DevBox records.
+// intersectAABB of the reference (src/raytracer/intersection.cpp:200-421) over
+// pre-digested box records held in shared memory.
 //
 // What is kept bit-for-bit: slab order x,y,z; the 1e-8
 // parallel test; strict comparisons so ties go to the lowest axis; the
@@ -11,11 +11,19 @@
 // and re-added around EACH step; renormalised local direction; t recomputed as
 // dot(p_world - o, d) for posed boxes; closest hit on strict t < best in box order.
 //
-// What is restructured: bounds, pose sines/cosines and face windows are read from the
-// DevBox instead of being recomputed per ray (the reference's computeAABB alone was
-// ~6x the slab test); the entry and exit faces come out of one pass over the axes; the
-// winner's normal and texel colour are materialised once after the loop; shadow rays
-// stop at the first occluder (same boolean as "closest hit closer than the light").
+// What is restructured.  Every query runs in two phases:
+//   1. a branch-free REJECT pass over all unposed boxes: the three slab intervals via
+//      FMNMX, tmin = max of the near values, tmax = min of the far values, and the
+//      reference's own rejection predicate (tmin > tmax || tmax < 0).  The values are
+//      the same floats the reference compares (min/max of the same two products), so
+//      the set of surviving boxes is identical; it only skips the bookkeeping of which
+//      axis won.  Survivors (typically 0-2 of 12) and all posed boxes go into a bit mask.
+//   2. the EXACT evaluation (entry/exit axis with the reference's tie rules, face, UV,
+//      texel, alpha rules, pose back-transform) for the boxes in the mask, in box order.
+// Bounds, pose sines/cosines and face windows are read from the record instead of being
+// recomputed per ray; the winner's normal and texel colour are materialised once after
+// the loop; shadow rays stop at the first occluder (same boolean as "closest hit closer
+// than the light") and reject boxes that start beyond the light.
 #pragma once
 #include "dev_math.cuh"
 #include "dev_types.cuh"
@@ -36,8 +44,12 @@ struct Hit {
     bool flip;  // outer-layer exit-face hit: normal = -faceNormal, isOuterLayer forced true
 };
 
+// Scene as the kernels see it: box records in shared memory (see SceneBlob in
+// dev_types.cuh), texels in global memory through the read-only path.
 struct SceneView {
-    const DevBox* __restrict__ boxes;
+    const float4* __restrict__ lo;      // xyz = bounds_min, w = flags (bit pattern)
+    const float4* __restrict__ hi;      // xyz = bounds_max
+    const DevBox* __restrict__ boxes;   // full records
     const float4* __restrict__ texels;
     int n_boxes;
 };
@@ -217,18 +229,44 @@ __device__ __forceinline__ bool mesh_test(const SceneView& sc, const DevBox& bx,
     return true;
 }
 
-// Conservative reject against the inflated bounds of the whole figure.
-__device__ __forceinline__ bool misses_cull_box(const DevFrame& fr, const Ray& ray) {
-    if (!fr.cull_valid) return false;
-    Slab s;
-    s.tmin = -FLT_MAX;
-    s.tmax = FLT_MAX;
-    s.axis = s.exitAxis = 0;
-    s.neg = s.exitNeg = false;
-    if (!slab_axis<0>(s, ray.o.x, ray.d.x, fr.cull_lo[0], fr.cull_hi[0])) return true;
-    if (!slab_axis<1>(s, ray.o.y, ray.d.y, fr.cull_lo[1], fr.cull_hi[1])) return true;
-    if (!slab_axis<2>(s, ray.o.z, ray.d.z, fr.cull_lo[2], fr.cull_hi[2])) return true;
-    return s.tmin > s.tmax || s.tmax < 0.0f;
+// ---- phase 1: candidate mask ------------------------------------------------------
+// Per-ray constants of the reject pass.
+struct RayPre {
+    V3 inv;          // 1/d per axis (IEEE division, like the reference's invD)
+    bool parallel;   // some |d_i| < 1e-8: the reject pass is skipped, every box is a candidate
+};
+__device__ __forceinline__ RayPre ray_pre(const Ray& r) {
+    RayPre p;
+    p.parallel = fabsf(r.d.x) < 1e-8f || fabsf(r.d.y) < 1e-8f || fabsf(r.d.z) < 1e-8f;
+    p.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    return p;
+}
+
+// Bit b set = box (base + b) may be hit: it survives the reference's slab rejection
+// (unposed boxes) or is posed / not pre-testable.  `limit`: boxes whose slab entry is at
+// or beyond it are dropped too (their hit distance is >= the entry distance).
+__device__ __forceinline__ uint32_t candidate_mask(const SceneView& sc, const Ray& ray, const RayPre& pre, int base,
+                                                   float limit) {
+    const int n = min(32, sc.n_boxes - base);
+    if (pre.parallel) return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+    uint32_t mask = 0u;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        const float4 L = sc.lo[base + i];
+        const float4 H = sc.hi[base + i];
+        const uint32_t flags = __float_as_uint(L.w);
+        // same products the reference forms: (min - o) * invD and (max - o) * invD
+        const float ax = (L.x - ray.o.x) * pre.inv.x, bx = (H.x - ray.o.x) * pre.inv.x;
+        const float ay = (L.y - ray.o.y) * pre.inv.y, by = (H.y - ray.o.y) * pre.inv.y;
+        const float az = (L.z - ray.o.z) * pre.inv.z, bz = (H.z - ray.o.z) * pre.inv.z;
+        const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        const bool reject = (tmin > tmax) || (tmax < 0.0f) || (tmin >= limit);
+        const bool special = flags & (kBoxRotated | kBoxEmpty);   // warp-uniform
+        const bool keep = special ? !(flags & kBoxEmpty) : !reject;
+        mask |= keep ? (1u << i) : 0u;
+    }
+    return mask;
 }
 
 // intersectScene (intersection.cpp:408-421).
@@ -240,15 +278,21 @@ __device__ __forceinline__ Hit closest_hit(const SceneView& sc, const Ray& ray) 
     best.texel = 0;
     best.flip = false;
     best.p = mk3(0.0f, 0.0f, 0.0f);
-    for (int b = 0; b < sc.n_boxes; ++b) {
-        BoxHit h;
-        if (mesh_test(sc, sc.boxes[b], ray, h) && h.t < best.t) {
-            best.t = h.t;
-            best.p = h.p;
-            best.box = b;
-            best.face = h.face;
-            best.texel = h.texel;
-            best.flip = h.flip;
+    const RayPre pre = ray_pre(ray);
+    for (int base = 0; base < sc.n_boxes; base += 32) {
+        uint32_t mask = candidate_mask(sc, ray, pre, base, FLT_MAX);
+        while (mask) {  // increasing box index: strict '<' keeps the reference's tie order
+            const int b = base + __ffs(mask) - 1;
+            mask &= mask - 1u;
+            BoxHit h;
+            if (mesh_test(sc, sc.boxes[b], ray, h) && h.t < best.t) {
+                best.t = h.t;
+                best.p = h.p;
+                best.box = b;
+                best.face = h.face;
+                best.texel = h.texel;
+                best.flip = h.flip;
+            }
         }
     }
     return best;
@@ -277,9 +321,15 @@ __device__ __forceinline__ Hit single_box_hit(const SceneView& sc, int b, const 
 
 // hit.hit of intersectScene, stopping at the first box that reports a hit.
 __device__ __forceinline__ bool any_hit(const SceneView& sc, const Ray& ray) {
-    for (int b = 0; b < sc.n_boxes; ++b) {
-        BoxHit h;
-        if (mesh_test(sc, sc.boxes[b], ray, h)) return true;
+    const RayPre pre = ray_pre(ray);
+    for (int base = 0; base < sc.n_boxes; base += 32) {
+        uint32_t mask = candidate_mask(sc, ray, pre, base, FLT_MAX);
+        while (mask) {
+            const int b = base + __ffs(mask) - 1;
+            mask &= mask - 1u;
+            BoxHit h;
+            if (mesh_test(sc, sc.boxes[b], ray, h)) return true;
+        }
     }
     return false;
 }
@@ -287,9 +337,15 @@ __device__ __forceinline__ bool any_hit(const SceneView& sc, const Ray& ray) {
 // isInShadow's `hit.hit && hit.t < distToLight` (shading.cpp:23-25): the closest hit is
 // nearer than the light iff some box reports a hit nearer than the light.
 __device__ __forceinline__ bool occluded(const SceneView& sc, const Ray& ray, float dist) {
-    for (int b = 0; b < sc.n_boxes; ++b) {
-        BoxHit h;
-        if (mesh_test(sc, sc.boxes[b], ray, h) && h.t < dist) return true;
+    const RayPre pre = ray_pre(ray);
+    for (int base = 0; base < sc.n_boxes; base += 32) {
+        uint32_t mask = candidate_mask(sc, ray, pre, base, dist);
+        while (mask) {
+            const int b = base + __ffs(mask) - 1;
+            mask &= mask - 1u;
+            BoxHit h;
+            if (mesh_test(sc, sc.boxes[b], ray, h) && h.t < dist) return true;
+        }
     }
     return false;
 }
@@ -309,6 +365,20 @@ __device__ __forceinline__ V3 hit_normal(const SceneView& sc, const Hit& h) {
 __device__ __forceinline__ float4 hit_texel(const SceneView& sc, const Hit& h) { return __ldg(&sc.texels[h.texel]); }
 __device__ __forceinline__ bool hit_is_outer(const SceneView& sc, const Hit& h) {
     return h.flip || (sc.boxes[h.box].flags & kBoxOuter);
+}
+
+// Conservative reject against the inflated bounds of the whole figure.
+__device__ __forceinline__ bool misses_cull_box(const DevFrame& fr, const Ray& ray) {
+    if (!fr.cull_valid) return false;
+    Slab s;
+    s.tmin = -FLT_MAX;
+    s.tmax = FLT_MAX;
+    s.axis = s.exitAxis = 0;
+    s.neg = s.exitNeg = false;
+    if (!slab_axis<0>(s, ray.o.x, ray.d.x, fr.cull_lo[0], fr.cull_hi[0])) return true;
+    if (!slab_axis<1>(s, ray.o.y, ray.d.y, fr.cull_lo[1], fr.cull_hi[1])) return true;
+    if (!slab_axis<2>(s, ray.o.z, ray.d.z, fr.cull_lo[2], fr.cull_hi[2])) return true;
+    return s.tmin > s.tmax || s.tmax < 0.0f;
 }
 
 }  // namespace mcskin

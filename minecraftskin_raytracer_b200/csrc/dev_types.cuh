@@ -7,7 +7,7 @@
 // value on the device.
 #pragma once
 #include <stdint.h>
-#include <vector_types.h>  // int2, __align__
+#include <cuda_runtime.h>  // int2, __align__, __host__ __device__
 
 namespace mcskin {
 
@@ -36,6 +36,19 @@ enum : uint32_t {
     kBoxRotX = 4u,       // |rotX| > 0.01 (intersection.cpp:16)
     kBoxRotZ = 8u,       // |rotZ| > 0.01 (intersection.cpp:26)
     kBoxEmpty = 16u      // no triangles: never hit (intersection.cpp:205)
+};
+
+// The scene blob: what a CTA stages into shared memory with one bulk copy.
+//   [ float4 lo[nPad] ][ float4 hi[nPad] ][ DevBox boxes[n] ]      nPad = n rounded up to 4
+// lo[i] = (bounds_min, flags as bit pattern), hi[i] = (bounds_max, 0): the compact
+// operands of the reject pass; the full records serve the exact evaluation.
+struct SceneBlobLayout {
+    int n, nPad;
+    __host__ __device__ explicit SceneBlobLayout(int nBoxes) : n(nBoxes), nPad((nBoxes + 3) & ~3) {}
+    __host__ __device__ unsigned loOffset() const { return 0u; }
+    __host__ __device__ unsigned hiOffset() const { return 16u * nPad; }
+    __host__ __device__ unsigned boxOffset() const { return 32u * nPad; }
+    __host__ __device__ unsigned bytes() const { return 32u * nPad + static_cast<unsigned>(sizeof(DevBox)) * n; }
 };
 
 // Frame constants, passed by value as a kernel parameter (constant bank).
@@ -69,6 +82,11 @@ struct DevFrame {
     // that miss it cannot hit any box
     float cull_lo[3], cull_hi[3];
     int cull_valid;
+    // the same bounds projected through the pinhole camera, in pixels (inclusive, with a
+    // 2-pixel margin): pinhole rays through pixels outside this rectangle miss everything.
+    // rect_valid == 0 (a corner behind the camera, degenerate basis, DOF): test every pixel.
+    int rect_valid;
+    int rect_x0, rect_y0, rect_x1, rect_y1;
 };
 
 }  // namespace mcskin

@@ -10,6 +10,7 @@
 // Compiled with -ffp-contract=off; x86-64 baseline has no FMA to contract anyway.
 #include "host_prep.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -260,6 +261,21 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
             }
         }
     }
+    // shared-memory image of the boxes
+    {
+        const SceneBlobLayout lay(scene->n_boxes);
+        out.blob.assign(std::max<size_t>(16, lay.bytes()), 0);
+        float* lo = reinterpret_cast<float*>(out.blob.data() + lay.loOffset());
+        float* hi = reinterpret_cast<float*>(out.blob.data() + lay.hiOffset());
+        for (int b = 0; b < scene->n_boxes; ++b) {
+            const DevBox& d = out.boxes[b];
+            std::memcpy(lo + 4 * b, d.lo, 3 * sizeof(float));
+            std::memcpy(lo + 4 * b + 3, &d.flags, sizeof(uint32_t));
+            std::memcpy(hi + 4 * b, d.hi, 3 * sizeof(float));
+        }
+        if (scene->n_boxes > 0)
+            std::memcpy(out.blob.data() + lay.boxOffset(), out.boxes.data(), sizeof(DevBox) * scene->n_boxes);
+    }
     f.cull_valid = 0;
     if (anyBox) {
         bool finite = true;
@@ -275,6 +291,43 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
         // nothing hittable: an empty box rejects every ray
         for (int k = 0; k < 3; ++k) { f.cull_lo[k] = 1.0f; f.cull_hi[k] = -1.0f; }
         f.cull_valid = 1;
+    }
+    // screen-space rectangle of the cull box for pinhole rays
+    f.rect_valid = 0;
+    if (f.cull_valid && !f.dof_on && cfg.width > 0 && cfg.height > 0 && halfW > 1e-6f && halfH > 1e-6f &&
+        lenh(right) > 0.5f && lenh(fwd) > 0.5f) {
+        if (!anyBox) {
+            f.rect_valid = 1;  // nothing to hit: an empty rectangle
+            f.rect_x0 = f.rect_y0 = 1;
+            f.rect_x1 = f.rect_y1 = 0;
+        } else {
+            double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+            bool allInFront = true;
+            for (int corner = 0; corner < 8 && allInFront; ++corner) {
+                const double p[3] = {(corner & 1) ? f.cull_hi[0] : f.cull_lo[0], (corner & 2) ? f.cull_hi[1] : f.cull_lo[1],
+                                     (corner & 4) ? f.cull_hi[2] : f.cull_lo[2]};
+                const double rel[3] = {p[0] - pos.x, p[1] - pos.y, p[2] - pos.z};
+                const double depth = rel[0] * fwd.x + rel[1] * fwd.y + rel[2] * fwd.z;
+                if (!(depth > 1e-3)) {
+                    allInFront = false;
+                    break;
+                }
+                const double su = (rel[0] * right.x + rel[1] * right.y + rel[2] * right.z) / depth;
+                const double sv = (rel[0] * trueUp.x + rel[1] * trueUp.y + rel[2] * trueUp.z) / depth;
+                const double px = (su / halfW + 1.0) * 0.5 * cfg.width;
+                const double py = (1.0 - (sv / halfH + 1.0) * 0.5) * cfg.height;
+                x0 = std::min(x0, px); x1 = std::max(x1, px);
+                y0 = std::min(y0, py); y1 = std::max(y1, py);
+            }
+            if (allInFront && std::isfinite(x0) && std::isfinite(x1) && std::isfinite(y0) && std::isfinite(y1)) {
+                const double big = 1e9;
+                f.rect_valid = 1;
+                f.rect_x0 = static_cast<int>(std::floor(std::max(-big, x0))) - 2;
+                f.rect_y0 = static_cast<int>(std::floor(std::max(-big, y0))) - 2;
+                f.rect_x1 = static_cast<int>(std::ceil(std::min(big, x1))) + 2;
+                f.rect_y1 = static_cast<int>(std::ceil(std::min(big, y1))) + 2;
+            }
+        }
     }
     return MC_OK;
 }

@@ -16,6 +16,7 @@ struct float4h {
 struct PreparedFrame {
     DevFrame frame;
     std::vector<DevBox> boxes;
+    std::vector<unsigned char> blob;  // SceneBlobLayout image of `boxes`, 16-byte granular
     std::vector<float4h> texels;  // scene pool + two synthetic 1x1 textures (magenta, default Color)
 };
 

@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 
 #include "dev_shade.cuh"
+#include "dev_stage.cuh"
 
 namespace mcskin {
 
@@ -50,30 +51,22 @@ struct SampleDraws {
 
 // Order of the draws of one sample in the tile stream: jitter x, y (spp > 1 only), then
 // lens angle, radius (DOF only) — tile_renderer.cpp:92-93 and :58-60.
-__device__ __forceinline__ SampleDraws unpack_draws(const DevFrame& fr, const float* d) {
+__device__ __forceinline__ SampleDraws assign_draws(const DevFrame& fr, float d0, float d1, float d2, float d3) {
     SampleDraws s;
-    s.jx = 0.5f;
-    s.jy = 0.5f;
-    s.r1 = 0.0f;
-    s.r2 = 0.0f;
-    int i = 0;
-    if (fr.spp > 1) {
-        s.jx = d[0];
-        s.jy = d[1];
-        i = 2;
-    }
-    if (fr.dof_on) {
-        s.r1 = d[i];
-        s.r2 = d[i + 1];
-    }
+    const bool jitter = fr.spp > 1;
+    s.jx = jitter ? d0 : 0.5f;
+    s.jy = jitter ? d1 : 0.5f;
+    s.r1 = jitter ? d2 : d0;
+    s.r2 = jitter ? d3 : d1;
     return s;
 }
 
-__device__ __forceinline__ Ray primary_ray(const DevFrame& fr, int px, int py, const SampleDraws& s, float* u,
-                                           float* v) {
+__device__ __forceinline__ void sample_uv(const DevFrame& fr, int px, int py, const SampleDraws& s, float* u, float* v) {
     *u = (static_cast<float>(px) + s.jx) / fr.width_f;   // tile_renderer.cpp:95-96
     *v = (static_cast<float>(py) + s.jy) / fr.height_f;
-    return fr.dof_on ? dof_ray(fr, *u, *v, s.r1, s.r2) : camera_ray(fr, *u, *v);
+}
+__device__ __forceinline__ Ray primary_ray(const DevFrame& fr, float u, float v, const SampleDraws& s) {
+    return fr.dof_on ? dof_ray(fr, u, v, s.r1, s.r2) : camera_ray(fr, u, v);
 }
 
 __device__ __forceinline__ void store_pixel(const BandView& band, unsigned int index, float4 c) {
@@ -86,18 +79,27 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) {
 }
 __device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 
+extern __shared__ __align__(16) unsigned char g_sceneSmem[];
+
 __global__ void __launch_bounds__(kBlockThreads)
 k_primary(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list, const int classify) {
     __shared__ TileStreamSmem mt;
     __shared__ float4 stage[kBlockThreads];
     __shared__ int pixHit[kBlockThreads];
     __shared__ unsigned int pixSlot[kBlockThreads];
+    __shared__ __align__(8) uint64_t stageBar;
 
     const int tid = threadIdx.x;
     const TileGeom tg = tile_geom(fr, band, blockIdx.x);
     const int spp = fr.spp, dps = fr.draws_per_sample;
     const int nPix = tg.w * tg.h;
-    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+
+    // Pinhole rays through a tile outside the projected bounds of the figure cannot hit
+    // anything: such a tile needs neither the scene nor any ray, only jitter -> background.
+    const bool tileCanHit = !fr.rect_valid || !(tg.x > fr.rect_x1 || tg.x + tg.w - 1 < fr.rect_x0 ||
+                                                tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
+    if (tileCanHit || !classify) stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
 
     TileStream stream;
     stream.sm = &mt;
@@ -110,6 +112,10 @@ k_primary(const DevFrame fr, const FramePointers fp, const BandView band, const 
         const int lanePix = tid / spp;
         const int s = tid - lanePix * spp;
         const bool laneOn = lanePix < pixPerPass;
+        // running (column, row) of this lane's pixel and of the pixel thread `tid` sums
+        int lx = lanePix % tg.w, ly = lanePix / tg.w;
+        int sx = tid % tg.w, sy = tid / tg.w;
+        const int stepX = pixPerPass % tg.w, stepY = pixPerPass / tg.w;
         for (int q0 = 0; q0 < nPix; q0 += pixPerPass) {
             if (tid < pixPerPass) pixHit[tid] = 0;
             if (dps > 0) stream.ensure(static_cast<long long>(min(q0 + pixPerPass, nPix)) * spp * dps);
@@ -117,52 +123,67 @@ k_primary(const DevFrame fr, const FramePointers fp, const BandView band, const 
 
             const int q = q0 + lanePix;
             const bool valid = laneOn && q < nPix;
-            float draws[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            int px = 0, py = 0;
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
             if (valid) {
-                const int ly = q / tg.w;
-                px = tg.x + (q - ly * tg.w);
-                py = tg.y + ly;
-                const long long base = (static_cast<long long>(q) * spp + s) * dps;
-                for (int i = 0; i < dps; ++i) draws[i] = stream.at(base + i);
-                const SampleDraws sd = unpack_draws(fr, draws);
+                const int px = tg.x + lx, py = tg.y + ly;
+                if (dps > 0) {
+                    const long long base = (static_cast<long long>(q) * spp + s) * dps;
+                    d0 = stream.at(base);
+                    d1 = stream.at(base + 1);
+                    if (dps > 2) {
+                        d2 = stream.at(base + 2);
+                        d3 = stream.at(base + 3);
+                    }
+                }
+                const SampleDraws sd = assign_draws(fr, d0, d1, d2, d3);
                 float u, v;
-                const Ray ray = primary_ray(fr, px, py, sd, &u, &v);
-                const bool hit = !misses_cull_box(fr, ray) && any_hit(sc, ray);
+                sample_uv(fr, px, py, sd, &u, &v);
                 stage[tid] = config_background(fr, u, v);  // tile_renderer.cpp:111-114
-                if (hit) pixHit[lanePix] = 1;
+                const bool pixelCanHit = tileCanHit && (!fr.rect_valid || (px >= fr.rect_x0 && px <= fr.rect_x1 &&
+                                                                           py >= fr.rect_y0 && py <= fr.rect_y1));
+                if (pixelCanHit) {
+                    const Ray ray = primary_ray(fr, u, v, sd);
+                    if (!misses_cull_box(fr, ray) && any_hit(sc, ray)) pixHit[lanePix] = 1;
+                }
             }
             __syncthreads();
 
             if (tid < pixPerPass && q0 + tid < nPix) {
-                const int qq = q0 + tid;
-                const int ly = qq / tg.w;
-                const int lx = qq - ly * tg.w;
                 const unsigned int outIndex =
-                    static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + (tg.x + lx);
+                    static_cast<unsigned int>(tg.bandRow0 + sy) * static_cast<unsigned int>(fr.width) + (tg.x + sx);
                 if (pixHit[tid]) {
                     const unsigned int slot = atomicAdd(list.count, 1u);
                     pixSlot[tid] = slot;
                     if (slot < list.capacity)
                         list.slot_pixel[slot] =
-                            make_uint2(outIndex, static_cast<unsigned int>(tg.x + lx) |
-                                                     (static_cast<unsigned int>(tg.y + ly) << 16));
+                            make_uint2(outIndex, static_cast<unsigned int>(tg.x + sx) |
+                                                     (static_cast<unsigned int>(tg.y + sy) << 16));
                 } else {
                     float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    for (int i = 0; i < spp; ++i) acc = add4(acc, stage[tid * spp + i]);
+                    const float4* mine = stage + tid * spp;
+                    for (int i = 0; i < spp; ++i) acc = add4(acc, mine[i]);
                     store_pixel(band, outIndex, scale4(acc, fr.inv_spp));
                 }
             }
             __syncthreads();
 
-            if (valid && pixHit[lanePix] && dps > 0) {
+            if (valid && dps > 0 && pixHit[lanePix]) {
                 const unsigned int slot = pixSlot[lanePix];
                 if (slot < list.capacity) {
                     float* rec = list.records + (static_cast<size_t>(slot) * spp + s) * dps;
-                    for (int i = 0; i < dps; ++i) rec[i] = draws[i];
+                    if (dps == 2) {
+                        *reinterpret_cast<float2*>(rec) = make_float2(d0, d1);
+                    } else {
+                        *reinterpret_cast<float4*>(rec) = make_float4(d0, d1, d2, d3);
+                    }
                 }
             }
             __syncthreads();
+            // advance both pixel cursors by pixPerPass
+            lx += stepX; ly += stepY;
+            if (lx >= tg.w) { lx -= tg.w; ++ly; }
+            sx += stepX; sy += stepY;
+            if (sx >= tg.w) { sx -= tg.w; ++sy; }
         }
         return;
     }
@@ -199,15 +220,20 @@ k_primary(const DevFrame fr, const FramePointers fp, const BandView band, const 
 __global__ void __launch_bounds__(kBlockThreads)
 k_shade(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list) {
     __shared__ float4 stage[kBlockThreads];
+    __shared__ __align__(8) uint64_t stageBar;
 
     const int tid = threadIdx.x;
     const int spp = fr.spp, dps = fr.draws_per_sample;
-    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
     unsigned int count = *list.count;
     if (count > list.capacity) count = list.capacity;
 
     const bool small = spp <= kBlockThreads;
     const int pixPerGroup = small ? kBlockThreads / spp : 1;
+    if (static_cast<unsigned long long>(blockIdx.x) * pixPerGroup >= count) return;  // nothing for this CTA
+
+    stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+
     const int chunks = small ? 1 : (spp + kBlockThreads - 1) / kBlockThreads;
     const int lanePix = small ? tid / spp : 0;
     const int laneSample = small ? tid - lanePix * spp : tid;
@@ -229,21 +255,28 @@ k_shade(const DevFrame fr, const FramePointers fp, const BandView band, const Ac
         for (int c = 0; c < chunks; ++c) {
             const int s = laneSample + c * kBlockThreads;
             if (slotOn && s < spp) {
-                float draws[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
                 const float* rec = list.records + (static_cast<size_t>(slot) * spp + s) * dps;
-                for (int i = 0; i < dps; ++i) draws[i] = rec[i];
-                const SampleDraws sd = unpack_draws(fr, draws);
+                if (dps == 2) {
+                    const float2 r = *reinterpret_cast<const float2*>(rec);
+                    d0 = r.x; d1 = r.y;
+                } else if (dps == 4) {
+                    const float4 r = *reinterpret_cast<const float4*>(rec);
+                    d0 = r.x; d1 = r.y; d2 = r.z; d3 = r.w;
+                }
+                const SampleDraws sd = assign_draws(fr, d0, d1, d2, d3);
                 TraceOptions opt;
                 opt.start_depth = 0;
                 opt.primary_uv = true;
-                const Ray ray = primary_ray(fr, px, py, sd, &opt.u, &opt.v);
+                sample_uv(fr, px, py, sd, &opt.u, &opt.v);
+                const Ray ray = primary_ray(fr, opt.u, opt.v, sd);
                 stage[tid] = trace_path(sc, fr, ray, opt);
             }
             __syncthreads();
             if (sumSp.x != kUnusedSlot) {
                 const int n = small ? spp : min(kBlockThreads, spp - c * kBlockThreads);
-                const int first = small ? tid * spp : 0;
-                for (int i = 0; i < n; ++i) acc = add4(acc, stage[first + i]);  // tile_renderer.cpp:116-119
+                const float4* mine = stage + (small ? tid * spp : 0);
+                for (int i = 0; i < n; ++i) acc = add4(acc, mine[i]);  // tile_renderer.cpp:116-119
             }
             __syncthreads();
         }
@@ -279,7 +312,7 @@ __device__ __forceinline__ void write_hit(const SceneView& sc, const Hit& h, McH
 __global__ void k_intersect(const DevFrame fr, const FramePointers fp, int box, const McRay* rays, int n, McHit* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
     Ray r{ld3(rays[i].origin), ld3(rays[i].dir)};
     const Hit h = box >= 0 ? single_box_hit(sc, box, r) : closest_hit(sc, r);
     write_hit(sc, h, &out[i]);
@@ -288,7 +321,7 @@ __global__ void k_intersect(const DevFrame fr, const FramePointers fp, int box, 
 __global__ void k_trace(const DevFrame fr, const FramePointers fp, int depth, const McRay* rays, int n, float4* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
     Ray r{ld3(rays[i].origin), ld3(rays[i].dir)};
     TraceOptions opt;
     opt.start_depth = depth;
@@ -301,7 +334,7 @@ __global__ void k_shade_hits(const DevFrame fr, const FramePointers fp, const Mc
                              const float* shadowFactors, int n, float4* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
     const McHit h = hits[i];
     out[i] = shade_hit(sc, fr, ld3(h.point), ld3(h.normal),
                        make_float4(h.tex_color[0], h.tex_color[1], h.tex_color[2], h.tex_color[3]),
@@ -312,7 +345,7 @@ __global__ void k_in_shadow(const DevFrame fr, const FramePointers fp, const flo
                             const float* lights, int n, int* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
     out[i] = in_shadow(sc, ld3(points + 3 * i), ld3(normals + 3 * i), ld3(lights + 3 * i)) ? 1 : 0;
 }
 
@@ -320,7 +353,7 @@ __global__ void k_soft_shadow(const DevFrame fr, const FramePointers fp, const f
                               const uint32_t* seeds, int samples, int n, float* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
     out[i] = soft_shadow(sc, fr, ld3(points + 3 * i), ld3(normals + 3 * i), samples, seeds[i]);
 }
 
@@ -329,7 +362,7 @@ __global__ void k_ambient_occlusion(const DevFrame fr, const FramePointers fp, c
                                     float* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
     out[i] = ambient_occlusion(sc, ld3(points + 3 * i), ld3(normals + 3 * i), samples, radius, seeds[i]);
 }
 
@@ -352,7 +385,7 @@ __global__ void k_aov(const DevFrame fr, const FramePointers fp, int* outTriId) 
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     const int py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= fr.width || py >= fr.height) return;
-    SceneView sc{fp.boxes, fp.texels, fr.n_boxes};
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
     const float u = (static_cast<float>(px) + 0.5f) / fr.width_f;
     const float v = (static_cast<float>(py) + 0.5f) / fr.height_f;
     const Hit h = closest_hit(sc, camera_ray(fr, u, v));
@@ -367,13 +400,13 @@ void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView&
                     int classify, cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     if (nTiles <= 0) return;
-    k_primary<<<nTiles, kBlockThreads, 0, stream>>>(fr, fp, band, list, classify);
+    k_primary<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, classify);
 }
 
 void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
                   int gridBlocks, cudaStream_t stream) {
     if (gridBlocks <= 0) return;
-    k_shade<<<gridBlocks, kBlockThreads, 0, stream>>>(fr, fp, band, list);
+    k_shade<<<gridBlocks, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list);
 }
 
 void launch_intersect(const DevFrame& fr, const FramePointers& fp, int box, const McRay* rays, int n, McHit* out,

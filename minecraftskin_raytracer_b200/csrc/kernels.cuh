@@ -9,6 +9,8 @@
 namespace mcskin {
 
 constexpr int kBlockThreads = 256;
+// scene blob staged per CTA; 40 KB keeps the default 48 KB dynamic+static shared memory limit (227 boxes)
+constexpr unsigned int kMaxSceneSmemBytes = 40u * 1024u;
 
 // Which tile rows of the frame a launch covers, and where its pixels land.
 // Local tile row r is frame tile row first_tile_row + r*tile_row_stride; the output
@@ -28,8 +30,9 @@ struct ActiveList {
 };
 
 struct FramePointers {
-    const DevBox* boxes;
+    const unsigned char* blob;  // SceneBlobLayout image (device memory)
     const float4* texels;
+    unsigned int blob_bytes;
 };
 
 // Primary pass: per-tile jitter stream, camera rays, hit/miss classification, background
