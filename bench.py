@@ -236,6 +236,9 @@ def run_own_arm(args):
             if rank == 0:
                 deinterleave()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     launches_per_step = 0
     for _ in range(args.warmup):
         flush.fill_(1)
@@ -243,9 +246,6 @@ def run_own_arm(args):
     torch.cuda.synchronize(dev)
     launches_per_step = ctx.sync()["n_kernel_launches"]
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -276,7 +276,9 @@ def run_own_arm(args):
     # ---- e2e: host scene in, host image out, copies inside the timed region
     h2d_bytes = scene.boxes.nbytes + scene.texels.nbytes + C.sizeof(_abi.McScene) + C.sizeof(_abi.McConfig)
     d2h_bytes = H * W * 16
-    if world == 1:
+    if args.kernel_only:
+        e2e_ms = float("nan")
+    elif world == 1:
         for _ in range(max(1, min(args.warmup, 3))):
             lib.render(scene, cfg, device=local_rank)
         t0 = time.perf_counter()
@@ -348,7 +350,7 @@ def run_own_arm(args):
         },
         "active_pixels": int(n_active),
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.kernel_only:
         try:
             res = cpu_reference_run(CPU_SAMPLE, 1, 0)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -366,6 +368,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["own", "reference"], default="own")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="tuning runs: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

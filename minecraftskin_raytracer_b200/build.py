@@ -13,7 +13,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "_lib"
 LIB_PATH = LIB_DIR / "libmcskin_cuda.so"
 
-CUDA_SOURCES = ["kernels.cu", "capi.cu"]
+CUDA_SOURCES = ["kernels.cu", "wavefront.cu", "capi.cu"]
 HOST_SOURCES = ["host_prep.cpp", "skin_scene.cpp"]
 
 # --fmad=false: the geometry chain must round like the x86-64 reference build (no FMA);
@@ -70,6 +70,34 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         print("\n".join(log))
     return LIB_PATH
+
+
+def build_variant(name: str, extra_flags: list[str]) -> Path:
+    """A tuning variant of the library: _lib/variants/libmcskin_cuda_<name>.so (select with MCSKIN_LIB)."""
+    vdir = LIB_DIR / "variants"
+    obj_dir = vdir / f"obj_{name}"
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+    inc = ["-I", str(ROOT / "include"), "-I", str(CSRC)]
+    procs, objs = [], []
+    for src in CUDA_SOURCES + HOST_SOURCES:
+        obj = obj_dir / (src.rsplit(".", 1)[0] + ".o")
+        objs.append(str(obj))
+        procs.append((src, subprocess.Popen([nvcc, "-Xptxas", "-v", *NVCC_FLAGS, *extra_flags, *inc, "-c", str(CSRC / src), "-o", str(obj)],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    out_path = vdir / f"libmcskin_cuda_{name}.so"
+    r = subprocess.run([nvcc, "-shared", "-o", str(out_path), *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    (vdir / f"build_{name}.log").write_text("\n".join(log))
+    return out_path
 
 
 if __name__ == "__main__":

@@ -13,6 +13,7 @@
 
 #include "host_prep.hpp"
 #include "kernels.cuh"
+#include "wavefront.cuh"
 #include "mcskin_cuda.h"
 
 using namespace mcskin;
@@ -85,11 +86,14 @@ struct McContext {
     DevBuf boxes, texels;
     DevBuf count, slotPixel, records;
     DevBuf imgF32, imgU8, scratchIn, scratchOut;
+    DevBuf wave;                 // queues of the wavefront shading pipeline
     PinnedBuf pinned;
     // options
     int forceAllActive = 0;
     long long recordBudgetBytes = 1ll << 31;
     int shadeBlocksPerSm = 8;
+    int shadeMode = 0;                       // 0 wavefront, 1 megakernel (block groups), 2 megakernel (warp groups)
+    long long waveBudgetBytes = 6ll << 30;   // queue storage; pixels beyond it fall back to the megakernel
     // stats of the last render
     McRenderStats stats{};
     bool statsPending = false;
@@ -162,15 +166,31 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
     if (slotCap > 0x7fffffffull) return fail(MC_ERR_LIMIT, "one tile row holds more than 2^31 pixels");
     const int nChunks = static_cast<int>((nRows + rowsPerChunk - 1) / rowsPerChunk);
 
-    CU_TRY(ctx->countLog.reserve(sizeof(unsigned int) * nChunks));
+    CU_TRY(ctx->countLog.reserve(sizeof(unsigned int) * 2 * nChunks));  // [active count | group counter] per chunk
     CU_TRY(ctx->slotPixel.reserve(slotCap * sizeof(uint2)));
     CU_TRY(ctx->records.reserve(std::max<size_t>(16, slotCap * recordBytesPerSlot)));
-    CU_TRY(cudaMemsetAsync(ctx->countLog.p, 0, sizeof(unsigned int) * nChunks, stream));
+    CU_TRY(cudaMemsetAsync(ctx->countLog.p, 0, sizeof(unsigned int) * 2 * nChunks, stream));
 
     while (ctx->passEvents.size() < static_cast<size_t>(3 * nChunks)) {
         cudaEvent_t e;
         CU_TRY(cudaEventCreate(&e));
         ctx->passEvents.push_back(e);
+    }
+    // wavefront queues: sized for a quarter of the worst case (every pixel of a chunk active),
+    // within the budget; anything beyond is shaded by the megakernel
+    WaveView wave{};
+    if (ctx->shadeMode == 0) {
+        const size_t perPath = wavefront_bytes_per_path(f);
+        const size_t worstPaths = slotCap * static_cast<size_t>(f.spp);
+        size_t paths = std::max<size_t>(std::min<size_t>(worstPaths, size_t(1) << 22), worstPaths / 4);
+        paths = std::min(paths, static_cast<size_t>(ctx->waveBudgetBytes) / perPath);
+        paths = std::min<size_t>(paths, 0x7fffff00u);
+        paths = std::max<size_t>(paths, static_cast<size_t>(f.spp));
+        const size_t bytes = paths * perPath + wavefront_fixed_bytes(f);
+        CU_TRY(ctx->wave.reserve(bytes));
+        if (!wavefront_carve(f, ctx->wave.p, ctx->wave.cap, static_cast<unsigned int>(paths),
+                             ctx->smCount * ctx->shadeBlocksPerSm, &wave))
+            return fail(MC_ERR_CUDA, "wavefront buffer carve failed");
     }
     CU_TRY(cudaEventRecord(ctx->ev0, stream));
     const FramePointers fp = frame_pointers(ctx);
@@ -198,9 +218,16 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
         launch_primary(f, fp, band, list, classify ? 1 : 0, stream);
         CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 1], stream));
-        launch_shade(f, fp, band, list, ctx->smCount * ctx->shadeBlocksPerSm, stream);
+        unsigned int* groupCounter = static_cast<unsigned int*>(ctx->countLog.p) + nChunks + c;
+        const int shadeGrid = ctx->smCount * ctx->shadeBlocksPerSm;
+        if (ctx->shadeMode == 0) {
+            launch_wavefront(f, fp, band, list, wave, groupCounter, stream, &launches);
+        } else {
+            launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
+            ++launches;
+        }
         CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 2], stream));
-        launches += 2;
+        ++launches;
     }
     CU_TRY(cudaEventRecord(ctx->ev1, stream));
     CU_TRY(cudaGetLastError());
@@ -337,6 +364,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     CU_TRY(cudaEventCreate(&ctx->ev0));
     CU_TRY(cudaEventCreate(&ctx->ev1));
     if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
+    if (const char* v = std::getenv("MCSKIN_SHADE_MODE")) ctx->shadeMode = std::min(2, std::max(0, std::atoi(v)));
     *out = ctx.release();
     return MC_OK;
 }
@@ -346,7 +374,7 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->boxes, &ctx->texels, &ctx->count, &ctx->slotPixel, &ctx->records, &ctx->imgF32, &ctx->imgU8,
-                      &ctx->scratchIn, &ctx->scratchOut, &ctx->countLog})
+                      &ctx->scratchIn, &ctx->scratchOut, &ctx->countLog, &ctx->wave})
         b->release();
     ctx->pinned.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -362,6 +390,8 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     if (k == "force_all_active") ctx->forceAllActive = value != 0;
     else if (k == "record_budget_bytes") ctx->recordBudgetBytes = std::max<int64_t>(1, value);
     else if (k == "shade_blocks_per_sm") ctx->shadeBlocksPerSm = static_cast<int>(std::max<int64_t>(1, value));
+    else if (k == "shade_mode") ctx->shadeMode = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
+    else if (k == "wave_budget_bytes") ctx->waveBudgetBytes = std::max<int64_t>(1 << 20, value);
     else return fail(MC_ERR_INVALID, "set_option: unknown option " + k);
     return MC_OK;
 }

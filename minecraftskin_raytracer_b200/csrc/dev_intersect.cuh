@@ -119,24 +119,27 @@ __device__ __forceinline__ bool slab_axis(Slab& s, float o, float d, float lo, f
 }
 
 // computeFaceUV + TextureRegion::sample addressing (intersection.cpp:136-196,
-// texture_region.h:19-26) -> texel pool index.
+// texture_region.h:19-26) -> texel pool index.  The two in-plane coordinates are picked
+// first so the (IEEE) divisions exist once: Z faces use (x, y), X faces (z, y), Y faces (x, z).
 __device__ __forceinline__ int face_texel(const DevBox& bx, V3 p, int axis, bool negSide, int face) {
+    const float pa = (axis == 0) ? p.z : p.x;
+    const float la0 = (axis == 0) ? bx.lo[2] : bx.lo[0];
+    const float sa = (axis == 0) ? bx.size[2] : bx.size[0];
+    const float pb = (axis == 1) ? p.z : p.y;
+    const float lb0 = (axis == 1) ? bx.lo[2] : bx.lo[1];
+    const float sb = (axis == 1) ? bx.size[2] : bx.size[1];
+    const float la = (pa - la0) / sa;   // localX (or localZ on X faces)
+    const float lb = (pb - lb0) / sb;   // localY (or localZ on Y faces)
     float u, v;
     if (axis == 2) {
-        const float lx = (p.x - bx.lo[0]) / bx.size[0];
-        const float ly = (p.y - bx.lo[1]) / bx.size[1];
-        u = negSide ? 1.0f - lx : lx;
-        v = 1.0f - ly;
+        u = negSide ? 1.0f - la : la;
+        v = 1.0f - lb;
     } else if (axis == 0) {
-        const float lz = (p.z - bx.lo[2]) / bx.size[2];
-        const float ly = (p.y - bx.lo[1]) / bx.size[1];
-        u = !negSide ? 1.0f - lz : lz;
-        v = 1.0f - ly;
+        u = !negSide ? 1.0f - la : la;
+        v = 1.0f - lb;
     } else {
-        const float lx = (p.x - bx.lo[0]) / bx.size[0];
-        const float lz = (p.z - bx.lo[2]) / bx.size[2];
-        u = lx;
-        v = !negSide ? lz : 1.0f - lz;
+        u = la;
+        v = !negSide ? lb : 1.0f - lb;
     }
     u = clamp01(u);
     v = clamp01(v);
@@ -181,51 +184,55 @@ __device__ __forceinline__ bool box_test(const SceneView& sc, const DevBox& bx, 
         axis = s.exitAxis;
         negSide = s.exitNeg;
     }
-    const V3 p = o + d * tHit;
-    const int face = face_index(axis, negSide);
-    const int texel = face_texel(bx, p, axis, negSide, face);
-    const float alpha = __ldg(&sc.texels[texel].w);
-    if (alpha == 0.0f) {  // intersection.cpp:311-361
-        if (!(bx.flags & kBoxOuter)) return false;
-        if (!(s.tmax > tHit)) return false;
-        const V3 bp = o + d * s.tmax;
-        const int bface = face_index(s.exitAxis, s.exitNeg);
-        const int btexel = face_texel(bx, bp, s.exitAxis, s.exitNeg, bface);
-        const float balpha = __ldg(&sc.texels[btexel].w);
-        if (!(balpha > 0.0f)) return false;
-        out.t = s.tmax;
-        out.p = bp;
-        out.face = bface;
-        out.texel = btexel;
-        out.flip = true;
-        return true;
+    // First the face found above; if its texel is fully transparent and the box is an outer
+    // layer, once more for the exit face at tmax with the normal flipped (intersection.cpp:311-361).
+    // Written as a two-trip loop so the face/UV/texel code exists once.
+    bool flip = false;
+    for (;;) {
+        const V3 p = o + d * tHit;
+        const int face = face_index(axis, negSide);
+        const int texel = face_texel(bx, p, axis, negSide, face);
+        const float alpha = __ldg(&sc.texels[texel].w);
+        const bool opaque = flip ? (alpha > 0.0f) : !(alpha == 0.0f);
+        if (opaque) {
+            out.t = tHit;
+            out.p = p;
+            out.face = face;
+            out.texel = texel;
+            out.flip = flip;
+            return true;
+        }
+        if (flip || !(bx.flags & kBoxOuter) || !(s.tmax > tHit)) return false;
+        flip = true;
+        tHit = s.tmax;
+        axis = s.exitAxis;
+        negSide = s.exitNeg;
     }
-    out.t = tHit;
-    out.p = p;
-    out.face = face;
-    out.texel = texel;
-    out.flip = false;
-    return true;
 }
 
 // intersectMesh (intersection.cpp:373-406): hit distance and point in WORLD space.
-__device__ __forceinline__ bool mesh_test(const SceneView& sc, const DevBox& bx, const Ray& ray, BoxHit& out) {
+__device__ __forceinline__ bool mesh_test(const SceneView sc, const int box, const Ray ray, BoxHit& out) {
+    const DevBox& bx = sc.boxes[box];
     const uint32_t flags = bx.flags;
     if (flags & kBoxEmpty) return false;
-    if (!(flags & kBoxRotated)) return box_test(sc, bx, ray.o, ray.d, out);
-
+    const bool rotated = flags & kBoxRotated;
     const V3 pivot = ld3(bx.pivot);
-    const V3 zero = mk3(0.0f, 0.0f, 0.0f);
     const bool doX = flags & kBoxRotX, doZ = flags & kBoxRotZ;
-    // rotatePoint(o, pivot, 0, -rotZ) then rotatePoint(., pivot, -rotX, 0); same for the direction about 0
-    V3 lo = rotate_about(ray.o, pivot, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
-    lo = rotate_about(lo, pivot, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
-    V3 ld = rotate_about(ray.d, zero, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
-    ld = rotate_about(ld, zero, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
-    ld = normalize3(ld);
-    if (!box_test(sc, bx, lo, ld, out)) return false;
-    out.p = rotate_about(out.p, pivot, doX, bx.fwd_cx, bx.fwd_sx, doZ, bx.fwd_cz, bx.fwd_sz);
-    out.t = dot3(out.p - ray.o, ray.d);
+    V3 o = ray.o, d = ray.d;
+    if (rotated) {
+        const V3 zero = mk3(0.0f, 0.0f, 0.0f);
+        // rotatePoint(o, pivot, 0, -rotZ) then rotatePoint(., pivot, -rotX, 0); same for the direction about 0
+        o = rotate_about(o, pivot, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
+        o = rotate_about(o, pivot, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
+        d = rotate_about(d, zero, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
+        d = rotate_about(d, zero, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
+        d = normalize3(d);
+    }
+    if (!box_test(sc, bx, o, d, out)) return false;
+    if (rotated) {
+        out.p = rotate_about(out.p, pivot, doX, bx.fwd_cx, bx.fwd_sx, doZ, bx.fwd_cz, bx.fwd_sz);
+        out.t = dot3(out.p - ray.o, ray.d);
+    }
     return true;
 }
 
@@ -285,7 +292,7 @@ __device__ __forceinline__ Hit closest_hit(const SceneView& sc, const Ray& ray) 
             const int b = base + __ffs(mask) - 1;
             mask &= mask - 1u;
             BoxHit h;
-            if (mesh_test(sc, sc.boxes[b], ray, h) && h.t < best.t) {
+            if (mesh_test(sc, b, ray, h) && h.t < best.t) {
                 best.t = h.t;
                 best.p = h.p;
                 best.box = b;
@@ -308,7 +315,7 @@ __device__ __forceinline__ Hit single_box_hit(const SceneView& sc, int b, const 
     best.flip = false;
     best.p = mk3(0.0f, 0.0f, 0.0f);
     BoxHit h;
-    if (b >= 0 && b < sc.n_boxes && mesh_test(sc, sc.boxes[b], ray, h)) {
+    if (b >= 0 && b < sc.n_boxes && mesh_test(sc, b, ray, h)) {
         best.t = h.t;
         best.p = h.p;
         best.box = b;
@@ -328,26 +335,76 @@ __device__ __forceinline__ bool any_hit(const SceneView& sc, const Ray& ray) {
             const int b = base + __ffs(mask) - 1;
             mask &= mask - 1u;
             BoxHit h;
-            if (mesh_test(sc, sc.boxes[b], ray, h)) return true;
+            if (mesh_test(sc, b, ray, h)) return true;
         }
     }
     return false;
 }
 
 // isInShadow's `hit.hit && hit.t < distToLight` (shading.cpp:23-25): the closest hit is
-// nearer than the light iff some box reports a hit nearer than the light.
-__device__ __forceinline__ bool occluded(const SceneView& sc, const Ray& ray, float dist) {
+// nearer than the light iff some box reports a hit nearer than the light.  `allow` limits
+// the first 32 boxes to a subset the caller has shown to be sufficient (bundle_box_mask).
+__device__ __forceinline__ bool occluded_among(const SceneView& sc, const Ray& ray, const float dist, const uint32_t allow) {
     const RayPre pre = ray_pre(ray);
     for (int base = 0; base < sc.n_boxes; base += 32) {
         uint32_t mask = candidate_mask(sc, ray, pre, base, dist);
+        if (base == 0) mask &= allow;
         while (mask) {
             const int b = base + __ffs(mask) - 1;
             mask &= mask - 1u;
             BoxHit h;
-            if (mesh_test(sc, sc.boxes[b], ray, h) && h.t < dist) return true;
+            if (mesh_test(sc, b, ray, h) && h.t < dist) return true;
         }
     }
     return false;
+}
+__device__ __forceinline__ bool occluded(const SceneView& sc, const Ray& ray, float dist) {
+    return occluded_among(sc, ray, dist, 0xffffffffu);
+}
+
+// Which of the first 32 boxes can be touched by ANY segment from `from` to a point within
+// `radius` of `to`?  Every such segment stays within `radius` of the centre segment (at the
+// same fraction of its length), so a box it touches, grown by `radius`, is crossed by the
+// centre segment.  Conservative by construction (own arithmetic, generous margins): it only
+// ever removes boxes that no segment of the bundle can reach, so using it to pre-select the
+// boxes of occluded_among() cannot change a result.
+__device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from, V3 to, float radius) {
+    const float grow = radius * 1.01f + 0.01f;
+    const int n = min(32, sc.n_boxes);
+    uint32_t mask = 0u;
+    for (int i = 0; i < n; ++i) {
+        const float4 L = sc.lo[i];
+        const float4 H = sc.hi[i];
+        const uint32_t flags = __float_as_uint(L.w);
+        if (flags & kBoxEmpty) continue;
+        V3 a = from, b = to;
+        if (flags & kBoxRotated) {  // rigid motion into box space; distances are preserved
+            const DevBox& bx = sc.boxes[i];
+            const V3 pivot = ld3(bx.pivot);
+            const bool doX = flags & kBoxRotX, doZ = flags & kBoxRotZ;
+            a = rotate_about(a, pivot, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
+            a = rotate_about(a, pivot, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
+            b = rotate_about(b, pivot, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
+            b = rotate_about(b, pivot, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
+        }
+        const float av[3] = {a.x, a.y, a.z}, dv[3] = {b.x - a.x, b.y - a.y, b.z - a.z};
+        const float lov[3] = {L.x - grow, L.y - grow, L.z - grow}, hiv[3] = {H.x + grow, H.y + grow, H.z + grow};
+        float s0 = 0.0f, s1 = 1.0f;
+        bool out = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (fabsf(dv[k]) < 1e-6f) {
+                out = out || av[k] < lov[k] || av[k] > hiv[k];
+            } else {
+                const float inv = 1.0f / dv[k];
+                const float ta = (lov[k] - av[k]) * inv, tb = (hiv[k] - av[k]) * inv;
+                s0 = fmaxf(s0, fminf(ta, tb));
+                s1 = fminf(s1, fmaxf(ta, tb));
+            }
+        }
+        if (!out && s0 <= s1 + 1e-3f) mask |= 1u << i;
+    }
+    return mask;
 }
 
 // Normal of the winning hit (intersection.cpp:355,366,399-401).

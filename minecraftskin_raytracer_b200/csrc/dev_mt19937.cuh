@@ -43,6 +43,16 @@ __device__ __forceinline__ float mt_canonical(uint32_t u) {
 }
 
 // ---- (b) fresh engine, first outputs only -------------------------------------
+// Word 397 of the seeding sequence, given word 1: 396 dependent LCG steps.  Kept as a
+// short rolled loop: fully unrolling it (19 KB of straight-line code) measured 20 % slower
+// on B200 — instruction-cache misses cost more than the loop counter.
+__device__ __forceinline__ uint32_t mt_seed_word397(uint32_t word1) {
+    uint32_t x = word1;
+#pragma unroll 6
+    for (uint32_t i = 2u; i <= static_cast<uint32_t>(kMtM); ++i) x = mt_lcg(x, i);
+    return x;
+}
+
 struct FreshStream {
     uint32_t cur, nxt, far;
     uint32_t j;
@@ -50,10 +60,7 @@ struct FreshStream {
     __device__ __forceinline__ void seed(uint32_t s) {
         cur = s;
         nxt = mt_lcg(s, 1u);
-        uint32_t x = nxt;
-#pragma unroll 4
-        for (uint32_t i = 2u; i <= static_cast<uint32_t>(kMtM); ++i) x = mt_lcg(x, i);
-        far = x;
+        far = mt_seed_word397(nxt);
         j = 0u;
     }
     // valid for the first kMtN - kMtM = 227 calls

@@ -69,6 +69,17 @@ __device__ __forceinline__ float4 config_background(const DevFrame& fr, float u,
                        fr.bg_center[2] * k + fr.bg_edge[2] * t, 1.0f);
 }
 
+// isInShadow, examining only the boxes of `allow` among the first 32 (see bundle_box_mask)
+__device__ __forceinline__ bool in_shadow_among(const SceneView& sc, V3 point, V3 normal, V3 lightPos, uint32_t allow) {
+    Ray r;
+    r.o = point + normal * kShadowEpsilon;
+    const V3 toLight = lightPos - r.o;
+    const float dist = len3(toLight);
+    if (dist < 1e-6f) return false;
+    r.d = div3(toLight, dist);
+    return occluded_among(sc, r, dist, allow);
+}
+
 // isInShadow
 __device__ __forceinline__ bool in_shadow(const SceneView& sc, V3 point, V3 normal, V3 lightPos) {
     Ray r;
@@ -94,6 +105,13 @@ __device__ __forceinline__ int soft_shadow_count(const SceneView& sc, const DevF
     const V3 toPoint = normalize3(point - lp);
     V3 tangent, bitangent;
     frame_about(toPoint, &tangent, &bitangent);
+    // all shadow rays of this hit start at the same point and end on the light's disk:
+    // pre-select once the boxes that bundle can reach
+#ifdef MCSKIN_BUNDLE
+    const uint32_t allow = bundle_box_mask(sc, point + normal * kShadowEpsilon, lp, fr.light_radius);
+#else
+    const uint32_t allow = 0xffffffffu;
+#endif
     int lit = 0;
     for (int i = 0; i < samples; ++i) {
         const float angle = MCSKIN_TWO_PI_F * rng.next();
@@ -102,22 +120,23 @@ __device__ __forceinline__ int soft_shadow_count(const SceneView& sc, const DevF
         sincos_ref(angle, &sn, &cs);
         const V3 offset = tangent * (r * cs) + bitangent * (r * sn);
         const V3 samplePos = lp + offset;
-        if (!in_shadow(sc, point, normal, samplePos)) ++lit;
+        if (!in_shadow_among(sc, point, normal, samplePos, allow)) ++lit;
     }
     return lit;
 }
 
 // computeSoftShadow
-__device__ __noinline__ float soft_shadow_large(const SceneView& sc, const DevFrame& fr, V3 point, V3 normal,
+static __device__ __noinline__ float soft_shadow_large(const SceneView& sc, const DevFrame& fr, V3 point, V3 normal,
                                                 int samples, uint32_t seed) {
+    if (samples <= 1 || fr.light_radius < 1e-4f) return in_shadow(sc, point, normal, ld3(fr.light_pos)) ? 0.0f : 1.0f;
     LocalEngine rng;
     rng.seed(seed);
     return static_cast<float>(soft_shadow_count(sc, fr, point, normal, samples, rng)) / static_cast<float>(samples);
 }
 __device__ __forceinline__ float soft_shadow(const SceneView& sc, const DevFrame& fr, V3 point, V3 normal,
                                              int samples, uint32_t seed) {
-    if (samples <= 1 || fr.light_radius < 1e-4f) return in_shadow(sc, point, normal, ld3(fr.light_pos)) ? 0.0f : 1.0f;
-    if (2 * samples > kFreshStreamMaxDraws) return soft_shadow_large(sc, fr, point, normal, samples, seed);
+    if (samples <= 1 || fr.light_radius < 1e-4f || 2 * samples > kFreshStreamMaxDraws)
+        return soft_shadow_large(sc, fr, point, normal, samples, seed);  // rare configurations, out of line
     FreshStream rng;
     rng.seed(seed);
     return static_cast<float>(soft_shadow_count(sc, fr, point, normal, samples, rng)) / static_cast<float>(samples);
@@ -146,14 +165,14 @@ __device__ __forceinline__ int ao_count(const SceneView& sc, V3 point, V3 normal
     }
     return occludedCount;
 }
-__device__ __noinline__ float ambient_occlusion_large(const SceneView& sc, V3 point, V3 normal, int samples,
+static __device__ __noinline__ float ambient_occlusion_large(const SceneView& sc, V3 point, V3 normal, int samples,
                                                       float radius, uint32_t seed) {
     LocalEngine rng;
     rng.seed(seed);
     return 1.0f - static_cast<float>(ao_count(sc, point, normal, samples, radius, rng)) / static_cast<float>(samples);
 }
 // RayTracer::computeAO
-__device__ __forceinline__ float ambient_occlusion(const SceneView& sc, V3 point, V3 normal, int samples,
+static __device__ __noinline__ float ambient_occlusion(const SceneView& sc, V3 point, V3 normal, int samples,
                                                    float radius, uint32_t seed) {
     if (2 * samples > kFreshStreamMaxDraws) return ambient_occlusion_large(sc, point, normal, samples, radius, seed);
     FreshStream rng;
@@ -161,15 +180,12 @@ __device__ __forceinline__ float ambient_occlusion(const SceneView& sc, V3 point
     return 1.0f - static_cast<float>(ao_count(sc, point, normal, samples, radius, rng)) / static_cast<float>(samples);
 }
 
-// shade(): Blinn-Phong with the visibility factor (negative = hard shadow test inside)
-__device__ __forceinline__ float4 shade_hit(const SceneView& sc, const DevFrame& fr, V3 P, V3 normal, float4 tex,
-                                            V3 viewDir, float shadowFactor) {
+// shade() with the visibility already known (shading.cpp:62-96 after its shadow test)
+__device__ __forceinline__ float4 shade_lit(const DevFrame& fr, V3 P, V3 normal, float4 tex, V3 viewDir, float vis) {
     const V3 lp = ld3(fr.light_pos);
     const V3 L = normalize3(lp - P);
     const V3 N = normalize3(normal);
     const V3 V = normalize3(viewDir);
-    float vis = shadowFactor;
-    if (vis < 0.0f) vis = in_shadow(sc, P, N, lp) ? 0.0f : 1.0f;
     const float ndl = fmaxf(0.0f, dot3(N, L));
     const float kdiff = fr.kd * ndl * vis;
     const V3 H = normalize3(L + V);
@@ -182,6 +198,45 @@ __device__ __forceinline__ float4 shade_hit(const SceneView& sc, const DevFrame&
     out.z = (tex.z * fr.ambient + tex.z * fr.light_color[2] * kdiff) + fr.light_color[2] * kspec;
     out.w = tex.w;
     return clamp4(out);
+}
+
+// shade(): Blinn-Phong with the visibility factor (negative = hard shadow test inside)
+__device__ __forceinline__ float4 shade_hit(const SceneView& sc, const DevFrame& fr, V3 P, V3 normal, float4 tex,
+                                            V3 viewDir, float shadowFactor) {
+    float vis = shadowFactor;
+    if (vis < 0.0f) vis = in_shadow(sc, P, normalize3(normal), ld3(fr.light_pos)) ? 0.0f : 1.0f;
+    return shade_lit(fr, P, normal, tex, viewDir, vis);
+}
+
+// The points on the light's disk computeSoftShadow samples for one hit, in order
+// (shading.cpp:35-52): frame at the light facing the point, then per sample
+// angle = 2*pi*draw, r = radius*sqrt(draw), position = light + t*(r cos) + b*(r sin).
+template <class Engine>
+__device__ __forceinline__ void soft_shadow_positions(const DevFrame& fr, V3 point, int samples, Engine& rng,
+                                                      float* out /* 3 floats per sample */) {
+    const V3 lp = ld3(fr.light_pos);
+    const V3 toPoint = normalize3(point - lp);
+    V3 tangent, bitangent;
+    frame_about(toPoint, &tangent, &bitangent);
+    for (int i = 0; i < samples; ++i) {
+        const float angle = MCSKIN_TWO_PI_F * rng.next();
+        const float r = fr.light_radius * sqrtf(rng.next());
+        float sn, cs;
+        sincos_ref(angle, &sn, &cs);
+        const V3 offset = tangent * (r * cs) + bitangent * (r * sn);
+        const V3 samplePos = lp + offset;
+        out[3 * i] = samplePos.x;
+        out[3 * i + 1] = samplePos.y;
+        out[3 * i + 2] = samplePos.z;
+    }
+}
+
+// The soft-shadow / AO seeds of traceRay (raytracer.cpp:110-112, :122-123)
+__device__ __forceinline__ uint32_t shadow_seed(V3 P, int depth) {
+    return seed_cast(P.x * 12345.0f + P.y * 67890.0f + P.z * 11111.0f + static_cast<float>(depth) * 99999.0f);
+}
+__device__ __forceinline__ uint32_t ao_seed(V3 P) {
+    return seed_cast(P.x * 73856093.0f + P.y * 19349663.0f + P.z * 83492791.0f);
 }
 
 // traceRay(ray, scene, startDepth, maxBounces, params, config) including the
@@ -222,14 +277,13 @@ __device__ __forceinline__ float4 trace_path(const SceneView& sc, const DevFrame
         const V3 viewDir = normalize3(ray.o - P);
         float shadowFactor = -1.0f;
         if (cfg && fr.soft_on) {
-            const uint32_t seed = seed_cast(P.x * 12345.0f + P.y * 67890.0f + P.z * 11111.0f +
-                                            static_cast<float>(depth) * 99999.0f);
+            const uint32_t seed = shadow_seed(P, depth);
             shadowFactor = soft_shadow(sc, fr, P, nrm, fr.shadow_samples, seed);
         }
         float4 shaded = shade_hit(sc, fr, P, nrm, tex, viewDir, shadowFactor);
         const float alpha = shaded.w;
         if (cfg && fr.ao_on && depth == 0) {
-            const uint32_t seed = seed_cast(P.x * 73856093.0f + P.y * 19349663.0f + P.z * 83492791.0f);
+            const uint32_t seed = ao_seed(P);
             const float ao = ambient_occlusion(sc, P, nrm, fr.ao_samples, fr.ao_radius, seed);
             const float f = 1.0f - fr.ao_intensity * (1.0f - ao);
             shaded.x *= f;

@@ -18,12 +18,11 @@
 
 #include "dev_shade.cuh"
 #include "dev_stage.cuh"
+#include "dev_sample.cuh"
 
 namespace mcskin {
 
 namespace {
-
-constexpr unsigned int kUnusedSlot = 0xffffffffu;
 
 struct TileGeom {
     int x, y, w, h;   // frame pixels
@@ -45,44 +44,8 @@ __device__ __forceinline__ TileGeom tile_geom(const DevFrame& fr, const BandView
     return g;
 }
 
-struct SampleDraws {
-    float jx, jy, r1, r2;
-};
-
-// Order of the draws of one sample in the tile stream: jitter x, y (spp > 1 only), then
-// lens angle, radius (DOF only) — tile_renderer.cpp:92-93 and :58-60.
-__device__ __forceinline__ SampleDraws assign_draws(const DevFrame& fr, float d0, float d1, float d2, float d3) {
-    SampleDraws s;
-    const bool jitter = fr.spp > 1;
-    s.jx = jitter ? d0 : 0.5f;
-    s.jy = jitter ? d1 : 0.5f;
-    s.r1 = jitter ? d2 : d0;
-    s.r2 = jitter ? d3 : d1;
-    return s;
-}
-
-__device__ __forceinline__ void sample_uv(const DevFrame& fr, int px, int py, const SampleDraws& s, float* u, float* v) {
-    *u = (static_cast<float>(px) + s.jx) / fr.width_f;   // tile_renderer.cpp:95-96
-    *v = (static_cast<float>(py) + s.jy) / fr.height_f;
-}
-__device__ __forceinline__ Ray primary_ray(const DevFrame& fr, float u, float v, const SampleDraws& s) {
-    return fr.dof_on ? dof_ray(fr, u, v, s.r1, s.r2) : camera_ray(fr, u, v);
-}
-
-__device__ __forceinline__ void store_pixel(const BandView& band, unsigned int index, float4 c) {
-    if (band.out_f32) band.out_f32[index] = c;
-    if (band.out_u8) band.out_u8[index] = quantize4(c);
-}
-
-__device__ __forceinline__ float4 add4(float4 a, float4 b) {
-    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-}
-__device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
-
-extern __shared__ __align__(16) unsigned char g_sceneSmem[];
-
 __global__ void __launch_bounds__(kBlockThreads)
-k_primary(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list, const int classify) {
+k_primary_cta(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list, const int classify) {
     __shared__ TileStreamSmem mt;
     __shared__ float4 stage[kBlockThreads];
     __shared__ int pixHit[kBlockThreads];
@@ -218,7 +181,8 @@ k_primary(const DevFrame fr, const FramePointers fp, const BandView band, const 
 }
 
 __global__ void __launch_bounds__(kBlockThreads)
-k_shade(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list) {
+k_shade_cta(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list,
+            const unsigned int firstSlot) {
     __shared__ float4 stage[kBlockThreads];
     __shared__ __align__(8) uint64_t stageBar;
 
@@ -226,6 +190,8 @@ k_shade(const DevFrame fr, const FramePointers fp, const BandView band, const Ac
     const int spp = fr.spp, dps = fr.draws_per_sample;
     unsigned int count = *list.count;
     if (count > list.capacity) count = list.capacity;
+    if (count <= firstSlot) return;
+    count -= firstSlot;  // slots [firstSlot, firstSlot + count) are this launch's
 
     const bool small = spp <= kBlockThreads;
     const int pixPerGroup = small ? kBlockThreads / spp : 1;
@@ -240,16 +206,16 @@ k_shade(const DevFrame fr, const FramePointers fp, const BandView band, const Ac
     const bool laneOn = lanePix < pixPerGroup;
 
     for (unsigned int g = blockIdx.x; static_cast<unsigned long long>(g) * pixPerGroup < count; g += gridDim.x) {
-        const unsigned int slot = g * pixPerGroup + lanePix;
+        const unsigned int slot = firstSlot + g * pixPerGroup + lanePix;
         uint2 sp = make_uint2(kUnusedSlot, 0u);
-        if (laneOn && slot < count) sp = list.slot_pixel[slot];
+        if (laneOn && slot - firstSlot < count) sp = list.slot_pixel[slot];
         const bool slotOn = sp.x != kUnusedSlot;
         const int px = static_cast<int>(sp.y & 0xffffu), py = static_cast<int>(sp.y >> 16);
 
         // the summing thread of pixel i of this group is thread i
-        const unsigned int sumSlot = g * pixPerGroup + tid;
+        const unsigned int sumSlot = firstSlot + g * pixPerGroup + tid;
         uint2 sumSp = make_uint2(kUnusedSlot, 0u);
-        if (tid < pixPerGroup && sumSlot < count) sumSp = list.slot_pixel[sumSlot];
+        if (tid < pixPerGroup && sumSlot - firstSlot < count) sumSp = list.slot_pixel[sumSlot];
         float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 
         for (int c = 0; c < chunks; ++c) {
@@ -281,6 +247,242 @@ k_shade(const DevFrame fr, const FramePointers fp, const BandView band, const Ac
             __syncthreads();
         }
         if (sumSp.x != kUnusedSlot) store_pixel(band, sumSp.x, scale4(acc, fr.inv_spp));
+    }
+}
+
+// ---------------------------------------------------------------- warp-autonomous variants
+// For spp a power of two <= 32 (1, 2, 4, 8, 16, 32) a pixel's samples sit in one warp, so
+// hit classification (ballot), the ordered average (warp_resolve) and work-list slots
+// (one atomic per warp) need no block barrier.  The only block-wide step left in the primary
+// pass is the regeneration of the tile's Mersenne-Twister stream, done in rounds of several
+// 624-word blocks between which the eight warps run free.
+
+constexpr int kBigRingSize = 4096;  // floats
+constexpr int kBigRingMask = kBigRingSize - 1;
+struct BigStreamSmem {
+    uint32_t state[2][kMtN];
+    float ring[kBigRingSize];
+};
+
+__device__ __forceinline__ void big_stream_seed(BigStreamSmem* sm, uint32_t seedValue) {
+    if (threadIdx.x == 0) {
+        uint32_t x = seedValue;
+        sm->state[0][0] = x;
+        for (uint32_t i = 1u; i < static_cast<uint32_t>(kMtN); ++i) {
+            x = mt_lcg(x, i);
+            sm->state[0][i] = x;
+        }
+    }
+    __syncthreads();
+}
+// one 624-word block: state[which] -> state[which^1], canonical floats into the ring
+__device__ __forceinline__ void big_stream_block(BigStreamSmem* sm, int which, long long produced) {
+    const uint32_t* a = sm->state[which];
+    uint32_t* b = sm->state[which ^ 1];
+    const int base = static_cast<int>(produced & kBigRingMask);
+    constexpr int kD = kMtN - kMtM;
+    for (int i = threadIdx.x; i < kD; i += blockDim.x) {
+        const uint32_t v = mt_mix(a[i], a[i + 1], a[i + kMtM]);
+        b[i] = v;
+        sm->ring[(base + i) & kBigRingMask] = mt_canonical(mt_temper(v));
+    }
+    __syncthreads();
+    for (int i = kD + threadIdx.x; i < 2 * kD; i += blockDim.x) {
+        const uint32_t v = mt_mix(a[i], a[i + 1], b[i - kD]);
+        b[i] = v;
+        sm->ring[(base + i) & kBigRingMask] = mt_canonical(mt_temper(v));
+    }
+    __syncthreads();
+    for (int i = 2 * kD + threadIdx.x; i < kMtN; i += blockDim.x) {
+        const uint32_t nextWord = (i + 1 == kMtN) ? b[0] : a[i + 1];
+        const uint32_t v = mt_mix(a[i], nextWord, b[i - kD]);
+        b[i] = v;
+        sm->ring[(base + i) & kBigRingMask] = mt_canonical(mt_temper(v));
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_primary_warp(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list, const int lgSpp) {
+    __shared__ BigStreamSmem mt;
+    __shared__ __align__(16) float stageAll[kWarpsPerBlock][kWarpStageFloats];
+    __shared__ __align__(8) uint64_t stageBar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileGeom tg = tile_geom(fr, band, blockIdx.x);
+    const int spp = fr.spp, dps = fr.draws_per_sample;
+    const int nPix = tg.w * tg.h;
+    const int nSamples = nPix * spp;               // <= 2^30 by the tile-size limit
+    const int nGroups = (nSamples + 31) >> 5;      // groups of 32 consecutive samples
+    float* stageW = stageAll[warp];
+
+    const bool tileCanHit = !fr.rect_valid || !(tg.x > fr.rect_x1 || tg.x + tg.w - 1 < fr.rect_x0 ||
+                                                tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
+    if (tileCanHit) stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+
+    if (dps > 0) big_stream_seed(&mt, static_cast<uint32_t>(tg.y * fr.width + tg.x));  // tile_renderer.cpp:78
+    int which = 0;
+    long long produced = 0;
+    // groups whose draws fit in the ring next to one block being written
+    const int groupsPerRound = dps > 0 ? max(kWarpsPerBlock, ((kBigRingSize - kMtN) / (32 * dps)) & ~(kWarpsPerBlock - 1))
+                                       : nGroups;
+    const bool wPow2 = (tg.w & (tg.w - 1)) == 0;
+    const int lgW = 31 - __clz(tg.w);
+
+    for (int g0 = 0; g0 < nGroups; g0 += groupsPerRound) {
+        const int g1 = min(nGroups, g0 + groupsPerRound);
+        if (dps > 0) {
+            const long long need = static_cast<long long>(min(nSamples, g1 * 32)) * dps;
+            while (produced < need) {  // block-uniform
+                big_stream_block(&mt, which, produced);
+                which ^= 1;
+                produced += kMtN;
+            }
+        }
+        for (int g = g0 + warp; g < g1; g += kWarpsPerBlock) {
+            const int k = g * 32 + lane;
+            const bool valid = k < nSamples;
+            const int q = k >> lgSpp;                     // pixel index inside the tile
+            const int ly = wPow2 ? (q >> lgW) : (q / tg.w);
+            const int lx = q - ly * tg.w;
+            const int px = tg.x + lx, py = tg.y + ly;
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            float4 colour = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            bool hit = false;
+            if (valid) {
+                if (dps > 0) {
+                    const int base = (k * dps) & kBigRingMask;   // k*dps < 2^32 wraps consistently with the mask
+                    d0 = mt.ring[base];
+                    d1 = mt.ring[(base + 1) & kBigRingMask];
+                    if (dps > 2) {
+                        d2 = mt.ring[(base + 2) & kBigRingMask];
+                        d3 = mt.ring[(base + 3) & kBigRingMask];
+                    }
+                }
+                const SampleDraws sd = assign_draws(fr, d0, d1, d2, d3);
+                float u, v;
+                sample_uv(fr, px, py, sd, &u, &v);
+                colour = config_background(fr, u, v);  // tile_renderer.cpp:111-114
+                const bool pixelCanHit = tileCanHit && (!fr.rect_valid || (px >= fr.rect_x0 && px <= fr.rect_x1 &&
+                                                                           py >= fr.rect_y0 && py <= fr.rect_y1));
+                if (pixelCanHit) {
+                    const Ray ray = primary_ray(fr, u, v, sd);
+                    hit = !misses_cull_box(fr, ray) && any_hit(sc, ray);
+                }
+            }
+            const unsigned int hitMask = __ballot_sync(kFullMask, hit);
+            const unsigned int validMask = __ballot_sync(kFullMask, valid);
+            // per-pixel view: pixel p of the warp owns lanes [p*spp, (p+1)*spp)
+            const int pix = lane >> lgSpp;
+            const unsigned int laneGroup = (spp == 32) ? kFullMask : (((1u << spp) - 1u) << (pix << lgSpp));
+            const bool pixelActive = (hitMask & laneGroup) != 0u;
+            const bool leader = valid && (lane & (spp - 1)) == 0;
+            const unsigned int outIndex =
+                static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + px;
+            // pixels to resolve here: valid, no sample hit (bit per pixel of the warp)
+            const unsigned int leadersInactive = __ballot_sync(kFullMask, leader && !pixelActive);
+            unsigned int resolveMask = 0u;
+            {
+                unsigned int m = leadersInactive;
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1u;
+                    resolveMask |= 1u << (l >> lgSpp);
+                }
+            }
+            (void)validMask;
+            warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, outIndex, resolveMask);
+
+            // work-list slots for the pixels with a hit: one atomic per warp
+            const unsigned int leadersActive = __ballot_sync(kFullMask, leader && pixelActive);
+            if (leadersActive) {
+                unsigned int base = 0u;
+                if (lane == 0) base = atomicAdd(list.count, static_cast<unsigned int>(__popc(leadersActive)));
+                base = __shfl_sync(kFullMask, base, 0);
+                const int leaderLane = (pix << lgSpp) & 31;
+                const unsigned int rank = __popc(leadersActive & ((1u << leaderLane) - 1u));
+                const unsigned int slot = base + rank;
+                if (valid && pixelActive && slot < list.capacity) {
+                    if (leader)
+                        list.slot_pixel[slot] = make_uint2(outIndex, static_cast<unsigned int>(px) |
+                                                                         (static_cast<unsigned int>(py) << 16));
+                    if (dps > 0) {
+                        float* rec = list.records + (static_cast<size_t>(slot) * spp + (lane & (spp - 1))) * dps;
+                        if (dps == 2) *reinterpret_cast<float2*>(rec) = make_float2(d0, d1);
+                        else *reinterpret_cast<float4*>(rec) = make_float4(d0, d1, d2, d3);
+                    }
+                }
+            }
+        }
+        if (dps > 0 && g1 < nGroups) __syncthreads();  // the ring is rewritten by the next round
+    }
+}
+
+#ifndef MCSKIN_SHADE_MIN_BLOCKS
+#define MCSKIN_SHADE_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kBlockThreads, MCSKIN_SHADE_MIN_BLOCKS)
+k_shade_warp(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list, const int lgSpp,
+             unsigned int* groupCounter, const unsigned int firstSlot) {
+    __shared__ __align__(16) float stageAll[kWarpsPerBlock][kWarpStageFloats];
+    __shared__ __align__(8) uint64_t stageBar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int spp = fr.spp, dps = fr.draws_per_sample;
+    unsigned int count = *list.count;
+    if (count > list.capacity) count = list.capacity;
+    if (count <= firstSlot) return;
+    count -= firstSlot;
+    const int pixPerGroup = 32 >> lgSpp;
+    const unsigned int nGroups = (count + pixPerGroup - 1) / pixPerGroup;
+    if (static_cast<unsigned int>(blockIdx.x) * kWarpsPerBlock >= nGroups) return;  // more warps than groups
+
+    stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    float* stageW = stageAll[warp];
+    const int pix = lane >> lgSpp, s = lane & (spp - 1);
+
+    for (;;) {
+        unsigned int g = 0u;
+        if (lane == 0) g = atomicAdd(groupCounter, 1u);   // dynamic: groups differ a lot in cost (bounces)
+        g = __shfl_sync(kFullMask, g, 0);
+        if (g >= nGroups) break;
+        const unsigned int slot = firstSlot + g * pixPerGroup + pix;
+        uint2 sp = make_uint2(kUnusedSlot, 0u);
+        if (slot - firstSlot < count) sp = list.slot_pixel[slot];
+        const bool on = sp.x != kUnusedSlot;
+        float4 colour = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (on) {
+            const int px = static_cast<int>(sp.y & 0xffffu), py = static_cast<int>(sp.y >> 16);
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            const float* rec = list.records + (static_cast<size_t>(slot) * spp + s) * dps;
+            if (dps == 2) {
+                const float2 r = *reinterpret_cast<const float2*>(rec);
+                d0 = r.x; d1 = r.y;
+            } else if (dps == 4) {
+                const float4 r = *reinterpret_cast<const float4*>(rec);
+                d0 = r.x; d1 = r.y; d2 = r.z; d3 = r.w;
+            }
+            const SampleDraws sd = assign_draws(fr, d0, d1, d2, d3);
+            TraceOptions opt;
+            opt.start_depth = 0;
+            opt.primary_uv = true;
+            sample_uv(fr, px, py, sd, &opt.u, &opt.v);
+            const Ray ray = primary_ray(fr, opt.u, opt.v, sd);
+            colour = trace_path(sc, fr, ray, opt);
+        }
+        const unsigned int leaders = __ballot_sync(kFullMask, on && s == 0);
+        unsigned int resolveMask = 0u;
+        {
+            unsigned int m = leaders;
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1u;
+                resolveMask |= 1u << (l >> lgSpp);
+            }
+        }
+        warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, sp.x, resolveMask);
     }
 }
 
@@ -396,17 +598,33 @@ inline int blocks_for(int n) { return (n + kBlockThreads - 1) / kBlockThreads; }
 
 }  // namespace
 
+static int log2_if_warp_spp(int spp) {
+    for (int lg = 0; lg <= 5; ++lg)
+        if (spp == (1 << lg)) return lg;
+    return -1;
+}
+
 void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
                     int classify, cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     if (nTiles <= 0) return;
-    k_primary<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, classify);
+    // the warp variant indexes a tile's samples with 32-bit integers
+    const long long tileDraws = static_cast<long long>(fr.tile_size) * fr.tile_size * fr.spp * (fr.draws_per_sample > 0 ? fr.draws_per_sample : 1);
+    const int lg = tileDraws < (1ll << 30) ? log2_if_warp_spp(fr.spp) : -1;
+    if (classify && lg >= 0)
+        k_primary_warp<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, lg);
+    else
+        k_primary_cta<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, classify);
 }
 
 void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                  int gridBlocks, cudaStream_t stream) {
+                  int gridBlocks, unsigned int* groupCounter, unsigned int firstSlot, cudaStream_t stream, int variant) {
     if (gridBlocks <= 0) return;
-    k_shade<<<gridBlocks, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list);
+    const int lg = log2_if_warp_spp(fr.spp);
+    if (variant == 2 && lg >= 0)
+        k_shade_warp<<<gridBlocks, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, lg, groupCounter, firstSlot);
+    else
+        k_shade_cta<<<gridBlocks, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, firstSlot);
 }
 
 void launch_intersect(const DevFrame& fr, const FramePointers& fp, int box, const McRay* rays, int n, McHit* out,

@@ -41,8 +41,12 @@ struct FramePointers {
 void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
                     int classify, cudaStream_t stream);
 // Shading pass: full integrator for every sample of every listed pixel, ordered resolve.
+// Megakernel form of the shading pass over the listed pixels from `firstSlot` on.
+// variant 1: block-synchronous groups; variant 2: warp-autonomous groups with dynamic
+// distribution (groupCounter: a zeroed device counter; spp must be a power of two <= 32).
 void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                  int gridBlocks, cudaStream_t stream);
+                  int gridBlocks, unsigned int* groupCounter, unsigned int firstSlot, cudaStream_t stream,
+                  int variant = 1);
 
 // Single-query views of the same device code (all pointers are device memory).
 void launch_intersect(const DevFrame& fr, const FramePointers& fp, int box, const McRay* rays, int n, McHit* out,

@@ -1,0 +1,418 @@
+// wavefront.cu — see wavefront.cuh for the design.  Every arithmetic step is the same
+// device code the megakernel uses (dev_intersect.cuh / dev_shade.cuh); only the order in
+// which threads meet the work differs, so results are bit-identical between the two.
+#include "wavefront.cuh"
+
+#include <algorithm>
+
+#include "dev_sample.cuh"
+
+namespace mcskin {
+
+namespace {
+
+constexpr int kWfThreads = 256;
+
+__device__ __forceinline__ unsigned int pack_hit(const Hit& h) {
+    return static_cast<unsigned int>(h.box & 0xffff) | (static_cast<unsigned int>(h.face) << 16) |
+           (h.flip ? (1u << 24) : 0u);
+}
+__device__ __forceinline__ Hit unpack_hit(float4 geo, float4 org) {
+    Hit h;
+    const unsigned int k = __float_as_uint(geo.w);
+    h.p = mk3(geo.x, geo.y, geo.z);
+    h.box = static_cast<int>(k & 0xffffu);
+    h.face = static_cast<int>((k >> 16) & 0xffu);
+    h.flip = (k >> 24) & 1u;
+    h.texel = __float_as_int(org.w);
+    h.t = 0.0f;
+    return h;
+}
+
+// Appends the hits of a warp to a queue with one atomic; all 32 lanes must call.
+__device__ __forceinline__ void enqueue_hit(const HitQueueView& q, unsigned int* counter, unsigned int capacity,
+                                            bool isHit, const Hit& h, const Ray& ray, unsigned int path) {
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int m = __ballot_sync(0xffffffffu, isHit);
+    if (m == 0u) return;
+    unsigned int base = 0u;
+    if (lane == 0u) base = atomicAdd(counter, static_cast<unsigned int>(__popc(m)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (isHit) {
+        const unsigned int i = base + __popc(m & ((1u << lane) - 1u));
+        if (i < capacity) {
+            q.geo[i] = make_float4(h.p.x, h.p.y, h.p.z, __uint_as_float(pack_hit(h)));
+            q.org[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, __int_as_float(h.texel));
+            q.dir[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(path));
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------- primary hits
+__global__ void __launch_bounds__(kWfThreads)
+k_wf_hit0(const DevFrame fr, const FramePointers fp, const ActiveList list, const WaveView wv) {
+    __shared__ __align__(8) uint64_t stageBar;
+    unsigned int count = *list.count;
+    if (count > list.capacity) count = list.capacity;
+    if (count > wv.slotCapacity) count = wv.slotCapacity;
+    const unsigned long long nPaths = static_cast<unsigned long long>(count) * fr.spp;
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kWfThreads;
+    if (static_cast<unsigned long long>(blockIdx.x) * kWfThreads >= nPaths) return;
+    stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const int spp = fr.spp, dps = fr.draws_per_sample;
+
+    for (unsigned long long p0 = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + (threadIdx.x & ~31u);
+         p0 < nPaths; p0 += stride) {
+        const unsigned long long p = p0 + (threadIdx.x & 31u);
+        bool isHit = false;
+        Hit hit;
+        hit.box = -1; hit.face = 0; hit.texel = 0; hit.flip = false; hit.t = 0.0f; hit.p = mk3(0.f, 0.f, 0.f);
+        Ray ray;
+        ray.o = mk3(0.f, 0.f, 0.f);
+        ray.d = mk3(0.f, 0.f, 0.f);
+        if (p < nPaths) {
+            const unsigned int slot = static_cast<unsigned int>(p / spp);
+            const int s = static_cast<int>(p - static_cast<unsigned long long>(slot) * spp);
+            const uint2 sp = list.slot_pixel[slot];
+            if (sp.x != kUnusedSlot) {
+                const int px = static_cast<int>(sp.y & 0xffffu), py = static_cast<int>(sp.y >> 16);
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+                const float* rec = list.records + (static_cast<size_t>(slot) * spp + s) * dps;
+                if (dps == 2) {
+                    const float2 r = *reinterpret_cast<const float2*>(rec);
+                    d0 = r.x; d1 = r.y;
+                } else if (dps == 4) {
+                    const float4 r = *reinterpret_cast<const float4*>(rec);
+                    d0 = r.x; d1 = r.y; d2 = r.z; d3 = r.w;
+                }
+                const SampleDraws sd = assign_draws(fr, d0, d1, d2, d3);
+                float u, v;
+                sample_uv(fr, px, py, sd, &u, &v);
+                ray = primary_ray(fr, u, v, sd);
+                hit = closest_hit(sc, ray);
+                if (fr.max_bounces < 0) {
+                    // traceRay returns at once (depth 0 > maxBounces, raytracer.cpp:86-90); the tile
+                    // renderer's re-test replaces misses by the gradient (tile_renderer.cpp:111-114)
+                    wv.tail[p] = hit.box < 0 ? config_background(fr, u, v) : config_background(fr, 0.5f, 0.5f);
+                    wv.top[p] = 0;
+                } else if (hit.box < 0) {
+                    wv.tail[p] = config_background(fr, u, v);
+                    wv.top[p] = 0;
+                } else {
+                    isHit = true;
+                }
+            } else {
+                wv.top[p] = -1;  // unused slot
+            }
+        }
+        enqueue_hit(wv.q[0], &wv.qCount[0], wv.pathCapacity, isHit, hit, ray, static_cast<unsigned int>(p));
+    }
+}
+
+// ---------------------------------------------------------------- shadow sample points
+__global__ void __launch_bounds__(kWfThreads)
+k_wf_seed(const DevFrame fr, const WaveView wv, const int which, const int depth) {
+    unsigned int n = wv.qCount[depth];
+    if (n > wv.pathCapacity) n = wv.pathCapacity;
+    const HitQueueView q = wv.q[which];
+    const int N = fr.shadow_samples;
+    for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) {
+        const float4 g = q.geo[i];
+        const V3 P = mk3(g.x, g.y, g.z);
+        FreshStream rng;
+        rng.seed(shadow_seed(P, depth));
+        soft_shadow_positions(fr, P, N, rng, wv.lightPos + static_cast<size_t>(i) * 3 * N);
+        wv.lit[i] = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kWfThreads)
+k_wf_clear_lit(const WaveView wv, const int depth) {
+    unsigned int n = wv.qCount[depth];
+    if (n > wv.pathCapacity) n = wv.pathCapacity;
+    for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) wv.lit[i] = 0u;
+}
+
+// ---------------------------------------------------------------- one shadow ray per thread
+__global__ void __launch_bounds__(kWfThreads)
+k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
+    __shared__ __align__(8) uint64_t stageBar;
+    unsigned int n = wv.qCount[depth];
+    if (n > wv.pathCapacity) n = wv.pathCapacity;
+    const int R = wv.shadowRays;
+    const unsigned long long nRays = static_cast<unsigned long long>(n) * R;
+    if (static_cast<unsigned long long>(blockIdx.x) * kWfThreads >= nRays) return;
+    stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const HitQueueView q = wv.q[which];
+    const bool soft = wv.shadowMode == kShadowSoft;
+    const V3 lightCentre = ld3(fr.light_pos);
+
+    for (unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + threadIdx.x; t < nRays;
+         t += static_cast<unsigned long long>(gridDim.x) * kWfThreads) {
+        const unsigned int i = static_cast<unsigned int>(t / R);
+        const int k = static_cast<int>(t - static_cast<unsigned long long>(i) * R);
+        const float4 g = q.geo[i];
+        const Hit h = unpack_hit(g, make_float4(0.f, 0.f, 0.f, 0.f));
+        V3 normal = hit_normal(sc, h);
+        V3 target = lightCentre;
+        if (soft) {
+            const float* lp = wv.lightPos + (static_cast<size_t>(i) * R + k) * 3;
+            target = mk3(lp[0], lp[1], lp[2]);
+        } else {
+            normal = normalize3(normal);  // shade() hands isInShadow the normalised normal (shading.cpp:69,78)
+        }
+        if (!in_shadow(sc, h.p, normal, target)) atomicAdd(&wv.lit[i], 1u);
+    }
+}
+
+// ---------------------------------------------------------------- shade + bounce
+__global__ void __launch_bounds__(kWfThreads)
+k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
+    __shared__ __align__(8) uint64_t stageBar;
+    unsigned int n = wv.qCount[depth];
+    if (n > wv.pathCapacity) n = wv.pathCapacity;
+    if (blockIdx.x * kWfThreads >= n) return;
+    stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const HitQueueView q = wv.q[which];
+    const HitQueueView qNext = wv.q[which ^ 1];
+    const bool cfg = fr.use_config != 0;
+    const size_t cap = wv.pathCapacity;
+
+    for (unsigned int i0 = blockIdx.x * kWfThreads + (threadIdx.x & ~31u); i0 < n; i0 += gridDim.x * kWfThreads) {
+        const unsigned int i = i0 + (threadIdx.x & 31u);
+        bool bounceHit = false;
+        Hit next;
+        next.box = -1; next.face = 0; next.texel = 0; next.flip = false; next.t = 0.0f; next.p = mk3(0.f, 0.f, 0.f);
+        Ray ray;
+        ray.o = mk3(0.f, 0.f, 0.f);
+        ray.d = mk3(0.f, 0.f, 0.f);
+        unsigned int path = 0u;
+        if (i < n) {
+            const float4 g = q.geo[i], o = q.org[i], d = q.dir[i];
+            const Hit h = unpack_hit(g, o);
+            path = __float_as_uint(d.w);
+            const V3 P = h.p;
+            const V3 nrm = hit_normal(sc, h);
+            const float4 tex = hit_texel(sc, h);
+            const V3 rayO = mk3(o.x, o.y, o.z), rayD = mk3(d.x, d.y, d.z);
+            const V3 viewDir = normalize3(rayO - P);
+            float vis;
+            if (wv.shadowMode == kShadowInThread) {
+                vis = soft_shadow(sc, fr, P, nrm, fr.shadow_samples, shadow_seed(P, depth));
+            } else {
+                vis = static_cast<float>(wv.lit[i]) / static_cast<float>(wv.shadowRays);
+                if (wv.shadowMode == kShadowHard) vis = wv.lit[i] ? 1.0f : 0.0f;
+            }
+            float4 shaded = shade_lit(fr, P, nrm, tex, viewDir, vis);
+            const float alpha = shaded.w;
+            if (cfg && fr.ao_on && depth == 0) {
+                const float ao = ambient_occlusion(sc, P, nrm, fr.ao_samples, fr.ao_radius, ao_seed(P));
+                const float f = 1.0f - fr.ao_intensity * (1.0f - ao);
+                shaded.x *= f;
+                shaded.y *= f;
+                shaded.z *= f;
+            }
+            if (depth < fr.max_bounces && depth < wv.levels) {
+                wv.stack[static_cast<size_t>(depth) * cap + path] = make_float4(shaded.x, shaded.y, shaded.z, alpha);
+                const V3 N = normalize3(nrm);
+                const V3 D = normalize3(rayD);
+                V3 Rd = D - N * (2.0f * dot3(D, N));
+                Rd = normalize3(Rd);
+                ray.o = P + N * kReflectEpsilon;
+                ray.d = Rd;
+                next = closest_hit(sc, ray);
+                if (next.box < 0) {
+                    wv.tail[path] = flat_background(fr);  // bounced rays see the flat colour (raytracer.cpp:101)
+                    wv.top[path] = depth + 1;
+                } else {
+                    bounceHit = true;
+                }
+            } else {
+                shaded.w = alpha;
+                wv.tail[path] = clamp4(shaded);
+                wv.top[path] = depth;
+            }
+        }
+        enqueue_hit(qNext, &wv.qCount[depth + 1], wv.pathCapacity, bounceHit, next, ray, path);
+    }
+}
+
+// ---------------------------------------------------------------- fold + ordered average
+__device__ __forceinline__ float4 fold_path(const WaveView& wv, size_t path) {
+    float4 c = wv.tail[path];
+    const int top = wv.top[path];
+    if (top > 0) {
+        const size_t cap = wv.pathCapacity;
+        const float alpha0 = wv.stack[path].w;
+        const float keep = 1.0f - kReflectivity;
+        for (int k = top - 1; k >= 0; --k) {  // raytracer.cpp:143-147, innermost level first
+            const float4 s = wv.stack[static_cast<size_t>(k) * cap + path];
+            float4 m;
+            m.x = s.x * keep + c.x * kReflectivity;
+            m.y = s.y * keep + c.y * kReflectivity;
+            m.z = s.z * keep + c.z * kReflectivity;
+            m.w = alpha0;
+            c = clamp4(m);
+        }
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(kWfThreads)
+k_wf_resolve_warp(const DevFrame fr, const BandView band, const ActiveList list, const WaveView wv, const int lgSpp) {
+    __shared__ __align__(16) float stageAll[kWfThreads / 32][kWarpStageFloats];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int count = *list.count;
+    if (count > list.capacity) count = list.capacity;
+    if (count > wv.slotCapacity) count = wv.slotCapacity;
+    const int spp = fr.spp;
+    const int pixPerGroup = 32 >> lgSpp;
+    const unsigned int nGroups = (count + pixPerGroup - 1) / pixPerGroup;
+    const int pix = lane >> lgSpp, s = lane & (spp - 1);
+    float* stageW = stageAll[warp];
+    for (unsigned int g = blockIdx.x * (kWfThreads / 32) + warp; g < nGroups; g += gridDim.x * (kWfThreads / 32)) {
+        const unsigned int slot = g * pixPerGroup + pix;
+        uint2 sp = make_uint2(kUnusedSlot, 0u);
+        if (slot < count) sp = list.slot_pixel[slot];
+        const bool on = sp.x != kUnusedSlot;
+        float4 colour = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) colour = fold_path(wv, static_cast<size_t>(slot) * spp + s);
+        const unsigned int leaders = __ballot_sync(0xffffffffu, on && s == 0);
+        unsigned int resolveMask = 0u;
+        {
+            unsigned int m = leaders;
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1u;
+                resolveMask |= 1u << (l >> lgSpp);
+            }
+        }
+        warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, sp.x, resolveMask);
+    }
+}
+
+// any spp: one thread sums a pixel's folded samples in order
+__global__ void __launch_bounds__(kWfThreads)
+k_wf_resolve_pixel(const DevFrame fr, const BandView band, const ActiveList list, const WaveView wv) {
+    unsigned int count = *list.count;
+    if (count > list.capacity) count = list.capacity;
+    if (count > wv.slotCapacity) count = wv.slotCapacity;
+    const int spp = fr.spp;
+    for (unsigned int slot = blockIdx.x * kWfThreads + threadIdx.x; slot < count; slot += gridDim.x * kWfThreads) {
+        const uint2 sp = list.slot_pixel[slot];
+        if (sp.x == kUnusedSlot) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < spp; ++s) acc = add4(acc, fold_path(wv, static_cast<size_t>(slot) * spp + s));
+        store_pixel(band, sp.x, scale4(acc, fr.inv_spp));
+    }
+}
+
+int log2_pow2_le32(int v) {
+    for (int lg = 0; lg <= 5; ++lg)
+        if (v == (1 << lg)) return lg;
+    return -1;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+int shadow_mode_of(const DevFrame& fr) {
+    if (!(fr.use_config && fr.soft_on)) return kShadowHard;
+    if (fr.shadow_samples <= 1 || fr.light_radius < 1e-4f || 2 * fr.shadow_samples > kFreshStreamMaxDraws)
+        return kShadowInThread;
+    return kShadowSoft;
+}
+int stack_levels_of(const DevFrame& fr) {
+    return fr.max_bounces < 0 ? 0 : (fr.max_bounces > kMaxStackDepth ? kMaxStackDepth : fr.max_bounces);
+}
+
+}  // namespace
+
+size_t wavefront_bytes_per_path(const DevFrame& fr) {
+    const int mode = shadow_mode_of(fr);
+    const size_t lightBytes = mode == kShadowSoft ? sizeof(float) * 3 * fr.shadow_samples : 0;
+    return 2 * 3 * sizeof(float4)            // two hit queues
+           + lightBytes + sizeof(unsigned)   // light sample points, lit counters
+           + sizeof(float4) + sizeof(int)    // tail, top
+           + sizeof(float4) * stack_levels_of(fr);
+}
+
+size_t wavefront_fixed_bytes(const DevFrame& fr) {
+    return 256 * 16 + sizeof(unsigned int) * (stack_levels_of(fr) + 3);
+}
+
+bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int pathCapacity, int gridBlocks,
+                     WaveView* out) {
+    WaveView w{};
+    w.pathCapacity = pathCapacity;
+    w.slotCapacity = pathCapacity / static_cast<unsigned int>(fr.spp);
+    w.levels = stack_levels_of(fr);
+    w.shadowMode = shadow_mode_of(fr);
+    w.shadowRays = w.shadowMode == kShadowSoft ? fr.shadow_samples : (w.shadowMode == kShadowHard ? 1 : 0);
+    w.gridBlocks = gridBlocks;
+    unsigned char* p = static_cast<unsigned char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        void* r = p + off;
+        off = align256(off + n);
+        return r;
+    };
+    const size_t cap = pathCapacity;
+    for (int k = 0; k < 2; ++k) {
+        w.q[k].geo = static_cast<float4*>(take(cap * sizeof(float4)));
+        w.q[k].org = static_cast<float4*>(take(cap * sizeof(float4)));
+        w.q[k].dir = static_cast<float4*>(take(cap * sizeof(float4)));
+    }
+    w.lightPos = static_cast<float*>(take(w.shadowMode == kShadowSoft ? cap * sizeof(float) * 3 * fr.shadow_samples : 16));
+    w.lit = static_cast<unsigned int*>(take(cap * sizeof(unsigned int)));
+    w.tail = static_cast<float4*>(take(cap * sizeof(float4)));
+    w.top = static_cast<int*>(take(cap * sizeof(int)));
+    w.stack = static_cast<float4*>(take(std::max<size_t>(16, cap * sizeof(float4) * w.levels)));
+    w.qCount = static_cast<unsigned int*>(take(sizeof(unsigned int) * (w.levels + 3)));
+    if (off > bytes) return false;
+    *out = w;
+    return true;
+}
+
+void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
+                      const WaveView& wv, unsigned int* groupCounter, cudaStream_t stream, int* launches) {
+    int n = 0;
+    const int grid = wv.gridBlocks;
+    cudaMemsetAsync(wv.qCount, 0, sizeof(unsigned int) * (wv.levels + 3), stream);
+    k_wf_hit0<<<grid, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv);
+    ++n;
+    if (fr.max_bounces >= 0) {
+        const int lastDepth = wv.levels;  // depth == levels is the deepest level that can hold hits
+        for (int depth = 0; depth <= lastDepth; ++depth) {
+            const int which = depth & 1;
+            if (wv.shadowMode == kShadowSoft) {
+                k_wf_seed<<<grid, kWfThreads, 0, stream>>>(fr, wv, which, depth);
+                ++n;
+            } else if (wv.shadowMode == kShadowHard) {
+                k_wf_clear_lit<<<grid, kWfThreads, 0, stream>>>(wv, depth);
+                ++n;
+            }
+            if (wv.shadowMode != kShadowInThread) {
+                k_wf_shadow<<<grid, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+                ++n;
+            }
+            k_wf_shade<<<grid, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+            ++n;
+        }
+    }
+    const int lg = log2_pow2_le32(fr.spp);
+    if (lg >= 0)
+        k_wf_resolve_warp<<<grid, kWfThreads, 0, stream>>>(fr, band, list, wv, lg);
+    else
+        k_wf_resolve_pixel<<<grid, kWfThreads, 0, stream>>>(fr, band, list, wv);
+    ++n;
+    // pixels the queues could not take: megakernel, starting at the first slot beyond them
+    launch_shade(fr, fp, band, list, grid, groupCounter, wv.slotCapacity, stream);
+    ++n;
+    if (launches) *launches += n;
+}
+
+}  // namespace mcskin

@@ -1,0 +1,71 @@
+// wavefront.cuh — the shading pass as a wavefront of small kernels.
+//
+// The megakernel (one thread walks one sample through hit -> 8 shadow rays -> shade ->
+// bounce -> ...) measured at half the issue rate of the chip: ncu showed warps waiting for
+// instructions (a 275 KB program whose live part does not fit the instruction cache once
+// warps drift apart) and, when they were kept together with block barriers, waiting for the
+// slowest warp of the block.  The wavefront form runs the same arithmetic as a sequence of
+// short, uniform kernels over compact queues in HBM:
+//
+//   k_wf_hit0    thread = sample of a listed pixel: primary ray, closest hit
+//                -> miss: the sample's colour is the gradient background
+//                -> hit : appended to the depth-0 hit queue
+//   per depth d:
+//     k_wf_seed    thread = hit: fresh std::mt19937 from the hit point (397-step seeding),
+//                  the N points on the light's disk computeSoftShadow would sample
+//     k_wf_shadow  thread = (hit, shadow sample): ONE shadow ray, all lanes identical work
+//     k_wf_shade   thread = hit: Blinn-Phong with the counted visibility, AO, mirror ray,
+//                  closest hit of the bounce -> next queue, or the chain's terminal colour
+//   k_wf_resolve thread = sample: folds the bounce chain back to front with the reference's
+//                mix, then the ordered per-pixel average.
+//
+// Every kernel is a persistent grid-stride loop over a device-side count, so nothing is
+// read back to the host between them.  Pixels beyond the queue capacity (extreme close-ups)
+// are shaded by the megakernel instead; results are identical either way.
+#pragma once
+#include "kernels.cuh"
+
+namespace mcskin {
+
+struct HitQueueView {
+    float4* geo;  // hit point xyz, w = box | face << 16 | flip << 24
+    float4* org;  // ray origin xyz, w = texel index
+    float4* dir;  // ray direction xyz, w = path index
+};
+
+struct WaveView {
+    HitQueueView q[2];       // ping-pong over depth
+    float* lightPos;         // per hit of the current queue: 3 floats per shadow sample
+    unsigned int* lit;       // per hit of the current queue: unoccluded shadow rays
+    float4* tail;            // per path: colour returned by the deepest traceRay call
+    float4* stack;           // [level][path]: shaded colour of every level that spawned a reflection (w = its alpha)
+    int* top;                // per path: number of stack levels in use
+    unsigned int* qCount;    // [levels + 2] queue sizes per depth (zeroed before the frame)
+    unsigned int pathCapacity;
+    unsigned int slotCapacity;  // pixels handled by the wavefront = pathCapacity / spp
+    int levels;              // stack levels allocated
+    int shadowMode;          // see enum below
+    int shadowRays;          // rays per hit cast by k_wf_shadow
+    int gridBlocks;
+};
+
+enum : int {
+    kShadowHard = 0,      // no soft shadows: one ray to the light centre, normalised normal (shade())
+    kShadowSoft = 1,      // computeSoftShadow with 2 <= N <= 113 samples: seed + N rays per hit
+    kShadowInThread = 2   // rare forms (N > 113, N <= 1, radius < 1e-4): evaluated inside k_wf_shade
+};
+
+// Bytes of queue / path storage needed per path for a frame description.
+size_t wavefront_bytes_per_path(const DevFrame& fr);
+// Carves the views out of one allocation of at least pathCapacity * wavefront_bytes_per_path bytes
+// plus wavefront_fixed_bytes; returns false if `bytes` is too small.
+size_t wavefront_fixed_bytes(const DevFrame& fr);
+bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int pathCapacity, int gridBlocks,
+                     WaveView* out);
+
+// Shades every listed pixel (slots < wave.slotCapacity through the wavefront, the rest through the
+// megakernel) and writes the band image.  groupCounter: zeroed device counter.
+void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
+                      const WaveView& wave, unsigned int* groupCounter, cudaStream_t stream, int* launches);
+
+}  // namespace mcskin

@@ -15,7 +15,10 @@ from . import _abi
 from ._abi import McConfig, McContext_p, McHit, McRay, McRenderStats, McScene, McTile  # noqa: F401
 from .scene import FlatScene, pose_array
 
-LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmcskin_cuda.so"
+import os
+
+# MCSKIN_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = Path(os.environ.get("MCSKIN_LIB") or (Path(__file__).resolve().parent / "_lib" / "libmcskin_cuda.so"))
 
 # every symbol include/mcskin_cuda.h declares
 EXPORTS = [

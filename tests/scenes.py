@@ -19,6 +19,12 @@ RENDER_CASES = [
     ("dof_spp1", 8, "64x64", None, dict(width=64, height=64, samples_per_pixel=1, max_bounces=0, dof_enabled=1, aperture=0.5, focus_distance=40.0, ao_enabled=1)),
     ("headline_small", 0, "64x64", None, dict(width=192, height=108, samples_per_pixel=16, max_bounces=4)),
     ("tile7_spp3", 9, "64x64", "walking", dict(width=53, height=41, samples_per_pixel=3, max_bounces=2, tile_size=7)),
+    ("tile7_spp4", 9, "64x64", "walking", dict(width=53, height=41, samples_per_pixel=4, max_bounces=2, tile_size=7)),
+    ("spp32", 11, "64x64", "dab", dict(width=64, height=48, samples_per_pixel=32, max_bounces=2)),
+    ("spp2_dof", 12, "64x64", None, dict(width=80, height=60, samples_per_pixel=2, max_bounces=3, dof_enabled=1, aperture=0.4)),
+    ("spp8_tile24", 13, "legacy", "running", dict(width=100, height=60, samples_per_pixel=8, max_bounces=3, tile_size=24)),
+    ("spp64", 14, "64x64", None, dict(width=40, height=40, samples_per_pixel=64, max_bounces=2)),
+    ("spp300", 15, "64x64", None, dict(width=24, height=24, samples_per_pixel=300, max_bounces=1)),
     ("many_shadow_samples", 10, "64x64", None, dict(width=48, height=48, samples_per_pixel=1, max_bounces=1, shadow_samples=64)),
 ]
 
