@@ -92,8 +92,9 @@ struct McContext {
     int forceAllActive = 0;
     long long recordBudgetBytes = 1ll << 31;
     int shadeBlocksPerSm = 8;
+    int waveQueueLevels = 2;                 // bounce depths handled by queues; deeper ones in-thread
     int shadeMode = 0;                       // 0 wavefront, 1 megakernel (block groups), 2 megakernel (warp groups)
-    long long waveBudgetBytes = 6ll << 30;   // queue storage; pixels beyond it fall back to the megakernel
+    long long waveBudgetBytes = 12ll << 30;   // queue storage; pixels beyond it fall back to the megakernel
     // stats of the last render
     McRenderStats stats{};
     bool statsPending = false;
@@ -182,8 +183,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
     if (ctx->shadeMode == 0) {
         const size_t perPath = wavefront_bytes_per_path(f);
         const size_t worstPaths = slotCap * static_cast<size_t>(f.spp);
-        size_t paths = std::max<size_t>(std::min<size_t>(worstPaths, size_t(1) << 22), worstPaths / 4);
-        paths = std::min(paths, static_cast<size_t>(ctx->waveBudgetBytes) / perPath);
+        size_t paths = std::min(worstPaths, static_cast<size_t>(ctx->waveBudgetBytes) / perPath);
         paths = std::min<size_t>(paths, 0x7fffff00u);
         paths = std::max<size_t>(paths, static_cast<size_t>(f.spp));
         const size_t bytes = paths * perPath + wavefront_fixed_bytes(f);
@@ -191,6 +191,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         if (!wavefront_carve(f, ctx->wave.p, ctx->wave.cap, static_cast<unsigned int>(paths),
                              ctx->smCount * ctx->shadeBlocksPerSm, &wave))
             return fail(MC_ERR_CUDA, "wavefront buffer carve failed");
+        wave.queueLevels = ctx->waveQueueLevels;
     }
     CU_TRY(cudaEventRecord(ctx->ev0, stream));
     const FramePointers fp = frame_pointers(ctx);
@@ -391,6 +392,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "record_budget_bytes") ctx->recordBudgetBytes = std::max<int64_t>(1, value);
     else if (k == "shade_blocks_per_sm") ctx->shadeBlocksPerSm = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "shade_mode") ctx->shadeMode = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
+    else if (k == "wave_queue_levels") ctx->waveQueueLevels = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "wave_budget_bytes") ctx->waveBudgetBytes = std::max<int64_t>(1 << 20, value);
     else return fail(MC_ERR_INVALID, "set_option: unknown option " + k);
     return MC_OK;

@@ -419,6 +419,152 @@ k_primary_warp(const DevFrame fr, const FramePointers fp, const BandView band, c
     }
 }
 
+// ---------------------------------------------------------------- pixel-per-lane primary pass
+// For small spp (spp * draws_per_sample <= 60, which covers the 1..16 spp renders) a lane owns
+// a PIXEL and walks its samples in order: the ordered sum lives in registers, the hit flag is
+// a register OR, and a pixel that turns out to be pure background is finished with one
+// coalesced store — no staging, no ballots.  A warp takes 32 consecutive pixels of the tile's
+// stream, a block 256, so one round needs 256*spp*dps stream words resident; the ring holds
+// that plus one 624-word block, addressed with a one-word skew per 32 so that lanes reading
+// at a stride of spp*dps words hit distinct banks.
+constexpr int kPixRingWords = 16384;
+constexpr int kPixRingMask = kPixRingWords - 1;
+__device__ __forceinline__ int pix_ring_slot(unsigned int n) {
+    const unsigned int m = n & kPixRingMask;
+    return static_cast<int>(m + (m >> 5));
+}
+struct PixStreamSmem {
+    uint32_t state[2][kMtN];
+    float ring[kPixRingWords + kPixRingWords / 32];
+};
+
+__device__ __forceinline__ void pix_stream_block(PixStreamSmem* sm, int which, unsigned int produced) {
+    const uint32_t* a = sm->state[which];
+    uint32_t* b = sm->state[which ^ 1];
+    constexpr int kD = kMtN - kMtM;
+    for (int i = threadIdx.x; i < kD; i += blockDim.x) {
+        const uint32_t v = mt_mix(a[i], a[i + 1], a[i + kMtM]);
+        b[i] = v;
+        sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
+    }
+    __syncthreads();
+    for (int i = kD + threadIdx.x; i < 2 * kD; i += blockDim.x) {
+        const uint32_t v = mt_mix(a[i], a[i + 1], b[i - kD]);
+        b[i] = v;
+        sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
+    }
+    __syncthreads();
+    for (int i = 2 * kD + threadIdx.x; i < kMtN; i += blockDim.x) {
+        const uint32_t nextWord = (i + 1 == kMtN) ? b[0] : a[i + 1];
+        const uint32_t v = mt_mix(a[i], nextWord, b[i - kD]);
+        b[i] = v;
+        sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
+    }
+    __syncthreads();
+}
+
+extern __shared__ __align__(16) unsigned char g_pixSmem[];  // [PixStreamSmem][scene blob]
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list) {
+    __shared__ __align__(8) uint64_t stageBar;
+    PixStreamSmem* mt = reinterpret_cast<PixStreamSmem*>(g_pixSmem);
+    unsigned char* sceneSmem = g_pixSmem + ((sizeof(PixStreamSmem) + 15) & ~size_t(15));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileGeom tg = tile_geom(fr, band, blockIdx.x);
+    const int spp = fr.spp, dps = fr.draws_per_sample;
+    const int nPix = tg.w * tg.h;
+    const unsigned int wordsPerPixel = static_cast<unsigned int>(spp * dps);
+
+    const bool tileCanHit = !fr.rect_valid || !(tg.x > fr.rect_x1 || tg.x + tg.w - 1 < fr.rect_x0 ||
+                                                tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
+    if (tileCanHit) stage_bulk(sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(sceneSmem, fp.texels, fr.n_boxes);
+
+    if (dps > 0) {
+        if (tid == 0) {
+            uint32_t x = static_cast<uint32_t>(tg.y * fr.width + tg.x);  // tile_renderer.cpp:78
+            mt->state[0][0] = x;
+            for (uint32_t i = 1u; i < static_cast<uint32_t>(kMtN); ++i) {
+                x = mt_lcg(x, i);
+                mt->state[0][i] = x;
+            }
+        }
+        __syncthreads();
+    }
+    int which = 0;
+    unsigned int produced = 0u;  // tile streams here are < 2^31 words (checked by the launcher)
+    const bool wPow2 = (tg.w & (tg.w - 1)) == 0;
+    const int lgW = 31 - __clz(tg.w);
+
+    for (int q0 = 0; q0 < nPix; q0 += kBlockThreads) {
+        if (dps > 0) {
+            const unsigned int need = static_cast<unsigned int>(min(nPix, q0 + kBlockThreads)) * wordsPerPixel;
+            while (produced < need) {  // block-uniform
+                pix_stream_block(mt, which, produced);
+                which ^= 1;
+                produced += kMtN;
+            }
+        }
+        const int q = q0 + warp * 32 + lane;
+        const bool valid = q < nPix;
+        const int ly = wPow2 ? (q >> lgW) : (q / tg.w);
+        const int lx = q - ly * tg.w;
+        const int px = tg.x + lx, py = tg.y + ly;
+        const bool pixelCanHit = valid && tileCanHit &&
+                                 (!fr.rect_valid || (px >= fr.rect_x0 && px <= fr.rect_x1 && py >= fr.rect_y0 && py <= fr.rect_y1));
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        bool hit = false;
+        if (valid) {
+            const unsigned int word0 = static_cast<unsigned int>(q) * wordsPerPixel;
+            for (int s = 0; s < spp; ++s) {
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+                if (dps > 0) {
+                    const unsigned int w = word0 + static_cast<unsigned int>(s * dps);
+                    d0 = mt->ring[pix_ring_slot(w)];
+                    d1 = mt->ring[pix_ring_slot(w + 1u)];
+                    if (dps > 2) {
+                        d2 = mt->ring[pix_ring_slot(w + 2u)];
+                        d3 = mt->ring[pix_ring_slot(w + 3u)];
+                    }
+                }
+                const SampleDraws sd = assign_draws(fr, d0, d1, d2, d3);
+                float u, v;
+                sample_uv(fr, px, py, sd, &u, &v);
+                acc = add4(acc, config_background(fr, u, v));  // tile_renderer.cpp:111-119
+                if (pixelCanHit && !hit) {
+                    const Ray ray = primary_ray(fr, u, v, sd);
+                    hit = !misses_cull_box(fr, ray) && any_hit(sc, ray);
+                }
+            }
+        }
+        const unsigned int outIndex = static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + px;
+        if (valid && !hit) store_pixel(band, outIndex, scale4(acc, fr.inv_spp));
+
+        const unsigned int hitMask = __ballot_sync(kFullMask, hit);
+        if (hitMask) {  // work-list slots: one atomic per warp
+            unsigned int base = 0u;
+            if (lane == 0) base = atomicAdd(list.count, static_cast<unsigned int>(__popc(hitMask)));
+            base = __shfl_sync(kFullMask, base, 0);
+            if (hit) {
+                const unsigned int slot = base + __popc(hitMask & ((1u << lane) - 1u));
+                if (slot < list.capacity) {
+                    list.slot_pixel[slot] = make_uint2(outIndex, static_cast<unsigned int>(px) | (static_cast<unsigned int>(py) << 16));
+                    if (dps > 0) {
+                        const unsigned int word0 = static_cast<unsigned int>(q) * wordsPerPixel;
+                        float* rec = list.records + static_cast<size_t>(slot) * wordsPerPixel;
+                        for (unsigned int k = 0; k < wordsPerPixel; k += 2)
+                            *reinterpret_cast<float2*>(rec + k) =
+                                make_float2(mt->ring[pix_ring_slot(word0 + k)], mt->ring[pix_ring_slot(word0 + k + 1u)]);
+                    }
+                }
+            }
+        }
+        if (dps > 0 && q0 + kBlockThreads < nPix) __syncthreads();  // the ring is rewritten by the next round
+    }
+}
+
 #ifndef MCSKIN_SHADE_MIN_BLOCKS
 #define MCSKIN_SHADE_MIN_BLOCKS 3
 #endif
@@ -608,13 +754,24 @@ void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView&
                     int classify, cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     if (nTiles <= 0) return;
-    // the warp variant indexes a tile's samples with 32-bit integers
+    // the warp / pixel variants index a tile's stream with 32-bit integers
     const long long tileDraws = static_cast<long long>(fr.tile_size) * fr.tile_size * fr.spp * (fr.draws_per_sample > 0 ? fr.draws_per_sample : 1);
-    const int lg = tileDraws < (1ll << 30) ? log2_if_warp_spp(fr.spp) : -1;
-    if (classify && lg >= 0)
+    const bool small = tileDraws < (1ll << 30);
+    const int lg = small ? log2_if_warp_spp(fr.spp) : -1;
+    const int wordsPerPixel = fr.spp * fr.draws_per_sample;
+    const size_t pixSmem = ((sizeof(PixStreamSmem) + 15) & ~size_t(15)) + fp.blob_bytes;
+    if (classify && small && kBlockThreads * wordsPerPixel + kMtN <= kPixRingWords) {
+        static bool attrSet = false;
+        if (!attrSet) {
+            cudaFuncSetAttribute(k_primary_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            attrSet = true;
+        }
+        k_primary_pix<<<nTiles, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list);
+    } else if (classify && lg >= 0) {
         k_primary_warp<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, lg);
-    else
+    } else {
         k_primary_cta<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, classify);
+    }
 }
 
 void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,

@@ -169,6 +169,10 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
 }
 
 // ---------------------------------------------------------------- shade + bounce
+// Levels up to wv.queueLevels-1 are queue-driven (their shadow rays ran in k_wf_shadow);
+// a bounce that lands on a deeper level is followed to its end inside the thread, with the
+// shadow rays evaluated in place: by then only a few per cent of the paths are left, too few
+// to be worth three more launches per level.
 __global__ void __launch_bounds__(kWfThreads)
 k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
     __shared__ __align__(8) uint64_t stageBar;
@@ -192,49 +196,62 @@ k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const i
         ray.d = mk3(0.f, 0.f, 0.f);
         unsigned int path = 0u;
         if (i < n) {
-            const float4 g = q.geo[i], o = q.org[i], d = q.dir[i];
-            const Hit h = unpack_hit(g, o);
-            path = __float_as_uint(d.w);
-            const V3 P = h.p;
-            const V3 nrm = hit_normal(sc, h);
-            const float4 tex = hit_texel(sc, h);
-            const V3 rayO = mk3(o.x, o.y, o.z), rayD = mk3(d.x, d.y, d.z);
-            const V3 viewDir = normalize3(rayO - P);
-            float vis;
-            if (wv.shadowMode == kShadowInThread) {
-                vis = soft_shadow(sc, fr, P, nrm, fr.shadow_samples, shadow_seed(P, depth));
-            } else {
-                vis = static_cast<float>(wv.lit[i]) / static_cast<float>(wv.shadowRays);
-                if (wv.shadowMode == kShadowHard) vis = wv.lit[i] ? 1.0f : 0.0f;
-            }
-            float4 shaded = shade_lit(fr, P, nrm, tex, viewDir, vis);
-            const float alpha = shaded.w;
-            if (cfg && fr.ao_on && depth == 0) {
-                const float ao = ambient_occlusion(sc, P, nrm, fr.ao_samples, fr.ao_radius, ao_seed(P));
-                const float f = 1.0f - fr.ao_intensity * (1.0f - ao);
-                shaded.x *= f;
-                shaded.y *= f;
-                shaded.z *= f;
-            }
-            if (depth < fr.max_bounces && depth < wv.levels) {
-                wv.stack[static_cast<size_t>(depth) * cap + path] = make_float4(shaded.x, shaded.y, shaded.z, alpha);
-                const V3 N = normalize3(nrm);
-                const V3 D = normalize3(rayD);
-                V3 Rd = D - N * (2.0f * dot3(D, N));
-                Rd = normalize3(Rd);
-                ray.o = P + N * kReflectEpsilon;
-                ray.d = Rd;
-                next = closest_hit(sc, ray);
-                if (next.box < 0) {
-                    wv.tail[path] = flat_background(fr);  // bounced rays see the flat colour (raytracer.cpp:101)
-                    wv.top[path] = depth + 1;
+            const float4 g = q.geo[i], o = q.org[i], dd = q.dir[i];
+            Hit h = unpack_hit(g, o);
+            path = __float_as_uint(dd.w);
+            V3 rayO = mk3(o.x, o.y, o.z), rayD = mk3(dd.x, dd.y, dd.z);
+            int d = depth;
+            for (;;) {
+                const V3 P = h.p;
+                const V3 nrm = hit_normal(sc, h);
+                const float4 tex = hit_texel(sc, h);
+                const V3 viewDir = normalize3(rayO - P);
+                float vis;
+                if (d == depth && wv.shadowMode != kShadowInThread) {
+                    vis = static_cast<float>(wv.lit[i]) / static_cast<float>(wv.shadowRays);
+                    if (wv.shadowMode == kShadowHard) vis = wv.lit[i] ? 1.0f : 0.0f;
+                } else if (cfg && fr.soft_on) {
+                    vis = soft_shadow(sc, fr, P, nrm, fr.shadow_samples, shadow_seed(P, d));
                 } else {
-                    bounceHit = true;
+                    vis = in_shadow(sc, P, normalize3(nrm), ld3(fr.light_pos)) ? 0.0f : 1.0f;
                 }
-            } else {
+                float4 shaded = shade_lit(fr, P, nrm, tex, viewDir, vis);
+                const float alpha = shaded.w;
+                if (cfg && fr.ao_on && d == 0) {
+                    const float ao = ambient_occlusion(sc, P, nrm, fr.ao_samples, fr.ao_radius, ao_seed(P));
+                    const float f = 1.0f - fr.ao_intensity * (1.0f - ao);
+                    shaded.x *= f;
+                    shaded.y *= f;
+                    shaded.z *= f;
+                }
+                if (d < fr.max_bounces && d < wv.levels) {
+                    wv.stack[static_cast<size_t>(d) * cap + path] = make_float4(shaded.x, shaded.y, shaded.z, alpha);
+                    const V3 N = normalize3(nrm);
+                    const V3 D = normalize3(rayD);
+                    V3 Rd = D - N * (2.0f * dot3(D, N));
+                    Rd = normalize3(Rd);
+                    ray.o = P + N * kReflectEpsilon;
+                    ray.d = Rd;
+                    next = closest_hit(sc, ray);
+                    if (next.box < 0) {
+                        wv.tail[path] = flat_background(fr);  // bounced rays see the flat colour (raytracer.cpp:101)
+                        wv.top[path] = d + 1;
+                        break;
+                    }
+                    if (d + 1 < wv.queueLevels) {  // hand the next level to the queues
+                        bounceHit = true;
+                        break;
+                    }
+                    h = next;
+                    rayO = ray.o;
+                    rayD = ray.d;
+                    ++d;
+                    continue;
+                }
                 shaded.w = alpha;
                 wv.tail[path] = clamp4(shaded);
-                wv.top[path] = depth;
+                wv.top[path] = d;
+                break;
             }
         }
         enqueue_hit(qNext, &wv.qCount[depth + 1], wv.pathCapacity, bounceHit, next, ray, path);
@@ -353,6 +370,7 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
     w.shadowMode = shadow_mode_of(fr);
     w.shadowRays = w.shadowMode == kShadowSoft ? fr.shadow_samples : (w.shadowMode == kShadowHard ? 1 : 0);
     w.gridBlocks = gridBlocks;
+    w.queueLevels = 2;
     unsigned char* p = static_cast<unsigned char*>(base);
     size_t off = 0;
     auto take = [&](size_t n) {
@@ -385,21 +403,23 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
     k_wf_hit0<<<grid, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv);
     ++n;
     if (fr.max_bounces >= 0) {
-        const int lastDepth = wv.levels;  // depth == levels is the deepest level that can hold hits
+        const int lastDepth = std::min(wv.levels, wv.queueLevels - 1);  // deeper levels run inside k_wf_shade
         for (int depth = 0; depth <= lastDepth; ++depth) {
             const int which = depth & 1;
+            // queues shrink roughly tenfold per bounce: do not pay for a full grid of idle blocks
+            const int g = depth == 0 ? grid : std::max(1, grid / 4);
             if (wv.shadowMode == kShadowSoft) {
-                k_wf_seed<<<grid, kWfThreads, 0, stream>>>(fr, wv, which, depth);
+                k_wf_seed<<<g, kWfThreads, 0, stream>>>(fr, wv, which, depth);
                 ++n;
             } else if (wv.shadowMode == kShadowHard) {
-                k_wf_clear_lit<<<grid, kWfThreads, 0, stream>>>(wv, depth);
+                k_wf_clear_lit<<<g, kWfThreads, 0, stream>>>(wv, depth);
                 ++n;
             }
             if (wv.shadowMode != kShadowInThread) {
-                k_wf_shadow<<<grid, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+                k_wf_shadow<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
                 ++n;
             }
-            k_wf_shade<<<grid, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+            k_wf_shade<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
             ++n;
         }
     }
@@ -410,8 +430,10 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
         k_wf_resolve_pixel<<<grid, kWfThreads, 0, stream>>>(fr, band, list, wv);
     ++n;
     // pixels the queues could not take: megakernel, starting at the first slot beyond them
-    launch_shade(fr, fp, band, list, grid, groupCounter, wv.slotCapacity, stream);
-    ++n;
+    if (wv.slotCapacity < list.capacity) {
+        launch_shade(fr, fp, band, list, grid, groupCounter, wv.slotCapacity, stream);
+        ++n;
+    }
     if (launches) *launches += n;
 }
 

@@ -44,6 +44,7 @@ struct WaveView {
     unsigned int pathCapacity;
     unsigned int slotCapacity;  // pixels handled by the wavefront = pathCapacity / spp
     int levels;              // stack levels allocated
+    int queueLevels;         // depths 0..queueLevels-1 go through the queues, deeper ones run in-thread
     int shadowMode;          // see enum below
     int shadowRays;          // rays per hit cast by k_wf_shadow
     int gridBlocks;

@@ -129,17 +129,26 @@ def test_trace_matches(gpu, oracle, use_config, depth):
     assert close.mean() >= 0.998, close.mean()
 
 
+# default: classified primary pass + wavefront shading.  The other modes run the alternative
+# code paths the library keeps (and falls back to) and must give the same image.
+RENDER_MODES = {
+    "default": {},
+    "all_active": {"force_all_active": 1},
+    "megakernel": {"shade_mode": 1},
+    "megakernel_warp": {"shade_mode": 2},
+    "tiny_wave_budget": {"wave_budget_bytes": 1 << 20},   # most pixels overflow to the megakernel
+    "deep_queues": {"wave_queue_levels": 6},
+}
+
+
 @pytest.mark.parametrize("case", RENDER_CASES, ids=[c[0] for c in RENDER_CASES])
-@pytest.mark.parametrize("all_active", [False, True], ids=["classified", "all_active"])
-def test_render_parity(gpu, oracle, case, all_active, monkeypatch):
+@pytest.mark.parametrize("mode", list(RENDER_MODES), ids=list(RENDER_MODES))
+def test_render_parity(gpu, oracle, case, mode):
     name, seed, kind, pose, over = case
     scene = _scene(gpu, seed, kind, pose)
     cfg = make_config(**over)
     want = oracle.render(scene, cfg)
-    if all_active:
-        ctx_opts = {"force_all_active": 1}
-    else:
-        ctx_opts = {}
+    ctx_opts = RENDER_MODES[mode]
     got = _render_with_options(gpu, scene, cfg, ctx_opts)
     rep = pixel_report(got, want, oracle.quantize)
     # hit mask / triangle id at pixel centres
