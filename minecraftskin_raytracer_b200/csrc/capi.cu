@@ -86,6 +86,7 @@ struct McContext {
     DevBuf boxes, texels;
     DevBuf count, slotPixel, records;
     DevBuf imgF32, imgU8, scratchIn, scratchOut;
+    DevBuf tileStates;           // seeded mt19937 state of every tile of a chunk
     DevBuf wave;                 // queues of the wavefront shading pipeline
     PinnedBuf pinned;
     // options
@@ -170,6 +171,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
     CU_TRY(ctx->countLog.reserve(sizeof(unsigned int) * 2 * nChunks));  // [active count | group counter] per chunk
     CU_TRY(ctx->slotPixel.reserve(slotCap * sizeof(uint2)));
     CU_TRY(ctx->records.reserve(std::max<size_t>(16, slotCap * recordBytesPerSlot)));
+    CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, rowsPerChunk * f.tiles_x * 624 * sizeof(uint32_t))));
     CU_TRY(cudaMemsetAsync(ctx->countLog.p, 0, sizeof(unsigned int) * 2 * nChunks, stream));
 
     while (ctx->passEvents.size() < static_cast<size_t>(3 * nChunks)) {
@@ -217,7 +219,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
             CU_TRY(cudaMemcpyAsync(list.count, &list.capacity, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
         }
         CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
-        launch_primary(f, fp, band, list, classify ? 1 : 0, stream);
+        launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p), stream);
         CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 1], stream));
         unsigned int* groupCounter = static_cast<unsigned int*>(ctx->countLog.p) + nChunks + c;
         const int shadeGrid = ctx->smCount * ctx->shadeBlocksPerSm;
@@ -365,6 +367,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     CU_TRY(cudaEventCreate(&ctx->ev0));
     CU_TRY(cudaEventCreate(&ctx->ev1));
     if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
+    if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) ctx->waveQueueLevels = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_SHADE_MODE")) ctx->shadeMode = std::min(2, std::max(0, std::atoi(v)));
     *out = ctx.release();
     return MC_OK;
@@ -375,7 +378,7 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->boxes, &ctx->texels, &ctx->count, &ctx->slotPixel, &ctx->records, &ctx->imgF32, &ctx->imgU8,
-                      &ctx->scratchIn, &ctx->scratchOut, &ctx->countLog, &ctx->wave})
+                      &ctx->scratchIn, &ctx->scratchOut, &ctx->countLog, &ctx->wave, &ctx->tileStates})
         b->release();
     ctx->pinned.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -52,6 +52,8 @@ struct SceneView {
     const DevBox* __restrict__ boxes;   // full records
     const float4* __restrict__ texels;
     int n_boxes;
+    uint32_t posed_mask;   // among boxes 0..31: posed (cannot be pre-rejected in world space)
+    uint32_t usable_mask;  // among boxes 0..31: exist and have triangles
 };
 
 __device__ __forceinline__ V3 face_normal(int face) {
@@ -96,10 +98,10 @@ struct Slab {
     int axis, exitAxis;
     bool neg, exitNeg;
 };
+// inv = 1.0f / d, evaluated once per ray (the reference divides per box; same operands, same result)
 template <int AXIS>
-__device__ __forceinline__ bool slab_axis(Slab& s, float o, float d, float lo, float hi) {
+__device__ __forceinline__ bool slab_axis(Slab& s, float o, float d, float inv, float lo, float hi) {
     if (fabsf(d) < 1e-8f) return !(o < lo || o > hi);
-    const float inv = 1.0f / d;
     const float t0 = (lo - o) * inv;
     const float t1 = (hi - o) * inv;
     const bool swapped = t0 > t1;
@@ -153,6 +155,19 @@ __device__ __forceinline__ int face_texel(const DevBox& bx, V3 p, int axis, bool
     return ft.x + y * w + x;
 }
 
+// ---- phase 1: candidate mask ------------------------------------------------------
+// Per-ray constants of the reject pass.
+struct RayPre {
+    V3 inv;          // 1/d per axis (IEEE division, like the reference's invD)
+    bool parallel;   // some |d_i| < 1e-8: the reject pass is skipped, every box is a candidate
+};
+__device__ __forceinline__ RayPre ray_pre(const Ray& r) {
+    RayPre p;
+    p.parallel = fabsf(r.d.x) < 1e-8f || fabsf(r.d.y) < 1e-8f || fabsf(r.d.z) < 1e-8f;
+    p.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    return p;
+}
+
 struct BoxHit {
     float t;
     V3 p;  // in the space of the ray handed to box_test
@@ -161,7 +176,7 @@ struct BoxHit {
 };
 
 // intersectAABB (intersection.cpp:200-371) against one box, ray already in box space.
-__device__ __forceinline__ bool box_test(const SceneView& sc, const DevBox& bx, V3 o, V3 d, BoxHit& out) {
+__device__ __forceinline__ bool box_test(const SceneView& sc, const DevBox& bx, V3 o, V3 d, V3 inv, BoxHit& out) {
     Slab s;
     s.tmin = -FLT_MAX;
     s.tmax = FLT_MAX;
@@ -169,9 +184,9 @@ __device__ __forceinline__ bool box_test(const SceneView& sc, const DevBox& bx, 
     s.exitAxis = 0;
     s.neg = false;
     s.exitNeg = false;
-    if (!slab_axis<0>(s, o.x, d.x, bx.lo[0], bx.hi[0])) return false;
-    if (!slab_axis<1>(s, o.y, d.y, bx.lo[1], bx.hi[1])) return false;
-    if (!slab_axis<2>(s, o.z, d.z, bx.lo[2], bx.hi[2])) return false;
+    if (!slab_axis<0>(s, o.x, d.x, inv.x, bx.lo[0], bx.hi[0])) return false;
+    if (!slab_axis<1>(s, o.y, d.y, inv.y, bx.lo[1], bx.hi[1])) return false;
+    if (!slab_axis<2>(s, o.z, d.z, inv.z, bx.lo[2], bx.hi[2])) return false;
     // the reference tests this after every axis; tmin only grows and tmax only shrinks,
     // so testing once at the end rejects exactly the same rays
     if (s.tmin > s.tmax || s.tmax < 0.0f) return false;
@@ -211,14 +226,14 @@ __device__ __forceinline__ bool box_test(const SceneView& sc, const DevBox& bx, 
 }
 
 // intersectMesh (intersection.cpp:373-406): hit distance and point in WORLD space.
-__device__ __forceinline__ bool mesh_test(const SceneView sc, const int box, const Ray ray, BoxHit& out) {
+__device__ __forceinline__ bool mesh_test(const SceneView& sc, const int box, const Ray& ray, const RayPre& pre, BoxHit& out) {
     const DevBox& bx = sc.boxes[box];
     const uint32_t flags = bx.flags;
     if (flags & kBoxEmpty) return false;
     const bool rotated = flags & kBoxRotated;
     const V3 pivot = ld3(bx.pivot);
     const bool doX = flags & kBoxRotX, doZ = flags & kBoxRotZ;
-    V3 o = ray.o, d = ray.d;
+    V3 o = ray.o, d = ray.d, inv = pre.inv;
     if (rotated) {
         const V3 zero = mk3(0.0f, 0.0f, 0.0f);
         // rotatePoint(o, pivot, 0, -rotZ) then rotatePoint(., pivot, -rotX, 0); same for the direction about 0
@@ -227,8 +242,9 @@ __device__ __forceinline__ bool mesh_test(const SceneView sc, const int box, con
         d = rotate_about(d, zero, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
         d = rotate_about(d, zero, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
         d = normalize3(d);
+        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     }
-    if (!box_test(sc, bx, o, d, out)) return false;
+    if (!box_test(sc, bx, o, d, inv, out)) return false;
     if (rotated) {
         out.p = rotate_about(out.p, pivot, doX, bx.fwd_cx, bx.fwd_sx, doZ, bx.fwd_cz, bx.fwd_sz);
         out.t = dot3(out.p - ray.o, ray.d);
@@ -236,44 +252,43 @@ __device__ __forceinline__ bool mesh_test(const SceneView sc, const int box, con
     return true;
 }
 
-// ---- phase 1: candidate mask ------------------------------------------------------
-// Per-ray constants of the reject pass.
-struct RayPre {
-    V3 inv;          // 1/d per axis (IEEE division, like the reference's invD)
-    bool parallel;   // some |d_i| < 1e-8: the reject pass is skipped, every box is a candidate
-};
-__device__ __forceinline__ RayPre ray_pre(const Ray& r) {
-    RayPre p;
-    p.parallel = fabsf(r.d.x) < 1e-8f || fabsf(r.d.y) < 1e-8f || fabsf(r.d.z) < 1e-8f;
-    p.inv = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-    return p;
-}
-
 // Bit b set = box (base + b) may be hit: it survives the reference's slab rejection
-// (unposed boxes) or is posed / not pre-testable.  `limit`: boxes whose slab entry is at
-// or beyond it are dropped too (their hit distance is >= the entry distance).
+// (unposed boxes) or is posed / not pre-testable.  With LIMITED, boxes whose slab entry is at
+// or beyond `limit` are dropped too (their hit distance is >= the entry distance).
+// The rejection predicate `tmin > tmax || tmax < 0` is evaluated as max(tmin, 0) > tmax, which
+// is the same boolean for every non-NaN pair.
+template <bool LIMITED>
 __device__ __forceinline__ uint32_t candidate_mask(const SceneView& sc, const Ray& ray, const RayPre& pre, int base,
                                                    float limit) {
     const int n = min(32, sc.n_boxes - base);
-    if (pre.parallel) return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
-    uint32_t mask = 0u;
+    const uint32_t all = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+    uint32_t posed = sc.posed_mask, usable = sc.usable_mask;
+    if (base != 0) {  // scenes with more than 32 meshes: derive the masks of this chunk
+        posed = 0u;
+        usable = 0u;
+        for (int i = 0; i < n; ++i) {
+            const uint32_t flags = __float_as_uint(sc.lo[base + i].w);
+            if (flags & kBoxRotated) posed |= 1u << i;
+            if (!(flags & kBoxEmpty)) usable |= 1u << i;
+        }
+    }
+    if (pre.parallel) return all & usable;
+    uint32_t rejected = 0u;
 #pragma unroll 4
     for (int i = 0; i < n; ++i) {
         const float4 L = sc.lo[base + i];
         const float4 H = sc.hi[base + i];
-        const uint32_t flags = __float_as_uint(L.w);
         // same products the reference forms: (min - o) * invD and (max - o) * invD
         const float ax = (L.x - ray.o.x) * pre.inv.x, bx = (H.x - ray.o.x) * pre.inv.x;
         const float ay = (L.y - ray.o.y) * pre.inv.y, by = (H.y - ray.o.y) * pre.inv.y;
         const float az = (L.z - ray.o.z) * pre.inv.z, bz = (H.z - ray.o.z) * pre.inv.z;
         const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
         const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-        const bool reject = (tmin > tmax) || (tmax < 0.0f) || (tmin >= limit);
-        const bool special = flags & (kBoxRotated | kBoxEmpty);   // warp-uniform
-        const bool keep = special ? !(flags & kBoxEmpty) : !reject;
-        mask |= keep ? (1u << i) : 0u;
+        bool reject = fmaxf(tmin, 0.0f) > tmax;
+        if (LIMITED) reject = reject || !(tmin < limit);
+        if (reject) rejected |= 1u << i;
     }
-    return mask;
+    return (~rejected | posed) & usable & all;
 }
 
 // intersectScene (intersection.cpp:408-421).
@@ -287,12 +302,12 @@ __device__ __forceinline__ Hit closest_hit(const SceneView& sc, const Ray& ray) 
     best.p = mk3(0.0f, 0.0f, 0.0f);
     const RayPre pre = ray_pre(ray);
     for (int base = 0; base < sc.n_boxes; base += 32) {
-        uint32_t mask = candidate_mask(sc, ray, pre, base, FLT_MAX);
+        uint32_t mask = candidate_mask<false>(sc, ray, pre, base, FLT_MAX);
         while (mask) {  // increasing box index: strict '<' keeps the reference's tie order
             const int b = base + __ffs(mask) - 1;
             mask &= mask - 1u;
             BoxHit h;
-            if (mesh_test(sc, b, ray, h) && h.t < best.t) {
+            if (mesh_test(sc, b, ray, pre, h) && h.t < best.t) {
                 best.t = h.t;
                 best.p = h.p;
                 best.box = b;
@@ -315,7 +330,8 @@ __device__ __forceinline__ Hit single_box_hit(const SceneView& sc, int b, const 
     best.flip = false;
     best.p = mk3(0.0f, 0.0f, 0.0f);
     BoxHit h;
-    if (b >= 0 && b < sc.n_boxes && mesh_test(sc, b, ray, h)) {
+    const RayPre pre = ray_pre(ray);
+    if (b >= 0 && b < sc.n_boxes && mesh_test(sc, b, ray, pre, h)) {
         best.t = h.t;
         best.p = h.p;
         best.box = b;
@@ -330,12 +346,12 @@ __device__ __forceinline__ Hit single_box_hit(const SceneView& sc, int b, const 
 __device__ __forceinline__ bool any_hit(const SceneView& sc, const Ray& ray) {
     const RayPre pre = ray_pre(ray);
     for (int base = 0; base < sc.n_boxes; base += 32) {
-        uint32_t mask = candidate_mask(sc, ray, pre, base, FLT_MAX);
+        uint32_t mask = candidate_mask<false>(sc, ray, pre, base, FLT_MAX);
         while (mask) {
             const int b = base + __ffs(mask) - 1;
             mask &= mask - 1u;
             BoxHit h;
-            if (mesh_test(sc, b, ray, h)) return true;
+            if (mesh_test(sc, b, ray, pre, h)) return true;
         }
     }
     return false;
@@ -347,13 +363,13 @@ __device__ __forceinline__ bool any_hit(const SceneView& sc, const Ray& ray) {
 __device__ __forceinline__ bool occluded_among(const SceneView& sc, const Ray& ray, const float dist, const uint32_t allow) {
     const RayPre pre = ray_pre(ray);
     for (int base = 0; base < sc.n_boxes; base += 32) {
-        uint32_t mask = candidate_mask(sc, ray, pre, base, dist);
+        uint32_t mask = candidate_mask<true>(sc, ray, pre, base, dist);
         if (base == 0) mask &= allow;
         while (mask) {
             const int b = base + __ffs(mask) - 1;
             mask &= mask - 1u;
             BoxHit h;
-            if (mesh_test(sc, b, ray, h) && h.t < dist) return true;
+            if (mesh_test(sc, b, ray, pre, h) && h.t < dist) return true;
         }
     }
     return false;
@@ -432,9 +448,9 @@ __device__ __forceinline__ bool misses_cull_box(const DevFrame& fr, const Ray& r
     s.tmax = FLT_MAX;
     s.axis = s.exitAxis = 0;
     s.neg = s.exitNeg = false;
-    if (!slab_axis<0>(s, ray.o.x, ray.d.x, fr.cull_lo[0], fr.cull_hi[0])) return true;
-    if (!slab_axis<1>(s, ray.o.y, ray.d.y, fr.cull_lo[1], fr.cull_hi[1])) return true;
-    if (!slab_axis<2>(s, ray.o.z, ray.d.z, fr.cull_lo[2], fr.cull_hi[2])) return true;
+    if (!slab_axis<0>(s, ray.o.x, ray.d.x, 1.0f / ray.d.x, fr.cull_lo[0], fr.cull_hi[0])) return true;
+    if (!slab_axis<1>(s, ray.o.y, ray.d.y, 1.0f / ray.d.y, fr.cull_lo[1], fr.cull_hi[1])) return true;
+    if (!slab_axis<2>(s, ray.o.z, ray.d.z, 1.0f / ray.d.z, fr.cull_lo[2], fr.cull_hi[2])) return true;
     return s.tmin > s.tmax || s.tmax < 0.0f;
 }
 

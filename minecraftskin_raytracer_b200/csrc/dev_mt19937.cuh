@@ -48,7 +48,17 @@ __device__ __forceinline__ float mt_canonical(uint32_t u) {
 // on B200 — instruction-cache misses cost more than the loop counter.
 __device__ __forceinline__ uint32_t mt_seed_word397(uint32_t word1) {
     uint32_t x = word1;
-#pragma unroll 6
+#pragma unroll 12
+    for (uint32_t i = 2u; i <= static_cast<uint32_t>(kMtM); ++i) x = mt_lcg(x, i);
+    return x;
+}
+
+// The same 396 steps fully unrolled (SHF + LOP3 + IMAD with the index as an immediate, no
+// loop counter): for small kernels that do little else (k_wf_seed), where 19 KB of
+// straight-line code sits comfortably in the instruction cache.
+__device__ __forceinline__ uint32_t mt_seed_word397_unrolled(uint32_t word1) {
+    uint32_t x = word1;
+#pragma unroll
     for (uint32_t i = 2u; i <= static_cast<uint32_t>(kMtM); ++i) x = mt_lcg(x, i);
     return x;
 }
@@ -56,6 +66,13 @@ __device__ __forceinline__ uint32_t mt_seed_word397(uint32_t word1) {
 struct FreshStream {
     uint32_t cur, nxt, far;
     uint32_t j;
+
+    __device__ __forceinline__ void seed_unrolled(uint32_t s) {
+        cur = s;
+        nxt = mt_lcg(s, 1u);
+        far = mt_seed_word397_unrolled(nxt);
+        j = 0u;
+    }
 
     __device__ __forceinline__ void seed(uint32_t s) {
         cur = s;

@@ -33,8 +33,7 @@ __device__ __forceinline__ Ray camera_ray(const DevFrame& fr, float u, float v) 
 
 // sinf/cosf of a float angle.  TODO(parity): glibc-exact double-precision evaluation.
 __device__ __forceinline__ void sincos_ref(float a, float* s, float* c) {
-    *s = sinf(a);
-    *c = cosf(a);
+    sincosf(a, s, c);
 }
 
 // generateDOFRay; r1, r2 are the two lens draws that follow the jitter draws.

@@ -41,7 +41,8 @@ __device__ __forceinline__ void stage_bulk(void* dst, const void* src, uint32_t 
 }
 
 // Scene view over a blob that already sits at `blob` (shared or global memory).
-__device__ __forceinline__ SceneView scene_view(const unsigned char* blob, const float4* texels, int nBoxes) {
+__device__ __forceinline__ SceneView scene_view(const unsigned char* blob, const float4* texels, const DevFrame& fr) {
+    const int nBoxes = fr.n_boxes;
     const SceneBlobLayout lay(nBoxes);
     SceneView sc;
     sc.lo = reinterpret_cast<const float4*>(blob + lay.loOffset());
@@ -49,6 +50,8 @@ __device__ __forceinline__ SceneView scene_view(const unsigned char* blob, const
     sc.boxes = reinterpret_cast<const DevBox*>(blob + lay.boxOffset());
     sc.texels = texels;
     sc.n_boxes = nBoxes;
+    sc.posed_mask = fr.posed_mask;
+    sc.usable_mask = fr.usable_mask;
     return sc;
 }
 

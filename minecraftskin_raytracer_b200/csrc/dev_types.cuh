@@ -66,6 +66,7 @@ struct DevFrame {
     float aperture, focus_dist;
     // scene
     int n_boxes;
+    uint32_t posed_mask, usable_mask;   // over boxes 0..31: posed / has triangles
     float light_pos[3], light_color[4], light_radius;
     float background[4];
     // integrator

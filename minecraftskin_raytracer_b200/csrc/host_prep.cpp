@@ -213,6 +213,10 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
             d.fwd_cz = std::cos(fz); d.fwd_sz = std::sin(fz);
         }
         d.flags = flags;
+        if (b < 32) {
+            if (flags & kBoxRotated) f.posed_mask |= 1u << b;
+            if (!(flags & kBoxEmpty)) f.usable_mask |= 1u << b;
+        }
         for (int k = 0; k < kFaceCount; ++k) {
             const McFaceTex& ft = src.face[k];
             int offset, w, h;

@@ -62,7 +62,7 @@ k_primary_cta(const DevFrame fr, const FramePointers fp, const BandView band, co
     const bool tileCanHit = !fr.rect_valid || !(tg.x > fr.rect_x1 || tg.x + tg.w - 1 < fr.rect_x0 ||
                                                 tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
     if (tileCanHit || !classify) stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
-    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
 
     TileStream stream;
     stream.sm = &mt;
@@ -198,7 +198,7 @@ k_shade_cta(const DevFrame fr, const FramePointers fp, const BandView band, cons
     if (static_cast<unsigned long long>(blockIdx.x) * pixPerGroup >= count) return;  // nothing for this CTA
 
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
-    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
 
     const int chunks = small ? 1 : (spp + kBlockThreads - 1) / kBlockThreads;
     const int lanePix = small ? tid / spp : 0;
@@ -319,7 +319,7 @@ k_primary_warp(const DevFrame fr, const FramePointers fp, const BandView band, c
     const bool tileCanHit = !fr.rect_valid || !(tg.x > fr.rect_x1 || tg.x + tg.w - 1 < fr.rect_x0 ||
                                                 tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
     if (tileCanHit) stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
-    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
 
     if (dps > 0) big_stream_seed(&mt, static_cast<uint32_t>(tg.y * fr.width + tg.x));  // tile_renderer.cpp:78
     int which = 0;
@@ -438,35 +438,59 @@ struct PixStreamSmem {
     float ring[kPixRingWords + kPixRingWords / 32];
 };
 
+// One 624-word block of the stream: state[which] -> state[which^1], canonical floats into
+// the ring.  Three dependent phases of 227 / 227 / 170 words, one word per thread.
 __device__ __forceinline__ void pix_stream_block(PixStreamSmem* sm, int which, unsigned int produced) {
+    static_assert(kBlockThreads >= kMtN - kMtM, "one thread per word of a phase");
     const uint32_t* a = sm->state[which];
     uint32_t* b = sm->state[which ^ 1];
     constexpr int kD = kMtN - kMtM;
-    for (int i = threadIdx.x; i < kD; i += blockDim.x) {
+    const int i = threadIdx.x;
+    if (i < kD) {
         const uint32_t v = mt_mix(a[i], a[i + 1], a[i + kMtM]);
         b[i] = v;
         sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
-    for (int i = kD + threadIdx.x; i < 2 * kD; i += blockDim.x) {
-        const uint32_t v = mt_mix(a[i], a[i + 1], b[i - kD]);
-        b[i] = v;
-        sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
+    if (i < kD) {
+        const int j = kD + i;
+        const uint32_t v = mt_mix(a[j], a[j + 1], b[i]);
+        b[j] = v;
+        sm->ring[pix_ring_slot(produced + j)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
-    for (int i = 2 * kD + threadIdx.x; i < kMtN; i += blockDim.x) {
-        const uint32_t nextWord = (i + 1 == kMtN) ? b[0] : a[i + 1];
-        const uint32_t v = mt_mix(a[i], nextWord, b[i - kD]);
-        b[i] = v;
-        sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
+    if (i < kMtN - 2 * kD) {
+        const int j = 2 * kD + i;
+        const uint32_t nextWord = (j + 1 == kMtN) ? b[0] : a[j + 1];
+        const uint32_t v = mt_mix(a[j], nextWord, b[j - kD]);
+        b[j] = v;
+        sm->ring[pix_ring_slot(produced + j)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
+}
+
+// Seeding of every tile's engine (state[0] = seed, state[i] = f(state[i-1], i)): 623
+// dependent steps that cannot be shared out inside a tile, so they run one tile per THREAD
+// in a small kernel of their own instead of idling 255 threads of each tile's block.
+__global__ void k_tile_seed(const DevFrame fr, const BandView band, uint32_t* states) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nTiles = band.n_tile_rows * fr.tiles_x;
+    if (t >= nTiles) return;
+    const TileGeom tg = tile_geom(fr, band, t);
+    uint32_t x = static_cast<uint32_t>(tg.y * fr.width + tg.x);  // tile_renderer.cpp:78
+    uint32_t* st = states + static_cast<size_t>(t) * kMtN;
+    st[0] = x;
+    for (uint32_t i = 1u; i < static_cast<uint32_t>(kMtN); ++i) {
+        x = mt_lcg(x, i);
+        st[i] = x;
+    }
 }
 
 extern __shared__ __align__(16) unsigned char g_pixSmem[];  // [PixStreamSmem][scene blob]
 
 __global__ void __launch_bounds__(kBlockThreads)
-k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list) {
+k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list,
+              const uint32_t* __restrict__ tileStates) {
     __shared__ __align__(8) uint64_t stageBar;
     PixStreamSmem* mt = reinterpret_cast<PixStreamSmem*>(g_pixSmem);
     unsigned char* sceneSmem = g_pixSmem + ((sizeof(PixStreamSmem) + 15) & ~size_t(15));
@@ -480,17 +504,11 @@ k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, co
     const bool tileCanHit = !fr.rect_valid || !(tg.x > fr.rect_x1 || tg.x + tg.w - 1 < fr.rect_x0 ||
                                                 tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
     if (tileCanHit) stage_bulk(sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
-    const SceneView sc = scene_view(sceneSmem, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(sceneSmem, fp.texels, fr);
 
-    if (dps > 0) {
-        if (tid == 0) {
-            uint32_t x = static_cast<uint32_t>(tg.y * fr.width + tg.x);  // tile_renderer.cpp:78
-            mt->state[0][0] = x;
-            for (uint32_t i = 1u; i < static_cast<uint32_t>(kMtN); ++i) {
-                x = mt_lcg(x, i);
-                mt->state[0][i] = x;
-            }
-        }
+    if (dps > 0) {  // this tile's freshly seeded engine (k_tile_seed)
+        const uint32_t* st = tileStates + static_cast<size_t>(blockIdx.x) * kMtN;
+        for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = st[i];
         __syncthreads();
     }
     int which = 0;
@@ -585,7 +603,7 @@ k_shade_warp(const DevFrame fr, const FramePointers fp, const BandView band, con
     if (static_cast<unsigned int>(blockIdx.x) * kWarpsPerBlock >= nGroups) return;  // more warps than groups
 
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
-    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
     float* stageW = stageAll[warp];
     const int pix = lane >> lgSpp, s = lane & (spp - 1);
 
@@ -660,7 +678,7 @@ __device__ __forceinline__ void write_hit(const SceneView& sc, const Hit& h, McH
 __global__ void k_intersect(const DevFrame fr, const FramePointers fp, int box, const McRay* rays, int n, McHit* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr);
     Ray r{ld3(rays[i].origin), ld3(rays[i].dir)};
     const Hit h = box >= 0 ? single_box_hit(sc, box, r) : closest_hit(sc, r);
     write_hit(sc, h, &out[i]);
@@ -669,7 +687,7 @@ __global__ void k_intersect(const DevFrame fr, const FramePointers fp, int box, 
 __global__ void k_trace(const DevFrame fr, const FramePointers fp, int depth, const McRay* rays, int n, float4* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr);
     Ray r{ld3(rays[i].origin), ld3(rays[i].dir)};
     TraceOptions opt;
     opt.start_depth = depth;
@@ -682,7 +700,7 @@ __global__ void k_shade_hits(const DevFrame fr, const FramePointers fp, const Mc
                              const float* shadowFactors, int n, float4* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr);
     const McHit h = hits[i];
     out[i] = shade_hit(sc, fr, ld3(h.point), ld3(h.normal),
                        make_float4(h.tex_color[0], h.tex_color[1], h.tex_color[2], h.tex_color[3]),
@@ -693,7 +711,7 @@ __global__ void k_in_shadow(const DevFrame fr, const FramePointers fp, const flo
                             const float* lights, int n, int* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr);
     out[i] = in_shadow(sc, ld3(points + 3 * i), ld3(normals + 3 * i), ld3(lights + 3 * i)) ? 1 : 0;
 }
 
@@ -701,7 +719,7 @@ __global__ void k_soft_shadow(const DevFrame fr, const FramePointers fp, const f
                               const uint32_t* seeds, int samples, int n, float* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr);
     out[i] = soft_shadow(sc, fr, ld3(points + 3 * i), ld3(normals + 3 * i), samples, seeds[i]);
 }
 
@@ -710,7 +728,7 @@ __global__ void k_ambient_occlusion(const DevFrame fr, const FramePointers fp, c
                                     float* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr);
     out[i] = ambient_occlusion(sc, ld3(points + 3 * i), ld3(normals + 3 * i), samples, radius, seeds[i]);
 }
 
@@ -733,7 +751,7 @@ __global__ void k_aov(const DevFrame fr, const FramePointers fp, int* outTriId) 
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     const int py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= fr.width || py >= fr.height) return;
-    const SceneView sc = scene_view(fp.blob, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr);
     const float u = (static_cast<float>(px) + 0.5f) / fr.width_f;
     const float v = (static_cast<float>(py) + 0.5f) / fr.height_f;
     const Hit h = closest_hit(sc, camera_ray(fr, u, v));
@@ -751,7 +769,7 @@ static int log2_if_warp_spp(int spp) {
 }
 
 void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                    int classify, cudaStream_t stream) {
+                    int classify, uint32_t* tileStates, cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     if (nTiles <= 0) return;
     // the warp / pixel variants index a tile's stream with 32-bit integers
@@ -766,7 +784,8 @@ void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView&
             cudaFuncSetAttribute(k_primary_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attrSet = true;
         }
-        k_primary_pix<<<nTiles, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list);
+        if (fr.draws_per_sample > 0) k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates);
+        k_primary_pix<<<nTiles, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates);
     } else if (classify && lg >= 0) {
         k_primary_warp<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, lg);
     } else {

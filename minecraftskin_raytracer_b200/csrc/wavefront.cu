@@ -60,7 +60,7 @@ k_wf_hit0(const DevFrame fr, const FramePointers fp, const ActiveList list, cons
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kWfThreads;
     if (static_cast<unsigned long long>(blockIdx.x) * kWfThreads >= nPaths) return;
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
-    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
     const int spp = fr.spp, dps = fr.draws_per_sample;
 
     for (unsigned long long p0 = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + (threadIdx.x & ~31u);
@@ -145,14 +145,16 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
     const unsigned long long nRays = static_cast<unsigned long long>(n) * R;
     if (static_cast<unsigned long long>(blockIdx.x) * kWfThreads >= nRays) return;
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
-    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
     const HitQueueView q = wv.q[which];
     const bool soft = wv.shadowMode == kShadowSoft;
     const V3 lightCentre = ld3(fr.light_pos);
+    const bool rPow2 = (R & (R - 1)) == 0;
+    const int lgR = 31 - __clz(R);
 
     for (unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + threadIdx.x; t < nRays;
          t += static_cast<unsigned long long>(gridDim.x) * kWfThreads) {
-        const unsigned int i = static_cast<unsigned int>(t / R);
+        const unsigned int i = rPow2 ? static_cast<unsigned int>(t >> lgR) : static_cast<unsigned int>(t / R);
         const int k = static_cast<int>(t - static_cast<unsigned long long>(i) * R);
         const float4 g = q.geo[i];
         const Hit h = unpack_hit(g, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -180,7 +182,7 @@ k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const i
     if (n > wv.pathCapacity) n = wv.pathCapacity;
     if (blockIdx.x * kWfThreads >= n) return;
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
-    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr.n_boxes);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
     const HitQueueView q = wv.q[which];
     const HitQueueView qNext = wv.q[which ^ 1];
     const bool cfg = fr.use_config != 0;
@@ -407,7 +409,7 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
         for (int depth = 0; depth <= lastDepth; ++depth) {
             const int which = depth & 1;
             // queues shrink roughly tenfold per bounce: do not pay for a full grid of idle blocks
-            const int g = depth == 0 ? grid : std::max(1, grid / 4);
+            const int g = depth == 0 ? grid : (depth == 1 ? std::max(1, grid / 4) : std::max(1, grid / 8));
             if (wv.shadowMode == kShadowSoft) {
                 k_wf_seed<<<g, kWfThreads, 0, stream>>>(fr, wv, which, depth);
                 ++n;
