@@ -106,11 +106,7 @@ __device__ __forceinline__ int soft_shadow_count(const SceneView& sc, const DevF
     frame_about(toPoint, &tangent, &bitangent);
     // all shadow rays of this hit start at the same point and end on the light's disk:
     // pre-select once the boxes that bundle can reach
-#ifdef MCSKIN_BUNDLE
     const uint32_t allow = bundle_box_mask(sc, point + normal * kShadowEpsilon, lp, fr.light_radius);
-#else
-    const uint32_t allow = 0xffffffffu;
-#endif
     int lit = 0;
     for (int i = 0; i < samples; ++i) {
         const float angle = MCSKIN_TWO_PI_F * rng.next();

@@ -113,18 +113,26 @@ k_wf_hit0(const DevFrame fr, const FramePointers fp, const ActiveList list, cons
 
 // ---------------------------------------------------------------- shadow sample points
 __global__ void __launch_bounds__(kWfThreads)
-k_wf_seed(const DevFrame fr, const WaveView wv, const int which, const int depth) {
+k_wf_seed(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
+    __shared__ __align__(8) uint64_t stageBar;
     unsigned int n = wv.qCount[depth];
     if (n > wv.pathCapacity) n = wv.pathCapacity;
+    if (blockIdx.x * kWfThreads >= n) return;
+    stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
     const HitQueueView q = wv.q[which];
     const int N = fr.shadow_samples;
     for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) {
         const float4 g = q.geo[i];
-        const V3 P = mk3(g.x, g.y, g.z);
+        const Hit h = unpack_hit(g, make_float4(0.f, 0.f, 0.f, 0.f));
+        const V3 P = h.p;
         FreshStream rng;
         rng.seed(shadow_seed(P, depth));
         soft_shadow_positions(fr, P, N, rng, wv.lightPos + static_cast<size_t>(i) * 3 * N);
         wv.lit[i] = 0u;
+        // the boxes the bundle of this hit's shadow rays can reach (computeSoftShadow hands
+        // isInShadow the raw hit normal: shading.cpp:54, raytracer.cpp:113)
+        wv.allow[i] = bundle_box_mask(sc, P + hit_normal(sc, h) * kShadowEpsilon, ld3(fr.light_pos), fr.light_radius);
     }
 }
 
@@ -166,7 +174,8 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
         } else {
             normal = normalize3(normal);  // shade() hands isInShadow the normalised normal (shading.cpp:69,78)
         }
-        if (!in_shadow(sc, h.p, normal, target)) atomicAdd(&wv.lit[i], 1u);
+        const uint32_t allow = soft ? wv.allow[i] : 0xffffffffu;
+        if (!in_shadow_among(sc, h.p, normal, target, allow)) atomicAdd(&wv.lit[i], 1u);
     }
 }
 
@@ -354,7 +363,7 @@ size_t wavefront_bytes_per_path(const DevFrame& fr) {
     const int mode = shadow_mode_of(fr);
     const size_t lightBytes = mode == kShadowSoft ? sizeof(float) * 3 * fr.shadow_samples : 0;
     return 2 * 3 * sizeof(float4)            // two hit queues
-           + lightBytes + sizeof(unsigned)   // light sample points, lit counters
+           + lightBytes + 2 * sizeof(unsigned)   // light sample points, lit counters, box masks
            + sizeof(float4) + sizeof(int)    // tail, top
            + sizeof(float4) * stack_levels_of(fr);
 }
@@ -388,6 +397,7 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
     }
     w.lightPos = static_cast<float*>(take(w.shadowMode == kShadowSoft ? cap * sizeof(float) * 3 * fr.shadow_samples : 16));
     w.lit = static_cast<unsigned int*>(take(cap * sizeof(unsigned int)));
+    w.allow = static_cast<unsigned int*>(take(cap * sizeof(unsigned int)));
     w.tail = static_cast<float4*>(take(cap * sizeof(float4)));
     w.top = static_cast<int*>(take(cap * sizeof(int)));
     w.stack = static_cast<float4*>(take(std::max<size_t>(16, cap * sizeof(float4) * w.levels)));
@@ -411,7 +421,7 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
             // queues shrink roughly tenfold per bounce: do not pay for a full grid of idle blocks
             const int g = depth == 0 ? grid : (depth == 1 ? std::max(1, grid / 4) : std::max(1, grid / 8));
             if (wv.shadowMode == kShadowSoft) {
-                k_wf_seed<<<g, kWfThreads, 0, stream>>>(fr, wv, which, depth);
+                k_wf_seed<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
                 ++n;
             } else if (wv.shadowMode == kShadowHard) {
                 k_wf_clear_lit<<<g, kWfThreads, 0, stream>>>(wv, depth);
