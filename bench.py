@@ -185,7 +185,7 @@ def run_own_arm(args):
 
     from minecraftskin_raytracer_b200 import _abi, build
     build.build()
-    from minecraftskin_raytracer_b200 import lib
+    from minecraftskin_raytracer_b200 import bands, lib
     from minecraftskin_raytracer_b200.scene import synth_skin
 
     rank, local_rank, world = dist_env()
@@ -206,9 +206,8 @@ def run_own_arm(args):
 
     ctx = lib.Context(local_rank)
     ctx.set_scene(scene, cfg)
-    tiles_y = (H + ts - 1) // ts
-    my_rows = ctx.band_rows(rank, world)
-    max_rows = ((tiles_y + world - 1) // world) * ts  # padded band height, equal on all ranks
+    max_rows = bands.padded_band_rows(H, ts, world)  # padded band height, equal on all ranks
+    assert ctx.band_rows(rank, world) == bands.band_pixel_rows(H, ts, rank, world)
     band = torch.zeros((max_rows, W, 4), dtype=torch.float32, device=dev)
     band_u8 = torch.zeros((max_rows, W, 4), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -219,22 +218,11 @@ def run_own_arm(args):
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
 
-    def deinterleave():
-        # tile row j of the frame is local tile row j // world of rank j % world
-        for r in range(world):
-            src = gathered[r] if world > 1 else band
-            n_local = (tiles_y - r + world - 1) // world if r < tiles_y else 0
-            for k in range(n_local):
-                y0 = (r + k * world) * ts
-                h = min(ts, H - y0)
-                frame[y0:y0 + h].copy_(src[k * ts:k * ts + h], non_blocking=True)
-
     def step():
         ctx.render_bands(rank, world, band.data_ptr(), band_u8.data_ptr(), stream.cuda_stream)
         if world > 1:
-            dist.gather(band, gathered, dst=0)
-            if rank == 0:
-                deinterleave()
+            # the path's only exchange: gather the bands on rank 0 (NCCL over NVLink), rows back in order
+            bands.gather_frame(band, frame, ts, gathered)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -296,6 +296,17 @@ class Reference(_Common):
         self.lib.mcref_render_tile(C.c_void_p(self._handle(scene)), C.byref(cfg), C.byref(t), _ptr(image, C.c_float))
         return image
 
+    def mt19937(self, seed: int, n: int):
+        u = np.zeros(n, dtype=np.uint32)
+        f = np.zeros(n, dtype=np.float32)
+        self.lib.mcref_mt19937(C.c_uint32(seed), C.c_int32(n), _ptr(u, C.c_uint32), _ptr(f, C.c_float))
+        return u, f
+
+    def seed_cast(self, f: float) -> int:
+        self.lib.mcref_seed_cast.restype = C.c_uint32
+        self.lib.mcref_seed_cast.argtypes = [C.c_float]
+        return int(self.lib.mcref_seed_cast(C.c_float(f)))
+
     def write_png(self, rgba: np.ndarray, path: str) -> bool:
         rgba = np.ascontiguousarray(rgba, dtype=np.float32)
         h, w = rgba.shape[:2]

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <random>
 #include <string>
 #include <thread>
 #include <unistd.h>
@@ -464,6 +465,23 @@ int mcref_write_png(const float* rgba, int w, int h, const char* path) {
     Image img(w, h);
     if (w > 0 && h > 0) std::memcpy(img.pixels.data(), rgba, img.pixels.size() * sizeof(Color));
     return ImageWriter::writePNG(img, path ? path : "") ? 1 : 0;
+}
+
+// The libstdc++ generator and distribution the reference draws from (tile_renderer.cpp:78-79,
+// shading.cpp:43-44): raw engine words and uniform_real_distribution<float>(0,1) values of one seed.
+void mcref_mt19937(uint32_t seed, int n, uint32_t* outU32, float* outCanonical) {
+    std::mt19937 a(seed), b(seed);
+    std::uniform_real_distribution<float> dist(0.0f, 1.0f);
+    for (int i = 0; i < n; ++i) {
+        if (outU32) outU32[i] = static_cast<uint32_t>(a());
+        if (outCanonical) outCanonical[i] = dist(b);
+    }
+}
+
+// static_cast<unsigned int>(float) as the reference's compiler lowers it (raytracer.cpp:110-112)
+uint32_t mcref_seed_cast(float f) {
+    volatile float v = f;
+    return static_cast<unsigned int>(v);
 }
 
 int mcref_hardware_threads(void) { return static_cast<int>(std::thread::hardware_concurrency()); }

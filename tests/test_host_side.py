@@ -1,0 +1,118 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every
+declared symbol, struct layouts agree, the skin -> scene builder equals the reference's
+SkinParser + MeshBuilder, tile generation, defaults, and loud failure without a GPU."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from minecraftskin_raytracer_b200 import _abi
+from minecraftskin_raytracer_b200.scene import BUILTIN_POSE_ORDER, BUILTIN_POSES, FlatScene, pose_array, synth_skin
+from tests.golden_data import golden_scene, vectors
+from tests.golden.make_golden import GOLDEN_RENDERS
+from tests.scenes import make_config
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(mclib):
+    header = (ROOT / "include" / "mcskin_cuda.h").read_text()
+    declared = set(re.findall(r"\b(mcskin_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    raw = mclib.raw()
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} is declared in include/mcskin_cuda.h but not exported"
+    assert declared == set(mclib.EXPORTS), declared ^ set(mclib.EXPORTS)
+    assert raw.mcskin_cuda_abi_version() == _abi.ABI_VERSION
+
+
+def test_struct_layouts_match(mclib):
+    mirror = [C.sizeof(t) for t in (_abi.McFaceTex, _abi.McBox, _abi.McScene, _abi.McConfig, _abi.McTile,
+                                    _abi.McRenderStats, _abi.McRay, _abi.McHit)]
+    assert mclib.abi_sizes() == mirror
+
+
+def test_config_defaults_are_the_reference_defaults(mclib):
+    d = mclib.config_defaults()
+    # raytracer.h:10-38, shading.h:9-14
+    assert (d.width, d.height, d.max_bounces, d.samples_per_pixel, d.tile_size, d.thread_count) == (256, 256, 3, 1, 32, 0)
+    assert (d.soft_shadows, d.shadow_samples, d.ao_enabled, d.ao_samples, d.dof_enabled, d.gradient_bg) == (1, 8, 0, 8, 0, 1)
+    assert np.allclose([d.ao_radius, d.ao_intensity, d.aperture, d.focus_distance, d.gradient_scale], [3.0, 0.5, 0.5, 0.0, 1.0])
+    assert np.allclose(list(d.bg_center), [0.91, 0.89, 0.86, 1.0]) and np.allclose(list(d.bg_edge), [0.56, 0.63, 0.71, 1.0])
+    assert np.allclose([d.kd, d.ks, d.ambient, d.shininess], [0.75, 0.15, 0.20, 16.0])
+    assert bytes(d) == bytes(_abi.default_config())
+
+
+@pytest.mark.parametrize("name,seed,kind,pose,_over", GOLDEN_RENDERS, ids=[g[0] for g in GOLDEN_RENDERS])
+def test_skin_scene_builder_equals_golden_reference_scene(mclib, name, seed, kind, pose, _over):
+    """mcskin_build_skin_scene == SkinParser::parse + MeshBuilder::buildScene (flattened), byte for byte."""
+    built = mclib.build_skin_scene(synth_skin(seed, kind), pose)
+    assert built.same_as(golden_scene(name))
+
+
+def test_skin_scene_builder_equals_live_reference(mclib, reference):
+    for seed, kind in ((0, "64x64"), (2, "legacy"), (3, "slim")):
+        for pose in [None] + BUILTIN_POSE_ORDER:
+            assert mclib.build_skin_scene(synth_skin(seed, kind), pose).same_as(
+                reference.scene_from_atlas(synth_skin(seed, kind), pose)), (seed, kind, pose)
+    # a fully transparent outer layer is dropped (mesh_builder.cpp:176-186); legacy skins keep 7 boxes
+    atlas = synth_skin(5)
+    atlas[:16, 32:, 3] = 0
+    a, b = mclib.build_skin_scene(atlas), reference.scene_from_atlas(atlas)
+    assert a.same_as(b) and len(a.boxes) == 11
+    assert len(mclib.build_skin_scene(synth_skin(2, "legacy")).boxes) == 7
+    poses = reference.builtin_poses()
+    for i, name in enumerate(BUILTIN_POSE_ORDER):          # src/scene/pose.h:25-92
+        assert np.array_equal(poses[i], pose_array(name)), name
+
+
+def test_skin_scene_builder_rejects_bad_sizes(mclib):
+    with pytest.raises(mclib.McSkinError) as e:
+        mclib.build_skin_scene(np.zeros((48, 64, 4), dtype=np.uint8))
+    assert "expected 64x64 or 64x32" in str(e.value)       # skin_parser.cpp:127-131
+
+
+def test_generate_tiles_matches_oracle(mclib, oracle):
+    for args in ((1920, 1080, 32), (100, 70, 32), (7, 5, 3), (64, 64, 64), (0, 5, 5), (5, 5, -1)):
+        assert np.array_equal(mclib.generate_tiles(*args), oracle.generate_tiles(*args)), args
+
+
+def test_band_rows(mclib):
+    cfg = make_config(width=1920, height=1080, tile_size=32)
+    raw = mclib.raw()
+    total = sum(raw.mcskin_cuda_band_rows(C.byref(cfg), C.c_int32(r), C.c_int32(8)) for r in range(8))
+    assert total == 1080
+    assert raw.mcskin_cuda_band_rows(C.byref(cfg), C.c_int32(1), C.c_int32(8)) == 5 * 32 - (34 * 32 - 1080)  # rows 1,9,17,25,33 (33 clipped)
+    assert raw.mcskin_cuda_band_rows(C.byref(cfg), C.c_int32(40), C.c_int32(8)) == 0
+
+
+def test_no_cpu_fallback(mclib):
+    """Without a CUDA device every compute entry point fails loudly with MC_ERR_NO_DEVICE."""
+    if mclib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    scene = mclib.build_skin_scene(synth_skin(0))
+    cfg = make_config(width=32, height=32)
+    for call in (lambda: mclib.render(scene, cfg), lambda: mclib.aov(scene, cfg), lambda: mclib.Context(0),
+                 lambda: mclib.intersect(scene, np.zeros(1, dtype=_abi.RAY_DTYPE))):
+        with pytest.raises(mclib.McSkinError) as e:
+            call()
+        assert e.value.code == _abi.MC_ERR_NO_DEVICE
+
+
+def test_argument_errors_do_not_need_a_device(mclib):
+    raw = mclib.raw()
+    assert raw.mcskin_cuda_render(None, None, 0, None, None, C.cast(None, _abi.McProgressFn), None, None) == _abi.MC_ERR_INVALID
+    assert b"null" in raw.mcskin_cuda_last_error()
+    # a zero-tile frame is an empty success (tile_renderer.cpp:144-146), with or without a GPU
+    f32, _, stats = mclib.render(FlatScene(), make_config(width=0, height=16))
+    assert f32.shape == (16, 0, 4) and stats["n_tiles"] == 0
+
+
+def test_synth_skin_is_deterministic():
+    a, b = synth_skin(3), synth_skin(3)
+    assert np.array_equal(a, b) and a.shape == (64, 64, 4) and synth_skin(3, "legacy").shape == (32, 64, 4)
+    assert not np.array_equal(a, synth_skin(4))
+    holes = a[..., 3] == 0
+    assert 0.1 < holes[:16, 32:].mean() < 0.9 and not holes[:16, :32].any()   # only outer-layer blocks have holes

@@ -1,0 +1,104 @@
+"""Pins the CPU oracle (oracle/mcskin_oracle.c) to the reference:
+  * against committed outputs of the UNMODIFIED reference (tests/golden/reference_vectors.npz) —
+    always, including on the GPU box where /root/reference does not exist;
+  * against the unmodified reference itself (oracle/_ref) when it was built.
+Everything is required to match bit for bit: both are CPU code using the same glibc/libstdc++
+arithmetic, so any difference is a restatement error.
+"""
+import numpy as np
+import pytest
+
+from minecraftskin_raytracer_b200 import _abi
+from tests.golden_data import golden_render_cases, golden_scene, ray_scene, vectors
+from tests.scenes import RENDER_CASES, make_config, random_rays, synth_skin
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _same_struct(a, b, fields):
+    return all(np.array_equal(a[f].view(np.uint32) if a[f].dtype == np.float32 else a[f],
+                              b[f].view(np.uint32) if b[f].dtype == np.float32 else b[f]) for f in fields)
+
+
+@pytest.mark.parametrize("name,cfg", golden_render_cases(), ids=[c[0] for c in golden_render_cases()])
+def test_oracle_renders_equal_golden(oracle, name, cfg):
+    v = vectors()
+    scene = golden_scene(name)
+    img, cnt = oracle.render(scene, cfg, counters=True)
+    assert np.array_equal(_bits(img), _bits(v[f"{name}/image"]))
+    assert cnt["n_intersect_scene"] == int(v[f"{name}/calls"])       # same number of intersectScene calls
+    assert np.array_equal(oracle.aov(scene, cfg), v[f"{name}/tri_id"])
+
+
+def test_oracle_single_ray_vectors_equal_golden(oracle, mclib):
+    v = vectors()
+    scene = ray_scene(mclib.build_skin_scene)
+    rays, want = v["rays/rays"], v["rays/hits"]
+    got = oracle.intersect(scene, rays)
+    assert np.array_equal(got["hit"], want["hit"]) and np.array_equal(got["box"], want["box"])
+    assert np.array_equal(got["face"], want["face"]) and np.array_equal(got["is_outer_layer"], want["is_outer_layer"])
+    for f in ("t", "point", "normal", "tex_color"):
+        assert np.array_equal(_bits(got[f]), _bits(want[f])), f
+    keep = want["hit"] == 1
+    cfg = make_config(max_bounces=3)
+    assert np.array_equal(_bits(oracle.shade(scene, cfg, want[keep], -rays["dir"][keep], None)), _bits(v["rays/shade_hard"]))
+    assert np.array_equal(_bits(oracle.shade(scene, cfg, want[keep], -rays["dir"][keep], v["rays/shade_sf"])), _bits(v["rays/shade_soft"]))
+    assert np.array_equal(_bits(oracle.trace(scene, cfg, rays[:1500], 0, True)), _bits(v["rays/trace_cfg"]))
+    assert np.array_equal(_bits(oracle.trace(scene, cfg, rays[:1500], 0, False)), _bits(v["rays/trace_nocfg"]))
+    seeds = v["rays/seeds"]
+    assert np.array_equal(_bits(oracle.soft_shadow(scene, want["point"][keep], want["normal"][keep], seeds, 8)), _bits(v["rays/soft8"]))
+    assert np.array_equal(_bits(oracle.ambient_occlusion(scene, want["point"][keep], want["normal"][keep], seeds, 16, 3.0)), _bits(v["rays/ao16"]))
+    cam = oracle.generate_rays(scene, 16.0 / 9.0, v["rays/uv"])
+    assert np.array_equal(_bits(cam["dir"]), _bits(v["rays/camera"]["dir"]))
+    assert np.array_equal(_bits(oracle.background(scene, cfg, v["rays/uv"])), _bits(v["rays/background"]))
+
+
+def test_oracle_rng_equals_libstdcxx(oracle):
+    """std::mt19937 and uniform_real_distribution<float>(0,1) of libstdc++ 13."""
+    v = vectors()
+    for seed in (0, 1, 5489, 1920 * 32 + 64, 0xFFFFFFFF):
+        u, f = oracle.mt19937(seed, 2000)
+        assert np.array_equal(u, v[f"rng/{seed}/u32"])
+        assert np.array_equal(_bits(f), _bits(v[f"rng/{seed}/canonical"]))
+    # the 10000th output of mt19937() seeded with 5489 is 4123659995 (ISO C++ [rand.predef])
+    assert oracle.mt19937(5489, 10000)[0][-1] == 4123659995
+    for x, want in zip(v["rng/seed_cast_in"], v["rng/seed_cast_out"]):
+        assert oracle.seed_cast(float(x)) == int(want), x
+
+
+@pytest.mark.parametrize("case", RENDER_CASES, ids=[c[0] for c in RENDER_CASES])
+def test_oracle_equals_live_reference(oracle, reference, case):
+    name, seed, kind, pose, over = case
+    scene = reference.scene_from_atlas(synth_skin(seed, kind), pose)
+    cfg = make_config(**over)
+    a, calls = reference.render(scene, cfg, counters=True)
+    b, cnt = oracle.render(scene, cfg, counters=True)
+    assert np.array_equal(_bits(a), _bits(b))
+    assert calls == cnt["n_intersect_scene"]
+    assert np.array_equal(reference.aov(scene, cfg), oracle.aov(scene, cfg))
+
+
+def test_oracle_equals_live_reference_single_rays(oracle, reference):
+    scene = reference.scene_from_atlas(synth_skin(21, "64x64"), "dab")
+    rays = random_rays(np.random.default_rng(3), 6000)
+    a, b = reference.intersect(scene, rays), oracle.intersect(scene, rays)
+    assert _same_struct(a, b, ("hit", "t", "point", "normal", "tex_color", "is_outer_layer", "box", "face"))
+    cfg = make_config(max_bounces=4, ao_enabled=1)
+    assert np.array_equal(_bits(reference.trace(scene, cfg, rays[:800])), _bits(oracle.trace(scene, cfg, rays[:800])))
+    assert reference.mt19937(77, 500)[0].tolist() == oracle.mt19937(77, 500)[0].tolist()
+
+
+def test_render_tile_equals_render(oracle, mclib):
+    """renderTile over generateTiles == render (tile_renderer.cpp:71-189)."""
+    scene = mclib.build_skin_scene(synth_skin(4), "walking")
+    cfg = make_config(width=70, height=45, samples_per_pixel=2, tile_size=16)
+    full = oracle.render(scene, cfg)
+    img = np.zeros_like(full)
+    img[..., 3] = 1
+    for t in oracle.generate_tiles(70, 45, 16):
+        img = oracle.render_tile(scene, cfg, tuple(t), img)
+    assert np.array_equal(_bits(img), _bits(full))
+    for threads in (1, 3):
+        assert np.array_equal(_bits(oracle.render(scene, cfg, threads=threads)), _bits(full))  # test_tile_renderer.cpp:122-145

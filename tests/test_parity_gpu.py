@@ -232,3 +232,80 @@ def test_empty_scene_and_degenerate_sizes(gpu, oracle):
         cfg = make_config(width=w, height=h, tile_size=ts)
         f32, _, stats = gpu.render(empty, cfg)   # tile_renderer.cpp:144-146: empty image, no error
         assert f32.size == max(w, 0) * max(h, 0) * 4
+
+
+# ---------------------------------------------------------------- against the committed reference outputs
+def test_cuda_vs_golden_reference_renders(gpu, oracle):
+    """CUDA frames vs frames rendered by the UNMODIFIED reference (tests/golden/reference_vectors.npz)."""
+    from tests.golden_data import golden_render_cases, golden_scene, vectors
+    v = vectors()
+    for name, cfg in golden_render_cases():
+        scene = golden_scene(name)
+        want = v[f"{name}/image"]
+        got, _, _ = gpu.render(scene, cfg)
+        rep = pixel_report(got, want, oracle.quantize)
+        assert rep["within1"] >= 0.999, (name, rep)
+        assert np.array_equal(gpu.aov(scene, cfg), v[f"{name}/tri_id"]), name
+
+
+def test_cuda_vs_golden_reference_rays(gpu):
+    from tests.golden_data import ray_scene, vectors
+    v = vectors()
+    scene = ray_scene(gpu.build_skin_scene)
+    rays, want = v["rays/rays"], v["rays/hits"]
+    got = gpu.intersect(scene, rays)
+    for f in ("hit", "box", "face", "is_outer_layer"):
+        assert np.array_equal(got[f], want[f]), f
+    for f in ("t", "point", "normal", "tex_color"):
+        assert np.array_equal(_bits(got[f]), _bits(want[f])), f
+    keep = want["hit"] == 1
+    cfg = make_config(max_bounces=3)
+    assert np.abs(gpu.shade(scene, cfg, want[keep], -rays["dir"][keep], v["rays/shade_sf"]) - v["rays/shade_soft"]).max() <= 2e-6
+    assert np.abs(gpu.shade(scene, cfg, want[keep], -rays["dir"][keep], None) - v["rays/shade_hard"]).max() <= 2e-6
+    for key, use_cfg in (("rays/trace_cfg", True), ("rays/trace_nocfg", False)):
+        close = np.abs(gpu.trace(scene, cfg, rays[:1500], 0, use_cfg) - v[key]).max(axis=1) <= 1e-5
+        assert close.mean() >= 0.998, key
+    assert (gpu.soft_shadow(scene, want["point"][keep], want["normal"][keep], v["rays/seeds"], 8) != v["rays/soft8"]).mean() <= 2e-3
+    cam = gpu.generate_rays(scene, 16.0 / 9.0, v["rays/uv"])
+    assert np.array_equal(_bits(cam["dir"]), _bits(v["rays/camera"]["dir"]))
+    assert np.array_equal(_bits(gpu.background(scene, cfg, v["rays/uv"])), _bits(v["rays/background"]))
+
+
+# ---------------------------------------------------------------- full-size properties (no oracle run)
+def test_headline_frame_properties(gpu, oracle):
+    """BASELINE headline size (1080p / 16 spp / 4 bounces): properties that need no CPU frame."""
+    import json
+    from pathlib import Path
+    counts = json.loads((Path(__file__).parent / "golden" / "work_counts.json").read_text())["headline_1080p_16spp_4b"]
+    scene = _scene(gpu, 0)
+    cfg = make_config(**counts["config"])
+    f32, u8, stats = gpu.render(scene, cfg, want_u8=True)
+    assert np.array_equal(u8, oracle.quantize(f32))
+    # background pixels = the empty-scene frame, bit for bit; everything else stays inside the figure's box
+    empty, _, _ = gpu.render(type(scene)(), cfg)
+    same = (f32.view(np.uint32) == empty.view(np.uint32)).all(axis=-1)
+    ys, xs = np.nonzero(~same)
+    assert 0.05 < (~same).mean() < 0.10
+    assert xs.min() > 700 and xs.max() < 1220 and ys.min() > 150 and ys.max() < 900
+    # pixels the classification pass found active == pixels where any of the 16 samples hits;
+    # the oracle counted the samples, so active pixels are bounded by it from both sides
+    hit_samples = counts["counters"]["n_primary_rays"] - counts["counters"]["n_background_primary"]
+    assert hit_samples / 16 <= stats["n_active_pixels"] <= hit_samples
+    assert np.all(np.isfinite(f32)) and f32.min() >= 0.0 and f32.max() <= 1.0
+    # tile-row partitions reassemble to the same frame (what the multi-GPU path relies on)
+    import torch
+    from minecraftskin_raytracer_b200 import bands
+    ctx = gpu.Context(0)
+    try:
+        ctx.set_scene(scene, cfg)
+        world = 3
+        parts = []
+        for r in range(world):
+            band = torch.zeros((bands.padded_band_rows(cfg.height, cfg.tile_size, world), cfg.width, 4), device="cuda:0")
+            ctx.render_bands(r, world, band.data_ptr(), 0, 0)
+            ctx.sync()
+            parts.append(band)
+        frame = bands.deinterleave(parts, torch.zeros((cfg.height, cfg.width, 4), device="cuda:0"), cfg.tile_size)
+        assert np.array_equal(frame.cpu().numpy().view(np.uint32), f32.view(np.uint32))
+    finally:
+        ctx.close()
