@@ -286,7 +286,7 @@ def test_headline_frame_properties(gpu, oracle):
     same = (f32.view(np.uint32) == empty.view(np.uint32)).all(axis=-1)
     ys, xs = np.nonzero(~same)
     assert 0.05 < (~same).mean() < 0.10
-    assert xs.min() > 700 and xs.max() < 1220 and ys.min() > 150 and ys.max() < 900
+    assert xs.min() > 700 and xs.max() < 1220 and ys.min() > 100 and ys.max() < 980
     # pixels the classification pass found active == pixels where any of the 16 samples hits;
     # the oracle counted the samples, so active pixels are bounded by it from both sides
     hit_samples = counts["counters"]["n_primary_rays"] - counts["counters"]["n_background_primary"]
