@@ -78,7 +78,7 @@ struct McContext {
     int device = 0;
     int smCount = 148;
     cudaStream_t stream = nullptr;  // used when the caller passes stream 0 to the host-facing calls
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evCopy = nullptr;
     std::vector<cudaEvent_t> passEvents;  // 3 per chunk: before primary, between, after shade
     bool hasScene = false;
     PreparedFrame prep;
@@ -289,12 +289,34 @@ int shared_context(int device, McContext** out) {
     return MC_OK;
 }
 
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// Device -> caller's host buffer.  Page-locked destinations (cudaHostAlloc / cudaHostRegister,
+// torch pin_memory) are written by DMA directly; pageable ones go through the context's pinned
+// staging buffer in two halves so the second DMA overlaps the first memcpy.
 int copy_out(McContext* ctx, void* hostDst, const void* devSrc, size_t bytes) {
-    // staged through pinned memory: a pageable destination would make the runtime do the same, slower
+    if (is_pinned_host(hostDst)) {
+        CU_TRY(cudaMemcpyAsync(hostDst, devSrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return MC_OK;  // the caller synchronises the stream
+    }
     CU_TRY(ctx->pinned.reserve(bytes));
-    CU_TRY(cudaMemcpyAsync(ctx->pinned.p, devSrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t half = (bytes / 2) & ~static_cast<size_t>(4095);
+    unsigned char* stage = static_cast<unsigned char*>(ctx->pinned.p);
+    const unsigned char* src = static_cast<const unsigned char*>(devSrc);
+    CU_TRY(cudaMemcpyAsync(stage, src, half, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaEventRecord(ctx->evCopy, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(stage + half, src + half, bytes - half, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaEventSynchronize(ctx->evCopy));
+    std::memcpy(hostDst, stage, half);
     CU_TRY(cudaStreamSynchronize(ctx->stream));
-    std::memcpy(hostDst, ctx->pinned.p, bytes);
+    std::memcpy(static_cast<unsigned char*>(hostDst) + half, stage + half, bytes - half);
     return MC_OK;
 }
 
@@ -366,6 +388,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&ctx->ev0));
     CU_TRY(cudaEventCreate(&ctx->ev1));
+    CU_TRY(cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming));
     if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
     if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) ctx->waveQueueLevels = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_SHADE_MODE")) ctx->shadeMode = std::min(2, std::max(0, std::atoi(v)));
@@ -383,6 +406,7 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     ctx->pinned.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
     for (cudaEvent_t e : ctx->passEvents) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -126,15 +126,29 @@ def build_skin_scene(atlas: np.ndarray, pose=None) -> FlatScene:
 
 # ---------------------------------------------------------------- whole-frame calls
 def render(scene: FlatScene, cfg: McConfig, device: int = 0, want_f32: bool = True, want_u8: bool = False,
-           progress=None, multi_devices: int = 0):
-    """mcskin_cuda_render: host scene in, host image(s) out.  Returns (f32|None, u8|None, stats dict)."""
+           progress=None, multi_devices: int = 0, out_f32: np.ndarray | None = None, out_u8: np.ndarray | None = None):
+    """mcskin_cuda_render: host scene in, host image(s) out.  Returns (f32|None, u8|None, stats dict).
+
+    out_f32 / out_u8: caller-owned [H, W, 4] arrays to render into (reused across frames; page-locked
+    arrays, e.g. numpy views of torch pin_memory tensors, are filled by DMA without a staging copy)."""
     h, w = max(cfg.height, 0), max(cfg.width, 0)
-    f32 = np.zeros((h, w, 4), dtype=np.float32) if want_f32 else None
-    if f32 is not None:
-        f32[..., 3] = 1.0  # Image(w,h) default-constructs pixels to (0,0,0,1) (image.h:15, color.h:8)
-    u8 = np.zeros((h, w, 4), dtype=np.uint8) if want_u8 else None
-    if u8 is not None:
-        u8[..., 3] = 255
+    n_tiles = len(generate_tiles(cfg.width, cfg.height, cfg.tile_size)) if (w and h) else 0
+
+    def _buffer(given, want, dtype, one):
+        if given is not None:
+            if given.shape != (h, w, 4) or given.dtype != dtype or not given.flags.c_contiguous:
+                raise ValueError(f"output buffer must be C-contiguous {dtype} [{h}, {w}, 4]")
+            return given
+        if not want:
+            return None
+        buf = np.empty((h, w, 4), dtype=dtype)
+        if n_tiles == 0 and buf.size:  # nothing is rendered: Image(w,h) pixels stay (0,0,0,1) (image.h:15, color.h:8)
+            buf[...] = 0
+            buf[..., 3] = one
+        return buf
+
+    f32 = _buffer(out_f32, want_f32, np.float32, 1.0)
+    u8 = _buffer(out_u8, want_u8, np.uint8, 255)
     stats = McRenderStats()
     cs = scene.as_c()
     if multi_devices and multi_devices > 0:
