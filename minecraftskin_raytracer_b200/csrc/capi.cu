@@ -93,7 +93,7 @@ struct McContext {
     int forceAllActive = 0;
     long long recordBudgetBytes = 1ll << 31;
     int shadeBlocksPerSm = 8;
-    int waveQueueLevels = 2;                 // bounce depths handled by queues; deeper ones in-thread
+    int waveQueueLevels = 3;                 // bounce depths handled by queues; deeper ones in-thread
     int shadeMode = 0;                       // 0 wavefront, 1 megakernel (block groups), 2 megakernel (warp groups)
     long long waveBudgetBytes = 12ll << 30;   // queue storage; pixels beyond it fall back to the megakernel
     // stats of the last render

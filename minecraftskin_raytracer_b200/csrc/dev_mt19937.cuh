@@ -24,7 +24,13 @@ constexpr int kMtN = 624;
 constexpr int kMtM = 397;
 
 __device__ __forceinline__ uint32_t mt_lcg(uint32_t prev, uint32_t i) {
+#ifdef MCSKIN_LCG_UMULHI
+    // prev >> 30 as the high word of prev * 4: IMAD.HI runs on the FMA pipe, which the
+    // recurrence (SHF + LOP3 + add on the ALU pipe, one IMAD on the FMA pipe) leaves idle
+    return 1812433253u * (prev ^ __umulhi(prev, 4u)) + i;
+#else
     return 1812433253u * (prev ^ (prev >> 30)) + i;
+#endif
 }
 __device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t next, uint32_t far) {
     const uint32_t y = (cur & 0x80000000u) | (next & 0x7fffffffu);
@@ -53,13 +59,20 @@ __device__ __forceinline__ uint32_t mt_seed_word397(uint32_t word1) {
     return x;
 }
 
-// The same 396 steps fully unrolled (SHF + LOP3 + IMAD with the index as an immediate, no
-// loop counter): for small kernels that do little else (k_wf_seed), where 19 KB of
-// straight-line code sits comfortably in the instruction cache.
-__device__ __forceinline__ uint32_t mt_seed_word397_unrolled(uint32_t word1) {
+// Pipe-balanced form for the seeding kernel.  The plain loop compiles to SHF + LOP3 + IADD on
+// the ALU pipe and one IMAD on the FMA pipe per step, and ncu shows the ALU pipe saturated
+// (83 %) with the FMA pipe at 27 %.  Here the index lives in a register that is advanced with a
+// multiply-add by a run-time 1 (`one`, opaque to the compiler), so every step is two ALU and two
+// FMA-pipe instructions, the index update off the dependent chain.
+__device__ __forceinline__ uint32_t mt_seed_word397_balanced(uint32_t word1, uint32_t one) {
     uint32_t x = word1;
-#pragma unroll
-    for (uint32_t i = 2u; i <= static_cast<uint32_t>(kMtM); ++i) x = mt_lcg(x, i);
+    uint32_t i = 2u * one;
+#pragma unroll 12
+    for (int k = 2; k <= kMtM; ++k) {
+        const uint32_t y = x ^ (x >> 30);
+        asm("mad.lo.u32 %0, %1, 1812433253, %2;" : "=r"(x) : "r"(y), "r"(i));
+        asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(i) : "r"(one));
+    }
     return x;
 }
 
@@ -67,10 +80,11 @@ struct FreshStream {
     uint32_t cur, nxt, far;
     uint32_t j;
 
-    __device__ __forceinline__ void seed_unrolled(uint32_t s) {
+    // `one` must be 1 at run time (see mt_seed_word397_balanced)
+    __device__ __forceinline__ void seed_balanced(uint32_t s, uint32_t one) {
         cur = s;
         nxt = mt_lcg(s, 1u);
-        far = mt_seed_word397_unrolled(nxt);
+        far = mt_seed_word397_balanced(nxt, one);
         j = 0u;
     }
 

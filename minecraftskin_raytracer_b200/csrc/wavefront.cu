@@ -122,12 +122,13 @@ k_wf_seed(const DevFrame fr, const FramePointers fp, const WaveView wv, const in
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
     const HitQueueView q = wv.q[which];
     const int N = fr.shadow_samples;
+    const uint32_t one = fr.spp > 0 ? 1u : 0u;  // a 1 the compiler cannot see through
     for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) {
         const float4 g = q.geo[i];
         const Hit h = unpack_hit(g, make_float4(0.f, 0.f, 0.f, 0.f));
         const V3 P = h.p;
         FreshStream rng;
-        rng.seed(shadow_seed(P, depth));
+        rng.seed_balanced(shadow_seed(P, depth), one);
         soft_shadow_positions(fr, P, N, rng, wv.lightPos + static_cast<size_t>(i) * 3 * N);
         wv.lit[i] = 0u;
         // the boxes the bundle of this hit's shadow rays can reach (computeSoftShadow hands
@@ -180,12 +181,14 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
 }
 
 // ---------------------------------------------------------------- shade + bounce
-// Levels up to wv.queueLevels-1 are queue-driven (their shadow rays ran in k_wf_shadow);
-// a bounce that lands on a deeper level is followed to its end inside the thread, with the
-// shadow rays evaluated in place: by then only a few per cent of the paths are left, too few
-// to be worth three more launches per level.
+// tail == 0: a queue level whose shadow rays ran in k_wf_shadow; bounce hits go to the next queue.
+// tail == 1: the last queue (depth == wv.queueLevels).  By then only ~2 % of the paths are left,
+//            too few to be worth three launches per level: each thread takes one queued hit and
+//            follows its chain to the end, evaluating shadow rays in place.  The queue is compact,
+//            so warps start full and only thin out at the deepest, rarest levels.
 __global__ void __launch_bounds__(kWfThreads)
-k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
+k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth,
+           const int tail) {
     __shared__ __align__(8) uint64_t stageBar;
     unsigned int n = wv.qCount[depth];
     if (n > wv.pathCapacity) n = wv.pathCapacity;
@@ -218,7 +221,7 @@ k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const i
                 const float4 tex = hit_texel(sc, h);
                 const V3 viewDir = normalize3(rayO - P);
                 float vis;
-                if (d == depth && wv.shadowMode != kShadowInThread) {
+                if (!tail && wv.shadowMode != kShadowInThread) {
                     vis = static_cast<float>(wv.lit[i]) / static_cast<float>(wv.shadowRays);
                     if (wv.shadowMode == kShadowHard) vis = wv.lit[i] ? 1.0f : 0.0f;
                 } else if (cfg && fr.soft_on) {
@@ -249,7 +252,7 @@ k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const i
                         wv.top[path] = d + 1;
                         break;
                     }
-                    if (d + 1 < wv.queueLevels) {  // hand the next level to the queues
+                    if (!tail) {  // hand the next level to the queues
                         bounceHit = true;
                         break;
                     }
@@ -381,7 +384,7 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
     w.shadowMode = shadow_mode_of(fr);
     w.shadowRays = w.shadowMode == kShadowSoft ? fr.shadow_samples : (w.shadowMode == kShadowHard ? 1 : 0);
     w.gridBlocks = gridBlocks;
-    w.queueLevels = 2;
+    w.queueLevels = 3;
     unsigned char* p = static_cast<unsigned char*>(base);
     size_t off = 0;
     auto take = [&](size_t n) {
@@ -415,8 +418,10 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
     k_wf_hit0<<<grid, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv);
     ++n;
     if (fr.max_bounces >= 0) {
-        const int lastDepth = std::min(wv.levels, wv.queueLevels - 1);  // deeper levels run inside k_wf_shade
-        for (int depth = 0; depth <= lastDepth; ++depth) {
+        // depths 0 .. queueLevels-1: seed / shadow / shade over the queue of that depth;
+        // depth queueLevels (if bounces go that deep): one tail launch that finishes every chain
+        const int queued = std::min(wv.levels + 1, std::max(1, wv.queueLevels));
+        for (int depth = 0; depth < queued; ++depth) {
             const int which = depth & 1;
             // queues shrink roughly tenfold per bounce: do not pay for a full grid of idle blocks
             const int g = depth == 0 ? grid : (depth == 1 ? std::max(1, grid / 4) : std::max(1, grid / 8));
@@ -431,7 +436,11 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
                 k_wf_shadow<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
                 ++n;
             }
-            k_wf_shade<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+            k_wf_shade<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0);
+            ++n;
+        }
+        if (queued <= wv.levels) {
+            k_wf_shade<<<std::max(1, grid / 8), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, queued & 1, queued, 1);
             ++n;
         }
     }
