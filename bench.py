@@ -211,7 +211,8 @@ def run_own_arm(args):
     band = torch.zeros((max_rows, W, 4), dtype=torch.float32, device=dev)
     band_u8 = torch.zeros((max_rows, W, 4), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    gathered = [torch.empty_like(band) for _ in range(world)] if (world > 1 and rank == 0) else None
+    gathered = torch.empty((world * max_rows, W, 4), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    row_index = bands.frame_row_index(H, ts, world, max_rows, dev) if rank == 0 else None
     frame = torch.zeros((H, W, 4), dtype=torch.float32, device=dev) if rank == 0 else None
     # a dedicated (non-default) stream: handle 0 would mean "the context's own stream" to the C ABI,
     # and torch.cuda.Event only sees the stream it is recorded on
@@ -222,7 +223,7 @@ def run_own_arm(args):
         ctx.render_bands(rank, world, band.data_ptr(), band_u8.data_ptr(), stream.cuda_stream)
         if world > 1:
             # the path's only exchange: gather the bands on rank 0 (NCCL over NVLink), rows back in order
-            bands.gather_frame(band, frame, ts, gathered)
+            bands.gather_frame(band, frame, ts, gathered, row_index)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

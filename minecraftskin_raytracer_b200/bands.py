@@ -31,29 +31,49 @@ def padded_band_rows(height: int, tile_size: int, world: int) -> int:
     return ((tiles_y(height, tile_size) + world - 1) // world) * tile_size
 
 
-def deinterleave(bands: list[torch.Tensor], frame: torch.Tensor, tile_size: int) -> torch.Tensor:
-    """bands[r]: [padded_rows, W, C] of rank r  ->  frame [H, W, C] with rows in image order."""
-    height = frame.shape[0]
-    world = len(bands)
-    for r, band in enumerate(bands):
+def frame_row_index(height: int, tile_size: int, world: int, padded_rows: int, device=None) -> torch.Tensor:
+    """For every frame row y: its row in the concatenation of all ranks' padded bands."""
+    idx = torch.empty(height, dtype=torch.long)
+    for r in range(world):
         for k, tile_row in enumerate(local_tile_rows(height, tile_size, r, world)):
             y0 = tile_row * tile_size
             h = min(tile_size, height - y0)
-            frame[y0:y0 + h].copy_(band[k * tile_size:k * tile_size + h], non_blocking=True)
+            idx[y0:y0 + h] = torch.arange(r * padded_rows + k * tile_size, r * padded_rows + k * tile_size + h)
+    return idx.to(device) if device is not None else idx
+
+
+def deinterleave(bands: list[torch.Tensor] | torch.Tensor, frame: torch.Tensor, tile_size: int,
+                 row_index: torch.Tensor | None = None) -> torch.Tensor:
+    """bands: one [padded_rows, W, C] tensor per rank (or their concatenation [world*padded_rows, W, C])
+    ->  frame [H, W, C] with rows in image order, as ONE gather over rows."""
+    if isinstance(bands, (list, tuple)):
+        world, padded = len(bands), bands[0].shape[0]
+        stacked = bands[0] if world == 1 else torch.cat(list(bands), dim=0)
+    else:
+        stacked = bands
+        padded = padded_band_rows(frame.shape[0], tile_size, 1) if row_index is None else None
+        world = stacked.shape[0] // padded if padded else None
+    if row_index is None:
+        row_index = frame_row_index(frame.shape[0], tile_size, world, padded, stacked.device)
+    torch.index_select(stacked, 0, row_index, out=frame)
     return frame
 
 
 def gather_frame(band: torch.Tensor, frame: torch.Tensor | None, tile_size: int,
-                 gathered: list[torch.Tensor] | None = None) -> torch.Tensor | None:
+                 gathered: torch.Tensor | None = None, row_index: torch.Tensor | None = None) -> torch.Tensor | None:
     """Collective: every rank passes its padded band; rank 0 returns the assembled frame.
-    The only exchange of the path: one gather, W*H*C*4/world bytes per non-root rank."""
+    The only exchange of the path: one gather, W*H*C*4/world bytes per non-root rank.
+    gathered (rank 0): optional preallocated [world*padded_rows, W, C] receive buffer."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     if world == 1:
-        return deinterleave([band], frame, tile_size)
-    if rank == 0 and gathered is None:
-        gathered = [torch.empty_like(band) for _ in range(world)]
-    dist.gather(band, gathered if rank == 0 else None, dst=0)
-    if rank != 0:
-        return None
-    return deinterleave(gathered, frame, tile_size)
+        return deinterleave([band], frame, tile_size, row_index)
+    if rank == 0:
+        if gathered is None:
+            gathered = torch.empty((world * band.shape[0],) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+        dist.gather(band, list(gathered.chunk(world, dim=0)), dst=0)
+        return deinterleave(gathered, frame, tile_size,
+                            row_index if row_index is not None else
+                            frame_row_index(frame.shape[0], tile_size, world, band.shape[0], band.device))
+    dist.gather(band, None, dst=0)
+    return None

@@ -93,6 +93,7 @@ struct McContext {
     int forceAllActive = 0;
     long long recordBudgetBytes = 1ll << 31;
     int shadeBlocksPerSm = 8;
+    int primaryBlocksPerSm = 9;              // split tiles over blocks until a launch has this many per SM
     int waveQueueLevels = 3;                 // bounce depths handled by queues; deeper ones in-thread
     int shadeMode = 0;                       // 0 wavefront, 1 megakernel (block groups), 2 megakernel (warp groups)
     long long waveBudgetBytes = 12ll << 30;   // queue storage; pixels beyond it fall back to the megakernel
@@ -219,7 +220,8 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
             CU_TRY(cudaMemcpyAsync(list.count, &list.capacity, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
         }
         CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
-        launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p), stream);
+        launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
+                       ctx->smCount * ctx->primaryBlocksPerSm, stream);
         CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 1], stream));
         unsigned int* groupCounter = static_cast<unsigned int*>(ctx->countLog.p) + nChunks + c;
         const int shadeGrid = ctx->smCount * ctx->shadeBlocksPerSm;
@@ -390,6 +392,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     CU_TRY(cudaEventCreate(&ctx->ev1));
     CU_TRY(cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming));
     if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
+    if (const char* v = std::getenv("MCSKIN_PRIMARY_BLOCKS")) ctx->primaryBlocksPerSm = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) ctx->waveQueueLevels = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_SHADE_MODE")) ctx->shadeMode = std::min(2, std::max(0, std::atoi(v)));
     *out = ctx.release();
@@ -418,6 +421,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     if (k == "force_all_active") ctx->forceAllActive = value != 0;
     else if (k == "record_budget_bytes") ctx->recordBudgetBytes = std::max<int64_t>(1, value);
     else if (k == "shade_blocks_per_sm") ctx->shadeBlocksPerSm = static_cast<int>(std::max<int64_t>(1, value));
+    else if (k == "primary_blocks_per_sm") ctx->primaryBlocksPerSm = static_cast<int>(std::max<int64_t>(0, value));
     else if (k == "shade_mode") ctx->shadeMode = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
     else if (k == "wave_queue_levels") ctx->waveQueueLevels = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "wave_budget_bytes") ctx->waveBudgetBytes = std::max<int64_t>(1 << 20, value);

@@ -440,6 +440,7 @@ struct PixStreamSmem {
 
 // One 624-word block of the stream: state[which] -> state[which^1], canonical floats into
 // the ring.  Three dependent phases of 227 / 227 / 170 words, one word per thread.
+template <bool STORE>
 __device__ __forceinline__ void pix_stream_block(PixStreamSmem* sm, int which, unsigned int produced) {
     static_assert(kBlockThreads >= kMtN - kMtM, "one thread per word of a phase");
     const uint32_t* a = sm->state[which];
@@ -449,14 +450,14 @@ __device__ __forceinline__ void pix_stream_block(PixStreamSmem* sm, int which, u
     if (i < kD) {
         const uint32_t v = mt_mix(a[i], a[i + 1], a[i + kMtM]);
         b[i] = v;
-        sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
+        if (STORE) sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
     if (i < kD) {
         const int j = kD + i;
         const uint32_t v = mt_mix(a[j], a[j + 1], b[i]);
         b[j] = v;
-        sm->ring[pix_ring_slot(produced + j)] = mt_canonical(mt_temper(v));
+        if (STORE) sm->ring[pix_ring_slot(produced + j)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
     if (i < kMtN - 2 * kD) {
@@ -464,7 +465,7 @@ __device__ __forceinline__ void pix_stream_block(PixStreamSmem* sm, int which, u
         const uint32_t nextWord = (j + 1 == kMtN) ? b[0] : a[j + 1];
         const uint32_t v = mt_mix(a[j], nextWord, b[j - kD]);
         b[j] = v;
-        sm->ring[pix_ring_slot(produced + j)] = mt_canonical(mt_temper(v));
+        if (STORE) sm->ring[pix_ring_slot(produced + j)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
 }
@@ -490,16 +491,21 @@ extern __shared__ __align__(16) unsigned char g_pixSmem[];  // [PixStreamSmem][s
 
 __global__ void __launch_bounds__(kBlockThreads)
 k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list,
-              const uint32_t* __restrict__ tileStates) {
+              const uint32_t* __restrict__ tileStates, const int parts) {
     __shared__ __align__(8) uint64_t stageBar;
     PixStreamSmem* mt = reinterpret_cast<PixStreamSmem*>(g_pixSmem);
     unsigned char* sceneSmem = g_pixSmem + ((sizeof(PixStreamSmem) + 15) & ~size_t(15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileGeom tg = tile_geom(fr, band, blockIdx.x);
+    // With few tiles per launch (small frames, one GPU's share of a frame) a tile is split over
+    // `parts` blocks, each taking every parts-th round of 256 pixels; a block reaches its rounds by
+    // running the tile's generator forward without storing the words it does not need.
+    const int tileIndex = blockIdx.x / parts, part = blockIdx.x - tileIndex * parts;
+    const TileGeom tg = tile_geom(fr, band, tileIndex);
     const int spp = fr.spp, dps = fr.draws_per_sample;
     const int nPix = tg.w * tg.h;
     const unsigned int wordsPerPixel = static_cast<unsigned int>(spp * dps);
+    if (part * kBlockThreads >= nPix) return;  // this part has no round in a clipped edge tile
 
     const bool tileCanHit = !fr.rect_valid || !(tg.x > fr.rect_x1 || tg.x + tg.w - 1 < fr.rect_x0 ||
                                                 tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
@@ -507,7 +513,7 @@ k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, co
     const SceneView sc = scene_view(sceneSmem, fp.texels, fr);
 
     if (dps > 0) {  // this tile's freshly seeded engine (k_tile_seed)
-        const uint32_t* st = tileStates + static_cast<size_t>(blockIdx.x) * kMtN;
+        const uint32_t* st = tileStates + static_cast<size_t>(tileIndex) * kMtN;
         for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = st[i];
         __syncthreads();
     }
@@ -516,11 +522,17 @@ k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, co
     const bool wPow2 = (tg.w & (tg.w - 1)) == 0;
     const int lgW = 31 - __clz(tg.w);
 
-    for (int q0 = 0; q0 < nPix; q0 += kBlockThreads) {
+    for (int q0 = part * kBlockThreads; q0 < nPix; q0 += parts * kBlockThreads) {
         if (dps > 0) {
+            const unsigned int first = static_cast<unsigned int>(q0) * wordsPerPixel;
             const unsigned int need = static_cast<unsigned int>(min(nPix, q0 + kBlockThreads)) * wordsPerPixel;
+            while (produced + kMtN <= first) {  // words of rounds other blocks take: state only
+                pix_stream_block<false>(mt, which, produced);
+                which ^= 1;
+                produced += kMtN;
+            }
             while (produced < need) {  // block-uniform
-                pix_stream_block(mt, which, produced);
+                pix_stream_block<true>(mt, which, produced);
                 which ^= 1;
                 produced += kMtN;
             }
@@ -579,7 +591,7 @@ k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, co
                 }
             }
         }
-        if (dps > 0 && q0 + kBlockThreads < nPix) __syncthreads();  // the ring is rewritten by the next round
+        if (dps > 0 && q0 + parts * kBlockThreads < nPix) __syncthreads();  // the ring is rewritten by the next round
     }
 }
 
@@ -769,7 +781,7 @@ static int log2_if_warp_spp(int spp) {
 }
 
 void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                    int classify, uint32_t* tileStates, cudaStream_t stream) {
+                    int classify, uint32_t* tileStates, int primaryTargetBlocks, cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     if (nTiles <= 0) return;
     // the warp / pixel variants index a tile's stream with 32-bit integers
@@ -785,7 +797,11 @@ void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView&
             attrSet = true;
         }
         if (fr.draws_per_sample > 0) k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates);
-        k_primary_pix<<<nTiles, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates);
+        // enough blocks to fill the machine a few times over, at most one block per round of 256 pixels
+        const int roundsPerTile = (fr.tile_size * fr.tile_size + kBlockThreads - 1) / kBlockThreads;
+        int parts = (primaryTargetBlocks + nTiles - 1) / nTiles;
+        parts = parts < 1 ? 1 : (parts > roundsPerTile ? roundsPerTile : parts);
+        k_primary_pix<<<nTiles * parts, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
     } else if (classify && lg >= 0) {
         k_primary_warp<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, lg);
     } else {

@@ -39,8 +39,9 @@ struct FramePointers {
 // resolve of pixels no sample of which hits, work records for the rest.
 // classify == 0 puts every pixel on the work list (used for spp > 256 and for tests).
 // tileStates: scratch of 624 words per tile of the band (seeded engine states).
+// primaryTargetBlocks: tiles are split over several blocks until the launch has about this many.
 void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                    int classify, uint32_t* tileStates, cudaStream_t stream);
+                    int classify, uint32_t* tileStates, int primaryTargetBlocks, cudaStream_t stream);
 // Shading pass: full integrator for every sample of every listed pixel, ordered resolve.
 // Megakernel form of the shading pass over the listed pixels from `firstSlot` on.
 // variant 1: block-synchronous groups; variant 2: warp-autonomous groups with dynamic

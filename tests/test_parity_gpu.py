@@ -138,6 +138,8 @@ RENDER_MODES = {
     "megakernel_warp": {"shade_mode": 2},
     "tiny_wave_budget": {"wave_budget_bytes": 1 << 20},   # most pixels overflow to the megakernel
     "deep_queues": {"wave_queue_levels": 6},
+    "shallow_queues": {"wave_queue_levels": 1},
+    "split_tiles": {"primary_blocks_per_sm": 100000},     # every tile split over one block per 256-pixel round
 }
 
 
