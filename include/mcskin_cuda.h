@@ -177,11 +177,15 @@ int32_t mcskin_cuda_band_rows(const McConfig* cfg, int32_t first_tile_row, int32
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats);
 /* Tuning / test knobs: "force_all_active" (0/1: skip the hit/miss classification and
  * shade every pixel), "record_budget_bytes" (work-list memory per launch pair),
- * "shade_blocks_per_sm" (persistent grid size of the shading pass). */
+ * "shade_blocks_per_sm" (persistent grid size of the shading pass), "shade_mode" (0 wavefront,
+ * 1/2 megakernel variants), "wave_queue_levels", "wave_budget_bytes", "primary_blocks_per_sm",
+ * "batch_lanes". */
 int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t value);
 
 /* Batched renders (one skin per scene, same config), scene i -> image i.
- * d_out_* are device pointers to n_scenes consecutive images. */
+ * d_out_* are device pointers to n_scenes consecutive images.  Asynchronous: frames are
+ * pipelined over a few internal streams ("batch_lanes" option); the given stream (or the
+ * context's) waits for all of them, mcskin_cuda_context_sync blocks until they are done. */
 int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, int32_t n_scenes,
                                          const McConfig* cfg, void* d_out_f32, void* d_out_u8, void* stream);
 

@@ -103,6 +103,9 @@ struct McContext {
     std::vector<unsigned int> hostCounts;  // active-pixel counts read back lazily
     DevBuf countLog;                       // one counter per chunk of the last render
     int chunksLastRender = 0;
+    // batch rendering
+    int batchLanes = 4;
+    std::vector<McContext*> lanes;
 };
 
 namespace {
@@ -401,6 +404,8 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
 
 void mcskin_cuda_context_destroy(McContext* ctx) {
     if (!ctx) return;
+    for (McContext* lane : ctx->lanes) mcskin_cuda_context_destroy(lane);
+    ctx->lanes.clear();
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->boxes, &ctx->texels, &ctx->count, &ctx->slotPixel, &ctx->records, &ctx->imgF32, &ctx->imgU8,
@@ -422,6 +427,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "record_budget_bytes") ctx->recordBudgetBytes = std::max<int64_t>(1, value);
     else if (k == "shade_blocks_per_sm") ctx->shadeBlocksPerSm = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "primary_blocks_per_sm") ctx->primaryBlocksPerSm = static_cast<int>(std::max<int64_t>(0, value));
+    else if (k == "batch_lanes") ctx->batchLanes = static_cast<int>(std::min<int64_t>(16, std::max<int64_t>(1, value)));
     else if (k == "shade_mode") ctx->shadeMode = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
     else if (k == "wave_queue_levels") ctx->waveQueueLevels = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "wave_budget_bytes") ctx->waveBudgetBytes = std::max<int64_t>(1 << 20, value);
@@ -465,6 +471,10 @@ int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats) {
     CU_TRY(cudaSetDevice(ctx->device));
     const int rc = finish_stats(ctx, stats);
     if (rc != MC_OK) return rc;
+    for (McContext* lane : ctx->lanes) {
+        CU_TRY(cudaStreamSynchronize(lane->stream));
+        lane->statsPending = false;
+    }
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     CU_TRY(cudaGetLastError());
     return MC_OK;
@@ -630,21 +640,53 @@ int32_t mcskin_cuda_render_multi(const McScene* scene, const McConfig* cfg, int3
     return MC_OK;
 }
 
+// Batches: scenes are independent frames.  They are spread round-robin
+// over a few "lanes" — child contexts with their own stream, scene buffers, work list and queues —
+// so that several small frames are in flight at once and nothing synchronises with the host until
+// the caller asks.  Lane k renders scenes k, k+L, k+2L, ... in stream order, which is what makes
+// reusing its buffers safe.
 int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, int32_t nScenes, const McConfig* cfg,
                                          void* dOutF32, void* dOutU8, void* stream) {
     if (!ctx || !scenes || !cfg || nScenes < 0) return fail(MC_ERR_INVALID, "render_batch: bad argument");
+    if (nScenes == 0) return MC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
     const size_t pixels = static_cast<size_t>(std::max(cfg->width, 0)) * std::max(cfg->height, 0);
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-    for (int i = 0; i < nScenes; ++i) {
-        // scenes are independent frames; the scene buffers are reused, so order the upload after the previous frame
-        CU_TRY(cudaStreamSynchronize(s));
-        int rc = mcskin_cuda_context_set_scene(ctx, &scenes[i], cfg);
+    cudaStream_t caller = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const int nLanes = std::min<int>(ctx->batchLanes, nScenes);
+    while (static_cast<int>(ctx->lanes.size()) < nLanes) {
+        McContext* lane = nullptr;
+        const int rc = mcskin_cuda_context_create(ctx->device, &lane);
         if (rc != MC_OK) return rc;
-        CU_TRY(cudaStreamSynchronize(ctx->stream));
-        rc = render_bands(ctx, 0, 1, dOutF32 ? static_cast<float4*>(dOutF32) + i * pixels : nullptr,
-                          dOutU8 ? static_cast<uchar4*>(dOutU8) + i * pixels : nullptr, s);
+        ctx->lanes.push_back(lane);
+    }
+    // lanes start after whatever the caller's stream did before (e.g. allocating the outputs)
+    CU_TRY(cudaEventRecord(ctx->evCopy, caller));
+    for (int k = 0; k < nLanes; ++k) {
+        McContext* lane = ctx->lanes[k];
+        lane->shadeMode = ctx->shadeMode;
+        lane->forceAllActive = ctx->forceAllActive;
+        lane->waveQueueLevels = ctx->waveQueueLevels;
+        lane->waveBudgetBytes = ctx->waveBudgetBytes;
+        lane->recordBudgetBytes = ctx->recordBudgetBytes;
+        lane->shadeBlocksPerSm = std::max(1, ctx->shadeBlocksPerSm / 2);  // several frames share the SMs
+        lane->primaryBlocksPerSm = ctx->primaryBlocksPerSm;
+        CU_TRY(cudaStreamWaitEvent(lane->stream, ctx->evCopy, 0));
+    }
+    for (int i = 0; i < nScenes; ++i) {
+        McContext* lane = ctx->lanes[i % nLanes];
+        int rc = mcskin_cuda_context_set_scene(lane, &scenes[i], cfg);
+        if (rc != MC_OK) return rc;
+        rc = render_bands(lane, 0, 1, dOutF32 ? static_cast<float4*>(dOutF32) + i * pixels : nullptr,
+                          dOutU8 ? static_cast<uchar4*>(dOutU8) + i * pixels : nullptr, lane->stream);
         if (rc != MC_OK) return rc;
     }
+    // the caller's stream continues once every lane is done
+    for (int k = 0; k < nLanes; ++k) {
+        CU_TRY(cudaEventRecord(ctx->lanes[k]->evCopy, ctx->lanes[k]->stream));
+        CU_TRY(cudaStreamWaitEvent(caller, ctx->lanes[k]->evCopy, 0));
+    }
+    ctx->stats = McRenderStats{};
+    ctx->statsPending = false;
     return MC_OK;
 }
 

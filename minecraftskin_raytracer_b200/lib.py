@@ -209,6 +209,15 @@ class Context:
                                                      C.c_void_p(d_out_f32 or None), C.c_void_p(d_out_u8 or None),
                                                      C.c_void_p(stream or None)))
 
+    def render_batch(self, scenes: list[FlatScene], cfg: McConfig, d_out_f32: int = 0, d_out_u8: int = 0, stream: int = 0):
+        """Asynchronous: scene i -> image i of the [n, H, W, 4] device buffer(s) (one skin per scene, same config)."""
+        arr = (McScene * len(scenes))(*[s.as_c() for s in scenes])
+        self._keep = (arr, scenes)
+        _check(_lib.mcskin_cuda_context_render_batch(self._h, arr, C.c_int32(len(scenes)), C.byref(cfg),
+                                                     C.c_void_p(d_out_f32 or None), C.c_void_p(d_out_u8 or None),
+                                                     C.c_void_p(stream or None)))
+        self.cfg = _abi.copy_config(cfg)
+
     def sync(self) -> dict:
         stats = McRenderStats()
         _check(_lib.mcskin_cuda_context_sync(self._h, C.byref(stats)))

@@ -311,3 +311,37 @@ def test_headline_frame_properties(gpu, oracle):
         assert np.array_equal(frame.cpu().numpy().view(np.uint32), f32.view(np.uint32))
     finally:
         ctx.close()
+
+
+def test_batch_of_skins(gpu, oracle):
+    """mcskin_cuda_context_render_batch (BASELINE config 4 in miniature): many skins, one config."""
+    import torch
+    n = 24
+    cfg = make_config(width=64, height=64, samples_per_pixel=4, max_bounces=2)
+    scenes = [_scene(gpu, 100 + i, "legacy" if i % 5 == 0 else "64x64", [None, "walking", "dab"][i % 3]) for i in range(n)]
+    ctx = gpu.Context(0)
+    try:
+        out = torch.zeros((n, 64, 64, 4), dtype=torch.float32, device="cuda:0")
+        out_u8 = torch.zeros((n, 64, 64, 4), dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        ctx.render_batch(scenes, cfg, out.data_ptr(), out_u8.data_ptr(), 0)
+        ctx.sync()
+        got = out.cpu().numpy()
+        for i in (0, 1, 5, 11, 23):
+            single, _, _ = gpu.render(scenes[i], cfg)
+            assert np.array_equal(_bits(got[i]), _bits(single)), i          # batched == one at a time
+            assert pixel_report(got[i], oracle.render(scenes[i], cfg), oracle.quantize)["within1"] >= 0.999
+        assert np.array_equal(out_u8.cpu().numpy(), oracle.quantize(got))
+    finally:
+        ctx.close()
+
+
+def test_render_multi_in_process(gpu):
+    """mcskin_cuda_render_multi over however many devices this process sees (1 on the test box)."""
+    scene = _scene(gpu, 3, "64x64", "running")
+    cfg = make_config(width=96, height=80, samples_per_pixel=2, max_bounces=2)
+    single, _, _ = gpu.render(scene, cfg)
+    n = gpu.device_count()
+    multi, multi_u8, stats = gpu.render(scene, cfg, want_u8=True, multi_devices=n)
+    assert np.array_equal(_bits(multi), _bits(single))
+    assert stats["n_tiles"] == len(gpu.generate_tiles(96, 80, 32))
