@@ -12,12 +12,14 @@
 // dot(p_world - o, d) for posed boxes; closest hit on strict t < best in box order.
 //
 // What is restructured.  Every query runs in two phases:
-//   1. a branch-free REJECT pass over all unposed boxes: the three slab intervals via
-//      FMNMX, tmin = max of the near values, tmax = min of the far values, and the
-//      reference's own rejection predicate (tmin > tmax || tmax < 0).  The values are
-//      the same floats the reference compares (min/max of the same two products), so
-//      the set of surviving boxes is identical; it only skips the bookkeeping of which
-//      axis won.  Survivors (typically 0-2 of 12) and all posed boxes go into a bit mask.
+//   1. a branch-free REJECT pass over all boxes: the three slab intervals via FMNMX,
+//      tmin = max of the near values, tmax = min of the far values, and the reference's
+//      own rejection predicate (tmin > tmax || tmax < 0).  For unposed boxes the values are
+//      the same floats the reference compares (min/max of the same two products), so the
+//      set of surviving boxes is identical; it only skips the bookkeeping of which axis
+//      won.  Posed boxes are tested against a world-space box around their rotated corners,
+//      inflated far beyond rounding, i.e. conservatively.  Survivors (typically 0-2 of 12)
+//      go into a bit mask.
 //   2. the EXACT evaluation (entry/exit axis with the reference's tie rules, face, UV,
 //      texel, alpha rules, pose back-transform) for the boxes in the mask, in box order.
 // Bounds, pose sines/cosines and face windows are read from the record instead of being
@@ -47,12 +49,12 @@ struct Hit {
 // Scene as the kernels see it: box records in shared memory (see SceneBlob in
 // dev_types.cuh), texels in global memory through the read-only path.
 struct SceneView {
-    const float4* __restrict__ lo;      // xyz = bounds_min, w = flags (bit pattern)
-    const float4* __restrict__ hi;      // xyz = bounds_max
+    const float4* __restrict__ lo;      // reject-pass bounds: xyz = min (the box, or a world box around a posed one), w = flags
+    const float4* __restrict__ hi;      // xyz = max
     const DevBox* __restrict__ boxes;   // full records
     const float4* __restrict__ texels;
     int n_boxes;
-    uint32_t posed_mask;   // among boxes 0..31: posed (cannot be pre-rejected in world space)
+    uint32_t posed_mask;   // among boxes 0..31: never pre-rejected (none today; posed boxes carry world bounds)
     uint32_t usable_mask;  // among boxes 0..31: exist and have triangles
 };
 
@@ -268,7 +270,6 @@ __device__ __forceinline__ uint32_t candidate_mask(const SceneView& sc, const Ra
         usable = 0u;
         for (int i = 0; i < n; ++i) {
             const uint32_t flags = __float_as_uint(sc.lo[base + i].w);
-            if (flags & kBoxRotated) posed |= 1u << i;
             if (!(flags & kBoxEmpty)) usable |= 1u << i;
         }
     }
@@ -438,34 +439,21 @@ __device__ __forceinline__ bool bundle_clip(V3 a, V3 d, V3 inv, V3 lo, V3 hi, fl
 
 __device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from, V3 to, float radius) {
     const int n = min(32, sc.n_boxes);
-    const V3 dWorld = to - from;
-    const V3 invWorld = mk3(rcp_fast(dWorld.x), rcp_fast(dWorld.y), rcp_fast(dWorld.z));
+    const V3 d = to - from;
+    const V3 inv = mk3(rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z));
     const float growFull = radius * 1.01f + 0.01f;
     uint32_t mask = 0u;
     for (int i = 0; i < n; ++i) {
+        // sc.lo / sc.hi: the box itself, or for a posed box a world-space box that contains it
         const float4 L = sc.lo[i];
         const float4 H = sc.hi[i];
-        const uint32_t flags = __float_as_uint(L.w);
-        if (flags & kBoxEmpty) continue;
-        V3 a = from, d = dWorld, inv = invWorld;
-        if (flags & kBoxRotated) {  // rigid motion into box space; distances are preserved
-            const DevBox& bx = sc.boxes[i];
-            const V3 pivot = ld3(bx.pivot);
-            const bool doX = flags & kBoxRotX, doZ = flags & kBoxRotZ;
-            V3 b = to;
-            a = rotate_about(a, pivot, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
-            a = rotate_about(a, pivot, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
-            b = rotate_about(b, pivot, false, 0.0f, 0.0f, doZ, bx.inv_cz, bx.inv_sz);
-            b = rotate_about(b, pivot, doX, bx.inv_cx, bx.inv_sx, false, 0.0f, 0.0f);
-            d = b - a;
-            inv = mk3(rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z));
-        }
+        if (__float_as_uint(L.w) & kBoxEmpty) continue;
         const V3 lo = mk3(L.x, L.y, L.z), hi = mk3(H.x, H.y, H.z);
         float sEnd;
-        if (!bundle_clip(a, d, inv, lo, hi, growFull, &sEnd)) continue;
+        if (!bundle_clip(from, d, inv, lo, hi, growFull, &sEnd)) continue;
         const float reach = fminf(fmaxf(sEnd + 1e-3f, 0.0f), 1.0f);
         float unused;
-        if (!bundle_clip(a, d, inv, lo, hi, reach * radius * 1.01f + 0.01f, &unused)) continue;
+        if (!bundle_clip(from, d, inv, lo, hi, reach * radius * 1.01f + 0.01f, &unused)) continue;
         mask |= 1u << i;
     }
     return mask;

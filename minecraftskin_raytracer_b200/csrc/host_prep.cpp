@@ -11,6 +11,7 @@
 #include "host_prep.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -183,6 +184,7 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
     out.texels[blankTexel] = {0.0f, 0.0f, 0.0f, 1.0f};
 
     out.boxes.resize(scene->n_boxes);
+    std::vector<std::array<float, 3>> rejectLo(scene->n_boxes), rejectHi(scene->n_boxes);
     double cullLo[3] = {1e300, 1e300, 1e300}, cullHi[3] = {-1e300, -1e300, -1e300};
     bool anyBox = false;
     for (int b = 0; b < scene->n_boxes; ++b) {
@@ -214,7 +216,6 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
         }
         d.flags = flags;
         if (b < 32) {
-            if (flags & kBoxRotated) f.posed_mask |= 1u << b;
             if (!(flags & kBoxEmpty)) f.usable_mask |= 1u << b;
         }
         for (int k = 0; k < kFaceCount; ++k) {
@@ -239,6 +240,7 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
             d.face[k].y = w | (h << 16);
         }
         // conservative world bounds of this box (posed boxes: rotate the 8 corners in double)
+        double boxLo[3] = {1e300, 1e300, 1e300}, boxHi[3] = {-1e300, -1e300, -1e300};
         if (!(flags & kBoxEmpty)) {
             anyBox = true;
             for (int corner = 0; corner < 8; ++corner) {
@@ -261,8 +263,28 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
                 for (int k = 0; k < 3; ++k) {
                     if (p[k] < cullLo[k]) cullLo[k] = p[k];
                     if (p[k] > cullHi[k]) cullHi[k] = p[k];
+                    if (p[k] < boxLo[k]) boxLo[k] = p[k];
+                    if (p[k] > boxHi[k]) boxHi[k] = p[k];
                 }
             }
+        }
+        // Bounds the reject pass tests.  Unposed box: the box itself — the pass then compares
+        // exactly the floats the reference compares.  Posed box: a world-space box around its
+        // rotated corners, inflated far beyond any rounding of the reference's local-space test
+        // (which the exact evaluation repeats for every survivor), so rejection stays conservative.
+        for (int k = 0; k < 3; ++k) {
+            float lo = d.lo[k], hi = d.hi[k];
+            if (src.has_rotation && !(flags & kBoxEmpty)) {
+                const double margin = 1e-3 * (std::fabs(boxLo[k]) + std::fabs(boxHi[k]) + (boxHi[k] - boxLo[k])) + 1e-2;
+                lo = static_cast<float>(boxLo[k] - margin);
+                hi = static_cast<float>(boxHi[k] + margin);
+                if (!std::isfinite(lo) || !std::isfinite(hi)) {  // degenerate pose: never pre-reject
+                    lo = -std::numeric_limits<float>::max();
+                    hi = std::numeric_limits<float>::max();
+                }
+            }
+            rejectLo[b][k] = lo;
+            rejectHi[b][k] = hi;
         }
     }
     // shared-memory image of the boxes
@@ -273,9 +295,9 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
         float* hi = reinterpret_cast<float*>(out.blob.data() + lay.hiOffset());
         for (int b = 0; b < scene->n_boxes; ++b) {
             const DevBox& d = out.boxes[b];
-            std::memcpy(lo + 4 * b, d.lo, 3 * sizeof(float));
+            std::memcpy(lo + 4 * b, rejectLo[b].data(), 3 * sizeof(float));
             std::memcpy(lo + 4 * b + 3, &d.flags, sizeof(uint32_t));
-            std::memcpy(hi + 4 * b, d.hi, 3 * sizeof(float));
+            std::memcpy(hi + 4 * b, rejectHi[b].data(), 3 * sizeof(float));
         }
         if (scene->n_boxes > 0)
             std::memcpy(out.blob.data() + lay.boxOffset(), out.boxes.data(), sizeof(DevBox) * scene->n_boxes);
