@@ -2,6 +2,8 @@
 next to the package so it travels with the repo snapshot to the GPU box."""
 from __future__ import annotations
 
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -31,17 +33,38 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; the CUDA extension cannot be built")
 
 
+def _source_digest() -> str:
+    """Hash of everything the library is built from (file contents, not mtimes: the snapshot that
+    travels to the GPU box does not preserve a meaningful order of timestamps)."""
+    h = hashlib.sha1(" ".join(NVCC_FLAGS).encode())
+    for path in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) +
+                       list(CSRC.glob("*.hpp")) + [ROOT / "include" / "mcskin_cuda.h"]):
+        h.update(path.name.encode())
+        h.update(path.read_bytes())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not LIB_PATH.exists():
-        return True
-    newest = max(p.stat().st_mtime for p in list(CSRC.glob("*")) + [ROOT / "include" / "mcskin_cuda.h"])
-    return LIB_PATH.stat().st_mtime < newest
+    stamp = LIB_DIR / "build.hash"
+    return not LIB_PATH.exists() or not stamp.exists() or stamp.read_text().strip() != _source_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB_PATH
     LIB_DIR.mkdir(exist_ok=True)
+    # one builder at a time (torchrun starts one process per GPU, all of which may get here)
+    with open(LIB_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> Path:
     obj_dir = LIB_DIR / "obj"
     obj_dir.mkdir(exist_ok=True)
     nvcc = _nvcc()
@@ -63,10 +86,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
     (LIB_DIR / "build.log").write_text("\n".join(log))
-    link = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB_DIR / f".libmcskin_cuda.{os.getpid()}.so"
+    link = [nvcc, "-shared", "-o", str(tmp), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)  # atomic: a concurrent dlopen sees the old or the new file, never half of one
+    (LIB_DIR / "build.hash").write_text(_source_digest())
     if verbose:
         print("\n".join(log))
     return LIB_PATH

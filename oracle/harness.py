@@ -11,6 +11,8 @@ Both expose the same operations on the flat PODs of include/mcskin_cuda.h.
 from __future__ import annotations
 
 import ctypes as C
+import fcntl
+import hashlib
 import os
 import subprocess
 from pathlib import Path
@@ -38,10 +40,34 @@ class McOracleCounters(C.Structure):
         return {name: int(getattr(self, name)) for name in COUNTER_FIELDS}
 
 
+def _oracle_digest() -> str:
+    h = hashlib.sha1()
+    for path in (HERE / "mcskin_oracle.c", HERE / "mcskin_oracle.h", HERE / "Makefile", HERE.parent / "include" / "mcskin_cuda.h"):
+        h.update(path.read_bytes())
+    return h.hexdigest()
+
+
 def build_oracle(force: bool = False) -> Path:
-    src = HERE / "mcskin_oracle.c"
-    if force or not ORACLE_SO.exists() or ORACLE_SO.stat().st_mtime < src.stat().st_mtime:
-        subprocess.run(["make", "-C", str(HERE), "libmcskin_oracle.so"], check=True, capture_output=True)
+    """gcc build of the C restatement; content-hashed and locked so parallel test workers and
+    torchrun ranks do not rebuild it on top of each other."""
+    stamp = HERE / ".oracle.hash"
+
+    def stale():
+        return not ORACLE_SO.exists() or not stamp.exists() or stamp.read_text().strip() != _oracle_digest()
+
+    if not force and not stale():
+        return ORACLE_SO
+    with open(HERE / ".oracle.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or stale():
+                tmp = HERE / f".libmcskin_oracle.{os.getpid()}.so"
+                subprocess.run(["make", "-C", str(HERE), "-B", "libmcskin_oracle.so", f"OUT={tmp.name}"], check=True,
+                               capture_output=True)
+                os.replace(tmp, ORACLE_SO)
+                stamp.write_text(_oracle_digest())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return ORACLE_SO
 
 
