@@ -205,6 +205,7 @@ def run_own_arm(args):
     unique_rays = entry["unique_rays"]
 
     ctx = lib.Context(local_rank)
+    lanes_default = int(os.environ.get("MCSKIN_FRAME_LANES", "0")) or lib.DEFAULT_FRAME_LANES
     ctx.set_scene(scene, cfg)
     max_rows = bands.padded_band_rows(H, ts, world)  # padded band height, equal on all ranks
     assert ctx.band_rows(rank, world) == bands.band_pixel_rows(H, ts, rank, world)
@@ -246,15 +247,27 @@ def run_own_arm(args):
         starts[i].record(stream)
         step()
         ends[i].record(stream)
-        st = ctx.sync()  # per-pass event times of this frame (blocks on the frame; the next flush follows anyway)
-        pass_ms["primary"] += st["ms_primary"]
-        pass_ms["shade"] += st["ms_shade"]
+        st = ctx.sync()  # the library's own events around this frame's launches (blocks on the frame; the next flush follows anyway)
         pass_ms["device"] += st["ms_device"]
         n_active = st["n_active_pixels"]
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    # Pass breakdown, outside the timed region: the same frame on ONE stream with direct launches
+    # (the timed frames interleave several lanes inside a CUDA graph, where pass times overlap).
+    ctx.set_option("use_graphs", 0)
+    ctx.set_option("frame_lanes", 1)
+    n_serial = max(1, min(args.steps, 5))
+    for i in range(1 + n_serial):
+        flush.fill_(i & 0xff)
+        ctx.render_bands(rank, world, band.data_ptr(), band_u8.data_ptr(), stream.cuda_stream)
+        st = ctx.sync()
+        if i > 0:
+            pass_ms["primary"] += st["ms_primary"] / n_serial
+            pass_ms["shade"] += st["ms_shade"] / n_serial
+    ctx.set_option("use_graphs", 1)
+    ctx.set_option("frame_lanes", lanes_default)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -308,13 +321,12 @@ def run_own_arm(args):
     peaks = measured_peaks()
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = sm_count * 128 * peaks["sm_max_mhz"] * 1e6 / 1e12  # T lane-ops/s, non-FMA issue rate
-    # dominant kernel = the shading pass; its algorithmic share and its own event time
-    shade_ms = pass_ms["shade"] / args.steps
-    primary_ms = pass_ms["primary"] / args.steps
-    # at N>1 each rank does ~1/N of the frame: per-GPU achieved rate uses the per-rank share
-    shade_ops = ops["shade_pass"] / world
-    achieved = shade_ops / (shade_ms * 1e-3) / 1e12 if shade_ms > 0 else 0.0
-    step_achieved = ops["total"] / world / (pass_ms["device"] / args.steps * 1e-3) / 1e12 if pass_ms["device"] > 0 else 0.0
+    # The frame is one pipeline of ~14 short kernels per lane, several lanes in flight at once, so
+    # the roofline entry is that of the whole step: the frame's algorithmic lane-ops over the
+    # event time of a frame's launches.  At N>1 each rank does ~1/N of the frame.
+    device_ms = pass_ms["device"] / args.steps
+    step_ops = ops["total"] / world
+    achieved = step_ops / (device_ms * 1e-3) / 1e12 if device_ms > 0 else 0.0
     fb_bytes = W * H * (16 + 4)
     line = {
         "metric": "Mrays/s", "value": unique_rays / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
@@ -324,19 +336,24 @@ def run_own_arm(args):
                    "max_bounces": cfg.max_bounces, "shadow_samples": cfg.shadow_samples, "tile_size": ts,
                    "skin": "synthetic 64x64 seed 0", "unique_rays_per_frame": unique_rays,
                    "partition": "whole frame" if world == 1 else f"interleaved tile rows over {world} GPUs + NCCL gather",
-                   "l2": "flushed between timed iterations (256 MiB fill outside the timed events)"},
+                   "l2": "flushed between timed iterations (256 MiB fill outside the timed events)",
+                   "frame_lanes": lanes_default, "launch": "CUDA graph replay of the frame's kernels"},
         "clocks": clocks,
         "e2e": {"value": unique_rays / (e2e_ms * 1e-3) / 1e6 if e2e_ms else None, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {
-            "bound": "fp32", "kernel": "k_shade", "achieved": achieved, "peak": fp32_peak, "unit": "Tlane-op/s",
+            "bound": "fp32", "kernel": f"frame pipeline ({launches_per_step} kernel launches: primary pass + wavefront shading)",
+            "achieved": achieved, "peak": fp32_peak, "unit": "Tlane-op/s",
             "frac": achieved / fp32_peak, "traffic": None,
             "peak_source": f"{sm_count} SMs x 128 FP32 lanes x {peaks['sm_max_mhz']:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json"
                            + (", fallback" if peaks.get("_fallback") else "") + "); non-FMA issue rate, SURVEY.md §8d",
-            "alg_ops_per_launch": shade_ops, "ms_per_launch": shade_ms,
-            "whole_step": {"achieved": step_achieved, "frac": step_achieved / fp32_peak, "alg_ops": ops["total"] / world,
-                           "ms_kernels": pass_ms["device"] / args.steps, "ms_primary_pass": primary_ms},
+            "alg_ops_per_launch": step_ops, "ms_per_launch": device_ms,
+            "serial_breakdown": {
+                "what": "one stream, direct launches, same frame (outside the timed region)",
+                "ms_primary_pass": pass_ms["primary"], "ms_shade_pass": pass_ms["shade"],
+                "frac_primary_pass": (ops["primary_pass"] / world / (pass_ms["primary"] * 1e-3) / 1e12 / fp32_peak) if pass_ms["primary"] > 0 else None,
+                "frac_shade_pass": (ops["shade_pass"] / world / (pass_ms["shade"] * 1e-3) / 1e12 / fp32_peak) if pass_ms["shade"] > 0 else None},
             "hbm_framebuffer": {"bytes_per_frame": fb_bytes, "achieved_gbs": fb_bytes / (ms_per_step * 1e-3) / 1e9,
                                 "peak_gbs": peaks["hbm_gbs"], "frac": fb_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
         },

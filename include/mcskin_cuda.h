@@ -236,6 +236,13 @@ int32_t mcskin_cuda_generate_rays(const McScene* scene, int32_t device, float as
 /* RayTracer::backgroundColor(scene, u, v, use_config ? &config : nullptr) (raytracer.cpp:16-34). */
 int32_t mcskin_cuda_background(const McScene* scene, const McConfig* cfg, int32_t device, int32_t use_config,
                                const float* uv, int32_t n, float* out_rgba);
+/* std::sin / std::cos of float angles as the device evaluates them for the light-disk, lens and AO
+ * samples (shading.cpp:51, tile_renderer.cpp:61-62, raytracer.cpp:62-64): bit-identical to glibc's
+ * sinf / cosf on an FMA-capable x86-64 host for |angle| < 120. */
+int32_t mcskin_cuda_sincos(int32_t device, const float* angles, int32_t n, float* out_sin, float* out_cos);
+/* The same arithmetic evaluated on the host (no device needed): lets a CPU-only test pin the
+ * restated algorithm to the host's libm. */
+void mcskin_sincos_model(const float* angles, int32_t n, float* out_sin, float* out_cos);
 /* Hit mask + triangle id of the pinhole ray through each pixel centre
  * (u=(px+.5)/W, v=(py+.5)/H): out_tri_id[py*W+px] = box*12+face*2, or -1. */
 int32_t mcskin_cuda_aov(const McScene* scene, const McConfig* cfg, int32_t device, int32_t* out_tri_id);

@@ -2,6 +2,7 @@
 // launches, host<->device copies.  No exceptions leave this file; every failure is a
 // negative MC_ERR_* plus a thread-local message (mcskin_cuda_last_error).
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -34,12 +35,16 @@ int cuda_fail(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
     } while (0)
 
+// Bumped whenever a device buffer is reallocated: captured frame graphs hold raw pointers.
+std::atomic<unsigned long long> g_allocEpoch{1};
+
 // Device buffer that only ever grows.
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        g_allocEpoch.fetch_add(1);
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -95,6 +100,51 @@ struct McContext {
     int shadeBlocksPerSm = 8;
     int primaryBlocksPerSm = 9;              // split tiles over blocks until a launch has this many per SM
     int waveQueueLevels = 3;                 // bounce depths handled by queues; deeper ones in-thread
+    int waveShadowPrefetch = 0;
+    int waveDeepGridDiv = 1;                 // launches of depth >= 1 use shade grid / this
+    int frameLanes = 2;                      // a frame's tile rows are rendered on this many streams at once
+    bool isChild = false;                    // a lane of another context (never splits frames itself)
+    // seeded tile engines kept from the previous frame: they depend on the image width, the tile
+    // size and the tile rows of the band only (tile_renderer.cpp:78), not on the scene
+    struct TileSeedKey {
+        int width = 0, tile_size = 0, first = 0, stride = 0, rows = 0;
+        const void* buf = nullptr;
+        cudaStream_t stream = nullptr;
+        bool operator==(const TileSeedKey& o) const {
+            return width == o.width && tile_size == o.tile_size && first == o.first && stride == o.stride &&
+                   rows == o.rows && buf == o.buf && stream == o.stream;
+        }
+    } tileSeedKey;
+    bool tileSeedValid = false;
+    int cacheTileSeeds = 1;
+    int splitLastRender = 0;                 // lanes (beyond this context) used by the last render
+    int staggerLanes = 1;                    // lane k's primary pass starts when lane k-1's has finished
+    cudaEvent_t evPrimaryDone = nullptr;     // (disable-timing) recorded after this lane's primary pass
+    cudaEvent_t evUpload = nullptr;          // (disable-timing) recorded after the scene upload on ctx->stream
+    unsigned long long seedGen = 0;          // bumped whenever tileStates is rewritten outside a graph
+    bool capturing = false;                  // the launches are being captured into a graph: no timing events
+    // The launches of a frame replayed as one CUDA graph (a frame is ~14 short kernels per lane;
+    // launching them one by one costs the host more than the device needs to run them).  A graph
+    // is captured the second time the same frame description is rendered and replayed while
+    // nothing it depends on changes.
+    int useGraphs = 1;
+    struct GraphKey {
+        DevFrame frame;
+        const void *blob, *texels, *outF32, *outU8;
+        unsigned int blobBytes;
+        int first, stride, lanes;
+        long long optionBits[12];
+        unsigned long long allocEpoch;
+        bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
+    };
+    GraphKey graphKey{}, graphCandidate{};
+    bool hasCandidate = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graphExec = nullptr;
+    std::vector<unsigned long long> graphSeedGens;  // seedGen of every lane when the graph was captured
+    int graphLaunches = 0, graphChunks = 0, graphSplit = 0;
+    std::vector<int> graphLaneLaunches, graphLaneChunks, graphLaneTiles;
+    bool graphLastRender = false;
     int shadeMode = 0;                       // 0 wavefront, 1 megakernel (block groups), 2 megakernel (warp groups)
     long long waveBudgetBytes = 12ll << 30;   // queue storage; pixels beyond it fall back to the megakernel
     // stats of the last render
@@ -121,7 +171,8 @@ int upload_scene(McContext* ctx) {
     CU_TRY(cudaMemcpyAsync(ctx->texels.p, pf.texels.data(), pf.texels.size() * sizeof(float4h),
                            cudaMemcpyHostToDevice, ctx->stream));
     // pageable sources: the copies above are staged synchronously by the runtime, so the
-    // host vectors may change afterwards
+    // host vectors may change afterwards; renders on another stream wait for this event
+    CU_TRY(cudaEventRecord(ctx->evUpload, ctx->stream));
     return MC_OK;
 }
 
@@ -143,11 +194,16 @@ int band_pixel_rows(const DevFrame& f, int first, int stride) {
     return (n - 1) * f.tile_size + lastHeight;
 }
 
-// Launches the two passes for the tile rows {first + k*stride}; output pointers are device memory.
-int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* outU8, cudaStream_t stream) {
-    const DevFrame& f = ctx->prep.frame;
+// Launches the two passes for the tile rows {first + k*stride} on one stream; output pointers are
+// device memory.  scn: the context whose scene (prepared frame, box and texel buffers) is rendered;
+// local tile row r is written at tile row outFirst + r*outStride of the output image.
+int render_bands_lane(McContext* ctx, const McContext* scn, int first, int stride, int outFirst, int outStride,
+                      float4* outF32, uchar4* outU8, cudaStream_t stream, cudaEvent_t waitBeforePrimary = nullptr,
+                      cudaEvent_t recordAfterPrimary = nullptr) {
+    const DevFrame& f = scn->prep.frame;
     const int nRows = local_tile_rows(f, first, stride);
     ctx->chunksLastRender = 0;
+    ctx->graphLastRender = false;
     ctx->stats = McRenderStats{};
     ctx->stats.n_samples = static_cast<int64_t>(std::max(f.width, 0)) * std::max(f.height, 0) * f.spp;
     ctx->stats.n_tiles = nRows * f.tiles_x;
@@ -198,10 +254,20 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
                              ctx->smCount * ctx->shadeBlocksPerSm, &wave))
             return fail(MC_ERR_CUDA, "wavefront buffer carve failed");
         wave.queueLevels = ctx->waveQueueLevels;
+        wave.deepGridDiv = ctx->waveDeepGridDiv;
+        wave.shadowPrefetch = ctx->waveShadowPrefetch;
     }
-    CU_TRY(cudaEventRecord(ctx->ev0, stream));
-    const FramePointers fp = frame_pointers(ctx);
+    if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->ev0, stream));
+    const FramePointers fp = frame_pointers(scn);
     int launches = 0;
+    McContext::TileSeedKey seedKey;
+    seedKey.width = f.width; seedKey.tile_size = f.tile_size; seedKey.first = first; seedKey.stride = stride;
+    seedKey.rows = nRows; seedKey.buf = ctx->tileStates.p; seedKey.stream = stream;
+    const bool seedsCacheable = ctx->cacheTileSeeds && nChunks == 1 && f.draws_per_sample > 0;
+    const bool seedTiles = !(seedsCacheable && ctx->tileSeedValid && seedKey == ctx->tileSeedKey);
+    ctx->tileSeedKey = seedKey;
+    ctx->tileSeedValid = false;
+    if (seedTiles) ++ctx->seedGen;
     for (int c = 0; c < nChunks; ++c) {
         const int row0 = static_cast<int>(c * rowsPerChunk);
         const int rows = static_cast<int>(std::min<size_t>(rowsPerChunk, nRows - row0));
@@ -209,9 +275,10 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         band.first_tile_row = first + row0 * stride;
         band.tile_row_stride = stride;
         band.n_tile_rows = rows;
-        const size_t pixelOffset = static_cast<size_t>(row0) * f.tile_size * f.width;
-        band.out_f32 = outF32 ? outF32 + pixelOffset : nullptr;
-        band.out_u8 = outU8 ? outU8 + pixelOffset : nullptr;
+        band.out_first_row = outFirst + row0 * outStride;
+        band.out_row_stride = outStride;
+        band.out_f32 = outF32;
+        band.out_u8 = outU8;
         ActiveList list;
         list.count = static_cast<unsigned int*>(ctx->countLog.p) + c;
         list.slot_pixel = static_cast<uint2*>(ctx->slotPixel.p);
@@ -222,10 +289,13 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
             CU_TRY(cudaMemsetAsync(list.slot_pixel, 0xff, static_cast<size_t>(list.capacity) * sizeof(uint2), stream));
             CU_TRY(cudaMemcpyAsync(list.count, &list.capacity, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
         }
-        CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
-        launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
-                       ctx->smCount * ctx->primaryBlocksPerSm, stream);
-        CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 1], stream));
+        if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
+        if (c == 0 && waitBeforePrimary) CU_TRY(cudaStreamWaitEvent(stream, waitBeforePrimary, 0));
+        const bool seeded = launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
+                                           seedTiles, ctx->smCount * ctx->primaryBlocksPerSm, stream);
+        ctx->tileSeedValid = seedsCacheable && seeded;
+        if (c == nChunks - 1 && recordAfterPrimary) CU_TRY(cudaEventRecord(recordAfterPrimary, stream));
+        if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 1], stream));
         unsigned int* groupCounter = static_cast<unsigned int*>(ctx->countLog.p) + nChunks + c;
         const int shadeGrid = ctx->smCount * ctx->shadeBlocksPerSm;
         if (ctx->shadeMode == 0) {
@@ -234,10 +304,10 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
             launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
             ++launches;
         }
-        CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 2], stream));
+        if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 2], stream));
         ++launches;
     }
-    CU_TRY(cudaEventRecord(ctx->ev1, stream));
+    if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->ev1, stream));
     CU_TRY(cudaGetLastError());
     ctx->chunksLastRender = nChunks;
     ctx->stats.n_kernel_launches = launches;
@@ -245,14 +315,188 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
     return MC_OK;
 }
 
+int ensure_lanes(McContext* ctx, int n) {
+    while (static_cast<int>(ctx->lanes.size()) < n) {
+        McContext* lane = nullptr;
+        const int rc = mcskin_cuda_context_create(ctx->device, &lane);
+        if (rc != MC_OK) return rc;
+        lane->isChild = true;
+        ctx->lanes.push_back(lane);
+    }
+    return MC_OK;
+}
+
+void inherit_options(McContext* lane, const McContext* ctx) {
+    lane->shadeMode = ctx->shadeMode;
+    lane->forceAllActive = ctx->forceAllActive;
+    lane->waveQueueLevels = ctx->waveQueueLevels;
+    lane->waveDeepGridDiv = ctx->waveDeepGridDiv;
+    lane->waveShadowPrefetch = ctx->waveShadowPrefetch;
+    lane->waveBudgetBytes = ctx->waveBudgetBytes;
+    lane->recordBudgetBytes = ctx->recordBudgetBytes;
+    lane->shadeBlocksPerSm = ctx->shadeBlocksPerSm;
+    lane->primaryBlocksPerSm = ctx->primaryBlocksPerSm;
+    lane->cacheTileSeeds = ctx->cacheTileSeeds;
+    lane->useGraphs = 0;
+}
+
+// Launches the lanes of one frame (see render_bands) on `stream` and the child lanes' streams.
+int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* outF32, uchar4* outU8, cudaStream_t stream) {
+    if (L <= 1) return render_bands_lane(ctx, ctx, first, stride, 0, 1, outF32, outU8, stream);
+    CU_TRY(cudaEventRecord(ctx->evCopy, stream));  // fork point
+    const bool stagger = ctx->staggerLanes != 0;
+    // lane 0 on the caller's stream, lanes 1..L-1 on their own; launched in lane order so that
+    // each lane's "primary pass done" record precedes the next lane's wait on it
+    int rc = render_bands_lane(ctx, ctx, first, stride * L, 0, L, outF32, outU8, stream, nullptr,
+                               stagger ? ctx->evPrimaryDone : nullptr);
+    if (rc != MC_OK) return rc;
+    for (int k = 1; k < L; ++k) {
+        McContext* lane = ctx->lanes[k - 1];
+        McContext* prev = k == 1 ? ctx : ctx->lanes[k - 2];
+        CU_TRY(cudaStreamWaitEvent(lane->stream, ctx->evCopy, 0));
+        rc = render_bands_lane(lane, ctx, first + k * stride, stride * L, k, L, outF32, outU8, lane->stream,
+                               stagger ? prev->evPrimaryDone : nullptr, stagger ? lane->evPrimaryDone : nullptr);
+        if (rc != MC_OK) return rc;
+        CU_TRY(cudaEventRecord(lane->evCopy, lane->stream));
+    }
+    for (int k = 1; k < L; ++k) CU_TRY(cudaStreamWaitEvent(stream, ctx->lanes[k - 1]->evCopy, 0));  // join
+    return MC_OK;
+}
+
+long long option_bits(const McContext* c, int i) {
+    const long long v[12] = {c->forceAllActive, c->recordBudgetBytes, c->shadeBlocksPerSm, c->primaryBlocksPerSm,
+                             c->waveQueueLevels, c->shadeMode, c->waveBudgetBytes, c->waveDeepGridDiv,
+                             c->waveShadowPrefetch, c->cacheTileSeeds, c->staggerLanes, c->frameLanes};
+    return v[i];
+}
+
+void drop_graph(McContext* ctx) {
+    if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
+    if (ctx->graph) cudaGraphDestroy(ctx->graph);
+    ctx->graphExec = nullptr;
+    ctx->graph = nullptr;
+}
+
+// Renders the tile rows {first + k*stride} of the context's scene into a compact band image.
+// With frameLanes = L > 1 the rows are dealt round-robin to L streams (this context's and L-1
+// child lanes with their own work lists and queues): the kernels of one lane are short and
+// latency-bound towards the end of a frame (deep bounce levels, the tails of every launch), and
+// the SMs fill those gaps with the other lanes' blocks.  Whole tile rows per lane, so the image
+// is bit-identical to the one-stream result.  The second time the same frame description comes
+// in, the launches are captured into a CUDA graph, which is replayed from then on.
+int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* outU8, cudaStream_t stream) {
+    const DevFrame& f = ctx->prep.frame;
+    const int nRows = local_tile_rows(f, first, stride);
+    const int L = ctx->isChild ? 1 : std::max(1, std::min(ctx->frameLanes, nRows / 2));
+    ctx->splitLastRender = 0;
+    ctx->graphLastRender = false;
+    if (stream != ctx->stream && ctx->evUpload) CU_TRY(cudaStreamWaitEvent(stream, ctx->evUpload, 0));
+    if (L > 1) {
+        const int rc = ensure_lanes(ctx, L - 1);
+        if (rc != MC_OK) return rc;
+        for (int k = 1; k < L; ++k) inherit_options(ctx->lanes[k - 1], ctx);
+    }
+    const bool graphable = ctx->useGraphs && !ctx->isChild && nRows > 0 && !ctx->forceAllActive && f.spp <= kBlockThreads &&
+                           f.width <= 65535 && f.height <= 65535;
+    McContext::GraphKey key;
+    std::memset(&key, 0, sizeof(key));
+    if (graphable) {
+        key.frame = f;
+        key.blob = ctx->boxes.p; key.texels = ctx->texels.p; key.outF32 = outF32; key.outU8 = outU8;
+        key.blobBytes = static_cast<unsigned int>(ctx->prep.blob.size());
+        key.first = first; key.stride = stride; key.lanes = L;
+        for (int i = 0; i < 12; ++i) key.optionBits[i] = option_bits(ctx, i);
+        key.allocEpoch = g_allocEpoch.load();
+        if (ctx->graphExec && key == ctx->graphKey) {
+            // the graph skips the tile seeding when the seeds were already in place at capture time
+            bool seedsIntact = ctx->graphSeedGens.size() == static_cast<size_t>(L) && ctx->graphSeedGens[0] == ctx->seedGen;
+            for (int k = 1; seedsIntact && k < L; ++k) seedsIntact = ctx->graphSeedGens[k] == ctx->lanes[k - 1]->seedGen;
+            if (seedsIntact) {
+                CU_TRY(cudaEventRecord(ctx->ev0, stream));
+                CU_TRY(cudaGraphLaunch(ctx->graphExec, stream));
+                CU_TRY(cudaEventRecord(ctx->ev1, stream));
+                ctx->stats = McRenderStats{};
+                ctx->stats.n_samples = static_cast<int64_t>(f.width) * f.height * f.spp;
+                ctx->stats.n_tiles = ctx->graphLaneTiles[0];
+                ctx->stats.n_kernel_launches = ctx->graphLaneLaunches[0];
+                ctx->chunksLastRender = ctx->graphLaneChunks[0];
+                ctx->statsPending = true;
+                for (int k = 1; k < L; ++k) {
+                    McContext* lane = ctx->lanes[k - 1];
+                    lane->stats = McRenderStats{};
+                    lane->stats.n_tiles = ctx->graphLaneTiles[k];
+                    lane->stats.n_kernel_launches = ctx->graphLaneLaunches[k];
+                    lane->chunksLastRender = ctx->graphLaneChunks[k];
+                    lane->statsPending = true;
+                    lane->graphLastRender = true;
+                }
+                ctx->splitLastRender = L - 1;
+                ctx->graphLastRender = true;
+                return MC_OK;
+            }
+            drop_graph(ctx);
+        }
+    }
+    const bool capture = graphable && ctx->hasCandidate && key == ctx->graphCandidate;
+    ctx->hasCandidate = graphable && !capture;
+    if (graphable) ctx->graphCandidate = key;
+    if (capture) {
+        drop_graph(ctx);
+        ctx->capturing = true;
+        for (int k = 1; k < L; ++k) ctx->lanes[k - 1]->capturing = true;
+        cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
+        int rc = e == cudaSuccess ? launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream) : MC_ERR_CUDA;
+        cudaGraph_t g = nullptr;
+        if (e == cudaSuccess) {
+            const cudaError_t e2 = cudaStreamEndCapture(stream, &g);
+            if (e2 != cudaSuccess) rc = MC_ERR_CUDA;
+        }
+        ctx->capturing = false;
+        for (int k = 1; k < L; ++k) ctx->lanes[k - 1]->capturing = false;
+        const bool reallocated = key.allocEpoch != g_allocEpoch.load();  // cannot happen for an unchanged frame; be safe
+        if (rc == MC_OK && g && !reallocated && cudaGraphInstantiate(&ctx->graphExec, g, 0) == cudaSuccess) {
+            ctx->graph = g;
+            ctx->graphKey = key;
+            ctx->graphSeedGens.assign(L, 0);
+            ctx->graphLaneLaunches.assign(L, 0);
+            ctx->graphLaneChunks.assign(L, 0);
+            ctx->graphLaneTiles.assign(L, 0);
+            for (int k = 0; k < L; ++k) {
+                const McContext* lane = k == 0 ? ctx : ctx->lanes[k - 1];
+                ctx->graphSeedGens[k] = lane->seedGen;
+                ctx->graphLaneLaunches[k] = lane->stats.n_kernel_launches;
+                ctx->graphLaneChunks[k] = lane->chunksLastRender;
+                ctx->graphLaneTiles[k] = static_cast<int>(lane->stats.n_tiles);
+            }
+            return render_bands(ctx, first, stride, outF32, outU8, stream);  // replays the graph just made
+        }
+        // capture failed (an operation that cannot be captured): clear the error state, render directly
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        ctx->graphExec = nullptr;
+        ctx->useGraphs = 0;
+    }
+    CU_TRY(cudaEventRecord(ctx->ev0, stream));
+    const int rc = launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream);
+    if (rc != MC_OK) return rc;
+    if (L > 1) {
+        CU_TRY(cudaEventRecord(ctx->ev1, stream));
+        ctx->splitLastRender = L - 1;
+        ctx->stats.n_samples = static_cast<int64_t>(std::max(f.width, 0)) * std::max(f.height, 0) * f.spp;
+    }
+    return MC_OK;
+}
+
 int finish_stats(McContext* ctx, McRenderStats* out) {
     if (ctx->statsPending) {
-        CU_TRY(cudaEventSynchronize(ctx->ev1));
         float ms = 0.0f;
-        CU_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (!(ctx->isChild && ctx->graphLastRender)) {  // a lane replayed inside its parent's graph has no events of its own
+            CU_TRY(cudaEventSynchronize(ctx->ev1));
+            CU_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        }
         ctx->stats.ms_device = ms;
         ctx->stats.ms_primary = ctx->stats.ms_shade = 0.0f;
-        for (int c = 0; c < ctx->chunksLastRender; ++c) {
+        for (int c = 0; c < ctx->chunksLastRender && !ctx->graphLastRender; ++c) {
             float a = 0.0f, b = 0.0f;
             CU_TRY(cudaEventElapsedTime(&a, ctx->passEvents[3 * c], ctx->passEvents[3 * c + 1]));
             CU_TRY(cudaEventElapsedTime(&b, ctx->passEvents[3 * c + 1], ctx->passEvents[3 * c + 2]));
@@ -267,6 +511,17 @@ int finish_stats(McContext* ctx, McRenderStats* out) {
         for (unsigned int v : ctx->hostCounts) active += v;
         ctx->stats.n_active_pixels = static_cast<int32_t>(std::min<long long>(active, 0x7fffffff));
         ctx->statsPending = false;
+        // a frame split over lanes: the lanes ran side by side, so counts add and pass times overlap
+        for (int k = 0; k < ctx->splitLastRender; ++k) {
+            McRenderStats s{};
+            const int rc = finish_stats(ctx->lanes[k], &s);
+            if (rc != MC_OK) return rc;
+            ctx->stats.n_tiles += s.n_tiles;
+            ctx->stats.n_active_pixels += s.n_active_pixels;
+            ctx->stats.n_kernel_launches += s.n_kernel_launches;
+            ctx->stats.ms_primary = std::max(ctx->stats.ms_primary, s.ms_primary);
+            ctx->stats.ms_shade = std::max(ctx->stats.ms_shade, s.ms_shade);
+        }
     }
     if (out) *out = ctx->stats;
     return MC_OK;
@@ -394,9 +649,18 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     CU_TRY(cudaEventCreate(&ctx->ev0));
     CU_TRY(cudaEventCreate(&ctx->ev1));
     CU_TRY(cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ctx->evPrimaryDone, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ctx->evUpload, cudaEventDisableTiming));
     if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
     if (const char* v = std::getenv("MCSKIN_PRIMARY_BLOCKS")) ctx->primaryBlocksPerSm = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) ctx->waveQueueLevels = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("MCSKIN_SHADOW_PREFETCH")) ctx->waveShadowPrefetch = std::atoi(v) != 0;
+    if (const char* v = std::getenv("MCSKIN_DEEP_GRID_DIV")) ctx->waveDeepGridDiv = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("MCSKIN_GRAPHS")) ctx->useGraphs = std::atoi(v) != 0;
+    if (const char* v = std::getenv("MCSKIN_STAGGER")) ctx->staggerLanes = std::atoi(v) != 0;
+    if (const char* v = std::getenv("MCSKIN_FRAME_LANES")) ctx->frameLanes = std::min(8, std::max(1, std::atoi(v)));
+    if (const char* v = std::getenv("MCSKIN_CACHE_TILE_SEEDS")) ctx->cacheTileSeeds = std::atoi(v) != 0;
+    if (const char* v = std::getenv("MCSKIN_SHADE_BLOCKS")) ctx->shadeBlocksPerSm = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_SHADE_MODE")) ctx->shadeMode = std::min(2, std::max(0, std::atoi(v)));
     *out = ctx.release();
     return MC_OK;
@@ -415,6 +679,10 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
+    if (ctx->evPrimaryDone) cudaEventDestroy(ctx->evPrimaryDone);
+    if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
+    if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
+    if (ctx->graph) cudaGraphDestroy(ctx->graph);
     for (cudaEvent_t e : ctx->passEvents) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -430,6 +698,11 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "batch_lanes") ctx->batchLanes = static_cast<int>(std::min<int64_t>(16, std::max<int64_t>(1, value)));
     else if (k == "shade_mode") ctx->shadeMode = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
     else if (k == "wave_queue_levels") ctx->waveQueueLevels = static_cast<int>(std::max<int64_t>(1, value));
+    else if (k == "wave_deep_grid_div") ctx->waveDeepGridDiv = static_cast<int>(std::max<int64_t>(1, value));
+    else if (k == "frame_lanes") ctx->frameLanes = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(1, value)));
+    else if (k == "cache_tile_seeds") ctx->cacheTileSeeds = value != 0;
+    else if (k == "use_graphs") ctx->useGraphs = value != 0;
+    else if (k == "stagger_lanes") ctx->staggerLanes = value != 0;
     else if (k == "wave_budget_bytes") ctx->waveBudgetBytes = std::max<int64_t>(1 << 20, value);
     else return fail(MC_ERR_INVALID, "set_option: unknown option " + k);
     return MC_OK;
@@ -653,23 +926,16 @@ int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, 
     const size_t pixels = static_cast<size_t>(std::max(cfg->width, 0)) * std::max(cfg->height, 0);
     cudaStream_t caller = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     const int nLanes = std::min<int>(ctx->batchLanes, nScenes);
-    while (static_cast<int>(ctx->lanes.size()) < nLanes) {
-        McContext* lane = nullptr;
-        const int rc = mcskin_cuda_context_create(ctx->device, &lane);
+    {
+        const int rc = ensure_lanes(ctx, nLanes);
         if (rc != MC_OK) return rc;
-        ctx->lanes.push_back(lane);
     }
     // lanes start after whatever the caller's stream did before (e.g. allocating the outputs)
     CU_TRY(cudaEventRecord(ctx->evCopy, caller));
     for (int k = 0; k < nLanes; ++k) {
         McContext* lane = ctx->lanes[k];
-        lane->shadeMode = ctx->shadeMode;
-        lane->forceAllActive = ctx->forceAllActive;
-        lane->waveQueueLevels = ctx->waveQueueLevels;
-        lane->waveBudgetBytes = ctx->waveBudgetBytes;
-        lane->recordBudgetBytes = ctx->recordBudgetBytes;
+        inherit_options(lane, ctx);
         lane->shadeBlocksPerSm = std::max(1, ctx->shadeBlocksPerSm / 2);  // several frames share the SMs
-        lane->primaryBlocksPerSm = ctx->primaryBlocksPerSm;
         CU_TRY(cudaStreamWaitEvent(lane->stream, ctx->evCopy, 0));
     }
     for (int i = 0; i < nScenes; ++i) {
@@ -824,6 +1090,22 @@ int32_t mcskin_cuda_background(const McScene* scene, const McConfig* cfg, int32_
     if ((rc = st.up(nullptr, sizeof(float4) * n, &dO)) != MC_OK) return rc;
     launch_background(ctx->prep.frame, static_cast<float*>(dU), n, static_cast<float4*>(dO), ctx->stream);
     return st.down(out, dO, sizeof(float4) * n);
+}
+
+int32_t mcskin_cuda_sincos(int32_t device, const float* angles, int32_t n, float* outSin, float* outCos) {
+    if (n < 0 || (n > 0 && (!angles || !outSin || !outCos))) return fail(MC_ERR_INVALID, "sincos: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = shared_context(device, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void *dA, *dS, *dC;
+    if ((rc = st.up(angles, sizeof(float) * n, &dA)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(float) * n, &dS)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(float) * n, &dC)) != MC_OK) return rc;
+    launch_sincos(static_cast<float*>(dA), n, static_cast<float*>(dS), static_cast<float*>(dC), ctx->stream);
+    if ((rc = st.down(outSin, dS, sizeof(float) * n)) != MC_OK) return rc;
+    return st.down(outCos, dC, sizeof(float) * n);
 }
 
 int32_t mcskin_cuda_aov(const McScene* scene, const McConfig* cfg, int32_t device, int32_t* outTriId) {

@@ -45,7 +45,7 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 }
 __device__ __forceinline__ float mt_canonical(uint32_t u) {
     const float r = __uint2float_rn(u) * 2.3283064365386963e-10f;  // exact scaling by 2^-32
-    return (r >= 1.0f) ? __uint_as_float(0x3f7fffffu) : r;
+    return fminf(r, __uint_as_float(0x3f7fffffu));  // r <= 1; only r == 1 is replaced
 }
 
 // ---- (b) fresh engine, first outputs only -------------------------------------
@@ -64,8 +64,15 @@ __device__ __forceinline__ uint32_t mt_seed_word397(uint32_t word1) {
 // (83 %) with the FMA pipe at 27 %.  Here the index lives in a register that is advanced with a
 // multiply-add by a run-time 1 (`one`, opaque to the compiler), so every step is two ALU and two
 // FMA-pipe instructions, the index update off the dependent chain.
+// Variant 4 (straight-line code, the step index an immediate addend of the IMAD: SHF + LOP3 + IMAD
+// per step) measured fastest on B200; the IMAD.HI forms (1-3) lose more on the FMA pipe than they
+// take off the ALU pipe.
+#ifndef MCSKIN_LCG_VARIANT
+#define MCSKIN_LCG_VARIANT 4
+#endif
 __device__ __forceinline__ uint32_t mt_seed_word397_balanced(uint32_t word1, uint32_t one) {
     uint32_t x = word1;
+#if MCSKIN_LCG_VARIANT == 0
     uint32_t i = 2u * one;
 #pragma unroll 12
     for (int k = 2; k <= kMtM; ++k) {
@@ -73,6 +80,43 @@ __device__ __forceinline__ uint32_t mt_seed_word397_balanced(uint32_t word1, uin
         asm("mad.lo.u32 %0, %1, 1812433253, %2;" : "=r"(x) : "r"(y), "r"(i));
         asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(i) : "r"(one));
     }
+#elif MCSKIN_LCG_VARIANT == 1
+    // x >> 30 as the high word of x * 4 (IMAD.HI, FMA pipe): one ALU and three FMA-pipe instructions per step
+    uint32_t i = 2u * one;
+#pragma unroll 12
+    for (int k = 2; k <= kMtM; ++k) {
+        const uint32_t y = x ^ __umulhi(x, 4u);
+        asm("mad.lo.u32 %0, %1, 1812433253, %2;" : "=r"(x) : "r"(y), "r"(i));
+        asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(i) : "r"(one));
+    }
+#elif MCSKIN_LCG_VARIANT == 2
+    // alternate the two forms: 3 ALU + 5 FMA-pipe instructions per two steps
+    uint32_t i = 2u * one;
+#pragma unroll 6
+    for (int k = 2; k <= kMtM; k += 2) {
+        uint32_t y = x ^ (x >> 30);
+        asm("mad.lo.u32 %0, %1, 1812433253, %2;" : "=r"(x) : "r"(y), "r"(i));
+        asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(i) : "r"(one));
+        y = x ^ __umulhi(x, 4u);
+        asm("mad.lo.u32 %0, %1, 1812433253, %2;" : "=r"(x) : "r"(y), "r"(i));
+        asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(i) : "r"(one));
+    }
+#elif MCSKIN_LCG_VARIANT == 3
+    // straight-line: the index is an immediate addend of the IMAD, three instructions per step
+    const uint32_t a = 1812433253u * one;
+#pragma unroll
+    for (int k = 2; k <= kMtM; ++k) {
+        const uint32_t y = (k & 1) ? (x ^ __umulhi(x, 4u)) : (x ^ (x >> 30));
+        x = y * a + static_cast<uint32_t>(k);
+    }
+#elif MCSKIN_LCG_VARIANT == 4
+    const uint32_t a = 1812433253u * one;
+#pragma unroll
+    for (int k = 2; k <= kMtM; ++k) {
+        const uint32_t y = x ^ (x >> 30);
+        x = y * a + static_cast<uint32_t>(k);
+    }
+#endif
     return x;
 }
 

@@ -31,9 +31,52 @@ __device__ __forceinline__ Ray camera_ray(const DevFrame& fr, float u, float v) 
     return r;
 }
 
-// sinf/cosf of a float angle.  TODO(parity): glibc-exact double-precision evaluation.
-__device__ __forceinline__ void sincos_ref(float a, float* s, float* c) {
-    sincosf(a, s, c);
+// sinf / cosf of a float angle, bit-identical to glibc 2.39's sinf / cosf / sincosf on an
+// x86-64 host with FMA (the variant its ifunc resolver picks on every CPU since Haswell / Zen):
+// the angle is widened to double, reduced by a multiple of pi/2 with one fused step, and the
+// result is a degree-7 / degree-8 polynomial in double rounded once to float (glibc
+// sysdeps/ieee754/flt-32/s_sincosf.h, sincosf_poly, reduce_fast; coefficients are
+// __sincosf_table's).  Every a + b*c of that source is a fused multiply-add in the host binary
+// (gcc contracts them under -mfma), hence the explicit fma() calls; the plain products stay
+// separate (--fmad=false).  Checked on the host against libm for all 1.12e9 floats in [0, 120)
+// (tests/test_host_side.py keeps a sampled version of that check).  |angle| >= 120, inf and NaN
+// (never produced here: angles are 2*pi*u, u in [0,1)) take CUDA's sincosf.
+__device__ __forceinline__ void sincos_ref(float a, float* sn, float* cs) {
+    const uint32_t top12 = (__float_as_uint(a) >> 20) & 0x7ffu;
+    if (top12 > 0x42eu) {  // |a| >= 120: out of the fast-reduction range
+        sincosf(a, sn, cs);
+        return;
+    }
+    if (top12 < 0x398u) {  // |a| < 2^-12
+        *sn = a;
+        *cs = 1.0f;
+        return;
+    }
+    double x = static_cast<double>(a);
+    double xs = x;
+    int n = 0;
+    if (top12 >= 0x3f4u) {  // |a| >= pi/4: x -= n * pi/2, n = round(x * 2/pi)
+        const double r = x * 0x1.45F306DC9C883p+23;
+        n = (__double2int_rz(r) + 0x800000) >> 24;
+        x = fma(-static_cast<double>(n), 0x1.921FB54442D18p0, x);
+        xs = ((n + 1) & 2) ? -x : x;  // sign[n & 3] = {1, -1, -1, 1}
+    }
+    const bool flipCos = (n & 2) != 0;  // second table: cosine coefficients negated
+    const double c0 = flipCos ? -0x1p0 : 0x1p0;
+    const double c1 = flipCos ? 0x1.ffffffd0c621cp-2 : -0x1.ffffffd0c621cp-2;
+    const double c2 = flipCos ? -0x1.55553e1068f19p-5 : 0x1.55553e1068f19p-5;
+    const double c3 = flipCos ? 0x1.6c087e89a359dp-10 : -0x1.6c087e89a359dp-10;
+    const double c4 = flipCos ? -0x1.99343027bf8c3p-16 : 0x1.99343027bf8c3p-16;
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double x2 = x * x;
+    const double x3 = xs * x2, x4 = x2 * x2;
+    const double sq = fma(x2, s3, s2), cq = fma(x2, c4, c3), cl = fma(x2, c1, c0);
+    const double x5 = x3 * x2, x6 = x4 * x2;
+    const double sl = fma(x3, s1, xs), cm = fma(x4, c2, cl);
+    const float fs = static_cast<float>(fma(x5, sq, sl));
+    const float fc = static_cast<float>(fma(x6, cq, cm));
+    *sn = (n & 1) ? fc : fs;
+    *cs = (n & 1) ? fs : fc;
 }
 
 // generateDOFRay; r1, r2 are the two lens draws that follow the jitter draws.

@@ -59,6 +59,10 @@ struct DevFrame {
     int draws_per_sample;     // 0 (spp==1, no DOF), 2 (jitter or lens), 4 (jitter + lens)
     float inv_spp;            // 1.0f / float(spp) (tile_renderer.cpp:122)
     float width_f, height_f, aspect;
+    // 1.0f / width_f, 1.0f / height_f rounded to nearest on the host: operands of the exact
+    // quotient in sample_uv (valid when uv_recip != 0, i.e. both sizes are in 1..65535)
+    float inv_width_f, inv_height_f;
+    int uv_recip;
     // camera (camera.cpp:10-16 evaluated once on the host)
     float cam_pos[3], cam_fwd[3], cam_right[3], cam_up[3];
     float half_w, half_h;

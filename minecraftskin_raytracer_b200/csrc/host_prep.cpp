@@ -127,6 +127,9 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
     f.inv_spp = 1.0f / static_cast<float>(f.spp);
     f.width_f = static_cast<float>(cfg.width);
     f.height_f = static_cast<float>(cfg.height);
+    f.uv_recip = (cfg.width >= 1 && cfg.width <= 65535 && cfg.height >= 1 && cfg.height <= 65535) ? 1 : 0;
+    f.inv_width_f = f.uv_recip ? 1.0f / f.width_f : 0.0f;
+    f.inv_height_f = f.uv_recip ? 1.0f / f.height_f : 0.0f;
     f.aspect = aspectOverride > 0.0f ? aspectOverride
                                      : static_cast<float>(cfg.width) / static_cast<float>(cfg.height);
 
@@ -359,3 +362,51 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
 }
 
 }  // namespace mcskin
+
+// Host model of the device's sincos_ref (dev_shade.cuh): glibc 2.39 sincosf as built for x86-64 with
+// FMA.  Same operations in the same order; std::fma is a correctly rounded fused multiply-add
+// whether or not this translation unit is compiled with -mfma.
+extern "C" void mcskin_sincos_model(const float* angles, int32_t n, float* outSin, float* outCos) {
+    for (int32_t i = 0; i < n; ++i) {
+        const float a = angles[i];
+        uint32_t bits;
+        std::memcpy(&bits, &a, sizeof(bits));
+        const uint32_t top12 = (bits >> 20) & 0x7ffu;
+        if (top12 > 0x42eu) {
+            outSin[i] = std::sin(a);
+            outCos[i] = std::cos(a);
+            continue;
+        }
+        if (top12 < 0x398u) {
+            outSin[i] = a;
+            outCos[i] = 1.0f;
+            continue;
+        }
+        double x = static_cast<double>(a), xs = x;
+        int nq = 0;
+        if (top12 >= 0x3f4u) {
+            const double r = x * 0x1.45F306DC9C883p+23;
+            nq = (static_cast<int32_t>(r) + 0x800000) >> 24;
+            x = std::fma(-static_cast<double>(nq), 0x1.921FB54442D18p0, x);
+            xs = ((nq + 1) & 2) ? -x : x;
+        }
+        const bool flipCos = (nq & 2) != 0;
+        const double c0 = flipCos ? -0x1p0 : 0x1p0;
+        const double c1 = flipCos ? 0x1.ffffffd0c621cp-2 : -0x1.ffffffd0c621cp-2;
+        const double c2 = flipCos ? -0x1.55553e1068f19p-5 : 0x1.55553e1068f19p-5;
+        const double c3 = flipCos ? 0x1.6c087e89a359dp-10 : -0x1.6c087e89a359dp-10;
+        const double c4 = flipCos ? -0x1.99343027bf8c3p-16 : 0x1.99343027bf8c3p-16;
+        const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+        // volatile-free, but every product below is a separate statement: this file is built with
+        // -ffp-contract=off, so only the std::fma calls fuse
+        const double x2 = x * x;
+        const double x3 = xs * x2, x4 = x2 * x2;
+        const double sq = std::fma(x2, s3, s2), cq = std::fma(x2, c4, c3), cl = std::fma(x2, c1, c0);
+        const double x5 = x3 * x2, x6 = x4 * x2;
+        const double sl = std::fma(x3, s1, xs), cm = std::fma(x4, c2, cl);
+        const float fs = static_cast<float>(std::fma(x5, sq, sl));
+        const float fc = static_cast<float>(std::fma(x6, cq, cm));
+        outSin[i] = (nq & 1) ? fc : fs;
+        outCos[i] = (nq & 1) ? fs : fc;
+    }
+}

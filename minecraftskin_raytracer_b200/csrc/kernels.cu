@@ -39,7 +39,7 @@ __device__ __forceinline__ TileGeom tile_geom(const DevFrame& fr, const BandView
     g.y = ty * fr.tile_size;
     g.w = min(fr.tile_size, fr.width - g.x);
     g.h = min(fr.tile_size, fr.height - g.y);
-    g.bandRow0 = localRow * fr.tile_size;
+    g.bandRow0 = (band.out_first_row + localRow * band.out_row_stride) * fr.tile_size;
     g.localIndex = localTile;
     return g;
 }
@@ -595,6 +595,121 @@ k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, co
     }
 }
 
+// The same pass with the sampling pattern known at compile time: SPP jittered samples, no lens
+// draws (2 stream words per sample), gradient or flat background.  A pixel's SPP*2 words are then
+// one contiguous run of the skewed ring (SPP*2 divides 32), so the sample loop unrolls into
+// loads at constant offsets, the frame constants live in registers, and the hit test — needed
+// only inside the projected bounds of the figure — is a second, rolled loop that stops at the
+// first sample that hits.  Arithmetic per sample is that of k_primary_pix, operation for operation.
+template <int SPP, bool GRADIENT>
+__global__ void __launch_bounds__(kBlockThreads)
+k_primary_pix_fixed(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list,
+                    const uint32_t* __restrict__ tileStates, const int parts) {
+    constexpr unsigned int kWords = SPP * 2;
+    static_assert(kWords <= 32 && 32 % kWords == 0, "a pixel's words must not straddle a 32-word ring group");
+    __shared__ __align__(8) uint64_t stageBar;
+    PixStreamSmem* mt = reinterpret_cast<PixStreamSmem*>(g_pixSmem);
+    unsigned char* sceneSmem = g_pixSmem + ((sizeof(PixStreamSmem) + 15) & ~size_t(15));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tileIndex = blockIdx.x / parts, part = blockIdx.x - tileIndex * parts;
+    const TileGeom tg = tile_geom(fr, band, tileIndex);
+    const int nPix = tg.w * tg.h;
+    if (part * kBlockThreads >= nPix) return;
+
+    const bool tileCanHit = !fr.rect_valid || !(tg.x > fr.rect_x1 || tg.x + tg.w - 1 < fr.rect_x0 ||
+                                                tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
+    if (tileCanHit) stage_bulk(sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(sceneSmem, fp.texels, fr);
+    {
+        const uint32_t* st = tileStates + static_cast<size_t>(tileIndex) * kMtN;
+        for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = st[i];
+        __syncthreads();
+    }
+    int which = 0;
+    unsigned int produced = 0u;
+    const bool wPow2 = (tg.w & (tg.w - 1)) == 0;
+    const int lgW = 31 - __clz(tg.w);
+    const float W = fr.width_f, H = fr.height_f, rW = fr.inv_width_f, rH = fr.inv_height_f;
+    const float gscale = fr.gradient_scale;
+    const float c0 = fr.bg_center[0], c1 = fr.bg_center[1], c2 = fr.bg_center[2];
+    const float e0 = fr.bg_edge[0], e1 = fr.bg_edge[1], e2 = fr.bg_edge[2];
+
+    for (int q0 = part * kBlockThreads; q0 < nPix; q0 += parts * kBlockThreads) {
+        {
+            const unsigned int first = static_cast<unsigned int>(q0) * kWords;
+            const unsigned int need = static_cast<unsigned int>(min(nPix, q0 + kBlockThreads)) * kWords;
+            while (produced + kMtN <= first) {
+                pix_stream_block<false>(mt, which, produced);
+                which ^= 1;
+                produced += kMtN;
+            }
+            while (produced < need) {
+                pix_stream_block<true>(mt, which, produced);
+                which ^= 1;
+                produced += kMtN;
+            }
+        }
+        const int q = q0 + warp * 32 + lane;
+        const bool valid = q < nPix;
+        const int ly = wPow2 ? (q >> lgW) : (q / tg.w);
+        const int lx = q - ly * tg.w;
+        const int px = tg.x + lx, py = tg.y + ly;
+        const bool pixelCanHit = valid && tileCanHit &&
+                                 (!fr.rect_valid || (px >= fr.rect_x0 && px <= fr.rect_x1 && py >= fr.rect_y0 && py <= fr.rect_y1));
+        const float* draws = mt->ring + pix_ring_slot(static_cast<unsigned int>(q) * kWords);
+        const float fx = static_cast<float>(px), fy = static_cast<float>(py);
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (valid) {
+#pragma unroll
+            for (int s = 0; s < SPP; ++s) {
+                const float u = div_by_size(fx + draws[2 * s], W, rW);      // tile_renderer.cpp:95-96
+                const float v = div_by_size(fy + draws[2 * s + 1], H, rH);
+                if (GRADIENT) {  // RayTracer::backgroundColor, raytracer.cpp:16-34
+                    const float cx = u - 0.5f, cy = v - 0.5f;
+                    const float dist = clamp01(sqrtf(cx * cx + cy * cy) * 2.0f * gscale);
+                    const float t = dist * dist;
+                    const float k = 1.0f - t;
+                    acc.x += c0 * k + e0 * t;
+                    acc.y += c1 * k + e1 * t;
+                    acc.z += c2 * k + e2 * t;
+                    acc.w += 1.0f;
+                } else {
+                    acc = add4(acc, flat_background(fr));
+                }
+            }
+        }
+        bool hit = false;
+        if (pixelCanHit) {
+            for (int s = 0; s < SPP && !hit; ++s) {
+                const float u = div_by_size(fx + draws[2 * s], W, rW);
+                const float v = div_by_size(fy + draws[2 * s + 1], H, rH);
+                const Ray ray = camera_ray(fr, u, v);
+                hit = !misses_cull_box(fr, ray) && any_hit(sc, ray);
+            }
+        }
+        const unsigned int outIndex = static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + px;
+        if (valid && !hit) store_pixel(band, outIndex, scale4(acc, fr.inv_spp));
+
+        const unsigned int hitMask = __ballot_sync(kFullMask, hit);
+        if (hitMask) {  // work-list slots: one atomic per warp
+            unsigned int base = 0u;
+            if (lane == 0) base = atomicAdd(list.count, static_cast<unsigned int>(__popc(hitMask)));
+            base = __shfl_sync(kFullMask, base, 0);
+            if (hit) {
+                const unsigned int slot = base + __popc(hitMask & ((1u << lane) - 1u));
+                if (slot < list.capacity) {
+                    list.slot_pixel[slot] = make_uint2(outIndex, static_cast<unsigned int>(px) | (static_cast<unsigned int>(py) << 16));
+                    float2* rec = reinterpret_cast<float2*>(list.records + static_cast<size_t>(slot) * kWords);
+#pragma unroll
+                    for (int s = 0; s < SPP; ++s) rec[s] = make_float2(draws[2 * s], draws[2 * s + 1]);
+                }
+            }
+        }
+        if (q0 + parts * kBlockThreads < nPix) __syncthreads();  // the ring is rewritten by the next round
+    }
+}
+
 #ifndef MCSKIN_SHADE_MIN_BLOCKS
 #define MCSKIN_SHADE_MIN_BLOCKS 3
 #endif
@@ -758,6 +873,15 @@ __global__ void k_background(const DevFrame fr, const float* uv, int n, float4* 
     out[i] = fr.use_config ? config_background(fr, uv[2 * i], uv[2 * i + 1]) : flat_background(fr);
 }
 
+__global__ void k_sincos(const float* angles, int n, float* outSin, float* outCos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float sn, cs;
+    sincos_ref(angles[i], &sn, &cs);
+    outSin[i] = sn;
+    outCos[i] = cs;
+}
+
 // hit mask + (box, face) id of the pinhole ray through each pixel centre
 __global__ void k_aov(const DevFrame fr, const FramePointers fp, int* outTriId) {
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
@@ -780,10 +904,10 @@ static int log2_if_warp_spp(int spp) {
     return -1;
 }
 
-void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                    int classify, uint32_t* tileStates, int primaryTargetBlocks, cudaStream_t stream) {
+bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
+                    int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
-    if (nTiles <= 0) return;
+    if (nTiles <= 0) return false;
     // the warp / pixel variants index a tile's stream with 32-bit integers
     const long long tileDraws = static_cast<long long>(fr.tile_size) * fr.tile_size * fr.spp * (fr.draws_per_sample > 0 ? fr.draws_per_sample : 1);
     const bool small = tileDraws < (1ll << 30);
@@ -794,19 +918,37 @@ void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView&
         static bool attrSet = false;
         if (!attrSet) {
             cudaFuncSetAttribute(k_primary_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(k_primary_pix_fixed<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(k_primary_pix_fixed<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(k_primary_pix_fixed<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(k_primary_pix_fixed<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
             attrSet = true;
         }
-        if (fr.draws_per_sample > 0) k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates);
+        if (fr.draws_per_sample > 0 && seedTiles) k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates);
         // enough blocks to fill the machine a few times over, at most one block per round of 256 pixels
         const int roundsPerTile = (fr.tile_size * fr.tile_size + kBlockThreads - 1) / kBlockThreads;
         int parts = (primaryTargetBlocks + nTiles - 1) / nTiles;
         parts = parts < 1 ? 1 : (parts > roundsPerTile ? roundsPerTile : parts);
-        k_primary_pix<<<nTiles * parts, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
+        const dim3 grid(nTiles * parts);
+        // jitter only (no lens draws), 4 or 16 spp, quotients by the host reciprocals: compile-time sample loop
+        const bool fixedForm = fr.draws_per_sample == 2 && fr.spp > 1 && !fr.dof_on && fr.uv_recip;
+        if (fixedForm && fr.spp == 16 && fr.gradient_bg)
+            k_primary_pix_fixed<16, true><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
+        else if (fixedForm && fr.spp == 16)
+            k_primary_pix_fixed<16, false><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
+        else if (fixedForm && fr.spp == 4 && fr.gradient_bg)
+            k_primary_pix_fixed<4, true><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
+        else if (fixedForm && fr.spp == 4)
+            k_primary_pix_fixed<4, false><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
+        else
+            k_primary_pix<<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
+        return fr.draws_per_sample > 0;
     } else if (classify && lg >= 0) {
         k_primary_warp<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, lg);
     } else {
         k_primary_cta<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, classify);
     }
+    return false;
 }
 
 void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
@@ -852,6 +994,9 @@ void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out
 }
 void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream) {
     if (n > 0) k_background<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, uv, n, out);
+}
+void launch_sincos(const float* angles, int n, float* outSin, float* outCos, cudaStream_t stream) {
+    if (n > 0) k_sincos<<<blocks_for(n), kBlockThreads, 0, stream>>>(angles, n, outSin, outCos);
 }
 void launch_aov(const DevFrame& fr, const FramePointers& fp, int* outTriId, cudaStream_t stream) {
     if (fr.width <= 0 || fr.height <= 0) return;

@@ -15,8 +15,12 @@ constexpr unsigned int kMaxSceneSmemBytes = 40u * 1024u;
 // Which tile rows of the frame a launch covers, and where its pixels land.
 // Local tile row r is frame tile row first_tile_row + r*tile_row_stride; the output
 // image is the compact band of those rows (tile_size pixel rows each, last clipped).
+// Local tile row r lands at tile row out_first_row + r*out_row_stride of the output image
+// (0 and 1 for a compact band; a frame split over several streams writes interleaved rows of
+// one shared band image).
 struct BandView {
     int first_tile_row, tile_row_stride, n_tile_rows;
+    int out_first_row, out_row_stride;
     float4* out_f32;  // may be null
     uchar4* out_u8;   // may be null
 };
@@ -39,9 +43,12 @@ struct FramePointers {
 // resolve of pixels no sample of which hits, work records for the rest.
 // classify == 0 puts every pixel on the work list (used for spp > 256 and for tests).
 // tileStates: scratch of 624 words per tile of the band (seeded engine states).
+// seedTiles: false when tileStates already holds the states of exactly these tiles (they depend on
+// the image width, the tile size and the tile rows of the band only, not on the scene).
 // primaryTargetBlocks: tiles are split over several blocks until the launch has about this many.
-void launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                    int classify, uint32_t* tileStates, int primaryTargetBlocks, cudaStream_t stream);
+// Returns true when tileStates holds the seeded engines of the band's tiles afterwards.
+bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
+                    int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, cudaStream_t stream);
 // Shading pass: full integrator for every sample of every listed pixel, ordered resolve.
 // Megakernel form of the shading pass over the listed pixels from `firstSlot` on.
 // variant 1: block-synchronous groups; variant 2: warp-autonomous groups with dynamic
@@ -66,6 +73,7 @@ void launch_ambient_occlusion(const DevFrame& fr, const FramePointers& fp, const
                               cudaStream_t stream);
 void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out, cudaStream_t stream);
 void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream);
+void launch_sincos(const float* angles, int n, float* outSin, float* outCos, cudaStream_t stream);
 void launch_aov(const DevFrame& fr, const FramePointers& fp, int* outTriId, cudaStream_t stream);
 
 }  // namespace mcskin

@@ -12,6 +12,23 @@ namespace mcskin {
 namespace {
 
 constexpr int kWfThreads = 256;
+// Minimum resident blocks per SM asked of the compiler (i.e. register caps), from a sweep on B200:
+// 4 blocks (64 registers) for the primary-hit and the queued shade kernels (+1.3 % frame rate),
+// compiler's choice for the shadow kernel (59 registers; capping it at 48 was slower) and for
+// the in-thread tail form of the shade kernel (128).
+#ifndef MCSKIN_WF_HIT0_MIN_BLOCKS
+#define MCSKIN_WF_HIT0_MIN_BLOCKS 4
+#endif
+#ifndef MCSKIN_WF_SHADE_MIN_BLOCKS
+#define MCSKIN_WF_SHADE_MIN_BLOCKS 4
+#endif
+#define WF_HIT0_BOUNDS __launch_bounds__(kWfThreads, MCSKIN_WF_HIT0_MIN_BLOCKS)
+#ifdef MCSKIN_WF_SHADOW_MIN_BLOCKS
+#define WF_SHADOW_BOUNDS __launch_bounds__(kWfThreads, MCSKIN_WF_SHADOW_MIN_BLOCKS)
+#else
+#define WF_SHADOW_BOUNDS __launch_bounds__(kWfThreads)
+#endif
+#define WF_SHADE_BOUNDS __launch_bounds__(kWfThreads, QUEUED ? MCSKIN_WF_SHADE_MIN_BLOCKS : 2)
 
 __device__ __forceinline__ unsigned int pack_hit(const Hit& h) {
     return static_cast<unsigned int>(h.box & 0xffff) | (static_cast<unsigned int>(h.face) << 16) |
@@ -50,7 +67,7 @@ __device__ __forceinline__ void enqueue_hit(const HitQueueView& q, unsigned int*
 
 
 // ---------------------------------------------------------------- primary hits
-__global__ void __launch_bounds__(kWfThreads)
+__global__ void WF_HIT0_BOUNDS
 k_wf_hit0(const DevFrame fr, const FramePointers fp, const ActiveList list, const WaveView wv) {
     __shared__ __align__(8) uint64_t stageBar;
     unsigned int count = *list.count;
@@ -145,7 +162,8 @@ k_wf_clear_lit(const WaveView wv, const int depth) {
 }
 
 // ---------------------------------------------------------------- one shadow ray per thread
-__global__ void __launch_bounds__(kWfThreads)
+template <bool PREFETCH>
+__global__ void WF_SHADOW_BOUNDS
 k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
     __shared__ __align__(8) uint64_t stageBar;
     unsigned int n = wv.qCount[depth];
@@ -161,22 +179,46 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
     const bool rPow2 = (R & (R - 1)) == 0;
     const int lgR = 31 - __clz(R);
 
-    for (unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + threadIdx.x; t < nRays;
-         t += static_cast<unsigned long long>(gridDim.x) * kWfThreads) {
-        const unsigned int i = rPow2 ? static_cast<unsigned int>(t >> lgR) : static_cast<unsigned int>(t / R);
-        const int k = static_cast<int>(t - static_cast<unsigned long long>(i) * R);
-        const float4 g = q.geo[i];
-        const Hit h = unpack_hit(g, make_float4(0.f, 0.f, 0.f, 0.f));
-        V3 normal = hit_normal(sc, h);
-        V3 target = lightCentre;
+    // One ray per trip of a grid-stride loop; the inputs of the next trip (hit record, light sample,
+    // box mask — three dependent global loads) are fetched before the current ray is traced, so
+    // their latency overlaps the slab tests instead of heading every trip.
+    struct RayIn {
+        float4 g;
+        float tx, ty, tz;
+        uint32_t allow;
+        unsigned int i;
+    };
+    auto fetch = [&](unsigned long long t) {
+        RayIn in;
+        in.i = rPow2 ? static_cast<unsigned int>(t >> lgR) : static_cast<unsigned int>(t / R);
+        const int k = static_cast<int>(t - static_cast<unsigned long long>(in.i) * R);
+        in.g = q.geo[in.i];
+        in.tx = lightCentre.x; in.ty = lightCentre.y; in.tz = lightCentre.z;
+        in.allow = 0xffffffffu;
         if (soft) {
-            const float* lp = wv.lightPos + (static_cast<size_t>(i) * R + k) * 3;
-            target = mk3(lp[0], lp[1], lp[2]);
-        } else {
-            normal = normalize3(normal);  // shade() hands isInShadow the normalised normal (shading.cpp:69,78)
+            const float* lp = wv.lightPos + (static_cast<size_t>(in.i) * R + k) * 3;
+            in.tx = lp[0]; in.ty = lp[1]; in.tz = lp[2];
+            in.allow = wv.allow[in.i];
         }
-        const uint32_t allow = soft ? wv.allow[i] : 0xffffffffu;
-        if (!in_shadow_among(sc, h.p, normal, target, allow)) atomicAdd(&wv.lit[i], 1u);
+        return in;
+    };
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kWfThreads;
+    unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + threadIdx.x;
+    if (t >= nRays) return;
+    RayIn next{};
+    if (PREFETCH) next = fetch(t);
+    for (; t < nRays; t += stride) {
+        RayIn cur;
+        if (PREFETCH) {
+            cur = next;
+            if (t + stride < nRays) next = fetch(t + stride);
+        } else {
+            cur = fetch(t);
+        }
+        const Hit h = unpack_hit(cur.g, make_float4(0.f, 0.f, 0.f, 0.f));
+        V3 normal = hit_normal(sc, h);
+        if (!soft) normal = normalize3(normal);  // shade() hands isInShadow the normalised normal (shading.cpp:69,78)
+        if (!in_shadow_among(sc, h.p, normal, mk3(cur.tx, cur.ty, cur.tz), cur.allow)) atomicAdd(&wv.lit[cur.i], 1u);
     }
 }
 
@@ -186,9 +228,14 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
 //            too few to be worth three launches per level: each thread takes one queued hit and
 //            follows its chain to the end, evaluating shadow rays in place.  The queue is compact,
 //            so warps start full and only thin out at the deepest, rarest levels.
-__global__ void __launch_bounds__(kWfThreads)
+// QUEUED: the visibility comes from k_wf_shadow's counters and bounce hits go to the next queue
+// (the lean form: no shadow code at all); otherwise shadows are evaluated in place, and with
+// tail != 0 the whole remaining chain is.
+template <bool QUEUED>
+__global__ void WF_SHADE_BOUNDS
 k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth,
-           const int tail) {
+           const int tailArg) {
+    const int tail = QUEUED ? 0 : tailArg;
     __shared__ __align__(8) uint64_t stageBar;
     unsigned int n = wv.qCount[depth];
     if (n > wv.pathCapacity) n = wv.pathCapacity;
@@ -221,7 +268,7 @@ k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const i
                 const float4 tex = hit_texel(sc, h);
                 const V3 viewDir = normalize3(rayO - P);
                 float vis;
-                if (!tail && wv.shadowMode != kShadowInThread) {
+                if (QUEUED) {
                     vis = static_cast<float>(wv.lit[i]) / static_cast<float>(wv.shadowRays);
                     if (wv.shadowMode == kShadowHard) vis = wv.lit[i] ? 1.0f : 0.0f;
                 } else if (cfg && fr.soft_on) {
@@ -385,6 +432,8 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
     w.shadowRays = w.shadowMode == kShadowSoft ? fr.shadow_samples : (w.shadowMode == kShadowHard ? 1 : 0);
     w.gridBlocks = gridBlocks;
     w.queueLevels = 3;
+    w.deepGridDiv = 1;
+    w.shadowPrefetch = 0;
     unsigned char* p = static_cast<unsigned char*>(base);
     size_t off = 0;
     auto take = [&](size_t n) {
@@ -423,8 +472,10 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
         const int queued = std::min(wv.levels + 1, std::max(1, wv.queueLevels));
         for (int depth = 0; depth < queued; ++depth) {
             const int which = depth & 1;
-            // queues shrink roughly tenfold per bounce: do not pay for a full grid of idle blocks
-            const int g = depth == 0 ? grid : (depth == 1 ? std::max(1, grid / 4) : std::max(1, grid / 8));
+            // Deeper queues are much shorter (~8 % of the primary hits at depth 1, then ~75 % of the
+            // previous level), but blocks beyond a queue's end return at once, and a short queue
+            // spread over every SM finishes sooner than one packed into a few resident blocks.
+            const int g = depth == 0 ? grid : std::max(1, grid / std::max(1, wv.deepGridDiv));
             if (wv.shadowMode == kShadowSoft) {
                 k_wf_seed<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
                 ++n;
@@ -433,14 +484,20 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
                 ++n;
             }
             if (wv.shadowMode != kShadowInThread) {
-                k_wf_shadow<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+                if (wv.shadowPrefetch)
+                    k_wf_shadow<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+                else
+                    k_wf_shadow<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
                 ++n;
             }
-            k_wf_shade<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0);
+            if (wv.shadowMode != kShadowInThread)
+                k_wf_shade<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0);
+            else
+                k_wf_shade<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0);
             ++n;
         }
         if (queued <= wv.levels) {
-            k_wf_shade<<<std::max(1, grid / 8), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, queued & 1, queued, 1);
+            k_wf_shade<false><<<std::max(1, grid / std::max(1, wv.deepGridDiv)), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, queued & 1, queued, 1);
             ++n;
         }
     }

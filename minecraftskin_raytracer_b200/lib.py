@@ -20,6 +20,9 @@ import os
 # MCSKIN_LIB selects an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = Path(os.environ.get("MCSKIN_LIB") or (Path(__file__).resolve().parent / "_lib" / "libmcskin_cuda.so"))
 
+# streams a frame's tile rows are dealt to by default (McContext::frameLanes in csrc/capi.cu)
+DEFAULT_FRAME_LANES = 2
+
 # every symbol include/mcskin_cuda.h declares
 EXPORTS = [
     "mcskin_config_defaults", "mcskin_generate_tiles", "mcskin_cuda_device_count", "mcskin_cuda_last_error",
@@ -29,7 +32,8 @@ EXPORTS = [
     "mcskin_cuda_context_sync", "mcskin_cuda_context_set_option", "mcskin_cuda_context_render_batch",
     "mcskin_cuda_intersect", "mcskin_cuda_trace", "mcskin_cuda_shade", "mcskin_cuda_in_shadow",
     "mcskin_cuda_soft_shadow", "mcskin_cuda_ambient_occlusion", "mcskin_cuda_generate_rays",
-    "mcskin_cuda_background", "mcskin_cuda_aov", "mcskin_build_skin_scene",
+    "mcskin_cuda_background", "mcskin_cuda_aov", "mcskin_build_skin_scene", "mcskin_cuda_sincos",
+    "mcskin_sincos_model",
 ]
 
 
@@ -305,6 +309,25 @@ def background(scene: FlatScene, cfg: McConfig, uv, use_config: bool = True, dev
     _check(_lib.mcskin_cuda_background(C.byref(cs), C.byref(cfg), C.c_int32(device), C.c_int32(int(use_config)),
                                        _ptr(uv, C.c_float), C.c_int32(len(uv)), _ptr(out, C.c_float)))
     return out
+
+
+def sincos(angles, device: int = 0):
+    """(sin, cos) of float32 angles as the kernels evaluate them (glibc-exact for |angle| < 120)."""
+    a = _f32(angles, (-1,))
+    sn = np.zeros(len(a), dtype=np.float32)
+    cs = np.zeros(len(a), dtype=np.float32)
+    _check(_lib.mcskin_cuda_sincos(C.c_int32(device), _ptr(a, C.c_float), C.c_int32(len(a)), _ptr(sn, C.c_float),
+                                   _ptr(cs, C.c_float)))
+    return sn, cs
+
+
+def sincos_model(angles):
+    """The device's sin/cos arithmetic evaluated on the host (needs no GPU)."""
+    a = _f32(angles, (-1,))
+    sn = np.zeros(len(a), dtype=np.float32)
+    cs = np.zeros(len(a), dtype=np.float32)
+    _lib.mcskin_sincos_model(_ptr(a, C.c_float), C.c_int32(len(a)), _ptr(sn, C.c_float), _ptr(cs, C.c_float))
+    return sn, cs
 
 
 def aov(scene: FlatScene, cfg: McConfig, device: int = 0) -> np.ndarray:

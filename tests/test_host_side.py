@@ -116,3 +116,45 @@ def test_synth_skin_is_deterministic():
     assert not np.array_equal(a, synth_skin(4))
     holes = a[..., 3] == 0
     assert 0.1 < holes[:16, 32:].mean() < 0.9 and not holes[:16, :32].any()   # only outer-layer blocks have holes
+
+
+def _libm_sincos(angles):
+    """sinf / cosf of the host's libm (what the reference calls per soft-shadow / lens / AO sample)."""
+    import ctypes.util
+    libm = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.sinf.restype = libm.cosf.restype = C.c_float
+    libm.sinf.argtypes = libm.cosf.argtypes = [C.c_float]
+    sn = np.array([libm.sinf(float(a)) for a in angles], dtype=np.float32)
+    cs = np.array([libm.cosf(float(a)) for a in angles], dtype=np.float32)
+    return sn, cs
+
+
+def _host_has_fma():
+    try:
+        return " fma " in Path("/proc/cpuinfo").read_text()
+    except OSError:
+        return False
+
+
+def sincos_test_angles(n=200_000, seed=7):
+    """Angles the path produces (2*pi*u for canonical draws u) plus the branch boundaries of the algorithm."""
+    rng = np.random.default_rng(seed)
+    u = (rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.float32) * np.float32(2.0**-32))
+    u = np.minimum(u, np.float32(0.99999994))
+    two_pi = np.float32(2.0) * np.float32(np.pi)
+    angles = [two_pi * u, rng.uniform(-119.9, 119.9, size=n // 4).astype(np.float32)]
+    edges = np.array([0.0, 2.0**-13, 2.0**-12, np.pi / 4, np.pi / 2, np.pi, 3 * np.pi / 2, 2 * np.pi, 119.99], dtype=np.float32)
+    for e in edges:  # every float within 64 ulps of each boundary
+        bits = np.float32(e).view(np.uint32).astype(np.int64) + np.arange(-64, 65)
+        angles.append(bits[bits >= 0].astype(np.uint32).view(np.float32))
+    return np.concatenate(angles).astype(np.float32)
+
+
+@pytest.mark.skipif(not _host_has_fma(), reason="glibc selects its non-FMA sinf/cosf on this CPU")
+def test_sincos_model_equals_libm(mclib):
+    """The restated glibc sincosf (host model of the device function) is bit-identical to libm's sinf/cosf."""
+    a = sincos_test_angles(60_000)
+    want_s, want_c = _libm_sincos(a)
+    got_s, got_c = mclib.sincos_model(a)
+    assert np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32))
+    assert np.array_equal(got_c.view(np.uint32), want_c.view(np.uint32))

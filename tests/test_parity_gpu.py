@@ -81,6 +81,28 @@ def test_in_shadow_exact(gpu, oracle):
     assert np.array_equal(got, want)
 
 
+def test_sincos_device_equals_host_model_and_libm(gpu):
+    """The device's sinf/cosf == its host model everywhere, == glibc's on an FMA host (bit for bit)."""
+    from tests.test_host_side import _host_has_fma, _libm_sincos, sincos_test_angles
+    a = sincos_test_angles(400_000)
+    got_s, got_c = gpu.sincos(a)
+    model_s, model_c = gpu.sincos_model(a)
+    assert np.array_equal(_bits(got_s), _bits(model_s)) and np.array_equal(_bits(got_c), _bits(model_c))
+    if _host_has_fma():
+        sub = a[:: max(1, len(a) // 50_000)]
+        want_s, want_c = _libm_sincos(sub)
+        s2, c2 = gpu.sincos(sub)
+        assert np.array_equal(_bits(s2), _bits(want_s)) and np.array_equal(_bits(c2), _bits(want_c))
+
+
+# With sinf/cosf bit-identical to the host's (FMA build of glibc) the sampled light points are the
+# reference's own, so shadow factors match exactly; on a host whose glibc picks the non-FMA
+# variant a last-ulp difference can move a shadow ray across an edge now and then.
+def _flip_budget():
+    from tests.test_host_side import _host_has_fma
+    return 0.0 if _host_has_fma() else 2e-3
+
+
 @pytest.mark.parametrize("samples", [2, 8, 64, 120])
 def test_soft_shadow(gpu, oracle, samples):
     scene = _scene(gpu, 1, "64x64", None)
@@ -88,10 +110,8 @@ def test_soft_shadow(gpu, oracle, samples):
     seeds = np.random.default_rng(2).integers(0, 2**32, size=len(hits), dtype=np.uint32)
     want = oracle.soft_shadow(scene, hits["point"], hits["normal"], seeds, samples)
     got = gpu.soft_shadow(scene, hits["point"], hits["normal"], seeds, samples)
-    # identical RNG stream; device sinf/cosf may differ from glibc in the last ulp, which can
-    # move a shadow ray across an edge: allow a vanishing fraction of single-sample flips
     differ = got != want
-    assert differ.mean() <= 2e-3, differ.mean()
+    assert differ.mean() <= _flip_budget(), differ.mean()
     assert np.abs(got - want).max() <= 1.0 / samples + 1e-6
 
 
@@ -103,7 +123,7 @@ def test_ambient_occlusion(gpu, oracle):
         want = oracle.ambient_occlusion(scene, hits["point"], hits["normal"], seeds, samples, 3.0)
         got = gpu.ambient_occlusion(scene, hits["point"], hits["normal"], seeds, samples, 3.0)
         differ = got != want
-        assert differ.mean() <= 2e-3, differ.mean()
+        assert differ.mean() <= _flip_budget(), differ.mean()
 
 
 def test_shade_matches(gpu, oracle):
@@ -140,6 +160,9 @@ RENDER_MODES = {
     "deep_queues": {"wave_queue_levels": 6},
     "shallow_queues": {"wave_queue_levels": 1},
     "split_tiles": {"primary_blocks_per_sm": 100000},     # every tile split over one block per 256-pixel round
+    "one_lane_no_graph": {"frame_lanes": 1, "use_graphs": 0, "cache_tile_seeds": 0},
+    "five_lanes_unstaggered": {"frame_lanes": 5, "stagger_lanes": 0},
+    "thin_deep_grids": {"wave_deep_grid_div": 8, "frame_lanes": 3},
 }
 
 
@@ -187,9 +210,15 @@ def _render_with_options(gpu, scene, cfg, opts):
         ctx.set_scene(scene, cfg)
         out = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.float32, device="cuda:0")
         torch.cuda.synchronize()
-        ctx.render_bands(0, 1, out.data_ptr(), 0, 0)
-        ctx.sync()
-        return out.cpu().numpy()
+        frames = []
+        for _ in range(3):  # direct launches, then the call that captures the graph, then a replay
+            out.zero_()
+            torch.cuda.synchronize()
+            ctx.render_bands(0, 1, out.data_ptr(), 0, 0)
+            ctx.sync()
+            frames.append(out.cpu().numpy())
+        assert np.array_equal(_bits(frames[0]), _bits(frames[1])) and np.array_equal(_bits(frames[0]), _bits(frames[2]))
+        return frames[2]
     finally:
         ctx.close()
 
@@ -222,6 +251,42 @@ def test_deterministic_run_to_run(gpu):
     a, _, _ = gpu.render(scene, cfg)
     b, _, _ = gpu.render(scene, cfg)
     assert np.array_equal(_bits(a), _bits(b))  # tests/test_tile_renderer_props.cpp:89-134
+
+
+def test_graph_replay_and_seed_cache_survive_interleaved_frames(gpu, oracle):
+    """A context replays a captured frame graph and keeps seeded tile engines between frames; other
+    frame sizes, scenes and partitions rendered in between must not leak into a later replay."""
+    import torch
+    scene_a, scene_b = _scene(gpu, 1, "64x64", "walking"), _scene(gpu, 7, "legacy", None)
+    cfg_a = make_config(width=160, height=192, samples_per_pixel=4, max_bounces=3)
+    cfg_b = make_config(width=160, height=128, samples_per_pixel=16, max_bounces=1)
+    want_a, want_b = oracle.render(scene_a, cfg_a), oracle.render(scene_b, cfg_a)
+    ctx = gpu.Context(0)
+    try:
+        out = torch.zeros((192, 160, 4), dtype=torch.float32, device="cuda:0")
+
+        def frame(scene, cfg, first=0, stride=1):
+            ctx.set_scene(scene, cfg)
+            out.zero_()
+            torch.cuda.synchronize()
+            ctx.render_bands(first, stride, out.data_ptr(), 0, 0)
+            ctx.sync()
+            return out.cpu().numpy()[: cfg.height]
+
+        first_a = frame(scene_a, cfg_a)
+        assert pixel_report(first_a, want_a, oracle.quantize)["within1"] >= 0.999
+        for _ in range(3):
+            assert np.array_equal(_bits(frame(scene_a, cfg_a)), _bits(first_a))      # capture, replay, replay
+        frame(scene_b, cfg_b)                                                        # other size and spp: reseeds the tiles
+        frame(scene_a, cfg_a, 1, 2)                                                  # other partition
+        assert np.array_equal(_bits(frame(scene_a, cfg_a)), _bits(first_a))
+        got_b = frame(scene_b, cfg_a)                                                # same frame shape, other scene
+        assert pixel_report(got_b, want_b, oracle.quantize)["within1"] >= 0.999
+        for _ in range(2):
+            assert np.array_equal(_bits(frame(scene_b, cfg_a)), _bits(got_b))
+        assert np.array_equal(_bits(frame(scene_a, cfg_a)), _bits(first_a))
+    finally:
+        ctx.close()
 
 
 def test_empty_scene_and_degenerate_sizes(gpu, oracle):
@@ -267,7 +332,7 @@ def test_cuda_vs_golden_reference_rays(gpu):
     for key, use_cfg in (("rays/trace_cfg", True), ("rays/trace_nocfg", False)):
         close = np.abs(gpu.trace(scene, cfg, rays[:1500], 0, use_cfg) - v[key]).max(axis=1) <= 1e-5
         assert close.mean() >= 0.998, key
-    assert (gpu.soft_shadow(scene, want["point"][keep], want["normal"][keep], v["rays/seeds"], 8) != v["rays/soft8"]).mean() <= 2e-3
+    assert (gpu.soft_shadow(scene, want["point"][keep], want["normal"][keep], v["rays/seeds"], 8) != v["rays/soft8"]).mean() <= _flip_budget()
     cam = gpu.generate_rays(scene, 16.0 / 9.0, v["rays/uv"])
     assert np.array_equal(_bits(cam["dir"]), _bits(v["rays/camera"]["dir"]))
     assert np.array_equal(_bits(gpu.background(scene, cfg, v["rays/uv"])), _bits(v["rays/background"]))
