@@ -98,11 +98,12 @@ struct McContext {
     int forceAllActive = 0;
     long long recordBudgetBytes = 1ll << 31;
     int shadeBlocksPerSm = 8;
-    int primaryBlocksPerSm = 9;              // split tiles over blocks until a launch has this many per SM
-    int waveQueueLevels = 3;                 // bounce depths handled by queues; deeper ones in-thread
+    int primaryBlocksPerSm = 2;              // split tiles over blocks only while a launch has fewer than this many per SM
+                                             // (every block of a split tile regenerates the tile's whole jitter stream)
+    int waveQueueLevels = 4;                 // bounce depths handled by queues; deeper ones in-thread
     int waveShadowPrefetch = 0;
     int waveDeepGridDiv = 1;                 // launches of depth >= 1 use shade grid / this
-    int frameLanes = 2;                      // a frame's tile rows are rendered on this many streams at once
+    int frameLanes = 3;                      // a frame's tile rows are rendered on this many streams at once
     bool isChild = false;                    // a lane of another context (never splits frames itself)
     // seeded tile engines kept from the previous frame: they depend on the image width, the tile
     // size and the tile rows of the band only (tile_renderer.cpp:78), not on the scene
@@ -118,8 +119,10 @@ struct McContext {
     bool tileSeedValid = false;
     int cacheTileSeeds = 1;
     int splitLastRender = 0;                 // lanes (beyond this context) used by the last render
-    int staggerLanes = 1;                    // lane k's primary pass starts when lane k-1's has finished
     cudaEvent_t evPrimaryDone = nullptr;     // (disable-timing) recorded after this lane's primary pass
+    cudaStream_t copyStream = nullptr;       // device -> host copies that overlap the shading pass
+    cudaEvent_t evFrameDone = nullptr;
+    int overlapCopyOut = 1;
     cudaEvent_t evUpload = nullptr;          // (disable-timing) recorded after the scene upload on ctx->stream
     unsigned long long seedGen = 0;          // bumped whenever tileStates is rewritten outside a graph
     bool capturing = false;                  // the launches are being captured into a graph: no timing events
@@ -198,8 +201,7 @@ int band_pixel_rows(const DevFrame& f, int first, int stride) {
 // device memory.  scn: the context whose scene (prepared frame, box and texel buffers) is rendered;
 // local tile row r is written at tile row outFirst + r*outStride of the output image.
 int render_bands_lane(McContext* ctx, const McContext* scn, int first, int stride, int outFirst, int outStride,
-                      float4* outF32, uchar4* outU8, cudaStream_t stream, cudaEvent_t waitBeforePrimary = nullptr,
-                      cudaEvent_t recordAfterPrimary = nullptr) {
+                      float4* outF32, uchar4* outU8, cudaStream_t stream) {
     const DevFrame& f = scn->prep.frame;
     const int nRows = local_tile_rows(f, first, stride);
     ctx->chunksLastRender = 0;
@@ -290,11 +292,14 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
             CU_TRY(cudaMemcpyAsync(list.count, &list.capacity, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
         }
         if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
-        if (c == 0 && waitBeforePrimary) CU_TRY(cudaStreamWaitEvent(stream, waitBeforePrimary, 0));
         const bool seeded = launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
                                            seedTiles, ctx->smCount * ctx->primaryBlocksPerSm, stream);
         ctx->tileSeedValid = seedsCacheable && seeded;
-        if (c == nChunks - 1 && recordAfterPrimary) CU_TRY(cudaEventRecord(recordAfterPrimary, stream));
+        // from here on every pixel of the band outside the figure's screen rectangle is final: the host
+        // copy of the image may start (render_host).  Inside a capture this must be a real event-record
+        // node, visible to streams outside the graph.
+        if (c == nChunks - 1)
+            CU_TRY(cudaEventRecordWithFlags(ctx->evPrimaryDone, stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
         if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 1], stream));
         unsigned int* groupCounter = static_cast<unsigned int*>(ctx->countLog.p) + nChunks + c;
         const int shadeGrid = ctx->smCount * ctx->shadeBlocksPerSm;
@@ -344,18 +349,13 @@ void inherit_options(McContext* lane, const McContext* ctx) {
 int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* outF32, uchar4* outU8, cudaStream_t stream) {
     if (L <= 1) return render_bands_lane(ctx, ctx, first, stride, 0, 1, outF32, outU8, stream);
     CU_TRY(cudaEventRecord(ctx->evCopy, stream));  // fork point
-    const bool stagger = ctx->staggerLanes != 0;
-    // lane 0 on the caller's stream, lanes 1..L-1 on their own; launched in lane order so that
-    // each lane's "primary pass done" record precedes the next lane's wait on it
-    int rc = render_bands_lane(ctx, ctx, first, stride * L, 0, L, outF32, outU8, stream, nullptr,
-                               stagger ? ctx->evPrimaryDone : nullptr);
+    // lane 0 on the caller's stream, lanes 1..L-1 on their own
+    int rc = render_bands_lane(ctx, ctx, first, stride * L, 0, L, outF32, outU8, stream);
     if (rc != MC_OK) return rc;
     for (int k = 1; k < L; ++k) {
         McContext* lane = ctx->lanes[k - 1];
-        McContext* prev = k == 1 ? ctx : ctx->lanes[k - 2];
         CU_TRY(cudaStreamWaitEvent(lane->stream, ctx->evCopy, 0));
-        rc = render_bands_lane(lane, ctx, first + k * stride, stride * L, k, L, outF32, outU8, lane->stream,
-                               stagger ? prev->evPrimaryDone : nullptr, stagger ? lane->evPrimaryDone : nullptr);
+        rc = render_bands_lane(lane, ctx, first + k * stride, stride * L, k, L, outF32, outU8, lane->stream);
         if (rc != MC_OK) return rc;
         CU_TRY(cudaEventRecord(lane->evCopy, lane->stream));
     }
@@ -366,7 +366,7 @@ int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* out
 long long option_bits(const McContext* c, int i) {
     const long long v[12] = {c->forceAllActive, c->recordBudgetBytes, c->shadeBlocksPerSm, c->primaryBlocksPerSm,
                              c->waveQueueLevels, c->shadeMode, c->waveBudgetBytes, c->waveDeepGridDiv,
-                             c->waveShadowPrefetch, c->cacheTileSeeds, c->staggerLanes, c->frameLanes};
+                             c->waveShadowPrefetch, c->cacheTileSeeds, 0, c->frameLanes};
     return v[i];
 }
 
@@ -650,6 +650,8 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     CU_TRY(cudaEventCreate(&ctx->ev1));
     CU_TRY(cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&ctx->evPrimaryDone, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ctx->evFrameDone, cudaEventDisableTiming));
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&ctx->evUpload, cudaEventDisableTiming));
     if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
     if (const char* v = std::getenv("MCSKIN_PRIMARY_BLOCKS")) ctx->primaryBlocksPerSm = std::max(0, std::atoi(v));
@@ -657,7 +659,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     if (const char* v = std::getenv("MCSKIN_SHADOW_PREFETCH")) ctx->waveShadowPrefetch = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_DEEP_GRID_DIV")) ctx->waveDeepGridDiv = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_GRAPHS")) ctx->useGraphs = std::atoi(v) != 0;
-    if (const char* v = std::getenv("MCSKIN_STAGGER")) ctx->staggerLanes = std::atoi(v) != 0;
+    if (const char* v = std::getenv("MCSKIN_OVERLAP_COPY")) ctx->overlapCopyOut = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_FRAME_LANES")) ctx->frameLanes = std::min(8, std::max(1, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_CACHE_TILE_SEEDS")) ctx->cacheTileSeeds = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_SHADE_BLOCKS")) ctx->shadeBlocksPerSm = std::max(1, std::atoi(v));
@@ -680,6 +682,8 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
     if (ctx->evPrimaryDone) cudaEventDestroy(ctx->evPrimaryDone);
+    if (ctx->evFrameDone) cudaEventDestroy(ctx->evFrameDone);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
     if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
     if (ctx->graph) cudaGraphDestroy(ctx->graph);
@@ -702,7 +706,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "frame_lanes") ctx->frameLanes = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(1, value)));
     else if (k == "cache_tile_seeds") ctx->cacheTileSeeds = value != 0;
     else if (k == "use_graphs") ctx->useGraphs = value != 0;
-    else if (k == "stagger_lanes") ctx->staggerLanes = value != 0;
+    else if (k == "overlap_copy_out") ctx->overlapCopyOut = value != 0;
     else if (k == "wave_budget_bytes") ctx->waveBudgetBytes = std::max<int64_t>(1 << 20, value);
     else return fail(MC_ERR_INVALID, "set_option: unknown option " + k);
     return MC_OK;
@@ -770,13 +774,45 @@ static int render_host(McContext* ctx, const McScene* scene, const McConfig* cfg
     rc = render_bands(ctx, first, stride, outF32 ? static_cast<float4*>(ctx->imgF32.p) : nullptr,
                       outU8 ? static_cast<uchar4*>(ctx->imgU8.p) : nullptr, ctx->stream);
     if (rc != MC_OK) return rc;
-    if (outF32) {
-        rc = copy_out(ctx, outF32, ctx->imgF32.p, pixels * sizeof(float4));
-        if (rc != MC_OK) return rc;
-    }
-    if (outU8) {
-        rc = copy_out(ctx, outU8, ctx->imgU8.p, pixels * sizeof(uchar4));
-        if (rc != MC_OK) return rc;
+    // Copy-out overlapped with shading: once the primary passes are done, every pixel outside the
+    // figure's screen rectangle is final (93 % of the headline frame), so the whole image starts its
+    // way to the host then, next to the shading kernels; when the frame is complete only the
+    // rectangle is sent again.  Needs page-locked destinations (DMA straight into the caller's
+    // buffers) and a whole frame in one chunk.
+    // (and the classifying primary pass: without it every pixel is written by the shading pass)
+    const bool overlap = ctx->overlapCopyOut && first == 0 && stride == 1 && f.rect_valid && ctx->chunksLastRender == 1 &&
+                         !ctx->forceAllActive && f.spp <= kBlockThreads && f.rect_x0 <= f.rect_x1 && f.rect_y0 <= f.rect_y1 &&
+                         (!outF32 || is_pinned_host(outF32)) && (!outU8 || is_pinned_host(outU8));
+    if (overlap) {
+        CU_TRY(cudaStreamWaitEvent(ctx->copyStream, ctx->evPrimaryDone, 0));
+        for (int k = 0; k < ctx->splitLastRender; ++k)
+            CU_TRY(cudaStreamWaitEvent(ctx->copyStream, ctx->lanes[k]->evPrimaryDone, 0));
+        if (outF32) CU_TRY(cudaMemcpyAsync(outF32, ctx->imgF32.p, pixels * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copyStream));
+        if (outU8) CU_TRY(cudaMemcpyAsync(outU8, ctx->imgU8.p, pixels * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->copyStream));
+        CU_TRY(cudaEventRecord(ctx->evFrameDone, ctx->stream));
+        CU_TRY(cudaStreamWaitEvent(ctx->copyStream, ctx->evFrameDone, 0));
+        const int x0 = std::max(0, f.rect_x0), x1 = std::min(f.width - 1, f.rect_x1);
+        const int y0 = std::max(0, f.rect_y0), y1 = std::min(f.height - 1, f.rect_y1);
+        if (x0 <= x1 && y0 <= y1) {
+            const size_t at = static_cast<size_t>(y0) * f.width + x0;
+            const size_t w = static_cast<size_t>(x1 - x0 + 1), h = static_cast<size_t>(y1 - y0 + 1);
+            if (outF32)
+                CU_TRY(cudaMemcpy2DAsync(outF32 + at * 4, f.width * sizeof(float4), static_cast<float4*>(ctx->imgF32.p) + at,
+                                         f.width * sizeof(float4), w * sizeof(float4), h, cudaMemcpyDeviceToHost, ctx->copyStream));
+            if (outU8)
+                CU_TRY(cudaMemcpy2DAsync(outU8 + at * 4, f.width * sizeof(uchar4), static_cast<uchar4*>(ctx->imgU8.p) + at,
+                                         f.width * sizeof(uchar4), w * sizeof(uchar4), h, cudaMemcpyDeviceToHost, ctx->copyStream));
+        }
+        CU_TRY(cudaStreamSynchronize(ctx->copyStream));
+    } else {
+        if (outF32) {
+            rc = copy_out(ctx, outF32, ctx->imgF32.p, pixels * sizeof(float4));
+            if (rc != MC_OK) return rc;
+        }
+        if (outU8) {
+            rc = copy_out(ctx, outU8, ctx->imgU8.p, pixels * sizeof(uchar4));
+            if (rc != MC_OK) return rc;
+        }
     }
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     CU_TRY(cudaGetLastError());

@@ -125,15 +125,33 @@ __device__ __forceinline__ bool slab_axis(Slab& s, float o, float d, float inv, 
 // computeFaceUV + TextureRegion::sample addressing (intersection.cpp:136-196,
 // texture_region.h:19-26) -> texel pool index.  The two in-plane coordinates are picked
 // first so the (IEEE) divisions exist once: Z faces use (x, y), X faces (z, y), Y faces (x, z).
+// a / b rounded to nearest from r = RN(1/b): two Newton steps on the quotient with exact (fused)
+// residuals.  After the first, the quotient is within a rounding of a/b; the second is then the
+// correctly rounded a/b (Markstein's theorem; the host clears kBoxRecip for the one excluded
+// family of divisors, significands of all ones).  Inputs here are box-local coordinates of
+// order 1..100: no overflow, and a residual of an exact zero stays zero.
+__device__ __forceinline__ float div_exact(float a, float b, float r) {
+    float q = a * r;
+    q = fmaf(fmaf(-q, b, a), r, q);
+    return fmaf(fmaf(-q, b, a), r, q);
+}
 __device__ __forceinline__ int face_texel(const DevBox& bx, V3 p, int axis, bool negSide, int face) {
     const float pa = (axis == 0) ? p.z : p.x;
     const float la0 = (axis == 0) ? bx.lo[2] : bx.lo[0];
     const float sa = (axis == 0) ? bx.size[2] : bx.size[0];
+    const float ra = (axis == 0) ? bx.inv_size_z : bx.inv_size_x;
     const float pb = (axis == 1) ? p.z : p.y;
     const float lb0 = (axis == 1) ? bx.lo[2] : bx.lo[1];
     const float sb = (axis == 1) ? bx.size[2] : bx.size[1];
-    const float la = (pa - la0) / sa;   // localX (or localZ on X faces)
-    const float lb = (pb - lb0) / sb;   // localY (or localZ on Y faces)
+    const float rb = (axis == 1) ? bx.inv_size_z : bx.inv_size_y;
+    float la, lb;   // localX (or localZ on X faces), localY (or localZ on Y faces)
+    if (bx.flags & kBoxRecip) {
+        la = div_exact(pa - la0, sa, ra);
+        lb = div_exact(pb - lb0, sb, rb);
+    } else {
+        la = (pa - la0) / sa;
+        lb = (pb - lb0) / sb;
+    }
     float u, v;
     if (axis == 2) {
         u = negSide ? 1.0f - la : la;

@@ -32,9 +32,14 @@ __device__ __forceinline__ uint32_t mt_lcg(uint32_t prev, uint32_t i) {
     return 1812433253u * (prev ^ (prev >> 30)) + i;
 #endif
 }
+// The twist: far ^ (y >> 1) ^ (y odd ? 0x9908b0df : 0), y = top bit of cur | low 31 bits of next.
+// Spelled so that it compiles to five instructions (bit-select LOP3, AND, IMAD for the conditional
+// constant — on the FMA pipe —, SHF, three-input XOR) instead of the seven of the plain C form.
 __device__ __forceinline__ uint32_t mt_mix(uint32_t cur, uint32_t next, uint32_t far) {
-    const uint32_t y = (cur & 0x80000000u) | (next & 0x7fffffffu);
-    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    uint32_t y, mag;
+    asm("lop3.b32 %0, %1, %2, 0x80000000, 0xE4;" : "=r"(y) : "r"(cur), "r"(next));  // (cur & m) | (next & ~m)
+    asm("{\n\t.reg .u32 t;\n\tand.b32 t, %1, 1;\n\tmul.lo.u32 %0, t, 0x9908b0df;\n\t}" : "=r"(mag) : "r"(next));
+    return far ^ (y >> 1) ^ mag;
 }
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= y >> 11;

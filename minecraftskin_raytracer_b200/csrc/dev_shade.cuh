@@ -111,15 +111,19 @@ __device__ __forceinline__ float4 config_background(const DevFrame& fr, float u,
                        fr.bg_center[2] * k + fr.bg_edge[2] * t, 1.0f);
 }
 
-// isInShadow, examining only the boxes of `allow` among the first 32 (see bundle_box_mask)
-__device__ __forceinline__ bool in_shadow_among(const SceneView& sc, V3 point, V3 normal, V3 lightPos, uint32_t allow) {
+// isInShadow from the offset origin point + normal*eps, examining only the boxes of `allow` among
+// the first 32 (see bundle_box_mask)
+__device__ __forceinline__ bool in_shadow_from(const SceneView& sc, V3 origin, V3 lightPos, uint32_t allow) {
     Ray r;
-    r.o = point + normal * kShadowEpsilon;
+    r.o = origin;
     const V3 toLight = lightPos - r.o;
     const float dist = len3(toLight);
     if (dist < 1e-6f) return false;
     r.d = div3(toLight, dist);
     return occluded_among(sc, r, dist, allow);
+}
+__device__ __forceinline__ bool in_shadow_among(const SceneView& sc, V3 point, V3 normal, V3 lightPos, uint32_t allow) {
+    return in_shadow_from(sc, point + normal * kShadowEpsilon, lightPos, allow);
 }
 
 // isInShadow

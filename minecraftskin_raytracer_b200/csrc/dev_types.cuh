@@ -19,11 +19,11 @@ struct __align__(16) DevBox {
     float lo[3];      // bounds_min
     uint32_t flags;   // kBox* bits
     float hi[3];      // bounds_max
-    float pad0;
+    float inv_size_x; // RN(1 / size[k]) (host division): operands of the exact quotients in face_texel,
     float size[3];    // hi-lo per axis, replaced by 1 where <= 1e-8 (intersection.cpp:141-143)
-    float pad1;
+    float inv_size_y; //   valid when kBoxRecip is set
     float pivot[3];
-    float pad2;
+    float inv_size_z;
     float inv_cx, inv_sx, inv_cz, inv_sz;  // cosf/sinf of rad(-rotX), rad(-rotZ): world -> local
     float fwd_cx, fwd_sx, fwd_cz, fwd_sz;  // cosf/sinf of rad(+rotX), rad(+rotZ): local -> world
     // face f: x = first texel in the pool, y = width | (height << 16)
@@ -35,7 +35,8 @@ enum : uint32_t {
     kBoxRotated = 2u,    // Mesh::hasRotation
     kBoxRotX = 4u,       // |rotX| > 0.01 (intersection.cpp:16)
     kBoxRotZ = 8u,       // |rotZ| > 0.01 (intersection.cpp:26)
-    kBoxEmpty = 16u      // no triangles: never hit (intersection.cpp:205)
+    kBoxEmpty = 16u,     // no triangles: never hit (intersection.cpp:205)
+    kBoxRecip = 32u      // inv_size_* may replace the divisions by size[] (see div_exact)
 };
 
 // The scene blob: what a CTA stages into shared memory with one bulk copy.

@@ -204,6 +204,22 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
             d.size[k] = (s > 1e-8f) ? s : 1.0f;
             d.pivot[k] = src.pivot[k];
         }
+        {
+            // Quotients by size[] are formed on the device as two Newton steps on a*RN(1/size) with
+            // exact (fused) residuals, which is the correctly rounded a/size unless size's
+            // significand is all ones (Markstein); also stay clear of the extreme exponents.
+            bool ok = true;
+            for (int k = 0; k < 3; ++k) {
+                uint32_t bits;
+                std::memcpy(&bits, &d.size[k], sizeof(bits));
+                const uint32_t expo = (bits >> 23) & 0xffu;
+                if ((bits & 0x7fffffu) == 0x7fffffu || expo < 64u || expo > 190u) ok = false;
+            }
+            d.inv_size_x = ok ? 1.0f / d.size[0] : 0.0f;
+            d.inv_size_y = ok ? 1.0f / d.size[1] : 0.0f;
+            d.inv_size_z = ok ? 1.0f / d.size[2] : 0.0f;
+            if (ok) d.flags |= kBoxRecip;
+        }
         d.inv_cx = d.inv_cz = d.fwd_cx = d.fwd_cz = 1.0f;
         if (src.has_rotation) {
             flags |= kBoxRotated;

@@ -150,15 +150,28 @@ k_wf_seed(const DevFrame fr, const FramePointers fp, const WaveView wv, const in
         wv.lit[i] = 0u;
         // the boxes the bundle of this hit's shadow rays can reach (computeSoftShadow hands
         // isInShadow the raw hit normal: shading.cpp:54, raytracer.cpp:113)
-        wv.allow[i] = bundle_box_mask(sc, P + hit_normal(sc, h) * kShadowEpsilon, ld3(fr.light_pos), fr.light_radius);
+        // the common origin of the hit's shadow rays, P + n*eps (isInShadow, shading.cpp:17; computeSoftShadow
+        // hands it the raw hit normal: shading.cpp:54, raytracer.cpp:113), and the boxes their bundle can reach
+        const V3 origin = P + hit_normal(sc, h) * kShadowEpsilon;
+        const uint32_t allow = bundle_box_mask(sc, origin, ld3(fr.light_pos), fr.light_radius);
+        wv.shadowOrg[i] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(allow));
     }
 }
 
+// hard shadows: no light samples to draw, only the counter and the shadow-ray origin of each hit
 __global__ void __launch_bounds__(kWfThreads)
-k_wf_clear_lit(const WaveView wv, const int depth) {
+k_wf_prep_hard(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
     unsigned int n = wv.qCount[depth];
     if (n > wv.pathCapacity) n = wv.pathCapacity;
-    for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) wv.lit[i] = 0u;
+    const SceneView sc = scene_view(fp.blob, fp.texels, fr);
+    const HitQueueView q = wv.q[which];
+    for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) {
+        const Hit h = unpack_hit(q.geo[i], make_float4(0.f, 0.f, 0.f, 0.f));
+        // shade() hands isInShadow the normalised normal (shading.cpp:69,78)
+        const V3 origin = h.p + normalize3(hit_normal(sc, h)) * kShadowEpsilon;
+        wv.shadowOrg[i] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(0xffffffffu));
+        wv.lit[i] = 0u;
+    }
 }
 
 // ---------------------------------------------------------------- one shadow ray per thread
@@ -173,7 +186,7 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
     if (static_cast<unsigned long long>(blockIdx.x) * kWfThreads >= nRays) return;
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
-    const HitQueueView q = wv.q[which];
+    (void)which;
     const bool soft = wv.shadowMode == kShadowSoft;
     const V3 lightCentre = ld3(fr.light_pos);
     const bool rPow2 = (R & (R - 1)) == 0;
@@ -183,22 +196,19 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
     // box mask — three dependent global loads) are fetched before the current ray is traced, so
     // their latency overlaps the slab tests instead of heading every trip.
     struct RayIn {
-        float4 g;
-        float tx, ty, tz;
-        uint32_t allow;
+        float4 org;        // shadow-ray origin, w = box mask
+        float tx, ty, tz;  // point on the light
         unsigned int i;
     };
     auto fetch = [&](unsigned long long t) {
         RayIn in;
         in.i = rPow2 ? static_cast<unsigned int>(t >> lgR) : static_cast<unsigned int>(t / R);
         const int k = static_cast<int>(t - static_cast<unsigned long long>(in.i) * R);
-        in.g = q.geo[in.i];
+        in.org = wv.shadowOrg[in.i];
         in.tx = lightCentre.x; in.ty = lightCentre.y; in.tz = lightCentre.z;
-        in.allow = 0xffffffffu;
         if (soft) {
             const float* lp = wv.lightPos + (static_cast<size_t>(in.i) * R + k) * 3;
             in.tx = lp[0]; in.ty = lp[1]; in.tz = lp[2];
-            in.allow = wv.allow[in.i];
         }
         return in;
     };
@@ -215,10 +225,9 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
         } else {
             cur = fetch(t);
         }
-        const Hit h = unpack_hit(cur.g, make_float4(0.f, 0.f, 0.f, 0.f));
-        V3 normal = hit_normal(sc, h);
-        if (!soft) normal = normalize3(normal);  // shade() hands isInShadow the normalised normal (shading.cpp:69,78)
-        if (!in_shadow_among(sc, h.p, normal, mk3(cur.tx, cur.ty, cur.tz), cur.allow)) atomicAdd(&wv.lit[cur.i], 1u);
+        const V3 origin = mk3(cur.org.x, cur.org.y, cur.org.z);
+        if (!in_shadow_from(sc, origin, mk3(cur.tx, cur.ty, cur.tz), __float_as_uint(cur.org.w)))
+            atomicAdd(&wv.lit[cur.i], 1u);
     }
 }
 
@@ -413,7 +422,7 @@ size_t wavefront_bytes_per_path(const DevFrame& fr) {
     const int mode = shadow_mode_of(fr);
     const size_t lightBytes = mode == kShadowSoft ? sizeof(float) * 3 * fr.shadow_samples : 0;
     return 2 * 3 * sizeof(float4)            // two hit queues
-           + lightBytes + 2 * sizeof(unsigned)   // light sample points, lit counters, box masks
+           + lightBytes + sizeof(unsigned) + sizeof(float4)   // light sample points, lit counters, shadow origins + box masks
            + sizeof(float4) + sizeof(int)    // tail, top
            + sizeof(float4) * stack_levels_of(fr);
 }
@@ -449,7 +458,7 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
     }
     w.lightPos = static_cast<float*>(take(w.shadowMode == kShadowSoft ? cap * sizeof(float) * 3 * fr.shadow_samples : 16));
     w.lit = static_cast<unsigned int*>(take(cap * sizeof(unsigned int)));
-    w.allow = static_cast<unsigned int*>(take(cap * sizeof(unsigned int)));
+    w.shadowOrg = static_cast<float4*>(take(cap * sizeof(float4)));
     w.tail = static_cast<float4*>(take(cap * sizeof(float4)));
     w.top = static_cast<int*>(take(cap * sizeof(int)));
     w.stack = static_cast<float4*>(take(std::max<size_t>(16, cap * sizeof(float4) * w.levels)));
@@ -480,7 +489,7 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
                 k_wf_seed<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
                 ++n;
             } else if (wv.shadowMode == kShadowHard) {
-                k_wf_clear_lit<<<g, kWfThreads, 0, stream>>>(wv, depth);
+                k_wf_prep_hard<<<g, kWfThreads, 0, stream>>>(fr, fp, wv, which, depth);
                 ++n;
             }
             if (wv.shadowMode != kShadowInThread) {

@@ -37,7 +37,7 @@ struct WaveView {
     HitQueueView q[2];       // ping-pong over depth
     float* lightPos;         // per hit of the current queue: 3 floats per shadow sample
     unsigned int* lit;       // per hit of the current queue: unoccluded shadow rays
-    unsigned int* allow;     // per hit of the current queue: boxes its shadow-ray bundle can reach
+    float4* shadowOrg;       // per hit of the current queue: origin of its shadow rays; w = boxes their bundle can reach
     float4* tail;            // per path: colour returned by the deepest traceRay call
     float4* stack;           // [level][path]: shaded colour of every level that spawned a reflection (w = its alpha)
     int* top;                // per path: number of stack levels in use

@@ -21,7 +21,7 @@ import os
 LIB_PATH = Path(os.environ.get("MCSKIN_LIB") or (Path(__file__).resolve().parent / "_lib" / "libmcskin_cuda.so"))
 
 # streams a frame's tile rows are dealt to by default (McContext::frameLanes in csrc/capi.cu)
-DEFAULT_FRAME_LANES = 2
+DEFAULT_FRAME_LANES = 3
 
 # every symbol include/mcskin_cuda.h declares
 EXPORTS = [

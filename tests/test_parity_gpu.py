@@ -161,7 +161,7 @@ RENDER_MODES = {
     "shallow_queues": {"wave_queue_levels": 1},
     "split_tiles": {"primary_blocks_per_sm": 100000},     # every tile split over one block per 256-pixel round
     "one_lane_no_graph": {"frame_lanes": 1, "use_graphs": 0, "cache_tile_seeds": 0},
-    "five_lanes_unstaggered": {"frame_lanes": 5, "stagger_lanes": 0},
+    "five_lanes": {"frame_lanes": 5},
     "thin_deep_grids": {"wave_deep_grid_div": 8, "frame_lanes": 3},
 }
 
@@ -232,6 +232,25 @@ def test_u8_output_and_progress(gpu, oracle):
     assert calls == [(i, total) for i in range(1, total + 1)]  # tests/test_tile_renderer.cpp:85-104
     assert np.array_equal(u8, oracle.quantize(f32))             # image_writer.cpp:18-22
     assert stats["n_kernel_launches"] >= 2 and stats["n_tiles"] == total
+
+
+def test_render_into_page_locked_buffers_overlaps_copy_out(gpu, oracle):
+    """With page-locked destinations the image leaves for the host while the shading pass runs
+    (whole frame after the primary pass, the figure's rectangle again at the end): same bytes."""
+    import torch
+    scene = _scene(gpu, 6, "64x64", "waving")
+    for over in (dict(width=320, height=200, samples_per_pixel=4, max_bounces=3),
+                 dict(width=96, height=128, samples_per_pixel=1, max_bounces=1)):
+        cfg = make_config(**over)
+        want, want_u8, _ = gpu.render(scene, cfg, want_u8=True)            # pageable destinations: plain copy
+        f32 = torch.empty((cfg.height, cfg.width, 4), dtype=torch.float32, pin_memory=True).numpy()
+        u8 = torch.empty((cfg.height, cfg.width, 4), dtype=torch.uint8, pin_memory=True).numpy()
+        for _ in range(3):  # direct launches, graph capture, graph replay
+            f32.fill(-1.0)
+            u8.fill(7)
+            gpu.render(scene, cfg, out_f32=f32, out_u8=u8)
+            assert np.array_equal(_bits(f32), _bits(want)) and np.array_equal(u8, want_u8)
+    assert pixel_report(want, oracle.render(scene, cfg), oracle.quantize)["within1"] >= 0.999
 
 
 def test_render_tile_matches_full_frame(gpu, oracle):
