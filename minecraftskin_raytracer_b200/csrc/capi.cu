@@ -158,6 +158,12 @@ struct McContext {
     int chunksLastRender = 0;
     // batch rendering
     int batchLanes = 4;
+    int batchGroup = 128;                    // scenes rendered by one set of launches (gridDim.y)
+    int batchMode = 1;                       // 1: grouped launches, 0: one frame at a time over the lanes
+    DevBuf batchScenes, batchSlots, batchRecords, batchWave, batchCounts;
+    PinnedBuf batchStage[2];
+    cudaEvent_t evStage[2] = {nullptr, nullptr};
+    std::vector<PreparedFrame> batchPreps;
     std::vector<McContext*> lanes;
 };
 
@@ -618,6 +624,164 @@ int query_setup(const McScene* scene, const McConfig* cfg, int device, int useCo
 }  // namespace
 
 // =============================================================== exported functions
+namespace {
+
+// Batches, grouped form (SURVEY.md §8e "one launch renders many skins"): the scenes of a chunk that
+// share a frame description — image size, sampling, camera, light, box layout; in a batch of skins
+// that is nearly all of them — are rendered by ONE set of launches whose gridDim.y is the scene.
+// Each scene has its own boxes, texels, output image, work list and queues (BatchSlice); the tile
+// engines are seeded once per launch set (they do not depend on the scene).  Returns MC_OK with
+// *handled = false when the frame description needs a path that has no batched form.
+int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, const McConfig* cfg, float4* outF32,
+                         uchar4* outU8, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (!ctx->batchMode || ctx->shadeMode != 0 || ctx->forceAllActive || nScenes < 2) return MC_OK;
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->tile_size <= 0 || cfg->width > 65535 || cfg->height > 65535) return MC_OK;
+    const int spp = std::max(1, cfg->samples_per_pixel);
+    if (spp > kBlockThreads) return MC_OK;
+    const size_t pixels = static_cast<size_t>(cfg->width) * cfg->height;
+    std::string err;
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->evStage[i]) CU_TRY(cudaEventCreateWithFlags(&ctx->evStage[i], cudaEventDisableTiming));
+
+    // sizes per scene (identical for every scene: they depend on the config only)
+    PreparedFrame probe;
+    int prc = prepare_frame(&scenes[0], cfg, 1, 0.0f, probe, err);
+    if (prc != MC_OK) return fail(prc, err);
+    const DevFrame& f0 = probe.frame;
+    const size_t slotCap = static_cast<size_t>(f0.tiles_x) * f0.tiles_y * f0.tile_size * f0.tile_size;
+    const size_t paths = slotCap * f0.spp;
+    if (paths > 0x7fffff00u) return MC_OK;
+    const size_t recordBytes = std::max<size_t>(16, slotCap * f0.spp * f0.draws_per_sample * sizeof(float));
+    const size_t waveBytes = (paths * wavefront_bytes_per_path(f0) + wavefront_fixed_bytes(f0) + 4096 + 255) & ~size_t(255);
+    const size_t perScene = waveBytes + recordBytes + slotCap * sizeof(uint2);
+    int G = std::min<int>(ctx->batchGroup, nScenes);
+    G = static_cast<int>(std::max<size_t>(1, std::min<size_t>(G, static_cast<size_t>(ctx->waveBudgetBytes) / std::max<size_t>(1, perScene))));
+    if (G < 2) return MC_OK;
+    // launch_primary_batch needs the pixel-per-lane kernels; probe with an empty launch description
+    {
+        const long long tileDraws = static_cast<long long>(f0.tile_size) * f0.tile_size * f0.spp * std::max(1, f0.draws_per_sample);
+        if (!(tileDraws < (1ll << 30) && kBlockThreads * f0.spp * f0.draws_per_sample + 624 <= 16384)) return MC_OK;
+    }
+    constexpr size_t kMaxBlob = kMaxSceneSmemBytes;
+    // blob + texel pool of the largest scene of the batch (a skin scene is ~55 KB)
+    size_t sceneStride = 0;
+    for (int i = 0; i < nScenes; ++i) {
+        if (scenes[i].n_boxes < 0 || scenes[i].n_texels < 0) return fail(MC_ERR_INVALID, "render_batch: scene has negative counts");
+        const size_t blob = (SceneBlobLayout(scenes[i].n_boxes).bytes() + 255) & ~size_t(255);
+        if (blob > kMaxBlob) return MC_OK;  // the frame-by-frame path reports the limit
+        const size_t tex = ((static_cast<size_t>(scenes[i].n_texels) + 2) * sizeof(float4h) + 255) & ~size_t(255);
+        sceneStride = std::max(sceneStride, blob + tex);
+    }
+    if (sceneStride > (8u << 20)) return MC_OK;
+    CU_TRY(ctx->batchScenes.reserve(static_cast<size_t>(G) * (sceneStride + sizeof(BatchSlice))));
+    CU_TRY(ctx->batchSlots.reserve(static_cast<size_t>(G) * slotCap * sizeof(uint2)));
+    CU_TRY(ctx->batchRecords.reserve(static_cast<size_t>(G) * recordBytes));
+    CU_TRY(ctx->batchWave.reserve(static_cast<size_t>(G) * waveBytes));
+    CU_TRY(ctx->batchCounts.reserve(static_cast<size_t>(G) * sizeof(unsigned int)));
+    CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, static_cast<size_t>(f0.tiles_x) * f0.tiles_y * 624 * sizeof(uint32_t))));
+    for (int i = 0; i < 2; ++i) CU_TRY(ctx->batchStage[i].reserve(static_cast<size_t>(G) * (sceneStride + sizeof(BatchSlice))));
+    if (ctx->batchPreps.size() < static_cast<size_t>(G)) ctx->batchPreps.resize(G);
+    ctx->tileSeedValid = false;  // this path seeds the engines itself
+    ++ctx->seedGen;
+
+    unsigned char* devScenes = static_cast<unsigned char*>(ctx->batchScenes.p);
+    const size_t sliceOffset = static_cast<size_t>(G) * sceneStride;  // slices follow the scene data
+    int stageSlot = 0;
+    bool seeded = false;
+    for (int c0 = 0; c0 < nScenes; c0 += G) {
+        const int nC = std::min(G, nScenes - c0);
+        for (int i = 0; i < nC; ++i) {
+            prc = prepare_frame(&scenes[c0 + i], cfg, 1, 0.0f, ctx->batchPreps[i], err);
+            if (prc != MC_OK) return fail(prc, err);
+            if (ctx->batchPreps[i].blob.size() > kMaxBlob ||
+                ((ctx->batchPreps[i].blob.size() + 255) & ~size_t(255)) + ctx->batchPreps[i].texels.size() * sizeof(float4h) > sceneStride)
+                return fail(MC_ERR_LIMIT, "render_batch: scene larger than its McScene counts imply");
+        }
+        // groups of equal frame descriptions (and blob sizes), in first-seen order
+        std::vector<int> groupOf(nC, -1);
+        std::vector<std::vector<int>> groups;
+        for (int i = 0; i < nC; ++i) {
+            for (size_t g = 0; g < groups.size() && groupOf[i] < 0; ++g) {
+                const PreparedFrame& ref = ctx->batchPreps[groups[g][0]];
+                if (std::memcmp(&ref.frame, &ctx->batchPreps[i].frame, sizeof(DevFrame)) == 0 &&
+                    ref.blob.size() == ctx->batchPreps[i].blob.size())
+                    groupOf[i] = static_cast<int>(g);
+            }
+            if (groupOf[i] < 0) {
+                groupOf[i] = static_cast<int>(groups.size());
+                groups.emplace_back();
+            }
+            groups[groupOf[i]].push_back(i);
+        }
+        // stage: scene data at slot i (chunk-local index), slices ordered group by group
+        CU_TRY(cudaEventSynchronize(ctx->evStage[stageSlot]));  // the copy that last read this staging buffer
+        unsigned char* stage = static_cast<unsigned char*>(ctx->batchStage[stageSlot].p);
+        BatchSlice* stageSlices = reinterpret_cast<BatchSlice*>(stage + sliceOffset);
+        int sliceAt = 0;
+        std::vector<int> groupFirstSlice(groups.size(), 0);
+        for (size_t g = 0; g < groups.size(); ++g) {
+            groupFirstSlice[g] = sliceAt;
+            for (int i : groups[g]) {
+                const PreparedFrame& pf = ctx->batchPreps[i];
+                unsigned char* dst = stage + static_cast<size_t>(i) * sceneStride;
+                const size_t blobBytes = (pf.blob.size() + 255) & ~size_t(255);
+                std::memcpy(dst, pf.blob.data(), pf.blob.size());
+                std::memcpy(dst + blobBytes, pf.texels.data(), pf.texels.size() * sizeof(float4h));
+                BatchSlice sl{};
+                sl.fp.blob = devScenes + static_cast<size_t>(i) * sceneStride;
+                sl.fp.texels = reinterpret_cast<const float4*>(devScenes + static_cast<size_t>(i) * sceneStride + blobBytes);
+                sl.fp.blob_bytes = static_cast<unsigned int>(pf.blob.size());
+                sl.band.first_tile_row = 0;
+                sl.band.tile_row_stride = 1;
+                sl.band.n_tile_rows = pf.frame.tiles_y;
+                sl.band.out_first_row = 0;
+                sl.band.out_row_stride = 1;
+                sl.band.out_f32 = outF32 ? outF32 + static_cast<size_t>(c0 + i) * pixels : nullptr;
+                sl.band.out_u8 = outU8 ? outU8 + static_cast<size_t>(c0 + i) * pixels : nullptr;
+                sl.list.count = static_cast<unsigned int*>(ctx->batchCounts.p) + i;
+                sl.list.slot_pixel = static_cast<uint2*>(ctx->batchSlots.p) + static_cast<size_t>(i) * slotCap;
+                sl.list.records = reinterpret_cast<float*>(static_cast<unsigned char*>(ctx->batchRecords.p) + static_cast<size_t>(i) * recordBytes);
+                sl.list.capacity = static_cast<unsigned int>(slotCap);
+                // few blocks per scene: a launch has gridDim.y scenes to fill the machine with
+                const int gridX = std::max(2, (ctx->smCount * ctx->shadeBlocksPerSm + nC - 1) / nC);
+                if (!wavefront_carve(pf.frame, static_cast<unsigned char*>(ctx->batchWave.p) + static_cast<size_t>(i) * waveBytes,
+                                     waveBytes, static_cast<unsigned int>(paths), gridX, &sl.wave))
+                    return fail(MC_ERR_CUDA, "render_batch: queue carve failed");
+                sl.wave.queueLevels = ctx->waveQueueLevels;
+                sl.wave.deepGridDiv = 1;
+                sl.wave.shadowPrefetch = 0;
+                stageSlices[sliceAt++] = sl;
+            }
+        }
+        const size_t usedScenes = static_cast<size_t>(nC) * sceneStride;
+        CU_TRY(cudaMemcpyAsync(devScenes, stage, usedScenes, cudaMemcpyHostToDevice, stream));
+        CU_TRY(cudaMemcpyAsync(devScenes + sliceOffset, stage + sliceOffset, static_cast<size_t>(nC) * sizeof(BatchSlice),
+                               cudaMemcpyHostToDevice, stream));
+        CU_TRY(cudaEventRecord(ctx->evStage[stageSlot], stream));
+        stageSlot ^= 1;
+        const BatchSlice* devSlices = reinterpret_cast<const BatchSlice*>(devScenes + sliceOffset);
+        for (size_t g = 0; g < groups.size(); ++g) {
+            const int nS = static_cast<int>(groups[g].size());
+            const BatchSlice* gs = devSlices + groupFirstSlice[g];
+            const BatchSlice& first = stageSlices[groupFirstSlice[g]];
+            const DevFrame& f = ctx->batchPreps[groups[g][0]].frame;
+            launch_batch_reset(gs, nS, first.wave.levels, stream);
+            if (!launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), !seeded, gs, nS, first.fp.blob_bytes,
+                                      ctx->smCount * ctx->primaryBlocksPerSm, stream))
+                return fail(MC_ERR_CUDA, "render_batch: no batched primary kernel for this frame description");
+            seeded = true;  // same image geometry for every scene of the batch
+            int launches = 0;
+            launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
+        }
+        CU_TRY(cudaGetLastError());
+    }
+    *handled = true;
+    return MC_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int32_t mcskin_cuda_device_count(void) {
@@ -658,6 +822,8 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) ctx->waveQueueLevels = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_SHADOW_PREFETCH")) ctx->waveShadowPrefetch = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_DEEP_GRID_DIV")) ctx->waveDeepGridDiv = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("MCSKIN_BATCH_GROUP")) ctx->batchGroup = std::min(4096, std::max(1, std::atoi(v)));
+    if (const char* v = std::getenv("MCSKIN_BATCH_MODE")) ctx->batchMode = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_GRAPHS")) ctx->useGraphs = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_OVERLAP_COPY")) ctx->overlapCopyOut = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_FRAME_LANES")) ctx->frameLanes = std::min(8, std::max(1, std::atoi(v)));
@@ -683,6 +849,11 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
     if (ctx->evPrimaryDone) cudaEventDestroy(ctx->evPrimaryDone);
     if (ctx->evFrameDone) cudaEventDestroy(ctx->evFrameDone);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->evStage[i]) cudaEventDestroy(ctx->evStage[i]);
+        ctx->batchStage[i].release();
+    }
+    for (DevBuf* b : {&ctx->batchScenes, &ctx->batchSlots, &ctx->batchRecords, &ctx->batchWave, &ctx->batchCounts}) b->release();
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
     if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
@@ -700,6 +871,8 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "shade_blocks_per_sm") ctx->shadeBlocksPerSm = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "primary_blocks_per_sm") ctx->primaryBlocksPerSm = static_cast<int>(std::max<int64_t>(0, value));
     else if (k == "batch_lanes") ctx->batchLanes = static_cast<int>(std::min<int64_t>(16, std::max<int64_t>(1, value)));
+    else if (k == "batch_group") ctx->batchGroup = static_cast<int>(std::min<int64_t>(4096, std::max<int64_t>(1, value)));
+    else if (k == "batch_mode") ctx->batchMode = value != 0;
     else if (k == "shade_mode") ctx->shadeMode = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
     else if (k == "wave_queue_levels") ctx->waveQueueLevels = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "wave_deep_grid_div") ctx->waveDeepGridDiv = static_cast<int>(std::max<int64_t>(1, value));
@@ -961,6 +1134,17 @@ int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, 
     CU_TRY(cudaSetDevice(ctx->device));
     const size_t pixels = static_cast<size_t>(std::max(cfg->width, 0)) * std::max(cfg->height, 0);
     cudaStream_t caller = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    {
+        bool handled = false;
+        const int rc = render_batch_grouped(ctx, scenes, nScenes, cfg, static_cast<float4*>(dOutF32), static_cast<uchar4*>(dOutU8),
+                                            caller, &handled);
+        if (rc != MC_OK) return rc;
+        if (handled) {
+            ctx->stats = McRenderStats{};
+            ctx->statsPending = false;
+            return MC_OK;
+        }
+    }
     const int nLanes = std::min<int>(ctx->batchLanes, nScenes);
     {
         const int rc = ensure_lanes(ctx, nLanes);

@@ -15,6 +15,7 @@
 // Both passes sum a pixel's samples in sample order, like the reference, so pixels are
 // reproducible bit-for-bit run to run and background pixels match the CPU result exactly.
 #include "kernels.cuh"
+#include "wavefront.cuh"
 
 #include "dev_shade.cuh"
 #include "dev_stage.cuh"
@@ -489,10 +490,14 @@ __global__ void k_tile_seed(const DevFrame fr, const BandView band, uint32_t* st
 
 extern __shared__ __align__(16) unsigned char g_pixSmem[];  // [PixStreamSmem][scene blob]
 
+template <bool BATCH>
 __global__ void __launch_bounds__(kBlockThreads)
-k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list,
-              const uint32_t* __restrict__ tileStates, const int parts) {
+k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, const ActiveList list_,
+              const uint32_t* __restrict__ tileStates, const int parts, const BatchSlice* __restrict__ batch) {
     __shared__ __align__(8) uint64_t stageBar;
+    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
+    const BandView& band = BATCH ? batch[blockIdx.y].band : band_;
+    const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
     PixStreamSmem* mt = reinterpret_cast<PixStreamSmem*>(g_pixSmem);
     unsigned char* sceneSmem = g_pixSmem + ((sizeof(PixStreamSmem) + 15) & ~size_t(15));
 
@@ -601,13 +606,16 @@ k_primary_pix(const DevFrame fr, const FramePointers fp, const BandView band, co
 // loads at constant offsets, the frame constants live in registers, and the hit test — needed
 // only inside the projected bounds of the figure — is a second, rolled loop that stops at the
 // first sample that hits.  Arithmetic per sample is that of k_primary_pix, operation for operation.
-template <int SPP, bool GRADIENT>
+template <int SPP, bool GRADIENT, bool BATCH>
 __global__ void __launch_bounds__(kBlockThreads)
-k_primary_pix_fixed(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list,
-                    const uint32_t* __restrict__ tileStates, const int parts) {
+k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView band_, const ActiveList list_,
+                    const uint32_t* __restrict__ tileStates, const int parts, const BatchSlice* __restrict__ batch) {
     constexpr unsigned int kWords = SPP * 2;
     static_assert(kWords <= 32 && 32 % kWords == 0, "a pixel's words must not straddle a 32-word ring group");
     __shared__ __align__(8) uint64_t stageBar;
+    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
+    const BandView& band = BATCH ? batch[blockIdx.y].band : band_;
+    const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
     PixStreamSmem* mt = reinterpret_cast<PixStreamSmem*>(g_pixSmem);
     unsigned char* sceneSmem = g_pixSmem + ((sizeof(PixStreamSmem) + 15) & ~size_t(15));
 
@@ -904,44 +912,70 @@ static int log2_if_warp_spp(int spp) {
     return -1;
 }
 
+// The pixel-per-lane primary kernels over one scene (batch == nullptr) or the scenes of a batch.
+static void launch_primary_pix(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
+                               uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, const BatchSlice* batch,
+                               int nScenes, unsigned int blobBytes, cudaStream_t stream) {
+    const int nTiles = band.n_tile_rows * fr.tiles_x;
+    const size_t pixSmem = ((sizeof(PixStreamSmem) + 15) & ~size_t(15)) + blobBytes;
+    static bool attrSet = false;
+    if (!attrSet) {
+        const int kMax = 100 * 1024;
+        cudaFuncSetAttribute(k_primary_pix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        cudaFuncSetAttribute(k_primary_pix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        cudaFuncSetAttribute(k_primary_pix_fixed<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        cudaFuncSetAttribute(k_primary_pix_fixed<16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        cudaFuncSetAttribute(k_primary_pix_fixed<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        cudaFuncSetAttribute(k_primary_pix_fixed<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        cudaFuncSetAttribute(k_primary_pix_fixed<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        cudaFuncSetAttribute(k_primary_pix_fixed<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        cudaFuncSetAttribute(k_primary_pix_fixed<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        cudaFuncSetAttribute(k_primary_pix_fixed<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+        attrSet = true;
+    }
+    // the seeded engines depend on the tile geometry only: one set serves every scene of a batch
+    if (fr.draws_per_sample > 0 && seedTiles) k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates);
+    // enough blocks to fill the machine, at most one block per round of 256 pixels
+    const int roundsPerTile = (fr.tile_size * fr.tile_size + kBlockThreads - 1) / kBlockThreads;
+    const int allTiles = nTiles * (batch ? nScenes : 1);
+    int parts = (primaryTargetBlocks + allTiles - 1) / allTiles;
+    parts = parts < 1 ? 1 : (parts > roundsPerTile ? roundsPerTile : parts);
+    const dim3 grid(nTiles * parts, batch ? nScenes : 1);
+    // jitter only (no lens draws), 4 or 16 spp, quotients by the host reciprocals: compile-time sample loop
+    const bool fixedForm = fr.draws_per_sample == 2 && fr.spp > 1 && !fr.dof_on && fr.uv_recip;
+#define MCSKIN_LAUNCH_PIX(KERNEL)                                                                                \
+    do {                                                                                                        \
+        if (batch) KERNEL<true><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts, batch);   \
+        else KERNEL<false><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts, batch);        \
+    } while (0)
+#define MCSKIN_LAUNCH_PIX_FIXED(SPP, GRAD)                                                                       \
+    do {                                                                                                        \
+        if (batch) k_primary_pix_fixed<SPP, GRAD, true><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts, batch);  \
+        else k_primary_pix_fixed<SPP, GRAD, false><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts, batch);       \
+    } while (0)
+    if (fixedForm && fr.spp == 16 && fr.gradient_bg) MCSKIN_LAUNCH_PIX_FIXED(16, true);
+    else if (fixedForm && fr.spp == 16) MCSKIN_LAUNCH_PIX_FIXED(16, false);
+    else if (fixedForm && fr.spp == 4 && fr.gradient_bg) MCSKIN_LAUNCH_PIX_FIXED(4, true);
+    else if (fixedForm && fr.spp == 4) MCSKIN_LAUNCH_PIX_FIXED(4, false);
+    else MCSKIN_LAUNCH_PIX(k_primary_pix);
+#undef MCSKIN_LAUNCH_PIX
+#undef MCSKIN_LAUNCH_PIX_FIXED
+}
+
+static bool pix_kernel_applies(const DevFrame& fr) {
+    // the warp / pixel variants index a tile's stream with 32-bit integers
+    const long long tileDraws = static_cast<long long>(fr.tile_size) * fr.tile_size * fr.spp * (fr.draws_per_sample > 0 ? fr.draws_per_sample : 1);
+    return tileDraws < (1ll << 30) && kBlockThreads * fr.spp * fr.draws_per_sample + kMtN <= kPixRingWords;
+}
+
 bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
                     int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     if (nTiles <= 0) return false;
-    // the warp / pixel variants index a tile's stream with 32-bit integers
     const long long tileDraws = static_cast<long long>(fr.tile_size) * fr.tile_size * fr.spp * (fr.draws_per_sample > 0 ? fr.draws_per_sample : 1);
-    const bool small = tileDraws < (1ll << 30);
-    const int lg = small ? log2_if_warp_spp(fr.spp) : -1;
-    const int wordsPerPixel = fr.spp * fr.draws_per_sample;
-    const size_t pixSmem = ((sizeof(PixStreamSmem) + 15) & ~size_t(15)) + fp.blob_bytes;
-    if (classify && small && kBlockThreads * wordsPerPixel + kMtN <= kPixRingWords) {
-        static bool attrSet = false;
-        if (!attrSet) {
-            cudaFuncSetAttribute(k_primary_pix, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            cudaFuncSetAttribute(k_primary_pix_fixed<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            cudaFuncSetAttribute(k_primary_pix_fixed<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            cudaFuncSetAttribute(k_primary_pix_fixed<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            cudaFuncSetAttribute(k_primary_pix_fixed<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            attrSet = true;
-        }
-        if (fr.draws_per_sample > 0 && seedTiles) k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates);
-        // enough blocks to fill the machine a few times over, at most one block per round of 256 pixels
-        const int roundsPerTile = (fr.tile_size * fr.tile_size + kBlockThreads - 1) / kBlockThreads;
-        int parts = (primaryTargetBlocks + nTiles - 1) / nTiles;
-        parts = parts < 1 ? 1 : (parts > roundsPerTile ? roundsPerTile : parts);
-        const dim3 grid(nTiles * parts);
-        // jitter only (no lens draws), 4 or 16 spp, quotients by the host reciprocals: compile-time sample loop
-        const bool fixedForm = fr.draws_per_sample == 2 && fr.spp > 1 && !fr.dof_on && fr.uv_recip;
-        if (fixedForm && fr.spp == 16 && fr.gradient_bg)
-            k_primary_pix_fixed<16, true><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
-        else if (fixedForm && fr.spp == 16)
-            k_primary_pix_fixed<16, false><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
-        else if (fixedForm && fr.spp == 4 && fr.gradient_bg)
-            k_primary_pix_fixed<4, true><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
-        else if (fixedForm && fr.spp == 4)
-            k_primary_pix_fixed<4, false><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
-        else
-            k_primary_pix<<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts);
+    const int lg = tileDraws < (1ll << 30) ? log2_if_warp_spp(fr.spp) : -1;
+    if (classify && pix_kernel_applies(fr)) {
+        launch_primary_pix(fr, fp, band, list, tileStates, seedTiles, primaryTargetBlocks, nullptr, 1, fp.blob_bytes, stream);
         return fr.draws_per_sample > 0;
     } else if (classify && lg >= 0) {
         k_primary_warp<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, lg);
@@ -949,6 +983,16 @@ bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView&
         k_primary_cta<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, classify);
     }
     return false;
+}
+
+bool launch_primary_batch(const DevFrame& fr, const BandView& band, uint32_t* tileStates, bool seedTiles,
+                          const BatchSlice* batch, int nScenes, unsigned int blobBytes, int primaryTargetBlocks,
+                          cudaStream_t stream) {
+    const int nTiles = band.n_tile_rows * fr.tiles_x;
+    if (nTiles <= 0 || nScenes <= 0 || !pix_kernel_applies(fr)) return false;
+    launch_primary_pix(fr, FramePointers{}, band, ActiveList{}, tileStates, seedTiles, primaryTargetBlocks, batch, nScenes,
+                       blobBytes, stream);
+    return true;
 }
 
 void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,

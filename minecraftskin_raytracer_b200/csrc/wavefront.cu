@@ -67,9 +67,14 @@ __device__ __forceinline__ void enqueue_hit(const HitQueueView& q, unsigned int*
 
 
 // ---------------------------------------------------------------- primary hits
+template <bool BATCH>
 __global__ void WF_HIT0_BOUNDS
-k_wf_hit0(const DevFrame fr, const FramePointers fp, const ActiveList list, const WaveView wv) {
+k_wf_hit0(const DevFrame fr, const FramePointers fp_, const ActiveList list_, const WaveView wv_,
+          const BatchSlice* __restrict__ batch) {
     __shared__ __align__(8) uint64_t stageBar;
+    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
+    const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
+    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     unsigned int count = *list.count;
     if (count > list.capacity) count = list.capacity;
     if (count > wv.slotCapacity) count = wv.slotCapacity;
@@ -129,9 +134,13 @@ k_wf_hit0(const DevFrame fr, const FramePointers fp, const ActiveList list, cons
 }
 
 // ---------------------------------------------------------------- shadow sample points
+template <bool BATCH>
 __global__ void __launch_bounds__(kWfThreads)
-k_wf_seed(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
+k_wf_seed(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
+          const BatchSlice* __restrict__ batch) {
     __shared__ __align__(8) uint64_t stageBar;
+    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
+    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     unsigned int n = wv.qCount[depth];
     if (n > wv.pathCapacity) n = wv.pathCapacity;
     if (blockIdx.x * kWfThreads >= n) return;
@@ -159,8 +168,12 @@ k_wf_seed(const DevFrame fr, const FramePointers fp, const WaveView wv, const in
 }
 
 // hard shadows: no light samples to draw, only the counter and the shadow-ray origin of each hit
+template <bool BATCH>
 __global__ void __launch_bounds__(kWfThreads)
-k_wf_prep_hard(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
+k_wf_prep_hard(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
+               const BatchSlice* __restrict__ batch) {
+    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
+    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     unsigned int n = wv.qCount[depth];
     if (n > wv.pathCapacity) n = wv.pathCapacity;
     const SceneView sc = scene_view(fp.blob, fp.texels, fr);
@@ -175,10 +188,13 @@ k_wf_prep_hard(const DevFrame fr, const FramePointers fp, const WaveView wv, con
 }
 
 // ---------------------------------------------------------------- one shadow ray per thread
-template <bool PREFETCH>
+template <bool PREFETCH, bool BATCH>
 __global__ void WF_SHADOW_BOUNDS
-k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth) {
+k_wf_shadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
+            const BatchSlice* __restrict__ batch) {
     __shared__ __align__(8) uint64_t stageBar;
+    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
+    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     unsigned int n = wv.qCount[depth];
     if (n > wv.pathCapacity) n = wv.pathCapacity;
     const int R = wv.shadowRays;
@@ -240,11 +256,13 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp, const WaveView wv, const 
 // QUEUED: the visibility comes from k_wf_shadow's counters and bounce hits go to the next queue
 // (the lean form: no shadow code at all); otherwise shadows are evaluated in place, and with
 // tail != 0 the whole remaining chain is.
-template <bool QUEUED>
+template <bool QUEUED, bool BATCH>
 __global__ void WF_SHADE_BOUNDS
-k_wf_shade(const DevFrame fr, const FramePointers fp, const WaveView wv, const int which, const int depth,
-           const int tailArg) {
+k_wf_shade(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
+           const int tailArg, const BatchSlice* __restrict__ batch) {
     const int tail = QUEUED ? 0 : tailArg;
+    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
+    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     __shared__ __align__(8) uint64_t stageBar;
     unsigned int n = wv.qCount[depth];
     if (n > wv.pathCapacity) n = wv.pathCapacity;
@@ -349,8 +367,13 @@ __device__ __forceinline__ float4 fold_path(const WaveView& wv, size_t path) {
     return c;
 }
 
+template <bool BATCH>
 __global__ void __launch_bounds__(kWfThreads)
-k_wf_resolve_warp(const DevFrame fr, const BandView band, const ActiveList list, const WaveView wv, const int lgSpp) {
+k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list_, const WaveView wv_, const int lgSpp,
+                  const BatchSlice* __restrict__ batch) {
+    const BandView& band = BATCH ? batch[blockIdx.y].band : band_;
+    const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
+    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     __shared__ __align__(16) float stageAll[kWfThreads / 32][kWarpStageFloats];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int count = *list.count;
@@ -383,8 +406,13 @@ k_wf_resolve_warp(const DevFrame fr, const BandView band, const ActiveList list,
 }
 
 // any spp: one thread sums a pixel's folded samples in order
+template <bool BATCH>
 __global__ void __launch_bounds__(kWfThreads)
-k_wf_resolve_pixel(const DevFrame fr, const BandView band, const ActiveList list, const WaveView wv) {
+k_wf_resolve_pixel(const DevFrame fr, const BandView band_, const ActiveList list_, const WaveView wv_,
+                   const BatchSlice* __restrict__ batch) {
+    const BandView& band = BATCH ? batch[blockIdx.y].band : band_;
+    const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
+    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     unsigned int count = *list.count;
     if (count > list.capacity) count = list.capacity;
     if (count > wv.slotCapacity) count = wv.slotCapacity;
@@ -396,6 +424,14 @@ k_wf_resolve_pixel(const DevFrame fr, const BandView band, const ActiveList list
         for (int s = 0; s < spp; ++s) acc = add4(acc, fold_path(wv, static_cast<size_t>(slot) * spp + s));
         store_pixel(band, sp.x, scale4(acc, fr.inv_spp));
     }
+}
+
+// zeroes the active-pixel counter and the queue counters of every scene of a batch
+__global__ void k_batch_reset(const BatchSlice* __restrict__ batch, const int nScenes, const int nQueueCounters) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nScenes) return;
+    *batch[s].list.count = 0u;
+    for (int i = 0; i < nQueueCounters; ++i) batch[s].wave.qCount[i] = 0u;
 }
 
 int log2_pow2_le32(int v) {
@@ -468,12 +504,19 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
     return true;
 }
 
+void launch_batch_reset(const BatchSlice* batch, int nScenes, int levels, cudaStream_t stream) {
+    if (nScenes > 0) k_batch_reset<<<(nScenes + 127) / 128, 128, 0, stream>>>(batch, nScenes, levels + 3);
+}
+
 void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                      const WaveView& wv, unsigned int* groupCounter, cudaStream_t stream, int* launches) {
+                      const WaveView& wv, unsigned int* groupCounter, cudaStream_t stream, int* launches,
+                      const BatchSlice* batch, int nScenes) {
     int n = 0;
     const int grid = wv.gridBlocks;
-    cudaMemsetAsync(wv.qCount, 0, sizeof(unsigned int) * (wv.levels + 3), stream);
-    k_wf_hit0<<<grid, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv);
+    const unsigned int ny = batch ? static_cast<unsigned int>(nScenes) : 1u;
+    // a batch's queue counters are zeroed by the caller (one memset over all scenes)
+    if (!batch) cudaMemsetAsync(wv.qCount, 0, sizeof(unsigned int) * (wv.levels + 3), stream);
+    if (batch) k_wf_hit0<true><<<dim3(grid, ny), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv, batch); else k_wf_hit0<false><<<dim3(grid, ny), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv, batch);
     ++n;
     if (fr.max_bounces >= 0) {
         // depths 0 .. queueLevels-1: seed / shadow / shade over the queue of that depth;
@@ -484,40 +527,46 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
             // Deeper queues are much shorter (~8 % of the primary hits at depth 1, then ~75 % of the
             // previous level), but blocks beyond a queue's end return at once, and a short queue
             // spread over every SM finishes sooner than one packed into a few resident blocks.
-            const int g = depth == 0 ? grid : std::max(1, grid / std::max(1, wv.deepGridDiv));
+            const dim3 g(depth == 0 ? grid : std::max(1, grid / std::max(1, wv.deepGridDiv)), ny);
             if (wv.shadowMode == kShadowSoft) {
-                k_wf_seed<<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+                { if (batch) k_wf_seed<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch); else k_wf_seed<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch); }
                 ++n;
             } else if (wv.shadowMode == kShadowHard) {
-                k_wf_prep_hard<<<g, kWfThreads, 0, stream>>>(fr, fp, wv, which, depth);
+                { if (batch) k_wf_prep_hard<true><<<g, kWfThreads, 0, stream>>>(fr, fp, wv, which, depth, batch); else k_wf_prep_hard<false><<<g, kWfThreads, 0, stream>>>(fr, fp, wv, which, depth, batch); }
                 ++n;
             }
             if (wv.shadowMode != kShadowInThread) {
-                if (wv.shadowPrefetch)
-                    k_wf_shadow<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+                if (batch)
+                    k_wf_shadow<false, true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
+                else if (wv.shadowPrefetch)
+                    k_wf_shadow<true, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
                 else
-                    k_wf_shadow<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth);
+                    k_wf_shadow<false, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
                 ++n;
             }
-            if (wv.shadowMode != kShadowInThread)
-                k_wf_shade<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0);
-            else
-                k_wf_shade<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0);
+            if (wv.shadowMode != kShadowInThread) {
+                if (batch) k_wf_shade<true, true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0, batch); else k_wf_shade<true, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0, batch);
+            } else {
+                if (batch) k_wf_shade<false, true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0, batch); else k_wf_shade<false, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0, batch);
+            }
             ++n;
         }
         if (queued <= wv.levels) {
-            k_wf_shade<false><<<std::max(1, grid / std::max(1, wv.deepGridDiv)), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, queued & 1, queued, 1);
+            const dim3 g(std::max(1, grid / std::max(1, wv.deepGridDiv)), ny);
+            if (batch) k_wf_shade<false, true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, queued & 1, queued, 1, batch); else k_wf_shade<false, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, queued & 1, queued, 1, batch);
             ++n;
         }
     }
     const int lg = log2_pow2_le32(fr.spp);
-    if (lg >= 0)
-        k_wf_resolve_warp<<<grid, kWfThreads, 0, stream>>>(fr, band, list, wv, lg);
-    else
-        k_wf_resolve_pixel<<<grid, kWfThreads, 0, stream>>>(fr, band, list, wv);
+    if (lg >= 0) {
+        if (batch) k_wf_resolve_warp<true><<<dim3(grid, ny), kWfThreads, 0, stream>>>(fr, band, list, wv, lg, batch); else k_wf_resolve_warp<false><<<dim3(grid, ny), kWfThreads, 0, stream>>>(fr, band, list, wv, lg, batch);
+    } else {
+        if (batch) k_wf_resolve_pixel<true><<<dim3(grid, ny), kWfThreads, 0, stream>>>(fr, band, list, wv, batch); else k_wf_resolve_pixel<false><<<dim3(grid, ny), kWfThreads, 0, stream>>>(fr, band, list, wv, batch);
+    }
     ++n;
     // pixels the queues could not take: megakernel, starting at the first slot beyond them
-    if (wv.slotCapacity < list.capacity) {
+    // (never in a batch: its queues are sized for every pixel of a scene)
+    if (!batch && wv.slotCapacity < list.capacity) {
         launch_shade(fr, fp, band, list, grid, groupCounter, wv.slotCapacity, stream);
         ++n;
     }

@@ -59,6 +59,17 @@ enum : int {
     kShadowInThread = 2   // rare forms (N > 113, N <= 1, radius < 1e-4): evaluated inside k_wf_shade
 };
 
+// One scene of a batched launch (many skins per launch).  Scenes that share a frame
+// description (image size, sampling, camera, light, box layout) are rendered by the same launches:
+// blockIdx.y picks the scene, and with it the scene's boxes and texels, its output image, its work
+// list and its queues.  A null batch pointer means the single scene passed by value.
+struct BatchSlice {
+    FramePointers fp;
+    BandView band;
+    ActiveList list;
+    WaveView wave;
+};
+
 // Bytes of queue / path storage needed per path for a frame description.
 size_t wavefront_bytes_per_path(const DevFrame& fr);
 // Carves the views out of one allocation of at least pathCapacity * wavefront_bytes_per_path bytes
@@ -69,7 +80,16 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
 
 // Shades every listed pixel (slots < wave.slotCapacity through the wavefront, the rest through the
 // megakernel) and writes the band image.  groupCounter: zeroed device counter.
+// batch / nScenes: device array of per-scene slices and its length (launches get gridDim.y = nScenes);
+// every slice must have slotCapacity >= its list's capacity (no megakernel overflow in batches).
 void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                      const WaveView& wave, unsigned int* groupCounter, cudaStream_t stream, int* launches);
+                      const WaveView& wave, unsigned int* groupCounter, cudaStream_t stream, int* launches,
+                      const BatchSlice* batch = nullptr, int nScenes = 1);
+void launch_batch_reset(const BatchSlice* batch, int nScenes, int levels, cudaStream_t stream);
+// The primary pass over the scenes of a batch (pixel-per-lane kernels only): returns false if the
+// frame description needs one of the other primary kernels, which have no batched form.
+bool launch_primary_batch(const DevFrame& fr, const BandView& band, uint32_t* tileStates, bool seedTiles,
+                          const BatchSlice* batch, int nScenes, unsigned int blobBytes, int primaryTargetBlocks,
+                          cudaStream_t stream);
 
 }  // namespace mcskin

@@ -397,25 +397,55 @@ def test_headline_frame_properties(gpu, oracle):
         ctx.close()
 
 
-def test_batch_of_skins(gpu, oracle):
-    """mcskin_cuda_context_render_batch (BASELINE config 4 in miniature): many skins, one config."""
+@pytest.mark.parametrize("mode", ["grouped", "grouped_small_groups", "frame_by_frame"])
+def test_batch_of_skins(gpu, oracle, mode):
+    """mcskin_cuda_context_render_batch (BASELINE config 4 in miniature): many skins, one config.
+    grouped: scenes with equal frame descriptions share launches (gridDim.y = scene);
+    frame_by_frame: one frame at a time over the context's lanes."""
     import torch
     n = 24
     cfg = make_config(width=64, height=64, samples_per_pixel=4, max_bounces=2)
     scenes = [_scene(gpu, 100 + i, "legacy" if i % 5 == 0 else "64x64", [None, "walking", "dab"][i % 3]) for i in range(n)]
     ctx = gpu.Context(0)
     try:
+        if mode == "frame_by_frame":
+            ctx.set_option("batch_mode", 0)
+        if mode == "grouped_small_groups":
+            ctx.set_option("batch_group", 7)   # chunks of 7 scenes: 24 = 7 + 7 + 7 + 3, several groups per chunk
         out = torch.zeros((n, 64, 64, 4), dtype=torch.float32, device="cuda:0")
         out_u8 = torch.zeros((n, 64, 64, 4), dtype=torch.uint8, device="cuda:0")
         torch.cuda.synchronize()
-        ctx.render_batch(scenes, cfg, out.data_ptr(), out_u8.data_ptr(), 0)
-        ctx.sync()
+        for _ in range(2):  # twice: buffers and staging are reused
+            ctx.render_batch(scenes, cfg, out.data_ptr(), out_u8.data_ptr(), 0)
+            ctx.sync()
         got = out.cpu().numpy()
-        for i in (0, 1, 5, 11, 23):
+        for i in (0, 1, 5, 6, 7, 11, 20, 23):
             single, _, _ = gpu.render(scenes[i], cfg)
             assert np.array_equal(_bits(got[i]), _bits(single)), i          # batched == one at a time
+        for i in (0, 5, 23):
             assert pixel_report(got[i], oracle.render(scenes[i], cfg), oracle.quantize)["within1"] >= 0.999
         assert np.array_equal(out_u8.cpu().numpy(), oracle.quantize(got))
+    finally:
+        ctx.close()
+
+
+def test_batch_headline_shape(gpu, oracle):
+    """BASELINE config 4's frame shape (256x256, 4 spp, 2 bounces) for a few dozen skins in one grouped batch."""
+    import torch
+    n = 40
+    cfg = make_config(width=256, height=256, samples_per_pixel=4, max_bounces=2)
+    scenes = [_scene(gpu, i) for i in range(n)]
+    ctx = gpu.Context(0)
+    try:
+        out = torch.zeros((n, 256, 256, 4), dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        ctx.render_batch(scenes, cfg, out.data_ptr(), 0, 0)
+        ctx.sync()
+        got = out.cpu().numpy()
+        for i in (0, 17, 39):
+            single, _, _ = gpu.render(scenes[i], cfg)
+            assert np.array_equal(_bits(got[i]), _bits(single)), i
+        assert pixel_report(got[3], oracle.render(scenes[3], cfg), oracle.quantize)["within1"] >= 0.999
     finally:
         ctx.close()
 
