@@ -243,6 +243,11 @@ int32_t mcskin_cuda_sincos(int32_t device, const float* angles, int32_t n, float
 /* The same arithmetic evaluated on the host (no device needed): lets a CPU-only test pin the
  * restated algorithm to the host's libm. */
 void mcskin_sincos_model(const float* angles, int32_t n, float* out_sin, float* out_cos);
+/* std::pow(x, y) for floats as the device evaluates the Blinn-Phong exponent (shading.cpp:90):
+ * bit-identical to glibc's powf on an FMA-capable x86-64 host for finite positive x and finite
+ * non-zero y below the overflow threshold.  mcskin_powf_model is the same arithmetic on the host. */
+int32_t mcskin_cuda_powf(int32_t device, const float* x, const float* y, int32_t n, float* out);
+void mcskin_powf_model(const float* x, const float* y, int32_t n, float* out);
 /* Hit mask + triangle id of the pinhole ray through each pixel centre
  * (u=(px+.5)/W, v=(py+.5)/H): out_tri_id[py*W+px] = box*12+face*2, or -1. */
 int32_t mcskin_cuda_aov(const McScene* scene, const McConfig* cfg, int32_t device, int32_t* out_tri_id);

@@ -1312,6 +1312,21 @@ int32_t mcskin_cuda_background(const McScene* scene, const McConfig* cfg, int32_
     return st.down(out, dO, sizeof(float4) * n);
 }
 
+int32_t mcskin_cuda_powf(int32_t device, const float* x, const float* y, int32_t n, float* out) {
+    if (n < 0 || (n > 0 && (!x || !y || !out))) return fail(MC_ERR_INVALID, "powf: bad argument");
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = shared_context(device, &ctx);
+    if (rc != MC_OK) return rc;
+    Staged st{ctx, {}};
+    void *dX, *dY, *dO;
+    if ((rc = st.up(x, sizeof(float) * n, &dX)) != MC_OK) return rc;
+    if ((rc = st.up(y, sizeof(float) * n, &dY)) != MC_OK) return rc;
+    if ((rc = st.up(nullptr, sizeof(float) * n, &dO)) != MC_OK) return rc;
+    launch_powf(static_cast<float*>(dX), static_cast<float*>(dY), n, static_cast<float*>(dO), ctx->stream);
+    return st.down(out, dO, sizeof(float) * n);
+}
+
 int32_t mcskin_cuda_sincos(int32_t device, const float* angles, int32_t n, float* outSin, float* outCos) {
     if (n < 0 || (n > 0 && (!angles || !outSin || !outCos))) return fail(MC_ERR_INVALID, "sincos: bad argument");
     std::lock_guard<std::mutex> lock(g_ctxMutex);

@@ -79,6 +79,72 @@ __device__ __forceinline__ void sincos_ref(float a, float* sn, float* cs) {
     *cs = (n & 1) ? fs : fc;
 }
 
+// powf(x, y) bit-identical to glibc 2.39's (x86-64 FMA variant; sysdeps/ieee754/flt-32/e_powf.c):
+// log2(x) from a 16-entry table of reciprocals plus a degree-5 polynomial, y*log2(x) in double,
+// exp2 from a 32-entry table plus a cubic, one rounding to float.  Tables are __powf_log2_data and
+// __exp2f_data; every a*b+c of the source is fused in the host binary, hence the explicit fma().
+// Checked on the host against libm for every positive float x <= 2 and nine exponents.  Zero,
+// negative, infinite or NaN x, zero / infinite / NaN y and results beyond 2^127.99 take CUDA's powf
+// (same special values).
+static __device__ const double kPowLog2Tab[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2}, {0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2},
+    {0x1.49539f0f010b0p+0, -0x1.7418b0a1fb77bp-2}, {0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2},
+    {0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2}, {0x1.25e227b0b8ea0p+0, -0x1.97c1d1b3b7af0p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3}, {0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4},
+    {0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5}, {0x1.0000000000000p+0, 0x0.0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4},  {0x1.ca4b31f026aa0p-1, 0x1.476a9543891bap-3},
+    {0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2},
+    {0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2},  {0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2}};
+static __device__ const unsigned long long kPowExp2Tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+static __device__ __noinline__ float powf_ref(float x, float y) {
+    uint32_t ix = __float_as_uint(x);
+    const uint32_t iy = __float_as_uint(y);
+    if (2u * iy - 1u > 0xfefffffeu) return powf(x, y);           // y is 0, inf or NaN
+    if (ix - 0x00800000u > 0x7effffffu) {
+        if (ix == 0u || ix >= 0x00800000u) return powf(x, y);    // x is 0, negative, inf or NaN
+        ix = __float_as_uint(x * 0x1p23f) & 0x7fffffffu;         // subnormal: normalise
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 19) & 15;
+    const uint32_t top = tmp & 0xff800000u;
+    const int k = static_cast<int>(top) >> 23;
+    const double z = static_cast<double>(__uint_as_float(ix - top));
+    const double r = fma(z, kPowLog2Tab[i][0], -1.0);
+    const double y0 = kPowLog2Tab[i][1] + static_cast<double>(k);
+    const double r2 = r * r;
+    double p = fma(0x1.27616c9496e0bp-2, r, -0x1.71969a075c67ap-2);
+    const double p1 = fma(0x1.ec70a6ca7baddp-2, r, -0x1.7154748bef6c8p-1);
+    double q = fma(0x1.71547652ab82bp+0, r, y0);
+    const double r4 = r2 * r2;
+    q = fma(p1, r2, q);
+    p = fma(p, r4, q);                                           // log2(x)
+    const double ylogx = static_cast<double>(y) * p;
+    if (((static_cast<unsigned long long>(__double_as_longlong(ylogx)) >> 47) & 0xffffull) > 0x80beull) {  // |y log2 x| >= 126
+        if (ylogx > 0x1.fffffffa3aae2p+6) return powf(x, y);     // overflow side
+        if (ylogx <= -150.0) return 0.0f;                        // __math_uflowf
+        if (ylogx < -149.0) return __uint_as_float(1u);          // __math_may_uflowf: 0x1.4p-75f squared = 2^-149
+    }
+    double kd = ylogx + 0x1.8p+47;
+    const unsigned long long ki = static_cast<unsigned long long>(__double_as_longlong(kd));
+    kd -= 0x1.8p+47;
+    const double rr = ylogx - kd;
+    const double s = __longlong_as_double(static_cast<long long>(kPowExp2Tab[ki & 31ull] + (ki << 47)));
+    const double zz = fma(0x1.c6af84b912394p-5, rr, 0x1.ebfce50fac4f3p-3);
+    const double rr2 = rr * rr;
+    double e = fma(0x1.62e42ff0c52d6p-1, rr, 1.0);
+    e = fma(zz, rr2, e);
+    return static_cast<float>(e * s);
+}
+
 // generateDOFRay; r1, r2 are the two lens draws that follow the jitter draws.
 __device__ __forceinline__ Ray dof_ray(const DevFrame& fr, float u, float v, float r1, float r2) {
     const Ray pin = camera_ray(fr, u, v);
@@ -232,7 +298,7 @@ __device__ __forceinline__ float4 shade_lit(const DevFrame& fr, V3 P, V3 normal,
     const float kdiff = fr.kd * ndl * vis;
     const V3 H = normalize3(L + V);
     const float ndh = fmaxf(0.0f, dot3(N, H));
-    const float spec = powf(ndh, fr.shininess);
+    const float spec = powf_ref(ndh, fr.shininess);  // std::pow(NdotH, shininess), shading.cpp:90
     const float kspec = fr.ks * spec * vis;
     float4 out;
     out.x = (tex.x * fr.ambient + tex.x * fr.light_color[0] * kdiff) + fr.light_color[0] * kspec;

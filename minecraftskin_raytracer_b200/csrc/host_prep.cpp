@@ -426,3 +426,74 @@ extern "C" void mcskin_sincos_model(const float* angles, int32_t n, float* outSi
         outCos[i] = (nq & 1) ? fs : fc;
     }
 }
+
+// Host model of the device's powf_ref (dev_shade.cuh): glibc 2.39 powf as built for x86-64 with FMA.
+namespace {
+const double kPowLog2Tab[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2}, {0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2},
+    {0x1.49539f0f010b0p+0, -0x1.7418b0a1fb77bp-2}, {0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2},
+    {0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2}, {0x1.25e227b0b8ea0p+0, -0x1.97c1d1b3b7af0p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3}, {0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4},
+    {0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5}, {0x1.0000000000000p+0, 0x0.0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4},  {0x1.ca4b31f026aa0p-1, 0x1.476a9543891bap-3},
+    {0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2},
+    {0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2},  {0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2}};
+const uint64_t kPowExp2Tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+uint32_t bits_of(float f) { uint32_t u; std::memcpy(&u, &f, sizeof(u)); return u; }
+float float_of(uint32_t u) { float f; std::memcpy(&f, &u, sizeof(f)); return f; }
+uint64_t bits_of(double f) { uint64_t u; std::memcpy(&u, &f, sizeof(u)); return u; }
+float powf_model(float x, float y) {
+    uint32_t ix = bits_of(x);
+    const uint32_t iy = bits_of(y);
+    if (2u * iy - 1u > 0xfefffffeu) return std::pow(x, y);
+    if (ix - 0x00800000u > 0x7effffffu) {
+        if (ix == 0u || ix >= 0x00800000u) return std::pow(x, y);
+        ix = bits_of(x * 0x1p23f) & 0x7fffffffu;
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 19) & 15;
+    const uint32_t top = tmp & 0xff800000u;
+    const int k = static_cast<int32_t>(top) >> 23;
+    const double z = static_cast<double>(float_of(ix - top));
+    const double r = std::fma(z, kPowLog2Tab[i][0], -1.0);
+    const double y0 = kPowLog2Tab[i][1] + static_cast<double>(k);
+    const double r2 = r * r;
+    double p = std::fma(0x1.27616c9496e0bp-2, r, -0x1.71969a075c67ap-2);
+    const double p1 = std::fma(0x1.ec70a6ca7baddp-2, r, -0x1.7154748bef6c8p-1);
+    double q = std::fma(0x1.71547652ab82bp+0, r, y0);
+    const double r4 = r2 * r2;
+    q = std::fma(p1, r2, q);
+    p = std::fma(p, r4, q);
+    const double ylogx = static_cast<double>(y) * p;
+    if (((bits_of(ylogx) >> 47) & 0xffffull) > 0x80beull) {
+        if (ylogx > 0x1.fffffffa3aae2p+6) return std::pow(x, y);
+        if (ylogx <= -150.0) return 0.0f;
+        if (ylogx < -149.0) return float_of(1u);
+    }
+    double kd = ylogx + 0x1.8p+47;
+    const uint64_t ki = bits_of(kd);
+    kd -= 0x1.8p+47;
+    const double rr = ylogx - kd;
+    const uint64_t sb = kPowExp2Tab[ki & 31ull] + (ki << 47);
+    double s;
+    std::memcpy(&s, &sb, sizeof(s));
+    const double zz = std::fma(0x1.c6af84b912394p-5, rr, 0x1.ebfce50fac4f3p-3);
+    const double rr2 = rr * rr;
+    double e = std::fma(0x1.62e42ff0c52d6p-1, rr, 1.0);
+    e = std::fma(zz, rr2, e);
+    return static_cast<float>(e * s);
+}
+}  // namespace
+
+extern "C" void mcskin_powf_model(const float* x, const float* y, int32_t n, float* out) {
+    for (int32_t i = 0; i < n; ++i) out[i] = powf_model(x[i], y[i]);
+}

@@ -881,6 +881,11 @@ __global__ void k_background(const DevFrame fr, const float* uv, int n, float4* 
     out[i] = fr.use_config ? config_background(fr, uv[2 * i], uv[2 * i + 1]) : flat_background(fr);
 }
 
+__global__ void k_powf(const float* x, const float* y, int n, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = powf_ref(x[i], y[i]);
+}
+
 __global__ void k_sincos(const float* angles, int n, float* outSin, float* outCos) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1038,6 +1043,9 @@ void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out
 }
 void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream) {
     if (n > 0) k_background<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, uv, n, out);
+}
+void launch_powf(const float* x, const float* y, int n, float* out, cudaStream_t stream) {
+    if (n > 0) k_powf<<<blocks_for(n), kBlockThreads, 0, stream>>>(x, y, n, out);
 }
 void launch_sincos(const float* angles, int n, float* outSin, float* outCos, cudaStream_t stream) {
     if (n > 0) k_sincos<<<blocks_for(n), kBlockThreads, 0, stream>>>(angles, n, outSin, outCos);

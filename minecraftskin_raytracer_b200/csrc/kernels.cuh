@@ -73,6 +73,7 @@ void launch_ambient_occlusion(const DevFrame& fr, const FramePointers& fp, const
                               cudaStream_t stream);
 void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out, cudaStream_t stream);
 void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream);
+void launch_powf(const float* x, const float* y, int n, float* out, cudaStream_t stream);
 void launch_sincos(const float* angles, int n, float* outSin, float* outCos, cudaStream_t stream);
 void launch_aov(const DevFrame& fr, const FramePointers& fp, int* outTriId, cudaStream_t stream);
 

@@ -33,7 +33,7 @@ EXPORTS = [
     "mcskin_cuda_intersect", "mcskin_cuda_trace", "mcskin_cuda_shade", "mcskin_cuda_in_shadow",
     "mcskin_cuda_soft_shadow", "mcskin_cuda_ambient_occlusion", "mcskin_cuda_generate_rays",
     "mcskin_cuda_background", "mcskin_cuda_aov", "mcskin_build_skin_scene", "mcskin_cuda_sincos",
-    "mcskin_sincos_model",
+    "mcskin_sincos_model", "mcskin_cuda_powf", "mcskin_powf_model",
 ]
 
 
@@ -319,6 +319,22 @@ def sincos(angles, device: int = 0):
     _check(_lib.mcskin_cuda_sincos(C.c_int32(device), _ptr(a, C.c_float), C.c_int32(len(a)), _ptr(sn, C.c_float),
                                    _ptr(cs, C.c_float)))
     return sn, cs
+
+
+def powf(x, y, device: int = 0) -> np.ndarray:
+    """std::pow(x, y) for float32 arrays as the shading kernels evaluate it."""
+    x, y = _f32(x, (-1,)), _f32(y, (-1,))
+    out = np.zeros(len(x), dtype=np.float32)
+    _check(_lib.mcskin_cuda_powf(C.c_int32(device), _ptr(x, C.c_float), _ptr(y, C.c_float), C.c_int32(len(x)), _ptr(out, C.c_float)))
+    return out
+
+
+def powf_model(x, y) -> np.ndarray:
+    """The device's powf arithmetic evaluated on the host (needs no GPU)."""
+    x, y = _f32(x, (-1,)), _f32(y, (-1,))
+    out = np.zeros(len(x), dtype=np.float32)
+    _lib.mcskin_powf_model(_ptr(x, C.c_float), _ptr(y, C.c_float), C.c_int32(len(x)), _ptr(out, C.c_float))
+    return out
 
 
 def sincos_model(angles):

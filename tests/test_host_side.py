@@ -158,3 +158,30 @@ def test_sincos_model_equals_libm(mclib):
     got_s, got_c = mclib.sincos_model(a)
     assert np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32))
     assert np.array_equal(got_c.view(np.uint32), want_c.view(np.uint32))
+
+
+def _libm_powf(x, y):
+    import ctypes.util
+    libm = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.powf.restype = C.c_float
+    libm.powf.argtypes = [C.c_float, C.c_float]
+    return np.array([libm.powf(float(a), float(b)) for a, b in zip(x, y)], dtype=np.float32)
+
+
+def powf_test_values(n=100_000, seed=11):
+    """(x, y) pairs: N.H values in [0, 1] raised to shininess-like exponents, plus the ranges where the
+    result underflows, subnormal x, x slightly above 1, and special values that take the fallback."""
+    rng = np.random.default_rng(seed)
+    x = [rng.random(n).astype(np.float32), (1.0 - rng.random(n // 4) ** 4).astype(np.float32),
+         rng.integers(1, 0x40000000, size=n // 2, dtype=np.uint32).view(np.float32),      # any positive float <= 2
+         np.array([0.0, 1.0, 1.0000001, 0.99999994, 1e-39, 5e-45, 0.5, 2.0], dtype=np.float32)]
+    x = np.concatenate(x)
+    y = rng.choice(np.array([16.0, 32.0, 8.0, 64.0, 1.0, 2.0, 0.5, 100.5, 3.7, 12.25], dtype=np.float32), size=len(x))
+    return x.astype(np.float32), y.astype(np.float32)
+
+
+@pytest.mark.skipif(not _host_has_fma(), reason="glibc selects its non-FMA powf on this CPU")
+def test_powf_model_equals_libm(mclib):
+    x, y = powf_test_values(40_000)
+    got = mclib.powf_model(x, y)
+    assert np.array_equal(got.view(np.uint32), _libm_powf(x, y).view(np.uint32))
