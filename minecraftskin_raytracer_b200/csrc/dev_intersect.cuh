@@ -461,17 +461,45 @@ __device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from
     const V3 inv = mk3(rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z));
     const float growFull = radius * 1.01f + 0.01f;
     uint32_t mask = 0u;
+    if (fabsf(d.x) < 1e-6f || fabsf(d.y) < 1e-6f || fabsf(d.z) < 1e-6f) {
+        // the centre segment does not move along some axis (rare): the general clip
+        for (int i = 0; i < n; ++i) {
+            // sc.lo / sc.hi: the box itself, or for a posed box a world-space box that contains it
+            const float4 L = sc.lo[i];
+            const float4 H = sc.hi[i];
+            if (__float_as_uint(L.w) & kBoxEmpty) continue;
+            const V3 lo = mk3(L.x, L.y, L.z), hi = mk3(H.x, H.y, H.z);
+            float sEnd;
+            if (!bundle_clip(from, d, inv, lo, hi, growFull, &sEnd)) continue;
+            const float reach = fminf(fmaxf(sEnd + 1e-3f, 0.0f), 1.0f);
+            float unused;
+            if (!bundle_clip(from, d, inv, lo, hi, reach * radius * 1.01f + 0.01f, &unused)) continue;
+            mask |= 1u << i;
+        }
+        return mask;
+    }
+    // Every axis moves: growing a slab by g widens its parameter interval by g*|1/d| at both ends,
+    // so the slab fractions of the ungrown box are computed once and serve both passes.
+    const V3 ainv = mk3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
+    const V3 g1 = ainv * growFull;
     for (int i = 0; i < n; ++i) {
-        // sc.lo / sc.hi: the box itself, or for a posed box a world-space box that contains it
         const float4 L = sc.lo[i];
         const float4 H = sc.hi[i];
         if (__float_as_uint(L.w) & kBoxEmpty) continue;
-        const V3 lo = mk3(L.x, L.y, L.z), hi = mk3(H.x, H.y, H.z);
-        float sEnd;
-        if (!bundle_clip(from, d, inv, lo, hi, growFull, &sEnd)) continue;
-        const float reach = fminf(fmaxf(sEnd + 1e-3f, 0.0f), 1.0f);
-        float unused;
-        if (!bundle_clip(from, d, inv, lo, hi, reach * radius * 1.01f + 0.01f, &unused)) continue;
+        const float ax = (L.x - from.x) * inv.x, bx = (H.x - from.x) * inv.x;
+        const float ay = (L.y - from.y) * inv.y, by = (H.y - from.y) * inv.y;
+        const float az = (L.z - from.z) * inv.z, bz = (H.z - from.z) * inv.z;
+        const float nx = fminf(ax, bx), fx = fmaxf(ax, bx);
+        const float ny = fminf(ay, by), fy = fmaxf(ay, by);
+        const float nz = fminf(az, bz), fz = fmaxf(az, bz);
+        const float s0 = fmaxf(fmaxf(nx - g1.x, ny - g1.y), fmaxf(nz - g1.z, 0.0f));
+        const float s1 = fminf(fminf(fx + g1.x, fy + g1.y), fminf(fz + g1.z, 1.0f));
+        if (!(s0 <= s1 + 1e-3f)) continue;
+        const float reach = fminf(fmaxf(s1 + 1e-3f, 0.0f), 1.0f);
+        const V3 g2 = ainv * (reach * radius * 1.01f + 0.01f);
+        const float t0 = fmaxf(fmaxf(nx - g2.x, ny - g2.y), fmaxf(nz - g2.z, 0.0f));
+        const float t1 = fminf(fminf(fx + g2.x, fy + g2.y), fminf(fz + g2.z, 1.0f));
+        if (!(t0 <= t1 + 1e-3f)) continue;
         mask |= 1u << i;
     }
     return mask;

@@ -218,7 +218,7 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
             d.inv_size_x = ok ? 1.0f / d.size[0] : 0.0f;
             d.inv_size_y = ok ? 1.0f / d.size[1] : 0.0f;
             d.inv_size_z = ok ? 1.0f / d.size[2] : 0.0f;
-            if (ok) d.flags |= kBoxRecip;
+            if (ok) flags |= kBoxRecip;
         }
         d.inv_cx = d.inv_cz = d.fwd_cx = d.fwd_cz = 1.0f;
         if (src.has_rotation) {

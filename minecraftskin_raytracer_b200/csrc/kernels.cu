@@ -440,29 +440,35 @@ struct PixStreamSmem {
 };
 
 // One 624-word block of the stream: state[which] -> state[which^1], canonical floats into
-// the ring.  Three dependent phases of 227 / 227 / 170 words, one word per thread.
+// the ring.  New word j needs old words j, j+1 and, for j < 227, old word j+397, else NEW word
+// j-227: three dependent phases.  They are cut at 224 / 448 (not 227 / 454) so that each phase
+// fills whole warps — 7 + 7 + 5.5 warps issue instead of 8 + 8 + 6; words 224..226 of the
+// second phase still read their far operand from the old block.
 template <bool STORE>
 __device__ __forceinline__ void pix_stream_block(PixStreamSmem* sm, int which, unsigned int produced) {
-    static_assert(kBlockThreads >= kMtN - kMtM, "one thread per word of a phase");
+    constexpr int kCut = 224;
+    constexpr int kD = kMtN - kMtM;  // 227
+    static_assert(kBlockThreads >= kCut && kCut <= kD && 2 * kCut - kD <= kCut && kMtN - 2 * kCut <= kCut,
+                  "phase cuts must respect the 227-word dependency distance");
     const uint32_t* a = sm->state[which];
     uint32_t* b = sm->state[which ^ 1];
-    constexpr int kD = kMtN - kMtM;
     const int i = threadIdx.x;
-    if (i < kD) {
+    if (i < kCut) {
         const uint32_t v = mt_mix(a[i], a[i + 1], a[i + kMtM]);
         b[i] = v;
         if (STORE) sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
-    if (i < kD) {
-        const int j = kD + i;
-        const uint32_t v = mt_mix(a[j], a[j + 1], b[i]);
+    if (i < kCut) {
+        const int j = kCut + i;
+        const uint32_t far = (j < kD) ? a[j + kMtM] : b[j - kD];
+        const uint32_t v = mt_mix(a[j], a[j + 1], far);
         b[j] = v;
         if (STORE) sm->ring[pix_ring_slot(produced + j)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
-    if (i < kMtN - 2 * kD) {
-        const int j = 2 * kD + i;
+    if (i < kMtN - 2 * kCut) {
+        const int j = 2 * kCut + i;
         const uint32_t nextWord = (j + 1 == kMtN) ? b[0] : a[j + 1];
         const uint32_t v = mt_mix(a[j], nextWord, b[j - kD]);
         b[j] = v;
