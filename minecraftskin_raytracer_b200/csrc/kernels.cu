@@ -45,6 +45,38 @@ __device__ __forceinline__ TileGeom tile_geom(const DevFrame& fr, const BandView
     return g;
 }
 
+// Launch order of the tiles of a band: the tiles that intersect the figure's screen rectangle
+// first (their pixels shoot rays; they take several times as long as pure-background tiles), then
+// the rest, which are short and uniform and fill the end of the launch evenly.  Block-uniform
+// arithmetic; a bijection of [0, tiles of the band).
+__device__ __forceinline__ int heavy_first_tile(const DevFrame& fr, const BandView& band, int slot) {
+    if (!fr.rect_valid) return slot;
+    const int ts = fr.tile_size, W = fr.tiles_x;
+    const int tx0 = max(0, fr.rect_x0) / ts, tx1 = min(W - 1, fr.rect_x1 / ts);
+    const int ty0 = max(0, fr.rect_y0) / ts, ty1 = min(fr.tiles_y - 1, fr.rect_y1 / ts);
+    if (fr.rect_x1 < 0 || fr.rect_y1 < 0 || tx0 > tx1 || ty0 > ty1) return slot;
+    // local rows r whose frame tile row first + r*stride lies in [ty0, ty1]
+    const int first = band.first_tile_row, st = band.tile_row_stride;
+    const int r0 = ty0 <= first ? 0 : (ty0 - first + st - 1) / st;
+    const int r1 = ty1 < first ? -1 : min(band.n_tile_rows - 1, (ty1 - first) / st);
+    if (r0 > r1) return slot;
+    const int hw = tx1 - tx0 + 1, hr = r1 - r0 + 1;
+    if (slot < hw * hr) {
+        const int r = slot / hw;
+        return (r0 + r) * W + tx0 + (slot - r * hw);
+    }
+    slot -= hw * hr;
+    if (slot < r0 * W) return slot;  // the rows above keep their index
+    slot -= r0 * W;
+    const int sideW = W - hw;
+    if (slot < sideW * hr) {         // left and right of the rectangle
+        const int r = slot / sideW, c = slot - r * sideW;
+        return (r0 + r) * W + (c < tx0 ? c : c + hw);
+    }
+    slot -= sideW * hr;
+    return (r1 + 1) * W + slot;      // the rows below
+}
+
 __global__ void __launch_bounds__(kBlockThreads)
 k_primary_cta(const DevFrame fr, const FramePointers fp, const BandView band, const ActiveList list, const int classify) {
     __shared__ TileStreamSmem mt;
@@ -438,25 +470,42 @@ struct PixStreamSmem {
     uint32_t state[2][kMtN];
     float ring[kPixRingWords + kPixRingWords / 32];
 };
+// The compile-time sample loops know their round size (256 pixels x SPP*2 words), so their ring is
+// just that plus one 624-word block (rounded to 32) instead of the next power of two: 36 KB rather
+// than 66 KB at 16 spp, which lets four blocks instead of two share an SM.  Positions are kept
+// modulo the ring size with conditional subtractions (RING words; 0 selects the power-of-two ring).
+template <int RING>
+struct PixStreamSmemT {
+    uint32_t state[2][kMtN];
+    float ring[RING + RING / 32];
+};
+template <int RING>
+__device__ __forceinline__ int pix_ring_slot_mod(unsigned int pos) {  // pos < 2*RING
+    const unsigned int m = min(pos, pos - static_cast<unsigned int>(RING));  // pos - RING wraps to a huge value when pos < RING
+    return static_cast<int>(m + (m >> 5));
+}
 
 // One 624-word block of the stream: state[which] -> state[which^1], canonical floats into
 // the ring.  New word j needs old words j, j+1 and, for j < 227, old word j+397, else NEW word
 // j-227: three dependent phases.  They are cut at 224 / 448 (not 227 / 454) so that each phase
 // fills whole warps — 7 + 7 + 5.5 warps issue instead of 8 + 8 + 6; words 224..226 of the
 // second phase still read their far operand from the old block.
-template <bool STORE>
-__device__ __forceinline__ void pix_stream_block(PixStreamSmem* sm, int which, unsigned int produced) {
+// state: the two 624-word engine states; ring: the float ring; produced: words generated so far
+// (RING == 0) or that count modulo RING.
+template <bool STORE, int RING = 0>
+__device__ __forceinline__ void pix_stream_block(uint32_t (*state)[kMtN], float* ring, int which, unsigned int produced) {
     constexpr int kCut = 224;
     constexpr int kD = kMtN - kMtM;  // 227
     static_assert(kBlockThreads >= kCut && kCut <= kD && 2 * kCut - kD <= kCut && kMtN - 2 * kCut <= kCut,
                   "phase cuts must respect the 227-word dependency distance");
-    const uint32_t* a = sm->state[which];
-    uint32_t* b = sm->state[which ^ 1];
+    const uint32_t* a = state[which];
+    uint32_t* b = state[which ^ 1];
     const int i = threadIdx.x;
+    auto slot = [&](unsigned int n) { return RING > 0 ? pix_ring_slot_mod<(RING > 0 ? RING : 32)>(n) : pix_ring_slot(n); };
     if (i < kCut) {
         const uint32_t v = mt_mix(a[i], a[i + 1], a[i + kMtM]);
         b[i] = v;
-        if (STORE) sm->ring[pix_ring_slot(produced + i)] = mt_canonical(mt_temper(v));
+        if (STORE) ring[slot(produced + i)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
     if (i < kCut) {
@@ -464,7 +513,7 @@ __device__ __forceinline__ void pix_stream_block(PixStreamSmem* sm, int which, u
         const uint32_t far = (j < kD) ? a[j + kMtM] : b[j - kD];
         const uint32_t v = mt_mix(a[j], a[j + 1], far);
         b[j] = v;
-        if (STORE) sm->ring[pix_ring_slot(produced + j)] = mt_canonical(mt_temper(v));
+        if (STORE) ring[slot(produced + j)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
     if (i < kMtN - 2 * kCut) {
@@ -472,7 +521,7 @@ __device__ __forceinline__ void pix_stream_block(PixStreamSmem* sm, int which, u
         const uint32_t nextWord = (j + 1 == kMtN) ? b[0] : a[j + 1];
         const uint32_t v = mt_mix(a[j], nextWord, b[j - kD]);
         b[j] = v;
-        if (STORE) sm->ring[pix_ring_slot(produced + j)] = mt_canonical(mt_temper(v));
+        if (STORE) ring[slot(produced + j)] = mt_canonical(mt_temper(v));
     }
     __syncthreads();
 }
@@ -511,7 +560,8 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
     // With few tiles per launch (small frames, one GPU's share of a frame) a tile is split over
     // `parts` blocks, each taking every parts-th round of 256 pixels; a block reaches its rounds by
     // running the tile's generator forward without storing the words it does not need.
-    const int tileIndex = blockIdx.x / parts, part = blockIdx.x - tileIndex * parts;
+    const int tileSlot = blockIdx.x / parts, part = blockIdx.x - tileSlot * parts;
+    const int tileIndex = heavy_first_tile(fr, band, tileSlot);
     const TileGeom tg = tile_geom(fr, band, tileIndex);
     const int spp = fr.spp, dps = fr.draws_per_sample;
     const int nPix = tg.w * tg.h;
@@ -538,12 +588,12 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
             const unsigned int first = static_cast<unsigned int>(q0) * wordsPerPixel;
             const unsigned int need = static_cast<unsigned int>(min(nPix, q0 + kBlockThreads)) * wordsPerPixel;
             while (produced + kMtN <= first) {  // words of rounds other blocks take: state only
-                pix_stream_block<false>(mt, which, produced);
+                pix_stream_block<false>(mt->state, mt->ring, which, produced);
                 which ^= 1;
                 produced += kMtN;
             }
             while (produced < need) {  // block-uniform
-                pix_stream_block<true>(mt, which, produced);
+                pix_stream_block<true>(mt->state, mt->ring, which, produced);
                 which ^= 1;
                 produced += kMtN;
             }
@@ -622,11 +672,14 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
     const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
     const BandView& band = BATCH ? batch[blockIdx.y].band : band_;
     const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
-    PixStreamSmem* mt = reinterpret_cast<PixStreamSmem*>(g_pixSmem);
-    unsigned char* sceneSmem = g_pixSmem + ((sizeof(PixStreamSmem) + 15) & ~size_t(15));
+    constexpr int kRing = (kBlockThreads * kWords + kMtN + 31) / 32 * 32;  // one round + one engine block
+    using Smem = PixStreamSmemT<kRing>;
+    Smem* mt = reinterpret_cast<Smem*>(g_pixSmem);
+    unsigned char* sceneSmem = g_pixSmem + ((sizeof(Smem) + 15) & ~size_t(15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tileIndex = blockIdx.x / parts, part = blockIdx.x - tileIndex * parts;
+    const int tileSlot = blockIdx.x / parts, part = blockIdx.x - tileSlot * parts;
+    const int tileIndex = heavy_first_tile(fr, band, tileSlot);
     const TileGeom tg = tile_geom(fr, band, tileIndex);
     const int nPix = tg.w * tg.h;
     if (part * kBlockThreads >= nPix) return;
@@ -641,7 +694,7 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
         __syncthreads();
     }
     int which = 0;
-    unsigned int produced = 0u;
+    unsigned int produced = 0u, producedMod = 0u;  // words generated; the same modulo the ring size
     const bool wPow2 = (tg.w & (tg.w - 1)) == 0;
     const int lgW = 31 - __clz(tg.w);
     const float W = fr.width_f, H = fr.height_f, rW = fr.inv_width_f, rH = fr.inv_height_f;
@@ -654,14 +707,18 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
             const unsigned int first = static_cast<unsigned int>(q0) * kWords;
             const unsigned int need = static_cast<unsigned int>(min(nPix, q0 + kBlockThreads)) * kWords;
             while (produced + kMtN <= first) {
-                pix_stream_block<false>(mt, which, produced);
+                pix_stream_block<false, kRing>(mt->state, mt->ring, which, producedMod);
                 which ^= 1;
                 produced += kMtN;
+                producedMod += kMtN;
+                if (producedMod >= kRing) producedMod -= kRing;
             }
             while (produced < need) {
-                pix_stream_block<true>(mt, which, produced);
+                pix_stream_block<true, kRing>(mt->state, mt->ring, which, producedMod);
                 which ^= 1;
                 produced += kMtN;
+                producedMod += kMtN;
+                if (producedMod >= kRing) producedMod -= kRing;
             }
         }
         const int q = q0 + warp * 32 + lane;
@@ -671,7 +728,10 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
         const int px = tg.x + lx, py = tg.y + ly;
         const bool pixelCanHit = valid && tileCanHit &&
                                  (!fr.rect_valid || (px >= fr.rect_x0 && px <= fr.rect_x1 && py >= fr.rect_y0 && py <= fr.rect_y1));
-        const float* draws = mt->ring + pix_ring_slot(static_cast<unsigned int>(q) * kWords);
+        // this round's first word modulo the ring size (block-uniform), then this lane's pixel:
+        // a pixel's words are one contiguous, 32-aligned run, so they never straddle the wrap
+        const unsigned int roundMod = (static_cast<unsigned int>(q0) * kWords) % static_cast<unsigned int>(kRing);
+        const float* draws = mt->ring + pix_ring_slot_mod<kRing>(roundMod + static_cast<unsigned int>(warp * 32 + lane) * kWords);
         const float fx = static_cast<float>(px), fy = static_cast<float>(py);
         float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (valid) {
@@ -961,8 +1021,9 @@ static void launch_primary_pix(const DevFrame& fr, const FramePointers& fp, cons
     } while (0)
 #define MCSKIN_LAUNCH_PIX_FIXED(SPP, GRAD)                                                                       \
     do {                                                                                                        \
-        if (batch) k_primary_pix_fixed<SPP, GRAD, true><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts, batch);  \
-        else k_primary_pix_fixed<SPP, GRAD, false><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts, batch);       \
+        const size_t smem = ((sizeof(PixStreamSmemT<(kBlockThreads * SPP * 2 + kMtN + 31) / 32 * 32>) + 15) & ~size_t(15)) + blobBytes; \
+        if (batch) k_primary_pix_fixed<SPP, GRAD, true><<<grid, kBlockThreads, smem, stream>>>(fr, fp, band, list, tileStates, parts, batch);  \
+        else k_primary_pix_fixed<SPP, GRAD, false><<<grid, kBlockThreads, smem, stream>>>(fr, fp, band, list, tileStates, parts, batch);       \
     } while (0)
     if (fixedForm && fr.spp == 16 && fr.gradient_bg) MCSKIN_LAUNCH_PIX_FIXED(16, true);
     else if (fixedForm && fr.spp == 16) MCSKIN_LAUNCH_PIX_FIXED(16, false);
