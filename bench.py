@@ -220,11 +220,40 @@ def run_own_arm(args):
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
 
-    def step():
+    # N>1: every rank stores its tile rows straight into rank 0's frame over NVLink peer memory and the
+    # exchange step is a barrier ("p2p", default); or rank 0 gathers compact bands with NCCL ("gather").
+    exchange = os.environ.get("MCSKIN_EXCHANGE", "p2p") if world > 1 else "none"
+    peer = None
+    if exchange == "p2p":
+        try:
+            peer = bands.PeerFrame(lib, H, W, local_rank)
+            frame_u8 = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)  # this rank's rows, quantised (stays local)
+        except Exception as exc:  # noqa: BLE001  (no peer access between these devices)
+            print(f"bench.py: peer frame unavailable ({exc}); falling back to the NCCL gather", file=sys.stderr)
+            exchange, peer = "gather", None
+        ok = torch.tensor([1.0 if peer is not None else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1.0:
+            exchange, peer = "gather", None
+
+    def step_gather():
         ctx.render_bands(rank, world, band.data_ptr(), band_u8.data_ptr(), stream.cuda_stream)
         if world > 1:
-            # the path's only exchange: gather the bands on rank 0 (NCCL over NVLink), rows back in order
+            # gather the bands on rank 0 (NCCL over NVLink), rows back in order
             bands.gather_frame(band, frame, ts, gathered, row_index)
+
+    def step_p2p():
+        ctx.render_rows_into_frame(rank, world, peer.ptr, frame_u8.data_ptr(), stream.cuda_stream)
+        peer.fence()
+
+    step = step_p2p if exchange == "p2p" else step_gather
+    if exchange == "p2p":
+        # one frame each way: the peer-written frame must equal the gathered one bit for bit
+        step_gather()
+        step_p2p()
+        torch.cuda.synchronize(dev)
+        if rank == 0 and not torch.equal(peer.frame.view(torch.int32), frame.view(torch.int32)):
+            raise SystemExit("bench.py: peer-written frame differs from the gathered frame")
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -297,7 +326,9 @@ def run_own_arm(args):
             ctx.set_scene(scene, cfg)  # host -> device on every rank
             step()
             if rank == 0:
-                host.copy_(frame, non_blocking=True)
+                host.copy_(peer.frame if exchange == "p2p" else frame, non_blocking=True)
+            if exchange == "p2p":
+                peer.fence()  # the peers may overwrite the root's frame only after it has left for the host
             torch.cuda.synchronize(dev)
 
         for _ in range(2):
@@ -335,7 +366,9 @@ def run_own_arm(args):
         "config": {"workload": WORKLOAD, "width": W, "height": H, "spp": cfg.samples_per_pixel,
                    "max_bounces": cfg.max_bounces, "shadow_samples": cfg.shadow_samples, "tile_size": ts,
                    "skin": "synthetic 64x64 seed 0", "unique_rays_per_frame": unique_rays,
-                   "partition": "whole frame" if world == 1 else f"interleaved tile rows over {world} GPUs + NCCL gather",
+                   "partition": "whole frame" if world == 1 else (
+                       f"interleaved tile rows over {world} GPUs, stored into rank 0's frame over NVLink peer memory + barrier"
+                       if exchange == "p2p" else f"interleaved tile rows over {world} GPUs + NCCL gather"),
                    "l2": "flushed between timed iterations (256 MiB fill outside the timed events)",
                    "frame_lanes": lanes_default, "launch": "CUDA graph replay of the frame's kernels"},
         "clocks": clocks,

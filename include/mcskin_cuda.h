@@ -173,6 +173,20 @@ int32_t mcskin_cuda_context_render_bands(McContext* ctx, int32_t first_tile_row,
                                          void* d_out_f32, void* d_out_u8, void* stream);
 /* Number of pixel rows the call above writes for that partition. */
 int32_t mcskin_cuda_band_rows(const McConfig* cfg, int32_t first_tile_row, int32_t tile_row_stride);
+/* The same rows written at their own place in a FULL-frame image (width*height pixels, rows in
+ * image order) instead of a compact band.  The image may live on another device of the box: with
+ * peer access (see mcskin_cuda_ipc_open) every GPU stores its tile rows straight into the root's
+ * frame over NVLink and no gather step is left — only a barrier before the root reads it. */
+int32_t mcskin_cuda_context_render_rows_into_frame(McContext* ctx, int32_t first_tile_row, int32_t stride,
+                                                    void* d_frame_f32, void* d_frame_u8, void* stream);
+/* Plain device allocations that can be shared between the processes of one box (one process per
+ * GPU): export on the owner, open on the peers (cudaIpcGetMemHandle / cudaIpcOpenMemHandle; the
+ * handle is 64 opaque bytes to pass over any channel, e.g. a torch.distributed broadcast). */
+int32_t mcskin_cuda_device_alloc(int32_t device, uint64_t bytes, void** out_ptr);
+int32_t mcskin_cuda_device_free(int32_t device, void* ptr);
+int32_t mcskin_cuda_ipc_export(int32_t device, void* ptr, uint8_t handle_out[64]);
+int32_t mcskin_cuda_ipc_open(int32_t device, const uint8_t handle[64], void** out_ptr);
+int32_t mcskin_cuda_ipc_close(int32_t device, void* ptr);
 /* Blocks until the context's work is done, fills stats of the last render. */
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats);
 /* Tuning / test knobs: "force_all_active" (0/1: skip the hit/miss classification and

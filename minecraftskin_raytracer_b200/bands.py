@@ -77,3 +77,41 @@ def gather_frame(band: torch.Tensor, frame: torch.Tensor | None, tile_size: int,
                             frame_row_index(frame.shape[0], tile_size, world, band.shape[0], band.device))
     dist.gather(band, None, dst=0)
     return None
+
+
+class PeerFrame:
+    """The root's full-frame image mapped into every rank of the box (one process per GPU).
+
+    Rank 0 owns a plain device allocation and broadcasts its 64-byte IPC handle; the other ranks map it
+    (peer access over NVLink).  Each rank's kernels then store their tile rows straight into the
+    root's frame (Context.render_rows_into_frame) and the path's only exchange step shrinks to a
+    barrier: `fence()` — a one-element all-reduce, stream-ordered after the rank's kernels — after
+    which rank 0 may read `frame`.  No CUDA call of its own: allocation and mapping go through the
+    C ABI (lib.DeviceBuffer / lib.ipc_open)."""
+
+    def __init__(self, lib, height: int, width: int, local_device: int):
+        self.lib, self.device = lib, local_device
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        dev = torch.device("cuda", local_device)
+        self.buffer = lib.DeviceBuffer(local_device, (height, width, 4)) if self.rank == 0 else None
+        box = [self.buffer.ipc_handle() if self.rank == 0 else None]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0)
+        self.ptr = self.buffer.ptr if self.rank == 0 else lib.ipc_open(local_device, box[0])
+        self.frame = torch.as_tensor(self.buffer, device=dev) if self.rank == 0 else None
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def fence(self):
+        """After this (in stream order) every rank's rows of the current frame are in the root's image."""
+        if self.world > 1:
+            dist.all_reduce(self._flag)
+
+    def close(self):
+        if self.rank != 0 and self.ptr:
+            self.lib.ipc_close(self.device, self.ptr)
+        self.ptr = 0
+        if self.buffer is not None:
+            self.frame = None
+            self.buffer.free()
+            self.buffer = None

@@ -98,6 +98,7 @@ struct McContext {
     int forceAllActive = 0;
     long long recordBudgetBytes = 1ll << 31;
     int shadeBlocksPerSm = 8;
+    int heavyTilesPerSm = 8;                 // the figure's tiles are split over more blocks while a frame (all lanes) has fewer tiles per SM
     int primaryBlocksPerSm = 2;              // split tiles over blocks only while a launch has fewer than this many per SM
                                              // (every block of a split tile regenerates the tile's whole jitter stream)
     int waveQueueLevels = 4;                 // bounce depths handled by queues; deeper ones in-thread
@@ -207,7 +208,7 @@ int band_pixel_rows(const DevFrame& f, int first, int stride) {
 // device memory.  scn: the context whose scene (prepared frame, box and texel buffers) is rendered;
 // local tile row r is written at tile row outFirst + r*outStride of the output image.
 int render_bands_lane(McContext* ctx, const McContext* scn, int first, int stride, int outFirst, int outStride,
-                      float4* outF32, uchar4* outU8, cudaStream_t stream) {
+                      float4* outF32, uchar4* outU8, cudaStream_t stream, int lanesInFlight = 1) {
     const DevFrame& f = scn->prep.frame;
     const int nRows = local_tile_rows(f, first, stride);
     ctx->chunksLastRender = 0;
@@ -299,7 +300,8 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
         }
         if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
         const bool seeded = launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
-                                           seedTiles, ctx->smCount * ctx->primaryBlocksPerSm, stream);
+                                           seedTiles, ctx->smCount * ctx->primaryBlocksPerSm,
+                                           ctx->smCount * ctx->heavyTilesPerSm / std::max(1, lanesInFlight), stream);
         ctx->tileSeedValid = seedsCacheable && seeded;
         // from here on every pixel of the band outside the figure's screen rectangle is final: the host
         // copy of the image may start (render_host).  Inside a capture this must be a real event-record
@@ -347,21 +349,27 @@ void inherit_options(McContext* lane, const McContext* ctx) {
     lane->recordBudgetBytes = ctx->recordBudgetBytes;
     lane->shadeBlocksPerSm = ctx->shadeBlocksPerSm;
     lane->primaryBlocksPerSm = ctx->primaryBlocksPerSm;
+    lane->heavyTilesPerSm = ctx->heavyTilesPerSm;
     lane->cacheTileSeeds = ctx->cacheTileSeeds;
     lane->useGraphs = 0;
 }
 
 // Launches the lanes of one frame (see render_bands) on `stream` and the child lanes' streams.
-int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* outF32, uchar4* outU8, cudaStream_t stream) {
-    if (L <= 1) return render_bands_lane(ctx, ctx, first, stride, 0, 1, outF32, outU8, stream);
+// frameLayout: the output is a full-frame image and every tile row lands at its own frame position
+// (output tile row = frame tile row) instead of a compact band.
+int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* outF32, uchar4* outU8, cudaStream_t stream,
+                       bool frameLayout) {
+    if (L <= 1)
+        return render_bands_lane(ctx, ctx, first, stride, frameLayout ? first : 0, frameLayout ? stride : 1, outF32, outU8, stream);
     CU_TRY(cudaEventRecord(ctx->evCopy, stream));  // fork point
     // lane 0 on the caller's stream, lanes 1..L-1 on their own
-    int rc = render_bands_lane(ctx, ctx, first, stride * L, 0, L, outF32, outU8, stream);
+    int rc = render_bands_lane(ctx, ctx, first, stride * L, frameLayout ? first : 0, frameLayout ? stride * L : L, outF32, outU8, stream, L);
     if (rc != MC_OK) return rc;
     for (int k = 1; k < L; ++k) {
         McContext* lane = ctx->lanes[k - 1];
         CU_TRY(cudaStreamWaitEvent(lane->stream, ctx->evCopy, 0));
-        rc = render_bands_lane(lane, ctx, first + k * stride, stride * L, k, L, outF32, outU8, lane->stream);
+        rc = render_bands_lane(lane, ctx, first + k * stride, stride * L, frameLayout ? first + k * stride : k,
+                               frameLayout ? stride * L : L, outF32, outU8, lane->stream, L);
         if (rc != MC_OK) return rc;
         CU_TRY(cudaEventRecord(lane->evCopy, lane->stream));
     }
@@ -372,7 +380,7 @@ int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* out
 long long option_bits(const McContext* c, int i) {
     const long long v[12] = {c->forceAllActive, c->recordBudgetBytes, c->shadeBlocksPerSm, c->primaryBlocksPerSm,
                              c->waveQueueLevels, c->shadeMode, c->waveBudgetBytes, c->waveDeepGridDiv,
-                             c->waveShadowPrefetch, c->cacheTileSeeds, 0, c->frameLanes};
+                             c->waveShadowPrefetch, c->cacheTileSeeds, c->heavyTilesPerSm, c->frameLanes};
     return v[i];
 }
 
@@ -390,7 +398,8 @@ void drop_graph(McContext* ctx) {
 // the SMs fill those gaps with the other lanes' blocks.  Whole tile rows per lane, so the image
 // is bit-identical to the one-stream result.  The second time the same frame description comes
 // in, the launches are captured into a CUDA graph, which is replayed from then on.
-int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* outU8, cudaStream_t stream) {
+int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* outU8, cudaStream_t stream,
+                 bool frameLayout = false) {
     const DevFrame& f = ctx->prep.frame;
     const int nRows = local_tile_rows(f, first, stride);
     const int L = ctx->isChild ? 1 : std::max(1, std::min(ctx->frameLanes, nRows / 2));
@@ -410,7 +419,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         key.frame = f;
         key.blob = ctx->boxes.p; key.texels = ctx->texels.p; key.outF32 = outF32; key.outU8 = outU8;
         key.blobBytes = static_cast<unsigned int>(ctx->prep.blob.size());
-        key.first = first; key.stride = stride; key.lanes = L;
+        key.first = first; key.stride = stride; key.lanes = L * 2 + (frameLayout ? 1 : 0);
         for (int i = 0; i < 12; ++i) key.optionBits[i] = option_bits(ctx, i);
         key.allocEpoch = g_allocEpoch.load();
         if (ctx->graphExec && key == ctx->graphKey) {
@@ -451,7 +460,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         ctx->capturing = true;
         for (int k = 1; k < L; ++k) ctx->lanes[k - 1]->capturing = true;
         cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
-        int rc = e == cudaSuccess ? launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream) : MC_ERR_CUDA;
+        int rc = e == cudaSuccess ? launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout) : MC_ERR_CUDA;
         cudaGraph_t g = nullptr;
         if (e == cudaSuccess) {
             const cudaError_t e2 = cudaStreamEndCapture(stream, &g);
@@ -474,7 +483,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
                 ctx->graphLaneChunks[k] = lane->chunksLastRender;
                 ctx->graphLaneTiles[k] = static_cast<int>(lane->stats.n_tiles);
             }
-            return render_bands(ctx, first, stride, outF32, outU8, stream);  // replays the graph just made
+            return render_bands(ctx, first, stride, outF32, outU8, stream, frameLayout);  // replays the graph just made
         }
         // capture failed (an operation that cannot be captured): clear the error state, render directly
         if (g) cudaGraphDestroy(g);
@@ -483,7 +492,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         ctx->useGraphs = 0;
     }
     CU_TRY(cudaEventRecord(ctx->ev0, stream));
-    const int rc = launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream);
+    const int rc = launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout);
     if (rc != MC_OK) return rc;
     if (L > 1) {
         CU_TRY(cudaEventRecord(ctx->ev1, stream));
@@ -818,6 +827,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     CU_TRY(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&ctx->evUpload, cudaEventDisableTiming));
     if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
+    if (const char* v = std::getenv("MCSKIN_HEAVY_TILES")) ctx->heavyTilesPerSm = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_PRIMARY_BLOCKS")) ctx->primaryBlocksPerSm = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) ctx->waveQueueLevels = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_SHADOW_PREFETCH")) ctx->waveShadowPrefetch = std::atoi(v) != 0;
@@ -870,6 +880,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "record_budget_bytes") ctx->recordBudgetBytes = std::max<int64_t>(1, value);
     else if (k == "shade_blocks_per_sm") ctx->shadeBlocksPerSm = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "primary_blocks_per_sm") ctx->primaryBlocksPerSm = static_cast<int>(std::max<int64_t>(0, value));
+    else if (k == "heavy_tiles_per_sm") ctx->heavyTilesPerSm = static_cast<int>(std::max<int64_t>(0, value));
     else if (k == "batch_lanes") ctx->batchLanes = static_cast<int>(std::min<int64_t>(16, std::max<int64_t>(1, value)));
     else if (k == "batch_group") ctx->batchGroup = static_cast<int>(std::min<int64_t>(4096, std::max<int64_t>(1, value)));
     else if (k == "batch_mode") ctx->batchMode = value != 0;
@@ -914,6 +925,53 @@ int32_t mcskin_cuda_context_render_bands(McContext* ctx, int32_t first, int32_t 
     CU_TRY(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     return render_bands(ctx, first, stride, static_cast<float4*>(dOutF32), static_cast<uchar4*>(dOutU8), s);
+}
+
+int32_t mcskin_cuda_context_render_rows_into_frame(McContext* ctx, int32_t first, int32_t stride, void* dFrameF32,
+                                                    void* dFrameU8, void* stream) {
+    if (!ctx || !ctx->hasScene) return fail(MC_ERR_INVALID, "render_rows_into_frame: no scene set");
+    if (stride <= 0 || first < 0) return fail(MC_ERR_INVALID, "render_rows_into_frame: bad partition");
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return render_bands(ctx, first, stride, static_cast<float4*>(dFrameF32), static_cast<uchar4*>(dFrameU8), s, true);
+}
+
+int32_t mcskin_cuda_device_alloc(int32_t device, uint64_t bytes, void** out) {
+    if (!out) return fail(MC_ERR_INVALID, "device_alloc: out is null");
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaMalloc(out, std::max<uint64_t>(bytes, 16)));
+    return MC_OK;
+}
+int32_t mcskin_cuda_device_free(int32_t device, void* ptr) {
+    if (!ptr) return MC_OK;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaFree(ptr));
+    return MC_OK;
+}
+int32_t mcskin_cuda_ipc_export(int32_t device, void* ptr, uint8_t handleOut[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!ptr || !handleOut) return fail(MC_ERR_INVALID, "ipc_export: null argument");
+    CU_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, ptr));
+    std::memcpy(handleOut, &h, sizeof(h));
+    return MC_OK;
+}
+int32_t mcskin_cuda_ipc_open(int32_t device, const uint8_t handle[64], void** out) {
+    if (!handle || !out) return fail(MC_ERR_INVALID, "ipc_open: null argument");
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CU_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return MC_OK;
+}
+int32_t mcskin_cuda_ipc_close(int32_t device, void* ptr) {
+    if (!ptr) return MC_OK;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaIpcCloseMemHandle(ptr));
+    return MC_OK;
 }
 
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats) {

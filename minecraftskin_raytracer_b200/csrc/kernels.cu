@@ -47,34 +47,68 @@ __device__ __forceinline__ TileGeom tile_geom(const DevFrame& fr, const BandView
 
 // Launch order of the tiles of a band: the tiles that intersect the figure's screen rectangle
 // first (their pixels shoot rays; they take several times as long as pure-background tiles), then
-// the rest, which are short and uniform and fill the end of the launch evenly.  Block-uniform
-// arithmetic; a bijection of [0, tiles of the band).
-__device__ __forceinline__ int heavy_first_tile(const DevFrame& fr, const BandView& band, int slot) {
-    if (!fr.rect_valid) return slot;
+// the rest, which are short and uniform and fill the end of the launch evenly.  When a launch has
+// few tiles (one GPU's share of a frame) the heavy tiles are also split over `parts_heavy` blocks,
+// each taking every parts_heavy-th round of 256 pixels, so that the launch is not as long as its
+// slowest tile.  Computed on the host, passed by value.
+struct TileOrder {
+    int r0, hr;        // local tile rows [r0, r0 + hr) intersect the rectangle
+    int tx0, hw;       // tile columns [tx0, tx0 + hw) do
+    int n_heavy;       // hw * hr (0: no reordering)
+    int parts_heavy;   // blocks per heavy tile
+    int parts_light;   // blocks per other tile
+};
+
+static TileOrder make_tile_order(const DevFrame& fr, const BandView& band, int partsHeavy, int partsLight) {
+    TileOrder o{0, 0, 0, 0, 0, partsLight, partsLight};
+    if (!fr.rect_valid || fr.rect_x1 < 0 || fr.rect_y1 < 0) return o;
     const int ts = fr.tile_size, W = fr.tiles_x;
-    const int tx0 = max(0, fr.rect_x0) / ts, tx1 = min(W - 1, fr.rect_x1 / ts);
-    const int ty0 = max(0, fr.rect_y0) / ts, ty1 = min(fr.tiles_y - 1, fr.rect_y1 / ts);
-    if (fr.rect_x1 < 0 || fr.rect_y1 < 0 || tx0 > tx1 || ty0 > ty1) return slot;
+    const int tx0 = std::max(0, fr.rect_x0) / ts, tx1 = std::min(W - 1, fr.rect_x1 / ts);
+    const int ty0 = std::max(0, fr.rect_y0) / ts, ty1 = std::min(fr.tiles_y - 1, fr.rect_y1 / ts);
+    if (tx0 > tx1 || ty0 > ty1) return o;
     // local rows r whose frame tile row first + r*stride lies in [ty0, ty1]
     const int first = band.first_tile_row, st = band.tile_row_stride;
     const int r0 = ty0 <= first ? 0 : (ty0 - first + st - 1) / st;
-    const int r1 = ty1 < first ? -1 : min(band.n_tile_rows - 1, (ty1 - first) / st);
-    if (r0 > r1) return slot;
-    const int hw = tx1 - tx0 + 1, hr = r1 - r0 + 1;
-    if (slot < hw * hr) {
-        const int r = slot / hw;
-        return (r0 + r) * W + tx0 + (slot - r * hw);
+    const int r1 = ty1 < first ? -1 : std::min(band.n_tile_rows - 1, (ty1 - first) / st);
+    if (r0 > r1) return o;
+    o.r0 = r0; o.hr = r1 - r0 + 1; o.tx0 = tx0; o.hw = tx1 - tx0 + 1;
+    o.n_heavy = o.hw * o.hr;
+    o.parts_heavy = partsHeavy;
+    return o;
+}
+
+// launch slot -> local tile index; a bijection of [0, tiles of the band)
+__device__ __forceinline__ int ordered_tile(const TileOrder& o, int W, int slot) {
+    if (o.n_heavy == 0) return slot;
+    if (slot < o.n_heavy) {
+        const int r = slot / o.hw;
+        return (o.r0 + r) * W + o.tx0 + (slot - r * o.hw);
     }
-    slot -= hw * hr;
-    if (slot < r0 * W) return slot;  // the rows above keep their index
-    slot -= r0 * W;
-    const int sideW = W - hw;
-    if (slot < sideW * hr) {         // left and right of the rectangle
+    slot -= o.n_heavy;
+    if (slot < o.r0 * W) return slot;  // the rows above keep their index
+    slot -= o.r0 * W;
+    const int sideW = W - o.hw;
+    if (slot < sideW * o.hr) {         // left and right of the rectangle
         const int r = slot / sideW, c = slot - r * sideW;
-        return (r0 + r) * W + (c < tx0 ? c : c + hw);
+        return (o.r0 + r) * W + (c < o.tx0 ? c : c + o.hw);
     }
-    slot -= sideW * hr;
-    return (r1 + 1) * W + slot;      // the rows below
+    slot -= sideW * o.hr;
+    return (o.r0 + o.hr) * W + slot;   // the rows below
+}
+// block -> (launch slot, part, parts of that tile)
+__device__ __forceinline__ void block_to_slot(const TileOrder& o, int block, int* slot, int* part, int* parts) {
+    const int heavyBlocks = o.n_heavy * o.parts_heavy;
+    if (block < heavyBlocks) {
+        *parts = o.parts_heavy;
+        *slot = block / o.parts_heavy;
+        *part = block - *slot * o.parts_heavy;
+    } else {
+        const int b = block - heavyBlocks;
+        *parts = o.parts_light;
+        const int s = b / o.parts_light;
+        *slot = o.n_heavy + s;
+        *part = b - s * o.parts_light;
+    }
 }
 
 __global__ void __launch_bounds__(kBlockThreads)
@@ -548,7 +582,7 @@ extern __shared__ __align__(16) unsigned char g_pixSmem[];  // [PixStreamSmem][s
 template <bool BATCH>
 __global__ void __launch_bounds__(kBlockThreads)
 k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, const ActiveList list_,
-              const uint32_t* __restrict__ tileStates, const int parts, const BatchSlice* __restrict__ batch) {
+              const uint32_t* __restrict__ tileStates, const TileOrder order, const BatchSlice* __restrict__ batch) {
     __shared__ __align__(8) uint64_t stageBar;
     const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
     const BandView& band = BATCH ? batch[blockIdx.y].band : band_;
@@ -560,8 +594,9 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
     // With few tiles per launch (small frames, one GPU's share of a frame) a tile is split over
     // `parts` blocks, each taking every parts-th round of 256 pixels; a block reaches its rounds by
     // running the tile's generator forward without storing the words it does not need.
-    const int tileSlot = blockIdx.x / parts, part = blockIdx.x - tileSlot * parts;
-    const int tileIndex = heavy_first_tile(fr, band, tileSlot);
+    int tileSlot, part, parts;
+    block_to_slot(order, blockIdx.x, &tileSlot, &part, &parts);
+    const int tileIndex = ordered_tile(order, fr.tiles_x, tileSlot);
     const TileGeom tg = tile_geom(fr, band, tileIndex);
     const int spp = fr.spp, dps = fr.draws_per_sample;
     const int nPix = tg.w * tg.h;
@@ -665,7 +700,7 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
 template <int SPP, bool GRADIENT, bool BATCH>
 __global__ void __launch_bounds__(kBlockThreads)
 k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView band_, const ActiveList list_,
-                    const uint32_t* __restrict__ tileStates, const int parts, const BatchSlice* __restrict__ batch) {
+                    const uint32_t* __restrict__ tileStates, const TileOrder order, const BatchSlice* __restrict__ batch) {
     constexpr unsigned int kWords = SPP * 2;
     static_assert(kWords <= 32 && 32 % kWords == 0, "a pixel's words must not straddle a 32-word ring group");
     __shared__ __align__(8) uint64_t stageBar;
@@ -678,8 +713,9 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
     unsigned char* sceneSmem = g_pixSmem + ((sizeof(Smem) + 15) & ~size_t(15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tileSlot = blockIdx.x / parts, part = blockIdx.x - tileSlot * parts;
-    const int tileIndex = heavy_first_tile(fr, band, tileSlot);
+    int tileSlot, part, parts;
+    block_to_slot(order, blockIdx.x, &tileSlot, &part, &parts);
+    const int tileIndex = ordered_tile(order, fr.tiles_x, tileSlot);
     const TileGeom tg = tile_geom(fr, band, tileIndex);
     const int nPix = tg.w * tg.h;
     if (part * kBlockThreads >= nPix) return;
@@ -985,8 +1021,8 @@ static int log2_if_warp_spp(int spp) {
 
 // The pixel-per-lane primary kernels over one scene (batch == nullptr) or the scenes of a batch.
 static void launch_primary_pix(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                               uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, const BatchSlice* batch,
-                               int nScenes, unsigned int blobBytes, cudaStream_t stream) {
+                               uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, int heavyTargetTiles,
+                               const BatchSlice* batch, int nScenes, unsigned int blobBytes, cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     const size_t pixSmem = ((sizeof(PixStreamSmem) + 15) & ~size_t(15)) + blobBytes;
     static bool attrSet = false;
@@ -1011,19 +1047,24 @@ static void launch_primary_pix(const DevFrame& fr, const FramePointers& fp, cons
     const int allTiles = nTiles * (batch ? nScenes : 1);
     int parts = (primaryTargetBlocks + allTiles - 1) / allTiles;
     parts = parts < 1 ? 1 : (parts > roundsPerTile ? roundsPerTile : parts);
-    const dim3 grid(nTiles * parts, batch ? nScenes : 1);
+    // the figure's tiles are split further while the launch has few tiles: it should not last as
+    // long as its slowest tile (one GPU's share of a frame is 255 tiles at 8 GPUs)
+    int partsHeavy = (heavyTargetTiles + allTiles - 1) / allTiles;
+    partsHeavy = partsHeavy < parts ? parts : (partsHeavy > roundsPerTile ? roundsPerTile : partsHeavy);
+    const TileOrder order = make_tile_order(fr, band, partsHeavy, parts);
+    const dim3 grid(order.n_heavy * order.parts_heavy + (nTiles - order.n_heavy) * order.parts_light, batch ? nScenes : 1);
     // jitter only (no lens draws), 4 or 16 spp, quotients by the host reciprocals: compile-time sample loop
     const bool fixedForm = fr.draws_per_sample == 2 && fr.spp > 1 && !fr.dof_on && fr.uv_recip;
 #define MCSKIN_LAUNCH_PIX(KERNEL)                                                                                \
     do {                                                                                                        \
-        if (batch) KERNEL<true><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts, batch);   \
-        else KERNEL<false><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, parts, batch);        \
+        if (batch) KERNEL<true><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, order, batch);   \
+        else KERNEL<false><<<grid, kBlockThreads, pixSmem, stream>>>(fr, fp, band, list, tileStates, order, batch);        \
     } while (0)
 #define MCSKIN_LAUNCH_PIX_FIXED(SPP, GRAD)                                                                       \
     do {                                                                                                        \
         const size_t smem = ((sizeof(PixStreamSmemT<(kBlockThreads * SPP * 2 + kMtN + 31) / 32 * 32>) + 15) & ~size_t(15)) + blobBytes; \
-        if (batch) k_primary_pix_fixed<SPP, GRAD, true><<<grid, kBlockThreads, smem, stream>>>(fr, fp, band, list, tileStates, parts, batch);  \
-        else k_primary_pix_fixed<SPP, GRAD, false><<<grid, kBlockThreads, smem, stream>>>(fr, fp, band, list, tileStates, parts, batch);       \
+        if (batch) k_primary_pix_fixed<SPP, GRAD, true><<<grid, kBlockThreads, smem, stream>>>(fr, fp, band, list, tileStates, order, batch);  \
+        else k_primary_pix_fixed<SPP, GRAD, false><<<grid, kBlockThreads, smem, stream>>>(fr, fp, band, list, tileStates, order, batch);       \
     } while (0)
     if (fixedForm && fr.spp == 16 && fr.gradient_bg) MCSKIN_LAUNCH_PIX_FIXED(16, true);
     else if (fixedForm && fr.spp == 16) MCSKIN_LAUNCH_PIX_FIXED(16, false);
@@ -1041,13 +1082,15 @@ static bool pix_kernel_applies(const DevFrame& fr) {
 }
 
 bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                    int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, cudaStream_t stream) {
+                    int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, int heavyTargetTiles,
+                    cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     if (nTiles <= 0) return false;
     const long long tileDraws = static_cast<long long>(fr.tile_size) * fr.tile_size * fr.spp * (fr.draws_per_sample > 0 ? fr.draws_per_sample : 1);
     const int lg = tileDraws < (1ll << 30) ? log2_if_warp_spp(fr.spp) : -1;
     if (classify && pix_kernel_applies(fr)) {
-        launch_primary_pix(fr, fp, band, list, tileStates, seedTiles, primaryTargetBlocks, nullptr, 1, fp.blob_bytes, stream);
+        launch_primary_pix(fr, fp, band, list, tileStates, seedTiles, primaryTargetBlocks, heavyTargetTiles, nullptr, 1,
+                           fp.blob_bytes, stream);
         return fr.draws_per_sample > 0;
     } else if (classify && lg >= 0) {
         k_primary_warp<<<nTiles, kBlockThreads, fp.blob_bytes, stream>>>(fr, fp, band, list, lg);
@@ -1062,7 +1105,7 @@ bool launch_primary_batch(const DevFrame& fr, const BandView& band, uint32_t* ti
                           cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     if (nTiles <= 0 || nScenes <= 0 || !pix_kernel_applies(fr)) return false;
-    launch_primary_pix(fr, FramePointers{}, band, ActiveList{}, tileStates, seedTiles, primaryTargetBlocks, batch, nScenes,
+    launch_primary_pix(fr, FramePointers{}, band, ActiveList{}, tileStates, seedTiles, primaryTargetBlocks, 0, batch, nScenes,
                        blobBytes, stream);
     return true;
 }

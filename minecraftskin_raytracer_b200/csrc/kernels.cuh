@@ -47,8 +47,11 @@ struct FramePointers {
 // the image width, the tile size and the tile rows of the band only, not on the scene).
 // primaryTargetBlocks: tiles are split over several blocks until the launch has about this many.
 // Returns true when tileStates holds the seeded engines of the band's tiles afterwards.
+// heavyTargetTiles: the tiles that intersect the figure are split over more blocks while the launch has
+// fewer tiles than this.
 bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                    int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, cudaStream_t stream);
+                    int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, int heavyTargetTiles,
+                    cudaStream_t stream);
 // Shading pass: full integrator for every sample of every listed pixel, ordered resolve.
 // Megakernel form of the shading pass over the listed pixels from `firstSlot` on.
 // variant 1: block-synchronous groups; variant 2: warp-autonomous groups with dynamic

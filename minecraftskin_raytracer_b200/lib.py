@@ -33,7 +33,9 @@ EXPORTS = [
     "mcskin_cuda_intersect", "mcskin_cuda_trace", "mcskin_cuda_shade", "mcskin_cuda_in_shadow",
     "mcskin_cuda_soft_shadow", "mcskin_cuda_ambient_occlusion", "mcskin_cuda_generate_rays",
     "mcskin_cuda_background", "mcskin_cuda_aov", "mcskin_build_skin_scene", "mcskin_cuda_sincos",
-    "mcskin_sincos_model", "mcskin_cuda_powf", "mcskin_powf_model",
+    "mcskin_sincos_model", "mcskin_cuda_powf", "mcskin_powf_model", "mcskin_cuda_context_render_rows_into_frame",
+    "mcskin_cuda_device_alloc", "mcskin_cuda_device_free", "mcskin_cuda_ipc_export", "mcskin_cuda_ipc_open",
+    "mcskin_cuda_ipc_close",
 ]
 
 
@@ -176,6 +178,44 @@ def render_tile(scene: FlatScene, cfg: McConfig, tile, image_f32: np.ndarray, de
     return image_f32
 
 
+class DeviceBuffer:
+    """A plain cudaMalloc allocation owned by this process, shareable with the other processes of the box
+    (one per GPU) through a 64-byte IPC handle.  Exposes __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, device: int, shape, dtype=np.float32):
+        self.device, self.shape, self.dtype = device, tuple(int(v) for v in shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(_lib.mcskin_cuda_device_alloc(C.c_int32(device), C.c_uint64(self.nbytes), C.byref(p)))
+        self.ptr = int(p.value)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False), "version": 2}
+
+    def ipc_handle(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        _check(_lib.mcskin_cuda_ipc_export(C.c_int32(self.device), C.c_void_p(self.ptr), h))
+        return bytes(h)
+
+    def free(self):
+        if self.ptr:
+            _check(_lib.mcskin_cuda_device_free(C.c_int32(self.device), C.c_void_p(self.ptr)))
+            self.ptr = 0
+
+
+def ipc_open(device: int, handle: bytes) -> int:
+    """Maps a peer process's DeviceBuffer into this process; returns the device address valid here."""
+    h = (C.c_uint8 * 64)(*handle)
+    p = C.c_void_p()
+    _check(_lib.mcskin_cuda_ipc_open(C.c_int32(device), h, C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(device: int, ptr: int):
+    _check(_lib.mcskin_cuda_ipc_close(C.c_int32(device), C.c_void_p(ptr)))
+
+
 class Context:
     """Device-resident renderer (McContext): scene uploaded once, output in caller-owned device memory."""
 
@@ -212,6 +252,12 @@ class Context:
         _check(_lib.mcskin_cuda_context_render_bands(self._h, C.c_int32(first_tile_row), C.c_int32(stride),
                                                      C.c_void_p(d_out_f32 or None), C.c_void_p(d_out_u8 or None),
                                                      C.c_void_p(stream or None)))
+
+    def render_rows_into_frame(self, first_tile_row: int, stride: int, d_frame_f32: int = 0, d_frame_u8: int = 0, stream: int = 0):
+        """Asynchronous: the same rows written at their own place in a full [H, W, 4] frame (possibly a peer's)."""
+        _check(_lib.mcskin_cuda_context_render_rows_into_frame(self._h, C.c_int32(first_tile_row), C.c_int32(stride),
+                                                               C.c_void_p(d_frame_f32 or None), C.c_void_p(d_frame_u8 or None),
+                                                               C.c_void_p(stream or None)))
 
     def render_batch(self, scenes: list[FlatScene], cfg: McConfig, d_out_f32: int = 0, d_out_u8: int = 0, stream: int = 0):
         """Asynchronous: scene i -> image i of the [n, H, W, 4] device buffer(s) (one skin per scene, same config)."""

@@ -175,6 +175,7 @@ RENDER_MODES = {
     "deep_queues": {"wave_queue_levels": 6},
     "shallow_queues": {"wave_queue_levels": 1},
     "split_tiles": {"primary_blocks_per_sm": 100000},     # every tile split over one block per 256-pixel round
+    "split_heavy_tiles": {"heavy_tiles_per_sm": 100000},  # the figure's tiles split over one block per round, the rest whole
     "one_lane_no_graph": {"frame_lanes": 1, "use_graphs": 0, "cache_tile_seeds": 0},
     "five_lanes": {"frame_lanes": 5},
     "thin_deep_grids": {"wave_deep_grid_div": 8, "frame_lanes": 3},
@@ -469,6 +470,37 @@ def test_batch_headline_shape(gpu, oracle):
         assert pixel_report(got[3], oracle.render(scenes[3], cfg), oracle.quantize)["within1"] >= 0.999
     finally:
         ctx.close()
+
+
+def test_rows_into_frame_partitions(gpu, oracle):
+    """render_rows_into_frame: tile-row partitions written at their own place in one full frame (what the
+    multi-GPU path does over peer memory) reassemble the single-device frame; the buffer is a plain
+    allocation of the C ABI viewed by torch through __cuda_array_interface__."""
+    import torch
+    scene = _scene(gpu, 8, "64x64", "running")
+    cfg = make_config(width=200, height=330, samples_per_pixel=4, max_bounces=3)
+    want, want_u8, _ = gpu.render(scene, cfg, want_u8=True)
+    buf = gpu.DeviceBuffer(0, (cfg.height, cfg.width, 4))
+    frame = torch.as_tensor(buf, device="cuda:0")
+    frame_u8 = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.uint8, device="cuda:0")
+    ctx = gpu.Context(0)
+    try:
+        ctx.set_scene(scene, cfg)
+        for world in (1, 2, 5):
+            for rep in range(3):  # direct, capture, replay
+                frame.fill_(-1.0)
+                frame_u8.zero_()
+                torch.cuda.synchronize()
+                for r in range(world):
+                    ctx.render_rows_into_frame(r, world, buf.ptr, frame_u8.data_ptr(), 0)
+                    ctx.sync()
+                assert np.array_equal(_bits(frame.cpu().numpy()), _bits(want)), (world, rep)
+                assert np.array_equal(frame_u8.cpu().numpy(), want_u8), (world, rep)
+        assert len(buf.ipc_handle()) == 64
+    finally:
+        ctx.close()
+        del frame
+        buf.free()
 
 
 def test_render_multi_in_process(gpu):
