@@ -378,7 +378,10 @@ def run_own_arm(args):
         "roofline": {
             "bound": "fp32", "kernel": f"frame pipeline ({launches_per_step} kernel launches: primary pass + wavefront shading)",
             "achieved": achieved, "peak": fp32_peak, "unit": "Tlane-op/s",
-            "frac": achieved / fp32_peak, "traffic": None,
+            "frac": achieved / fp32_peak,
+            # DRAM bytes of one frame's kernels (dram__bytes_read.sum + dram__bytes_write.sum over the 16 launches of a
+            # serial frame, ncu --set full): queue traffic, ~13 % of HBM bandwidth at this frame time
+            "traffic": 1.06e9 if world == 1 else None, "traffic_source": "profiles/r01/final_ncu_summary.md",
             "peak_source": f"{sm_count} SMs x 128 FP32 lanes x {peaks['sm_max_mhz']:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json"
                            + (", fallback" if peaks.get("_fallback") else "") + "); non-FMA issue rate, SURVEY.md §8d",
             "alg_ops_per_launch": step_ops, "ms_per_launch": device_ms,

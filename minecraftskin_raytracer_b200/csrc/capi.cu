@@ -98,7 +98,7 @@ struct McContext {
     int forceAllActive = 0;
     long long recordBudgetBytes = 1ll << 31;
     int shadeBlocksPerSm = 8;
-    int heavyTilesPerSm = 8;                 // the figure's tiles are split over more blocks while a frame (all lanes) has fewer tiles per SM
+    int heavyTilesPerSm = 16;                // the figure's tiles are split over more blocks while a frame (all lanes) has fewer tiles per SM
     int primaryBlocksPerSm = 2;              // split tiles over blocks only while a launch has fewer than this many per SM
                                              // (every block of a split tile regenerates the tile's whole jitter stream)
     int waveQueueLevels = 4;                 // bounce depths handled by queues; deeper ones in-thread
@@ -277,6 +277,12 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
     ctx->tileSeedKey = seedKey;
     ctx->tileSeedValid = false;
     if (seedTiles) ++ctx->seedGen;
+    // Splitting the figure's tiles pays only when the frame (all lanes in flight) has too few tiles to
+    // keep every SM busy for as long as its slowest tile takes: below ~10 tiles per SM (B200 sweep:
+    // a whole 1080p frame, 2040 tiles, is best unsplit; half a frame is best split in three).
+    const long long tilesInFlight = static_cast<long long>(nRows) * f.tiles_x * std::max(1, lanesInFlight);
+    const int heavyTarget = tilesInFlight * 3 >= 2ll * ctx->smCount * ctx->heavyTilesPerSm
+                                ? 0 : ctx->smCount * ctx->heavyTilesPerSm / std::max(1, lanesInFlight);
     for (int c = 0; c < nChunks; ++c) {
         const int row0 = static_cast<int>(c * rowsPerChunk);
         const int rows = static_cast<int>(std::min<size_t>(rowsPerChunk, nRows - row0));
@@ -301,7 +307,7 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
         if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
         const bool seeded = launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
                                            seedTiles, ctx->smCount * ctx->primaryBlocksPerSm,
-                                           ctx->smCount * ctx->heavyTilesPerSm / std::max(1, lanesInFlight), stream);
+                                           heavyTarget, stream);
         ctx->tileSeedValid = seedsCacheable && seeded;
         // from here on every pixel of the band outside the figure's screen rectangle is final: the host
         // copy of the image may start (render_host).  Inside a capture this must be a real event-record
