@@ -352,6 +352,10 @@ def run_own_arm(args):
     peaks = measured_peaks()
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = sm_count * 128 * peaks["sm_max_mhz"] * 1e6 / 1e12  # T lane-ops/s, non-FMA issue rate
+    try:
+        fp32_peak_measured = lib.fp32_issue_peak(local_rank) / 1e12  # FADD/FMUL microbenchmark on this device
+    except Exception:  # noqa: BLE001
+        fp32_peak_measured = None
     # The frame is one pipeline of ~14 short kernels per lane, several lanes in flight at once, so
     # the roofline entry is that of the whole step: the frame's algorithmic lane-ops over the
     # event time of a frame's launches.  At N>1 each rank does ~1/N of the frame.
@@ -384,6 +388,9 @@ def run_own_arm(args):
             "traffic": 1.06e9 if world == 1 else None, "traffic_source": "profiles/r01/final_ncu_summary.md",
             "peak_source": f"{sm_count} SMs x 128 FP32 lanes x {peaks['sm_max_mhz']:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json"
                            + (", fallback" if peaks.get("_fallback") else "") + "); non-FMA issue rate, SURVEY.md §8d",
+            "peak_measured": fp32_peak_measured,
+            "frac_of_measured_peak": (achieved / fp32_peak_measured) if fp32_peak_measured else None,
+            "peak_measured_source": "mcskin_cuda_fp32_issue_peak: 8 independent unfused FMUL+FADD chains per thread, best of 6 launches",
             "alg_ops_per_launch": step_ops, "ms_per_launch": device_ms,
             "serial_breakdown": {
                 "what": "one stream, direct launches, same frame (outside the timed region)",

@@ -262,6 +262,9 @@ void mcskin_sincos_model(const float* angles, int32_t n, float* out_sin, float* 
  * non-zero y below the overflow threshold.  mcskin_powf_model is the same arithmetic on the host. */
 int32_t mcskin_cuda_powf(int32_t device, const float* x, const float* y, int32_t n, float* out);
 void mcskin_powf_model(const float* x, const float* y, int32_t n, float* out);
+/* Measured ceiling of the roofline the bench reports against: a kernel of independent,
+ * unfused FADD / FMUL chains on every SM; returns the best of a few launches in lane-ops per second. */
+int32_t mcskin_cuda_fp32_issue_peak(int32_t device, double* out_lane_ops_per_second);
 /* Hit mask + triangle id of the pinhole ray through each pixel centre
  * (u=(px+.5)/W, v=(py+.5)/H): out_tri_id[py*W+px] = box*12+face*2, or -1. */
 int32_t mcskin_cuda_aov(const McScene* scene, const McConfig* cfg, int32_t device, int32_t* out_tri_id);

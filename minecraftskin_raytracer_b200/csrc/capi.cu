@@ -1376,6 +1376,38 @@ int32_t mcskin_cuda_background(const McScene* scene, const McConfig* cfg, int32_
     return st.down(out, dO, sizeof(float4) * n);
 }
 
+int32_t mcskin_cuda_fp32_issue_peak(int32_t device, double* out) {
+    if (!out) return fail(MC_ERR_INVALID, "fp32_issue_peak: out is null");
+    *out = 0.0;
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    McContext* ctx = nullptr;
+    int rc = shared_context(device, &ctx);
+    if (rc != MC_OK) return rc;
+    float* sink = nullptr;
+    CU_TRY(cudaMalloc(&sink, sizeof(float)));
+    const int blocks = ctx->smCount * 8, iters = 1 << 15;
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {  // the first launches warm the clocks up
+        CU_TRY(cudaEventRecord(e0, ctx->stream));
+        launch_fp32_peak(blocks, iters, sink, ctx->stream);
+        CU_TRY(cudaEventRecord(e1, ctx->stream));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = static_cast<double>(blocks) * kBlockThreads * iters * 16.0;
+        if (ms > 0.0f) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    CU_TRY(cudaGetLastError());
+    *out = best;
+    return MC_OK;
+}
+
 int32_t mcskin_cuda_powf(int32_t device, const float* x, const float* y, int32_t n, float* out) {
     if (n < 0 || (n > 0 && (!x || !y || !out))) return fail(MC_ERR_INVALID, "powf: bad argument");
     std::lock_guard<std::mutex> lock(g_ctxMutex);

@@ -983,6 +983,21 @@ __global__ void k_background(const DevFrame fr, const float* uv, int n, float4* 
     out[i] = fr.use_config ? config_background(fr, uv[2 * i], uv[2 * i + 1]) : flat_background(fr);
 }
 
+// Eight independent chains per thread, each step one FMUL and one FADD (this translation unit is built
+// with --fmad=false, so they stay two instructions): the non-FMA FP32 issue rate the path is measured against.
+__global__ void __launch_bounds__(kBlockThreads) k_fp32_peak(const int iters, float* sink) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 0.1f, x2 = x0 + 0.2f, x3 = x0 + 0.3f;
+    float x4 = x0 + 0.4f, x5 = x0 + 0.5f, x6 = x0 + 0.6f, x7 = x0 + 0.7f;
+    const float a = 0.999f + blockIdx.x * 1e-9f, b = 1e-3f;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+        x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) sink[0] = s;  // keeps the chains alive
+}
+
 __global__ void k_powf(const float* x, const float* y, int n, float* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = powf_ref(x[i], y[i]);
@@ -1153,6 +1168,9 @@ void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out
 }
 void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream) {
     if (n > 0) k_background<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, uv, n, out);
+}
+void launch_fp32_peak(int blocks, int iters, float* sink, cudaStream_t stream) {
+    k_fp32_peak<<<blocks, kBlockThreads, 0, stream>>>(iters, sink);
 }
 void launch_powf(const float* x, const float* y, int n, float* out, cudaStream_t stream) {
     if (n > 0) k_powf<<<blocks_for(n), kBlockThreads, 0, stream>>>(x, y, n, out);

@@ -35,7 +35,7 @@ EXPORTS = [
     "mcskin_cuda_background", "mcskin_cuda_aov", "mcskin_build_skin_scene", "mcskin_cuda_sincos",
     "mcskin_sincos_model", "mcskin_cuda_powf", "mcskin_powf_model", "mcskin_cuda_context_render_rows_into_frame",
     "mcskin_cuda_device_alloc", "mcskin_cuda_device_free", "mcskin_cuda_ipc_export", "mcskin_cuda_ipc_open",
-    "mcskin_cuda_ipc_close",
+    "mcskin_cuda_ipc_close", "mcskin_cuda_fp32_issue_peak",
 ]
 
 
@@ -381,6 +381,13 @@ def powf_model(x, y) -> np.ndarray:
     out = np.zeros(len(x), dtype=np.float32)
     _lib.mcskin_powf_model(_ptr(x, C.c_float), _ptr(y, C.c_float), C.c_int32(len(x)), _ptr(out, C.c_float))
     return out
+
+
+def fp32_issue_peak(device: int = 0) -> float:
+    """Measured non-FMA FP32 issue rate of the device in lane-ops per second (FADD/FMUL microbenchmark)."""
+    out = C.c_double(0.0)
+    _check(_lib.mcskin_cuda_fp32_issue_peak(C.c_int32(device), C.byref(out)))
+    return float(out.value)
 
 
 def sincos_model(angles):
