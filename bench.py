@@ -244,7 +244,7 @@ def run_own_arm(args):
 
     def step_p2p():
         ctx.render_rows_into_frame(rank, world, peer.ptr, frame_u8.data_ptr(), stream.cuda_stream)
-        peer.fence()
+        peer.fence(stream.cuda_stream)  # ranks release a flag in the root's memory; the root's stream acquires them
 
     step = step_p2p if exchange == "p2p" else step_gather
     if exchange == "p2p":
@@ -252,6 +252,7 @@ def run_own_arm(args):
         step_gather()
         step_p2p()
         torch.cuda.synchronize(dev)
+        dist.barrier()
         if rank == 0 and not torch.equal(peer.frame.view(torch.int32), frame.view(torch.int32)):
             raise SystemExit("bench.py: peer-written frame differs from the gathered frame")
 
@@ -328,7 +329,7 @@ def run_own_arm(args):
             if rank == 0:
                 host.copy_(peer.frame if exchange == "p2p" else frame, non_blocking=True)
             if exchange == "p2p":
-                peer.fence()  # the peers may overwrite the root's frame only after it has left for the host
+                peer.fence_all()  # the peers may overwrite the root's frame only after it has left for the host
             torch.cuda.synchronize(dev)
 
         for _ in range(2):

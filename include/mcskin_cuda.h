@@ -187,6 +187,13 @@ int32_t mcskin_cuda_device_free(int32_t device, void* ptr);
 int32_t mcskin_cuda_ipc_export(int32_t device, void* ptr, uint8_t handle_out[64]);
 int32_t mcskin_cuda_ipc_open(int32_t device, const uint8_t handle[64], void** out_ptr);
 int32_t mcskin_cuda_ipc_close(int32_t device, void* ptr);
+/* Stream-ordered flags in (peer-mapped) device memory, the barrier of the peer-store exchange:
+ * signal stores `value` into *d_flag with system-scope release semantics after everything queued
+ * before it on `stream` (so a peer that sees the value also sees the rows stored before it);
+ * wait holds `stream` until each of the n 32-bit flags is >= value (acquire), or ~2 s have passed
+ * (then *d_timeout, if given, is set to 1 and the stream continues: no device hang on a dead peer). */
+int32_t mcskin_cuda_peer_signal(int32_t device, void* d_flag, uint32_t value, void* stream);
+int32_t mcskin_cuda_peer_wait(int32_t device, const void* d_flags, int32_t n, uint32_t value, void* d_timeout, void* stream);
 /* Blocks until the context's work is done, fills stats of the last render. */
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats);
 /* Tuning / test knobs: "force_all_active" (0/1: skip the hit/miss classification and

@@ -82,28 +82,55 @@ def gather_frame(band: torch.Tensor, frame: torch.Tensor | None, tile_size: int,
 class PeerFrame:
     """The root's full-frame image mapped into every rank of the box (one process per GPU).
 
-    Rank 0 owns a plain device allocation and broadcasts its 64-byte IPC handle; the other ranks map it
-    (peer access over NVLink).  Each rank's kernels then store their tile rows straight into the
-    root's frame (Context.render_rows_into_frame) and the path's only exchange step shrinks to a
-    barrier: `fence()` — a one-element all-reduce, stream-ordered after the rank's kernels — after
-    which rank 0 may read `frame`.  No CUDA call of its own: allocation and mapping go through the
-    C ABI (lib.DeviceBuffer / lib.ipc_open)."""
+    Rank 0 owns a plain device allocation — the frame followed by one 32-bit flag per rank — and
+    broadcasts its 64-byte IPC handle; the other ranks map it (peer access over NVLink).  Each rank's
+    kernels then store their tile rows straight into the root's frame (Context.render_rows_into_frame)
+    and the path's only exchange step shrinks to a barrier, `fence(stream)`: every other rank releases
+    its flag in the root's memory after its kernels (stream-ordered, system scope), and the root's
+    stream acquires all of them; after that (in stream order) rank 0 may read `frame`.
+    `fence_all()` is the two-way form (a one-element NCCL all-reduce) for when the peers must also
+    wait for the root, e.g. before they overwrite a frame the root is still copying out.
+    No CUDA call of its own: allocation, mapping and flags go through the C ABI."""
+
+    FLAG_BYTES = 4096  # one page after the frame: a 32-bit flag per rank
 
     def __init__(self, lib, height: int, width: int, local_device: int):
         self.lib, self.device = lib, local_device
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         dev = torch.device("cuda", local_device)
-        self.buffer = lib.DeviceBuffer(local_device, (height, width, 4)) if self.rank == 0 else None
+        frame_bytes = height * width * 16
+        self.buffer = lib.DeviceBuffer(local_device, (frame_bytes + self.FLAG_BYTES,), dtype="uint8") if self.rank == 0 else None
         box = [self.buffer.ipc_handle() if self.rank == 0 else None]
         if self.world > 1:
             dist.broadcast_object_list(box, src=0)
         self.ptr = self.buffer.ptr if self.rank == 0 else lib.ipc_open(local_device, box[0])
-        self.frame = torch.as_tensor(self.buffer, device=dev) if self.rank == 0 else None
+        self.flags_ptr = self.ptr + frame_bytes
+        self.frame = None
+        self._whole = None
+        if self.rank == 0:
+            self._whole = torch.as_tensor(self.buffer, device=dev)
+            self._whole[frame_bytes:].zero_()
+            self.frame = self._whole[:frame_bytes].view(torch.float32).view(height, width, 4)
+            torch.cuda.synchronize(dev)
         self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.epoch = 0
+        if self.world > 1:
+            dist.barrier()  # flags are zeroed before anyone signals
 
-    def fence(self):
-        """After this (in stream order) every rank's rows of the current frame are in the root's image."""
+    def fence(self, stream: int = 0):
+        """One-way barrier: after this (in the root's stream order) every rank's rows of the current frame
+        are in the root's image.  Non-root ranks only signal and run ahead."""
+        self.epoch += 1
+        if self.world == 1:
+            return
+        if self.rank == 0:
+            self.lib.peer_wait(self.device, self.flags_ptr + 4, self.world - 1, self.epoch, 0, stream)
+        else:
+            self.lib.peer_signal(self.device, self.flags_ptr + 4 * self.rank, self.epoch, stream)
+
+    def fence_all(self):
+        """Two-way barrier on the current torch stream (NCCL): nobody passes before everybody arrived."""
         if self.world > 1:
             dist.all_reduce(self._flag)
 
@@ -113,5 +140,6 @@ class PeerFrame:
         self.ptr = 0
         if self.buffer is not None:
             self.frame = None
+            self._whole = None
             self.buffer.free()
             self.buffer = None

@@ -980,6 +980,22 @@ int32_t mcskin_cuda_ipc_close(int32_t device, void* ptr) {
     return MC_OK;
 }
 
+int32_t mcskin_cuda_peer_signal(int32_t device, void* dFlag, uint32_t value, void* stream) {
+    if (!dFlag) return fail(MC_ERR_INVALID, "peer_signal: null flag");
+    CU_TRY(cudaSetDevice(device));
+    launch_peer_signal(static_cast<unsigned int*>(dFlag), value, static_cast<cudaStream_t>(stream));
+    CU_TRY(cudaGetLastError());
+    return MC_OK;
+}
+int32_t mcskin_cuda_peer_wait(int32_t device, const void* dFlags, int32_t n, uint32_t value, void* dTimeout, void* stream) {
+    if (n < 0 || n > 1024 || (n > 0 && !dFlags)) return fail(MC_ERR_INVALID, "peer_wait: bad argument");
+    CU_TRY(cudaSetDevice(device));
+    launch_peer_wait(static_cast<const unsigned int*>(dFlags), n, value, static_cast<unsigned int*>(dTimeout),
+                     static_cast<cudaStream_t>(stream));
+    CU_TRY(cudaGetLastError());
+    return MC_OK;
+}
+
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats) {
     if (!ctx) return fail(MC_ERR_INVALID, "sync: null context");
     CU_TRY(cudaSetDevice(ctx->device));

@@ -983,6 +983,32 @@ __global__ void k_background(const DevFrame fr, const float* uv, int n, float4* 
     out[i] = fr.use_config ? config_background(fr, uv[2 * i], uv[2 * i + 1]) : flat_background(fr);
 }
 
+// The barrier of the peer-store exchange (bands.PeerFrame): a rank that has stored its rows into the
+// root's frame releases a flag there; the root's stream acquires every rank's flag.
+__global__ void k_peer_signal(unsigned int* flag, const unsigned int value) {
+    // the kernels queued before this one have completed; the system-scope release makes their stores
+    // to peer memory visible to whoever acquires the flag
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__global__ void k_peer_wait(const unsigned int* flags, const int n, const unsigned int value, unsigned int* timedOut) {
+    const int i = threadIdx.x;
+    if (i < n) {
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned int v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+            if (static_cast<int>(v - value) >= 0) break;           // counters wrap: compare as a signed distance
+            if (clock64() - t0 > 4000000000ll) {                   // ~2 s at 2 GHz: give up rather than hang the device
+                if (timedOut) *timedOut = 1u;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
 // Eight independent chains per thread, each step one FMUL and one FADD (this translation unit is built
 // with --fmad=false, so they stay two instructions): the non-FMA FP32 issue rate the path is measured against.
 __global__ void __launch_bounds__(kBlockThreads) k_fp32_peak(const int iters, float* sink) {
@@ -1171,6 +1197,12 @@ void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, 
 }
 void launch_fp32_peak(int blocks, int iters, float* sink, cudaStream_t stream) {
     k_fp32_peak<<<blocks, kBlockThreads, 0, stream>>>(iters, sink);
+}
+void launch_peer_signal(unsigned int* flag, unsigned int value, cudaStream_t stream) {
+    k_peer_signal<<<1, 1, 0, stream>>>(flag, value);
+}
+void launch_peer_wait(const unsigned int* flags, int n, unsigned int value, unsigned int* timedOut, cudaStream_t stream) {
+    if (n > 0) k_peer_wait<<<1, ((n + 31) / 32) * 32, 0, stream>>>(flags, n, value, timedOut);
 }
 void launch_powf(const float* x, const float* y, int n, float* out, cudaStream_t stream) {
     if (n > 0) k_powf<<<blocks_for(n), kBlockThreads, 0, stream>>>(x, y, n, out);

@@ -78,6 +78,8 @@ void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out
 void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream);
 // FADD/FMUL issue-rate microbenchmark: `iters` rounds of 16 unfused operations per thread; result written to sink
 void launch_fp32_peak(int blocks, int iters, float* sink, cudaStream_t stream);
+void launch_peer_signal(unsigned int* flag, unsigned int value, cudaStream_t stream);
+void launch_peer_wait(const unsigned int* flags, int n, unsigned int value, unsigned int* timedOut, cudaStream_t stream);
 void launch_powf(const float* x, const float* y, int n, float* out, cudaStream_t stream);
 void launch_sincos(const float* angles, int n, float* outSin, float* outCos, cudaStream_t stream);
 void launch_aov(const DevFrame& fr, const FramePointers& fp, int* outTriId, cudaStream_t stream);

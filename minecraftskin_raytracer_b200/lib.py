@@ -35,7 +35,7 @@ EXPORTS = [
     "mcskin_cuda_background", "mcskin_cuda_aov", "mcskin_build_skin_scene", "mcskin_cuda_sincos",
     "mcskin_sincos_model", "mcskin_cuda_powf", "mcskin_powf_model", "mcskin_cuda_context_render_rows_into_frame",
     "mcskin_cuda_device_alloc", "mcskin_cuda_device_free", "mcskin_cuda_ipc_export", "mcskin_cuda_ipc_open",
-    "mcskin_cuda_ipc_close", "mcskin_cuda_fp32_issue_peak",
+    "mcskin_cuda_ipc_close", "mcskin_cuda_fp32_issue_peak", "mcskin_cuda_peer_signal", "mcskin_cuda_peer_wait",
 ]
 
 
@@ -210,6 +210,17 @@ def ipc_open(device: int, handle: bytes) -> int:
     p = C.c_void_p()
     _check(_lib.mcskin_cuda_ipc_open(C.c_int32(device), h, C.byref(p)))
     return int(p.value)
+
+
+def peer_signal(device: int, d_flag: int, value: int, stream: int = 0):
+    """Stream-ordered release of a 32-bit flag in (peer-mapped) device memory."""
+    _check(_lib.mcskin_cuda_peer_signal(C.c_int32(device), C.c_void_p(d_flag), C.c_uint32(value & 0xffffffff), C.c_void_p(stream or None)))
+
+
+def peer_wait(device: int, d_flags: int, n: int, value: int, d_timeout: int = 0, stream: int = 0):
+    """Holds `stream` until the n flags at d_flags have all reached `value` (or ~2 s have passed)."""
+    _check(_lib.mcskin_cuda_peer_wait(C.c_int32(device), C.c_void_p(d_flags), C.c_int32(n), C.c_uint32(value & 0xffffffff),
+                                      C.c_void_p(d_timeout or None), C.c_void_p(stream or None)))
 
 
 def ipc_close(device: int, ptr: int):

@@ -503,6 +503,30 @@ def test_rows_into_frame_partitions(gpu, oracle):
         buf.free()
 
 
+def test_peer_flags_signal_and_wait(gpu):
+    """The barrier of the peer-store exchange: stream-ordered release / acquire of 32-bit flags, with a
+    bounded wait (a flag that never arrives sets the timeout word instead of hanging the device)."""
+    import torch
+    buf = gpu.DeviceBuffer(0, (64,), dtype="uint32")
+    words = torch.as_tensor(buf, device="cuda:0")
+    try:
+        words.zero_()
+        torch.cuda.synchronize()
+        for epoch in (1, 2, 3):
+            for r in (1, 2, 3):
+                gpu.peer_signal(0, buf.ptr + 4 * r, epoch)
+            gpu.peer_wait(0, buf.ptr + 4, 3, epoch, buf.ptr + 4 * 32)
+            torch.cuda.synchronize()
+            assert words[1:4].tolist() == [epoch] * 3 and int(words[32]) == 0
+        gpu.peer_wait(0, buf.ptr + 4, 3, 2)              # already reached: returns at once
+        gpu.peer_wait(0, buf.ptr + 4, 3, 9, buf.ptr + 4 * 32)   # never reached: gives up after ~2 s
+        torch.cuda.synchronize()
+        assert int(words[32]) == 1
+    finally:
+        del words
+        buf.free()
+
+
 def test_render_multi_in_process(gpu):
     """mcskin_cuda_render_multi over however many devices this process sees (1 on the test box)."""
     scene = _scene(gpu, 3, "64x64", "running")
