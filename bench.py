@@ -189,6 +189,8 @@ def run_own_arm(args):
     from minecraftskin_raytracer_b200.scene import synth_skin
 
     rank, local_rank, world = dist_env()
+    # tuning aid: time ONE rank's share of an N-way split on a single GPU (no exchange): MCSKIN_BENCH_SPLIT=N
+    emulate = int(os.environ.get("MCSKIN_BENCH_SPLIT", "0")) if world == 1 else 0
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -207,7 +209,8 @@ def run_own_arm(args):
     ctx = lib.Context(local_rank)
     lanes_default = int(os.environ.get("MCSKIN_FRAME_LANES", "0")) or lib.DEFAULT_FRAME_LANES
     ctx.set_scene(scene, cfg)
-    max_rows = bands.padded_band_rows(H, ts, world)  # padded band height, equal on all ranks
+    split = emulate if emulate > 1 else world
+    max_rows = bands.padded_band_rows(H, ts, split)  # padded band height, equal on all ranks
     assert ctx.band_rows(rank, world) == bands.band_pixel_rows(H, ts, rank, world)
     band = torch.zeros((max_rows, W, 4), dtype=torch.float32, device=dev)
     band_u8 = torch.zeros((max_rows, W, 4), dtype=torch.uint8, device=dev)
@@ -237,7 +240,7 @@ def run_own_arm(args):
             exchange, peer = "gather", None
 
     def step_gather():
-        ctx.render_bands(rank, world, band.data_ptr(), band_u8.data_ptr(), stream.cuda_stream)
+        ctx.render_bands(rank, split, band.data_ptr(), band_u8.data_ptr(), stream.cuda_stream)
         if world > 1:
             # gather the bands on rank 0 (NCCL over NVLink), rows back in order
             bands.gather_frame(band, frame, ts, gathered, row_index)
@@ -291,7 +294,7 @@ def run_own_arm(args):
     n_serial = max(1, min(args.steps, 5))
     for i in range(1 + n_serial):
         flush.fill_(i & 0xff)
-        ctx.render_bands(rank, world, band.data_ptr(), band_u8.data_ptr(), stream.cuda_stream)
+        ctx.render_bands(rank, split, band.data_ptr(), band_u8.data_ptr(), stream.cuda_stream)
         st = ctx.sync()
         if i > 0:
             pass_ms["primary"] += st["ms_primary"] / n_serial

@@ -102,7 +102,6 @@ struct McContext {
     int primaryBlocksPerSm = 2;              // split tiles over blocks only while a launch has fewer than this many per SM
                                              // (every block of a split tile regenerates the tile's whole jitter stream)
     int waveQueueLevels = 4;                 // bounce depths handled by queues; deeper ones in-thread
-    int waveShadowPrefetch = 0;
     int waveDeepGridDiv = 1;                 // launches of depth >= 1 use shade grid / this
     int frameLanes = 3;                      // a frame's tile rows are rendered on this many streams at once
     bool isChild = false;                    // a lane of another context (never splits frames itself)
@@ -264,7 +263,6 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
             return fail(MC_ERR_CUDA, "wavefront buffer carve failed");
         wave.queueLevels = ctx->waveQueueLevels;
         wave.deepGridDiv = ctx->waveDeepGridDiv;
-        wave.shadowPrefetch = ctx->waveShadowPrefetch;
     }
     if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->ev0, stream));
     const FramePointers fp = frame_pointers(scn);
@@ -350,7 +348,6 @@ void inherit_options(McContext* lane, const McContext* ctx) {
     lane->forceAllActive = ctx->forceAllActive;
     lane->waveQueueLevels = ctx->waveQueueLevels;
     lane->waveDeepGridDiv = ctx->waveDeepGridDiv;
-    lane->waveShadowPrefetch = ctx->waveShadowPrefetch;
     lane->waveBudgetBytes = ctx->waveBudgetBytes;
     lane->recordBudgetBytes = ctx->recordBudgetBytes;
     lane->shadeBlocksPerSm = ctx->shadeBlocksPerSm;
@@ -386,7 +383,7 @@ int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* out
 long long option_bits(const McContext* c, int i) {
     const long long v[12] = {c->forceAllActive, c->recordBudgetBytes, c->shadeBlocksPerSm, c->primaryBlocksPerSm,
                              c->waveQueueLevels, c->shadeMode, c->waveBudgetBytes, c->waveDeepGridDiv,
-                             c->waveShadowPrefetch, c->cacheTileSeeds, c->heavyTilesPerSm, c->frameLanes};
+                             0, c->cacheTileSeeds, c->heavyTilesPerSm, c->frameLanes};
     return v[i];
 }
 
@@ -765,7 +762,6 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
                     return fail(MC_ERR_CUDA, "render_batch: queue carve failed");
                 sl.wave.queueLevels = ctx->waveQueueLevels;
                 sl.wave.deepGridDiv = 1;
-                sl.wave.shadowPrefetch = 0;
                 stageSlices[sliceAt++] = sl;
             }
         }
@@ -836,7 +832,6 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     if (const char* v = std::getenv("MCSKIN_HEAVY_TILES")) ctx->heavyTilesPerSm = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_PRIMARY_BLOCKS")) ctx->primaryBlocksPerSm = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) ctx->waveQueueLevels = std::max(1, std::atoi(v));
-    if (const char* v = std::getenv("MCSKIN_SHADOW_PREFETCH")) ctx->waveShadowPrefetch = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_DEEP_GRID_DIV")) ctx->waveDeepGridDiv = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_BATCH_GROUP")) ctx->batchGroup = std::min(4096, std::max(1, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_BATCH_MODE")) ctx->batchMode = std::atoi(v) != 0;

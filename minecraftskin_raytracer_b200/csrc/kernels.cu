@@ -1,19 +1,23 @@
-// kernels.cu — the CUDA kernels of the render hot path (sm_100a).
+// kernels.cu — the primary pass and the megakernel form of the shading pass (sm_100a).
 //
-//   k_primary : TileRenderer::renderTile's sample loop up to "did anything get hit"
-//               (tile_renderer.cpp:71-127): one CTA per reference tile regenerates that
-//               tile's std::mt19937 jitter stream, shoots the camera / thin-lens rays,
-//               resolves every pixel whose samples all miss to the averaged gradient
-//               background, and appends the others — with their jitter draws — to a
-//               compact work list.
-//   k_shade   : RayTracer::traceRay for every sample of every listed pixel (closest hit,
-//               soft/hard shadows, Blinn-Phong, AO, mirror bounces), then the ordered
-//               per-pixel average.  One thread per pixel-sample over a persistent grid, so
-//               the ~7 % of the frame that carries ~95 % of the work is spread evenly over
-//               all SMs instead of being pinned to the tiles that contain the figure.
+//   primary pass : TileRenderer::renderTile's sample loop up to "did anything get hit"
+//               (tile_renderer.cpp:71-127): one CTA per reference tile (or per part of one)
+//               regenerates that tile's std::mt19937 jitter stream, shoots the camera /
+//               thin-lens rays, resolves every pixel whose samples all miss to the averaged
+//               gradient background, and appends the others — with their jitter draws — to a
+//               compact work list.  Forms, fastest first: k_primary_pix_fixed (compile-time
+//               sample loop: 4 / 16 spp, jitter only), k_primary_pix (a lane owns a pixel),
+//               k_primary_warp (a warp owns 32 samples), k_primary_cta (any spp).
+//   shading pass : wavefront.cu in the default configuration.  k_shade_cta / k_shade_warp here
+//               are its megakernel form — RayTracer::traceRay for every sample of every listed
+//               pixel in one thread — kept for pixels beyond the queue capacity and as an A/B
+//               mode; the two forms give identical images.
+//   single-query kernels : the reference's free functions (intersect, traceRay, shade, isInShadow,
+//               computeSoftShadow, computeAO, generateRay, backgroundColor) over arrays, for the
+//               reference's unit cases; sincos / powf / issue-rate / peer-flag helpers.
 //
-// Both passes sum a pixel's samples in sample order, like the reference, so pixels are
-// reproducible bit-for-bit run to run and background pixels match the CPU result exactly.
+// All passes sum a pixel's samples in sample order, like the reference, so frames are
+// reproducible bit for bit run to run and equal the CPU result exactly.
 #include "kernels.cuh"
 #include "wavefront.cuh"
 

@@ -188,7 +188,7 @@ k_wf_prep_hard(const DevFrame fr, const FramePointers fp_, const WaveView wv_, c
 }
 
 // ---------------------------------------------------------------- one shadow ray per thread
-template <bool PREFETCH, bool BATCH>
+template <bool BATCH>
 __global__ void WF_SHADOW_BOUNDS
 k_wf_shadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
             const BatchSlice* __restrict__ batch) {
@@ -208,9 +208,8 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, cons
     const bool rPow2 = (R & (R - 1)) == 0;
     const int lgR = 31 - __clz(R);
 
-    // One ray per trip of a grid-stride loop; the inputs of the next trip (hit record, light sample,
-    // box mask — three dependent global loads) are fetched before the current ray is traced, so
-    // their latency overlaps the slab tests instead of heading every trip.
+    // One ray per trip of a grid-stride loop.  (Fetching the next trip's inputs ahead of the trace was
+    // measured slower: the extra registers cost a resident block.)
     struct RayIn {
         float4 org;        // shadow-ray origin, w = box mask
         float tx, ty, tz;  // point on the light
@@ -231,16 +230,8 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, cons
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kWfThreads;
     unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + threadIdx.x;
     if (t >= nRays) return;
-    RayIn next{};
-    if (PREFETCH) next = fetch(t);
     for (; t < nRays; t += stride) {
-        RayIn cur;
-        if (PREFETCH) {
-            cur = next;
-            if (t + stride < nRays) next = fetch(t + stride);
-        } else {
-            cur = fetch(t);
-        }
+        const RayIn cur = fetch(t);
         const V3 origin = mk3(cur.org.x, cur.org.y, cur.org.z);
         if (!in_shadow_from(sc, origin, mk3(cur.tx, cur.ty, cur.tz), __float_as_uint(cur.org.w)))
             atomicAdd(&wv.lit[cur.i], 1u);
@@ -478,7 +469,6 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
     w.gridBlocks = gridBlocks;
     w.queueLevels = 3;
     w.deepGridDiv = 1;
-    w.shadowPrefetch = 0;
     unsigned char* p = static_cast<unsigned char*>(base);
     size_t off = 0;
     auto take = [&](size_t n) {
@@ -537,11 +527,9 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
             }
             if (wv.shadowMode != kShadowInThread) {
                 if (batch)
-                    k_wf_shadow<false, true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
-                else if (wv.shadowPrefetch)
-                    k_wf_shadow<true, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
+                    k_wf_shadow<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
                 else
-                    k_wf_shadow<false, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
+                    k_wf_shadow<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
                 ++n;
             }
             if (wv.shadowMode != kShadowInThread) {

@@ -49,7 +49,6 @@ struct WaveView {
     int shadowMode;          // see enum below
     int shadowRays;          // rays per hit cast by k_wf_shadow
     int gridBlocks;
-    int shadowPrefetch;      // k_wf_shadow fetches the next ray's inputs before tracing the current one
     int deepGridDiv;         // grid of the launches of depth >= 1 = gridBlocks / deepGridDiv
 };
 
