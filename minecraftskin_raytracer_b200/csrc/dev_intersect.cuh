@@ -486,6 +486,15 @@ __device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from
         const float4 L = sc.lo[i];
         const float4 H = sc.hi[i];
         if (__float_as_uint(L.w) & kBoxEmpty) continue;
+        // A ray that starts beyond a slab of the box and moves further away along that axis cannot
+        // enter the box (the reference's own slab test gives tmax < 0 for it).  Every ray of the
+        // bundle has a direction within growFull of d, so this holds for all of them at once.  It is
+        // what releases the box a hit lies ON (origin = hit point + normal * 1e-3, just outside it):
+        // without it that box would survive every distance-based clip.
+        if ((from.x > H.x && d.x > growFull) || (from.x < L.x && d.x < -growFull) ||
+            (from.y > H.y && d.y > growFull) || (from.y < L.y && d.y < -growFull) ||
+            (from.z > H.z && d.z > growFull) || (from.z < L.z && d.z < -growFull))
+            continue;
         const float ax = (L.x - from.x) * inv.x, bx = (H.x - from.x) * inv.x;
         const float ay = (L.y - from.y) * inv.y, by = (H.y - from.y) * inv.y;
         const float az = (L.z - from.z) * inv.z, bz = (H.z - from.z) * inv.z;

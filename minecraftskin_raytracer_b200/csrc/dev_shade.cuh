@@ -212,14 +212,11 @@ __device__ __forceinline__ void frame_about(V3 n, V3* t, V3* b) {
 
 template <class Engine>
 __device__ __forceinline__ int soft_shadow_count(const SceneView& sc, const DevFrame& fr, V3 point, V3 normal,
-                                                 int samples, Engine& rng) {
+                                                 int samples, Engine& rng, uint32_t allow) {
     const V3 lp = ld3(fr.light_pos);
     const V3 toPoint = normalize3(point - lp);
     V3 tangent, bitangent;
     frame_about(toPoint, &tangent, &bitangent);
-    // all shadow rays of this hit start at the same point and end on the light's disk:
-    // pre-select once the boxes that bundle can reach
-    const uint32_t allow = bundle_box_mask(sc, point + normal * kShadowEpsilon, lp, fr.light_radius);
     int lit = 0;
     for (int i = 0; i < samples; ++i) {
         const float angle = MCSKIN_TWO_PI_F * rng.next();
@@ -239,15 +236,19 @@ static __device__ __noinline__ float soft_shadow_large(const SceneView& sc, cons
     if (samples <= 1 || fr.light_radius < 1e-4f) return in_shadow(sc, point, normal, ld3(fr.light_pos)) ? 0.0f : 1.0f;
     LocalEngine rng;
     rng.seed(seed);
-    return static_cast<float>(soft_shadow_count(sc, fr, point, normal, samples, rng)) / static_cast<float>(samples);
+    return static_cast<float>(soft_shadow_count(sc, fr, point, normal, samples, rng, 0xffffffffu)) / static_cast<float>(samples);
 }
 __device__ __forceinline__ float soft_shadow(const SceneView& sc, const DevFrame& fr, V3 point, V3 normal,
                                              int samples, uint32_t seed) {
     if (samples <= 1 || fr.light_radius < 1e-4f || 2 * samples > kFreshStreamMaxDraws)
         return soft_shadow_large(sc, fr, point, normal, samples, seed);  // rare configurations, out of line
+    // all shadow rays of this hit start at the same point and end on the light's disk: pre-select once
+    // the boxes that bundle can reach; with none in reach every ray is lit and no sample is drawn
+    const uint32_t allow = bundle_box_mask(sc, point + normal * kShadowEpsilon, ld3(fr.light_pos), fr.light_radius);
+    if (allow == 0u && sc.n_boxes <= 32) return 1.0f;  // samples / samples
     FreshStream rng;
     rng.seed(seed);
-    return static_cast<float>(soft_shadow_count(sc, fr, point, normal, samples, rng)) / static_cast<float>(samples);
+    return static_cast<float>(soft_shadow_count(sc, fr, point, normal, samples, rng, allow)) / static_cast<float>(samples);
 }
 
 template <class Engine>

@@ -153,16 +153,23 @@ k_wf_seed(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const 
         const float4 g = q.geo[i];
         const Hit h = unpack_hit(g, make_float4(0.f, 0.f, 0.f, 0.f));
         const V3 P = h.p;
-        FreshStream rng;
-        rng.seed_balanced(shadow_seed(P, depth), one);
-        soft_shadow_positions(fr, P, N, rng, wv.lightPos + static_cast<size_t>(i) * 3 * N);
-        wv.lit[i] = 0u;
-        // the boxes the bundle of this hit's shadow rays can reach (computeSoftShadow hands
-        // isInShadow the raw hit normal: shading.cpp:54, raytracer.cpp:113)
         // the common origin of the hit's shadow rays, P + n*eps (isInShadow, shading.cpp:17; computeSoftShadow
         // hands it the raw hit normal: shading.cpp:54, raytracer.cpp:113), and the boxes their bundle can reach
         const V3 origin = P + hit_normal(sc, h) * kShadowEpsilon;
         const uint32_t allow = bundle_box_mask(sc, origin, ld3(fr.light_pos), fr.light_radius);
+        if (allow == 0u && sc.n_boxes <= 32) {
+            // No box lies within reach of any segment from this hit to the light's disk: every one of the
+            // N shadow rays is unoccluded wherever its sample falls, so neither the engine nor the sample
+            // points are needed (lit = N; k_wf_shadow skips hits with an empty mask).  Warps are mostly
+            // uniform in this: the samples of a pixel hit the same face of the same box.
+            wv.lit[i] = static_cast<unsigned int>(N);
+            wv.shadowOrg[i] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(0u));
+            continue;
+        }
+        FreshStream rng;
+        rng.seed_balanced(shadow_seed(P, depth), one);
+        soft_shadow_positions(fr, P, N, rng, wv.lightPos + static_cast<size_t>(i) * 3 * N);
+        wv.lit[i] = 0u;
         wv.shadowOrg[i] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(allow));
     }
 }
@@ -233,6 +240,7 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, cons
     for (; t < nRays; t += stride) {
         const RayIn cur = fetch(t);
         const V3 origin = mk3(cur.org.x, cur.org.y, cur.org.z);
+        if (__float_as_uint(cur.org.w) == 0u && sc.n_boxes <= 32) continue;  // nothing in reach: counted as lit by k_wf_seed
         if (!in_shadow_from(sc, origin, mk3(cur.tx, cur.ty, cur.tz), __float_as_uint(cur.org.w)))
             atomicAdd(&wv.lit[cur.i], 1u);
     }
