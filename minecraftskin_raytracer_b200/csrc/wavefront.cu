@@ -189,6 +189,7 @@ k_wf_prep_hard(const DevFrame fr, const FramePointers fp_, const WaveView wv_, c
         const Hit h = unpack_hit(q.geo[i], make_float4(0.f, 0.f, 0.f, 0.f));
         // shade() hands isInShadow the normalised normal (shading.cpp:69,78)
         const V3 origin = h.p + normalize3(hit_normal(sc, h)) * kShadowEpsilon;
+        // (a box mask for the single ray, as for soft-shadow bundles, costs more than the one ray it can save)
         wv.shadowOrg[i] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(0xffffffffu));
         wv.lit[i] = 0u;
     }
@@ -226,7 +227,7 @@ k_wf_shadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, cons
         RayIn in;
         in.i = rPow2 ? static_cast<unsigned int>(t >> lgR) : static_cast<unsigned int>(t / R);
         const int k = static_cast<int>(t - static_cast<unsigned long long>(in.i) * R);
-        in.org = wv.shadowOrg[in.i];
+        in.org = wv.shadowOrg[in.i];  // w: the boxes in reach of the hit's shadow rays (soft and hard mode alike)
         in.tx = lightCentre.x; in.ty = lightCentre.y; in.tz = lightCentre.z;
         if (soft) {
             const float* lp = wv.lightPos + (static_cast<size_t>(in.i) * R + k) * 3;

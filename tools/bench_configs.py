@@ -67,7 +67,7 @@ def main():
     scenes = [lib.build_skin_scene(synth_skin(i)) for i in range(n)]
     out = torch.empty((n, 256, 256, 4), dtype=torch.float32, device="cuda:0")
     torch.cuda.synchronize()
-    ctx.render_batch(scenes[:8], cfg, out.data_ptr(), 0, 0)
+    ctx.render_batch(scenes[:min(n, 128)], cfg, out.data_ptr(), 0, 0)  # warm-up at the steady-state chunk size
     ctx.sync()
     t = time.perf_counter()
     ctx.render_batch(scenes, cfg, out.data_ptr(), 0, 0)
