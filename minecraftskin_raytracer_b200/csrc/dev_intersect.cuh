@@ -51,6 +51,7 @@ struct Hit {
 struct SceneView {
     const float4* __restrict__ lo;      // reject-pass bounds: xyz = min (the box, or a world box around a posed one), w = flags
     const float4* __restrict__ hi;      // xyz = max
+    const int4* __restrict__ rect;      // per box: pixels a pinhole ray must pass through to reach it (or null)
     const DevBox* __restrict__ boxes;   // full records
     const float4* __restrict__ texels;
     int n_boxes;
@@ -308,6 +309,80 @@ __device__ __forceinline__ uint32_t candidate_mask(const SceneView& sc, const Ra
         if (reject) rejected |= 1u << i;
     }
     return (~rejected | posed) & usable & all;
+}
+
+// The boxes a pinhole ray through pixel (px, py) can reach: those whose screen rectangle holds the
+// pixel (conservative: projected bounds plus a 2-pixel margin, host_prep.cpp).  All boxes when the
+// scene carries no rectangles (depth of field, a box behind the camera, more than 32 boxes).
+__device__ __forceinline__ uint32_t pixel_box_mask(const SceneView& sc, int px, int py) {
+    if (sc.rect == nullptr) return 0xffffffffu;
+    uint32_t mask = 0u;
+    const int n = min(32, sc.n_boxes);
+    for (int i = 0; i < n; ++i) {
+        const int4 r = sc.rect[i];
+        if (px >= r.x && px <= r.z && py >= r.y && py <= r.w) mask |= 1u << i;
+    }
+    return mask;
+}
+
+// The reject pass over the boxes of `allow` only (first 32 boxes): survivors of the reference's slab rejection.
+__device__ __forceinline__ uint32_t candidate_mask_among(const SceneView& sc, const Ray& ray, const RayPre& pre, uint32_t allow) {
+    uint32_t todo = allow & sc.usable_mask;
+    if (sc.n_boxes < 32) todo &= (1u << sc.n_boxes) - 1u;
+    if (pre.parallel) return todo;
+    uint32_t mask = todo, rejected = 0u;
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const float4 L = sc.lo[i];
+        const float4 H = sc.hi[i];
+        const float ax = (L.x - ray.o.x) * pre.inv.x, bx = (H.x - ray.o.x) * pre.inv.x;
+        const float ay = (L.y - ray.o.y) * pre.inv.y, by = (H.y - ray.o.y) * pre.inv.y;
+        const float az = (L.z - ray.o.z) * pre.inv.z, bz = (H.z - ray.o.z) * pre.inv.z;
+        const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        if (fmaxf(tmin, 0.0f) > tmax) rejected |= 1u << i;
+    }
+    return mask & (~rejected | sc.posed_mask);
+}
+
+// intersectScene for a ray known to reach only the boxes of `allow` (see pixel_box_mask): same result as
+// closest_hit, since a box outside the mask cannot be hit.
+__device__ __forceinline__ Hit closest_hit_among(const SceneView& sc, const Ray& ray, uint32_t allow) {
+    Hit best;
+    best.t = FLT_MAX;
+    best.box = -1;
+    best.face = 0;
+    best.texel = 0;
+    best.flip = false;
+    best.p = mk3(0.0f, 0.0f, 0.0f);
+    const RayPre pre = ray_pre(ray);
+    uint32_t mask = candidate_mask_among(sc, ray, pre, allow);
+    while (mask) {  // increasing box index: strict '<' keeps the reference's tie order
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        BoxHit h;
+        if (mesh_test(sc, b, ray, pre, h) && h.t < best.t) {
+            best.t = h.t;
+            best.p = h.p;
+            best.box = b;
+            best.face = h.face;
+            best.texel = h.texel;
+            best.flip = h.flip;
+        }
+    }
+    return best;
+}
+__device__ __forceinline__ bool any_hit_among(const SceneView& sc, const Ray& ray, uint32_t allow) {
+    const RayPre pre = ray_pre(ray);
+    uint32_t mask = candidate_mask_among(sc, ray, pre, allow);
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        BoxHit h;
+        if (mesh_test(sc, b, ray, pre, h)) return true;
+    }
+    return false;
 }
 
 // intersectScene (intersection.cpp:408-421).

@@ -47,6 +47,7 @@ __device__ __forceinline__ SceneView scene_view(const unsigned char* blob, const
     SceneView sc;
     sc.lo = reinterpret_cast<const float4*>(blob + lay.loOffset());
     sc.hi = reinterpret_cast<const float4*>(blob + lay.hiOffset());
+    sc.rect = fr.box_rects_valid ? reinterpret_cast<const int4*>(blob + lay.rectOffset()) : nullptr;
     sc.boxes = reinterpret_cast<const DevBox*>(blob + lay.boxOffset());
     sc.texels = texels;
     sc.n_boxes = nBoxes;

@@ -40,16 +40,19 @@ enum : uint32_t {
 };
 
 // The scene blob: what a CTA stages into shared memory with one bulk copy.
-//   [ float4 lo[nPad] ][ float4 hi[nPad] ][ DevBox boxes[n] ]      nPad = n rounded up to 4
+//   [ float4 lo[nPad] ][ float4 hi[nPad] ][ int4 rect[nPad] ][ DevBox boxes[n] ]      nPad = n rounded up to 4
 // lo[i] = (bounds_min, flags as bit pattern), hi[i] = (bounds_max, 0): the compact
-// operands of the reject pass; the full records serve the exact evaluation.
+// operands of the reject pass; rect[i] = (x0, y0, x1, y1), the pixels (inclusive, 2-pixel margin) a pinhole
+// ray must pass through to reach box i (valid when DevFrame::box_rects_valid); the full records serve the
+// exact evaluation.
 struct SceneBlobLayout {
     int n, nPad;
     __host__ __device__ explicit SceneBlobLayout(int nBoxes) : n(nBoxes), nPad((nBoxes + 3) & ~3) {}
     __host__ __device__ unsigned loOffset() const { return 0u; }
     __host__ __device__ unsigned hiOffset() const { return 16u * nPad; }
-    __host__ __device__ unsigned boxOffset() const { return 32u * nPad; }
-    __host__ __device__ unsigned bytes() const { return 32u * nPad + static_cast<unsigned>(sizeof(DevBox)) * n; }
+    __host__ __device__ unsigned rectOffset() const { return 32u * nPad; }
+    __host__ __device__ unsigned boxOffset() const { return 48u * nPad; }
+    __host__ __device__ unsigned bytes() const { return 48u * nPad + static_cast<unsigned>(sizeof(DevBox)) * n; }
 };
 
 // Frame constants, passed by value as a kernel parameter (constant bank).
@@ -93,6 +96,8 @@ struct DevFrame {
     // rect_valid == 0 (a corner behind the camera, degenerate basis, DOF): test every pixel.
     int rect_valid;
     int rect_x0, rect_y0, rect_x1, rect_y1;
+    // the same per box (SceneBlobLayout::rect): primary rays only test the boxes whose rectangle holds their pixel
+    int box_rects_valid;
 };
 
 }  // namespace mcskin

@@ -337,42 +337,69 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
         for (int k = 0; k < 3; ++k) { f.cull_lo[k] = 1.0f; f.cull_hi[k] = -1.0f; }
         f.cull_valid = 1;
     }
-    // screen-space rectangle of the cull box for pinhole rays
+    // screen-space rectangle of a world-space box for pinhole rays: the pixels (inclusive, with a
+    // 2-pixel margin) whose rays can reach it; false if a corner is not in front of the camera
+    const bool canProject = !f.dof_on && cfg.width > 0 && cfg.height > 0 && halfW > 1e-6f && halfH > 1e-6f &&
+                            lenh(right) > 0.5f && lenh(fwd) > 0.5f;
+    auto project_box = [&](const float* lo, const float* hi, int* rect) {
+        double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+        for (int corner = 0; corner < 8; ++corner) {
+            const double p[3] = {(corner & 1) ? hi[0] : lo[0], (corner & 2) ? hi[1] : lo[1], (corner & 4) ? hi[2] : lo[2]};
+            const double rel[3] = {p[0] - pos.x, p[1] - pos.y, p[2] - pos.z};
+            const double depth = rel[0] * fwd.x + rel[1] * fwd.y + rel[2] * fwd.z;
+            if (!(depth > 1e-3)) return false;
+            const double su = (rel[0] * right.x + rel[1] * right.y + rel[2] * right.z) / depth;
+            const double sv = (rel[0] * trueUp.x + rel[1] * trueUp.y + rel[2] * trueUp.z) / depth;
+            const double px = (su / halfW + 1.0) * 0.5 * cfg.width;
+            const double py = (1.0 - (sv / halfH + 1.0) * 0.5) * cfg.height;
+            x0 = std::min(x0, px); x1 = std::max(x1, px);
+            y0 = std::min(y0, py); y1 = std::max(y1, py);
+        }
+        if (!(std::isfinite(x0) && std::isfinite(x1) && std::isfinite(y0) && std::isfinite(y1))) return false;
+        const double big = 1e9;
+        rect[0] = static_cast<int>(std::floor(std::max(-big, x0))) - 2;
+        rect[1] = static_cast<int>(std::floor(std::max(-big, y0))) - 2;
+        rect[2] = static_cast<int>(std::ceil(std::min(big, x1))) + 2;
+        rect[3] = static_cast<int>(std::ceil(std::min(big, y1))) + 2;
+        return true;
+    };
     f.rect_valid = 0;
-    if (f.cull_valid && !f.dof_on && cfg.width > 0 && cfg.height > 0 && halfW > 1e-6f && halfH > 1e-6f &&
-        lenh(right) > 0.5f && lenh(fwd) > 0.5f) {
+    if (f.cull_valid && canProject) {
         if (!anyBox) {
             f.rect_valid = 1;  // nothing to hit: an empty rectangle
             f.rect_x0 = f.rect_y0 = 1;
             f.rect_x1 = f.rect_y1 = 0;
         } else {
-            double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
-            bool allInFront = true;
-            for (int corner = 0; corner < 8 && allInFront; ++corner) {
-                const double p[3] = {(corner & 1) ? f.cull_hi[0] : f.cull_lo[0], (corner & 2) ? f.cull_hi[1] : f.cull_lo[1],
-                                     (corner & 4) ? f.cull_hi[2] : f.cull_lo[2]};
-                const double rel[3] = {p[0] - pos.x, p[1] - pos.y, p[2] - pos.z};
-                const double depth = rel[0] * fwd.x + rel[1] * fwd.y + rel[2] * fwd.z;
-                if (!(depth > 1e-3)) {
-                    allInFront = false;
-                    break;
-                }
-                const double su = (rel[0] * right.x + rel[1] * right.y + rel[2] * right.z) / depth;
-                const double sv = (rel[0] * trueUp.x + rel[1] * trueUp.y + rel[2] * trueUp.z) / depth;
-                const double px = (su / halfW + 1.0) * 0.5 * cfg.width;
-                const double py = (1.0 - (sv / halfH + 1.0) * 0.5) * cfg.height;
-                x0 = std::min(x0, px); x1 = std::max(x1, px);
-                y0 = std::min(y0, py); y1 = std::max(y1, py);
-            }
-            if (allInFront && std::isfinite(x0) && std::isfinite(x1) && std::isfinite(y0) && std::isfinite(y1)) {
-                const double big = 1e9;
+            int r[4];
+            if (project_box(f.cull_lo, f.cull_hi, r)) {
                 f.rect_valid = 1;
-                f.rect_x0 = static_cast<int>(std::floor(std::max(-big, x0))) - 2;
-                f.rect_y0 = static_cast<int>(std::floor(std::max(-big, y0))) - 2;
-                f.rect_x1 = static_cast<int>(std::ceil(std::min(big, x1))) + 2;
-                f.rect_y1 = static_cast<int>(std::ceil(std::min(big, y1))) + 2;
+                f.rect_x0 = r[0]; f.rect_y0 = r[1]; f.rect_x1 = r[2]; f.rect_y1 = r[3];
             }
         }
+    }
+    // and of every box (its reject bounds, inflated like the cull box)
+    f.box_rects_valid = 0;
+    if (f.rect_valid && scene->n_boxes > 0 && scene->n_boxes <= 32) {
+        const SceneBlobLayout lay(scene->n_boxes);
+        int* rects = reinterpret_cast<int*>(out.blob.data() + lay.rectOffset());
+        bool ok = true;
+        for (int b = 0; b < scene->n_boxes && ok; ++b) {
+            int* r = rects + 4 * b;
+            if (out.boxes[b].flags & kBoxEmpty) {
+                r[0] = r[1] = 1; r[2] = r[3] = 0;
+                continue;
+            }
+            float lo[3], hi[3];
+            for (int k = 0; k < 3; ++k) {
+                const double l = rejectLo[b][k], h = rejectHi[b][k];
+                const double margin = 1e-3 * (std::fabs(l) + std::fabs(h) + (h - l)) + 1e-2;
+                lo[k] = static_cast<float>(l - margin);
+                hi[k] = static_cast<float>(h + margin);
+                if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) ok = false;
+            }
+            if (ok) ok = project_box(lo, hi, r);
+        }
+        f.box_rects_valid = ok ? 1 : 0;
     }
     return MC_OK;
 }

@@ -646,6 +646,7 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
                                  (!fr.rect_valid || (px >= fr.rect_x0 && px <= fr.rect_x1 && py >= fr.rect_y0 && py <= fr.rect_y1));
         float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         bool hit = false;
+        const uint32_t boxMask = pixelCanHit ? pixel_box_mask(sc, px, py) : 0u;  // boxes whose screen rectangle holds the pixel
         if (valid) {
             const unsigned int word0 = static_cast<unsigned int>(q) * wordsPerPixel;
             for (int s = 0; s < spp; ++s) {
@@ -663,9 +664,9 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
                 float u, v;
                 sample_uv(fr, px, py, sd, &u, &v);
                 acc = add4(acc, config_background(fr, u, v));  // tile_renderer.cpp:111-119
-                if (pixelCanHit && !hit) {
+                if (boxMask && !hit) {
                     const Ray ray = primary_ray(fr, u, v, sd);
-                    hit = !misses_cull_box(fr, ray) && any_hit(sc, ray);
+                    hit = sc.rect ? any_hit_among(sc, ray, boxMask) : (!misses_cull_box(fr, ray) && any_hit(sc, ray));
                 }
             }
         }
@@ -794,12 +795,14 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
             }
         }
         bool hit = false;
-        if (pixelCanHit) {
+        // the boxes whose own screen rectangle holds this pixel (none: no ray at all)
+        const uint32_t boxMask = pixelCanHit ? pixel_box_mask(sc, px, py) : 0u;
+        if (boxMask) {
             for (int s = 0; s < SPP && !hit; ++s) {
                 const float u = div_by_size(fx + draws[2 * s], W, rW);
                 const float v = div_by_size(fy + draws[2 * s + 1], H, rH);
                 const Ray ray = camera_ray(fr, u, v);
-                hit = !misses_cull_box(fr, ray) && any_hit(sc, ray);
+                hit = sc.rect ? any_hit_among(sc, ray, boxMask) : (!misses_cull_box(fr, ray) && any_hit(sc, ray));
             }
         }
         const unsigned int outIndex = static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + px;
