@@ -388,8 +388,8 @@ def run_own_arm(args):
             "achieved": achieved, "peak": fp32_peak, "unit": "Tlane-op/s",
             "frac": achieved / fp32_peak,
             # DRAM bytes of one frame's kernels (dram__bytes_read.sum + dram__bytes_write.sum over the 16 launches of a
-            # serial frame, ncu --set full): queue traffic, ~13 % of HBM bandwidth at this frame time
-            "traffic": 1.06e9 if world == 1 else None, "traffic_source": "profiles/r01/final_ncu_summary.md",
+            # serial frame, ncu --set full): queue traffic, ~12 % of HBM bandwidth at this frame time
+            "traffic": 0.93e9 if world == 1 else None, "traffic_source": "profiles/r01/final_ncu_summary.md",
             "peak_source": f"{sm_count} SMs x 128 FP32 lanes x {peaks['sm_max_mhz']:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json"
                            + (", fallback" if peaks.get("_fallback") else "") + "); non-FMA issue rate, SURVEY.md §8d",
             "peak_measured": fp32_peak_measured,

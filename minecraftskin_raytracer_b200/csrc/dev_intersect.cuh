@@ -346,33 +346,7 @@ __device__ __forceinline__ uint32_t candidate_mask_among(const SceneView& sc, co
     return mask & (~rejected | sc.posed_mask);
 }
 
-// intersectScene for a ray known to reach only the boxes of `allow` (see pixel_box_mask): same result as
-// closest_hit, since a box outside the mask cannot be hit.
-__device__ __forceinline__ Hit closest_hit_among(const SceneView& sc, const Ray& ray, uint32_t allow) {
-    Hit best;
-    best.t = FLT_MAX;
-    best.box = -1;
-    best.face = 0;
-    best.texel = 0;
-    best.flip = false;
-    best.p = mk3(0.0f, 0.0f, 0.0f);
-    const RayPre pre = ray_pre(ray);
-    uint32_t mask = candidate_mask_among(sc, ray, pre, allow);
-    while (mask) {  // increasing box index: strict '<' keeps the reference's tie order
-        const int b = __ffs(mask) - 1;
-        mask &= mask - 1u;
-        BoxHit h;
-        if (mesh_test(sc, b, ray, pre, h) && h.t < best.t) {
-            best.t = h.t;
-            best.p = h.p;
-            best.box = b;
-            best.face = h.face;
-            best.texel = h.texel;
-            best.flip = h.flip;
-        }
-    }
-    return best;
-}
+// any_hit for a ray known to reach only the boxes of `allow` (see pixel_box_mask): a box outside the mask cannot be hit
 __device__ __forceinline__ bool any_hit_among(const SceneView& sc, const Ray& ray, uint32_t allow) {
     const RayPre pre = ray_pre(ray);
     uint32_t mask = candidate_mask_among(sc, ray, pre, allow);

@@ -113,8 +113,10 @@ k_wf_hit0(const DevFrame fr, const FramePointers fp_, const ActiveList list_, co
                 float u, v;
                 sample_uv(fr, px, py, sd, &u, &v);
                 ray = primary_ray(fr, u, v, sd);
-                // a pinhole ray can only reach the boxes whose screen rectangle holds its pixel
-                hit = sc.rect ? closest_hit_among(sc, ray, pixel_box_mask(sc, px, py)) : closest_hit(sc, ray);
+                // (restricting this query to the boxes whose screen rectangle holds the pixel, as the primary
+                // pass does, measured slower here: the branch-free reject pass over all boxes is cheaper than
+                // the mask plus a bit loop when nearly every ray hits)
+                hit = closest_hit(sc, ray);
                 if (fr.max_bounces < 0) {
                     // traceRay returns at once (depth 0 > maxBounces, raytracer.cpp:86-90); the tile
                     // renderer's re-test replaces misses by the gradient (tile_renderer.cpp:111-114)
