@@ -269,6 +269,13 @@ void mcskin_sincos_model(const float* angles, int32_t n, float* out_sin, float* 
  * non-zero y below the overflow threshold.  mcskin_powf_model is the same arithmetic on the host. */
 int32_t mcskin_cuda_powf(int32_t device, const float* x, const float* y, int32_t n, float* out);
 void mcskin_powf_model(const float* x, const float* y, int32_t n, float* out);
+/* The launch order of the primary pass for the tile rows {first + k*stride} of a frame (no device needed):
+ * block b renders part out_part[b] of out_parts[b] of local tile out_tile[b] (row-major in the band).  The
+ * tiles that intersect the figure's screen rectangle come first and are split over parts_heavy blocks.
+ * Returns the number of blocks, or a negative MC_ERR_*; fills at most `capacity` entries. */
+int32_t mcskin_primary_launch_order(const McScene* scene, const McConfig* cfg, int32_t first_tile_row, int32_t stride,
+                                    int32_t parts_heavy, int32_t parts_light, int32_t* out_tile, int32_t* out_part,
+                                    int32_t* out_parts, int32_t capacity);
 /* Measured ceiling of the roofline the bench reports against: a kernel of independent,
  * unfused FADD / FMUL chains on every SM; returns the best of a few launches in lane-ops per second. */
 int32_t mcskin_cuda_fp32_issue_peak(int32_t device, double* out_lane_ops_per_second);

@@ -1387,6 +1387,17 @@ int32_t mcskin_cuda_background(const McScene* scene, const McConfig* cfg, int32_
     return st.down(out, dO, sizeof(float4) * n);
 }
 
+int32_t mcskin_primary_launch_order(const McScene* scene, const McConfig* cfg, int32_t first, int32_t stride,
+                                    int32_t partsHeavy, int32_t partsLight, int32_t* outTile, int32_t* outPart,
+                                    int32_t* outParts, int32_t capacity) {
+    if (!scene || !cfg || capacity < 0) return fail(MC_ERR_INVALID, "primary_launch_order: bad argument");
+    PreparedFrame pf;
+    std::string err;
+    const int rc = prepare_frame(scene, cfg, 1, 0.0f, pf, err);
+    if (rc != MC_OK) return fail(rc, err);
+    return primary_launch_order(pf.frame, first, stride, partsHeavy, partsLight, outTile, outPart, outParts, capacity);
+}
+
 int32_t mcskin_cuda_fp32_issue_peak(int32_t device, double* out) {
     if (!out) return fail(MC_ERR_INVALID, "fp32_issue_peak: out is null");
     *out = 0.0;

@@ -24,13 +24,7 @@ constexpr int kMtN = 624;
 constexpr int kMtM = 397;
 
 __device__ __forceinline__ uint32_t mt_lcg(uint32_t prev, uint32_t i) {
-#ifdef MCSKIN_LCG_UMULHI
-    // prev >> 30 as the high word of prev * 4: IMAD.HI runs on the FMA pipe, which the
-    // recurrence (SHF + LOP3 + add on the ALU pipe, one IMAD on the FMA pipe) leaves idle
-    return 1812433253u * (prev ^ __umulhi(prev, 4u)) + i;
-#else
     return 1812433253u * (prev ^ (prev >> 30)) + i;
-#endif
 }
 // The twist: far ^ (y >> 1) ^ (y odd ? 0x9908b0df : 0), y = top bit of cur | low 31 bits of next.
 // Spelled so that it compiles to five instructions (bit-select LOP3, AND, IMAD for the conditional
@@ -64,64 +58,20 @@ __device__ __forceinline__ uint32_t mt_seed_word397(uint32_t word1) {
     return x;
 }
 
-// Pipe-balanced form for the seeding kernel.  The plain loop compiles to SHF + LOP3 + IADD on
-// the ALU pipe and one IMAD on the FMA pipe per step, and ncu shows the ALU pipe saturated
-// (83 %) with the FMA pipe at 27 %.  Here the index lives in a register that is advanced with a
-// multiply-add by a run-time 1 (`one`, opaque to the compiler), so every step is two ALU and two
-// FMA-pipe instructions, the index update off the dependent chain.
-// Variant 4 (straight-line code, the step index an immediate addend of the IMAD: SHF + LOP3 + IMAD
-// per step) measured fastest on B200; the IMAD.HI forms (1-3) lose more on the FMA pipe than they
-// take off the ALU pipe.
-#ifndef MCSKIN_LCG_VARIANT
-#define MCSKIN_LCG_VARIANT 4
-#endif
+// Word 397 for the seeding kernel, as straight-line code: the step index becomes an immediate addend of the
+// IMAD, so a step is SHF + LOP3 + IMAD (19 KB of code, but every warp of the kernel walks it in step).
+// `one` must be 1 at run time: it keeps the multiplier in a register, so the compiler emits the
+// register-times-register IMAD with an immediate addend.  Measured on B200 against: the rolled loop with a
+// register index (4 instructions per step, ALU pipe saturated), and forms that move the shift to the FMA
+// pipe as IMAD.HI (slower: IMAD.HI issues at a lower rate than it relieves the ALU pipe).
 __device__ __forceinline__ uint32_t mt_seed_word397_balanced(uint32_t word1, uint32_t one) {
     uint32_t x = word1;
-#if MCSKIN_LCG_VARIANT == 0
-    uint32_t i = 2u * one;
-#pragma unroll 12
-    for (int k = 2; k <= kMtM; ++k) {
-        const uint32_t y = x ^ (x >> 30);
-        asm("mad.lo.u32 %0, %1, 1812433253, %2;" : "=r"(x) : "r"(y), "r"(i));
-        asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(i) : "r"(one));
-    }
-#elif MCSKIN_LCG_VARIANT == 1
-    // x >> 30 as the high word of x * 4 (IMAD.HI, FMA pipe): one ALU and three FMA-pipe instructions per step
-    uint32_t i = 2u * one;
-#pragma unroll 12
-    for (int k = 2; k <= kMtM; ++k) {
-        const uint32_t y = x ^ __umulhi(x, 4u);
-        asm("mad.lo.u32 %0, %1, 1812433253, %2;" : "=r"(x) : "r"(y), "r"(i));
-        asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(i) : "r"(one));
-    }
-#elif MCSKIN_LCG_VARIANT == 2
-    // alternate the two forms: 3 ALU + 5 FMA-pipe instructions per two steps
-    uint32_t i = 2u * one;
-#pragma unroll 6
-    for (int k = 2; k <= kMtM; k += 2) {
-        uint32_t y = x ^ (x >> 30);
-        asm("mad.lo.u32 %0, %1, 1812433253, %2;" : "=r"(x) : "r"(y), "r"(i));
-        asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(i) : "r"(one));
-        y = x ^ __umulhi(x, 4u);
-        asm("mad.lo.u32 %0, %1, 1812433253, %2;" : "=r"(x) : "r"(y), "r"(i));
-        asm("mad.lo.u32 %0, %0, %1, %1;" : "+r"(i) : "r"(one));
-    }
-#elif MCSKIN_LCG_VARIANT == 3
-    // straight-line: the index is an immediate addend of the IMAD, three instructions per step
-    const uint32_t a = 1812433253u * one;
-#pragma unroll
-    for (int k = 2; k <= kMtM; ++k) {
-        const uint32_t y = (k & 1) ? (x ^ __umulhi(x, 4u)) : (x ^ (x >> 30));
-        x = y * a + static_cast<uint32_t>(k);
-    }
-#elif MCSKIN_LCG_VARIANT == 4
     const uint32_t a = 1812433253u * one;
 #pragma unroll
     for (int k = 2; k <= kMtM; ++k) {
         const uint32_t y = x ^ (x >> 30);
         x = y * a + static_cast<uint32_t>(k);
     }
-#endif
     return x;
 }
 

@@ -82,7 +82,7 @@ static TileOrder make_tile_order(const DevFrame& fr, const BandView& band, int p
 }
 
 // launch slot -> local tile index; a bijection of [0, tiles of the band)
-__device__ __forceinline__ int ordered_tile(const TileOrder& o, int W, int slot) {
+__host__ __device__ __forceinline__ int ordered_tile(const TileOrder& o, int W, int slot) {
     if (o.n_heavy == 0) return slot;
     if (slot < o.n_heavy) {
         const int r = slot / o.hw;
@@ -100,7 +100,7 @@ __device__ __forceinline__ int ordered_tile(const TileOrder& o, int W, int slot)
     return (o.r0 + o.hr) * W + slot;   // the rows below
 }
 // block -> (launch slot, part, parts of that tile)
-__device__ __forceinline__ void block_to_slot(const TileOrder& o, int block, int* slot, int* part, int* parts) {
+__host__ __device__ __forceinline__ void block_to_slot(const TileOrder& o, int block, int* slot, int* part, int* parts) {
     const int heavyBlocks = o.n_heavy * o.parts_heavy;
     if (block < heavyBlocks) {
         *parts = o.parts_heavy;
@@ -1202,6 +1202,28 @@ void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out
 void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream) {
     if (n > 0) k_background<<<blocks_for(n), kBlockThreads, 0, stream>>>(fr, uv, n, out);
 }
+int primary_launch_order(const DevFrame& fr, int first, int stride, int partsHeavy, int partsLight, int* outTile,
+                         int* outPart, int* outParts, int capacity) {
+    BandView band{};
+    band.first_tile_row = first;
+    band.tile_row_stride = stride;
+    band.n_tile_rows = (fr.tiles_y <= 0 || first < 0 || stride <= 0 || first >= fr.tiles_y) ? 0 : (fr.tiles_y - first + stride - 1) / stride;
+    const int nTiles = band.n_tile_rows * fr.tiles_x;
+    if (nTiles <= 0) return 0;
+    partsLight = partsLight < 1 ? 1 : partsLight;
+    partsHeavy = partsHeavy < partsLight ? partsLight : partsHeavy;
+    const TileOrder order = make_tile_order(fr, band, partsHeavy, partsLight);
+    const int blocks = order.n_heavy * order.parts_heavy + (nTiles - order.n_heavy) * order.parts_light;
+    for (int b = 0; b < blocks && b < capacity; ++b) {
+        int slot, part, parts;
+        block_to_slot(order, b, &slot, &part, &parts);
+        if (outTile) outTile[b] = ordered_tile(order, fr.tiles_x, slot);
+        if (outPart) outPart[b] = part;
+        if (outParts) outParts[b] = parts;
+    }
+    return blocks;
+}
+
 void launch_fp32_peak(int blocks, int iters, float* sink, cudaStream_t stream) {
     k_fp32_peak<<<blocks, kBlockThreads, 0, stream>>>(iters, sink);
 }

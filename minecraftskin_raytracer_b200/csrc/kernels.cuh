@@ -76,6 +76,10 @@ void launch_ambient_occlusion(const DevFrame& fr, const FramePointers& fp, const
                               cudaStream_t stream);
 void launch_generate_rays(const DevFrame& fr, const float* uv, int n, McRay* out, cudaStream_t stream);
 void launch_background(const DevFrame& fr, const float* uv, int n, float4* out, cudaStream_t stream);
+// Host evaluation of the primary pass's block -> (tile, part) map for a band (the same functions the
+// kernels run): returns the number of blocks, fills at most `capacity` entries.
+int primary_launch_order(const DevFrame& fr, int first, int stride, int partsHeavy, int partsLight, int* outTile,
+                         int* outPart, int* outParts, int capacity);
 // FADD/FMUL issue-rate microbenchmark: `iters` rounds of 16 unfused operations per thread; result written to sink
 void launch_fp32_peak(int blocks, int iters, float* sink, cudaStream_t stream);
 void launch_peer_signal(unsigned int* flag, unsigned int value, cudaStream_t stream);

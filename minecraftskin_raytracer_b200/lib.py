@@ -36,6 +36,7 @@ EXPORTS = [
     "mcskin_sincos_model", "mcskin_cuda_powf", "mcskin_powf_model", "mcskin_cuda_context_render_rows_into_frame",
     "mcskin_cuda_device_alloc", "mcskin_cuda_device_free", "mcskin_cuda_ipc_export", "mcskin_cuda_ipc_open",
     "mcskin_cuda_ipc_close", "mcskin_cuda_fp32_issue_peak", "mcskin_cuda_peer_signal", "mcskin_cuda_peer_wait",
+    "mcskin_primary_launch_order",
 ]
 
 
@@ -392,6 +393,21 @@ def powf_model(x, y) -> np.ndarray:
     out = np.zeros(len(x), dtype=np.float32)
     _lib.mcskin_powf_model(_ptr(x, C.c_float), _ptr(y, C.c_float), C.c_int32(len(x)), _ptr(out, C.c_float))
     return out
+
+
+def primary_launch_order(scene: FlatScene, cfg: McConfig, first_tile_row: int = 0, stride: int = 1, parts_heavy: int = 1,
+                         parts_light: int = 1):
+    """(tile, part, parts) per block of the primary pass for a band, as the kernels map them (no GPU needed)."""
+    cs = scene.as_c()
+    n = _lib.mcskin_primary_launch_order(C.byref(cs), C.byref(cfg), C.c_int32(first_tile_row), C.c_int32(stride),
+                                         C.c_int32(parts_heavy), C.c_int32(parts_light), None, None, None, C.c_int32(0))
+    _check(min(n, 0))
+    tile, part, parts = (np.zeros(n, dtype=np.int32) for _ in range(3))
+    if n:
+        _lib.mcskin_primary_launch_order(C.byref(cs), C.byref(cfg), C.c_int32(first_tile_row), C.c_int32(stride),
+                                         C.c_int32(parts_heavy), C.c_int32(parts_light), _ptr(tile, C.c_int32),
+                                         _ptr(part, C.c_int32), _ptr(parts, C.c_int32), C.c_int32(n))
+    return tile, part, parts
 
 
 def fp32_issue_peak(device: int = 0) -> float:

@@ -185,3 +185,31 @@ def test_powf_model_equals_libm(mclib):
     x, y = powf_test_values(40_000)
     got = mclib.powf_model(x, y)
     assert np.array_equal(got.view(np.uint32), _libm_powf(x, y).view(np.uint32))
+
+
+@pytest.mark.parametrize("width,height,tile,first,stride", [(1920, 1080, 32, 0, 1), (1920, 1080, 32, 1, 3), (300, 200, 16, 0, 1),
+                                                             (300, 200, 16, 2, 4), (97, 131, 32, 0, 2), (64, 64, 32, 1, 2)])
+@pytest.mark.parametrize("parts", [(1, 1), (3, 1), (4, 2)])
+def test_primary_launch_order_covers_every_tile_part_once(mclib, width, height, tile, first, stride, parts):
+    """The primary pass launches the figure's tiles first and may split them over several blocks: every
+    (tile, part) of the band must be rendered by exactly one block, heavy tiles ahead of the rest."""
+    scene = mclib.build_skin_scene(synth_skin(0), "walking")
+    cfg = make_config(width=width, height=height, tile_size=tile, samples_per_pixel=4)
+    t, p, n = mclib.primary_launch_order(scene, cfg, first, stride, parts_heavy=parts[0], parts_light=parts[1])
+    tiles_x, tiles_y = -(-width // tile), -(-height // tile)
+    rows = len(range(first, tiles_y, stride))
+    n_tiles = rows * tiles_x
+    assert t.min() >= 0 and t.max() < n_tiles and set(t.tolist()) == set(range(n_tiles))
+    seen = set(zip(t.tolist(), p.tolist()))
+    assert len(seen) == len(t)                                     # no (tile, part) twice
+    per_tile = {}
+    for ti, ni in zip(t.tolist(), n.tolist()):
+        assert per_tile.setdefault(ti, ni) == ni                   # one split factor per tile
+    assert all((ti, k) in seen for ti, ni in per_tile.items() for k in range(ni))
+    assert set(per_tile.values()) <= {max(parts), parts[1]}
+    heavy = [ti for ti, ni in per_tile.items() if ni == max(parts)] if parts[0] > parts[1] else []
+    if heavy:                                                      # split tiles come first, and form a rectangle of tiles
+        first_light = next((i for i, ni in enumerate(n.tolist()) if ni == parts[1]), len(n))
+        assert set(t[:first_light].tolist()) == set(heavy)
+        cols, rws = sorted({h % tiles_x for h in heavy}), sorted({h // tiles_x for h in heavy})
+        assert len(heavy) == len(cols) * len(rws) and cols == list(range(cols[0], cols[-1] + 1))
