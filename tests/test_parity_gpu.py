@@ -379,6 +379,29 @@ def test_cuda_vs_golden_reference_rays(gpu):
     assert np.array_equal(_bits(gpu.background(scene, cfg, v["rays/uv"])), _bits(v["rays/background"]))
 
 
+# ---------------------------------------------------------------- BASELINE.json configurations at full size
+@pytest.mark.parametrize("name,seed,kind,over", [
+    ("C1", 1, "64x64", dict(width=512, height=512, samples_per_pixel=1, max_bounces=2)),
+    ("C2", 2, "legacy", dict(width=1920, height=1080, samples_per_pixel=4, max_bounces=4)),
+    ("headline", 0, "64x64", dict(width=1920, height=1080, samples_per_pixel=16, max_bounces=4)),
+], ids=["C1", "C2", "headline"])
+def test_baseline_configs_at_full_size(gpu, oracle, name, seed, kind, over):
+    """BASELINE.json configs[0], configs[1] and the headline frame, whole, against the CPU path run here on
+    the box's host cores (the unmodified reference when its library travelled, else the C restatement):
+    the north star's bar (>= 99.9 % of pixels within 1 LSB, hit ids exact) — and, on an FMA host, the same bits."""
+    from oracle.harness import Reference
+    scene = _scene(gpu, seed, kind, None)
+    cfg = make_config(**over)
+    ref = Reference.load()
+    want = ref.render(scene, cfg) if ref is not None else oracle.render(scene, cfg)
+    got, _, _ = gpu.render(scene, cfg)
+    rep = pixel_report(got, want, oracle.quantize)
+    assert rep["within1"] >= 0.999, (name, rep)
+    if _flip_budget() == 0.0:
+        assert np.array_equal(_bits(got), _bits(want)), (name, rep)
+    assert np.array_equal(gpu.aov(scene, cfg), oracle.aov(scene, cfg)), name
+
+
 # ---------------------------------------------------------------- full-size properties (no oracle run)
 def test_headline_frame_properties(gpu, oracle):
     """BASELINE headline size (1080p / 16 spp / 4 bounces): properties that need no CPU frame."""
