@@ -102,6 +102,7 @@ struct McContext {
     int primaryBlocksPerSm = 2;              // split tiles over blocks only while a launch has fewer than this many per SM
                                              // (every block of a split tile regenerates the tile's whole jitter stream)
     int waveQueueLevels = 4;                 // bounce depths handled by queues; deeper ones in-thread
+    bool waveQueueLevelsAuto = true;         // small shares of a frame (few tiles per SM) use 1 level: see render_bands_lane
     int waveDeepGridDiv = 1;                 // launches of depth >= 1 use shade grid / this
     int frameLanes = 3;                      // a frame's tile rows are rendered on this many streams at once
     bool isChild = false;                    // a lane of another context (never splits frames itself)
@@ -261,7 +262,11 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
         if (!wavefront_carve(f, ctx->wave.p, ctx->wave.cap, static_cast<unsigned int>(paths),
                              ctx->smCount * ctx->shadeBlocksPerSm, &wave))
             return fail(MC_ERR_CUDA, "wavefront buffer carve failed");
-        wave.queueLevels = ctx->waveQueueLevels;
+        // A small share of a frame (one GPU's rows of an 8-way split, a 512x512 frame) has too few hits per
+        // bounce level to amortise three launches a level: only the primary hits go through the queues,
+        // the bounces are finished in-thread (B200 sweep: -7 % on an eighth of the 1080p frame).
+        const bool smallShare = static_cast<long long>(nRows) * f.tiles_x * std::max(1, lanesInFlight) * 2 < 5ll * ctx->smCount;
+        wave.queueLevels = (ctx->waveQueueLevelsAuto && smallShare) ? 1 : ctx->waveQueueLevels;
         wave.deepGridDiv = ctx->waveDeepGridDiv;
     }
     if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->ev0, stream));
@@ -347,6 +352,7 @@ void inherit_options(McContext* lane, const McContext* ctx) {
     lane->shadeMode = ctx->shadeMode;
     lane->forceAllActive = ctx->forceAllActive;
     lane->waveQueueLevels = ctx->waveQueueLevels;
+    lane->waveQueueLevelsAuto = ctx->waveQueueLevelsAuto;
     lane->waveDeepGridDiv = ctx->waveDeepGridDiv;
     lane->waveBudgetBytes = ctx->waveBudgetBytes;
     lane->recordBudgetBytes = ctx->recordBudgetBytes;
@@ -382,7 +388,7 @@ int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* out
 
 long long option_bits(const McContext* c, int i) {
     const long long v[12] = {c->forceAllActive, c->recordBudgetBytes, c->shadeBlocksPerSm, c->primaryBlocksPerSm,
-                             c->waveQueueLevels, c->shadeMode, c->waveBudgetBytes, c->waveDeepGridDiv,
+                             c->waveQueueLevelsAuto ? -c->waveQueueLevels : c->waveQueueLevels, c->shadeMode, c->waveBudgetBytes, c->waveDeepGridDiv,
                              0, c->cacheTileSeeds, c->heavyTilesPerSm, c->frameLanes};
     return v[i];
 }
@@ -831,7 +837,10 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
     if (const char* v = std::getenv("MCSKIN_HEAVY_TILES")) ctx->heavyTilesPerSm = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_PRIMARY_BLOCKS")) ctx->primaryBlocksPerSm = std::max(0, std::atoi(v));
-    if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) ctx->waveQueueLevels = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) {
+        ctx->waveQueueLevels = std::max(1, std::atoi(v));
+        ctx->waveQueueLevelsAuto = false;
+    }
     if (const char* v = std::getenv("MCSKIN_DEEP_GRID_DIV")) ctx->waveDeepGridDiv = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_BATCH_GROUP")) ctx->batchGroup = std::min(4096, std::max(1, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_BATCH_MODE")) ctx->batchMode = std::atoi(v) != 0;
@@ -886,7 +895,10 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "batch_group") ctx->batchGroup = static_cast<int>(std::min<int64_t>(4096, std::max<int64_t>(1, value)));
     else if (k == "batch_mode") ctx->batchMode = value != 0;
     else if (k == "shade_mode") ctx->shadeMode = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
-    else if (k == "wave_queue_levels") ctx->waveQueueLevels = static_cast<int>(std::max<int64_t>(1, value));
+    else if (k == "wave_queue_levels") {
+        ctx->waveQueueLevels = static_cast<int>(std::max<int64_t>(1, value));
+        ctx->waveQueueLevelsAuto = false;
+    }
     else if (k == "wave_deep_grid_div") ctx->waveDeepGridDiv = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "frame_lanes") ctx->frameLanes = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(1, value)));
     else if (k == "cache_tile_seeds") ctx->cacheTileSeeds = value != 0;
