@@ -213,3 +213,18 @@ def test_primary_launch_order_covers_every_tile_part_once(mclib, width, height, 
         assert set(t[:first_light].tolist()) == set(heavy)
         cols, rws = sorted({h % tiles_x for h in heavy}), sorted({h // tiles_x for h in heavy})
         assert len(heavy) == len(cols) * len(rws) and cols == list(range(cols[0], cols[-1] + 1))
+
+
+def libm_golden():
+    return np.load(ROOT / "tests" / "golden" / "libm_vectors.npz")
+
+
+def test_sincos_and_powf_models_equal_golden_libm_vectors(mclib):
+    """Host models of the device's sinf/cosf/powf against committed outputs of glibc 2.39 (FMA variants),
+    whatever libm variant this host would pick (tests/golden/make_libm_golden.py)."""
+    g = libm_golden()
+    sn, cs = mclib.sincos_model(g["angles"])
+    assert np.array_equal(sn.view(np.uint32), g["sin"].view(np.uint32))
+    assert np.array_equal(cs.view(np.uint32), g["cos"].view(np.uint32))
+    pw = mclib.powf_model(g["pow_x"], g["pow_y"])
+    assert np.array_equal(pw.view(np.uint32), g["pow"].view(np.uint32))

@@ -105,6 +105,15 @@ def test_powf_device_equals_host_model_and_libm(gpu):
         assert np.array_equal(_bits(gpu.powf(x[sub], y[sub])), _bits(_libm_powf(x[sub], y[sub])))
 
 
+def test_sincos_and_powf_device_equal_golden_libm_vectors(gpu):
+    """The device functions against committed glibc outputs (host-independent pin of the libm parity)."""
+    from tests.test_host_side import libm_golden
+    g = libm_golden()
+    sn, cs = gpu.sincos(g["angles"])
+    assert np.array_equal(_bits(sn), _bits(g["sin"])) and np.array_equal(_bits(cs), _bits(g["cos"]))
+    assert np.array_equal(_bits(gpu.powf(g["pow_x"], g["pow_y"])), _bits(g["pow"]))
+
+
 # With sinf/cosf bit-identical to the host's (FMA build of glibc) the sampled light points are the
 # reference's own, so shadow factors match exactly; on a host whose glibc picks the non-FMA
 # variant a last-ulp difference can move a shadow ray across an edge now and then.
