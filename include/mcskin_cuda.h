@@ -139,7 +139,9 @@ int32_t mcskin_cuda_abi_version(void);
  * as compiled, so a binding can verify its mirror of this header. */
 void mcskin_cuda_abi_sizes(int32_t* out8);
 
-/* TileRenderer::render: host scene in, host image out (row-major, width*height pixels).
+/* TileRenderer::render (tile_renderer.h:26-28, tile_renderer.cpp:129-189): host scene in, host image out
+ * (row-major, width*height pixels).  With page-locked destinations the image leaves for the host while the
+ * shading pass still runs.
  * out_rgba_f32 : width*height*4 floats (Image::pixels), may be NULL
  * out_rgba_u8  : width*height*4 bytes, uint8(clamp(c)*255+0.5) (image_writer.cpp:18-22), may be NULL
  * Renders on the current thread's CUDA device `device` (>= 0). */
@@ -196,17 +198,22 @@ int32_t mcskin_cuda_peer_signal(int32_t device, void* d_flag, uint32_t value, vo
 int32_t mcskin_cuda_peer_wait(int32_t device, const void* d_flags, int32_t n, uint32_t value, void* d_timeout, void* stream);
 /* Blocks until the context's work is done, fills stats of the last render. */
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats);
-/* Tuning / test knobs: "force_all_active" (0/1: skip the hit/miss classification and
- * shade every pixel), "record_budget_bytes" (work-list memory per launch pair),
- * "shade_blocks_per_sm" (persistent grid size of the shading pass), "shade_mode" (0 wavefront,
- * 1/2 megakernel variants), "wave_queue_levels", "wave_budget_bytes", "primary_blocks_per_sm",
- * "batch_lanes". */
+/* Tuning / test knobs (every combination renders the same bits; INTEGRATION.md §6 has the table):
+ * "frame_lanes" (streams a frame's tile rows are dealt to), "use_graphs" (replay a repeated frame as a CUDA
+ * graph), "cache_tile_seeds", "wave_queue_levels", "wave_deep_grid_div", "wave_budget_bytes",
+ * "record_budget_bytes", "shade_blocks_per_sm", "primary_blocks_per_sm", "heavy_tiles_per_sm",
+ * "shade_mode" (0 wavefront, 1/2 megakernel forms), "force_all_active" (0/1: skip the hit/miss
+ * classification and shade every pixel), "overlap_copy_out", "batch_mode", "batch_group", "batch_lanes".
+ * Unknown names return MC_ERR_INVALID. */
 int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t value);
 
-/* Batched renders (one skin per scene, same config), scene i -> image i.
- * d_out_* are device pointers to n_scenes consecutive images.  Asynchronous: frames are
- * pipelined over a few internal streams ("batch_lanes" option); the given stream (or the
- * context's) waits for all of them, mcskin_cuda_context_sync blocks until they are done. */
+/* Batched renders (one skin per scene, same config), scene i -> image i (SURVEY.md §8e).
+ * d_out_* are device pointers to n_scenes consecutive images.  Asynchronous.  Scenes that share a frame
+ * description (image size, sampling, camera, light, box layout) are rendered by one set of launches whose
+ * gridDim.y is the scene, "batch_group" scenes at a time; with "batch_mode" 0, or for frame descriptions
+ * without a batched kernel form, frames are pipelined one by one over "batch_lanes" internal streams.
+ * The given stream (or the context's) carries or waits for all of it; mcskin_cuda_context_sync blocks
+ * until the images are complete. */
 int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, int32_t n_scenes,
                                          const McConfig* cfg, void* d_out_f32, void* d_out_u8, void* stream);
 
