@@ -98,6 +98,7 @@ struct McContext {
     int forceAllActive = 0;
     long long recordBudgetBytes = 1ll << 31;
     int shadeBlocksPerSm = 8;
+    int softBlocksPerSm = 4;                 // persistent blocks of the soft-shadow kernel (its shared memory fits 4 per SM)
     int heavyTilesPerSm = 16;                // the figure's tiles are split over more blocks while a frame (all lanes) has fewer tiles per SM
     int primaryBlocksPerSm = 2;              // split tiles over blocks only while a launch has fewer than this many per SM
                                              // (every block of a split tile regenerates the tile's whole jitter stream)
@@ -268,6 +269,7 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
         const bool smallShare = static_cast<long long>(nRows) * f.tiles_x * std::max(1, lanesInFlight) * 2 < 5ll * ctx->smCount;
         wave.queueLevels = (ctx->waveQueueLevelsAuto && smallShare) ? 1 : ctx->waveQueueLevels;
         wave.deepGridDiv = ctx->waveDeepGridDiv;
+        wave.softGrid = ctx->smCount * ctx->softBlocksPerSm;
     }
     if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->ev0, stream));
     const FramePointers fp = frame_pointers(scn);
@@ -357,6 +359,7 @@ void inherit_options(McContext* lane, const McContext* ctx) {
     lane->waveBudgetBytes = ctx->waveBudgetBytes;
     lane->recordBudgetBytes = ctx->recordBudgetBytes;
     lane->shadeBlocksPerSm = ctx->shadeBlocksPerSm;
+    lane->softBlocksPerSm = ctx->softBlocksPerSm;
     lane->primaryBlocksPerSm = ctx->primaryBlocksPerSm;
     lane->heavyTilesPerSm = ctx->heavyTilesPerSm;
     lane->cacheTileSeeds = ctx->cacheTileSeeds;
@@ -389,7 +392,7 @@ int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* out
 long long option_bits(const McContext* c, int i) {
     const long long v[12] = {c->forceAllActive, c->recordBudgetBytes, c->shadeBlocksPerSm, c->primaryBlocksPerSm,
                              c->waveQueueLevelsAuto ? -c->waveQueueLevels : c->waveQueueLevels, c->shadeMode, c->waveBudgetBytes, c->waveDeepGridDiv,
-                             0, c->cacheTileSeeds, c->heavyTilesPerSm, c->frameLanes};
+                             c->softBlocksPerSm, c->cacheTileSeeds, c->heavyTilesPerSm, c->frameLanes};
     return v[i];
 }
 
@@ -765,7 +768,7 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
                 const int gridX = std::max(2, (ctx->smCount * ctx->shadeBlocksPerSm + nC - 1) / nC);
                 if (!wavefront_carve(pf.frame, static_cast<unsigned char*>(ctx->batchWave.p) + static_cast<size_t>(i) * waveBytes,
                                      waveBytes, static_cast<unsigned int>(paths), gridX, &sl.wave))
-                    return fail(MC_ERR_CUDA, "render_batch: queue carve failed");
+                    return MC_OK;  // (cannot happen: sizes come from the same frame description) frame-by-frame path instead
                 sl.wave.queueLevels = ctx->waveQueueLevels;
                 sl.wave.deepGridDiv = 1;
                 stageSlices[sliceAt++] = sl;
@@ -786,7 +789,7 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
             launch_batch_reset(gs, nS, first.wave.levels, stream);
             if (!launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), !seeded, gs, nS, first.fp.blob_bytes,
                                       ctx->smCount * ctx->primaryBlocksPerSm, stream))
-                return fail(MC_ERR_CUDA, "render_batch: no batched primary kernel for this frame description");
+                return MC_OK;  // no batched primary kernel for this frame description: frame-by-frame path instead
             seeded = true;  // same image geometry for every scene of the batch
             int launches = 0;
             launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
@@ -849,6 +852,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     if (const char* v = std::getenv("MCSKIN_FRAME_LANES")) ctx->frameLanes = std::min(8, std::max(1, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_CACHE_TILE_SEEDS")) ctx->cacheTileSeeds = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_SHADE_BLOCKS")) ctx->shadeBlocksPerSm = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("MCSKIN_SOFT_BLOCKS")) ctx->softBlocksPerSm = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_SHADE_MODE")) ctx->shadeMode = std::min(2, std::max(0, std::atoi(v)));
     *out = ctx.release();
     return MC_OK;
@@ -889,6 +893,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     if (k == "force_all_active") ctx->forceAllActive = value != 0;
     else if (k == "record_budget_bytes") ctx->recordBudgetBytes = std::max<int64_t>(1, value);
     else if (k == "shade_blocks_per_sm") ctx->shadeBlocksPerSm = static_cast<int>(std::max<int64_t>(1, value));
+    else if (k == "soft_blocks_per_sm") ctx->softBlocksPerSm = static_cast<int>(std::max<int64_t>(1, value));
     else if (k == "primary_blocks_per_sm") ctx->primaryBlocksPerSm = static_cast<int>(std::max<int64_t>(0, value));
     else if (k == "heavy_tiles_per_sm") ctx->heavyTilesPerSm = static_cast<int>(std::max<int64_t>(0, value));
     else if (k == "batch_lanes") ctx->batchLanes = static_cast<int>(std::min<int64_t>(16, std::max<int64_t>(1, value)));

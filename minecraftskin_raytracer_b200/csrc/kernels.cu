@@ -1067,27 +1067,24 @@ static int log2_if_warp_spp(int spp) {
     return -1;
 }
 
+// Dynamic shared memory the pixel-per-lane kernels may use on the current device (see SmemOptIn).
+static size_t pix_smem_limit() {
+    static SmemOptIn optIn;
+    static const void* const fns[] = {
+        reinterpret_cast<const void*>(k_primary_pix<false>), reinterpret_cast<const void*>(k_primary_pix<true>),
+        reinterpret_cast<const void*>(k_primary_pix_fixed<16, true, false>), reinterpret_cast<const void*>(k_primary_pix_fixed<16, false, false>),
+        reinterpret_cast<const void*>(k_primary_pix_fixed<4, true, false>), reinterpret_cast<const void*>(k_primary_pix_fixed<4, false, false>),
+        reinterpret_cast<const void*>(k_primary_pix_fixed<16, true, true>), reinterpret_cast<const void*>(k_primary_pix_fixed<16, false, true>),
+        reinterpret_cast<const void*>(k_primary_pix_fixed<4, true, true>), reinterpret_cast<const void*>(k_primary_pix_fixed<4, false, true>)};
+    return optIn.limit(fns, static_cast<int>(sizeof(fns) / sizeof(fns[0])));
+}
+
 // The pixel-per-lane primary kernels over one scene (batch == nullptr) or the scenes of a batch.
 static void launch_primary_pix(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
                                uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, int heavyTargetTiles,
                                const BatchSlice* batch, int nScenes, unsigned int blobBytes, cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
     const size_t pixSmem = ((sizeof(PixStreamSmem) + 15) & ~size_t(15)) + blobBytes;
-    static bool attrSet = false;
-    if (!attrSet) {
-        const int kMax = 100 * 1024;
-        cudaFuncSetAttribute(k_primary_pix<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        cudaFuncSetAttribute(k_primary_pix<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        cudaFuncSetAttribute(k_primary_pix_fixed<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        cudaFuncSetAttribute(k_primary_pix_fixed<16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        cudaFuncSetAttribute(k_primary_pix_fixed<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        cudaFuncSetAttribute(k_primary_pix_fixed<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        cudaFuncSetAttribute(k_primary_pix_fixed<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        cudaFuncSetAttribute(k_primary_pix_fixed<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        cudaFuncSetAttribute(k_primary_pix_fixed<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        cudaFuncSetAttribute(k_primary_pix_fixed<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-        attrSet = true;
-    }
     // the seeded engines depend on the tile geometry only: one set serves every scene of a batch
     if (fr.draws_per_sample > 0 && seedTiles) k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates);
     // enough blocks to fill the machine, at most one block per round of 256 pixels
@@ -1123,10 +1120,13 @@ static void launch_primary_pix(const DevFrame& fr, const FramePointers& fp, cons
 #undef MCSKIN_LAUNCH_PIX_FIXED
 }
 
-static bool pix_kernel_applies(const DevFrame& fr) {
+static bool pix_kernel_applies(const DevFrame& fr, unsigned int blobBytes) {
     // the warp / pixel variants index a tile's stream with 32-bit integers
     const long long tileDraws = static_cast<long long>(fr.tile_size) * fr.tile_size * fr.spp * (fr.draws_per_sample > 0 ? fr.draws_per_sample : 1);
-    return tileDraws < (1ll << 30) && kBlockThreads * fr.spp * fr.draws_per_sample + kMtN <= kPixRingWords;
+    if (!(tileDraws < (1ll << 30) && kBlockThreads * fr.spp * fr.draws_per_sample + kMtN <= kPixRingWords)) return false;
+    // ring + scene blob must fit the device's opt-in shared memory (the generic ring is 72.5 KB, the blob up to 40 KB)
+    const size_t need = ((sizeof(PixStreamSmem) + 15) & ~size_t(15)) + blobBytes + 64;
+    return need <= pix_smem_limit();
 }
 
 bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
@@ -1136,7 +1136,7 @@ bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView&
     if (nTiles <= 0) return false;
     const long long tileDraws = static_cast<long long>(fr.tile_size) * fr.tile_size * fr.spp * (fr.draws_per_sample > 0 ? fr.draws_per_sample : 1);
     const int lg = tileDraws < (1ll << 30) ? log2_if_warp_spp(fr.spp) : -1;
-    if (classify && pix_kernel_applies(fr)) {
+    if (classify && pix_kernel_applies(fr, fp.blob_bytes)) {
         launch_primary_pix(fr, fp, band, list, tileStates, seedTiles, primaryTargetBlocks, heavyTargetTiles, nullptr, 1,
                            fp.blob_bytes, stream);
         return fr.draws_per_sample > 0;
@@ -1152,7 +1152,7 @@ bool launch_primary_batch(const DevFrame& fr, const BandView& band, uint32_t* ti
                           const BatchSlice* batch, int nScenes, unsigned int blobBytes, int primaryTargetBlocks,
                           cudaStream_t stream) {
     const int nTiles = band.n_tile_rows * fr.tiles_x;
-    if (nTiles <= 0 || nScenes <= 0 || !pix_kernel_applies(fr)) return false;
+    if (nTiles <= 0 || nScenes <= 0 || !pix_kernel_applies(fr, blobBytes)) return false;
     launch_primary_pix(fr, FramePointers{}, band, ActiveList{}, tileStates, seedTiles, primaryTargetBlocks, 0, batch, nScenes,
                        blobBytes, stream);
     return true;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "dev_types.cuh"
 #include "mcskin_cuda.h"
 
@@ -11,6 +13,37 @@ namespace mcskin {
 constexpr int kBlockThreads = 256;
 // scene blob staged per CTA; 40 KB keeps the default 48 KB dynamic+static shared memory limit (227 boxes)
 constexpr unsigned int kMaxSceneSmemBytes = 40u * 1024u;
+
+// Dynamic shared memory above the default 48 KB is an opt-in that CUDA keeps per function AND per
+// device: a process that renders on several GPUs (mcskin_cuda_render_multi, one context per device)
+// has to raise it on each of them.  One instance per group of kernels; limit() raises the attribute
+// of every kernel of the group to the device's opt-in maximum (227 KB on sm_100) the first time it is
+// called with that device current, and returns the bytes a launch may ask for (0: could not be raised,
+// keep to kernels that fit 48 KB).
+class SmemOptIn {
+public:
+    size_t limit(const void* const* fns, int nFns) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+        std::lock_guard<std::mutex> lock(mu_);
+        if (known_[dev]) return limit_[dev];
+        int optin = 0;
+        if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) optin = 0;
+        bool ok = optin > 48 * 1024;
+        for (int i = 0; ok && i < nFns; ++i)
+            ok = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        limit_[dev] = ok ? static_cast<size_t>(optin) : 0;
+        known_[dev] = true;
+        return limit_[dev];
+    }
+
+private:
+    static constexpr int kMaxDevices = 64;
+    std::mutex mu_;
+    size_t limit_[kMaxDevices] = {};
+    bool known_[kMaxDevices] = {};
+};
 
 // Which tile rows of the frame a launch covers, and where its pixels land.
 // Local tile row r is frame tile row first_tile_row + r*tile_row_stride; the output

@@ -136,11 +136,149 @@ k_wf_hit0(const DevFrame fr, const FramePointers fp_, const ActiveList list_, co
     }
 }
 
-// ---------------------------------------------------------------- shadow sample points
+// ---------------------------------------------------------------- soft shadows of one queue level
+// computeSoftShadow (shading.cpp:28-60) for every hit of a queue, in ONE kernel.  A block works through
+// chunks of 256 hits, claimed from a device counter, in three block-synchronous phases:
+//   A  thread = hit: the common origin of the hit's shadow rays and the boxes their bundle can reach.
+//      Nothing in reach -> all N rays are lit by construction, the hit is done.  The others are
+//      COMPACTED into a ring in shared memory, so that phase B runs with full warps however the
+//      "nothing in reach" hits are spread over the queue (they were a third of the lanes of the
+//      seeding loop when it ran per queue entry).
+//   B  thread = pending hit, once 256 of them are waiting (or the queue is exhausted): the fresh
+//      std::mt19937 of the hit (raytracer.cpp:110-113) — 396 dependent LCG steps — and its next
+//      8 points on the light's disk, into shared memory.
+//   C  thread = (pending hit, sample): one shadow ray; unoccluded rays are counted per hit.
+// The light points never leave the SM (they were 96 B per hit written to and read back from HBM), and
+// the engine runs only for hits that cast rays.  N > 8 samples: phases B and C repeat in rounds of 8,
+// the engine state waiting in shared memory in between.
+constexpr int kPendCap = 2 * kWfThreads;    // ring of hits waiting for their engine (power of two)
+constexpr int kShadowRound = 8;             // light samples per hit and round
+constexpr int kPtStride = kShadowRound * 3 + 1;  // floats per hit in the point table (odd: no bank conflicts)
+struct ShadowSmem {
+    float4 pendP[kPendCap];                 // hit point xyz, w = index in the queue
+    float4 pendO[kPendCap];                 // shadow-ray origin xyz, w = box mask of the bundle
+    float pts[kWfThreads * kPtStride];      // this round's sample points
+    uint4 engine[kWfThreads];               // FreshStream between rounds (N > kShadowRound only)
+    unsigned int lit[kWfThreads];
+    unsigned int head, tail;                // monotonic: ring entries [head, tail) are pending
+    unsigned int chunk;                     // the chunk claimed for this trip
+};
+static_assert((kPendCap & (kPendCap - 1)) == 0, "ring size must be a power of two");
+
+#ifndef MCSKIN_WF_SOFT_MIN_BLOCKS
+#define MCSKIN_WF_SOFT_MIN_BLOCKS 4
+#endif
+template <bool BATCH>
+__global__ void __launch_bounds__(kWfThreads, MCSKIN_WF_SOFT_MIN_BLOCKS)
+k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
+                const BatchSlice* __restrict__ batch) {
+    __shared__ __align__(8) uint64_t stageBar;
+    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
+    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
+    unsigned int n = wv.qCount[depth];
+    if (n > wv.pathCapacity) n = wv.pathCapacity;
+    const unsigned int nChunks = (n + kWfThreads - 1) / kWfThreads;
+    if (blockIdx.x >= nChunks) return;
+    stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
+    ShadowSmem* sm = reinterpret_cast<ShadowSmem*>(g_sceneSmem + ((fp.blob_bytes + 15u) & ~15u));
+    const int tid = threadIdx.x, lane = tid & 31;
+    const HitQueueView q = wv.q[which];
+    const int N = fr.shadow_samples;
+    const int rounds = (N + kShadowRound - 1) / kShadowRound;
+    const V3 lightCentre = ld3(fr.light_pos);
+    const uint32_t one = fr.spp > 0 ? 1u : 0u;  // a 1 the compiler cannot see through
+    unsigned int* chunkCounter = wv.qCount + (wv.levels + 3) + depth;
+    if (tid == 0) {
+        sm->head = 0u;
+        sm->tail = 0u;
+    }
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sm->chunk = atomicAdd(chunkCounter, 1u);
+        __syncthreads();
+        const unsigned int c = sm->chunk;
+        const bool last = c >= nChunks;  // the queue is exhausted: flush what is pending and leave
+        if (!last) {  // ---- phase A
+            const unsigned int i = c * kWfThreads + tid;
+            bool pend = false;
+            float4 eP = make_float4(0.f, 0.f, 0.f, 0.f), eO = eP;
+            if (i < n) {
+                const Hit h = unpack_hit(q.geo[i], make_float4(0.f, 0.f, 0.f, 0.f));
+                // P + n*eps (isInShadow, shading.cpp:17); computeSoftShadow hands it the raw hit normal
+                // (shading.cpp:54, raytracer.cpp:113)
+                const V3 origin = h.p + hit_normal(sc, h) * kShadowEpsilon;
+                const uint32_t allow = bundle_box_mask(sc, origin, lightCentre, fr.light_radius);
+                if (allow == 0u && sc.n_boxes <= 32) {
+                    wv.lit[i] = static_cast<unsigned int>(N);
+                } else {
+                    pend = true;
+                    eP = make_float4(h.p.x, h.p.y, h.p.z, __uint_as_float(i));
+                    eO = make_float4(origin.x, origin.y, origin.z, __uint_as_float(allow));
+                }
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, pend);
+            if (m) {
+                unsigned int base = 0u;
+                if (lane == 0) base = atomicAdd(&sm->tail, static_cast<unsigned int>(__popc(m)));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pend) {
+                    const unsigned int pos = (base + __popc(m & ((1u << lane) - 1u))) & (kPendCap - 1);
+                    sm->pendP[pos] = eP;
+                    sm->pendO[pos] = eO;
+                }
+            }
+            __syncthreads();
+        }
+        for (;;) {  // ---- drain the ring, 256 hits at a time
+            const unsigned int head = sm->head;
+            const unsigned int avail = sm->tail - head;
+            if (avail == 0u || (!last && avail < static_cast<unsigned int>(kWfThreads))) break;
+            const unsigned int cnt = avail < static_cast<unsigned int>(kWfThreads) ? avail : static_cast<unsigned int>(kWfThreads);
+            const bool mine = static_cast<unsigned int>(tid) < cnt;
+            if (mine) sm->lit[tid] = 0u;
+            for (int round = 0; round < rounds; ++round) {
+                const int ns = min(kShadowRound, N - round * kShadowRound);
+                if (mine) {  // ---- phase B
+                    const float4 eP = sm->pendP[(head + tid) & (kPendCap - 1)];
+                    const V3 P = mk3(eP.x, eP.y, eP.z);
+                    FreshStream rng;
+                    if (round == 0) {
+                        rng.seed_balanced(shadow_seed(P, depth), one);
+                    } else {
+                        const uint4 e = sm->engine[tid];
+                        rng.cur = e.x; rng.nxt = e.y; rng.far = e.z; rng.j = e.w;
+                    }
+                    soft_shadow_positions(fr, P, ns, rng, sm->pts + tid * kPtStride);
+                    if (round + 1 < rounds) sm->engine[tid] = make_uint4(rng.cur, rng.nxt, rng.far, rng.j);
+                }
+                __syncthreads();
+                const unsigned int nRays = cnt * static_cast<unsigned int>(ns);  // ---- phase C
+                for (unsigned int r = tid; r < nRays; r += kWfThreads) {
+                    const unsigned int e = ns == kShadowRound ? r >> 3 : r / static_cast<unsigned int>(ns);
+                    const unsigned int k = r - e * static_cast<unsigned int>(ns);
+                    const float4 eO = sm->pendO[(head + e) & (kPendCap - 1)];
+                    const float* pt = sm->pts + e * kPtStride + k * 3u;
+                    if (!in_shadow_from(sc, mk3(eO.x, eO.y, eO.z), mk3(pt[0], pt[1], pt[2]), __float_as_uint(eO.w)))
+                        atomicAdd(&sm->lit[e], 1u);
+                }
+                __syncthreads();
+            }
+            if (mine) wv.lit[__float_as_uint(sm->pendP[(head + tid) & (kPendCap - 1)].w)] = sm->lit[tid];
+            __syncthreads();
+            if (tid == 0) sm->head = head + cnt;
+            __syncthreads();
+        }
+        if (last) break;
+    }
+}
+
+// hard shadows: one ray from every hit to the light's centre (isInShadow as shade() calls it, with the
+// normalised normal: shading.cpp:69,78)
 template <bool BATCH>
 __global__ void __launch_bounds__(kWfThreads)
-k_wf_seed(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
-          const BatchSlice* __restrict__ batch) {
+k_wf_hardshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
+                const BatchSlice* __restrict__ batch) {
     __shared__ __align__(8) uint64_t stageBar;
     const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
     const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
@@ -150,113 +288,21 @@ k_wf_seed(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const 
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
     const HitQueueView q = wv.q[which];
-    const int N = fr.shadow_samples;
-    const uint32_t one = fr.spp > 0 ? 1u : 0u;  // a 1 the compiler cannot see through
-    for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) {
-        const float4 g = q.geo[i];
-        const Hit h = unpack_hit(g, make_float4(0.f, 0.f, 0.f, 0.f));
-        const V3 P = h.p;
-        // the common origin of the hit's shadow rays, P + n*eps (isInShadow, shading.cpp:17; computeSoftShadow
-        // hands it the raw hit normal: shading.cpp:54, raytracer.cpp:113), and the boxes their bundle can reach
-        const V3 origin = P + hit_normal(sc, h) * kShadowEpsilon;
-        const uint32_t allow = bundle_box_mask(sc, origin, ld3(fr.light_pos), fr.light_radius);
-        if (allow == 0u && sc.n_boxes <= 32) {
-            // No box lies within reach of any segment from this hit to the light's disk: every one of the
-            // N shadow rays is unoccluded wherever its sample falls, so neither the engine nor the sample
-            // points are needed (lit = N; k_wf_shadow skips hits with an empty mask).  Warps are mostly
-            // uniform in this: the samples of a pixel hit the same face of the same box.
-            wv.lit[i] = static_cast<unsigned int>(N);
-            wv.shadowOrg[i] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(0u));
-            continue;
-        }
-        FreshStream rng;
-        rng.seed_balanced(shadow_seed(P, depth), one);
-        soft_shadow_positions(fr, P, N, rng, wv.lightPos + static_cast<size_t>(i) * 3 * N);
-        wv.lit[i] = 0u;
-        wv.shadowOrg[i] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(allow));
-    }
-}
-
-// hard shadows: no light samples to draw, only the counter and the shadow-ray origin of each hit
-template <bool BATCH>
-__global__ void __launch_bounds__(kWfThreads)
-k_wf_prep_hard(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
-               const BatchSlice* __restrict__ batch) {
-    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
-    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
-    unsigned int n = wv.qCount[depth];
-    if (n > wv.pathCapacity) n = wv.pathCapacity;
-    const SceneView sc = scene_view(fp.blob, fp.texels, fr);
-    const HitQueueView q = wv.q[which];
+    const V3 lightCentre = ld3(fr.light_pos);
     for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) {
         const Hit h = unpack_hit(q.geo[i], make_float4(0.f, 0.f, 0.f, 0.f));
-        // shade() hands isInShadow the normalised normal (shading.cpp:69,78)
-        const V3 origin = h.p + normalize3(hit_normal(sc, h)) * kShadowEpsilon;
         // (a box mask for the single ray, as for soft-shadow bundles, costs more than the one ray it can save)
-        wv.shadowOrg[i] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(0xffffffffu));
-        wv.lit[i] = 0u;
-    }
-}
-
-// ---------------------------------------------------------------- one shadow ray per thread
-template <bool BATCH>
-__global__ void WF_SHADOW_BOUNDS
-k_wf_shadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
-            const BatchSlice* __restrict__ batch) {
-    __shared__ __align__(8) uint64_t stageBar;
-    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
-    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
-    unsigned int n = wv.qCount[depth];
-    if (n > wv.pathCapacity) n = wv.pathCapacity;
-    const int R = wv.shadowRays;
-    const unsigned long long nRays = static_cast<unsigned long long>(n) * R;
-    if (static_cast<unsigned long long>(blockIdx.x) * kWfThreads >= nRays) return;
-    stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
-    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
-    (void)which;
-    const bool soft = wv.shadowMode == kShadowSoft;
-    const V3 lightCentre = ld3(fr.light_pos);
-    const bool rPow2 = (R & (R - 1)) == 0;
-    const int lgR = 31 - __clz(R);
-
-    // One ray per trip of a grid-stride loop.  (Fetching the next trip's inputs ahead of the trace was
-    // measured slower: the extra registers cost a resident block.)
-    struct RayIn {
-        float4 org;        // shadow-ray origin, w = box mask
-        float tx, ty, tz;  // point on the light
-        unsigned int i;
-    };
-    auto fetch = [&](unsigned long long t) {
-        RayIn in;
-        in.i = rPow2 ? static_cast<unsigned int>(t >> lgR) : static_cast<unsigned int>(t / R);
-        const int k = static_cast<int>(t - static_cast<unsigned long long>(in.i) * R);
-        in.org = wv.shadowOrg[in.i];  // w: the boxes in reach of the hit's shadow rays (soft and hard mode alike)
-        in.tx = lightCentre.x; in.ty = lightCentre.y; in.tz = lightCentre.z;
-        if (soft) {
-            const float* lp = wv.lightPos + (static_cast<size_t>(in.i) * R + k) * 3;
-            in.tx = lp[0]; in.ty = lp[1]; in.tz = lp[2];
-        }
-        return in;
-    };
-    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kWfThreads;
-    unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + threadIdx.x;
-    if (t >= nRays) return;
-    for (; t < nRays; t += stride) {
-        const RayIn cur = fetch(t);
-        const V3 origin = mk3(cur.org.x, cur.org.y, cur.org.z);
-        if (__float_as_uint(cur.org.w) == 0u && sc.n_boxes <= 32) continue;  // nothing in reach: counted as lit by k_wf_seed
-        if (!in_shadow_from(sc, origin, mk3(cur.tx, cur.ty, cur.tz), __float_as_uint(cur.org.w)))
-            atomicAdd(&wv.lit[cur.i], 1u);
+        wv.lit[i] = in_shadow(sc, h.p, normalize3(hit_normal(sc, h)), lightCentre) ? 0u : 1u;
     }
 }
 
 // ---------------------------------------------------------------- shade + bounce
-// tail == 0: a queue level whose shadow rays ran in k_wf_shadow; bounce hits go to the next queue.
+// tail == 0: a queue level whose shadow rays ran in k_wf_softshadow / k_wf_hardshadow; bounce hits go to the next queue.
 // tail == 1: the last queue (depth == wv.queueLevels).  By then only ~2 % of the paths are left,
 //            too few to be worth three launches per level: each thread takes one queued hit and
 //            follows its chain to the end, evaluating shadow rays in place.  The queue is compact,
 //            so warps start full and only thin out at the deepest, rarest levels.
-// QUEUED: the visibility comes from k_wf_shadow's counters and bounce hits go to the next queue
+// QUEUED: the visibility comes from the shadow kernel's counters and bounce hits go to the next queue
 // (the lean form: no shadow code at all); otherwise shadows are evaluated in place, and with
 // tail != 0 the whole remaining chain is.
 template <bool QUEUED, bool BATCH>
@@ -458,16 +504,14 @@ int stack_levels_of(const DevFrame& fr) {
 }  // namespace
 
 size_t wavefront_bytes_per_path(const DevFrame& fr) {
-    const int mode = shadow_mode_of(fr);
-    const size_t lightBytes = mode == kShadowSoft ? sizeof(float) * 3 * fr.shadow_samples : 0;
     return 2 * 3 * sizeof(float4)            // two hit queues
-           + lightBytes + sizeof(unsigned) + sizeof(float4)   // light sample points, lit counters, shadow origins + box masks
+           + sizeof(unsigned)                // lit counters
            + sizeof(float4) + sizeof(int)    // tail, top
            + sizeof(float4) * stack_levels_of(fr);
 }
 
 size_t wavefront_fixed_bytes(const DevFrame& fr) {
-    return 256 * 16 + sizeof(unsigned int) * (stack_levels_of(fr) + 3);
+    return 256 * 16 + 2 * sizeof(unsigned int) * (stack_levels_of(fr) + 3);
 }
 
 bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int pathCapacity, int gridBlocks,
@@ -481,6 +525,7 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
     w.gridBlocks = gridBlocks;
     w.queueLevels = 3;
     w.deepGridDiv = 1;
+    w.softGrid = gridBlocks;
     unsigned char* p = static_cast<unsigned char*>(base);
     size_t off = 0;
     auto take = [&](size_t n) {
@@ -494,20 +539,19 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
         w.q[k].org = static_cast<float4*>(take(cap * sizeof(float4)));
         w.q[k].dir = static_cast<float4*>(take(cap * sizeof(float4)));
     }
-    w.lightPos = static_cast<float*>(take(w.shadowMode == kShadowSoft ? cap * sizeof(float) * 3 * fr.shadow_samples : 16));
     w.lit = static_cast<unsigned int*>(take(cap * sizeof(unsigned int)));
-    w.shadowOrg = static_cast<float4*>(take(cap * sizeof(float4)));
     w.tail = static_cast<float4*>(take(cap * sizeof(float4)));
     w.top = static_cast<int*>(take(cap * sizeof(int)));
     w.stack = static_cast<float4*>(take(std::max<size_t>(16, cap * sizeof(float4) * w.levels)));
-    w.qCount = static_cast<unsigned int*>(take(sizeof(unsigned int) * (w.levels + 3)));
+    // queue sizes per depth, then the chunk counters of the shadow kernel per depth (zeroed together)
+    w.qCount = static_cast<unsigned int*>(take(2 * sizeof(unsigned int) * (w.levels + 3)));
     if (off > bytes) return false;
     *out = w;
     return true;
 }
 
 void launch_batch_reset(const BatchSlice* batch, int nScenes, int levels, cudaStream_t stream) {
-    if (nScenes > 0) k_batch_reset<<<(nScenes + 127) / 128, 128, 0, stream>>>(batch, nScenes, levels + 3);
+    if (nScenes > 0) k_batch_reset<<<(nScenes + 127) / 128, 128, 0, stream>>>(batch, nScenes, 2 * (levels + 3));
 }
 
 void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
@@ -516,8 +560,14 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
     int n = 0;
     const int grid = wv.gridBlocks;
     const unsigned int ny = batch ? static_cast<unsigned int>(nScenes) : 1u;
+    if (wv.shadowMode == kShadowSoft) {  // ring + point table + scene blob exceed the default 48 KB
+        static SmemOptIn optIn;
+        static const void* const fns[] = {reinterpret_cast<const void*>(k_wf_softshadow<false>),
+                                          reinterpret_cast<const void*>(k_wf_softshadow<true>)};
+        optIn.limit(fns, 2);
+    }
     // a batch's queue counters are zeroed by the caller (one memset over all scenes)
-    if (!batch) cudaMemsetAsync(wv.qCount, 0, sizeof(unsigned int) * (wv.levels + 3), stream);
+    if (!batch) cudaMemsetAsync(wv.qCount, 0, 2 * sizeof(unsigned int) * (wv.levels + 3), stream);
     if (batch) k_wf_hit0<true><<<dim3(grid, ny), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv, batch); else k_wf_hit0<false><<<dim3(grid, ny), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv, batch);
     ++n;
     if (fr.max_bounces >= 0) {
@@ -531,17 +581,15 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
             // spread over every SM finishes sooner than one packed into a few resident blocks.
             const dim3 g(depth == 0 ? grid : std::max(1, grid / std::max(1, wv.deepGridDiv)), ny);
             if (wv.shadowMode == kShadowSoft) {
-                { if (batch) k_wf_seed<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch); else k_wf_seed<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch); }
+                // persistent blocks that claim chunks of 256 hits: no more of them than can be resident
+                const dim3 gs(std::max(1, std::min<int>(g.x, wv.softGrid)), ny);
+                const size_t smem = ((fp.blob_bytes + 15u) & ~15u) + sizeof(ShadowSmem);
+                if (batch) k_wf_softshadow<true><<<gs, kWfThreads, smem, stream>>>(fr, fp, wv, which, depth, batch);
+                else k_wf_softshadow<false><<<gs, kWfThreads, smem, stream>>>(fr, fp, wv, which, depth, batch);
                 ++n;
             } else if (wv.shadowMode == kShadowHard) {
-                { if (batch) k_wf_prep_hard<true><<<g, kWfThreads, 0, stream>>>(fr, fp, wv, which, depth, batch); else k_wf_prep_hard<false><<<g, kWfThreads, 0, stream>>>(fr, fp, wv, which, depth, batch); }
-                ++n;
-            }
-            if (wv.shadowMode != kShadowInThread) {
-                if (batch)
-                    k_wf_shadow<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
-                else
-                    k_wf_shadow<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
+                if (batch) k_wf_hardshadow<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
+                else k_wf_hardshadow<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
                 ++n;
             }
             if (wv.shadowMode != kShadowInThread) {

@@ -11,9 +11,11 @@
 //                -> miss: the sample's colour is the gradient background
 //                -> hit : appended to the depth-0 hit queue
 //   per depth d:
-//     k_wf_seed    thread = hit: fresh std::mt19937 from the hit point (397-step seeding),
-//                  the N points on the light's disk computeSoftShadow would sample
-//     k_wf_shadow  thread = (hit, shadow sample): ONE shadow ray, all lanes identical work
+//     k_wf_softshadow  block = chunks of 256 hits: the boxes each hit's shadow-ray bundle can reach; hits
+//                  that reach none are lit; the others are compacted in shared memory, get their fresh
+//                  std::mt19937 (397-step seeding) and the N points on the light's disk
+//                  computeSoftShadow would sample, then one thread per (hit, sample) casts the ray
+//                  (k_wf_hardshadow with soft shadows off: one ray per hit to the light's centre)
 //     k_wf_shade   thread = hit: Blinn-Phong with the counted visibility, AO, mirror ray,
 //                  closest hit of the bounce -> next queue, or the chain's terminal colour
 //   k_wf_resolve thread = sample: folds the bounce chain back to front with the reference's
@@ -35,21 +37,20 @@ struct HitQueueView {
 
 struct WaveView {
     HitQueueView q[2];       // ping-pong over depth
-    float* lightPos;         // per hit of the current queue: 3 floats per shadow sample
     unsigned int* lit;       // per hit of the current queue: unoccluded shadow rays
-    float4* shadowOrg;       // per hit of the current queue: origin of its shadow rays; w = boxes their bundle can reach
     float4* tail;            // per path: colour returned by the deepest traceRay call
     float4* stack;           // [level][path]: shaded colour of every level that spawned a reflection (w = its alpha)
     int* top;                // per path: number of stack levels in use
-    unsigned int* qCount;    // [levels + 2] queue sizes per depth (zeroed before the frame)
+    unsigned int* qCount;    // [levels + 3] queue sizes per depth, then [levels + 3] chunk counters of the shadow kernel (zeroed before the frame)
     unsigned int pathCapacity;
     unsigned int slotCapacity;  // pixels handled by the wavefront = pathCapacity / spp
     int levels;              // stack levels allocated
     int queueLevels;         // depths 0..queueLevels-1 go through the queues, deeper ones run in-thread
     int shadowMode;          // see enum below
-    int shadowRays;          // rays per hit cast by k_wf_shadow
+    int shadowRays;          // rays per hit cast by the shadow kernel
     int gridBlocks;
     int deepGridDiv;         // grid of the launches of depth >= 1 = gridBlocks / deepGridDiv
+    int softGrid;            // blocks of the soft-shadow kernel (persistent: what fits the device at once)
 };
 
 enum : int {

@@ -125,6 +125,34 @@ int main(int argc, char** argv) {
         Image byTile(c.width, c.height);
         for (const Tile& t : TileRenderer::generateTiles(c.width, c.height, c.tileSize)) TileRenderer::renderTile(t, skin, c, byTile);
         for (size_t i = 0; i < full.pixels.size(); ++i) CHECK(full.pixels[i] == byTile.pixels[i]);
+        // MCSKIN_DEVICES spreads the same render(scene, settings) call over the GPUs of the process
+        // (tile_renderer.h:26-28 stays the entry point); same pixels, callback count unchanged
+        {
+            const int nDev = mcskin_cuda_device_count();
+            for (const char* spread : {"all", "2", "3"}) {
+                if (std::atoi(spread) > nDev) continue;
+                setenv("MCSKIN_DEVICES", spread, 1);
+                int calls = 0;
+                Image multi = TileRenderer::render(skin, c, [&](int, int) { ++calls; });
+                CHECK(TileRenderer::lastErrors().empty());
+                CHECK(calls == static_cast<int>(TileRenderer::generateTiles(c.width, c.height, c.tileSize).size()));
+                for (size_t i = 0; i < full.pixels.size(); ++i) CHECK(full.pixels[i] == multi.pixels[i]);
+            }
+            unsetenv("MCSKIN_DEVICES");
+            // a frame that fails (no such device) still reports every tile, records the error and
+            // returns a default image (tile_renderer.cpp:150-171: progress is reported for tiles that threw, too)
+            setenv("MCSKIN_DEVICE", "99", 1);
+            int calls = 0, lastDone = 0;
+            Image failed = TileRenderer::render(skin, c, [&](int done, int) { ++calls; lastDone = done; });
+            unsetenv("MCSKIN_DEVICE");
+            const int total = static_cast<int>(TileRenderer::generateTiles(c.width, c.height, c.tileSize).size());
+            CHECK(TileRenderer::lastErrors().size() == 1 && TileRenderer::lastErrors()[0].tileIndex == -1);
+            CHECK(calls == total && lastDone == total);
+            CHECK(failed.width == c.width && failed.pixels.size() == full.pixels.size());
+            Image again = TileRenderer::render(skin, c);   // and the next frame is fine again
+            CHECK(TileRenderer::lastErrors().empty());
+            for (size_t i = 0; i < full.pixels.size(); ++i) CHECK(full.pixels[i] == again.pixels[i]);
+        }
         if (argc > 1) {
             FILE* fp = std::fopen(argv[1], "wb");
             CHECK(fp != nullptr);
