@@ -30,10 +30,20 @@ public:
         int optin = 0;
         if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) optin = 0;
         bool ok = optin > 48 * 1024;
-        for (int i = 0; ok && i < nFns; ++i)
-            ok = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess;
+        // static + dynamic shared memory of a kernel may not exceed the opt-in maximum: the attribute is
+        // the dynamic part, so each kernel's static bytes come off (asking for the full maximum is refused
+        // with cudaErrorInvalidValue as soon as a kernel has one static __shared__ variable)
+        int room = optin;
+        for (int i = 0; ok && i < nFns; ++i) {
+            cudaFuncAttributes fa{};
+            ok = cudaFuncGetAttributes(&fa, fns[i]) == cudaSuccess;
+            if (!ok) break;
+            const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
+            ok = dyn > 0 && cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) == cudaSuccess;
+            if (dyn < room) room = dyn;
+        }
         if (!ok) cudaGetLastError();
-        limit_[dev] = ok ? static_cast<size_t>(optin) : 0;
+        limit_[dev] = ok ? static_cast<size_t>(room) : 0;
         known_[dev] = true;
         return limit_[dev];
     }
