@@ -200,7 +200,8 @@ int32_t mcskin_cuda_peer_wait(int32_t device, const void* d_flags, int32_t n, ui
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats);
 /* Tuning / test knobs (every combination renders the same bits; INTEGRATION.md §6 has the table):
  * "frame_lanes" (streams a frame's tile rows are dealt to), "use_graphs" (replay a repeated frame as a CUDA
- * graph), "cache_tile_seeds", "wave_queue_levels", "wave_deep_grid_div", "wave_budget_bytes",
+ * graph), "cache_tile_seeds", "wave_queue_pct" (hit-queue entries as a percentage of the paths; 0 = cannot overflow),
+ * "soft_blocks_per_sm", "wave_budget_bytes",
  * "record_budget_bytes", "shade_blocks_per_sm", "primary_blocks_per_sm", "heavy_tiles_per_sm",
  * "shade_mode" (0 wavefront, 1/2 megakernel forms), "force_all_active" (0/1: skip the hit/miss
  * classification and shade every pixel), "overlap_copy_out", "batch_mode", "batch_group", "batch_lanes".

@@ -102,9 +102,8 @@ struct McContext {
     int heavyTilesPerSm = 16;                // the figure's tiles are split over more blocks while a frame (all lanes) has fewer tiles per SM
     int primaryBlocksPerSm = 2;              // split tiles over blocks only while a launch has fewer than this many per SM
                                              // (every block of a split tile regenerates the tile's whole jitter stream)
-    int waveQueueLevels = 4;                 // bounce depths handled by queues; deeper ones in-thread
-    bool waveQueueLevelsAuto = true;         // small shares of a frame (few tiles per SM) use 1 level: see render_bands_lane
-    int waveDeepGridDiv = 1;                 // launches of depth >= 1 use shade grid / this
+    int waveQueuePct = 0;                    // hit-queue entries as a percentage of the paths (0: paths x (bounces + 1),
+                                             // which cannot overflow; smaller queues redo overflowing paths in-thread)
     int frameLanes = 3;                      // a frame's tile rows are rendered on this many streams at once
     bool isChild = false;                    // a lane of another context (never splits frames itself)
     // seeded tile engines kept from the previous frame: they depend on the image width, the tile
@@ -223,7 +222,13 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
         return fail(MC_ERR_LIMIT, "tile_size too large");
 
     const bool classify = !ctx->forceAllActive && f.spp <= kBlockThreads;
-    const size_t slotsPerTileRow = static_cast<size_t>(f.tiles_x) * f.tile_size * f.tile_size;
+    // work-list slots a tile row can need: every pixel, or — the classifying primary pass only lists pixels
+    // inside the figure's screen rectangle — the rectangle's columns
+    size_t slotsPerTileRow = static_cast<size_t>(f.tiles_x) * f.tile_size * f.tile_size;
+    if (classify && f.rect_valid) {
+        const long long rectW = static_cast<long long>(std::min(f.width - 1, f.rect_x1)) - std::max(0, f.rect_x0) + 1;
+        slotsPerTileRow = std::min(slotsPerTileRow, static_cast<size_t>(std::max<long long>(rectW, 1)) * f.tile_size);
+    }
     const size_t recordBytesPerSlot = static_cast<size_t>(f.spp) * f.draws_per_sample * sizeof(float);
     // tile rows per chunk so that the worst-case work list fits the budget
     size_t rowsPerChunk = nRows;
@@ -249,26 +254,29 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
         CU_TRY(cudaEventCreate(&e));
         ctx->passEvents.push_back(e);
     }
-    // wavefront queues: sized for a quarter of the worst case (every pixel of a chunk active),
-    // within the budget; anything beyond is shaded by the megakernel
+    // wavefront storage: per path (terminal colour, bounce stack) and per hit-queue entry.  A queue of
+    // paths x (bounces + 1) entries cannot overflow; if the budget does not allow it the queue shrinks (to no
+    // less than 1.25 entries per path; paths whose hits do not fit are redone in-thread), then the number of
+    // paths does (pixels beyond them are shaded by the megakernel).
     WaveView wave{};
     if (ctx->shadeMode == 0) {
-        const size_t perPath = wavefront_bytes_per_path(f);
+        const size_t perPath = wavefront_bytes_per_path(f), perEntry = wavefront_bytes_per_entry();
+        const size_t hitsMax = static_cast<size_t>(wavefront_max_hits_per_path(f));
+        const size_t budget = static_cast<size_t>(ctx->waveBudgetBytes);
         const size_t worstPaths = slotCap * static_cast<size_t>(f.spp);
-        size_t paths = std::min(worstPaths, static_cast<size_t>(ctx->waveBudgetBytes) / perPath);
+        size_t paths = std::min(worstPaths, budget / (perPath + perEntry * std::min<size_t>(hitsMax, 2)));
         paths = std::min<size_t>(paths, 0x7fffff00u);
         paths = std::max<size_t>(paths, static_cast<size_t>(f.spp));
-        const size_t bytes = paths * perPath + wavefront_fixed_bytes(f);
+        size_t entries = paths * hitsMax;
+        if (ctx->waveQueuePct > 0) entries = std::min(entries, std::max<size_t>(32, paths * static_cast<size_t>(ctx->waveQueuePct) / 100));
+        const size_t room = budget > paths * perPath ? (budget - paths * perPath) / perEntry : 0;
+        entries = std::min(entries, std::max(room, paths + paths / 4));
+        entries = std::min<size_t>(entries, 0xffffff00u);
+        const size_t bytes = paths * perPath + entries * perEntry + wavefront_fixed_bytes(f) + 16 * 256;
         CU_TRY(ctx->wave.reserve(bytes));
-        if (!wavefront_carve(f, ctx->wave.p, ctx->wave.cap, static_cast<unsigned int>(paths),
+        if (!wavefront_carve(f, ctx->wave.p, ctx->wave.cap, static_cast<unsigned int>(paths), static_cast<unsigned int>(entries),
                              ctx->smCount * ctx->shadeBlocksPerSm, &wave))
             return fail(MC_ERR_CUDA, "wavefront buffer carve failed");
-        // A small share of a frame (one GPU's rows of an 8-way split, a 512x512 frame) has too few hits per
-        // bounce level to amortise three launches a level: only the primary hits go through the queues,
-        // the bounces are finished in-thread (B200 sweep: -7 % on an eighth of the 1080p frame).
-        const bool smallShare = static_cast<long long>(nRows) * f.tiles_x * std::max(1, lanesInFlight) * 2 < 5ll * ctx->smCount;
-        wave.queueLevels = (ctx->waveQueueLevelsAuto && smallShare) ? 1 : ctx->waveQueueLevels;
-        wave.deepGridDiv = ctx->waveDeepGridDiv;
         wave.softGrid = ctx->smCount * ctx->softBlocksPerSm;
     }
     if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->ev0, stream));
@@ -353,9 +361,7 @@ int ensure_lanes(McContext* ctx, int n) {
 void inherit_options(McContext* lane, const McContext* ctx) {
     lane->shadeMode = ctx->shadeMode;
     lane->forceAllActive = ctx->forceAllActive;
-    lane->waveQueueLevels = ctx->waveQueueLevels;
-    lane->waveQueueLevelsAuto = ctx->waveQueueLevelsAuto;
-    lane->waveDeepGridDiv = ctx->waveDeepGridDiv;
+    lane->waveQueuePct = ctx->waveQueuePct;
     lane->waveBudgetBytes = ctx->waveBudgetBytes;
     lane->recordBudgetBytes = ctx->recordBudgetBytes;
     lane->shadeBlocksPerSm = ctx->shadeBlocksPerSm;
@@ -391,7 +397,7 @@ int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* out
 
 long long option_bits(const McContext* c, int i) {
     const long long v[12] = {c->forceAllActive, c->recordBudgetBytes, c->shadeBlocksPerSm, c->primaryBlocksPerSm,
-                             c->waveQueueLevelsAuto ? -c->waveQueueLevels : c->waveQueueLevels, c->shadeMode, c->waveBudgetBytes, c->waveDeepGridDiv,
+                             c->waveQueuePct, c->shadeMode, c->waveBudgetBytes, 0,
                              c->softBlocksPerSm, c->cacheTileSeeds, c->heavyTilesPerSm, c->frameLanes};
     return v[i];
 }
@@ -674,7 +680,10 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
     const size_t paths = slotCap * f0.spp;
     if (paths > 0x7fffff00u) return MC_OK;
     const size_t recordBytes = std::max<size_t>(16, slotCap * f0.spp * f0.draws_per_sample * sizeof(float));
-    const size_t waveBytes = (paths * wavefront_bytes_per_path(f0) + wavefront_fixed_bytes(f0) + 4096 + 255) & ~size_t(255);
+    const size_t entries = paths * static_cast<size_t>(wavefront_max_hits_per_path(f0));  // cannot overflow
+    if (entries > 0xffffff00u) return MC_OK;
+    const size_t waveBytes = (paths * wavefront_bytes_per_path(f0) + entries * wavefront_bytes_per_entry() +
+                              wavefront_fixed_bytes(f0) + 16 * 256 + 255) & ~size_t(255);
     const size_t perScene = waveBytes + recordBytes + slotCap * sizeof(uint2);
     int G = std::min<int>(ctx->batchGroup, nScenes);
     G = static_cast<int>(std::max<size_t>(1, std::min<size_t>(G, static_cast<size_t>(ctx->waveBudgetBytes) / std::max<size_t>(1, perScene))));
@@ -767,10 +776,8 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
                 // few blocks per scene: a launch has gridDim.y scenes to fill the machine with
                 const int gridX = std::max(2, (ctx->smCount * ctx->shadeBlocksPerSm + nC - 1) / nC);
                 if (!wavefront_carve(pf.frame, static_cast<unsigned char*>(ctx->batchWave.p) + static_cast<size_t>(i) * waveBytes,
-                                     waveBytes, static_cast<unsigned int>(paths), gridX, &sl.wave))
-                    return MC_OK;  // (cannot happen: sizes come from the same frame description) frame-by-frame path instead
-                sl.wave.queueLevels = ctx->waveQueueLevels;
-                sl.wave.deepGridDiv = 1;
+                                     waveBytes, static_cast<unsigned int>(paths), static_cast<unsigned int>(entries), gridX, &sl.wave))
+                    return MC_OK;  // (cannot happen: the sizes depend on the config only) frame-by-frame path instead
                 stageSlices[sliceAt++] = sl;
             }
         }
@@ -786,7 +793,7 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
             const BatchSlice* gs = devSlices + groupFirstSlice[g];
             const BatchSlice& first = stageSlices[groupFirstSlice[g]];
             const DevFrame& f = ctx->batchPreps[groups[g][0]].frame;
-            launch_batch_reset(gs, nS, first.wave.levels, stream);
+            launch_batch_reset(gs, nS, stream);
             if (!launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), !seeded, gs, nS, first.fp.blob_bytes,
                                       ctx->smCount * ctx->primaryBlocksPerSm, stream))
                 return MC_OK;  // no batched primary kernel for this frame description: frame-by-frame path instead
@@ -840,11 +847,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     if (const char* v = std::getenv("MCSKIN_FORCE_ALL_ACTIVE")) ctx->forceAllActive = std::atoi(v);
     if (const char* v = std::getenv("MCSKIN_HEAVY_TILES")) ctx->heavyTilesPerSm = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_PRIMARY_BLOCKS")) ctx->primaryBlocksPerSm = std::max(0, std::atoi(v));
-    if (const char* v = std::getenv("MCSKIN_WAVE_LEVELS")) {
-        ctx->waveQueueLevels = std::max(1, std::atoi(v));
-        ctx->waveQueueLevelsAuto = false;
-    }
-    if (const char* v = std::getenv("MCSKIN_DEEP_GRID_DIV")) ctx->waveDeepGridDiv = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("MCSKIN_WAVE_QUEUE_PCT")) ctx->waveQueuePct = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("MCSKIN_BATCH_GROUP")) ctx->batchGroup = std::min(4096, std::max(1, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_BATCH_MODE")) ctx->batchMode = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_GRAPHS")) ctx->useGraphs = std::atoi(v) != 0;
@@ -900,11 +903,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "batch_group") ctx->batchGroup = static_cast<int>(std::min<int64_t>(4096, std::max<int64_t>(1, value)));
     else if (k == "batch_mode") ctx->batchMode = value != 0;
     else if (k == "shade_mode") ctx->shadeMode = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
-    else if (k == "wave_queue_levels") {
-        ctx->waveQueueLevels = static_cast<int>(std::max<int64_t>(1, value));
-        ctx->waveQueueLevelsAuto = false;
-    }
-    else if (k == "wave_deep_grid_div") ctx->waveDeepGridDiv = static_cast<int>(std::max<int64_t>(1, value));
+    else if (k == "wave_queue_pct") ctx->waveQueuePct = static_cast<int>(std::min<int64_t>(100000, std::max<int64_t>(0, value)));
     else if (k == "frame_lanes") ctx->frameLanes = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(1, value)));
     else if (k == "cache_tile_seeds") ctx->cacheTileSeeds = value != 0;
     else if (k == "use_graphs") ctx->useGraphs = value != 0;

@@ -30,47 +30,63 @@ constexpr int kWfThreads = 256;
 #endif
 #define WF_SHADE_BOUNDS __launch_bounds__(kWfThreads, QUEUED ? MCSKIN_WF_SHADE_MIN_BLOCKS : 2)
 
-__device__ __forceinline__ unsigned int pack_hit(const Hit& h) {
-    return static_cast<unsigned int>(h.box & 0xffff) | (static_cast<unsigned int>(h.face) << 16) |
-           (h.flip ? (1u << 24) : 0u);
+// geo.w of a queue entry: box (16 bits) | face (3) | flip (1) | bounce depth (7; kMaxStackDepth = 64)
+__device__ __forceinline__ unsigned int pack_hit(const Hit& h, int depth) {
+    return static_cast<unsigned int>(h.box & 0xffff) | (static_cast<unsigned int>(h.face & 7) << 16) |
+           (h.flip ? (1u << 19) : 0u) | (static_cast<unsigned int>(depth) << 20);
 }
+__device__ __forceinline__ int unpack_depth(float4 geo) { return static_cast<int>((__float_as_uint(geo.w) >> 20) & 0x7fu); }
 __device__ __forceinline__ Hit unpack_hit(float4 geo, float4 org) {
     Hit h;
     const unsigned int k = __float_as_uint(geo.w);
     h.p = mk3(geo.x, geo.y, geo.z);
     h.box = static_cast<int>(k & 0xffffu);
-    h.face = static_cast<int>((k >> 16) & 0xffu);
-    h.flip = (k >> 24) & 1u;
+    h.face = static_cast<int>((k >> 16) & 7u);
+    h.flip = (k >> 19) & 1u;
     h.texel = __float_as_int(org.w);
     h.t = 0.0f;
     return h;
 }
+static_assert(kMaxStackDepth < 128, "the bounce depth of a queue entry has 7 bits");
 
-// Appends the hits of a warp to a queue with one atomic; all 32 lanes must call.
-__device__ __forceinline__ void enqueue_hit(const HitQueueView& q, unsigned int* counter, unsigned int capacity,
-                                            bool isHit, const Hit& h, const Ray& ray, unsigned int path) {
+// Appends the hits of a warp to the queue with one atomic; all 32 lanes must call.  Returns false for a
+// lane whose hit found the queue full.
+__device__ __forceinline__ bool enqueue_hit(const HitQueueView& q, unsigned int* counter, unsigned int capacity,
+                                            bool isHit, const Hit& h, const Ray& ray, unsigned int path, int depth) {
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int m = __ballot_sync(0xffffffffu, isHit);
-    if (m == 0u) return;
+    if (m == 0u) return true;
     unsigned int base = 0u;
     if (lane == 0u) base = atomicAdd(counter, static_cast<unsigned int>(__popc(m)));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (isHit) {
         const unsigned int i = base + __popc(m & ((1u << lane) - 1u));
-        if (i < capacity) {
-            q.geo[i] = make_float4(h.p.x, h.p.y, h.p.z, __uint_as_float(pack_hit(h)));
-            q.org[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, __int_as_float(h.texel));
-            q.dir[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(path));
-        }
+        if (i >= capacity) return false;
+        q.geo[i] = make_float4(h.p.x, h.p.y, h.p.z, __uint_as_float(pack_hit(h, depth)));
+        q.org[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, __int_as_float(h.texel));
+        q.dir[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(path));
     }
+    return true;
 }
 
 
-// ---------------------------------------------------------------- primary hits
+// ---------------------------------------------------------------- the paths' geometry
+// Which surfaces a path meets does not depend on how they are shaded: the mirror ray of a hit is a
+// function of the hit point, the normal and the incoming direction only (raytracer.cpp:133-140).  So one
+// thread walks its sample's whole chain — primary ray, closest hit, mirror ray, closest hit, ... — and
+// appends EVERY hit, tagged with its bounce depth, to the one hit queue.  The shadow and shading kernels
+// then run once over all hits of all depths instead of once per depth: the frame has no chain of
+// ever-shorter launches for the deeper bounces (they were a fifth of the frame time for a twentieth of
+// its work).  How a chain ends is recorded here as well: a ray that leaves the scene fixes the path's
+// terminal colour (gradient for camera rays, flat colour for mirror rays); a chain that reaches the
+// bounce limit ends in a hit whose shaded colour the shading kernel stores as the terminal colour.
+// The 32 samples of a warp belong to 32 / spp neighbouring pixels, so the lanes that bounce do so together.
+constexpr int kPathOverflow = -2;  // top[path]: the queue was full; the path is redone in-thread (k_wf_overflow)
+
 template <bool BATCH>
 __global__ void WF_HIT0_BOUNDS
-k_wf_hit0(const DevFrame fr, const FramePointers fp_, const ActiveList list_, const WaveView wv_,
-          const BatchSlice* __restrict__ batch) {
+k_wf_trace(const DevFrame fr, const FramePointers fp_, const ActiveList list_, const WaveView wv_,
+           const BatchSlice* __restrict__ batch) {
     __shared__ __align__(8) uint64_t stageBar;
     const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
     const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
@@ -84,11 +100,12 @@ k_wf_hit0(const DevFrame fr, const FramePointers fp_, const ActiveList list_, co
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
     const int spp = fr.spp, dps = fr.draws_per_sample;
+    const int lastBounce = min(fr.max_bounces, wv.levels);  // hits at this depth spawn no mirror ray
 
     for (unsigned long long p0 = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + (threadIdx.x & ~31u);
          p0 < nPaths; p0 += stride) {
         const unsigned long long p = p0 + (threadIdx.x & 31u);
-        bool isHit = false;
+        bool alive = false;
         Hit hit;
         hit.box = -1; hit.face = 0; hit.texel = 0; hit.flip = false; hit.t = 0.0f; hit.p = mk3(0.f, 0.f, 0.f);
         Ray ray;
@@ -126,18 +143,85 @@ k_wf_hit0(const DevFrame fr, const FramePointers fp_, const ActiveList list_, co
                     wv.tail[p] = config_background(fr, u, v);
                     wv.top[p] = 0;
                 } else {
-                    isHit = true;
+                    alive = true;
                 }
             } else {
                 wv.top[p] = -1;  // unused slot
             }
         }
-        enqueue_hit(wv.q[0], &wv.qCount[0], wv.pathCapacity, isHit, hit, ray, static_cast<unsigned int>(p));
+        // every live lane of the warp is at the same depth: they advance together
+        for (int depth = 0; __any_sync(0xffffffffu, alive); ++depth) {
+            const bool queued = enqueue_hit(wv.q, &wv.qCount[0], wv.qCapacity, alive, hit, ray, static_cast<unsigned int>(p), depth);
+            if (!alive) continue;
+            if (!queued) {
+                wv.top[p] = kPathOverflow;
+                alive = false;
+            } else if (depth < lastBounce) {  // raytracer.cpp:133-140
+                const V3 N = normalize3(hit_normal(sc, hit));
+                const V3 D = normalize3(ray.d);
+                V3 Rd = D - N * (2.0f * dot3(D, N));
+                Rd = normalize3(Rd);
+                ray.o = hit.p + N * kReflectEpsilon;
+                ray.d = Rd;
+                hit = closest_hit(sc, ray);
+                if (hit.box < 0) {
+                    wv.tail[p] = flat_background(fr);  // bounced rays see the flat colour (raytracer.cpp:101)
+                    wv.top[p] = depth + 1;
+                    alive = false;
+                }
+            } else {
+                alive = false;  // the chain ends in this hit: k_wf_shade stores its colour as the terminal one
+            }
+        }
     }
 }
 
-// ---------------------------------------------------------------- soft shadows of one queue level
-// computeSoftShadow (shading.cpp:28-60) for every hit of a queue, in ONE kernel.  A block works through
+// Paths whose hits did not fit the queue (only possible when the queue is smaller than
+// paths x (bounces + 1), i.e. when the budget cut it): the whole path again, in one thread.
+template <bool BATCH>
+__global__ void __launch_bounds__(kWfThreads)
+k_wf_overflow(const DevFrame fr, const FramePointers fp_, const ActiveList list_, const WaveView wv_,
+              const BatchSlice* __restrict__ batch) {
+    __shared__ __align__(8) uint64_t stageBar;
+    const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
+    const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
+    const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
+    if (wv.qCount[0] <= wv.qCapacity) return;  // nothing overflowed
+    unsigned int count = *list.count;
+    if (count > list.capacity) count = list.capacity;
+    if (count > wv.slotCapacity) count = wv.slotCapacity;
+    const unsigned long long nPaths = static_cast<unsigned long long>(count) * fr.spp;
+    stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
+    const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
+    const int spp = fr.spp, dps = fr.draws_per_sample;
+    for (unsigned long long p = static_cast<unsigned long long>(blockIdx.x) * kWfThreads + threadIdx.x; p < nPaths;
+         p += static_cast<unsigned long long>(gridDim.x) * kWfThreads) {
+        if (wv.top[p] != kPathOverflow) continue;
+        const unsigned int slot = static_cast<unsigned int>(p / spp);
+        const int s = static_cast<int>(p - static_cast<unsigned long long>(slot) * spp);
+        const uint2 sp = list.slot_pixel[slot];
+        const int px = static_cast<int>(sp.y & 0xffffu), py = static_cast<int>(sp.y >> 16);
+        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+        const float* rec = list.records + (static_cast<size_t>(slot) * spp + s) * dps;
+        if (dps == 2) {
+            const float2 r = *reinterpret_cast<const float2*>(rec);
+            d0 = r.x; d1 = r.y;
+        } else if (dps == 4) {
+            const float4 r = *reinterpret_cast<const float4*>(rec);
+            d0 = r.x; d1 = r.y; d2 = r.z; d3 = r.w;
+        }
+        const SampleDraws sd = assign_draws(fr, d0, d1, d2, d3);
+        TraceOptions opt;
+        opt.start_depth = 0;
+        opt.primary_uv = true;
+        sample_uv(fr, px, py, sd, &opt.u, &opt.v);
+        wv.tail[p] = trace_path(sc, fr, primary_ray(fr, opt.u, opt.v, sd), opt);
+        wv.top[p] = 0;
+    }
+}
+
+// ---------------------------------------------------------------- soft shadows of every hit
+// computeSoftShadow (shading.cpp:28-60) for every hit of the queue (all depths), in ONE kernel.  A block works through
 // chunks of 256 hits, claimed from a device counter, in three block-synchronous phases:
 //   A  thread = hit: the common origin of the hit's shadow rays and the boxes their bundle can reach.
 //      Nothing in reach -> all N rays are lit by construction, the hit is done.  The others are
@@ -155,8 +239,9 @@ constexpr int kPendCap = 2 * kWfThreads;    // ring of hits waiting for their en
 constexpr int kShadowRound = 8;             // light samples per hit and round
 constexpr int kPtStride = kShadowRound * 3 + 1;  // floats per hit in the point table (odd: no bank conflicts)
 struct ShadowSmem {
-    float4 pendP[kPendCap];                 // hit point xyz, w = index in the queue
+    float4 pendP[kPendCap];                 // hit point xyz, w = seed of the hit's engine (raytracer.cpp:110-112)
     float4 pendO[kPendCap];                 // shadow-ray origin xyz, w = box mask of the bundle
+    unsigned int pendI[kPendCap];           // index in the queue
     float pts[kWfThreads * kPtStride];      // this round's sample points
     uint4 engine[kWfThreads];               // FreshStream between rounds (N > kShadowRound only)
     unsigned int lit[kWfThreads];
@@ -170,25 +255,24 @@ static_assert((kPendCap & (kPendCap - 1)) == 0, "ring size must be a power of tw
 #endif
 template <bool BATCH>
 __global__ void __launch_bounds__(kWfThreads, MCSKIN_WF_SOFT_MIN_BLOCKS)
-k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
-                const BatchSlice* __restrict__ batch) {
+k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const BatchSlice* __restrict__ batch) {
     __shared__ __align__(8) uint64_t stageBar;
     const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
     const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
-    unsigned int n = wv.qCount[depth];
-    if (n > wv.pathCapacity) n = wv.pathCapacity;
+    unsigned int n = wv.qCount[0];
+    if (n > wv.qCapacity) n = wv.qCapacity;
     const unsigned int nChunks = (n + kWfThreads - 1) / kWfThreads;
     if (blockIdx.x >= nChunks) return;
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
     ShadowSmem* sm = reinterpret_cast<ShadowSmem*>(g_sceneSmem + ((fp.blob_bytes + 15u) & ~15u));
     const int tid = threadIdx.x, lane = tid & 31;
-    const HitQueueView q = wv.q[which];
+    const HitQueueView q = wv.q;
     const int N = fr.shadow_samples;
     const int rounds = (N + kShadowRound - 1) / kShadowRound;
     const V3 lightCentre = ld3(fr.light_pos);
     const uint32_t one = fr.spp > 0 ? 1u : 0u;  // a 1 the compiler cannot see through
-    unsigned int* chunkCounter = wv.qCount + (wv.levels + 3) + depth;
+    unsigned int* chunkCounter = wv.qCount + 1;
     if (tid == 0) {
         sm->head = 0u;
         sm->tail = 0u;
@@ -204,7 +288,8 @@ k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, 
             bool pend = false;
             float4 eP = make_float4(0.f, 0.f, 0.f, 0.f), eO = eP;
             if (i < n) {
-                const Hit h = unpack_hit(q.geo[i], make_float4(0.f, 0.f, 0.f, 0.f));
+                const float4 g = q.geo[i];
+                const Hit h = unpack_hit(g, make_float4(0.f, 0.f, 0.f, 0.f));
                 // P + n*eps (isInShadow, shading.cpp:17); computeSoftShadow hands it the raw hit normal
                 // (shading.cpp:54, raytracer.cpp:113)
                 const V3 origin = h.p + hit_normal(sc, h) * kShadowEpsilon;
@@ -213,7 +298,7 @@ k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, 
                     wv.lit[i] = static_cast<unsigned int>(N);
                 } else {
                     pend = true;
-                    eP = make_float4(h.p.x, h.p.y, h.p.z, __uint_as_float(i));
+                    eP = make_float4(h.p.x, h.p.y, h.p.z, __uint_as_float(shadow_seed(h.p, unpack_depth(g))));
                     eO = make_float4(origin.x, origin.y, origin.z, __uint_as_float(allow));
                 }
             }
@@ -226,6 +311,7 @@ k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, 
                     const unsigned int pos = (base + __popc(m & ((1u << lane) - 1u))) & (kPendCap - 1);
                     sm->pendP[pos] = eP;
                     sm->pendO[pos] = eO;
+                    sm->pendI[pos] = i;
                 }
             }
             __syncthreads();
@@ -244,7 +330,7 @@ k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, 
                     const V3 P = mk3(eP.x, eP.y, eP.z);
                     FreshStream rng;
                     if (round == 0) {
-                        rng.seed_balanced(shadow_seed(P, depth), one);
+                        rng.seed_balanced(__float_as_uint(eP.w), one);
                     } else {
                         const uint4 e = sm->engine[tid];
                         rng.cur = e.x; rng.nxt = e.y; rng.far = e.z; rng.j = e.w;
@@ -264,7 +350,7 @@ k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, 
                 }
                 __syncthreads();
             }
-            if (mine) wv.lit[__float_as_uint(sm->pendP[(head + tid) & (kPendCap - 1)].w)] = sm->lit[tid];
+            if (mine) wv.lit[sm->pendI[(head + tid) & (kPendCap - 1)]] = sm->lit[tid];
             __syncthreads();
             if (tid == 0) sm->head = head + cnt;
             __syncthreads();
@@ -277,17 +363,16 @@ k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, 
 // normalised normal: shading.cpp:69,78)
 template <bool BATCH>
 __global__ void __launch_bounds__(kWfThreads)
-k_wf_hardshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
-                const BatchSlice* __restrict__ batch) {
+k_wf_hardshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const BatchSlice* __restrict__ batch) {
     __shared__ __align__(8) uint64_t stageBar;
     const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
     const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
-    unsigned int n = wv.qCount[depth];
-    if (n > wv.pathCapacity) n = wv.pathCapacity;
+    unsigned int n = wv.qCount[0];
+    if (n > wv.qCapacity) n = wv.qCapacity;
     if (blockIdx.x * kWfThreads >= n) return;
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
-    const HitQueueView q = wv.q[which];
+    const HitQueueView q = wv.q;
     const V3 lightCentre = ld3(fr.light_pos);
     for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) {
         const Hit h = unpack_hit(q.geo[i], make_float4(0.f, 0.f, 0.f, 0.f));
@@ -296,102 +381,63 @@ k_wf_hardshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, 
     }
 }
 
-// ---------------------------------------------------------------- shade + bounce
-// tail == 0: a queue level whose shadow rays ran in k_wf_softshadow / k_wf_hardshadow; bounce hits go to the next queue.
-// tail == 1: the last queue (depth == wv.queueLevels).  By then only ~2 % of the paths are left,
-//            too few to be worth three launches per level: each thread takes one queued hit and
-//            follows its chain to the end, evaluating shadow rays in place.  The queue is compact,
-//            so warps start full and only thin out at the deepest, rarest levels.
-// QUEUED: the visibility comes from the shadow kernel's counters and bounce hits go to the next queue
-// (the lean form: no shadow code at all); otherwise shadows are evaluated in place, and with
-// tail != 0 the whole remaining chain is.
+// ---------------------------------------------------------------- shading
+// shade() for every hit of the queue (shading.cpp:62-96 + raytracer.cpp:116-131): Blinn-Phong with the
+// visibility the shadow kernel counted, ambient occlusion for camera-ray hits.  A hit that spawned a mirror
+// ray stores its colour on the path's bounce stack; the last hit of a chain that reached the bounce limit
+// stores the path's terminal colour.
+// QUEUED: the visibility comes from the shadow kernel's counters; otherwise (rare shadow settings: N > 113,
+// N <= 1, a point light) shadows are evaluated in place.
 template <bool QUEUED, bool BATCH>
 __global__ void WF_SHADE_BOUNDS
-k_wf_shade(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const int which, const int depth,
-           const int tailArg, const BatchSlice* __restrict__ batch) {
-    const int tail = QUEUED ? 0 : tailArg;
+k_wf_shade(const DevFrame fr, const FramePointers fp_, const WaveView wv_, const BatchSlice* __restrict__ batch) {
     const FramePointers& fp = BATCH ? batch[blockIdx.y].fp : fp_;
     const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     __shared__ __align__(8) uint64_t stageBar;
-    unsigned int n = wv.qCount[depth];
-    if (n > wv.pathCapacity) n = wv.pathCapacity;
+    unsigned int n = wv.qCount[0];
+    if (n > wv.qCapacity) n = wv.qCapacity;
     if (blockIdx.x * kWfThreads >= n) return;
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
-    const HitQueueView q = wv.q[which];
-    const HitQueueView qNext = wv.q[which ^ 1];
+    const HitQueueView q = wv.q;
     const bool cfg = fr.use_config != 0;
     const size_t cap = wv.pathCapacity;
+    const int lastBounce = min(fr.max_bounces, wv.levels);
 
-    for (unsigned int i0 = blockIdx.x * kWfThreads + (threadIdx.x & ~31u); i0 < n; i0 += gridDim.x * kWfThreads) {
-        const unsigned int i = i0 + (threadIdx.x & 31u);
-        bool bounceHit = false;
-        Hit next;
-        next.box = -1; next.face = 0; next.texel = 0; next.flip = false; next.t = 0.0f; next.p = mk3(0.f, 0.f, 0.f);
-        Ray ray;
-        ray.o = mk3(0.f, 0.f, 0.f);
-        ray.d = mk3(0.f, 0.f, 0.f);
-        unsigned int path = 0u;
-        if (i < n) {
-            const float4 g = q.geo[i], o = q.org[i], dd = q.dir[i];
-            Hit h = unpack_hit(g, o);
-            path = __float_as_uint(dd.w);
-            V3 rayO = mk3(o.x, o.y, o.z), rayD = mk3(dd.x, dd.y, dd.z);
-            int d = depth;
-            for (;;) {
-                const V3 P = h.p;
-                const V3 nrm = hit_normal(sc, h);
-                const float4 tex = hit_texel(sc, h);
-                const V3 viewDir = normalize3(rayO - P);
-                float vis;
-                if (QUEUED) {
-                    vis = static_cast<float>(wv.lit[i]) / static_cast<float>(wv.shadowRays);
-                    if (wv.shadowMode == kShadowHard) vis = wv.lit[i] ? 1.0f : 0.0f;
-                } else if (cfg && fr.soft_on) {
-                    vis = soft_shadow(sc, fr, P, nrm, fr.shadow_samples, shadow_seed(P, d));
-                } else {
-                    vis = in_shadow(sc, P, normalize3(nrm), ld3(fr.light_pos)) ? 0.0f : 1.0f;
-                }
-                float4 shaded = shade_lit(fr, P, nrm, tex, viewDir, vis);
-                const float alpha = shaded.w;
-                if (cfg && fr.ao_on && d == 0) {
-                    const float ao = ambient_occlusion(sc, P, nrm, fr.ao_samples, fr.ao_radius, ao_seed(P));
-                    const float f = 1.0f - fr.ao_intensity * (1.0f - ao);
-                    shaded.x *= f;
-                    shaded.y *= f;
-                    shaded.z *= f;
-                }
-                if (d < fr.max_bounces && d < wv.levels) {
-                    wv.stack[static_cast<size_t>(d) * cap + path] = make_float4(shaded.x, shaded.y, shaded.z, alpha);
-                    const V3 N = normalize3(nrm);
-                    const V3 D = normalize3(rayD);
-                    V3 Rd = D - N * (2.0f * dot3(D, N));
-                    Rd = normalize3(Rd);
-                    ray.o = P + N * kReflectEpsilon;
-                    ray.d = Rd;
-                    next = closest_hit(sc, ray);
-                    if (next.box < 0) {
-                        wv.tail[path] = flat_background(fr);  // bounced rays see the flat colour (raytracer.cpp:101)
-                        wv.top[path] = d + 1;
-                        break;
-                    }
-                    if (!tail) {  // hand the next level to the queues
-                        bounceHit = true;
-                        break;
-                    }
-                    h = next;
-                    rayO = ray.o;
-                    rayD = ray.d;
-                    ++d;
-                    continue;
-                }
-                shaded.w = alpha;
-                wv.tail[path] = clamp4(shaded);
-                wv.top[path] = d;
-                break;
-            }
+    for (unsigned int i = blockIdx.x * kWfThreads + threadIdx.x; i < n; i += gridDim.x * kWfThreads) {
+        const float4 g = q.geo[i], o = q.org[i], dd = q.dir[i];
+        const Hit h = unpack_hit(g, o);
+        const int d = unpack_depth(g);
+        const unsigned int path = __float_as_uint(dd.w);
+        const V3 P = h.p;
+        const V3 nrm = hit_normal(sc, h);
+        const float4 tex = hit_texel(sc, h);
+        const V3 viewDir = normalize3(mk3(o.x, o.y, o.z) - P);
+        float vis;
+        if (QUEUED) {
+            vis = static_cast<float>(wv.lit[i]) / static_cast<float>(wv.shadowRays);
+            if (wv.shadowMode == kShadowHard) vis = wv.lit[i] ? 1.0f : 0.0f;
+        } else if (cfg && fr.soft_on) {
+            vis = soft_shadow(sc, fr, P, nrm, fr.shadow_samples, shadow_seed(P, d));
+        } else {
+            vis = in_shadow(sc, P, normalize3(nrm), ld3(fr.light_pos)) ? 0.0f : 1.0f;
         }
-        enqueue_hit(qNext, &wv.qCount[depth + 1], wv.pathCapacity, bounceHit, next, ray, path);
+        float4 shaded = shade_lit(fr, P, nrm, tex, viewDir, vis);
+        const float alpha = shaded.w;
+        if (cfg && fr.ao_on && d == 0) {
+            const float ao = ambient_occlusion(sc, P, nrm, fr.ao_samples, fr.ao_radius, ao_seed(P));
+            const float f = 1.0f - fr.ao_intensity * (1.0f - ao);
+            shaded.x *= f;
+            shaded.y *= f;
+            shaded.z *= f;
+        }
+        if (d < lastBounce) {
+            wv.stack[static_cast<size_t>(d) * cap + path] = make_float4(shaded.x, shaded.y, shaded.z, alpha);
+        } else {
+            shaded.w = alpha;
+            wv.tail[path] = clamp4(shaded);
+            wv.top[path] = d;
+        }
     }
 }
 
@@ -500,31 +546,28 @@ int shadow_mode_of(const DevFrame& fr) {
 int stack_levels_of(const DevFrame& fr) {
     return fr.max_bounces < 0 ? 0 : (fr.max_bounces > kMaxStackDepth ? kMaxStackDepth : fr.max_bounces);
 }
+constexpr size_t kEntryBytes = 3 * sizeof(float4) + sizeof(unsigned int);  // geo, org, dir, lit
+constexpr int kQueueCounters = 4;
 
 }  // namespace
 
+int wavefront_max_hits_per_path(const DevFrame& fr) { return stack_levels_of(fr) + 1; }
 size_t wavefront_bytes_per_path(const DevFrame& fr) {
-    return 2 * 3 * sizeof(float4)            // two hit queues
-           + sizeof(unsigned)                // lit counters
-           + sizeof(float4) + sizeof(int)    // tail, top
-           + sizeof(float4) * stack_levels_of(fr);
+    return sizeof(float4) + sizeof(int) + sizeof(float4) * stack_levels_of(fr);  // tail, top, bounce stack
 }
+size_t wavefront_bytes_per_entry() { return kEntryBytes; }
+size_t wavefront_fixed_bytes(const DevFrame&) { return 256 * 16 + sizeof(unsigned int) * kQueueCounters; }
 
-size_t wavefront_fixed_bytes(const DevFrame& fr) {
-    return 256 * 16 + 2 * sizeof(unsigned int) * (stack_levels_of(fr) + 3);
-}
-
-bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int pathCapacity, int gridBlocks,
-                     WaveView* out) {
+bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int pathCapacity, unsigned int entryCapacity,
+                     int gridBlocks, WaveView* out) {
     WaveView w{};
     w.pathCapacity = pathCapacity;
     w.slotCapacity = pathCapacity / static_cast<unsigned int>(fr.spp);
+    w.qCapacity = entryCapacity;
     w.levels = stack_levels_of(fr);
     w.shadowMode = shadow_mode_of(fr);
     w.shadowRays = w.shadowMode == kShadowSoft ? fr.shadow_samples : (w.shadowMode == kShadowHard ? 1 : 0);
     w.gridBlocks = gridBlocks;
-    w.queueLevels = 3;
-    w.deepGridDiv = 1;
     w.softGrid = gridBlocks;
     unsigned char* p = static_cast<unsigned char*>(base);
     size_t off = 0;
@@ -533,25 +576,23 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
         off = align256(off + n);
         return r;
     };
-    const size_t cap = pathCapacity;
-    for (int k = 0; k < 2; ++k) {
-        w.q[k].geo = static_cast<float4*>(take(cap * sizeof(float4)));
-        w.q[k].org = static_cast<float4*>(take(cap * sizeof(float4)));
-        w.q[k].dir = static_cast<float4*>(take(cap * sizeof(float4)));
-    }
-    w.lit = static_cast<unsigned int*>(take(cap * sizeof(unsigned int)));
+    const size_t cap = pathCapacity, ents = entryCapacity;
+    w.q.geo = static_cast<float4*>(take(ents * sizeof(float4)));
+    w.q.org = static_cast<float4*>(take(ents * sizeof(float4)));
+    w.q.dir = static_cast<float4*>(take(ents * sizeof(float4)));
+    w.lit = static_cast<unsigned int*>(take(ents * sizeof(unsigned int)));
     w.tail = static_cast<float4*>(take(cap * sizeof(float4)));
     w.top = static_cast<int*>(take(cap * sizeof(int)));
     w.stack = static_cast<float4*>(take(std::max<size_t>(16, cap * sizeof(float4) * w.levels)));
-    // queue sizes per depth, then the chunk counters of the shadow kernel per depth (zeroed together)
-    w.qCount = static_cast<unsigned int*>(take(2 * sizeof(unsigned int) * (w.levels + 3)));
+    // [0] hits in the queue (counts on beyond the capacity: overflow), [1] chunk counter of the soft-shadow kernel
+    w.qCount = static_cast<unsigned int*>(take(sizeof(unsigned int) * kQueueCounters));
     if (off > bytes) return false;
     *out = w;
     return true;
 }
 
-void launch_batch_reset(const BatchSlice* batch, int nScenes, int levels, cudaStream_t stream) {
-    if (nScenes > 0) k_batch_reset<<<(nScenes + 127) / 128, 128, 0, stream>>>(batch, nScenes, 2 * (levels + 3));
+void launch_batch_reset(const BatchSlice* batch, int nScenes, cudaStream_t stream) {
+    if (nScenes > 0) k_batch_reset<<<(nScenes + 127) / 128, 128, 0, stream>>>(batch, nScenes, kQueueCounters);
 }
 
 void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
@@ -560,58 +601,49 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
     int n = 0;
     const int grid = wv.gridBlocks;
     const unsigned int ny = batch ? static_cast<unsigned int>(nScenes) : 1u;
+    const dim3 g(grid, ny);
+    const size_t blob = fp.blob_bytes;
+#define MCSKIN_WF_LAUNCH(KERNEL, GRID, SMEM, ...)                                                   \
+    do {                                                                                            \
+        if (batch) KERNEL<true><<<GRID, kWfThreads, SMEM, stream>>>(__VA_ARGS__, batch);            \
+        else KERNEL<false><<<GRID, kWfThreads, SMEM, stream>>>(__VA_ARGS__, batch);                 \
+        ++n;                                                                                        \
+    } while (0)
     if (wv.shadowMode == kShadowSoft) {  // ring + point table + scene blob exceed the default 48 KB
         static SmemOptIn optIn;
         static const void* const fns[] = {reinterpret_cast<const void*>(k_wf_softshadow<false>),
                                           reinterpret_cast<const void*>(k_wf_softshadow<true>)};
         optIn.limit(fns, 2);
     }
-    // a batch's queue counters are zeroed by the caller (one memset over all scenes)
-    if (!batch) cudaMemsetAsync(wv.qCount, 0, 2 * sizeof(unsigned int) * (wv.levels + 3), stream);
-    if (batch) k_wf_hit0<true><<<dim3(grid, ny), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv, batch); else k_wf_hit0<false><<<dim3(grid, ny), kWfThreads, fp.blob_bytes, stream>>>(fr, fp, list, wv, batch);
-    ++n;
+    // a batch's queue counters are zeroed by the caller (one kernel over all scenes)
+    if (!batch) cudaMemsetAsync(wv.qCount, 0, sizeof(unsigned int) * kQueueCounters, stream);
+    // every hit of every path, all bounce depths, into the one queue
+    MCSKIN_WF_LAUNCH(k_wf_trace, g, blob, fr, fp, list, wv);
     if (fr.max_bounces >= 0) {
-        // depths 0 .. queueLevels-1: seed / shadow / shade over the queue of that depth;
-        // depth queueLevels (if bounces go that deep): one tail launch that finishes every chain
-        const int queued = std::min(wv.levels + 1, std::max(1, wv.queueLevels));
-        for (int depth = 0; depth < queued; ++depth) {
-            const int which = depth & 1;
-            // Deeper queues are much shorter (~8 % of the primary hits at depth 1, then ~75 % of the
-            // previous level), but blocks beyond a queue's end return at once, and a short queue
-            // spread over every SM finishes sooner than one packed into a few resident blocks.
-            const dim3 g(depth == 0 ? grid : std::max(1, grid / std::max(1, wv.deepGridDiv)), ny);
-            if (wv.shadowMode == kShadowSoft) {
-                // persistent blocks that claim chunks of 256 hits: no more of them than can be resident
-                const dim3 gs(std::max(1, std::min<int>(g.x, wv.softGrid)), ny);
-                const size_t smem = ((fp.blob_bytes + 15u) & ~15u) + sizeof(ShadowSmem);
-                if (batch) k_wf_softshadow<true><<<gs, kWfThreads, smem, stream>>>(fr, fp, wv, which, depth, batch);
-                else k_wf_softshadow<false><<<gs, kWfThreads, smem, stream>>>(fr, fp, wv, which, depth, batch);
-                ++n;
-            } else if (wv.shadowMode == kShadowHard) {
-                if (batch) k_wf_hardshadow<true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
-                else k_wf_hardshadow<false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, batch);
-                ++n;
-            }
-            if (wv.shadowMode != kShadowInThread) {
-                if (batch) k_wf_shade<true, true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0, batch); else k_wf_shade<true, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0, batch);
-            } else {
-                if (batch) k_wf_shade<false, true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0, batch); else k_wf_shade<false, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, which, depth, 0, batch);
-            }
-            ++n;
+        if (wv.shadowMode == kShadowSoft) {
+            // persistent blocks that claim chunks of 256 hits: no more of them than can be resident
+            const dim3 gs(std::max(1, std::min<int>(grid, wv.softGrid)), ny);
+            const size_t smem = ((blob + 15u) & ~size_t(15)) + sizeof(ShadowSmem);
+            MCSKIN_WF_LAUNCH(k_wf_softshadow, gs, smem, fr, fp, wv);
+        } else if (wv.shadowMode == kShadowHard) {
+            MCSKIN_WF_LAUNCH(k_wf_hardshadow, g, blob, fr, fp, wv);
         }
-        if (queued <= wv.levels) {
-            const dim3 g(std::max(1, grid / std::max(1, wv.deepGridDiv)), ny);
-            if (batch) k_wf_shade<false, true><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, queued & 1, queued, 1, batch); else k_wf_shade<false, false><<<g, kWfThreads, fp.blob_bytes, stream>>>(fr, fp, wv, queued & 1, queued, 1, batch);
-            ++n;
+        if (wv.shadowMode != kShadowInThread) {
+            if (batch) k_wf_shade<true, true><<<g, kWfThreads, blob, stream>>>(fr, fp, wv, batch);
+            else k_wf_shade<true, false><<<g, kWfThreads, blob, stream>>>(fr, fp, wv, batch);
+        } else {
+            if (batch) k_wf_shade<false, true><<<g, kWfThreads, blob, stream>>>(fr, fp, wv, batch);
+            else k_wf_shade<false, false><<<g, kWfThreads, blob, stream>>>(fr, fp, wv, batch);
         }
+        ++n;
+        // only a queue smaller than paths x (bounces + 1) can overflow
+        if (static_cast<unsigned long long>(wv.qCapacity) < static_cast<unsigned long long>(wv.pathCapacity) * (wv.levels + 1))
+            MCSKIN_WF_LAUNCH(k_wf_overflow, g, blob, fr, fp, list, wv);
     }
     const int lg = log2_pow2_le32(fr.spp);
-    if (lg >= 0) {
-        if (batch) k_wf_resolve_warp<true><<<dim3(grid, ny), kWfThreads, 0, stream>>>(fr, band, list, wv, lg, batch); else k_wf_resolve_warp<false><<<dim3(grid, ny), kWfThreads, 0, stream>>>(fr, band, list, wv, lg, batch);
-    } else {
-        if (batch) k_wf_resolve_pixel<true><<<dim3(grid, ny), kWfThreads, 0, stream>>>(fr, band, list, wv, batch); else k_wf_resolve_pixel<false><<<dim3(grid, ny), kWfThreads, 0, stream>>>(fr, band, list, wv, batch);
-    }
-    ++n;
+    if (lg >= 0) MCSKIN_WF_LAUNCH(k_wf_resolve_warp, g, 0, fr, band, list, wv, lg);
+    else MCSKIN_WF_LAUNCH(k_wf_resolve_pixel, g, 0, fr, band, list, wv);
+#undef MCSKIN_WF_LAUNCH
     // pixels the queues could not take: megakernel, starting at the first slot beyond them
     // (never in a batch: its queues are sized for every pixel of a scene)
     if (!batch && wv.slotCapacity < list.capacity) {

@@ -7,49 +7,53 @@
 // slowest warp of the block.  The wavefront form runs the same arithmetic as a sequence of
 // short, uniform kernels over compact queues in HBM:
 //
-//   k_wf_hit0    thread = sample of a listed pixel: primary ray, closest hit
-//                -> miss: the sample's colour is the gradient background
-//                -> hit : appended to the depth-0 hit queue
-//   per depth d:
-//     k_wf_softshadow  block = chunks of 256 hits: the boxes each hit's shadow-ray bundle can reach; hits
-//                  that reach none are lit; the others are compacted in shared memory, get their fresh
-//                  std::mt19937 (397-step seeding) and the N points on the light's disk
-//                  computeSoftShadow would sample, then one thread per (hit, sample) casts the ray
-//                  (k_wf_hardshadow with soft shadows off: one ray per hit to the light's centre)
-//     k_wf_shade   thread = hit: Blinn-Phong with the counted visibility, AO, mirror ray,
-//                  closest hit of the bounce -> next queue, or the chain's terminal colour
+//   k_wf_trace   thread = sample of a listed pixel: primary ray, closest hit, mirror ray, closest hit, ...
+//                The chain a path follows does not depend on shading, so the whole of it is walked here and
+//                EVERY hit, tagged with its bounce depth, goes into the one hit queue; a ray that leaves the
+//                scene fixes the path's terminal colour (gradient for camera rays, flat colour for mirror rays)
+//   k_wf_softshadow  block = chunks of 256 hits (all depths): the boxes each hit's shadow-ray bundle can reach;
+//                hits that reach none are lit; the others are compacted in shared memory, get their fresh
+//                std::mt19937 (397-step seeding) and the N points on the light's disk computeSoftShadow
+//                would sample, then one thread per (hit, sample) casts the ray
+//                (k_wf_hardshadow with soft shadows off: one ray per hit to the light's centre)
+//   k_wf_shade   thread = hit: Blinn-Phong with the counted visibility, AO -> the path's bounce stack,
+//                or its terminal colour if the chain ends in this hit
 //   k_wf_resolve thread = sample: folds the bounce chain back to front with the reference's
 //                mix, then the ordered per-pixel average.
+// Five launches per frame whatever the bounce limit: the deeper bounces, a twentieth of the work, used to be a
+// chain of ever-shorter launches per depth that took a fifth of the frame time (and nearly half of one GPU's
+// share of a frame split eight ways).
 //
 // Every kernel is a persistent grid-stride loop over a device-side count, so nothing is
-// read back to the host between them.  Pixels beyond the queue capacity (extreme close-ups)
-// are shaded by the megakernel instead; results are identical either way.
+// read back to the host between them.  Pixels beyond the path capacity (extreme close-ups) are shaded by
+// the megakernel instead, and paths whose hits do not fit a budget-limited queue are redone in one thread
+// (k_wf_overflow); results are identical either way.
 #pragma once
 #include "kernels.cuh"
 
 namespace mcskin {
 
 struct HitQueueView {
-    float4* geo;  // hit point xyz, w = box | face << 16 | flip << 24
+    float4* geo;  // hit point xyz, w = box | face << 16 | flip << 19 | bounce depth << 20
     float4* org;  // ray origin xyz, w = texel index
     float4* dir;  // ray direction xyz, w = path index
 };
 
 struct WaveView {
-    HitQueueView q[2];       // ping-pong over depth
-    unsigned int* lit;       // per hit of the current queue: unoccluded shadow rays
+    HitQueueView q;          // every hit of every path, all bounce depths
+    unsigned int* lit;       // per queue entry: unoccluded shadow rays
     float4* tail;            // per path: colour returned by the deepest traceRay call
     float4* stack;           // [level][path]: shaded colour of every level that spawned a reflection (w = its alpha)
-    int* top;                // per path: number of stack levels in use
-    unsigned int* qCount;    // [levels + 3] queue sizes per depth, then [levels + 3] chunk counters of the shadow kernel (zeroed before the frame)
+    int* top;                // per path: number of stack levels in use (-1: unused slot, -2: queue overflow)
+    unsigned int* qCount;    // [0] hits appended to the queue (keeps counting beyond qCapacity), [1] chunk counter of
+                             // the soft-shadow kernel; zeroed before the frame
     unsigned int pathCapacity;
     unsigned int slotCapacity;  // pixels handled by the wavefront = pathCapacity / spp
-    int levels;              // stack levels allocated
-    int queueLevels;         // depths 0..queueLevels-1 go through the queues, deeper ones run in-thread
+    unsigned int qCapacity;  // queue entries; paths x (levels + 1) can never overflow
+    int levels;              // stack levels allocated = bounce depths traced
     int shadowMode;          // see enum below
     int shadowRays;          // rays per hit cast by the shadow kernel
     int gridBlocks;
-    int deepGridDiv;         // grid of the launches of depth >= 1 = gridBlocks / deepGridDiv
     int softGrid;            // blocks of the soft-shadow kernel (persistent: what fits the device at once)
 };
 
@@ -70,13 +74,16 @@ struct BatchSlice {
     WaveView wave;
 };
 
-// Bytes of queue / path storage needed per path for a frame description.
+// Storage: per path (terminal colour, stack height, bounce stack), per queue entry (hit record + lit counter).
 size_t wavefront_bytes_per_path(const DevFrame& fr);
-// Carves the views out of one allocation of at least pathCapacity * wavefront_bytes_per_path bytes
-// plus wavefront_fixed_bytes; returns false if `bytes` is too small.
+size_t wavefront_bytes_per_entry();
 size_t wavefront_fixed_bytes(const DevFrame& fr);
-bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int pathCapacity, int gridBlocks,
-                     WaveView* out);
+// Hits a path can put into the queue: bounce levels + 1.  A queue of pathCapacity times this cannot overflow.
+int wavefront_max_hits_per_path(const DevFrame& fr);
+// Carves the views out of one allocation of at least pathCapacity * wavefront_bytes_per_path +
+// entryCapacity * wavefront_bytes_per_entry + wavefront_fixed_bytes (+ 256 per array) bytes; false if too small.
+bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int pathCapacity, unsigned int entryCapacity,
+                     int gridBlocks, WaveView* out);
 
 // Shades every listed pixel (slots < wave.slotCapacity through the wavefront, the rest through the
 // megakernel) and writes the band image.  groupCounter: zeroed device counter.
@@ -85,7 +92,7 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
 void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
                       const WaveView& wave, unsigned int* groupCounter, cudaStream_t stream, int* launches,
                       const BatchSlice* batch = nullptr, int nScenes = 1);
-void launch_batch_reset(const BatchSlice* batch, int nScenes, int levels, cudaStream_t stream);
+void launch_batch_reset(const BatchSlice* batch, int nScenes, cudaStream_t stream);
 // The primary pass over the scenes of a batch (pixel-per-lane kernels only): returns false if the
 // frame description needs one of the other primary kernels, which have no batched form.
 bool launch_primary_batch(const DevFrame& fr, const BandView& band, uint32_t* tileStates, bool seedTiles,

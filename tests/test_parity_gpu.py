@@ -181,13 +181,13 @@ RENDER_MODES = {
     "megakernel": {"shade_mode": 1},
     "megakernel_warp": {"shade_mode": 2},
     "tiny_wave_budget": {"wave_budget_bytes": 1 << 20},   # most pixels overflow to the megakernel
-    "deep_queues": {"wave_queue_levels": 6},
-    "shallow_queues": {"wave_queue_levels": 1},
+    "small_queue": {"wave_queue_pct": 20},                # part of the paths overflow the hit queue: redone in-thread
+    "tiny_queue": {"wave_queue_pct": 1},                  # nearly all of them do
     "split_tiles": {"primary_blocks_per_sm": 100000},     # every tile split over one block per 256-pixel round
     "split_heavy_tiles": {"heavy_tiles_per_sm": 100000},  # the figure's tiles split over one block per round, the rest whole
     "one_lane_no_graph": {"frame_lanes": 1, "use_graphs": 0, "cache_tile_seeds": 0},
     "five_lanes": {"frame_lanes": 5},
-    "thin_deep_grids": {"wave_deep_grid_div": 8, "frame_lanes": 3},
+    "two_soft_blocks": {"soft_blocks_per_sm": 1, "shade_blocks_per_sm": 2, "frame_lanes": 2},
 }
 
 

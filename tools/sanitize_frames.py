@@ -42,8 +42,8 @@ def main():
         "megakernel": {"shade_mode": 1},
         "megakernel_warp": {"shade_mode": 2},
         "tiny_wave_budget": {"wave_budget_bytes": 1 << 20},
-        "deep_queues": {"wave_queue_levels": 6},
-        "shallow_queues": {"wave_queue_levels": 1},
+        "small_queue": {"wave_queue_pct": 20},
+        "tiny_queue": {"wave_queue_pct": 1},
         "split_tiles": {"primary_blocks_per_sm": 100000},
         "one_lane_no_graph": {"frame_lanes": 1, "use_graphs": 0, "cache_tile_seeds": 0},
         "five_lanes": {"frame_lanes": 5},
