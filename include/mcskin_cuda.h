@@ -181,6 +181,26 @@ int32_t mcskin_cuda_band_rows(const McConfig* cfg, int32_t first_tile_row, int32
  * frame over NVLink and no gather step is left — only a barrier before the root reads it. */
 int32_t mcskin_cuda_context_render_rows_into_frame(McContext* ctx, int32_t first_tile_row, int32_t stride,
                                                     void* d_frame_f32, void* d_frame_u8, void* stream);
+/* Any set of whole tiles (frame tile indices ty*tiles_x + tx, each at most once, any order) written at their
+ * own place in a FULL-frame image — the unit the reference's own load balancer hands out
+ * (tile_renderer.cpp:148-186: threads steal tiles from an atomic counter).  Every tile has its own jitter stream
+ * (tile_renderer.cpp:78), so any partition of a frame into tile sets gives the bits of the whole frame.  With
+ * mcskin_partition_tiles this is the multi-GPU split of one frame: cost-balanced tile sets, stored by every GPU
+ * straight into the root's frame (peer memory) or into one page-locked host frame (mcskin_cuda_host_register). */
+int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_t* tiles, int32_t n_tiles,
+                                                     void* d_frame_f32, void* d_frame_u8, void* stream);
+/* Deals the tiles of a frame to n_parts renderers so that every part costs about the same: tiles are weighted
+ * by how much of them the figure's screen rectangles cover (covered pixels cost ~50x a background pixel) and
+ * dealt greedily, heaviest first, to the least loaded part; deterministic, the parts are disjoint and cover the
+ * frame.  Returns the number of tiles of `part` (negative MC_ERR_* on failure) and writes at most `capacity`
+ * of them to out_tiles (may be null to query the count).  Host code only: needs no device. */
+int32_t mcskin_partition_tiles(const McScene* scene, const McConfig* cfg, int32_t n_parts, int32_t part,
+                               int32_t* out_tiles, int32_t capacity);
+/* Page-locks a host range (e.g. a shared-memory segment every process of the box has mapped) and maps it into
+ * the device address space: *d_ptr is what kernels store to (zero-copy over PCIe), so N GPUs can write their
+ * tiles of one frame into one host image through N PCIe links at once. */
+int32_t mcskin_cuda_host_register(void* host_ptr, uint64_t bytes, void** d_ptr);
+int32_t mcskin_cuda_host_unregister(void* host_ptr);
 /* Plain device allocations that can be shared between the processes of one box (one process per
  * GPU): export on the owner, open on the peers (cudaIpcGetMemHandle / cudaIpcOpenMemHandle; the
  * handle is 64 opaque bytes to pass over any channel, e.g. a torch.distributed broadcast). */

@@ -1,7 +1,15 @@
-"""Multi-GPU partition of one frame: tile row j of the frame belongs to rank
-j % world, every rank renders its rows into a compact band image, rank 0 gathers the bands
-and puts the rows back in order.  The tile stream (per-tile RNG) makes any partition made
-of whole reference tiles bit-identical to the single-device frame.
+"""Multi-GPU partition of one frame.  The tile stream (per-tile RNG) makes any partition
+made of whole reference tiles bit-identical to the single-device frame.  Two forms:
+
+* tiles (default): the frame's tiles are dealt to the ranks by cost (lib.partition_tiles: the tiles the
+  figure covers cost ~50x a background tile), every rank's kernels store its tiles straight into ONE frame —
+  rank 0's device image mapped into every process over NVLink peer memory (PeerFrame), or one page-locked
+  host image in shared memory that every GPU writes through its own PCIe link (HostFrame) — and the only
+  exchange left is a barrier;
+* rows (MCSKIN_EXCHANGE=gather, SURVEY's original plan): tile row j belongs to rank j % world, every rank
+  renders its rows into a compact band image, rank 0 gathers the bands with NCCL and puts the rows back in order.
+
+Batches shard by skin: skin i belongs to rank i % world (shard_batch), no exchange at all.
 
 Pure torch / torch.distributed code with no CUDA calls of its own, so the same functions
 run under NCCL on GPUs (bench.py) and under gloo on CPU (tests).
@@ -10,6 +18,11 @@ from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+
+def shard_batch(n_items: int, rank: int, world: int) -> list[int]:
+    """Indices of the skins of a batch rendered by `rank` (skin i -> GPU i mod n)."""
+    return list(range(rank, n_items, world))
 
 
 def tiles_y(height: int, tile_size: int) -> int:
@@ -114,20 +127,28 @@ class PeerFrame:
             self.frame = self._whole[:frame_bytes].view(torch.float32).view(height, width, 4)
             torch.cuda.synchronize(dev)
         self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._timed_out = torch.zeros(1, dtype=torch.int32, device=dev)  # set by the wait kernel if a rank never signals
         self.epoch = 0
         if self.world > 1:
             dist.barrier()  # flags are zeroed before anyone signals
 
     def fence(self, stream: int = 0):
-        """One-way barrier: after this (in the root's stream order) every rank's rows of the current frame
-        are in the root's image.  Non-root ranks only signal and run ahead."""
+        """One-way barrier: after this (in the root's stream order) every rank's tiles of the current frame
+        are in the root's image.  Non-root ranks only signal and run ahead: use it only while the root does not
+        consume the frame between steps (else follow it with fence_all).  A rank that never signals makes the
+        root's wait give up after ~2 s; check_timeout() raises then."""
         self.epoch += 1
         if self.world == 1:
             return
         if self.rank == 0:
-            self.lib.peer_wait(self.device, self.flags_ptr + 4, self.world - 1, self.epoch, 0, stream)
+            self.lib.peer_wait(self.device, self.flags_ptr + 4, self.world - 1, self.epoch, self._timed_out.data_ptr(), stream)
         else:
             self.lib.peer_signal(self.device, self.flags_ptr + 4 * self.rank, self.epoch, stream)
+
+    def check_timeout(self):
+        """Root, after synchronising: raises if a wait of this frame or an earlier one gave up on a rank."""
+        if self.rank == 0 and self.world > 1 and int(self._timed_out.item()) != 0:
+            raise RuntimeError("PeerFrame: a rank did not signal within the wait kernel's time limit; the frame is incomplete")
 
     def fence_all(self):
         """Two-way barrier on the current torch stream (NCCL): nobody passes before everybody arrived."""
@@ -143,3 +164,76 @@ class PeerFrame:
             self._whole = None
             self.buffer.free()
             self.buffer = None
+
+
+class HostFrame:
+    """ONE page-locked host image shared by every rank of the box: a POSIX shared-memory segment created by
+    rank 0, mapped by all ranks and registered with CUDA in each of them, so that every GPU's kernels store
+    their tiles of the frame straight into it (zero-copy, one PCIe link per GPU instead of a single
+    device-to-host copy of the whole frame from the root).  After the pixels: one 64-bit counter per rank and
+    one for the root, the barrier between the processes (`publish` / `wait_all` / `release` / `wait_released`)."""
+
+    def __init__(self, lib, height: int, width: int):
+        from multiprocessing import shared_memory
+
+        import numpy as np
+        self.lib = lib
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.frame_bytes = height * width * 16
+        total = self.frame_bytes + 4096
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=total)
+            name[0] = self.shm.name
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=0)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        self.bytes = np.ndarray((total,), dtype=np.uint8, buffer=self.shm.buf)
+        self.frame = self.bytes[:self.frame_bytes].view(np.float32).reshape(height, width, 4)
+        self.flags = self.bytes[self.frame_bytes:self.frame_bytes + 8 * (self.world + 1)].view(np.uint64)
+        if self.rank == 0:
+            self.flags[:] = 0
+        self.ptr = lib.host_register(self.bytes)  # device address of the same pages
+        self.epoch = 0
+        if self.world > 1:
+            dist.barrier()
+
+    def publish(self):
+        """This rank's tiles of the current frame are in host memory (call after synchronising its stream)."""
+        self.epoch += 1
+        self.flags[self.rank] = self.epoch
+
+    def wait_all(self, timeout_s: float = 20.0):
+        """Root: every rank has published the current frame."""
+        import time
+        t0 = time.perf_counter()
+        for r in range(self.world):
+            while int(self.flags[r]) < self.epoch:
+                if time.perf_counter() - t0 > timeout_s:
+                    raise RuntimeError(f"HostFrame: rank {r} did not publish frame {self.epoch}")
+
+    def release(self):
+        """Root: the frame has been consumed, the ranks may overwrite it."""
+        self.flags[self.world] = self.epoch
+
+    def wait_released(self, timeout_s: float = 20.0):
+        import time
+        t0 = time.perf_counter()
+        while int(self.flags[self.world]) < self.epoch:
+            if time.perf_counter() - t0 > timeout_s:
+                raise RuntimeError(f"HostFrame: the root did not release frame {self.epoch}")
+
+    def close(self):
+        try:
+            self.lib.host_unregister(self.bytes)
+        except Exception:  # noqa: BLE001
+            pass
+        self.frame = self.flags = self.bytes = None
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:  # noqa: BLE001
+            pass

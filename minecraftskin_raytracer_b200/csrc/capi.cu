@@ -92,6 +92,11 @@ struct McContext {
     DevBuf count, slotPixel, records;
     DevBuf imgF32, imgU8, scratchIn, scratchOut;
     DevBuf tileStates;           // seeded mt19937 state of every tile of a chunk
+    DevBuf tileMap;              // render_tiles_into_frame: frame tile indices, heavy tiles first
+    std::vector<int32_t> tileMapHost, tileMapOrdered;
+    unsigned long long tileMapVersion = 0;
+    int tileMapHeavy = 0;
+    DevFrame tileMapFrame{};     // the frame description the map was ordered for
     DevBuf wave;                 // queues of the wavefront shading pipeline
     PinnedBuf pinned;
     // options
@@ -104,7 +109,7 @@ struct McContext {
                                              // (every block of a split tile regenerates the tile's whole jitter stream)
     int waveQueuePct = 0;                    // hit-queue entries as a percentage of the paths (0: paths x (bounces + 1),
                                              // which cannot overflow; smaller queues redo overflowing paths in-thread)
-    int frameLanes = 3;                      // a frame's tile rows are rendered on this many streams at once
+    int frameLanes = 2;                      // a frame's tile rows are rendered on this many streams at once
     bool isChild = false;                    // a lane of another context (never splits frames itself)
     // seeded tile engines kept from the previous frame: they depend on the image width, the tile
     // size and the tile rows of the band only (tile_renderer.cpp:78), not on the scene
@@ -112,9 +117,11 @@ struct McContext {
         int width = 0, tile_size = 0, first = 0, stride = 0, rows = 0;
         const void* buf = nullptr;
         cudaStream_t stream = nullptr;
+        const void* map = nullptr;
+        unsigned long long mapVersion = 0;
         bool operator==(const TileSeedKey& o) const {
             return width == o.width && tile_size == o.tile_size && first == o.first && stride == o.stride &&
-                   rows == o.rows && buf == o.buf && stream == o.stream;
+                   rows == o.rows && buf == o.buf && stream == o.stream && map == o.map && mapVersion == o.mapVersion;
         }
     } tileSeedKey;
     bool tileSeedValid = false;
@@ -137,6 +144,9 @@ struct McContext {
         const void *blob, *texels, *outF32, *outU8;
         unsigned int blobBytes;
         int first, stride, lanes;
+        const void* tileMap;
+        unsigned long long mapVersion;
+        int nTiles, nHeavy;
         long long optionBits[12];
         unsigned long long allocEpoch;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
@@ -204,49 +214,68 @@ int band_pixel_rows(const DevFrame& f, int first, int stride) {
     return (n - 1) * f.tile_size + lastHeight;
 }
 
-// Launches the two passes for the tile rows {first + k*stride} on one stream; output pointers are
-// device memory.  scn: the context whose scene (prepared frame, box and texel buffers) is rendered;
-// local tile row r is written at tile row outFirst + r*outStride of the output image.
-int render_bands_lane(McContext* ctx, const McContext* scn, int first, int stride, int outFirst, int outStride,
-                      float4* outF32, uchar4* outU8, cudaStream_t stream, int lanesInFlight = 1) {
+// What one launch sequence covers: tile rows {first + k*stride} written at tile rows outFirst + k*outStride of
+// the output image, or (map != null) any set of whole tiles — a device array of frame tile indices, the
+// nHeavy tiles that intersect the figure's screen rectangle first — written at their own place in a full frame.
+struct BandSpec {
+    int first = 0, stride = 1, outFirst = 0, outStride = 1;
+    const int* map = nullptr;
+    int nTiles = 0, nHeavy = 0;
+    unsigned long long mapVersion = 0;
+};
+
+// Launches the two passes of a band on one stream; output pointers are device memory.  scn: the context whose
+// scene (prepared frame, box and texel buffers) is rendered.
+int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec, float4* outF32, uchar4* outU8,
+                      cudaStream_t stream, int lanesInFlight = 1) {
     const DevFrame& f = scn->prep.frame;
-    const int nRows = local_tile_rows(f, first, stride);
+    const bool mapped = spec.map != nullptr;
+    const int first = spec.first, stride = spec.stride;
+    const int nRows = mapped ? 0 : local_tile_rows(f, first, stride);
+    const long long nTilesAll = mapped ? spec.nTiles : static_cast<long long>(nRows) * f.tiles_x;
     ctx->chunksLastRender = 0;
     ctx->graphLastRender = false;
     ctx->stats = McRenderStats{};
     ctx->stats.n_samples = static_cast<int64_t>(std::max(f.width, 0)) * std::max(f.height, 0) * f.spp;
-    ctx->stats.n_tiles = nRows * f.tiles_x;
-    if (nRows == 0) return MC_OK;
+    ctx->stats.n_tiles = nTilesAll;
+    if (nTilesAll == 0) return MC_OK;
     if (f.width > 65535 || f.height > 65535) return fail(MC_ERR_LIMIT, "image larger than 65535 pixels on a side");
     if (static_cast<long long>(f.tile_size) * f.tile_size > (1ll << 30))
         return fail(MC_ERR_LIMIT, "tile_size too large");
 
     const bool classify = !ctx->forceAllActive && f.spp <= kBlockThreads;
-    // work-list slots a tile row can need: every pixel, or — the classifying primary pass only lists pixels
-    // inside the figure's screen rectangle — the rectangle's columns
-    size_t slotsPerTileRow = static_cast<size_t>(f.tiles_x) * f.tile_size * f.tile_size;
-    if (classify && f.rect_valid) {
+    // A band is rendered in chunks of UNITS — whole tile rows, or tiles of the map — so that the worst-case
+    // work list of a chunk fits the budget.  Work-list slots a unit can need: every pixel, or, as the
+    // classifying primary pass only lists pixels inside the figure's screen rectangle, the rectangle's columns
+    // of a tile row / the pixels of a tile that intersects it (the first nHeavy of a map).
+    const size_t tilePixels = static_cast<size_t>(f.tile_size) * f.tile_size;
+    size_t slotsPerUnit = mapped ? tilePixels : static_cast<size_t>(f.tiles_x) * tilePixels;
+    if (!mapped && classify && f.rect_valid) {
         const long long rectW = static_cast<long long>(std::min(f.width - 1, f.rect_x1)) - std::max(0, f.rect_x0) + 1;
-        slotsPerTileRow = std::min(slotsPerTileRow, static_cast<size_t>(std::max<long long>(rectW, 1)) * f.tile_size);
+        slotsPerUnit = std::min(slotsPerUnit, static_cast<size_t>(std::max<long long>(rectW, 1)) * f.tile_size);
     }
+    const size_t nUnits = mapped ? static_cast<size_t>(spec.nTiles) : static_cast<size_t>(nRows);
+    const size_t tilesPerUnit = mapped ? 1 : static_cast<size_t>(f.tiles_x);
+    // units that can list pixels at all (the rest need no slots): every row; the heavy tiles of a map
+    const size_t nListingUnits = (mapped && classify && f.rect_valid) ? static_cast<size_t>(spec.nHeavy) : nUnits;
     const size_t recordBytesPerSlot = static_cast<size_t>(f.spp) * f.draws_per_sample * sizeof(float);
-    // tile rows per chunk so that the worst-case work list fits the budget
-    size_t rowsPerChunk = nRows;
-    if (recordBytesPerSlot > 0) {
-        const size_t perRow = slotsPerTileRow * recordBytesPerSlot;
-        rowsPerChunk = std::max<size_t>(1, static_cast<size_t>(ctx->recordBudgetBytes) / std::max<size_t>(1, perRow));
-        rowsPerChunk = std::min<size_t>(rowsPerChunk, nRows);
+    size_t unitsPerChunk = nUnits;
+    if (recordBytesPerSlot > 0 && nListingUnits > 0) {
+        const size_t perUnit = slotsPerUnit * recordBytesPerSlot;
+        const size_t fit = std::max<size_t>(1, static_cast<size_t>(ctx->recordBudgetBytes) / std::max<size_t>(1, perUnit));
+        // (a map lists its heavy tiles first: chunks of `fit` units hold at most `fit` listing units each)
+        if (fit < nListingUnits) unitsPerChunk = fit;
     }
     // slot indices are 32-bit
-    while (rowsPerChunk > 1 && rowsPerChunk * slotsPerTileRow > 0x7fffffffull) --rowsPerChunk;
-    const size_t slotCap = rowsPerChunk * slotsPerTileRow;
+    while (unitsPerChunk > 1 && std::min(unitsPerChunk, nListingUnits) * slotsPerUnit > 0x7fffffffull) --unitsPerChunk;
+    const size_t slotCap = std::max<size_t>(1, std::min(unitsPerChunk, std::max<size_t>(nListingUnits, 0)) * slotsPerUnit);
     if (slotCap > 0x7fffffffull) return fail(MC_ERR_LIMIT, "one tile row holds more than 2^31 pixels");
-    const int nChunks = static_cast<int>((nRows + rowsPerChunk - 1) / rowsPerChunk);
+    const int nChunks = static_cast<int>((nUnits + unitsPerChunk - 1) / unitsPerChunk);
 
     CU_TRY(ctx->countLog.reserve(sizeof(unsigned int) * 2 * nChunks));  // [active count | group counter] per chunk
     CU_TRY(ctx->slotPixel.reserve(slotCap * sizeof(uint2)));
     CU_TRY(ctx->records.reserve(std::max<size_t>(16, slotCap * recordBytesPerSlot)));
-    CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, rowsPerChunk * f.tiles_x * 624 * sizeof(uint32_t))));
+    CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, unitsPerChunk * tilesPerUnit * 624 * sizeof(uint32_t))));
     CU_TRY(cudaMemsetAsync(ctx->countLog.p, 0, sizeof(unsigned int) * 2 * nChunks, stream));
 
     while (ctx->passEvents.size() < static_cast<size_t>(3 * nChunks)) {
@@ -284,7 +313,8 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
     int launches = 0;
     McContext::TileSeedKey seedKey;
     seedKey.width = f.width; seedKey.tile_size = f.tile_size; seedKey.first = first; seedKey.stride = stride;
-    seedKey.rows = nRows; seedKey.buf = ctx->tileStates.p; seedKey.stream = stream;
+    seedKey.rows = mapped ? spec.nTiles : nRows; seedKey.buf = ctx->tileStates.p; seedKey.stream = stream;
+    seedKey.map = spec.map; seedKey.mapVersion = spec.mapVersion;
     const bool seedsCacheable = ctx->cacheTileSeeds && nChunks == 1 && f.draws_per_sample > 0;
     const bool seedTiles = !(seedsCacheable && ctx->tileSeedValid && seedKey == ctx->tileSeedKey);
     ctx->tileSeedKey = seedKey;
@@ -293,25 +323,33 @@ int render_bands_lane(McContext* ctx, const McContext* scn, int first, int strid
     // Splitting the figure's tiles pays only when the frame (all lanes in flight) has too few tiles to
     // keep every SM busy for as long as its slowest tile takes: below ~10 tiles per SM (B200 sweep:
     // a whole 1080p frame, 2040 tiles, is best unsplit; half a frame is best split in three).
-    const long long tilesInFlight = static_cast<long long>(nRows) * f.tiles_x * std::max(1, lanesInFlight);
+    const long long tilesInFlight = nTilesAll * std::max(1, lanesInFlight);
     const int heavyTarget = tilesInFlight * 3 >= 2ll * ctx->smCount * ctx->heavyTilesPerSm
                                 ? 0 : ctx->smCount * ctx->heavyTilesPerSm / std::max(1, lanesInFlight);
     for (int c = 0; c < nChunks; ++c) {
-        const int row0 = static_cast<int>(c * rowsPerChunk);
-        const int rows = static_cast<int>(std::min<size_t>(rowsPerChunk, nRows - row0));
-        BandView band;
-        band.first_tile_row = first + row0 * stride;
-        band.tile_row_stride = stride;
-        band.n_tile_rows = rows;
-        band.out_first_row = outFirst + row0 * outStride;
-        band.out_row_stride = outStride;
+        const size_t unit0 = static_cast<size_t>(c) * unitsPerChunk;
+        const size_t units = std::min<size_t>(unitsPerChunk, nUnits - unit0);
+        BandView band{};
         band.out_f32 = outF32;
         band.out_u8 = outU8;
+        size_t listing = units;
+        if (mapped) {
+            band.tile_map = spec.map + unit0;
+            band.n_tiles = static_cast<int>(units);
+            band.n_heavy = static_cast<int>(unit0 >= static_cast<size_t>(spec.nHeavy) ? 0 : std::min<size_t>(units, spec.nHeavy - unit0));
+            if (classify && f.rect_valid) listing = static_cast<size_t>(band.n_heavy);
+        } else {
+            band.first_tile_row = first + static_cast<int>(unit0) * stride;
+            band.tile_row_stride = stride;
+            band.n_tile_rows = static_cast<int>(units);
+            band.out_first_row = spec.outFirst + static_cast<int>(unit0) * spec.outStride;
+            band.out_row_stride = spec.outStride;
+        }
         ActiveList list;
         list.count = static_cast<unsigned int*>(ctx->countLog.p) + c;
         list.slot_pixel = static_cast<uint2*>(ctx->slotPixel.p);
         list.records = static_cast<float*>(ctx->records.p);
-        list.capacity = static_cast<unsigned int>(static_cast<size_t>(rows) * slotsPerTileRow);
+        list.capacity = static_cast<unsigned int>(std::min(slotCap, std::max<size_t>(1, listing * slotsPerUnit)));
         if (!classify) {
             // positional slots: mark all unused, preset the count to the capacity
             CU_TRY(cudaMemsetAsync(list.slot_pixel, 0xff, static_cast<size_t>(list.capacity) * sizeof(uint2), stream));
@@ -376,18 +414,24 @@ void inherit_options(McContext* lane, const McContext* ctx) {
 // frameLayout: the output is a full-frame image and every tile row lands at its own frame position
 // (output tile row = frame tile row) instead of a compact band.
 int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* outF32, uchar4* outU8, cudaStream_t stream,
-                       bool frameLayout) {
+                       bool frameLayout, const BandSpec* tiles) {
+    if (tiles) return render_bands_lane(ctx, ctx, *tiles, outF32, outU8, stream);  // a tile map is one lane
+    auto rows = [&](int f0, int st, int out0, int outSt) {
+        BandSpec b;
+        b.first = f0; b.stride = st; b.outFirst = out0; b.outStride = outSt;
+        return b;
+    };
     if (L <= 1)
-        return render_bands_lane(ctx, ctx, first, stride, frameLayout ? first : 0, frameLayout ? stride : 1, outF32, outU8, stream);
+        return render_bands_lane(ctx, ctx, rows(first, stride, frameLayout ? first : 0, frameLayout ? stride : 1), outF32, outU8, stream);
     CU_TRY(cudaEventRecord(ctx->evCopy, stream));  // fork point
     // lane 0 on the caller's stream, lanes 1..L-1 on their own
-    int rc = render_bands_lane(ctx, ctx, first, stride * L, frameLayout ? first : 0, frameLayout ? stride * L : L, outF32, outU8, stream, L);
+    int rc = render_bands_lane(ctx, ctx, rows(first, stride * L, frameLayout ? first : 0, frameLayout ? stride * L : L), outF32, outU8, stream, L);
     if (rc != MC_OK) return rc;
     for (int k = 1; k < L; ++k) {
         McContext* lane = ctx->lanes[k - 1];
         CU_TRY(cudaStreamWaitEvent(lane->stream, ctx->evCopy, 0));
-        rc = render_bands_lane(lane, ctx, first + k * stride, stride * L, frameLayout ? first + k * stride : k,
-                               frameLayout ? stride * L : L, outF32, outU8, lane->stream, L);
+        rc = render_bands_lane(lane, ctx, rows(first + k * stride, stride * L, frameLayout ? first + k * stride : k,
+                                               frameLayout ? stride * L : L), outF32, outU8, lane->stream, L);
         if (rc != MC_OK) return rc;
         CU_TRY(cudaEventRecord(lane->evCopy, lane->stream));
     }
@@ -416,11 +460,12 @@ void drop_graph(McContext* ctx) {
 // the SMs fill those gaps with the other lanes' blocks.  Whole tile rows per lane, so the image
 // is bit-identical to the one-stream result.  The second time the same frame description comes
 // in, the launches are captured into a CUDA graph, which is replayed from then on.
+// tiles: instead of tile rows, the tile map of `tiles` (always written in frame layout, one lane).
 int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* outU8, cudaStream_t stream,
-                 bool frameLayout = false) {
+                 bool frameLayout = false, const BandSpec* tiles = nullptr) {
     const DevFrame& f = ctx->prep.frame;
-    const int nRows = local_tile_rows(f, first, stride);
-    const int L = ctx->isChild ? 1 : std::max(1, std::min(ctx->frameLanes, nRows / 2));
+    const int nRows = tiles ? (tiles->nTiles > 0 ? 1 : 0) : local_tile_rows(f, first, stride);
+    const int L = (ctx->isChild || tiles) ? 1 : std::max(1, std::min(ctx->frameLanes, nRows / 2));
     ctx->splitLastRender = 0;
     ctx->graphLastRender = false;
     if (stream != ctx->stream && ctx->evUpload) CU_TRY(cudaStreamWaitEvent(stream, ctx->evUpload, 0));
@@ -438,6 +483,9 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         key.blob = ctx->boxes.p; key.texels = ctx->texels.p; key.outF32 = outF32; key.outU8 = outU8;
         key.blobBytes = static_cast<unsigned int>(ctx->prep.blob.size());
         key.first = first; key.stride = stride; key.lanes = L * 2 + (frameLayout ? 1 : 0);
+        if (tiles) {
+            key.tileMap = tiles->map; key.mapVersion = tiles->mapVersion; key.nTiles = tiles->nTiles; key.nHeavy = tiles->nHeavy;
+        }
         for (int i = 0; i < 12; ++i) key.optionBits[i] = option_bits(ctx, i);
         key.allocEpoch = g_allocEpoch.load();
         if (ctx->graphExec && key == ctx->graphKey) {
@@ -478,7 +526,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         ctx->capturing = true;
         for (int k = 1; k < L; ++k) ctx->lanes[k - 1]->capturing = true;
         cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
-        int rc = e == cudaSuccess ? launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout) : MC_ERR_CUDA;
+        int rc = e == cudaSuccess ? launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout, tiles) : MC_ERR_CUDA;
         cudaGraph_t g = nullptr;
         if (e == cudaSuccess) {
             const cudaError_t e2 = cudaStreamEndCapture(stream, &g);
@@ -501,7 +549,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
                 ctx->graphLaneChunks[k] = lane->chunksLastRender;
                 ctx->graphLaneTiles[k] = static_cast<int>(lane->stats.n_tiles);
             }
-            return render_bands(ctx, first, stride, outF32, outU8, stream, frameLayout);  // replays the graph just made
+            return render_bands(ctx, first, stride, outF32, outU8, stream, frameLayout, tiles);  // replays the graph just made
         }
         // capture failed (an operation that cannot be captured): clear the error state, render directly
         if (g) cudaGraphDestroy(g);
@@ -510,7 +558,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         ctx->useGraphs = 0;
     }
     CU_TRY(cudaEventRecord(ctx->ev0, stream));
-    const int rc = launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout);
+    const int rc = launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout, tiles);
     if (rc != MC_OK) return rc;
     if (L > 1) {
         CU_TRY(cudaEventRecord(ctx->ev1, stream));
@@ -868,7 +916,7 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->boxes, &ctx->texels, &ctx->count, &ctx->slotPixel, &ctx->records, &ctx->imgF32, &ctx->imgU8,
-                      &ctx->scratchIn, &ctx->scratchOut, &ctx->countLog, &ctx->wave, &ctx->tileStates})
+                      &ctx->scratchIn, &ctx->scratchOut, &ctx->countLog, &ctx->wave, &ctx->tileStates, &ctx->tileMap})
         b->release();
     ctx->pinned.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -951,6 +999,76 @@ int32_t mcskin_cuda_context_render_rows_into_frame(McContext* ctx, int32_t first
     CU_TRY(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     return render_bands(ctx, first, stride, static_cast<float4*>(dFrameF32), static_cast<uchar4*>(dFrameU8), s, true);
+}
+
+int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_t* tiles, int32_t nTiles, void* dFrameF32,
+                                                     void* dFrameU8, void* stream) {
+    if (!ctx || !ctx->hasScene) return fail(MC_ERR_INVALID, "render_tiles_into_frame: no scene set");
+    if (nTiles < 0 || (nTiles > 0 && !tiles)) return fail(MC_ERR_INVALID, "render_tiles_into_frame: bad tile list");
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const DevFrame& f = ctx->prep.frame;
+    const bool sameList = ctx->tileMapVersion != 0 && ctx->tileMapHost.size() == static_cast<size_t>(nTiles) &&
+                          (nTiles == 0 || std::memcmp(ctx->tileMapHost.data(), tiles, sizeof(int32_t) * nTiles) == 0);
+    // the heavy-first order depends on the figure's screen rectangle and the tile grid
+    const bool sameOrder = sameList && f.rect_valid == ctx->tileMapFrame.rect_valid && f.rect_x0 == ctx->tileMapFrame.rect_x0 &&
+                           f.rect_y0 == ctx->tileMapFrame.rect_y0 && f.rect_x1 == ctx->tileMapFrame.rect_x1 &&
+                           f.rect_y1 == ctx->tileMapFrame.rect_y1 && f.tiles_x == ctx->tileMapFrame.tiles_x &&
+                           f.tiles_y == ctx->tileMapFrame.tiles_y && f.tile_size == ctx->tileMapFrame.tile_size;
+    if (!sameOrder) {
+        const long long total = static_cast<long long>(f.tiles_x) * f.tiles_y;
+        std::vector<unsigned char> seen(static_cast<size_t>(std::max<long long>(total, 0)), 0);
+        std::vector<int32_t> heavy, light;
+        for (int i = 0; i < nTiles; ++i) {
+            const int id = tiles[i];
+            if (id < 0 || id >= total) return fail(MC_ERR_INVALID, "render_tiles_into_frame: tile index out of range");
+            if (seen[id]) return fail(MC_ERR_INVALID, "render_tiles_into_frame: tile listed twice");
+            seen[id] = 1;
+            const int ty = id / f.tiles_x, tx = id - ty * f.tiles_x;
+            const int x = tx * f.tile_size, y = ty * f.tile_size;
+            const int w = std::min(f.tile_size, f.width - x), h = std::min(f.tile_size, f.height - y);
+            // the primary kernels' own test (tileCanHit)
+            const bool canHit = !f.rect_valid || !(x > f.rect_x1 || x + w - 1 < f.rect_x0 || y > f.rect_y1 || y + h - 1 < f.rect_y0);
+            (canHit ? heavy : light).push_back(id);
+        }
+        ctx->tileMapHost.assign(tiles, tiles + nTiles);
+        ctx->tileMapHeavy = static_cast<int>(heavy.size());
+        ctx->tileMapOrdered = heavy;
+        ctx->tileMapOrdered.insert(ctx->tileMapOrdered.end(), light.begin(), light.end());
+        ctx->tileMapFrame = f;
+        if (nTiles > 0) {
+            CU_TRY(ctx->tileMap.reserve(sizeof(int32_t) * static_cast<size_t>(nTiles)));
+            // (pageable source: staged before the call returns; ordered after the previous frame's kernels on `s`)
+            CU_TRY(cudaMemcpyAsync(ctx->tileMap.p, ctx->tileMapOrdered.data(), sizeof(int32_t) * nTiles, cudaMemcpyHostToDevice, s));
+        }
+        ++ctx->tileMapVersion;
+    }
+    if (nTiles == 0) {
+        ctx->stats = McRenderStats{};
+        ctx->statsPending = false;
+        return MC_OK;
+    }
+    BandSpec spec;
+    spec.map = static_cast<const int*>(ctx->tileMap.p);
+    spec.nTiles = nTiles;
+    spec.nHeavy = ctx->tileMapHeavy;
+    spec.mapVersion = ctx->tileMapVersion;
+    return render_bands(ctx, 0, 1, static_cast<float4*>(dFrameF32), static_cast<uchar4*>(dFrameU8), s, true, &spec);
+}
+
+int32_t mcskin_cuda_host_register(void* hostPtr, uint64_t bytes, void** dPtr) {
+    if (!hostPtr || bytes == 0) return fail(MC_ERR_INVALID, "host_register: null or empty range");
+    CU_TRY(cudaHostRegister(hostPtr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    if (dPtr) {
+        *dPtr = nullptr;
+        CU_TRY(cudaHostGetDevicePointer(dPtr, hostPtr, 0));
+    }
+    return MC_OK;
+}
+int32_t mcskin_cuda_host_unregister(void* hostPtr) {
+    if (!hostPtr) return MC_OK;
+    CU_TRY(cudaHostUnregister(hostPtr));
+    return MC_OK;
 }
 
 int32_t mcskin_cuda_device_alloc(int32_t device, uint64_t bytes, void** out) {

@@ -57,6 +57,7 @@ struct SceneView {
     int n_boxes;
     uint32_t posed_mask;   // among boxes 0..31: never pre-rejected (none today; posed boxes carry world bounds)
     uint32_t usable_mask;  // among boxes 0..31: exist and have triangles
+    uint32_t opaque_mask;  // among boxes 0..31: unposed and without see-through texels (kBoxOpaque)
 };
 
 __device__ __forceinline__ V3 face_normal(int face) {
@@ -350,6 +351,8 @@ __device__ __forceinline__ uint32_t candidate_mask_among(const SceneView& sc, co
 __device__ __forceinline__ bool any_hit_among(const SceneView& sc, const Ray& ray, uint32_t allow) {
     const RayPre pre = ray_pre(ray);
     uint32_t mask = candidate_mask_among(sc, ray, pre, allow);
+    // a surviving box without see-through texels is a hit (see occluded_among)
+    if (!pre.parallel && (mask & sc.opaque_mask)) return true;
     while (mask) {
         const int b = __ffs(mask) - 1;
         mask &= mask - 1u;
@@ -449,7 +452,15 @@ __device__ __forceinline__ bool occluded_among(const SceneView& sc, const Ray& r
                     const float az = (L.z - ray.o.z) * pre.inv.z, bz = (H.z - ray.o.z) * pre.inv.z;
                     const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
                     const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-                    if (fmaxf(tmin, 0.0f) > tmax || !(tmin < dist)) rejected |= 1u << i;
+                    if (fmaxf(tmin, 0.0f) > tmax || !(tmin < dist)) {
+                        rejected |= 1u << i;
+                    } else if ((sc.opaque_mask >> i) & 1u) {
+                        // An unposed box with no see-through texel: intersectAABB reports a hit for every ray
+                        // that passes its slab test, at tmin — or at tmax when the origin is inside
+                        // (intersection.cpp:246-288); tmin / tmax above are the reference's own values.
+                        if ((tmin < 0.0f ? tmax : tmin) < dist) return true;
+                        rejected |= 1u << i;  // hit, but beyond the light
+                    }
                 }
                 mask &= ~rejected | sc.posed_mask;
             }

@@ -53,6 +53,7 @@ __device__ __forceinline__ SceneView scene_view(const unsigned char* blob, const
     sc.n_boxes = nBoxes;
     sc.posed_mask = fr.posed_mask;
     sc.usable_mask = fr.usable_mask;
+    sc.opaque_mask = fr.opaque_mask;
     return sc;
 }
 

@@ -36,7 +36,8 @@ enum : uint32_t {
     kBoxRotX = 4u,       // |rotX| > 0.01 (intersection.cpp:16)
     kBoxRotZ = 8u,       // |rotZ| > 0.01 (intersection.cpp:26)
     kBoxEmpty = 16u,     // no triangles: never hit (intersection.cpp:205)
-    kBoxRecip = 32u      // inv_size_* may replace the divisions by size[] (see div_exact)
+    kBoxRecip = 32u,     // inv_size_* may replace the divisions by size[] (see div_exact)
+    kBoxOpaque = 64u     // unposed, and no texel of any face has alpha == 0: every ray that passes the slab test hits
 };
 
 // The scene blob: what a CTA stages into shared memory with one bulk copy.
@@ -75,6 +76,7 @@ struct DevFrame {
     // scene
     int n_boxes;
     uint32_t posed_mask, usable_mask;   // over boxes 0..31: posed / has triangles
+    uint32_t opaque_mask;               // over boxes 0..31: kBoxOpaque
     float light_pos[3], light_color[4], light_radius;
     float background[4];
     // integrator

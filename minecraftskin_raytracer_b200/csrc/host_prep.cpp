@@ -237,6 +237,7 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
         if (b < 32) {
             if (!(flags & kBoxEmpty)) f.usable_mask |= 1u << b;
         }
+        bool opaque = true;  // no texel of any face has alpha == 0 (the pass-through rule, intersection.cpp:311)
         for (int k = 0; k < kFaceCount; ++k) {
             const McFaceTex& ft = src.face[k];
             int offset, w, h;
@@ -257,6 +258,15 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
             }
             d.face[k].x = offset;
             d.face[k].y = w | (h << 16);
+            for (long long t = 0; opaque && t < static_cast<long long>(w) * h; ++t)
+                if (out.texels[static_cast<size_t>(offset + t)].w == 0.0f) opaque = false;
+        }
+        // an unposed box without see-through texels is hit by exactly the rays that pass the slab test, at
+        // the slab distance: occlusion queries need no face / texel evaluation for it (occluded_among)
+        if (opaque && !src.has_rotation && !(flags & kBoxEmpty)) {
+            flags |= kBoxOpaque;
+            d.flags = flags;
+            if (b < 32) f.opaque_mask |= 1u << b;
         }
         // conservative world bounds of this box (posed boxes: rotate the 8 corners in double)
         double boxLo[3] = {1e300, 1e300, 1e300}, boxHi[3] = {-1e300, -1e300, -1e300};
@@ -405,6 +415,75 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
 }
 
 }  // namespace mcskin
+
+// Cost-balanced deal of a frame's tiles (see mcskin_cuda.h).  The weight of a tile: 1 for its primary pass plus
+// kCoveredCost times the fraction of it that box rectangles cover (every box counted: overlapping inner and
+// outer layers do mean more work), or that the figure's rectangle covers when the boxes have none.
+extern "C" int32_t mcskin_partition_tiles(const McScene* scene, const McConfig* cfg, int32_t nParts, int32_t part,
+                                          int32_t* outTiles, int32_t capacity) {
+    using namespace mcskin;
+    if (!scene || !cfg || nParts <= 0 || part < 0 || part >= nParts || capacity < 0) {
+        set_last_error("partition_tiles: bad argument");
+        return MC_ERR_INVALID;
+    }
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->tile_size <= 0) return 0;
+    PreparedFrame pf;
+    std::string err;
+    const int rc = prepare_frame(scene, cfg, 1, 0.0f, pf, err);
+    if (rc != MC_OK) {
+        set_last_error(err);
+        return rc;
+    }
+    const DevFrame& f = pf.frame;
+    const int ts = f.tile_size;
+    const long long nTiles = static_cast<long long>(f.tiles_x) * f.tiles_y;
+    if (nTiles > 0x7fffffff) {
+        set_last_error("partition_tiles: too many tiles");
+        return MC_ERR_LIMIT;
+    }
+    constexpr double kCoveredCost = 50.0;
+    std::vector<std::array<int, 4>> rects;
+    if (f.box_rects_valid) {
+        const SceneBlobLayout lay(f.n_boxes);
+        const int* r = reinterpret_cast<const int*>(pf.blob.data() + lay.rectOffset());
+        for (int b = 0; b < f.n_boxes; ++b)
+            if (!(pf.boxes[b].flags & kBoxEmpty)) rects.push_back({r[4 * b], r[4 * b + 1], r[4 * b + 2], r[4 * b + 3]});
+    } else if (f.rect_valid) {
+        rects.push_back({f.rect_x0, f.rect_y0, f.rect_x1, f.rect_y1});
+    } else {
+        rects.push_back({0, 0, f.width - 1, f.height - 1});  // any pixel may hit: cost follows the tile's area
+    }
+    std::vector<std::pair<double, int>> order(static_cast<size_t>(nTiles));
+    for (int id = 0; id < nTiles; ++id) {
+        const int tileY = id / f.tiles_x, tileX = id - tileY * f.tiles_x;
+        const int left = tileX * ts, top = tileY * ts;
+        const int right = std::min(f.width, left + ts) - 1, bottom = std::min(f.height, top + ts) - 1;
+        double covered = 0.0;
+        for (const auto& r : rects) {
+            const long long w = static_cast<long long>(std::min(right, r[2])) - std::max(left, r[0]) + 1;
+            const long long h = static_cast<long long>(std::min(bottom, r[3])) - std::max(top, r[1]) + 1;
+            if (w > 0 && h > 0) covered += static_cast<double>(w) * static_cast<double>(h);
+        }
+        const double area = static_cast<double>(right - left + 1) * (bottom - top + 1);
+        order[id] = {area / (static_cast<double>(ts) * ts) + kCoveredCost * covered / (static_cast<double>(ts) * ts), id};
+    }
+    std::stable_sort(order.begin(), order.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
+        return a.first > b.first;  // heaviest first; equal weights keep frame order
+    });
+    std::vector<double> load(nParts, 0.0);
+    std::vector<int32_t> mine;
+    for (const auto& t : order) {
+        int best = 0;
+        for (int p = 1; p < nParts; ++p)
+            if (load[p] < load[best]) best = p;
+        load[best] += t.first;
+        if (best == part) mine.push_back(t.second);
+    }
+    std::sort(mine.begin(), mine.end());
+    if (outTiles)
+        for (size_t i = 0; i < mine.size() && i < static_cast<size_t>(capacity); ++i) outTiles[i] = mine[i];
+    return static_cast<int32_t>(mine.size());
+}
 
 // Host model of the device's sincos_ref (dev_shade.cuh): glibc 2.39 sincosf as built for x86-64 with
 // FMA.  Same operations in the same order; std::fma is a correctly rounded fused multiply-add

@@ -37,14 +37,23 @@ struct TileGeom {
 
 __device__ __forceinline__ TileGeom tile_geom(const DevFrame& fr, const BandView& band, int localTile) {
     TileGeom g;
-    const int localRow = localTile / fr.tiles_x;
-    const int tx = localTile - localRow * fr.tiles_x;
-    const int ty = band.first_tile_row + localRow * band.tile_row_stride;
+    int tx, ty, outRow;
+    if (band.tile_map) {  // any set of tiles, written at their own place in a full frame
+        const int id = __ldg(band.tile_map + localTile);
+        ty = id / fr.tiles_x;
+        tx = id - ty * fr.tiles_x;
+        outRow = ty;
+    } else {
+        const int localRow = localTile / fr.tiles_x;
+        tx = localTile - localRow * fr.tiles_x;
+        ty = band.first_tile_row + localRow * band.tile_row_stride;
+        outRow = band.out_first_row + localRow * band.out_row_stride;
+    }
     g.x = tx * fr.tile_size;
     g.y = ty * fr.tile_size;
     g.w = min(fr.tile_size, fr.width - g.x);
     g.h = min(fr.tile_size, fr.height - g.y);
-    g.bandRow0 = (band.out_first_row + localRow * band.out_row_stride) * fr.tile_size;
+    g.bandRow0 = outRow * fr.tile_size;
     g.localIndex = localTile;
     return g;
 }
@@ -65,6 +74,11 @@ struct TileOrder {
 
 static TileOrder make_tile_order(const DevFrame& fr, const BandView& band, int partsHeavy, int partsLight) {
     TileOrder o{0, 0, 0, 0, 0, partsLight, partsLight};
+    if (band.tile_map) {  // the map lists the heavy tiles first: launch slot == local tile (hw == 0 marks it)
+        o.n_heavy = band.n_heavy;
+        o.parts_heavy = band.n_heavy > 0 ? partsHeavy : partsLight;
+        return o;
+    }
     if (!fr.rect_valid || fr.rect_x1 < 0 || fr.rect_y1 < 0) return o;
     const int ts = fr.tile_size, W = fr.tiles_x;
     const int tx0 = std::max(0, fr.rect_x0) / ts, tx1 = std::min(W - 1, fr.rect_x1 / ts);
@@ -83,7 +97,7 @@ static TileOrder make_tile_order(const DevFrame& fr, const BandView& band, int p
 
 // launch slot -> local tile index; a bijection of [0, tiles of the band)
 __host__ __device__ __forceinline__ int ordered_tile(const TileOrder& o, int W, int slot) {
-    if (o.n_heavy == 0) return slot;
+    if (o.n_heavy == 0 || o.hw == 0) return slot;
     if (slot < o.n_heavy) {
         const int r = slot / o.hw;
         return (o.r0 + r) * W + o.tx0 + (slot - r * o.hw);
@@ -569,7 +583,7 @@ __device__ __forceinline__ void pix_stream_block(uint32_t (*state)[kMtN], float*
 // in a small kernel of their own instead of idling 255 threads of each tile's block.
 __global__ void k_tile_seed(const DevFrame fr, const BandView band, uint32_t* states) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nTiles = band.n_tile_rows * fr.tiles_x;
+    const int nTiles = band_tile_count(band, fr.tiles_x);
     if (t >= nTiles) return;
     const TileGeom tg = tile_geom(fr, band, t);
     uint32_t x = static_cast<uint32_t>(tg.y * fr.width + tg.x);  // tile_renderer.cpp:78
@@ -1083,7 +1097,7 @@ static size_t pix_smem_limit() {
 static void launch_primary_pix(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
                                uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, int heavyTargetTiles,
                                const BatchSlice* batch, int nScenes, unsigned int blobBytes, cudaStream_t stream) {
-    const int nTiles = band.n_tile_rows * fr.tiles_x;
+    const int nTiles = band_tile_count(band, fr.tiles_x);
     const size_t pixSmem = ((sizeof(PixStreamSmem) + 15) & ~size_t(15)) + blobBytes;
     // the seeded engines depend on the tile geometry only: one set serves every scene of a batch
     if (fr.draws_per_sample > 0 && seedTiles) k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates);
@@ -1132,7 +1146,7 @@ static bool pix_kernel_applies(const DevFrame& fr, unsigned int blobBytes) {
 bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
                     int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, int heavyTargetTiles,
                     cudaStream_t stream) {
-    const int nTiles = band.n_tile_rows * fr.tiles_x;
+    const int nTiles = band_tile_count(band, fr.tiles_x);
     if (nTiles <= 0) return false;
     const long long tileDraws = static_cast<long long>(fr.tile_size) * fr.tile_size * fr.spp * (fr.draws_per_sample > 0 ? fr.draws_per_sample : 1);
     const int lg = tileDraws < (1ll << 30) ? log2_if_warp_spp(fr.spp) : -1;

@@ -55,18 +55,26 @@ private:
     bool known_[kMaxDevices] = {};
 };
 
-// Which tile rows of the frame a launch covers, and where its pixels land.
-// Local tile row r is frame tile row first_tile_row + r*tile_row_stride; the output
-// image is the compact band of those rows (tile_size pixel rows each, last clipped).
-// Local tile row r lands at tile row out_first_row + r*out_row_stride of the output image
-// (0 and 1 for a compact band; a frame split over several streams writes interleaved rows of
-// one shared band image).
+// Which tiles of the frame a launch covers, and where its pixels land.
+// Row form (tile_map == null): local tile row r is frame tile row first_tile_row + r*tile_row_stride and lands
+// at tile row out_first_row + r*out_row_stride of the output image (0 and 1 for a compact band of those rows;
+// a frame split over several streams writes interleaved rows of one shared band image; out = frame row for a
+// full-frame image).
+// Map form (tile_map != null): local tile t is frame tile tile_map[t] (= ty*tiles_x + tx), any set of whole
+// tiles, the ones that intersect the figure's screen rectangle first (n_heavy of them); the output image is a
+// full frame and every tile lands at its own place.
 struct BandView {
     int first_tile_row, tile_row_stride, n_tile_rows;
     int out_first_row, out_row_stride;
     float4* out_f32;  // may be null
     uchar4* out_u8;   // may be null
+    const int* tile_map;  // device memory, or null
+    int n_tiles, n_heavy;
 };
+// tiles of a band
+__host__ __device__ inline int band_tile_count(const BandView& band, int tilesX) {
+    return band.tile_map ? band.n_tiles : band.n_tile_rows * tilesX;
+}
 
 // Work list produced by the primary pass for the shading pass.
 struct ActiveList {

@@ -12,12 +12,12 @@ namespace mcskin {
 namespace {
 
 constexpr int kWfThreads = 256;
-// Minimum resident blocks per SM asked of the compiler (i.e. register caps), from a sweep on B200:
-// 4 blocks (64 registers) for the primary-hit and the queued shade kernels (+1.3 % frame rate),
-// compiler's choice for the shadow kernel (59 registers; capping it at 48 was slower) and for
-// the in-thread tail form of the shade kernel (128).
+// Minimum resident blocks per SM asked of the compiler (i.e. register caps), from sweeps on B200:
+// 3 blocks (80 registers, no spills) for the trace kernel (at 64 registers it spills 116 bytes: -1.5 % frame
+// rate), 4 blocks (64 registers) for the queued shade kernel, compiler's choice for the hard-shadow kernel and
+// for the in-thread shadow form of the shade kernel.
 #ifndef MCSKIN_WF_HIT0_MIN_BLOCKS
-#define MCSKIN_WF_HIT0_MIN_BLOCKS 4
+#define MCSKIN_WF_HIT0_MIN_BLOCKS 3
 #endif
 #ifndef MCSKIN_WF_SHADE_MIN_BLOCKS
 #define MCSKIN_WF_SHADE_MIN_BLOCKS 4

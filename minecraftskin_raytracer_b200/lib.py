@@ -21,7 +21,7 @@ import os
 LIB_PATH = Path(os.environ.get("MCSKIN_LIB") or (Path(__file__).resolve().parent / "_lib" / "libmcskin_cuda.so"))
 
 # streams a frame's tile rows are dealt to by default (McContext::frameLanes in csrc/capi.cu)
-DEFAULT_FRAME_LANES = 3
+DEFAULT_FRAME_LANES = 2
 
 # every symbol include/mcskin_cuda.h declares
 EXPORTS = [
@@ -36,7 +36,8 @@ EXPORTS = [
     "mcskin_sincos_model", "mcskin_cuda_powf", "mcskin_powf_model", "mcskin_cuda_context_render_rows_into_frame",
     "mcskin_cuda_device_alloc", "mcskin_cuda_device_free", "mcskin_cuda_ipc_export", "mcskin_cuda_ipc_open",
     "mcskin_cuda_ipc_close", "mcskin_cuda_fp32_issue_peak", "mcskin_cuda_peer_signal", "mcskin_cuda_peer_wait",
-    "mcskin_primary_launch_order",
+    "mcskin_primary_launch_order", "mcskin_cuda_context_render_tiles_into_frame", "mcskin_partition_tiles",
+    "mcskin_cuda_host_register", "mcskin_cuda_host_unregister",
 ]
 
 
@@ -224,6 +225,31 @@ def peer_wait(device: int, d_flags: int, n: int, value: int, d_timeout: int = 0,
                                       C.c_void_p(d_timeout or None), C.c_void_p(stream or None)))
 
 
+def partition_tiles(scene: FlatScene, cfg: McConfig, n_parts: int, part: int) -> np.ndarray:
+    """Frame tile indices (ty * tiles_x + tx, ascending) of `part` in the cost-balanced deal of the frame's tiles
+    to n_parts renderers (host code, needs no GPU).  The parts are disjoint and cover the frame."""
+    cs = scene.as_c()
+    n = _lib.mcskin_partition_tiles(C.byref(cs), C.byref(cfg), C.c_int32(n_parts), C.c_int32(part), None, C.c_int32(0))
+    _check(min(n, 0))
+    out = np.zeros(n, dtype=np.int32)
+    if n:
+        _check(min(_lib.mcskin_partition_tiles(C.byref(cs), C.byref(cfg), C.c_int32(n_parts), C.c_int32(part),
+                                               _ptr(out, C.c_int32), C.c_int32(n)), 0))
+    return out
+
+
+def host_register(array: np.ndarray) -> int:
+    """Page-locks a host array (e.g. a view of a shared-memory segment) and maps it into the device address
+    space; returns the device address kernels can store to."""
+    p = C.c_void_p()
+    _check(_lib.mcskin_cuda_host_register(C.c_void_p(array.ctypes.data), C.c_uint64(array.nbytes), C.byref(p)))
+    return int(p.value)
+
+
+def host_unregister(array: np.ndarray):
+    _check(_lib.mcskin_cuda_host_unregister(C.c_void_p(array.ctypes.data)))
+
+
 def ipc_close(device: int, ptr: int):
     _check(_lib.mcskin_cuda_ipc_close(C.c_int32(device), C.c_void_p(ptr)))
 
@@ -270,6 +296,13 @@ class Context:
         _check(_lib.mcskin_cuda_context_render_rows_into_frame(self._h, C.c_int32(first_tile_row), C.c_int32(stride),
                                                                C.c_void_p(d_frame_f32 or None), C.c_void_p(d_frame_u8 or None),
                                                                C.c_void_p(stream or None)))
+
+    def render_tiles_into_frame(self, tiles: np.ndarray, d_frame_f32: int = 0, d_frame_u8: int = 0, stream: int = 0):
+        """Asynchronous: any set of whole tiles (frame tile indices) written at their own place in a full frame."""
+        tiles = np.ascontiguousarray(tiles, dtype=np.int32)
+        _check(_lib.mcskin_cuda_context_render_tiles_into_frame(self._h, _ptr(tiles, C.c_int32), C.c_int32(len(tiles)),
+                                                                C.c_void_p(d_frame_f32 or None), C.c_void_p(d_frame_u8 or None),
+                                                                C.c_void_p(stream or None)))
 
     def render_batch(self, scenes: list[FlatScene], cfg: McConfig, d_out_f32: int = 0, d_out_u8: int = 0, stream: int = 0):
         """Asynchronous: scene i -> image i of the [n, H, W, 4] device buffer(s) (one skin per scene, same config)."""
