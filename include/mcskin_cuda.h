@@ -237,6 +237,11 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
  * until the images are complete. */
 int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, int32_t n_scenes,
                                          const McConfig* cfg, void* d_out_f32, void* d_out_u8, void* stream);
+/* The same, host to host and sharded by skin over devices 0..n_devices-1 of this process (BASELINE config 4):
+ * skin i is rendered by device i % n_devices — scenes are independent frames, there is no exchange — one host
+ * thread per device, image i lands at out_*[i] (n_scenes consecutive host images; either may be null).  Blocking. */
+int32_t mcskin_cuda_render_batch_multi(const McScene* scenes, int32_t n_scenes, const McConfig* cfg, int32_t n_devices,
+                                       float* out_rgba_f32, uint8_t* out_rgba_u8);
 
 /* ---- single-ray entry points: the reference's free functions, exercised through
  *      the same device code (no CPU fallback).  All arrays are HOST memory. ---- */

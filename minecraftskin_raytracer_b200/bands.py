@@ -173,7 +173,7 @@ class HostFrame:
     device-to-host copy of the whole frame from the root).  After the pixels: one 64-bit counter per rank and
     one for the root, the barrier between the processes (`publish` / `wait_all` / `release` / `wait_released`)."""
 
-    def __init__(self, lib, height: int, width: int):
+    def __init__(self, lib, height: int, width: int, register: bool = True):
         from multiprocessing import shared_memory
 
         import numpy as np
@@ -195,7 +195,9 @@ class HostFrame:
         self.flags = self.bytes[self.frame_bytes:self.frame_bytes + 8 * (self.world + 1)].view(np.uint64)
         if self.rank == 0:
             self.flags[:] = 0
-        self.ptr = lib.host_register(self.bytes)  # device address of the same pages
+        # device address of the same pages (register=False: host-only use, e.g. the gloo tests on a CPU box)
+        self.registered = bool(register)
+        self.ptr = lib.host_register(self.bytes) if register else 0
         self.epoch = 0
         if self.world > 1:
             dist.barrier()
@@ -226,10 +228,11 @@ class HostFrame:
                 raise RuntimeError(f"HostFrame: the root did not release frame {self.epoch}")
 
     def close(self):
-        try:
-            self.lib.host_unregister(self.bytes)
-        except Exception:  # noqa: BLE001
-            pass
+        if self.registered:
+            try:
+                self.lib.host_unregister(self.bytes)
+            except Exception:  # noqa: BLE001
+                pass
         self.frame = self.flags = self.bytes = None
         try:
             self.shm.close()

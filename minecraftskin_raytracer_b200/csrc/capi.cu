@@ -8,6 +8,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -1382,6 +1383,85 @@ int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, 
     }
     ctx->stats = McRenderStats{};
     ctx->statsPending = false;
+    return MC_OK;
+}
+
+// A batch sharded by skin over the devices of this process (BASELINE config 4): skin i belongs to
+// device i mod nDevices, no exchange of any kind.  One host thread per device prepares, stages and launches
+// that device's skins chunk by chunk (mcskin_cuda_context_render_batch) and sends every finished chunk's
+// images to the caller's host arrays on a copy stream while the next chunk renders.
+int32_t mcskin_cuda_render_batch_multi(const McScene* scenes, int32_t nScenes, const McConfig* cfg, int32_t nDevices,
+                                       float* outF32, uint8_t* outU8) {
+    if (!scenes || !cfg || nScenes < 0) return fail(MC_ERR_INVALID, "render_batch_multi: bad argument");
+    const int avail = mcskin_cuda_device_count();
+    if (avail <= 0) return fail(MC_ERR_NO_DEVICE, "no CUDA device");
+    if (nDevices <= 0 || nDevices > avail) return fail(MC_ERR_INVALID, "render_batch_multi: bad device count");
+    if (nScenes == 0 || (!outF32 && !outU8)) return MC_OK;
+    if (cfg->width <= 0 || cfg->height <= 0) return MC_OK;
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    std::vector<McContext*> ctxs(nDevices, nullptr);
+    for (int d = 0; d < nDevices; ++d) {
+        const int rc = shared_context(d, &ctxs[d]);
+        if (rc != MC_OK) return rc;
+    }
+    const size_t pixels = static_cast<size_t>(cfg->width) * cfg->height;
+    std::vector<int> rcs(nDevices, MC_OK);
+    std::vector<std::string> errs(nDevices);
+    auto work = [&](int d) {
+        McContext* ctx = ctxs[d];
+        auto run = [&]() -> int {
+            CU_TRY(cudaSetDevice(d));
+            std::vector<McScene> mine;
+            std::vector<int> index;
+            for (int i = d; i < nScenes; i += nDevices) {
+                mine.push_back(scenes[i]);
+                index.push_back(i);
+            }
+            if (mine.empty()) return MC_OK;
+            const int chunk = std::max(1, ctx->batchGroup);
+            const size_t slots = std::min<size_t>(mine.size(), 2 * static_cast<size_t>(chunk));  // two chunks in flight
+            if (outF32) CU_TRY(ctx->imgF32.reserve(slots * pixels * sizeof(float4)));
+            if (outU8) CU_TRY(ctx->imgU8.reserve(slots * pixels * sizeof(uchar4)));
+            cudaEvent_t copied[2] = {nullptr, nullptr};
+            for (auto& e : copied) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            int rc = MC_OK;
+            int half = 0;
+            for (size_t c0 = 0; c0 < mine.size() && rc == MC_OK; c0 += chunk, half ^= 1) {
+                const int n = static_cast<int>(std::min<size_t>(chunk, mine.size() - c0));
+                float4* dF = outF32 ? static_cast<float4*>(ctx->imgF32.p) + static_cast<size_t>(half) * chunk * pixels : nullptr;
+                uchar4* dU = outU8 ? static_cast<uchar4*>(ctx->imgU8.p) + static_cast<size_t>(half) * chunk * pixels : nullptr;
+                // this half of the image buffer is free once the copies of the chunk before last have left it
+                if (cudaStreamWaitEvent(ctx->stream, copied[half], 0) != cudaSuccess) { rc = MC_ERR_CUDA; break; }
+                rc = mcskin_cuda_context_render_batch(ctx, mine.data() + c0, n, cfg, dF, dU, ctx->stream);
+                if (rc != MC_OK) break;
+                if (cudaEventRecord(ctx->evFrameDone, ctx->stream) != cudaSuccess ||
+                    cudaStreamWaitEvent(ctx->copyStream, ctx->evFrameDone, 0) != cudaSuccess) { rc = MC_ERR_CUDA; break; }
+                for (int k = 0; k < n && rc == MC_OK; ++k) {
+                    const size_t dst = static_cast<size_t>(index[c0 + k]) * pixels;
+                    if (outF32 && cudaMemcpyAsync(outF32 + dst * 4, dF + static_cast<size_t>(k) * pixels, pixels * sizeof(float4),
+                                                  cudaMemcpyDeviceToHost, ctx->copyStream) != cudaSuccess) rc = MC_ERR_CUDA;
+                    if (outU8 && cudaMemcpyAsync(outU8 + dst * 4, dU + static_cast<size_t>(k) * pixels, pixels * sizeof(uchar4),
+                                                 cudaMemcpyDeviceToHost, ctx->copyStream) != cudaSuccess) rc = MC_ERR_CUDA;
+                }
+                if (rc == MC_OK && cudaEventRecord(copied[half], ctx->copyStream) != cudaSuccess) rc = MC_ERR_CUDA;
+            }
+            if (rc == MC_ERR_CUDA && errs[d].empty()) set_last_error(std::string("render_batch_multi: ") + cudaGetErrorString(cudaGetLastError()));
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->copyStream);
+            for (auto& e : copied) cudaEventDestroy(e);
+            if (rc != MC_OK) return rc;
+            CU_TRY(cudaGetLastError());
+            return MC_OK;
+        };
+        rcs[d] = run();
+        if (rcs[d] != MC_OK) errs[d] = mcskin_cuda_last_error();  // the message is thread-local: carry it out
+    };
+    std::vector<std::thread> threads;
+    for (int d = 1; d < nDevices; ++d) threads.emplace_back(work, d);
+    work(0);
+    for (auto& t : threads) t.join();
+    for (int d = 0; d < nDevices; ++d)
+        if (rcs[d] != MC_OK) return fail(rcs[d], "device " + std::to_string(d) + ": " + errs[d]);
     return MC_OK;
 }
 

@@ -37,7 +37,7 @@ EXPORTS = [
     "mcskin_cuda_device_alloc", "mcskin_cuda_device_free", "mcskin_cuda_ipc_export", "mcskin_cuda_ipc_open",
     "mcskin_cuda_ipc_close", "mcskin_cuda_fp32_issue_peak", "mcskin_cuda_peer_signal", "mcskin_cuda_peer_wait",
     "mcskin_primary_launch_order", "mcskin_cuda_context_render_tiles_into_frame", "mcskin_partition_tiles",
-    "mcskin_cuda_host_register", "mcskin_cuda_host_unregister",
+    "mcskin_cuda_host_register", "mcskin_cuda_host_unregister", "mcskin_cuda_render_batch_multi",
 ]
 
 
@@ -169,6 +169,19 @@ def render(scene: FlatScene, cfg: McConfig, device: int = 0, want_f32: bool = Tr
                                        None if f32 is None else _ptr(f32, C.c_float),
                                        None if u8 is None else _ptr(u8, C.c_uint8), cb, None, C.byref(stats)))
     return f32, u8, {k: getattr(stats, k) for k, _ in McRenderStats._fields_}
+
+
+def render_batch_multi(scenes: list[FlatScene], cfg: McConfig, n_devices: int, want_f32: bool = True, want_u8: bool = False):
+    """mcskin_cuda_render_batch_multi: a batch of skins, host scenes in, host images out, skin i on device i % n_devices.
+    Returns (f32 [n, H, W, 4] | None, u8 [n, H, W, 4] | None)."""
+    n, h, w = len(scenes), max(cfg.height, 0), max(cfg.width, 0)
+    f32 = np.zeros((n, h, w, 4), dtype=np.float32) if want_f32 else None
+    u8 = np.zeros((n, h, w, 4), dtype=np.uint8) if want_u8 else None
+    arr = (McScene * n)(*[s.as_c() for s in scenes])
+    _check(_lib.mcskin_cuda_render_batch_multi(arr, C.c_int32(n), C.byref(cfg), C.c_int32(n_devices),
+                                               None if f32 is None else _ptr(f32, C.c_float),
+                                               None if u8 is None else _ptr(u8, C.c_uint8)))
+    return f32, u8
 
 
 def render_tile(scene: FlatScene, cfg: McConfig, tile, image_f32: np.ndarray, device: int = 0) -> np.ndarray:

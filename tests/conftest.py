@@ -14,6 +14,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_report_header(config):
+    """Which parity bar the GPU tests apply on this host (tests/test_parity_gpu.py::_flip_budget)."""
+    try:
+        from tests.test_host_side import _host_has_fma
+        fma = _host_has_fma()
+    except Exception as exc:  # noqa: BLE001
+        return f"parity bar: unknown ({exc})"
+    return ("parity bar: BIT-EXACT float images (this host's glibc selects its FMA sinf/cosf/powf variants, the ones the device "
+            "functions restate)" if fma else
+            "parity bar: 8-bit RGBA within +-1 LSB on >= 99.9 % of pixels, shadow-ray flips <= 2e-3 (non-FMA glibc host: "
+            "sinf/cosf/powf differ in the last ulp from the device restatement)")
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """The CPU parity oracle (oracle/mcskin_oracle.c), built on demand."""

@@ -122,6 +122,12 @@ def _flip_budget():
     return 0.0 if _host_has_fma() else 2e-3
 
 
+@pytest.fixture(autouse=True)
+def _log_parity_bar(record_property):
+    """Every GPU test records which bar its float comparisons applied (junit property + the session header)."""
+    record_property("parity_bar", "bit-exact" if _flip_budget() == 0.0 else "within 1 LSB on >= 99.9 % of pixels")
+
+
 @pytest.mark.parametrize("samples", [2, 8, 64, 120])
 def test_soft_shadow(gpu, oracle, samples):
     scene = _scene(gpu, 1, "64x64", None)
@@ -568,3 +574,280 @@ def test_render_multi_in_process(gpu):
     multi, multi_u8, stats = gpu.render(scene, cfg, want_u8=True, multi_devices=n)
     assert np.array_equal(_bits(multi), _bits(single))
     assert stats["n_tiles"] == len(gpu.generate_tiles(96, 80, 32))
+
+
+# ---------------------------------------------------------------- tile sets (the multi-GPU split of one frame)
+def test_tile_sets_into_frame(gpu, oracle):
+    """render_tiles_into_frame: the cost-balanced tile sets of mcskin_partition_tiles, each rendered on its own
+    (as each GPU of a box does) into ONE full frame, reassemble the single-device frame bit for bit — for any
+    number of parts, listed in any order, through direct launches, graph capture and replay."""
+    import torch
+    scene = _scene(gpu, 8, "64x64", "running")
+    cfg = make_config(width=200, height=330, samples_per_pixel=4, max_bounces=3)
+    want, want_u8, _ = gpu.render(scene, cfg, want_u8=True)
+    n_tiles = len(gpu.generate_tiles(cfg.width, cfg.height, cfg.tile_size))
+    frame = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.float32, device="cuda:0")
+    frame_u8 = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.uint8, device="cuda:0")
+    rng = np.random.default_rng(5)
+    ctxs = []
+    try:
+        for world in (1, 3, 8):
+            parts = [gpu.partition_tiles(scene, cfg, world, r) for r in range(world)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n_tiles))
+            ctxs = [gpu.Context(0) for _ in range(world)]  # one context per part, like one per GPU
+            for c in ctxs:
+                c.set_scene(scene, cfg)
+            for rep in range(4):  # direct launches, graph capture, replay, then the same set listed in another order
+                frame.fill_(-1.0)
+                frame_u8.zero_()
+                torch.cuda.synchronize()
+                for r in range(world):
+                    tiles = parts[r] if rep < 3 else rng.permutation(parts[r])
+                    ctxs[r].render_tiles_into_frame(tiles, frame.data_ptr(), frame_u8.data_ptr(), 0)
+                    ctxs[r].sync()
+                assert np.array_equal(_bits(frame.cpu().numpy()), _bits(want)), (world, rep)
+                assert np.array_equal(frame_u8.cpu().numpy(), want_u8), (world, rep)
+            for c in ctxs:
+                c.close()
+            ctxs = []
+        # a tile set smaller than a frame touches nothing else; bad lists are refused
+        ctx = gpu.Context(0)
+        ctxs = [ctx]
+        ctx.set_scene(scene, cfg)
+        frame.fill_(-1.0)
+        torch.cuda.synchronize()
+        some = np.array([0, n_tiles - 1, n_tiles // 2], dtype=np.int32)
+        ctx.render_tiles_into_frame(some, frame.data_ptr(), 0, 0)
+        ctx.sync()
+        got = frame.cpu().numpy()
+        tiles = gpu.generate_tiles(cfg.width, cfg.height, cfg.tile_size)
+        mask = np.zeros((cfg.height, cfg.width), dtype=bool)
+        for t in tiles[some]:
+            mask[t["y"]:t["y"] + t["height"], t["x"]:t["x"] + t["width"]] = True
+        assert np.array_equal(_bits(got[mask]), _bits(want[mask])) and np.all(got[~mask] == -1.0)
+        with pytest.raises(gpu.McSkinError):
+            ctx.render_tiles_into_frame(np.array([1, 1], dtype=np.int32), frame.data_ptr(), 0, 0)
+        with pytest.raises(gpu.McSkinError):
+            ctx.render_tiles_into_frame(np.array([n_tiles], dtype=np.int32), frame.data_ptr(), 0, 0)
+        ctx.render_tiles_into_frame(np.zeros(0, dtype=np.int32), frame.data_ptr(), 0, 0)  # nothing to do
+        ctx.sync()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_tile_sets_chunked_and_all_active(gpu, oracle):
+    """The tile-set form through the alternative paths: a work-list budget that forces several chunks per set,
+    every pixel active, DOF (no screen rectangle: every tile may list pixels)."""
+    import torch
+    scene = _scene(gpu, 4, "64x64", "dab")
+    for over, opts in [
+        (dict(width=160, height=128, samples_per_pixel=4, max_bounces=2, tile_size=16), {"record_budget_bytes": 16 * 16 * 4 * 8 * 3}),
+        (dict(width=96, height=80, samples_per_pixel=2, max_bounces=2), {"force_all_active": 1}),
+        (dict(width=96, height=80, samples_per_pixel=4, max_bounces=2, dof_enabled=1, aperture=0.3), {}),
+        (dict(width=96, height=80, samples_per_pixel=4, max_bounces=1), {"wave_queue_pct": 10, "shade_mode": 0}),
+        (dict(width=96, height=80, samples_per_pixel=4, max_bounces=1), {"shade_mode": 1}),
+    ]:
+        cfg = make_config(**over)
+        want, _, _ = gpu.render(scene, cfg)
+        frame = torch.full((cfg.height, cfg.width, 4), -1.0, dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        for r in range(3):
+            ctx = gpu.Context(0)
+            try:
+                for k, v in opts.items():
+                    ctx.set_option(k, v)
+                ctx.set_scene(scene, cfg)
+                ctx.render_tiles_into_frame(gpu.partition_tiles(scene, cfg, 3, r), frame.data_ptr(), 0, 0)
+                ctx.sync()
+            finally:
+                ctx.close()
+        assert np.array_equal(_bits(frame.cpu().numpy()), _bits(want)), (over, opts)
+
+
+def test_host_frame_zero_copy(gpu, oracle):
+    """mcskin_cuda_host_register: kernels store their tiles straight into a page-locked host image (what every
+    rank of a box does with one shared-memory frame); the image equals the frame rendered into device memory."""
+    scene = _scene(gpu, 2, "legacy", "walking")
+    cfg = make_config(width=224, height=160, samples_per_pixel=4, max_bounces=2)
+    want, _, _ = gpu.render(scene, cfg)
+    host = np.full((cfg.height, cfg.width, 4), -1.0, dtype=np.float32)
+    dptr = gpu.host_register(host)
+    ctx = gpu.Context(0)
+    try:
+        ctx.set_scene(scene, cfg)
+        for r in range(2):
+            ctx.render_tiles_into_frame(gpu.partition_tiles(scene, cfg, 2, r), dptr, 0, 0)
+            ctx.sync()
+        assert np.array_equal(_bits(host), _bits(want))
+    finally:
+        ctx.close()
+        gpu.host_unregister(host)
+
+
+# ---------------------------------------------------------------- BASELINE configs 3, 4, 5 against the reference
+def _reference_tiles(checker, scene, cfg, tile_ids, threads=16):
+    """The listed tiles (frame tile indices) rendered by the CPU checker's renderTile, in parallel (the calls
+    release the GIL); returns {tile id: (tile record, float pixels of the tile)}."""
+    from concurrent.futures import ThreadPoolExecutor
+    tiles = checker.generate_tiles(cfg.width, cfg.height, cfg.tile_size)
+
+    def one(i):
+        t = tiles[i]
+        image = np.zeros((cfg.height, cfg.width, 4), dtype=np.float32)
+        image = checker.render_tile(scene, cfg, (t["x"], t["y"], t["width"], t["height"]), image)
+        return i, t, image[t["y"]:t["y"] + t["height"], t["x"]:t["x"] + t["width"]].copy()
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        return {i: (t, px) for i, t, px in pool.map(one, tile_ids)}
+
+
+@pytest.mark.parametrize("name,seed,kind,over,picks", [
+    # figure tiles (head, torso + arms, legs), a background tile, the clipped bottom-right corner tile
+    ("C3", 3, "slim", dict(width=3840, height=2160, samples_per_pixel=16, max_bounces=4),
+     [(60, 20), (58, 33), (61, 34), (59, 46), (0, 0), (119, 67)]),
+    ("C5", 5, "64x64", dict(width=7680, height=4320, samples_per_pixel=64, max_bounces=8),
+     [(120, 40), (117, 67), (122, 92), (0, 0), (239, 134)]),
+], ids=["C3", "C5"])
+def test_baseline_c3_c5_tiles_against_reference(gpu, oracle, name, seed, kind, over, picks):
+    """BASELINE.json configs[2] (4K, slim skin, 16 spp) and configs[4] (8K, 64 spp, 8 bounces): the WHOLE frame
+    on the GPU — 8K goes through the chunked-frame path — and a fixed crop of its tiles against
+    TileRenderer::renderTile of the unmodified reference (the C restatement when its library did not travel),
+    SURVEY.md §8d: the CPU side of a whole 8K frame would take ~20 minutes."""
+    from oracle.harness import Reference
+    scene = _scene(gpu, seed, kind, None)
+    cfg = make_config(**over)
+    tiles_x = (cfg.width + cfg.tile_size - 1) // cfg.tile_size
+    ids = [ty * tiles_x + tx for tx, ty in picks]
+    checker = Reference.load() or oracle
+    want = _reference_tiles(checker, scene, cfg, ids)
+    got, _, stats = gpu.render(scene, cfg)
+    for i in ids:
+        t, px = want[i]
+        mine = got[t["y"]:t["y"] + t["height"], t["x"]:t["x"] + t["width"]]
+        rep = pixel_report(mine, px, oracle.quantize)
+        assert rep["within1"] >= 0.999, (name, i, rep)
+        if _flip_budget() == 0.0:
+            assert np.array_equal(_bits(mine), _bits(px)), (name, i, rep)
+    assert stats["n_active_pixels"] > 0.03 * cfg.width * cfg.height
+    # the same frame again from cost-balanced tile sets (what N GPUs render)
+    import torch
+    frame = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.float32, device="cuda:0")
+    ctx = gpu.Context(0)
+    try:
+        ctx.set_scene(scene, cfg)
+        for r in range(4):
+            ctx.render_tiles_into_frame(gpu.partition_tiles(scene, cfg, 4, r), frame.data_ptr(), 0, 0)
+            ctx.sync()
+        assert torch.equal(frame.cpu().view(torch.int32), torch.from_numpy(got).view(torch.int32)), name
+    finally:
+        ctx.close()
+
+
+def test_baseline_c4_skins_against_reference(gpu, oracle):
+    """BASELINE.json configs[3]: skins 0..15 of the batch (256x256, 4 spp, 2 bounces) rendered as ONE batch on the
+    GPU, each against the unmodified reference's whole frame."""
+    import torch
+    from oracle.harness import Reference
+    n = 16
+    cfg = make_config(width=256, height=256, samples_per_pixel=4, max_bounces=2)
+    scenes = [_scene(gpu, i) for i in range(n)]
+    checker = Reference.load() or oracle
+    ctx = gpu.Context(0)
+    try:
+        out = torch.zeros((n, 256, 256, 4), dtype=torch.float32, device="cuda:0")
+        out_u8 = torch.zeros((n, 256, 256, 4), dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        ctx.render_batch(scenes, cfg, out.data_ptr(), out_u8.data_ptr(), 0)
+        ctx.sync()
+        got, got_u8 = out.cpu().numpy(), out_u8.cpu().numpy()
+    finally:
+        ctx.close()
+    for i in range(n):
+        want = checker.render(scenes[i], cfg)
+        rep = pixel_report(got[i], want, oracle.quantize)
+        assert rep["within1"] >= 0.999, (i, rep)
+        if _flip_budget() == 0.0:
+            assert np.array_equal(_bits(got[i]), _bits(want)), (i, rep)
+        assert np.array_equal(got_u8[i], oracle.quantize(got[i])), i
+
+
+# ---------------------------------------------------------------- more than one device in one process
+def _need_devices(gpu, n):
+    if gpu.device_count() < n:
+        pytest.skip(f"needs {n} CUDA devices in this process (have {gpu.device_count()})")
+
+
+@pytest.mark.parametrize("over", [
+    dict(width=200, height=170, samples_per_pixel=4, max_bounces=3),
+    dict(width=200, height=170, samples_per_pixel=8, max_bounces=2),                      # the generic pixel-per-lane kernel
+    dict(width=160, height=128, samples_per_pixel=4, max_bounces=2, dof_enabled=1, aperture=0.3),
+], ids=["spp4", "spp8", "dof"])
+def test_render_multi_two_devices(gpu, oracle, over):
+    """mcskin_cuda_render_multi over two (and all) devices of this process: every device has its own context,
+    shared-memory opt-in and tile rows; the frame equals the one-device frame and the oracle's."""
+    _need_devices(gpu, 2)
+    scene = _scene(gpu, 3, "64x64", "running")
+    cfg = make_config(**over)
+    single, _, _ = gpu.render(scene, cfg)
+    for n in sorted({2, gpu.device_count()}):
+        multi, multi_u8, stats = gpu.render(scene, cfg, want_u8=True, multi_devices=n)
+        assert np.array_equal(_bits(multi), _bits(single)), n
+        assert np.array_equal(multi_u8, oracle.quantize(single)), n
+    assert pixel_report(single, oracle.render(scene, cfg), oracle.quantize)["within1"] >= 0.999
+
+
+def test_tile_sets_over_peer_memory(gpu, oracle):
+    """Two devices of one process: device 1 stores its tile set straight into device 0's frame (peer access),
+    the flags of the peer-store exchange order the root's read after it; the frame equals one device's."""
+    _need_devices(gpu, 2)
+    import torch
+    if not torch.cuda.can_device_access_peer(1, 0):
+        pytest.skip("no peer access between devices 0 and 1")
+    scene = _scene(gpu, 6, "64x64", "walking")
+    cfg = make_config(width=320, height=256, samples_per_pixel=4, max_bounces=3)
+    want, _, _ = gpu.render(scene, cfg)
+    frame = torch.full((cfg.height * cfg.width * 4 + 1024,), -1.0, dtype=torch.float32, device="cuda:0")
+    flags = frame[cfg.height * cfg.width * 4:].view(torch.int32)
+    flags.zero_()
+    torch.cuda.synchronize(0)
+    with torch.cuda.device(1):
+        torch.zeros(1, device="cuda:1")  # peer access is enabled lazily by torch on first cross-device use
+        torch.cuda.synchronize(1)
+    ctxs = [gpu.Context(0), gpu.Context(1)]
+    try:
+        # torch enables peer access between the devices it has touched when a copy needs it
+        probe = torch.empty(4, device="cuda:1")
+        probe.copy_(frame[:4])
+        torch.cuda.synchronize(1)
+        for epoch in (1, 2, 3):
+            for d in (0, 1):
+                ctxs[d].set_scene(scene, cfg)
+                ctxs[d].render_tiles_into_frame(gpu.partition_tiles(scene, cfg, 2, d), frame.data_ptr(), 0, 0)
+            gpu.peer_signal(1, flags.data_ptr() + 4, epoch, 0)  # NB: stream 0 of device 1 = the context's own stream
+            ctxs[1].sync()
+            gpu.peer_wait(0, flags.data_ptr() + 4, 1, epoch, 0, 0)
+            ctxs[0].sync()
+            torch.cuda.synchronize(0)
+            got = frame[:cfg.height * cfg.width * 4].view(cfg.height, cfg.width, 4).cpu().numpy()
+            assert np.array_equal(_bits(got), _bits(want)), epoch
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_batch_sharded_by_skin_over_devices(gpu, oracle):
+    """mcskin_cuda_render_batch_multi: a batch sharded by skin over every device of this process (1 on the
+    single-GPU test box, where it still runs the chunked host-to-host pipeline; more on a multi-GPU box),
+    each image equal to the single render's bits."""
+    n = 37
+    cfg = make_config(width=64, height=48, samples_per_pixel=4, max_bounces=2)
+    scenes = [_scene(gpu, 200 + i, "legacy" if i % 7 == 0 else "64x64", [None, "walking"][i % 2]) for i in range(n)]
+    for devices in sorted({1, gpu.device_count()}):
+        f32, u8 = gpu.render_batch_multi(scenes, cfg, devices, want_u8=True)
+        for i in (0, 1, 7, 18, 35, 36):
+            single, _, _ = gpu.render(scenes[i], cfg)
+            assert np.array_equal(_bits(f32[i]), _bits(single)), (devices, i)
+        assert np.array_equal(u8, oracle.quantize(f32)), devices
+    with pytest.raises(gpu.McSkinError):
+        gpu.render_batch_multi(scenes, cfg, gpu.device_count() + 1)
