@@ -219,6 +219,9 @@ class FrameJob:
         self.exchange = exchange if world > 1 else "none"
         self.peer = None
         self.tiles = None
+        self.diag = os.environ.get("MCSKIN_BENCH_DIAG", "")  # "local" / "nofence": see step()
+        if self.diag == "local":
+            self.local_frame = torch.zeros((self.H, self.W, 4), dtype=torch.float32, device=self.dev)
         if self.split > 1 and self.exchange != "gather":
             part = int(os.environ.get("MCSKIN_BENCH_PART", "0")) if emulate > 1 else rank
             self.tiles = lib.partition_tiles(scene, cfg, self.split, part)
@@ -255,6 +258,10 @@ class FrameJob:
         if self.exchange == "gather":
             self.ctx.render_bands(self.rank, self.world, self.band.data_ptr(), 0, self.stream.cuda_stream)
             self.bands.gather_frame(self.band, self.frame, self.ts, self.gathered, self.row_index)
+        elif self.diag == "local":      # diagnosis only: every rank into a frame of its own, no exchange at all
+            self.render_into(self.local_frame.data_ptr())
+        elif self.diag == "nofence":    # diagnosis only: peer stores without the barrier
+            self.render_into(self.frame_ptr)
         else:
             self.render_into(self.frame_ptr)
             if self.peer is not None:
@@ -269,7 +276,8 @@ class FrameJob:
 def time_steps(torch, dist, job, flush, steps, warmup, world, dev):
     """W warm-up + K timed steps: CUDA events on the job's stream around every step, an L2 flush before each,
     barrier + synchronize on both sides, max over ranks.  Returns (ms per step, library stats of the last frame,
-    sum of the library's own event times, wall-clock window of the timed loop)."""
+    ms of this rank's launches per frame — the timed events themselves on one GPU, without the exchange step at
+    N>1 —, wall-clock window of the timed loop)."""
     for i in range(warmup):
         flush.fill_(1)
         job.step()
@@ -280,23 +288,35 @@ def time_steps(torch, dist, job, flush, steps, warmup, world, dev):
     torch.cuda.synchronize(dev)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-    device_ms = 0.0
-    st = None
     w0 = time.time()
+    # Every step is queued without a host round trip in between (a rank that synchronised with its host after each frame
+    # would start the next one late, and the root, whose queue is already full, would count that as exchange time).
     for i in range(steps):
         flush.fill_(i & 0xff)  # L2 flush between timed iterations (outside the timed events)
         starts[i].record(job.stream)
         job.step()
         ends[i].record(job.stream)
-        st = job.ctx.sync()  # the library's own events around this frame's launches (blocks on the frame; the next flush follows anyway)
-        device_ms += st["ms_device"]
     torch.cuda.synchronize(dev)
     w1 = time.time()
+    st = job.ctx.sync()
     if world > 1:
         dist.barrier()
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    if world > 1:
+        # this rank's launches without the exchange step: one more frame on its own, the library's events around it
+        flush.fill_(1)
+        job.render_local()
+        device_ms = job.ctx.sync()["ms_device"] * steps
+    else:
+        device_ms = total_ms  # one GPU: the step IS the frame's launches
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
+        if os.environ.get("MCSKIN_BENCH_VERBOSE"):  # per-rank view: event time of the step, the library's own kernel time
+            mine = torch.tensor([total_ms / steps, device_ms / steps], dtype=torch.float64, device=dev)
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            if dist.get_rank() == 0:
+                print("per-rank ms (step, kernels): " + "  ".join(f"{float(e[0]):.4f}/{float(e[1]):.4f}" for e in every), file=sys.stderr)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item()) / steps, st, device_ms / steps, (w0, w1)
 

@@ -215,6 +215,9 @@ int32_t mcskin_cuda_ipc_close(int32_t device, void* ptr);
  * wait holds `stream` until each of the n 32-bit flags is >= value (acquire), or ~2 s have passed
  * (then *d_timeout, if given, is set to 1 and the stream continues: no device hang on a dead peer). */
 int32_t mcskin_cuda_peer_signal(int32_t device, void* d_flag, uint32_t value, void* stream);
+/* One process driving several devices: lets kernels on `device` address memory allocated on `peer` (frames opened
+ * with mcskin_cuda_ipc_open need no such call). */
+int32_t mcskin_cuda_enable_peer_access(int32_t device, int32_t peer);
 int32_t mcskin_cuda_peer_wait(int32_t device, const void* d_flags, int32_t n, uint32_t value, void* d_timeout, void* stream);
 /* Blocks until the context's work is done, fills stats of the last render. */
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats);

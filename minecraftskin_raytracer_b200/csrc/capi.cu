@@ -1110,6 +1110,21 @@ int32_t mcskin_cuda_ipc_close(int32_t device, void* ptr) {
     return MC_OK;
 }
 
+int32_t mcskin_cuda_enable_peer_access(int32_t device, int32_t peer) {
+    if (device == peer) return MC_OK;
+    CU_TRY(cudaSetDevice(device));
+    int can = 0;
+    CU_TRY(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return fail(MC_ERR_INVALID, "enable_peer_access: device " + std::to_string(device) + " cannot access device " + std::to_string(peer));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return MC_OK;
+    }
+    CU_TRY(e);
+    return MC_OK;
+}
+
 int32_t mcskin_cuda_peer_signal(int32_t device, void* dFlag, uint32_t value, void* stream) {
     if (!dFlag) return fail(MC_ERR_INVALID, "peer_signal: null flag");
     CU_TRY(cudaSetDevice(device));

@@ -38,6 +38,7 @@ EXPORTS = [
     "mcskin_cuda_ipc_close", "mcskin_cuda_fp32_issue_peak", "mcskin_cuda_peer_signal", "mcskin_cuda_peer_wait",
     "mcskin_primary_launch_order", "mcskin_cuda_context_render_tiles_into_frame", "mcskin_partition_tiles",
     "mcskin_cuda_host_register", "mcskin_cuda_host_unregister", "mcskin_cuda_render_batch_multi",
+    "mcskin_cuda_enable_peer_access",
 ]
 
 
@@ -225,6 +226,11 @@ def ipc_open(device: int, handle: bytes) -> int:
     p = C.c_void_p()
     _check(_lib.mcskin_cuda_ipc_open(C.c_int32(device), h, C.byref(p)))
     return int(p.value)
+
+
+def enable_peer_access(device: int, peer: int):
+    """Kernels on `device` may address memory allocated on `peer` afterwards (one process, several devices)."""
+    _check(_lib.mcskin_cuda_enable_peer_access(C.c_int32(device), C.c_int32(peer)))
 
 
 def peer_signal(device: int, d_flag: int, value: int, stream: int = 0):

@@ -811,15 +811,9 @@ def test_tile_sets_over_peer_memory(gpu, oracle):
     flags = frame[cfg.height * cfg.width * 4:].view(torch.int32)
     flags.zero_()
     torch.cuda.synchronize(0)
-    with torch.cuda.device(1):
-        torch.zeros(1, device="cuda:1")  # peer access is enabled lazily by torch on first cross-device use
-        torch.cuda.synchronize(1)
+    gpu.enable_peer_access(1, 0)   # kernels on device 1 may store to device 0's memory
     ctxs = [gpu.Context(0), gpu.Context(1)]
     try:
-        # torch enables peer access between the devices it has touched when a copy needs it
-        probe = torch.empty(4, device="cuda:1")
-        probe.copy_(frame[:4])
-        torch.cuda.synchronize(1)
         for epoch in (1, 2, 3):
             for d in (0, 1):
                 ctxs[d].set_scene(scene, cfg)
