@@ -189,6 +189,11 @@ int32_t mcskin_cuda_context_render_rows_into_frame(McContext* ctx, int32_t first
  * straight into the root's frame (peer memory) or into one page-locked host frame (mcskin_cuda_host_register). */
 int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_t* tiles, int32_t n_tiles,
                                                      void* d_frame_f32, void* d_frame_u8, void* stream);
+/* The per-frame call of a host that keeps the scene on the CPU: set_scene (upload) + render_tiles_into_frame on
+ * the context's own stream + wait.  *ms_device (may be null): the frame's kernels, CUDA events.  Blocking. */
+int32_t mcskin_cuda_context_render_scene_tiles(McContext* ctx, const McScene* scene, const McConfig* cfg,
+                                                const int32_t* tiles, int32_t n_tiles, void* d_frame_f32, void* d_frame_u8,
+                                                float* ms_device);
 /* Deals the tiles of a frame to n_parts renderers so that every part costs about the same: tiles are weighted
  * by how much of them the figure's screen rectangles cover (covered pixels cost ~50x a background pixel) and
  * dealt greedily, heaviest first, to the least loaded part; deterministic, the parts are disjoint and cover the

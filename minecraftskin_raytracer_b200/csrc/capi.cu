@@ -1057,6 +1057,25 @@ int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_
     return render_bands(ctx, 0, 1, static_cast<float4*>(dFrameF32), static_cast<uchar4*>(dFrameU8), s, true, &spec);
 }
 
+// One blocking call per frame and rank for hosts that hold the scene on the CPU: upload, this rank's tiles
+// rendered into the (host- or peer-resident) frame, wait.  What bench.py's multi-GPU e2e step calls.
+int32_t mcskin_cuda_context_render_scene_tiles(McContext* ctx, const McScene* scene, const McConfig* cfg, const int32_t* tiles,
+                                                int32_t nTiles, void* dFrameF32, void* dFrameU8, float* msDevice) {
+    if (!ctx) return fail(MC_ERR_INVALID, "render_scene_tiles: null context");
+    int rc = mcskin_cuda_context_set_scene(ctx, scene, cfg);
+    if (rc != MC_OK) return rc;
+    rc = mcskin_cuda_context_render_tiles_into_frame(ctx, tiles, nTiles, dFrameF32, dFrameU8, nullptr);
+    if (rc != MC_OK) return rc;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    for (McContext* lane : ctx->lanes) CU_TRY(cudaStreamSynchronize(lane->stream));
+    CU_TRY(cudaGetLastError());
+    if (msDevice) {
+        *msDevice = 0.0f;
+        if (nTiles > 0) CU_TRY(cudaEventElapsedTime(msDevice, ctx->ev0, ctx->ev1));
+    }
+    return MC_OK;
+}
+
 int32_t mcskin_cuda_host_register(void* hostPtr, uint64_t bytes, void** dPtr) {
     if (!hostPtr || bytes == 0) return fail(MC_ERR_INVALID, "host_register: null or empty range");
     CU_TRY(cudaHostRegister(hostPtr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));

@@ -38,7 +38,7 @@ EXPORTS = [
     "mcskin_cuda_ipc_close", "mcskin_cuda_fp32_issue_peak", "mcskin_cuda_peer_signal", "mcskin_cuda_peer_wait",
     "mcskin_primary_launch_order", "mcskin_cuda_context_render_tiles_into_frame", "mcskin_partition_tiles",
     "mcskin_cuda_host_register", "mcskin_cuda_host_unregister", "mcskin_cuda_render_batch_multi",
-    "mcskin_cuda_enable_peer_access",
+    "mcskin_cuda_enable_peer_access", "mcskin_cuda_context_render_scene_tiles",
 ]
 
 
@@ -134,14 +134,14 @@ def build_skin_scene(atlas: np.ndarray, pose=None) -> FlatScene:
 
 
 # ---------------------------------------------------------------- whole-frame calls
-def render(scene: FlatScene, cfg: McConfig, device: int = 0, want_f32: bool = True, want_u8: bool = False,
+def render(scene, cfg: McConfig, device: int = 0, want_f32: bool = True, want_u8: bool = False,
            progress=None, multi_devices: int = 0, out_f32: np.ndarray | None = None, out_u8: np.ndarray | None = None):
     """mcskin_cuda_render: host scene in, host image(s) out.  Returns (f32|None, u8|None, stats dict).
 
+    scene: a FlatScene, or its C view (FlatScene.as_c(), for callers that render the same scene object again and again).
     out_f32 / out_u8: caller-owned [H, W, 4] arrays to render into (reused across frames; page-locked
     arrays, e.g. numpy views of torch pin_memory tensors, are filled by DMA without a staging copy)."""
     h, w = max(cfg.height, 0), max(cfg.width, 0)
-    n_tiles = len(generate_tiles(cfg.width, cfg.height, cfg.tile_size)) if (w and h) else 0
 
     def _buffer(given, want, dtype, one):
         if given is not None:
@@ -151,6 +151,7 @@ def render(scene: FlatScene, cfg: McConfig, device: int = 0, want_f32: bool = Tr
         if not want:
             return None
         buf = np.empty((h, w, 4), dtype=dtype)
+        n_tiles = len(generate_tiles(cfg.width, cfg.height, cfg.tile_size)) if (w and h) else 0
         if n_tiles == 0 and buf.size:  # nothing is rendered: Image(w,h) pixels stay (0,0,0,1) (image.h:15, color.h:8)
             buf[...] = 0
             buf[..., 3] = one
@@ -159,7 +160,7 @@ def render(scene: FlatScene, cfg: McConfig, device: int = 0, want_f32: bool = Tr
     f32 = _buffer(out_f32, want_f32, np.float32, 1.0)
     u8 = _buffer(out_u8, want_u8, np.uint8, 255)
     stats = McRenderStats()
-    cs = scene.as_c()
+    cs = scene.as_c() if isinstance(scene, FlatScene) else scene
     if multi_devices and multi_devices > 0:
         _check(_lib.mcskin_cuda_render_multi(C.byref(cs), C.byref(cfg), C.c_int32(multi_devices),
                                              None if f32 is None else _ptr(f32, C.c_float),
@@ -322,6 +323,17 @@ class Context:
         _check(_lib.mcskin_cuda_context_render_tiles_into_frame(self._h, _ptr(tiles, C.c_int32), C.c_int32(len(tiles)),
                                                                 C.c_void_p(d_frame_f32 or None), C.c_void_p(d_frame_u8 or None),
                                                                 C.c_void_p(stream or None)))
+
+    def render_scene_tiles(self, scene: FlatScene, cfg: McConfig, tiles: np.ndarray, d_frame_f32: int = 0, d_frame_u8: int = 0) -> float:
+        """Blocking: upload the scene, render these tiles into the frame, wait.  Returns the kernels' milliseconds.
+        `scene` may be a FlatScene or its cached C view (FlatScene.as_c())."""
+        cs = scene.as_c() if isinstance(scene, FlatScene) else scene
+        ms = C.c_float(0.0)
+        _check(_lib.mcskin_cuda_context_render_scene_tiles(self._h, C.byref(cs), C.byref(cfg), _ptr(tiles, C.c_int32),
+                                                           C.c_int32(len(tiles)), C.c_void_p(d_frame_f32 or None),
+                                                           C.c_void_p(d_frame_u8 or None), C.byref(ms)))
+        self.cfg = cfg
+        return float(ms.value)
 
     def render_batch(self, scenes: list[FlatScene], cfg: McConfig, d_out_f32: int = 0, d_out_u8: int = 0, stream: int = 0):
         """Asynchronous: scene i -> image i of the [n, H, W, 4] device buffer(s) (one skin per scene, same config)."""

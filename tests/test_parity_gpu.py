@@ -680,6 +680,13 @@ def test_host_frame_zero_copy(gpu, oracle):
             ctx.render_tiles_into_frame(gpu.partition_tiles(scene, cfg, 2, r), dptr, 0, 0)
             ctx.sync()
         assert np.array_equal(_bits(host), _bits(want))
+        # the one-call form (upload + tiles + wait) a host with a CPU-side scene uses per frame
+        host[...] = -1.0
+        c_scene = scene.as_c()
+        for r in range(2):
+            ms = ctx.render_scene_tiles(c_scene, cfg, gpu.partition_tiles(scene, cfg, 2, r), dptr, 0)
+            assert ms > 0.0
+        assert np.array_equal(_bits(host), _bits(want))
     finally:
         ctx.close()
         gpu.host_unregister(host)
