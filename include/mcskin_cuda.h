@@ -224,6 +224,10 @@ int32_t mcskin_cuda_peer_signal(int32_t device, void* d_flag, uint32_t value, vo
  * with mcskin_cuda_ipc_open need no such call). */
 int32_t mcskin_cuda_enable_peer_access(int32_t device, int32_t peer);
 int32_t mcskin_cuda_peer_wait(int32_t device, const void* d_flags, int32_t n, uint32_t value, void* d_timeout, void* stream);
+/* Diagnosis: with the option "debug_primary_timing" (one lane, no graph) the blocks of the pixel-per-lane primary
+ * kernels record when they ran: 4 words per block (entry ns, exit ns, frame tile, part | parts << 16; zeros for
+ * blocks that had nothing to do).  Returns the number of records of the last launch. */
+int32_t mcskin_cuda_context_debug_block_times(McContext* ctx, uint64_t* out, int32_t capacity);
 /* Blocks until the context's work is done, fills stats of the last render. */
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats);
 /* Tuning / test knobs (every combination renders the same bits; INTEGRATION.md §6 has the table):

@@ -93,6 +93,9 @@ struct McContext {
     DevBuf count, slotPixel, records;
     DevBuf imgF32, imgU8, scratchIn, scratchOut;
     DevBuf tileStates;           // seeded mt19937 state of every tile of a chunk
+    DevBuf blockTimes;           // "debug_primary_timing": 4 words per block of the last primary launch
+    int debugPrimaryTiming = 0;
+    int blockTimesCount = 0;
     DevBuf tileMap;              // render_tiles_into_frame: frame tile indices, heavy tiles first
     std::vector<int32_t> tileMapHost, tileMapOrdered;
     unsigned long long tileMapVersion = 0;
@@ -333,6 +336,13 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
         BandView band{};
         band.out_f32 = outF32;
         band.out_u8 = outU8;
+        if (ctx->debugPrimaryTiming && nChunks == 1) {  // room for the finest split: one block per 256-pixel round of every tile
+            const size_t blocks = static_cast<size_t>(nTilesAll) * ((tilePixels + kBlockThreads - 1) / kBlockThreads);
+            CU_TRY(ctx->blockTimes.reserve(blocks * 4 * sizeof(unsigned long long)));
+            CU_TRY(cudaMemsetAsync(ctx->blockTimes.p, 0, blocks * 4 * sizeof(unsigned long long), stream));
+            band.block_times = static_cast<unsigned long long*>(ctx->blockTimes.p);
+            ctx->blockTimesCount = static_cast<int>(blocks);
+        }
         size_t listing = units;
         if (mapped) {
             band.tile_map = spec.map + unit0;
@@ -917,7 +927,8 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->boxes, &ctx->texels, &ctx->count, &ctx->slotPixel, &ctx->records, &ctx->imgF32, &ctx->imgU8,
-                      &ctx->scratchIn, &ctx->scratchOut, &ctx->countLog, &ctx->wave, &ctx->tileStates, &ctx->tileMap})
+                      &ctx->scratchIn, &ctx->scratchOut, &ctx->countLog, &ctx->wave, &ctx->tileStates, &ctx->tileMap,
+                      &ctx->blockTimes})
         b->release();
     ctx->pinned.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -952,6 +963,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "batch_group") ctx->batchGroup = static_cast<int>(std::min<int64_t>(4096, std::max<int64_t>(1, value)));
     else if (k == "batch_mode") ctx->batchMode = value != 0;
     else if (k == "shade_mode") ctx->shadeMode = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
+    else if (k == "debug_primary_timing") ctx->debugPrimaryTiming = value != 0;
     else if (k == "wave_queue_pct") ctx->waveQueuePct = static_cast<int>(std::min<int64_t>(100000, std::max<int64_t>(0, value)));
     else if (k == "frame_lanes") ctx->frameLanes = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(1, value)));
     else if (k == "cache_tile_seeds") ctx->cacheTileSeeds = value != 0;
@@ -1158,6 +1170,17 @@ int32_t mcskin_cuda_peer_wait(int32_t device, const void* dFlags, int32_t n, uin
                      static_cast<cudaStream_t>(stream));
     CU_TRY(cudaGetLastError());
     return MC_OK;
+}
+
+// diagnosis: (entry ns, exit ns, frame tile, part | parts << 16) of every block of the last primary launch of a
+// context rendered with "debug_primary_timing" (one lane, no graph); returns the number of records
+int32_t mcskin_cuda_context_debug_block_times(McContext* ctx, uint64_t* out, int32_t capacity) {
+    if (!ctx || capacity < 0) return fail(MC_ERR_INVALID, "debug_block_times: bad argument");
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaDeviceSynchronize());
+    const int n = std::min(ctx->blockTimesCount, capacity);
+    if (out && n > 0) CU_TRY(cudaMemcpy(out, ctx->blockTimes.p, static_cast<size_t>(n) * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return ctx->blockTimesCount;
 }
 
 int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats) {

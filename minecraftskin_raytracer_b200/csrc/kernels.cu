@@ -597,6 +597,30 @@ __global__ void k_tile_seed(const DevFrame fr, const BandView band, uint32_t* st
 
 extern __shared__ __align__(16) unsigned char g_pixSmem[];  // [PixStreamSmem][scene blob]
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// diagnosis: when and for which tile a block of the primary pass ran (BandView::block_times)
+struct BlockTimer {
+    unsigned long long* slot;
+    __device__ __forceinline__ BlockTimer(const BandView& band, const DevFrame& fr, const TileGeom& tg, int part, int parts)
+        : slot(band.block_times ? band.block_times + 4ull * (blockIdx.x + static_cast<unsigned long long>(blockIdx.y) * gridDim.x) : nullptr) {
+        if (slot && threadIdx.x == 0) {
+            slot[0] = global_timer_ns();
+            slot[2] = static_cast<unsigned long long>((tg.y / fr.tile_size) * fr.tiles_x + tg.x / fr.tile_size);
+            slot[3] = static_cast<unsigned long long>(part) | (static_cast<unsigned long long>(parts) << 16);
+        }
+    }
+    __device__ __forceinline__ void stop() const {  // all threads call: the block's time is its slowest warp's
+        if (slot) {
+            __syncthreads();
+            if (threadIdx.x == 0) slot[1] = global_timer_ns();
+        }
+    }
+};
+
 template <bool BATCH>
 __global__ void __launch_bounds__(kBlockThreads)
 k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, const ActiveList list_,
@@ -727,6 +751,14 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
     const BandView& band = BATCH ? batch[blockIdx.y].band : band_;
     const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
     constexpr int kRing = (kBlockThreads * kWords + kMtN + 31) / 32 * 32;  // one round + one engine block
+    __shared__ struct {
+        unsigned int n;                       // open pixels of this round
+        unsigned int mask[kBlockThreads];     // their box masks, by thread
+        unsigned char pixel[kBlockThreads];   // compacted: the threads that own them
+        unsigned char hit[kBlockThreads];     // by thread: some pooled sample hit
+    } coop;
+    static_assert(kBlockThreads <= 256, "open pixels are indexed with a byte");
+    if (threadIdx.x == 0) coop.n = 0u;        // (several barriers follow before the first use)
     using Smem = PixStreamSmemT<kRing>;
     Smem* mt = reinterpret_cast<Smem*>(g_pixSmem);
     unsigned char* sceneSmem = g_pixSmem + ((sizeof(Smem) + 15) & ~size_t(15));
@@ -738,6 +770,7 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
     const TileGeom tg = tile_geom(fr, band, tileIndex);
     const int nPix = tg.w * tg.h;
     if (part * kBlockThreads >= nPix) return;
+    const BlockTimer timer(band, fr, tg, part, parts);
 
     const bool tileCanHit = !fr.rect_valid || !(tg.x > fr.rect_x1 || tg.x + tg.w - 1 < fr.rect_x0 ||
                                                 tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
@@ -811,13 +844,51 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
         bool hit = false;
         // the boxes whose own screen rectangle holds this pixel (none: no ray at all)
         const uint32_t boxMask = pixelCanHit ? pixel_box_mask(sc, px, py) : 0u;
-        if (boxMask) {
-            for (int s = 0; s < SPP && !hit; ++s) {
-                const float u = div_by_size(fx + draws[2 * s], W, rW);
-                const float v = div_by_size(fy + draws[2 * s + 1], H, rH);
-                const Ray ray = camera_ray(fr, u, v);
-                hit = sc.rect ? any_hit_among(sc, ray, boxMask) : (!misses_cull_box(fr, ray) && any_hit(sc, ray));
+        // does sample s of the pixel at (x, y) with draws d hit any box of `mask`?
+        auto sample_hits = [&](float x, float y, const float* d, int s, uint32_t mask) {
+            const float u = div_by_size(x + d[2 * s], W, rW);
+            const float v = div_by_size(y + d[2 * s + 1], H, rH);
+            const Ray ray = camera_ray(fr, u, v);
+            return sc.rect ? any_hit_among(sc, ray, mask) : (!misses_cull_box(fr, ray) && any_hit(sc, ray));
+        };
+        if (tileCanHit) {  // (block-uniform)
+            // "Does ANY sample of the pixel hit?" is an OR: the order of the tests is free.  The owning lane tests
+            // sample 0, which settles nearly every pixel of the figure.  The pixels it leaves open are the
+            // expensive ones — rays that graze a box or pass through the holes of an outer layer miss sample
+            // after sample, each with full face / texel evaluations — and a lane that walked all SPP of them
+            // alone was the longest chain of the whole pass (65 us in one warp of an eighth of the frame, whose
+            // other blocks were done after 40).  So the block pools them: open pixels are compacted in shared
+            // memory and their remaining (pixel, sample) pairs are dealt to all 256 threads.
+            if (boxMask) hit = sample_hits(fx, fy, draws, 0, boxMask);
+            const bool open = boxMask != 0u && !hit;
+            coop.hit[tid] = 0;
+            const unsigned int openMask = __ballot_sync(kFullMask, open);
+            if (openMask) {
+                unsigned int base = 0u;
+                if (lane == 0) base = atomicAdd(&coop.n, static_cast<unsigned int>(__popc(openMask)));
+                base = __shfl_sync(kFullMask, base, 0);
+                if (open) {
+                    coop.pixel[base + __popc(openMask & ((1u << lane) - 1u))] = static_cast<unsigned char>(tid);
+                    coop.mask[tid] = boxMask;
+                }
             }
+            __syncthreads();
+            const int nOpen = static_cast<int>(coop.n);
+            const int items = nOpen * (SPP - 1);
+            for (int w = tid; w < items; w += kBlockThreads) {
+                const int k = w / (SPP - 1);
+                const int smp = 1 + (w - k * (SPP - 1));
+                const int p = coop.pixel[k];
+                if (*reinterpret_cast<volatile unsigned char*>(&coop.hit[p])) continue;  // settled meanwhile (a stale 0 only costs a test)
+                const int qp = q0 + p;
+                const int yy = wPow2 ? (qp >> lgW) : (qp / tg.w);
+                const int xx = qp - yy * tg.w;
+                const float* dp = mt->ring + pix_ring_slot_mod<kRing>(roundMod + static_cast<unsigned int>(p) * kWords);
+                if (sample_hits(static_cast<float>(tg.x + xx), static_cast<float>(tg.y + yy), dp, smp, coop.mask[p])) coop.hit[p] = 1;
+            }
+            __syncthreads();
+            hit = hit || coop.hit[tid] != 0;
+            if (tid == 0) coop.n = 0u;  // (the barrier that ends the round, or the kernel's end, comes before the next use)
         }
         const unsigned int outIndex = static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + px;
         if (valid && !hit) store_pixel(band, outIndex, scale4(acc, fr.inv_spp));
@@ -839,6 +910,7 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
         }
         if (q0 + parts * kBlockThreads < nPix) __syncthreads();  // the ring is rewritten by the next round
     }
+    timer.stop();
 }
 
 #ifndef MCSKIN_SHADE_MIN_BLOCKS

@@ -70,6 +70,9 @@ struct BandView {
     uchar4* out_u8;   // may be null
     const int* tile_map;  // device memory, or null
     int n_tiles, n_heavy;
+    // diagnosis ("debug_primary_timing" option): 4 words per block of the pixel-per-lane primary kernels —
+    // %globaltimer at entry and exit, the block's frame tile, part | parts << 16; null otherwise
+    unsigned long long* block_times;
 };
 // tiles of a band
 __host__ __device__ inline int band_tile_count(const BandView& band, int tilesX) {

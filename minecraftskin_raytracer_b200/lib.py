@@ -39,6 +39,7 @@ EXPORTS = [
     "mcskin_primary_launch_order", "mcskin_cuda_context_render_tiles_into_frame", "mcskin_partition_tiles",
     "mcskin_cuda_host_register", "mcskin_cuda_host_unregister", "mcskin_cuda_render_batch_multi",
     "mcskin_cuda_enable_peer_access", "mcskin_cuda_context_render_scene_tiles",
+    "mcskin_cuda_context_debug_block_times",
 ]
 
 
@@ -343,6 +344,16 @@ class Context:
                                                      C.c_void_p(d_out_f32 or None), C.c_void_p(d_out_u8 or None),
                                                      C.c_void_p(stream or None)))
         self.cfg = _abi.copy_config(cfg)
+
+    def debug_block_times(self) -> np.ndarray:
+        """[n, 4] uint64 (entry ns, exit ns, frame tile, part | parts << 16) of the last primary launch
+        (option "debug_primary_timing")."""
+        n = _lib.mcskin_cuda_context_debug_block_times(self._h, None, C.c_int32(0))
+        _check(min(n, 0))
+        out = np.zeros((n, 4), dtype=np.uint64)
+        if n:
+            _check(min(_lib.mcskin_cuda_context_debug_block_times(self._h, _ptr(out, C.c_uint64), C.c_int32(n)), 0))
+        return out
 
     def sync(self) -> dict:
         stats = McRenderStats()
