@@ -189,11 +189,15 @@ int32_t mcskin_cuda_context_render_rows_into_frame(McContext* ctx, int32_t first
  * straight into the root's frame (peer memory) or into one page-locked host frame (mcskin_cuda_host_register). */
 int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_t* tiles, int32_t n_tiles,
                                                      void* d_frame_f32, void* d_frame_u8, void* stream);
-/* The per-frame call of a host that keeps the scene on the CPU: set_scene (upload) + render_tiles_into_frame on
- * the context's own stream + wait.  *ms_device (may be null): the frame's kernels, CUDA events.  Blocking. */
+/* The per-frame call of a rank whose scene lives on the CPU and whose result goes to a HOST image shared by every rank
+ * of the box: set_scene (upload) + this rank's tiles + wait.  host_frame_* must be page-locked and mapped
+ * (mcskin_cuda_host_register, cudaHostAlloc, torch pin_memory).  The tiles the figure's screen rectangle touches are
+ * stored by the kernels straight into the host image; the others are final after the primary pass and leave a
+ * device image by DMA, as a few rectangles, next to the shading kernels.  *ms_device (may be null): the frame's
+ * kernels, CUDA events.  Blocking. */
 int32_t mcskin_cuda_context_render_scene_tiles(McContext* ctx, const McScene* scene, const McConfig* cfg,
-                                                const int32_t* tiles, int32_t n_tiles, void* d_frame_f32, void* d_frame_u8,
-                                                float* ms_device);
+                                                const int32_t* tiles, int32_t n_tiles, float* host_frame_f32,
+                                                uint8_t* host_frame_u8, float* ms_device);
 /* Deals the tiles of a frame to n_parts renderers so that every part costs about the same: tiles are weighted
  * by how much of them the figure's screen rectangles cover (covered pixels cost ~50x a background pixel) and
  * dealt greedily, heaviest first, to the least loaded part; deterministic, the parts are disjoint and cover the

@@ -78,6 +78,10 @@ struct PinnedBuf {
     }
 };
 
+struct PixelRect {
+    int x, y, w, h;
+};
+
 }  // namespace
 
 struct McContext {
@@ -98,6 +102,7 @@ struct McContext {
     int blockTimesCount = 0;
     DevBuf tileMap;              // render_tiles_into_frame: frame tile indices, heavy tiles first
     std::vector<int32_t> tileMapHost, tileMapOrdered;
+    std::vector<PixelRect> tileMapLightRects;  // the tiles of the map the figure's rectangle does not touch, as rectangles
     unsigned long long tileMapVersion = 0;
     int tileMapHeavy = 0;
     DevFrame tileMapFrame{};     // the frame description the map was ordered for
@@ -134,7 +139,8 @@ struct McContext {
     cudaEvent_t evPrimaryDone = nullptr;     // (disable-timing) recorded after this lane's primary pass
     cudaStream_t copyStream = nullptr;       // device -> host copies that overlap the shading pass
     cudaEvent_t evFrameDone = nullptr;
-    int overlapCopyOut = 1;
+    int overlapCopyOut = 2;                  // 0: copy after the frame; 1: whole image after the primary pass + the figure's
+                                             // rectangle again at the end; 2: two destinations (see render_host)
     cudaEvent_t evUpload = nullptr;          // (disable-timing) recorded after the scene upload on ctx->stream
     unsigned long long seedGen = 0;          // bumped whenever tileStates is rewritten outside a graph
     bool capturing = false;                  // the launches are being captured into a graph: no timing events
@@ -151,6 +157,7 @@ struct McContext {
         const void* tileMap;
         unsigned long long mapVersion;
         int nTiles, nHeavy;
+        const void *hotF32, *hotU8;
         long long optionBits[12];
         unsigned long long allocEpoch;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
@@ -226,6 +233,8 @@ struct BandSpec {
     const int* map = nullptr;
     int nTiles = 0, nHeavy = 0;
     unsigned long long mapVersion = 0;
+    float4* hotF32 = nullptr;  // BandView::hot_*: where the tiles the figure's rectangle touches are written instead
+    uchar4* hotU8 = nullptr;
 };
 
 // Launches the two passes of a band on one stream; output pointers are device memory.  scn: the context whose
@@ -336,6 +345,8 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
         BandView band{};
         band.out_f32 = outF32;
         band.out_u8 = outU8;
+        band.hot_f32 = spec.hotF32;
+        band.hot_u8 = spec.hotU8;
         if (ctx->debugPrimaryTiming && nChunks == 1) {  // room for the finest split: one block per 256-pixel round of every tile
             const size_t blocks = static_cast<size_t>(nTilesAll) * ((tilePixels + kBlockThreads - 1) / kBlockThreads);
             CU_TRY(ctx->blockTimes.reserve(blocks * 4 * sizeof(unsigned long long)));
@@ -425,11 +436,16 @@ void inherit_options(McContext* lane, const McContext* ctx) {
 // frameLayout: the output is a full-frame image and every tile row lands at its own frame position
 // (output tile row = frame tile row) instead of a compact band.
 int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* outF32, uchar4* outU8, cudaStream_t stream,
-                       bool frameLayout, const BandSpec* tiles) {
-    if (tiles) return render_bands_lane(ctx, ctx, *tiles, outF32, outU8, stream);  // a tile map is one lane
+                       bool frameLayout, const BandSpec* tiles, float4* hotF32, uchar4* hotU8) {
+    if (tiles) {  // a tile map is one lane
+        BandSpec t = *tiles;
+        t.hotF32 = hotF32; t.hotU8 = hotU8;
+        return render_bands_lane(ctx, ctx, t, outF32, outU8, stream);
+    }
     auto rows = [&](int f0, int st, int out0, int outSt) {
         BandSpec b;
         b.first = f0; b.stride = st; b.outFirst = out0; b.outStride = outSt;
+        b.hotF32 = hotF32; b.hotU8 = hotU8;
         return b;
     };
     if (L <= 1)
@@ -472,8 +488,9 @@ void drop_graph(McContext* ctx) {
 // is bit-identical to the one-stream result.  The second time the same frame description comes
 // in, the launches are captured into a CUDA graph, which is replayed from then on.
 // tiles: instead of tile rows, the tile map of `tiles` (always written in frame layout, one lane).
+// hotF32 / hotU8: BandView::hot_* (the output must then be in frame layout, or the whole frame).
 int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* outU8, cudaStream_t stream,
-                 bool frameLayout = false, const BandSpec* tiles = nullptr) {
+                 bool frameLayout = false, const BandSpec* tiles = nullptr, float4* hotF32 = nullptr, uchar4* hotU8 = nullptr) {
     const DevFrame& f = ctx->prep.frame;
     const int nRows = tiles ? (tiles->nTiles > 0 ? 1 : 0) : local_tile_rows(f, first, stride);
     const int L = (ctx->isChild || tiles) ? 1 : std::max(1, std::min(ctx->frameLanes, nRows / 2));
@@ -494,6 +511,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         key.blob = ctx->boxes.p; key.texels = ctx->texels.p; key.outF32 = outF32; key.outU8 = outU8;
         key.blobBytes = static_cast<unsigned int>(ctx->prep.blob.size());
         key.first = first; key.stride = stride; key.lanes = L * 2 + (frameLayout ? 1 : 0);
+        key.hotF32 = hotF32; key.hotU8 = hotU8;
         if (tiles) {
             key.tileMap = tiles->map; key.mapVersion = tiles->mapVersion; key.nTiles = tiles->nTiles; key.nHeavy = tiles->nHeavy;
         }
@@ -537,7 +555,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         ctx->capturing = true;
         for (int k = 1; k < L; ++k) ctx->lanes[k - 1]->capturing = true;
         cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
-        int rc = e == cudaSuccess ? launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout, tiles) : MC_ERR_CUDA;
+        int rc = e == cudaSuccess ? launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout, tiles, hotF32, hotU8) : MC_ERR_CUDA;
         cudaGraph_t g = nullptr;
         if (e == cudaSuccess) {
             const cudaError_t e2 = cudaStreamEndCapture(stream, &g);
@@ -560,7 +578,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
                 ctx->graphLaneChunks[k] = lane->chunksLastRender;
                 ctx->graphLaneTiles[k] = static_cast<int>(lane->stats.n_tiles);
             }
-            return render_bands(ctx, first, stride, outF32, outU8, stream, frameLayout, tiles);  // replays the graph just made
+            return render_bands(ctx, first, stride, outF32, outU8, stream, frameLayout, tiles, hotF32, hotU8);  // replays the graph just made
         }
         // capture failed (an operation that cannot be captured): clear the error state, render directly
         if (g) cudaGraphDestroy(g);
@@ -569,7 +587,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
         ctx->useGraphs = 0;
     }
     CU_TRY(cudaEventRecord(ctx->ev0, stream));
-    const int rc = launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout, tiles);
+    const int rc = launch_frame_lanes(ctx, first, stride, L, outF32, outU8, stream, frameLayout, tiles, hotF32, hotU8);
     if (rc != MC_OK) return rc;
     if (L > 1) {
         CU_TRY(cudaEventRecord(ctx->ev1, stream));
@@ -649,6 +667,80 @@ bool is_pinned_host(const void* p) {
     }
     return attr.type == cudaMemoryTypeHost;
 }
+
+// A page-locked host range as the device sees it (cudaHostAlloc / torch pin_memory / cudaHostRegisterMapped), or null.
+void* device_alias_of_host(void* host) {
+    if (!host || !is_pinned_host(host)) return nullptr;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return d;
+}
+
+// Copies rectangles of the device images to the same places of the host images (both full frames of width W).
+int copy_rects_to_host(const std::vector<PixelRect>& rects, int W, const void* dF32, float* hF32, const void* dU8, uint8_t* hU8,
+                       cudaStream_t s) {
+    for (const PixelRect& r : rects) {
+        if (r.w <= 0 || r.h <= 0) continue;
+        const size_t at = static_cast<size_t>(r.y) * W + r.x;
+        if (hF32)
+            CU_TRY(cudaMemcpy2DAsync(hF32 + at * 4, static_cast<size_t>(W) * sizeof(float4), static_cast<const float4*>(dF32) + at,
+                                     static_cast<size_t>(W) * sizeof(float4), static_cast<size_t>(r.w) * sizeof(float4), r.h,
+                                     cudaMemcpyDeviceToHost, s));
+        if (hU8)
+            CU_TRY(cudaMemcpy2DAsync(hU8 + at * 4, static_cast<size_t>(W) * sizeof(uchar4), static_cast<const uchar4*>(dU8) + at,
+                                     static_cast<size_t>(W) * sizeof(uchar4), static_cast<size_t>(r.w) * sizeof(uchar4), r.h,
+                                     cudaMemcpyDeviceToHost, s));
+    }
+    return MC_OK;
+}
+
+// The tiles a primary kernel treats as able to hit (its tileCanHit): tile columns [tx0, tx1] x rows [ty0, ty1],
+// empty (returns false) when the figure's rectangle misses the frame.
+bool hot_tile_range(const DevFrame& f, int* tx0, int* tx1, int* ty0, int* ty1) {
+    if (!f.rect_valid || f.rect_x0 > f.rect_x1 || f.rect_y0 > f.rect_y1) return false;
+    if (f.rect_x1 < 0 || f.rect_y1 < 0 || f.rect_x0 >= f.width || f.rect_y0 >= f.height) return false;
+    *tx0 = std::max(0, f.rect_x0) / f.tile_size;
+    *tx1 = std::min(f.width - 1, f.rect_x1) / f.tile_size;
+    *ty0 = std::max(0, f.rect_y0) / f.tile_size;
+    *ty1 = std::min(f.height - 1, f.rect_y1) / f.tile_size;
+    return true;
+}
+
+// Maximal rectangles of a set of tiles (frame tile indices): horizontally adjacent tiles of a tile row merge into
+// spans, equal spans of consecutive tile rows merge vertically.
+std::vector<PixelRect> tile_rects(const DevFrame& f, std::vector<int32_t> tiles) {
+    std::vector<PixelRect> out;
+    std::sort(tiles.begin(), tiles.end());
+    struct Span { int ty, tx0, tx1; };
+    std::vector<Span> spans;
+    for (size_t i = 0; i < tiles.size();) {
+        const int ty = tiles[i] / f.tiles_x, tx0 = tiles[i] % f.tiles_x;
+        int tx1 = tx0;
+        size_t j = i + 1;
+        while (j < tiles.size() && tiles[j] / f.tiles_x == ty && tiles[j] % f.tiles_x == tx1 + 1) { ++tx1; ++j; }
+        spans.push_back({ty, tx0, tx1});
+        i = j;
+    }
+    std::vector<char> used(spans.size(), 0);
+    for (size_t i = 0; i < spans.size(); ++i) {
+        if (used[i]) continue;
+        int tyEnd = spans[i].ty;
+        for (size_t j = i + 1; j < spans.size(); ++j) {  // spans are sorted by row, then column
+            if (spans[j].ty > tyEnd + 1) break;
+            if (!used[j] && spans[j].ty == tyEnd + 1 && spans[j].tx0 == spans[i].tx0 && spans[j].tx1 == spans[i].tx1) {
+                used[j] = 1;
+                tyEnd = spans[j].ty;
+            }
+        }
+        const int x = spans[i].tx0 * f.tile_size, y = spans[i].ty * f.tile_size;
+        out.push_back({x, y, std::min(f.width, (spans[i].tx1 + 1) * f.tile_size) - x, std::min(f.height, (tyEnd + 1) * f.tile_size) - y});
+    }
+    return out;
+}
+
 
 // Device -> caller's host buffer.  Page-locked destinations (cudaHostAlloc / cudaHostRegister,
 // torch pin_memory) are written by DMA directly; pageable ones go through the context's pinned
@@ -910,7 +1002,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     if (const char* v = std::getenv("MCSKIN_BATCH_GROUP")) ctx->batchGroup = std::min(4096, std::max(1, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_BATCH_MODE")) ctx->batchMode = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_GRAPHS")) ctx->useGraphs = std::atoi(v) != 0;
-    if (const char* v = std::getenv("MCSKIN_OVERLAP_COPY")) ctx->overlapCopyOut = std::atoi(v) != 0;
+    if (const char* v = std::getenv("MCSKIN_OVERLAP_COPY")) ctx->overlapCopyOut = std::min(2, std::max(0, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_FRAME_LANES")) ctx->frameLanes = std::min(8, std::max(1, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_CACHE_TILE_SEEDS")) ctx->cacheTileSeeds = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_SHADE_BLOCKS")) ctx->shadeBlocksPerSm = std::max(1, std::atoi(v));
@@ -968,7 +1060,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "frame_lanes") ctx->frameLanes = static_cast<int>(std::min<int64_t>(8, std::max<int64_t>(1, value)));
     else if (k == "cache_tile_seeds") ctx->cacheTileSeeds = value != 0;
     else if (k == "use_graphs") ctx->useGraphs = value != 0;
-    else if (k == "overlap_copy_out") ctx->overlapCopyOut = value != 0;
+    else if (k == "overlap_copy_out") ctx->overlapCopyOut = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
     else if (k == "wave_budget_bytes") ctx->waveBudgetBytes = std::max<int64_t>(1 << 20, value);
     else return fail(MC_ERR_INVALID, "set_option: unknown option " + k);
     return MC_OK;
@@ -1014,12 +1106,9 @@ int32_t mcskin_cuda_context_render_rows_into_frame(McContext* ctx, int32_t first
     return render_bands(ctx, first, stride, static_cast<float4*>(dFrameF32), static_cast<uchar4*>(dFrameU8), s, true);
 }
 
-int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_t* tiles, int32_t nTiles, void* dFrameF32,
-                                                     void* dFrameU8, void* stream) {
-    if (!ctx || !ctx->hasScene) return fail(MC_ERR_INVALID, "render_tiles_into_frame: no scene set");
-    if (nTiles < 0 || (nTiles > 0 && !tiles)) return fail(MC_ERR_INVALID, "render_tiles_into_frame: bad tile list");
-    CU_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+// Validates a tile list, orders it (tiles the figure's rectangle touches first), uploads it when it changed and
+// describes it for render_bands.  *empty: nothing to render.
+static int prepare_tile_map(McContext* ctx, const int32_t* tiles, int32_t nTiles, cudaStream_t s, BandSpec* spec, bool* empty) {
     const DevFrame& f = ctx->prep.frame;
     const bool sameList = ctx->tileMapVersion != 0 && ctx->tileMapHost.size() == static_cast<size_t>(nTiles) &&
                           (nTiles == 0 || std::memcmp(ctx->tileMapHost.data(), tiles, sizeof(int32_t) * nTiles) == 0);
@@ -1027,15 +1116,16 @@ int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_
     const bool sameOrder = sameList && f.rect_valid == ctx->tileMapFrame.rect_valid && f.rect_x0 == ctx->tileMapFrame.rect_x0 &&
                            f.rect_y0 == ctx->tileMapFrame.rect_y0 && f.rect_x1 == ctx->tileMapFrame.rect_x1 &&
                            f.rect_y1 == ctx->tileMapFrame.rect_y1 && f.tiles_x == ctx->tileMapFrame.tiles_x &&
-                           f.tiles_y == ctx->tileMapFrame.tiles_y && f.tile_size == ctx->tileMapFrame.tile_size;
+                           f.tiles_y == ctx->tileMapFrame.tiles_y && f.tile_size == ctx->tileMapFrame.tile_size &&
+                           f.width == ctx->tileMapFrame.width && f.height == ctx->tileMapFrame.height;
     if (!sameOrder) {
         const long long total = static_cast<long long>(f.tiles_x) * f.tiles_y;
         std::vector<unsigned char> seen(static_cast<size_t>(std::max<long long>(total, 0)), 0);
         std::vector<int32_t> heavy, light;
         for (int i = 0; i < nTiles; ++i) {
             const int id = tiles[i];
-            if (id < 0 || id >= total) return fail(MC_ERR_INVALID, "render_tiles_into_frame: tile index out of range");
-            if (seen[id]) return fail(MC_ERR_INVALID, "render_tiles_into_frame: tile listed twice");
+            if (id < 0 || id >= total) return fail(MC_ERR_INVALID, "render_tiles: tile index out of range");
+            if (seen[id]) return fail(MC_ERR_INVALID, "render_tiles: tile listed twice");
             seen[id] = 1;
             const int ty = id / f.tiles_x, tx = id - ty * f.tiles_x;
             const int x = tx * f.tile_size, y = ty * f.tile_size;
@@ -1048,6 +1138,7 @@ int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_
         ctx->tileMapHeavy = static_cast<int>(heavy.size());
         ctx->tileMapOrdered = heavy;
         ctx->tileMapOrdered.insert(ctx->tileMapOrdered.end(), light.begin(), light.end());
+        ctx->tileMapLightRects = tile_rects(f, light);
         ctx->tileMapFrame = f;
         if (nTiles > 0) {
             CU_TRY(ctx->tileMap.reserve(sizeof(int32_t) * static_cast<size_t>(nTiles)));
@@ -1056,35 +1147,74 @@ int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_
         }
         ++ctx->tileMapVersion;
     }
+    *empty = nTiles == 0;
     if (nTiles == 0) {
         ctx->stats = McRenderStats{};
         ctx->statsPending = false;
         return MC_OK;
     }
+    spec->map = static_cast<const int*>(ctx->tileMap.p);
+    spec->nTiles = nTiles;
+    spec->nHeavy = ctx->tileMapHeavy;
+    spec->mapVersion = ctx->tileMapVersion;
+    return MC_OK;
+}
+
+int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_t* tiles, int32_t nTiles, void* dFrameF32,
+                                                     void* dFrameU8, void* stream) {
+    if (!ctx || !ctx->hasScene) return fail(MC_ERR_INVALID, "render_tiles_into_frame: no scene set");
+    if (nTiles < 0 || (nTiles > 0 && !tiles)) return fail(MC_ERR_INVALID, "render_tiles_into_frame: bad tile list");
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     BandSpec spec;
-    spec.map = static_cast<const int*>(ctx->tileMap.p);
-    spec.nTiles = nTiles;
-    spec.nHeavy = ctx->tileMapHeavy;
-    spec.mapVersion = ctx->tileMapVersion;
+    bool empty = false;
+    const int rc = prepare_tile_map(ctx, tiles, nTiles, s, &spec, &empty);
+    if (rc != MC_OK || empty) return rc;
     return render_bands(ctx, 0, 1, static_cast<float4*>(dFrameF32), static_cast<uchar4*>(dFrameU8), s, true, &spec);
 }
 
-// One blocking call per frame and rank for hosts that hold the scene on the CPU: upload, this rank's tiles
-// rendered into the (host- or peer-resident) frame, wait.  What bench.py's multi-GPU e2e step calls.
+// The per-frame call of a rank whose scene lives on the CPU and whose result goes to a host image every rank of the
+// box shares: upload, this rank's tiles, wait.  The image must be page-locked and mapped (mcskin_cuda_host_register,
+// cudaHostAlloc, torch pin_memory).  Tiles the figure's rectangle touches are stored by the kernels straight into it;
+// the others go to a device image and leave by DMA, in a few rectangles, once the primary pass is done.
 int32_t mcskin_cuda_context_render_scene_tiles(McContext* ctx, const McScene* scene, const McConfig* cfg, const int32_t* tiles,
-                                                int32_t nTiles, void* dFrameF32, void* dFrameU8, float* msDevice) {
+                                                int32_t nTiles, float* hostF32, uint8_t* hostU8, float* msDevice) {
     if (!ctx) return fail(MC_ERR_INVALID, "render_scene_tiles: null context");
+    if (nTiles < 0 || (nTiles > 0 && !tiles)) return fail(MC_ERR_INVALID, "render_scene_tiles: bad tile list");
     int rc = mcskin_cuda_context_set_scene(ctx, scene, cfg);
     if (rc != MC_OK) return rc;
-    rc = mcskin_cuda_context_render_tiles_into_frame(ctx, tiles, nTiles, dFrameF32, dFrameU8, nullptr);
-    if (rc != MC_OK) return rc;
+    if (msDevice) *msDevice = 0.0f;
+    const DevFrame& f = ctx->prep.frame;
+    void* aliasF32 = device_alias_of_host(hostF32);
+    void* aliasU8 = device_alias_of_host(hostU8);
+    if ((hostF32 && !aliasF32) || (hostU8 && !aliasU8))
+        return fail(MC_ERR_INVALID, "render_scene_tiles: the host image must be page-locked and mapped (mcskin_cuda_host_register)");
+    BandSpec spec;
+    bool empty = false;
+    rc = prepare_tile_map(ctx, tiles, nTiles, ctx->stream, &spec, &empty);
+    if (rc != MC_OK || empty) return rc;
+    const bool classified = !ctx->forceAllActive && f.spp <= kBlockThreads;
+    const bool dual = ctx->overlapCopyOut >= 2 && classified && !ctx->tileMapLightRects.empty();
+    if (dual) {
+        const size_t pixels = static_cast<size_t>(f.width) * f.height;
+        if (hostF32) CU_TRY(ctx->imgF32.reserve(pixels * sizeof(float4)));
+        if (hostU8) CU_TRY(ctx->imgU8.reserve(pixels * sizeof(uchar4)));
+        rc = render_bands(ctx, 0, 1, hostF32 ? static_cast<float4*>(ctx->imgF32.p) : nullptr,
+                          hostU8 ? static_cast<uchar4*>(ctx->imgU8.p) : nullptr, ctx->stream, true, &spec,
+                          static_cast<float4*>(aliasF32), static_cast<uchar4*>(aliasU8));
+        if (rc != MC_OK) return rc;
+        CU_TRY(cudaStreamWaitEvent(ctx->copyStream, ctx->evPrimaryDone, 0));
+        rc = copy_rects_to_host(ctx->tileMapLightRects, f.width, ctx->imgF32.p, hostF32, ctx->imgU8.p, hostU8, ctx->copyStream);
+        if (rc != MC_OK) return rc;
+        CU_TRY(cudaStreamSynchronize(ctx->copyStream));
+    } else {  // every tile straight into the host image
+        rc = render_bands(ctx, 0, 1, static_cast<float4*>(aliasF32), static_cast<uchar4*>(aliasU8), ctx->stream, true, &spec);
+        if (rc != MC_OK) return rc;
+    }
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     for (McContext* lane : ctx->lanes) CU_TRY(cudaStreamSynchronize(lane->stream));
     CU_TRY(cudaGetLastError());
-    if (msDevice) {
-        *msDevice = 0.0f;
-        if (nTiles > 0) CU_TRY(cudaEventElapsedTime(msDevice, ctx->ev0, ctx->ev1));
-    }
+    if (msDevice) CU_TRY(cudaEventElapsedTime(msDevice, ctx->ev0, ctx->ev1));
     return MC_OK;
 }
 
@@ -1211,6 +1341,38 @@ static int render_host(McContext* ctx, const McScene* scene, const McConfig* cfg
     }
     if (outF32) CU_TRY(ctx->imgF32.reserve(pixels * sizeof(float4)));
     if (outU8) CU_TRY(ctx->imgU8.reserve(pixels * sizeof(uchar4)));
+    // Two destinations (whole frames into page-locked images the device can address): the tiles the figure's screen
+    // rectangle touches — the only ones with pixels that are final as late as the frame's last kernel — are written by
+    // the kernels straight into the caller's image (a few MB over PCIe, spread over the frame); all other tiles are
+    // final after the primary passes and leave the device image by DMA then, next to the shading kernels.  Nothing
+    // is left to copy when the last kernel ends.
+    int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+    const bool wholeFrame = first == 0 && stride == 1;
+    const bool classified = !ctx->forceAllActive && f.spp <= kBlockThreads;
+    void* aliasF32 = (ctx->overlapCopyOut && wholeFrame && classified && outF32) ? device_alias_of_host(outF32) : nullptr;
+    void* aliasU8 = (ctx->overlapCopyOut && wholeFrame && classified && outU8) ? device_alias_of_host(outU8) : nullptr;
+    const bool dual = ctx->overlapCopyOut >= 2 && wholeFrame && classified && hot_tile_range(f, &tx0, &tx1, &ty0, &ty1) &&
+                      (!outF32 || aliasF32) && (!outU8 || aliasU8);
+    if (dual) {
+        rc = render_bands(ctx, 0, 1, outF32 ? static_cast<float4*>(ctx->imgF32.p) : nullptr,
+                          outU8 ? static_cast<uchar4*>(ctx->imgU8.p) : nullptr, ctx->stream, false, nullptr,
+                          static_cast<float4*>(aliasF32), static_cast<uchar4*>(aliasU8));
+        if (rc != MC_OK) return rc;
+        CU_TRY(cudaStreamWaitEvent(ctx->copyStream, ctx->evPrimaryDone, 0));
+        for (int k = 0; k < ctx->splitLastRender; ++k)
+            CU_TRY(cudaStreamWaitEvent(ctx->copyStream, ctx->lanes[k]->evPrimaryDone, 0));
+        const int ts = f.tile_size;
+        const int X0 = tx0 * ts, X1 = std::min(f.width, (tx1 + 1) * ts), Y0 = ty0 * ts, Y1 = std::min(f.height, (ty1 + 1) * ts);
+        const std::vector<PixelRect> light = {{0, 0, f.width, Y0}, {0, Y1, f.width, f.height - Y1},
+                                              {0, Y0, X0, Y1 - Y0}, {X1, Y0, f.width - X1, Y1 - Y0}};
+        rc = copy_rects_to_host(light, f.width, ctx->imgF32.p, outF32, ctx->imgU8.p, outU8, ctx->copyStream);
+        if (rc != MC_OK) return rc;
+        CU_TRY(cudaStreamSynchronize(ctx->copyStream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < ctx->splitLastRender; ++k) CU_TRY(cudaStreamSynchronize(ctx->lanes[k]->stream));
+        CU_TRY(cudaGetLastError());
+        return finish_stats(ctx, stats);
+    }
     rc = render_bands(ctx, first, stride, outF32 ? static_cast<float4*>(ctx->imgF32.p) : nullptr,
                       outU8 ? static_cast<uchar4*>(ctx->imgU8.p) : nullptr, ctx->stream);
     if (rc != MC_OK) return rc;

@@ -52,6 +52,14 @@ __device__ __forceinline__ Ray primary_ray(const DevFrame& fr, float u, float v,
     return fr.dof_on ? dof_ray(fr, u, v, s.r1, s.r2) : camera_ray(fr, u, v);
 }
 
+// The view through which the tiles that intersect the figure's screen rectangle are written (BandView::hot_*).
+__device__ __forceinline__ BandView hot_band(const BandView& band) {
+    BandView h = band;
+    if (band.hot_f32) h.out_f32 = band.hot_f32;
+    if (band.hot_u8) h.out_u8 = band.hot_u8;
+    return h;
+}
+
 __device__ __forceinline__ void store_pixel(const BandView& band, unsigned int index, float4 c) {
     if (band.out_f32) band.out_f32[index] = c;
     if (band.out_u8) band.out_u8[index] = quantize4(c);
@@ -100,7 +108,12 @@ __device__ __forceinline__ void warp_resolve(const DevFrame& fr, const BandView&
         }
         const int leader = (p << lgSpp) & 31;
         const unsigned int idx = __shfl_sync(kFullMask, outIndex, leader);
-        if (band.out_f32 && on) reinterpret_cast<float*>(band.out_f32)[static_cast<size_t>(idx) * 4 + ch] = acc;
+        if (band.out_f32) {  // the four channel lanes of a pixel -> one 16-byte store (matters when the image is host memory)
+            const float a1 = __shfl_down_sync(kFullMask, acc, 1);
+            const float a2 = __shfl_down_sync(kFullMask, acc, 2);
+            const float a3 = __shfl_down_sync(kFullMask, acc, 3);
+            if (on && ch == 0) band.out_f32[idx] = make_float4(acc, a1, a2, a3);
+        }
         if (band.out_u8) {
             unsigned int q = on ? quantize8(acc) : 0u;
             q |= __shfl_down_sync(kFullMask, q, 1) << 8;

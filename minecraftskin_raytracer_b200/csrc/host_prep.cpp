@@ -453,7 +453,13 @@ extern "C" int32_t mcskin_partition_tiles(const McScene* scene, const McConfig* 
     } else {
         rects.push_back({0, 0, f.width - 1, f.height - 1});  // any pixel may hit: cost follows the tile's area
     }
-    std::vector<std::pair<double, int>> order(static_cast<size_t>(nTiles));
+    // Tiles the figure's screen rectangle touches ("hot": the kernels write them through BandView::hot_*) are dealt
+    // one by one, heaviest first, to the least loaded part.  The others cost the same (their primary pass) and are
+    // final after it: they are dealt as CONTIGUOUS runs in frame order, so that a part's background pixels are a
+    // few rectangles (one DMA each on the way to a host frame) — each part gets the run that fills it up to the mean.
+    std::vector<std::pair<double, int>> hot;
+    std::vector<int> light;
+    double total = 0.0;
     for (int id = 0; id < nTiles; ++id) {
         const int tileY = id / f.tiles_x, tileX = id - tileY * f.tiles_x;
         const int left = tileX * ts, top = tileY * ts;
@@ -465,19 +471,51 @@ extern "C" int32_t mcskin_partition_tiles(const McScene* scene, const McConfig* 
             if (w > 0 && h > 0) covered += static_cast<double>(w) * static_cast<double>(h);
         }
         const double area = static_cast<double>(right - left + 1) * (bottom - top + 1);
-        order[id] = {area / (static_cast<double>(ts) * ts) + kCoveredCost * covered / (static_cast<double>(ts) * ts), id};
+        const double weight = area / (static_cast<double>(ts) * ts) + kCoveredCost * covered / (static_cast<double>(ts) * ts);
+        total += weight;
+        // the primary kernels' own test (tileCanHit)
+        const bool canHit = !f.rect_valid || !(left > f.rect_x1 || right < f.rect_x0 || top > f.rect_y1 || bottom < f.rect_y0);
+        if (canHit) hot.push_back({weight, id});
+        else light.push_back(id);
     }
-    std::stable_sort(order.begin(), order.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
+    std::stable_sort(hot.begin(), hot.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
         return a.first > b.first;  // heaviest first; equal weights keep frame order
     });
     std::vector<double> load(nParts, 0.0);
     std::vector<int32_t> mine;
-    for (const auto& t : order) {
+    for (const auto& t : hot) {
         int best = 0;
         for (int p = 1; p < nParts; ++p)
             if (load[p] < load[best]) best = p;
         load[best] += t.first;
         if (best == part) mine.push_back(t.second);
+    }
+    {
+        auto weight_of = [&](int id) {
+            const int tileY = id / f.tiles_x, tileX = id - tileY * f.tiles_x;
+            return static_cast<double>(std::min(f.width, (tileX + 1) * ts) - tileX * ts) *
+                   (std::min(f.height, (tileY + 1) * ts) - tileY * ts) / (static_cast<double>(ts) * ts);
+        };
+        double lightLeft = 0.0;
+        for (int id : light) lightLeft += weight_of(id);
+        // the level part p is filled to: the mean of what is left for parts p.. when its run starts
+        auto level = [&](int p) {
+            double rest = lightLeft;
+            for (int q = p; q < nParts; ++q) rest += load[q];
+            return rest / (nParts - p);
+        };
+        int p = 0;
+        double target = level(0);
+        for (int id : light) {
+            const double w = weight_of(id);
+            while (p < nParts - 1 && load[p] + 0.5 * w > target) {
+                ++p;
+                target = level(p);
+            }
+            load[p] += w;
+            lightLeft -= w;
+            if (p == part) mine.push_back(id);
+        }
     }
     std::sort(mine.begin(), mine.end());
     if (outTiles)

@@ -148,6 +148,7 @@ k_primary_cta(const DevFrame fr, const FramePointers fp, const BandView band, co
                                                 tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
     if (tileCanHit || !classify) stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
+    const BandView out = tileCanHit ? hot_band(band) : band;
 
     TileStream stream;
     stream.sm = &mt;
@@ -210,7 +211,7 @@ k_primary_cta(const DevFrame fr, const FramePointers fp, const BandView band, co
                     float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     const float4* mine = stage + tid * spp;
                     for (int i = 0; i < spp; ++i) acc = add4(acc, mine[i]);
-                    store_pixel(band, outIndex, scale4(acc, fr.inv_spp));
+                    store_pixel(out, outIndex, scale4(acc, fr.inv_spp));
                 }
             }
             __syncthreads();
@@ -284,6 +285,7 @@ k_shade_cta(const DevFrame fr, const FramePointers fp, const BandView band, cons
 
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
+    const BandView out = hot_band(band);  // listed pixels lie in tiles the figure's rectangle touches
 
     const int chunks = small ? 1 : (spp + kBlockThreads - 1) / kBlockThreads;
     const int lanePix = small ? tid / spp : 0;
@@ -331,7 +333,7 @@ k_shade_cta(const DevFrame fr, const FramePointers fp, const BandView band, cons
             }
             __syncthreads();
         }
-        if (sumSp.x != kUnusedSlot) store_pixel(band, sumSp.x, scale4(acc, fr.inv_spp));
+        if (sumSp.x != kUnusedSlot) store_pixel(out, sumSp.x, scale4(acc, fr.inv_spp));
     }
 }
 
@@ -405,6 +407,7 @@ k_primary_warp(const DevFrame fr, const FramePointers fp, const BandView band, c
                                                 tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
     if (tileCanHit) stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
+    const BandView out = tileCanHit ? hot_band(band) : band;
 
     if (dps > 0) big_stream_seed(&mt, static_cast<uint32_t>(tg.y * fr.width + tg.x));  // tile_renderer.cpp:78
     int which = 0;
@@ -477,7 +480,7 @@ k_primary_warp(const DevFrame fr, const FramePointers fp, const BandView band, c
                 }
             }
             (void)validMask;
-            warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, outIndex, resolveMask);
+            warp_resolve(fr, out, stageW, lane, spp, lgSpp, colour, outIndex, resolveMask);
 
             // work-list slots for the pixels with a hit: one atomic per warp
             const unsigned int leadersActive = __ballot_sync(kFullMask, leader && pixelActive);
@@ -649,6 +652,7 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
                                                 tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
     if (tileCanHit) stage_bulk(sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(sceneSmem, fp.texels, fr);
+    const BandView out = tileCanHit ? hot_band(band) : band;
 
     if (dps > 0) {  // this tile's freshly seeded engine (k_tile_seed)
         const uint32_t* st = tileStates + static_cast<size_t>(tileIndex) * kMtN;
@@ -709,7 +713,7 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
             }
         }
         const unsigned int outIndex = static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + px;
-        if (valid && !hit) store_pixel(band, outIndex, scale4(acc, fr.inv_spp));
+        if (valid && !hit) store_pixel(out, outIndex, scale4(acc, fr.inv_spp));
 
         const unsigned int hitMask = __ballot_sync(kFullMask, hit);
         if (hitMask) {  // work-list slots: one atomic per warp
@@ -776,6 +780,7 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
                                                 tg.y > fr.rect_y1 || tg.y + tg.h - 1 < fr.rect_y0);
     if (tileCanHit) stage_bulk(sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(sceneSmem, fp.texels, fr);
+    const BandView out = tileCanHit ? hot_band(band) : band;
     {
         const uint32_t* st = tileStates + static_cast<size_t>(tileIndex) * kMtN;
         for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = st[i];
@@ -891,7 +896,7 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
             if (tid == 0) coop.n = 0u;  // (the barrier that ends the round, or the kernel's end, comes before the next use)
         }
         const unsigned int outIndex = static_cast<unsigned int>(tg.bandRow0 + ly) * static_cast<unsigned int>(fr.width) + px;
-        if (valid && !hit) store_pixel(band, outIndex, scale4(acc, fr.inv_spp));
+        if (valid && !hit) store_pixel(out, outIndex, scale4(acc, fr.inv_spp));
 
         const unsigned int hitMask = __ballot_sync(kFullMask, hit);
         if (hitMask) {  // work-list slots: one atomic per warp
@@ -934,6 +939,7 @@ k_shade_warp(const DevFrame fr, const FramePointers fp, const BandView band, con
 
     stage_bulk(g_sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(g_sceneSmem, fp.texels, fr);
+    const BandView out = hot_band(band);
     float* stageW = stageAll[warp];
     const int pix = lane >> lgSpp, s = lane & (spp - 1);
 
@@ -976,7 +982,7 @@ k_shade_warp(const DevFrame fr, const FramePointers fp, const BandView band, con
                 resolveMask |= 1u << (l >> lgSpp);
             }
         }
-        warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, sp.x, resolveMask);
+        warp_resolve(fr, out, stageW, lane, spp, lgSpp, colour, sp.x, resolveMask);
     }
 }
 

@@ -68,6 +68,12 @@ struct BandView {
     int out_first_row, out_row_stride;
     float4* out_f32;  // may be null
     uchar4* out_u8;   // may be null
+    // If set: the image the tiles that intersect the figure's screen rectangle are written to instead (same
+    // layout).  The host API points these at the caller's page-locked image (mapped into the device address space),
+    // so that the pixels that are final only when the frame ends need no copy afterwards, while the background
+    // tiles — final after the primary pass — go to device memory and leave by DMA next to the shading kernels.
+    float4* hot_f32;
+    uchar4* hot_u8;
     const int* tile_map;  // device memory, or null
     int n_tiles, n_heavy;
     // diagnosis ("debug_primary_timing" option): 4 words per block of the pixel-per-lane primary kernels —

@@ -466,7 +466,7 @@ template <bool BATCH>
 __global__ void __launch_bounds__(kWfThreads)
 k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list_, const WaveView wv_, const int lgSpp,
                   const BatchSlice* __restrict__ batch) {
-    const BandView& band = BATCH ? batch[blockIdx.y].band : band_;
+    const BandView band = hot_band(BATCH ? batch[blockIdx.y].band : band_);  // listed pixels lie in tiles the figure's rectangle touches
     const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
     const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     __shared__ __align__(16) float stageAll[kWfThreads / 32][kWarpStageFloats];
@@ -505,7 +505,7 @@ template <bool BATCH>
 __global__ void __launch_bounds__(kWfThreads)
 k_wf_resolve_pixel(const DevFrame fr, const BandView band_, const ActiveList list_, const WaveView wv_,
                    const BatchSlice* __restrict__ batch) {
-    const BandView& band = BATCH ? batch[blockIdx.y].band : band_;
+    const BandView band = hot_band(BATCH ? batch[blockIdx.y].band : band_);
     const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
     const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     unsigned int count = *list.count;

@@ -325,14 +325,17 @@ class Context:
                                                                 C.c_void_p(d_frame_f32 or None), C.c_void_p(d_frame_u8 or None),
                                                                 C.c_void_p(stream or None)))
 
-    def render_scene_tiles(self, scene: FlatScene, cfg: McConfig, tiles: np.ndarray, d_frame_f32: int = 0, d_frame_u8: int = 0) -> float:
-        """Blocking: upload the scene, render these tiles into the frame, wait.  Returns the kernels' milliseconds.
+    def render_scene_tiles(self, scene, cfg: McConfig, tiles: np.ndarray, host_f32: np.ndarray | None = None,
+                           host_u8: np.ndarray | None = None) -> float:
+        """Blocking: upload the scene, render these tiles into the page-locked, mapped HOST image(s) (full frames,
+        e.g. bands.HostFrame.frame or a registered array), wait.  Returns the kernels' milliseconds.
         `scene` may be a FlatScene or its cached C view (FlatScene.as_c())."""
         cs = scene.as_c() if isinstance(scene, FlatScene) else scene
         ms = C.c_float(0.0)
-        _check(_lib.mcskin_cuda_context_render_scene_tiles(self._h, C.byref(cs), C.byref(cfg), _ptr(tiles, C.c_int32),
-                                                           C.c_int32(len(tiles)), C.c_void_p(d_frame_f32 or None),
-                                                           C.c_void_p(d_frame_u8 or None), C.byref(ms)))
+        _check(_lib.mcskin_cuda_context_render_scene_tiles(
+            self._h, C.byref(cs), C.byref(cfg), _ptr(tiles, C.c_int32), C.c_int32(len(tiles)),
+            None if host_f32 is None else C.cast(C.c_void_p(host_f32.ctypes.data), C.POINTER(C.c_float)),
+            None if host_u8 is None else C.cast(C.c_void_p(host_u8.ctypes.data), C.POINTER(C.c_uint8)), C.byref(ms)))
         self.cfg = cfg
         return float(ms.value)
 

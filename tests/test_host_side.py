@@ -248,7 +248,17 @@ def test_partition_tiles_covers_the_frame_and_balances(mclib):
         again = [mclib.partition_tiles(scene, cfg, n, p) for p in range(n)]
         assert all(np.array_equal(a, b) for a, b in zip(parts, again))
         assert sorted(np.concatenate(parts).tolist()) == list(range(tx * ty))
-        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= max(2, tx * ty // (20 * n))
+        # (tile COUNTS may differ by what one figure tile weighs in background tiles: the deal balances cost)
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= max(2, 51 if n > 1 else 0)
+        # the background tiles of a part are a contiguous run in frame order: few rectangles on the way to a host frame
+        hot_cols = [c for c in range(tx) if per_tile.reshape(ty, tx)[:, c].any()]
+        hot_rows = [r for r in range(ty) if per_tile.reshape(ty, tx)[r].any()]
+        for p in parts:
+            light = [t for t in p.tolist() if not (min(hot_rows) - 1 <= t // tx <= max(hot_rows) + 1 and min(hot_cols) - 1 <= t % tx <= max(hot_cols) + 1)]
+            if light:
+                inside = [t for t in range(min(light), max(light) + 1)
+                          if not (min(hot_rows) - 1 <= t // tx <= max(hot_rows) + 1 and min(hot_cols) - 1 <= t % tx <= max(hot_cols) + 1)]
+                assert len(inside) - len(light) <= 4 * (max(hot_cols) - min(hot_cols) + 3), (n, len(inside), len(light))
         share = np.array([per_tile[p].sum() for p in parts], dtype=np.float64)
         assert share.max() / share.mean() < 1.05, (n, share)
     rows = np.array([per_tile.reshape(ty, tx)[r::8].sum() for r in range(8)], dtype=np.float64)

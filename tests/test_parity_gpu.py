@@ -684,7 +684,7 @@ def test_host_frame_zero_copy(gpu, oracle):
         host[...] = -1.0
         c_scene = scene.as_c()
         for r in range(2):
-            ms = ctx.render_scene_tiles(c_scene, cfg, gpu.partition_tiles(scene, cfg, 2, r), dptr, 0)
+            ms = ctx.render_scene_tiles(c_scene, cfg, gpu.partition_tiles(scene, cfg, 2, r), host)
             assert ms > 0.0
         assert np.array_equal(_bits(host), _bits(want))
     finally:
