@@ -639,16 +639,16 @@ def run_extra_workloads(torch, dist, lib, bands, _abi, synth_skin, rank, world, 
     n_total = C4_SKINS_PER_GPU * world
     mine = bands.shard_batch(n_total, rank, world)
     cfg = _abi.default_config(**C4_CONFIG)
-    scenes = [lib.build_skin_scene(synth_skin(i)) for i in mine]
+    atlases = np.stack([synth_skin(i) for i in mine])  # raw RGBA8 atlases: sliced into texel pools on the device
     ctx = lib.Context(local_rank)
     imgs = torch.empty((len(mine), cfg.height, cfg.width, 4), dtype=torch.uint8, device=dev)
-    ctx.render_batch(scenes[:128], cfg, 0, imgs.data_ptr(), stream.cuda_stream)  # warm-up at the steady-state chunk size
+    ctx.render_skin_batch(atlases[:128], cfg, None, 0, imgs.data_ptr(), stream.cuda_stream)  # warm-up at the steady-state chunk size
     ctx.sync()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    ctx.render_batch(scenes, cfg, 0, imgs.data_ptr(), stream.cuda_stream)
+    ctx.render_skin_batch(atlases, cfg, None, 0, imgs.data_ptr(), stream.cuda_stream)
     ctx.sync()
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
@@ -658,8 +658,9 @@ def run_extra_workloads(torch, dist, lib, bands, _abi, synth_skin, rank, world, 
     dt = float(tt.item())
     out["c4_batch_256_4spp_2b"] = {"skins": n_total, "skins_per_gpu": C4_SKINS_PER_GPU, "n_gpus": world, "seconds": dt,
                                    "skins_per_s": n_total / dt, "ms_per_skin_per_gpu": dt * 1e3 / C4_SKINS_PER_GPU,
-                                   "what": "host scenes in (flattened skins, staged and uploaded inside the call), 8-bit images left on "
-                                           "the device; wall clock around render_batch + sync, max over ranks; sharded by skin, no exchange"}
+                                   "what": "host RGBA8 atlases in (box layout on the host, atlas uploaded and sliced into the texel pool on the "
+                                           "device inside the call), 8-bit images left on the device; wall clock around render_skin_batch + sync, "
+                                           "max over ranks; sharded by skin, no exchange"}
     ctx.close()
     return out
 

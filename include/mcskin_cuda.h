@@ -253,6 +253,24 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
  * until the images are complete. */
 int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, int32_t n_scenes,
                                          const McConfig* cfg, void* d_out_f32, void* d_out_u8, void* stream);
+/* The flat scene of a skin WITHOUT its float texels (host code): the boxes mcskin_build_skin_scene would emit, their
+ * face windows into a texel pool of scene_out->n_texels texels that is not materialised (scene_out->texels_rgba is
+ * null), where every face's texels come from in the atlas (faces_out: 6 int32 per face — first texel in the pool, atlas
+ * x, y, w, h, mirrored — for up to 72 faces), and per box whether no texel has alpha 0 (box_opaque_out[12]).  Only the
+ * alpha bytes of the atlas are read.  What render_skin_batch does per skin before the device cuts the pool. */
+int32_t mcskin_skin_layout(const uint8_t* atlas_rgba8, int32_t atlas_w, int32_t atlas_h, const float* pose12, McBox* boxes_out,
+                           int32_t* faces_out, int32_t* n_faces_out, uint8_t* box_opaque_out, McScene* scene_out);
+/* Batches of skins straight from their atlases (SkinParser::parse -> MeshBuilder::buildScene -> TileRenderer::render
+ * per skin; skin_parser.cpp:11-132, mesh_builder.cpp:145-202): n_skins RGBA8 atlases of atlas_w x atlas_h (64x64 or
+ * 64x32), one after the other in host memory, skin i -> image i of the device buffer(s).  poses12: 12 floats per skin
+ * (rotX, rotZ in degrees for head, body, right arm, left arm, right leg, left leg) at a stride of pose_stride floats
+ * (0: the same pose for every skin), or null for the standing pose.  The atlas is sliced into the scene's texel
+ * pool on the DEVICE (16 KB per skin cross PCIe instead of 52 KB of float texels); the host only lays out the boxes,
+ * from the alpha bytes.  Results equal mcskin_build_skin_scene + mcskin_cuda_context_render_batch bit for bit.
+ * Asynchronous like render_batch. */
+int32_t mcskin_cuda_context_render_skin_batch(McContext* ctx, const uint8_t* atlases_rgba8, int32_t atlas_w, int32_t atlas_h,
+                                              int32_t n_skins, const float* poses12, int32_t pose_stride, const McConfig* cfg,
+                                              void* d_out_f32, void* d_out_u8, void* stream);
 /* The same, host to host and sharded by skin over devices 0..n_devices-1 of this process (BASELINE config 4):
  * skin i is rendered by device i % n_devices — scenes are independent frames, there is no exchange — one host
  * thread per device, image i lands at out_*[i] (n_scenes consecutive host images; either may be null).  Blocking. */

@@ -183,6 +183,9 @@ struct McContext {
     int batchGroup = 128;                    // scenes rendered by one set of launches (gridDim.y)
     int batchMode = 1;                       // 1: grouped launches, 0: one frame at a time over the lanes
     DevBuf batchScenes, batchSlots, batchRecords, batchWave, batchCounts;
+    DevBuf batchSkinSrc;                     // render_skin_batch: per skin the raw atlas, its face table, the slicing job
+    PinnedBuf batchSkinStage[2];
+    std::vector<McBox> batchSkinBoxes;
     PinnedBuf batchStage[2];
     cudaEvent_t evStage[2] = {nullptr, nullptr};
     std::vector<PreparedFrame> batchPreps;
@@ -810,8 +813,19 @@ namespace {
 // Each scene has its own boxes, texels, output image, work list and queues (BatchSlice); the tile
 // engines are seeded once per launch set (they do not depend on the scene).  Returns MC_OK with
 // *handled = false when the frame description needs a path that has no batched form.
-int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, const McConfig* cfg, float4* outF32,
-                         uchar4* outU8, cudaStream_t stream, bool* handled) {
+// skins: instead of flat scenes, raw RGBA8 atlases: the host lays out the boxes of every skin
+// from the alpha bytes alone (skin_layout) and uploads the 16 KB atlas; k_slice_skins cuts it into the scene's
+// float texel pool on the device (SkinParser::parse, skin_parser.cpp:11-110 + image.cpp:14-21) — a third of
+// the bytes per skin over PCIe, and no float conversion on the host.
+struct SkinBatchSrc {
+    const uint8_t* atlases;
+    int w, h;
+    const float* poses;   // 12 floats per skin, or one set for all (poseStride 0), or null
+    int poseStride;
+};
+
+int render_batch_grouped(McContext* ctx, const McScene* scenes, const SkinBatchSrc* skins, int nScenes, const McConfig* cfg,
+                         float4* outF32, uchar4* outU8, cudaStream_t stream, bool* handled) {
     *handled = false;
     if (!ctx->batchMode || ctx->shadeMode != 0 || ctx->forceAllActive || nScenes < 2) return MC_OK;
     if (cfg->width <= 0 || cfg->height <= 0 || cfg->tile_size <= 0 || cfg->width > 65535 || cfg->height > 65535) return MC_OK;
@@ -824,7 +838,28 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
 
     // sizes per scene (identical for every scene: they depend on the config only)
     PreparedFrame probe;
-    int prc = prepare_frame(&scenes[0], cfg, 1, 0.0f, probe, err);
+    const size_t atlasBytes = skins ? static_cast<size_t>(skins->w) * skins->h * 4 : 0;
+    // one skin's staging record: atlas | face table | slicing job
+    const size_t skinRecord = (atlasBytes + kSkinMaxFaces * sizeof(SkinFaceSource) + sizeof(SkinSliceJob) + 255) & ~size_t(255);
+    McBox skinBoxes[kSkinMaxBoxes];
+    SkinFaceSource skinFaces[kSkinMaxFaces];
+    uint8_t skinOpaque[kSkinMaxBoxes];
+    // the flat scene of skin k of the batch (boxes into `boxes`)
+    auto layout_skin = [&](int k, McBox* boxes, SkinFaceSource* faces, int* nFaces, uint8_t* opaque, McScene* sc) {
+        const float* pose = skins->poses ? skins->poses + static_cast<size_t>(k) * skins->poseStride : nullptr;
+        return skin_layout(skins->atlases + static_cast<size_t>(k) * atlasBytes, skins->w, skins->h, pose, boxes, faces, nFaces, opaque, sc);
+    };
+    int prc;
+    if (skins) {
+        McScene sc;
+        int nFaces = 0;
+        if (layout_skin(0, skinBoxes, skinFaces, &nFaces, skinOpaque, &sc) != MC_OK)
+            return fail(MC_ERR_INVALID, "render_skin_batch: atlases must be 64x64 or 64x32 RGBA8");
+        const ExternalTexels ext{skinOpaque};
+        prc = prepare_frame(&sc, cfg, 1, 0.0f, probe, err, &ext);
+    } else {
+        prc = prepare_frame(&scenes[0], cfg, 1, 0.0f, probe, err);
+    }
     if (prc != MC_OK) return fail(prc, err);
     const DevFrame& f0 = probe.frame;
     const size_t slotCap = static_cast<size_t>(f0.tiles_x) * f0.tiles_y * f0.tile_size * f0.tile_size;
@@ -847,7 +882,10 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
     constexpr size_t kMaxBlob = kMaxSceneSmemBytes;
     // blob + texel pool of the largest scene of the batch (a skin scene is ~55 KB)
     size_t sceneStride = 0;
-    for (int i = 0; i < nScenes; ++i) {
+    if (skins)
+        sceneStride = ((SceneBlobLayout(kSkinMaxBoxes).bytes() + 255) & ~size_t(255)) +
+                      (((static_cast<size_t>(kSkinMaxTexels) + 2) * sizeof(float4h) + 255) & ~size_t(255));
+    for (int i = 0; i < nScenes && !skins; ++i) {
         if (scenes[i].n_boxes < 0 || scenes[i].n_texels < 0) return fail(MC_ERR_INVALID, "render_batch: scene has negative counts");
         const size_t blob = (SceneBlobLayout(scenes[i].n_boxes).bytes() + 255) & ~size_t(255);
         if (blob > kMaxBlob) return MC_OK;  // the frame-by-frame path reports the limit
@@ -862,6 +900,11 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
     CU_TRY(ctx->batchCounts.reserve(static_cast<size_t>(G) * sizeof(unsigned int)));
     CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, static_cast<size_t>(f0.tiles_x) * f0.tiles_y * 624 * sizeof(uint32_t))));
     for (int i = 0; i < 2; ++i) CU_TRY(ctx->batchStage[i].reserve(static_cast<size_t>(G) * (sceneStride + sizeof(BatchSlice))));
+    if (skins) {
+        CU_TRY(ctx->batchSkinSrc.reserve(static_cast<size_t>(G) * skinRecord));
+        for (int i = 0; i < 2; ++i) CU_TRY(ctx->batchSkinStage[i].reserve(static_cast<size_t>(G) * skinRecord));
+        ctx->batchSkinBoxes.resize(static_cast<size_t>(G) * kSkinMaxBoxes);
+    }
     if (ctx->batchPreps.size() < static_cast<size_t>(G)) ctx->batchPreps.resize(G);
     ctx->tileSeedValid = false;  // this path seeds the engines itself
     ++ctx->seedGen;
@@ -872,7 +915,38 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
     bool seeded = false;
     for (int c0 = 0; c0 < nScenes; c0 += G) {
         const int nC = std::min(G, nScenes - c0);
+        // (the staging buffers of this slot are free once the copies that last read them are done)
+        CU_TRY(cudaEventSynchronize(ctx->evStage[stageSlot]));
+        unsigned char* skinStage = skins ? static_cast<unsigned char*>(ctx->batchSkinStage[stageSlot].p) : nullptr;
+        unsigned char* devSkin = static_cast<unsigned char*>(ctx->batchSkinSrc.p);
         for (int i = 0; i < nC; ++i) {
+            if (skins) {
+                // atlas, face table and slicing job of skin i into its staging record; the boxes stay on the host
+                unsigned char* rec = skinStage + static_cast<size_t>(i) * skinRecord;
+                SkinFaceSource* faces = reinterpret_cast<SkinFaceSource*>(rec + atlasBytes);
+                SkinSliceJob* job = reinterpret_cast<SkinSliceJob*>(rec + atlasBytes + kSkinMaxFaces * sizeof(SkinFaceSource));
+                McScene sc;
+                int nFaces = 0;
+                McBox* boxes = ctx->batchSkinBoxes.data() + static_cast<size_t>(i) * kSkinMaxBoxes;
+                if (layout_skin(c0 + i, boxes, faces, &nFaces, skinOpaque, &sc) != MC_OK)
+                    return fail(MC_ERR_INVALID, "render_skin_batch: atlases must be 64x64 or 64x32 RGBA8");
+                std::memcpy(rec, skins->atlases + static_cast<size_t>(c0 + i) * atlasBytes, atlasBytes);
+                const ExternalTexels ext{skinOpaque};
+                prc = prepare_frame(&sc, cfg, 1, 0.0f, ctx->batchPreps[i], err, &ext);
+                if (prc != MC_OK) return fail(prc, err);
+                const size_t blobBytes = (ctx->batchPreps[i].blob.size() + 255) & ~size_t(255);
+                unsigned char* devRec = devSkin + static_cast<size_t>(i) * skinRecord;
+                job->atlas = reinterpret_cast<const uchar4*>(devRec);
+                job->faces = reinterpret_cast<const SkinFaceSource*>(devRec + atlasBytes);
+                job->texels = reinterpret_cast<float4*>(static_cast<unsigned char*>(ctx->batchScenes.p) + static_cast<size_t>(i) * sceneStride + blobBytes);
+                job->atlasW = skins->w;
+                job->atlasH = skins->h;
+                job->nFaces = nFaces;
+                job->nTexels = sc.n_texels;
+                if (blobBytes + (static_cast<size_t>(sc.n_texels) + 2) * sizeof(float4h) > sceneStride)
+                    return fail(MC_ERR_LIMIT, "render_skin_batch: skin scene larger than a skin can be");
+                continue;
+            }
             prc = prepare_frame(&scenes[c0 + i], cfg, 1, 0.0f, ctx->batchPreps[i], err);
             if (prc != MC_OK) return fail(prc, err);
             if (ctx->batchPreps[i].blob.size() > kMaxBlob ||
@@ -896,7 +970,6 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
             groups[groupOf[i]].push_back(i);
         }
         // stage: scene data at slot i (chunk-local index), slices ordered group by group
-        CU_TRY(cudaEventSynchronize(ctx->evStage[stageSlot]));  // the copy that last read this staging buffer
         unsigned char* stage = static_cast<unsigned char*>(ctx->batchStage[stageSlot].p);
         BatchSlice* stageSlices = reinterpret_cast<BatchSlice*>(stage + sliceOffset);
         int sliceAt = 0;
@@ -908,7 +981,7 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
                 unsigned char* dst = stage + static_cast<size_t>(i) * sceneStride;
                 const size_t blobBytes = (pf.blob.size() + 255) & ~size_t(255);
                 std::memcpy(dst, pf.blob.data(), pf.blob.size());
-                std::memcpy(dst + blobBytes, pf.texels.data(), pf.texels.size() * sizeof(float4h));
+                if (!skins) std::memcpy(dst + blobBytes, pf.texels.data(), pf.texels.size() * sizeof(float4h));
                 BatchSlice sl{};
                 sl.fp.blob = devScenes + static_cast<size_t>(i) * sceneStride;
                 sl.fp.texels = reinterpret_cast<const float4*>(devScenes + static_cast<size_t>(i) * sceneStride + blobBytes);
@@ -933,7 +1006,15 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, int nScenes, con
             }
         }
         const size_t usedScenes = static_cast<size_t>(nC) * sceneStride;
-        CU_TRY(cudaMemcpyAsync(devScenes, stage, usedScenes, cudaMemcpyHostToDevice, stream));
+        if (skins) {
+            // only the box records of every scene go up (one strided copy), and the raw atlases; the texel pools are cut on the device
+            const size_t blobMax = (SceneBlobLayout(kSkinMaxBoxes).bytes() + 255) & ~size_t(255);
+            CU_TRY(cudaMemcpy2DAsync(devScenes, sceneStride, stage, sceneStride, blobMax, nC, cudaMemcpyHostToDevice, stream));
+            CU_TRY(cudaMemcpyAsync(devSkin, skinStage, static_cast<size_t>(nC) * skinRecord, cudaMemcpyHostToDevice, stream));
+            launch_slice_skins(devSkin, skinRecord, atlasBytes + kSkinMaxFaces * sizeof(SkinFaceSource), nC, stream);
+        } else {
+            CU_TRY(cudaMemcpyAsync(devScenes, stage, usedScenes, cudaMemcpyHostToDevice, stream));
+        }
         CU_TRY(cudaMemcpyAsync(devScenes + sliceOffset, stage + sliceOffset, static_cast<size_t>(nC) * sizeof(BatchSlice),
                                cudaMemcpyHostToDevice, stream));
         CU_TRY(cudaEventRecord(ctx->evStage[stageSlot], stream));
@@ -1032,7 +1113,8 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
         if (ctx->evStage[i]) cudaEventDestroy(ctx->evStage[i]);
         ctx->batchStage[i].release();
     }
-    for (DevBuf* b : {&ctx->batchScenes, &ctx->batchSlots, &ctx->batchRecords, &ctx->batchWave, &ctx->batchCounts}) b->release();
+    for (DevBuf* b : {&ctx->batchScenes, &ctx->batchSlots, &ctx->batchRecords, &ctx->batchWave, &ctx->batchCounts, &ctx->batchSkinSrc}) b->release();
+    for (int i = 0; i < 2; ++i) ctx->batchSkinStage[i].release();
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
     if (ctx->graphExec) cudaGraphExecDestroy(ctx->graphExec);
@@ -1565,7 +1647,7 @@ int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, 
     cudaStream_t caller = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     {
         bool handled = false;
-        const int rc = render_batch_grouped(ctx, scenes, nScenes, cfg, static_cast<float4*>(dOutF32), static_cast<uchar4*>(dOutU8),
+        const int rc = render_batch_grouped(ctx, scenes, nullptr, nScenes, cfg, static_cast<float4*>(dOutF32), static_cast<uchar4*>(dOutU8),
                                             caller, &handled);
         if (rc != MC_OK) return rc;
         if (handled) {
@@ -1602,6 +1684,55 @@ int32_t mcskin_cuda_context_render_batch(McContext* ctx, const McScene* scenes, 
     }
     ctx->stats = McRenderStats{};
     ctx->statsPending = false;
+    return MC_OK;
+}
+
+// Batches of skins straight from their atlases: n RGBA8 atlases (64x64 or 64x32, one
+// after the other) -> n images.  The grouped form lays every skin out on the host from its alpha bytes alone
+// and cuts the texel pools on the device; frame descriptions without a batched kernel form build the flat scenes
+// on the host (mcskin_build_skin_scene) and take render_batch's frame-by-frame path.
+int32_t mcskin_cuda_context_render_skin_batch(McContext* ctx, const uint8_t* atlases, int32_t atlasW, int32_t atlasH,
+                                              int32_t nSkins, const float* poses12, int32_t poseStride, const McConfig* cfg,
+                                              void* dOutF32, void* dOutU8, void* stream) {
+    if (!ctx || !atlases || !cfg || nSkins < 0 || poseStride < 0) return fail(MC_ERR_INVALID, "render_skin_batch: bad argument");
+    if (!((atlasW == 64 && atlasH == 64) || (atlasW == 64 && atlasH == 32)))
+        return fail(MC_ERR_INVALID, "Invalid skin dimensions: " + std::to_string(atlasW) + "x" + std::to_string(atlasH) +
+                                        " (expected 64x64 or 64x32)");
+    if (nSkins == 0) return MC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t caller = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const SkinBatchSrc src{atlases, atlasW, atlasH, poses12, poses12 ? poseStride : 0};
+    bool handled = false;
+    int rc = render_batch_grouped(ctx, nullptr, &src, nSkins, cfg, static_cast<float4*>(dOutF32), static_cast<uchar4*>(dOutU8),
+                                  caller, &handled);
+    if (rc != MC_OK) return rc;
+    if (handled) {
+        ctx->stats = McRenderStats{};
+        ctx->statsPending = false;
+        return MC_OK;
+    }
+    // host-built scenes, a chunk at a time (each needs 52 KB of texels)
+    const size_t atlasBytes = static_cast<size_t>(atlasW) * atlasH * 4;
+    const int chunk = 64;
+    std::vector<McBox> boxes(static_cast<size_t>(chunk) * kSkinMaxBoxes);
+    std::vector<float> texels(static_cast<size_t>(chunk) * (kSkinMaxTexels + 16) * 4);
+    std::vector<McScene> scenes(chunk);
+    const size_t pixels = static_cast<size_t>(std::max(cfg->width, 0)) * std::max(cfg->height, 0);
+    for (int c0 = 0; c0 < nSkins; c0 += chunk) {
+        const int n = std::min(chunk, nSkins - c0);
+        for (int i = 0; i < n; ++i) {
+            const float* pose = poses12 ? poses12 + static_cast<size_t>(c0 + i) * poseStride : nullptr;
+            rc = mcskin_build_skin_scene(atlases + static_cast<size_t>(c0 + i) * atlasBytes, atlasW, atlasH, pose,
+                                         boxes.data() + static_cast<size_t>(i) * kSkinMaxBoxes,
+                                         texels.data() + static_cast<size_t>(i) * (kSkinMaxTexels + 16) * 4, &scenes[i]);
+            if (rc != MC_OK) return rc;
+        }
+        rc = mcskin_cuda_context_render_batch(ctx, scenes.data(), n, cfg,
+                                              dOutF32 ? static_cast<float4*>(dOutF32) + static_cast<size_t>(c0) * pixels : nullptr,
+                                              dOutU8 ? static_cast<uchar4*>(dOutU8) + static_cast<size_t>(c0) * pixels : nullptr, caller);
+        if (rc != MC_OK) return rc;
+        // the host arrays are reused by the next chunk: the uploads above are staged synchronously (pageable sources)
+    }
     return MC_OK;
 }
 

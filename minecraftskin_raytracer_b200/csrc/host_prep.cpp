@@ -99,13 +99,13 @@ extern "C" int32_t mcskin_generate_tiles(int32_t w, int32_t h, int32_t ts, McTil
 }
 
 int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, float aspectOverride,
-                  PreparedFrame& out, std::string& error) {
+                  PreparedFrame& out, std::string& error, const ExternalTexels* ext) {
     if (!scene) {
         error = "scene is null";
         return MC_ERR_INVALID;
     }
     if (scene->n_boxes < 0 || scene->n_texels < 0 || (scene->n_boxes > 0 && !scene->boxes) ||
-        (scene->n_texels > 0 && !scene->texels_rgba)) {
+        (scene->n_texels > 0 && !scene->texels_rgba && !ext)) {
         error = "scene has negative counts or null arrays";
         return MC_ERR_INVALID;
     }
@@ -179,12 +179,18 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
     f.shininess = cfg.shininess;
 
     // texel pool + the two synthetic 1x1 textures
-    out.texels.resize(static_cast<size_t>(scene->n_texels) + 2);
-    if (scene->n_texels > 0) std::memcpy(out.texels.data(), scene->texels_rgba, sizeof(float4h) * scene->n_texels);
     const int magentaTexel = scene->n_texels;      // null Triangle::texture (intersection.cpp:303-306)
     const int blankTexel = scene->n_texels + 1;    // empty TextureRegion -> Color() (texture_region.h:20-22)
-    out.texels[magentaTexel] = {1.0f, 0.0f, 1.0f, 1.0f};
-    out.texels[blankTexel] = {0.0f, 0.0f, 0.0f, 1.0f};
+    if (ext) {  // the pool is filled on the device; only the two synthetic texels that follow it live here
+        out.texels.resize(2);
+        out.texels[0] = {1.0f, 0.0f, 1.0f, 1.0f};
+        out.texels[1] = {0.0f, 0.0f, 0.0f, 1.0f};
+    } else {
+        out.texels.resize(static_cast<size_t>(scene->n_texels) + 2);
+        if (scene->n_texels > 0) std::memcpy(out.texels.data(), scene->texels_rgba, sizeof(float4h) * scene->n_texels);
+        out.texels[magentaTexel] = {1.0f, 0.0f, 1.0f, 1.0f};
+        out.texels[blankTexel] = {0.0f, 0.0f, 0.0f, 1.0f};
+    }
 
     out.boxes.resize(scene->n_boxes);
     std::vector<std::array<float, 3>> rejectLo(scene->n_boxes), rejectHi(scene->n_boxes);
@@ -258,8 +264,13 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
             }
             d.face[k].x = offset;
             d.face[k].y = w | (h << 16);
-            for (long long t = 0; opaque && t < static_cast<long long>(w) * h; ++t)
-                if (out.texels[static_cast<size_t>(offset + t)].w == 0.0f) opaque = false;
+            if (ext) {
+                // (windows into the device-side pool; the synthetic texels are opaque)
+                if (offset < scene->n_texels) opaque = opaque && ext->boxOpaque[b] != 0;
+            } else {
+                for (long long t = 0; opaque && t < static_cast<long long>(w) * h; ++t)
+                    if (out.texels[static_cast<size_t>(offset + t)].w == 0.0f) opaque = false;
+            }
         }
         // an unposed box without see-through texels is hit by exactly the rays that pass the slab test, at
         // the slab distance: occlusion queries need no face / texel evaluation for it (occluded_among)

@@ -1149,6 +1149,32 @@ __global__ void k_aov(const DevFrame fr, const FramePointers fp, int* outTriId) 
     outTriId[py * fr.width + px] = h.box >= 0 ? h.box * 12 + h.face * 2 : -1;
 }
 
+// Texel pools of a batch of skins cut out of their raw atlases: block (f, k) = face f of skin k.
+// Texel = byte / 255.0f per channel (image.cpp:14-21: an IEEE division, as on the host); a window position outside
+// the atlas keeps Color() = (0, 0, 0, 1) (image.h:21-33).
+__global__ void k_slice_skins(const unsigned char* records, const size_t recordStride, const size_t jobOffset) {
+    const SkinSliceJob job = *reinterpret_cast<const SkinSliceJob*>(records + blockIdx.y * recordStride + jobOffset);
+    const int f = blockIdx.x;
+    if (f == 0 && threadIdx.x == 0) {  // the synthetic texels that follow every pool (host_prep.cpp)
+        job.texels[job.nTexels] = make_float4(1.0f, 0.0f, 1.0f, 1.0f);
+        job.texels[job.nTexels + 1] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    }
+    if (f >= job.nFaces) return;
+    const SkinFaceSource src = job.faces[f];
+    const int n = src.w * src.h;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int row = i / src.w, col = i - row * src.w;
+        const int sx = src.x + (src.mirror ? src.w - 1 - col : col), sy = src.y + row;
+        float4 t = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+        if (sx >= 0 && sx < job.atlasW && sy >= 0 && sy < job.atlasH) {
+            const uchar4 b = job.atlas[sy * job.atlasW + sx];
+            t = make_float4(static_cast<float>(b.x) / 255.0f, static_cast<float>(b.y) / 255.0f, static_cast<float>(b.z) / 255.0f,
+                            static_cast<float>(b.w) / 255.0f);
+        }
+        job.texels[src.dst + i] = t;
+    }
+}
+
 inline int blocks_for(int n) { return (n + kBlockThreads - 1) / kBlockThreads; }
 
 }  // namespace
@@ -1330,6 +1356,9 @@ void launch_powf(const float* x, const float* y, int n, float* out, cudaStream_t
 }
 void launch_sincos(const float* angles, int n, float* outSin, float* outCos, cudaStream_t stream) {
     if (n > 0) k_sincos<<<blocks_for(n), kBlockThreads, 0, stream>>>(angles, n, outSin, outCos);
+}
+void launch_slice_skins(const unsigned char* records, size_t recordStride, size_t jobOffset, int nSkins, cudaStream_t stream) {
+    if (nSkins > 0) k_slice_skins<<<dim3(kSkinMaxFaces, nSkins), 96, 0, stream>>>(records, recordStride, jobOffset);
 }
 void launch_aov(const DevFrame& fr, const FramePointers& fp, int* outTriId, cudaStream_t stream) {
     if (fr.width <= 0 || fr.height <= 0) return;

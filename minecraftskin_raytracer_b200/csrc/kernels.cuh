@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "dev_types.cuh"
+#include "host_prep.hpp"
 #include "mcskin_cuda.h"
 
 namespace mcskin {
@@ -147,5 +148,15 @@ void launch_peer_wait(const unsigned int* flags, int n, unsigned int value, unsi
 void launch_powf(const float* x, const float* y, int n, float* out, cudaStream_t stream);
 void launch_sincos(const float* angles, int n, float* outSin, float* outCos, cudaStream_t stream);
 void launch_aov(const DevFrame& fr, const FramePointers& fp, int* outTriId, cudaStream_t stream);
+
+// Skin slicing on the device (SkinParser::parse, skin_parser.cpp:11-110): one job per skin.
+struct SkinSliceJob {
+    const uchar4* atlas;            // raw RGBA8 atlas, atlasW x atlasH
+    const SkinFaceSource* faces;    // where every face's texels come from (host_prep.hpp)
+    float4* texels;                 // the scene's pool: nTexels texels, then the two synthetic ones
+    int atlasW, atlasH, nFaces, nTexels;
+};
+// records: nSkins staging records of recordStride bytes in device memory, each with its SkinSliceJob at jobOffset
+void launch_slice_skins(const unsigned char* records, size_t recordStride, size_t jobOffset, int nSkins, cudaStream_t stream);
 
 }  // namespace mcskin

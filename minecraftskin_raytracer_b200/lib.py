@@ -39,7 +39,8 @@ EXPORTS = [
     "mcskin_primary_launch_order", "mcskin_cuda_context_render_tiles_into_frame", "mcskin_partition_tiles",
     "mcskin_cuda_host_register", "mcskin_cuda_host_unregister", "mcskin_cuda_render_batch_multi",
     "mcskin_cuda_enable_peer_access", "mcskin_cuda_context_render_scene_tiles",
-    "mcskin_cuda_context_debug_block_times",
+    "mcskin_cuda_context_debug_block_times", "mcskin_cuda_context_render_skin_batch",
+    "mcskin_skin_layout",
 ]
 
 
@@ -132,6 +133,22 @@ def build_skin_scene(atlas: np.ndarray, pose=None) -> FlatScene:
                                         None if p is None else _ptr(p, C.c_float), _ptr(boxes, _abi.McBox),
                                         _ptr(texels, C.c_float), C.byref(cs)))
     return FlatScene.from_c(cs)
+
+
+def skin_layout(atlas: np.ndarray, pose=None):
+    """mcskin_skin_layout: (boxes, faces [n, 6] = (dst, x, y, w, h, mirror), box_opaque, n_texels) of a skin — its flat
+    scene without the float texels (host code)."""
+    atlas = np.ascontiguousarray(atlas, dtype=np.uint8)
+    p = pose_array(pose)
+    boxes = np.zeros(12, dtype=_abi.BOX_DTYPE)
+    faces = np.zeros((72, 6), dtype=np.int32)
+    opaque = np.zeros(12, dtype=np.uint8)
+    n_faces = C.c_int32(0)
+    cs = McScene()
+    _check(_lib.mcskin_skin_layout(_ptr(atlas, C.c_uint8), C.c_int32(atlas.shape[1]), C.c_int32(atlas.shape[0]),
+                                   None if p is None else _ptr(p, C.c_float), _ptr(boxes, _abi.McBox), _ptr(faces, C.c_int32),
+                                   C.byref(n_faces), _ptr(opaque, C.c_uint8), C.byref(cs)))
+    return boxes[:cs.n_boxes].copy(), faces[:n_faces.value].copy(), opaque[:cs.n_boxes].copy(), int(cs.n_texels)
 
 
 # ---------------------------------------------------------------- whole-frame calls
@@ -346,6 +363,27 @@ class Context:
         _check(_lib.mcskin_cuda_context_render_batch(self._h, arr, C.c_int32(len(scenes)), C.byref(cfg),
                                                      C.c_void_p(d_out_f32 or None), C.c_void_p(d_out_u8 or None),
                                                      C.c_void_p(stream or None)))
+        self.cfg = _abi.copy_config(cfg)
+
+    def render_skin_batch(self, atlases: np.ndarray, cfg: McConfig, poses=None, d_out_f32: int = 0, d_out_u8: int = 0, stream: int = 0):
+        """Asynchronous: skins straight from their RGBA8 atlases, uint8 [n, H, 64, 4] (H = 64 or 32) -> image i of the
+        [n, H, W, 4] device buffer(s).  poses: None (standing), one pose (name / index / 12 numbers) for all, or [n, 12]."""
+        atlases = np.ascontiguousarray(atlases, dtype=np.uint8)
+        if atlases.ndim != 4 or atlases.shape[3] != 4:
+            raise ValueError("atlases must be uint8 [n, H, W, 4]")
+        n, h, w = atlases.shape[:3]
+        p, stride = None, 0
+        if poses is not None:
+            arr = np.asarray(poses, dtype=np.float32) if not isinstance(poses, (str, int)) else None
+            if arr is not None and arr.ndim == 2:
+                p, stride = np.ascontiguousarray(arr.reshape(n, 12)), 12
+            else:
+                p = pose_array(poses)
+        self._keep = (atlases, p)
+        _check(_lib.mcskin_cuda_context_render_skin_batch(self._h, _ptr(atlases, C.c_uint8), C.c_int32(w), C.c_int32(h), C.c_int32(n),
+                                                          None if p is None else _ptr(p, C.c_float), C.c_int32(stride), C.byref(cfg),
+                                                          C.c_void_p(d_out_f32 or None), C.c_void_p(d_out_u8 or None),
+                                                          C.c_void_p(stream or None)))
         self.cfg = _abi.copy_config(cfg)
 
     def debug_block_times(self) -> np.ndarray:

@@ -68,6 +68,36 @@ def test_skin_scene_builder_equals_live_reference(mclib, reference):
         assert np.array_equal(poses[i], pose_array(name)), name
 
 
+def test_skin_layout_equals_the_scene_builder(mclib):
+    """mcskin_skin_layout (what render_skin_batch runs per skin before the device cuts the texel pool): the same boxes
+    and face windows as mcskin_build_skin_scene, and face sources that reproduce its texel pool from the atlas bytes."""
+    cases = [(synth_skin(0), None), (synth_skin(2, "legacy"), "walking"), (synth_skin(3, "slim"), "dab")]
+    a = synth_skin(5)
+    a[:16, 32:, 3] = 0          # head overlay fully transparent: dropped
+    a[16:32, 16:40, 3] = 255    # (body inner stays opaque)
+    cases.append((a, "running"))
+    b = synth_skin(6)
+    b[..., 3] = 255             # no holes at all
+    cases.append((b, None))
+    for atlas, pose in cases:
+        scene = mclib.build_skin_scene(atlas, pose)
+        boxes, faces, opaque, n_texels = mclib.skin_layout(atlas, pose)
+        assert boxes.tobytes() == np.ascontiguousarray(scene.boxes).tobytes()
+        assert n_texels == len(scene.texels) and len(faces) == 6 * len(boxes)
+        pool = np.zeros((n_texels, 4), dtype=np.float32)
+        for dst, x, y, w, h, mirror in faces:
+            win = atlas[y:y + h, x:x + w].astype(np.float32) / np.float32(255.0)
+            if mirror:
+                win = win[:, ::-1]
+            pool[dst:dst + w * h] = win.reshape(-1, 4)
+        assert np.array_equal(pool.view(np.uint32), np.ascontiguousarray(scene.texels, dtype=np.float32).view(np.uint32))
+        for i, bx in enumerate(boxes):
+            alphas = np.concatenate([pool[o:o + w * h, 3] for o, w, h in bx["face"]])
+            assert bool(opaque[i]) == bool((alphas != 0).all()), i
+    with pytest.raises(mclib.McSkinError):
+        mclib.skin_layout(np.zeros((48, 64, 4), dtype=np.uint8))
+
+
 def test_skin_scene_builder_rejects_bad_sizes(mclib):
     with pytest.raises(mclib.McSkinError) as e:
         mclib.build_skin_scene(np.zeros((48, 64, 4), dtype=np.uint8))

@@ -852,3 +852,56 @@ def test_batch_sharded_by_skin_over_devices(gpu, oracle):
         assert np.array_equal(u8, oracle.quantize(f32)), devices
     with pytest.raises(gpu.McSkinError):
         gpu.render_batch_multi(scenes, cfg, gpu.device_count() + 1)
+
+
+@pytest.mark.parametrize("kind,poses", [("64x64", None), ("64x64", "walking"), ("legacy", "dab"), ("64x64", "per_skin")],
+                         ids=["standing", "walking", "legacy_dab", "pose_per_skin"])
+def test_skin_batch_sliced_on_the_device(gpu, oracle, kind, poses):
+    """mcskin_cuda_context_render_skin_batch: raw atlases in, the texel pools cut on the device — the same bits as the
+    host builder's scenes through render_batch, and as the reference; skins whose outer layers are partly absent,
+    fully opaque or fully transparent change the box list per skin."""
+    import torch
+    from minecraftskin_raytracer_b200.scene import BUILTIN_POSE_ORDER, pose_array
+    n = 21
+    cfg = make_config(width=96, height=96, samples_per_pixel=4, max_bounces=2)
+    atlases = np.stack([synth_skin(300 + i, kind) for i in range(n)])
+    if kind == "64x64":
+        atlases[1, :, :, 3] = 255                      # no holes anywhere: every box opaque
+        atlases[2, 32:48, :, 3] = 0                    # body / arm / right-leg outer layers fully transparent: not built
+        atlases[3, :16, 32:, 3] = 0                    # head overlay fully transparent
+        atlases[4, 48:, :16, 3] = 0                    # left-leg outer layer fully transparent
+        atlases[4, 48:, 48:, 3] = 0                    # left-arm outer layer fully transparent
+        atlases[5, 16:32, 16:40, 3] = 0                # holes in an INNER box (body): pass-through
+    pose_list = None
+    if poses == "per_skin":
+        pose_list = np.stack([pose_array(BUILTIN_POSE_ORDER[i % len(BUILTIN_POSE_ORDER)]) for i in range(n)])
+    scenes = [gpu.build_skin_scene(atlases[i], poses if pose_list is None else pose_list[i]) for i in range(n)]
+    assert len({len(s.boxes) for s in scenes}) > (1 if kind == "64x64" else 0)
+    ctx = gpu.Context(0)
+    try:
+        ctx.set_option("batch_group", 8)   # 21 = 8 + 8 + 5: staging buffers are reused
+        a = torch.zeros((n, cfg.height, cfg.width, 4), dtype=torch.float32, device="cuda:0")
+        b = torch.zeros_like(a)
+        b8 = torch.zeros((n, cfg.height, cfg.width, 4), dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        ctx.render_batch(scenes, cfg, a.data_ptr(), 0, 0)
+        ctx.sync()
+        for _ in range(2):
+            ctx.render_skin_batch(atlases, cfg, poses if pose_list is None else pose_list, b.data_ptr(), b8.data_ptr(), 0)
+            ctx.sync()
+        got, want = b.cpu().numpy(), a.cpu().numpy()
+        assert np.array_equal(_bits(got), _bits(want))
+        assert np.array_equal(b8.cpu().numpy(), oracle.quantize(got))
+        for i in (0, 2, 5):
+            assert pixel_report(got[i], oracle.render(scenes[i], cfg), oracle.quantize)["within1"] >= 0.999
+        # a frame description without a batched kernel form (spp 3 has no pixel-per-lane... DOF draws): host-built scenes
+        cfg2 = make_config(width=64, height=64, samples_per_pixel=300, max_bounces=1)
+        c = torch.zeros((2, 64, 64, 4), dtype=torch.float32, device="cuda:0")
+        ctx.render_skin_batch(atlases[:2], cfg2, None, c.data_ptr(), 0, 0)
+        ctx.sync()
+        single, _, _ = gpu.render(gpu.build_skin_scene(atlases[1]), cfg2)
+        assert np.array_equal(_bits(c[1].cpu().numpy()), _bits(single))
+        with pytest.raises(gpu.McSkinError):
+            ctx.render_skin_batch(np.zeros((1, 48, 64, 4), dtype=np.uint8), cfg, None, b.data_ptr(), 0, 0)
+    finally:
+        ctx.close()
