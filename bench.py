@@ -51,6 +51,9 @@ EXTRA_FRAMES = [
     ("c2_legacy_1080p_4spp_4b", 2, "legacy", None, dict(width=1920, height=1080, samples_per_pixel=4, max_bounces=4)),
     ("c3_slim_4k_16spp_4b", 3, "slim", None, dict(width=3840, height=2160, samples_per_pixel=16, max_bounces=4)),
     ("c5_8k_64spp_8b", 5, "64x64", None, dict(width=7680, height=4320, samples_per_pixel=64, max_bounces=8)),
+    # SURVEY §8d secondary rows of the headline: pose 1 ("walking", 8 rotated boxes) and hard shadows
+    ("headline_walking_1080p_16spp_4b", 0, "64x64", "walking", dict(width=1920, height=1080, samples_per_pixel=16, max_bounces=4)),
+    ("headline_hard_shadows_1080p_16spp_4b", 0, "64x64", None, dict(width=1920, height=1080, samples_per_pixel=16, max_bounces=4, soft_shadows=0)),
 ]
 C4_SKINS_PER_GPU = 512
 C4_CONFIG = dict(width=256, height=256, samples_per_pixel=4, max_bounces=2)

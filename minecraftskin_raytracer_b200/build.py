@@ -15,7 +15,8 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "_lib"
 LIB_PATH = LIB_DIR / "libmcskin_cuda.so"
 
-CUDA_SOURCES = ["kernels.cu", "wavefront.cu", "capi.cu"]
+# kernels_plain.cu / wavefront_plain.cu: the same kernels built without pose code (csrc/dev_types.cuh)
+CUDA_SOURCES = ["kernels.cu", "wavefront.cu", "kernels_plain.cu", "wavefront_plain.cu", "capi.cu"]
 HOST_SOURCES = ["host_prep.cpp", "skin_scene.cpp"]
 
 # --fmad=false: the geometry chain must round like the x86-64 reference build (no FMA);

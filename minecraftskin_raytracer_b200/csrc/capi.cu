@@ -381,9 +381,12 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
             CU_TRY(cudaMemcpyAsync(list.count, &list.capacity, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
         }
         if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
-        const bool seeded = launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
-                                           seedTiles, ctx->smCount * ctx->primaryBlocksPerSm,
-                                           heavyTarget, stream);
+        // (two builds of the kernels: the one without pose code for scenes in which no box is posed; dev_types.cuh)
+        const bool posed = f.any_rotated != 0;
+        const bool seeded = posed ? launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
+                                                   seedTiles, ctx->smCount * ctx->primaryBlocksPerSm, heavyTarget, stream)
+                                  : plain::launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
+                                                          seedTiles, ctx->smCount * ctx->primaryBlocksPerSm, heavyTarget, stream);
         ctx->tileSeedValid = seedsCacheable && seeded;
         // from here on every pixel of the band outside the figure's screen rectangle is final: the host
         // copy of the image may start (render_host).  Inside a capture this must be a real event-record
@@ -394,9 +397,11 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
         unsigned int* groupCounter = static_cast<unsigned int*>(ctx->countLog.p) + nChunks + c;
         const int shadeGrid = ctx->smCount * ctx->shadeBlocksPerSm;
         if (ctx->shadeMode == 0) {
-            launch_wavefront(f, fp, band, list, wave, groupCounter, stream, &launches);
+            if (posed) launch_wavefront(f, fp, band, list, wave, groupCounter, stream, &launches);
+            else plain::launch_wavefront(f, fp, band, list, wave, groupCounter, stream, &launches);
         } else {
-            launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
+            if (posed) launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
+            else plain::launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
             ++launches;
         }
         if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 2], stream));
@@ -1026,12 +1031,16 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, const SkinBatchS
             const BatchSlice& first = stageSlices[groupFirstSlice[g]];
             const DevFrame& f = ctx->batchPreps[groups[g][0]].frame;
             launch_batch_reset(gs, nS, stream);
-            if (!launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), !seeded, gs, nS, first.fp.blob_bytes,
-                                      ctx->smCount * ctx->primaryBlocksPerSm, stream))
-                return MC_OK;  // no batched primary kernel for this frame description: frame-by-frame path instead
+            const bool posed = f.any_rotated != 0;  // (equal frame descriptions: equal for the whole group)
+            const bool launched = posed ? launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), !seeded, gs, nS,
+                                                               first.fp.blob_bytes, ctx->smCount * ctx->primaryBlocksPerSm, stream)
+                                        : plain::launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), !seeded, gs, nS,
+                                                                      first.fp.blob_bytes, ctx->smCount * ctx->primaryBlocksPerSm, stream);
+            if (!launched) return MC_OK;  // no batched primary kernel for this frame description: frame-by-frame path instead
             seeded = true;  // same image geometry for every scene of the batch
             int launches = 0;
-            launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
+            if (posed) launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
+            else plain::launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
         }
         CU_TRY(cudaGetLastError());
     }

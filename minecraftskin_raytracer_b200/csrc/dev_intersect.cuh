@@ -58,6 +58,7 @@ struct SceneView {
     uint32_t posed_mask;   // among boxes 0..31: never pre-rejected (none today; posed boxes carry world bounds)
     uint32_t usable_mask;  // among boxes 0..31: exist and have triangles
     uint32_t opaque_mask;  // among boxes 0..31: unposed and without see-through texels (kBoxOpaque)
+    uint32_t rotated_mask; // among boxes 0..31: posed (kBoxRotated); their lo / hi are loose world-space bounds
 };
 
 __device__ __forceinline__ V3 face_normal(int face) {
@@ -197,6 +198,75 @@ struct BoxHit {
     bool flip;
 };
 
+__device__ __forceinline__ float rcp_fast(float x) {  // approximate reciprocal: the margins absorb its error
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// World -> box space of a posed box for CONSERVATIVE tests only (the exact path is mesh_test): undo rotZ, then rotX,
+// about the pivot.  Same formulas, but nothing downstream depends on their last bits — every user adds margins
+// four orders of magnitude above their rounding.
+__device__ __forceinline__ V3 to_box_space(const DevBox& bx, V3 p, bool isPoint) {
+    const V3 pivot = isPoint ? ld3(bx.pivot) : mk3(0.0f, 0.0f, 0.0f);
+    V3 q = p - pivot;
+    if (bx.flags & kBoxRotZ) {
+        const float nx = q.x * bx.inv_cz - q.y * bx.inv_sz, ny = q.x * bx.inv_sz + q.y * bx.inv_cz;
+        q.x = nx;
+        q.y = ny;
+    }
+    if (bx.flags & kBoxRotX) {
+        const float ny = q.y * bx.inv_cx - q.z * bx.inv_sx, nz = q.y * bx.inv_sx + q.z * bx.inv_cx;
+        q.y = ny;
+        q.z = nz;
+    }
+    return q + pivot;
+}
+
+// A cheap second opinion on a posed box that survived the test against its (loose) world-space bounds: the slab
+// test again in the box's own space, in approximate arithmetic, against the box grown by 1e-2 (the transform and
+// the approximate reciprocals are good to ~1e-5 here).  true = the ray surely misses the box, or — LIMITED — enters
+// it beyond `limit`; false = the exact evaluation has to decide.
+template <bool LIMITED>
+__device__ __forceinline__ bool posed_box_missed(const DevBox& bx, const Ray& ray, float limit) {
+    constexpr float kPad = 1e-2f;
+    const V3 o = to_box_space(bx, ray.o, true);
+    const V3 d = to_box_space(bx, ray.d, false);  // |d| = 1 up to rounding: distances along it are world distances
+    float tmin = -FLT_MAX, tmax = FLT_MAX;
+    const float os[3] = {o.x, o.y, o.z}, ds[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float lo = bx.lo[k] - kPad, hi = bx.hi[k] + kPad;
+        if (fabsf(ds[k]) < 1e-6f) {
+            if (os[k] < lo || os[k] > hi) return true;
+            continue;
+        }
+        const float inv = rcp_fast(ds[k]);
+        const float a = (lo - os[k]) * inv, b = (hi - os[k]) * inv;
+        tmin = fmaxf(tmin, fminf(a, b));
+        tmax = fminf(tmax, fmaxf(a, b));
+    }
+    // relative slack on the distances for the approximate reciprocal (2^-22) and |d| != 1
+    const float slack = 1e-4f * (fabsf(tmin) + fabsf(tmax)) + 1e-3f;
+    if (fmaxf(tmin, 0.0f) > tmax + slack) return true;
+    if (LIMITED && !(tmin - slack < limit)) return true;
+    return false;
+}
+
+// Clears from `mask` (boxes 0..31 that survived the world-space reject pass) the posed boxes the ray surely misses.
+template <bool LIMITED>
+__device__ __forceinline__ uint32_t drop_missed_posed(const SceneView& sc, const Ray& ray, uint32_t mask, float limit) {
+    if (!kPosedScenes) return mask;  // (this build of the kernels is only ever given scenes without poses)
+    uint32_t todo = mask & sc.rotated_mask;
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        if (posed_box_missed<LIMITED>(sc.boxes[i], ray, limit)) mask &= ~(1u << i);
+    }
+    return mask;
+}
+
+
 // intersectAABB (intersection.cpp:200-371) against one box, ray already in box space.
 __device__ __forceinline__ bool box_test(const SceneView& sc, const DevBox& bx, V3 o, V3 d, V3 inv, BoxHit& out) {
     Slab s;
@@ -252,7 +322,7 @@ __device__ __forceinline__ bool mesh_test(const SceneView& sc, const int box, co
     const DevBox& bx = sc.boxes[box];
     const uint32_t flags = bx.flags;
     if (flags & kBoxEmpty) return false;
-    const bool rotated = flags & kBoxRotated;
+    const bool rotated = kPosedScenes && (flags & kBoxRotated);
     const V3 pivot = ld3(bx.pivot);
     const bool doX = flags & kBoxRotX, doZ = flags & kBoxRotZ;
     V3 o = ray.o, d = ray.d, inv = pre.inv;
@@ -309,7 +379,11 @@ __device__ __forceinline__ uint32_t candidate_mask(const SceneView& sc, const Ra
         if (LIMITED) reject = reject || !(tmin < limit);
         if (reject) rejected |= 1u << i;
     }
-    return (~rejected | posed) & usable & all;
+    uint32_t mask = (~rejected | posed) & usable & all;
+    // posed boxes were tested against loose world-space bounds: ask again in their own space before the exact
+    // evaluation (nothing to do — one uniform branch — in a scene without poses)
+    if (base == 0) mask = drop_missed_posed<LIMITED>(sc, ray, mask, limit);
+    return mask;
 }
 
 // The boxes a pinhole ray through pixel (px, py) can reach: those whose screen rectangle holds the
@@ -344,7 +418,7 @@ __device__ __forceinline__ uint32_t candidate_mask_among(const SceneView& sc, co
         const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
         if (fmaxf(tmin, 0.0f) > tmax) rejected |= 1u << i;
     }
-    return mask & (~rejected | sc.posed_mask);
+    return drop_missed_posed<false>(sc, ray, mask & (~rejected | sc.posed_mask), 0.0f);
 }
 
 // any_hit for a ray known to reach only the boxes of `allow` (see pixel_box_mask): a box outside the mask cannot be hit
@@ -463,6 +537,7 @@ __device__ __forceinline__ bool occluded_among(const SceneView& sc, const Ray& r
                     }
                 }
                 mask &= ~rejected | sc.posed_mask;
+                mask = drop_missed_posed<true>(sc, ray, mask, dist);
             }
         } else {
             mask = candidate_mask<true>(sc, ray, pre, base, dist);
@@ -492,11 +567,6 @@ __device__ __forceinline__ bool occluded(const SceneView& sc, const Ray& ray, fl
 // Own arithmetic with generous margins (1 % + 0.01 on the growth, 1e-3 on the fractions):
 // the mask only ever drops boxes no shadow ray of the hit can reach, so restricting
 // occluded_among() to it cannot change a result.  Typical skins: ~2 of 12 boxes survive.
-__device__ __forceinline__ float rcp_fast(float x) {  // approximate reciprocal: the margins absorb its error
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 // Clips the segment a + s*d, s in [0,1], against the box [lo-grow, hi+grow]; inv = 1/d.
 __device__ __forceinline__ bool bundle_clip(V3 a, V3 d, V3 inv, V3 lo, V3 hi, float grow, float* sEnd) {
     const float ax0 = (lo.x - grow - a.x) * inv.x, ax1 = (hi.x + grow - a.x) * inv.x;
@@ -514,6 +584,71 @@ __device__ __forceinline__ bool bundle_clip(V3 a, V3 d, V3 inv, V3 lo, V3 hi, fl
     *sEnd = s1;
     return !(outX || outY || outZ) && s0 <= s1 + 1e-3f;
 }
+
+// Can any segment from `from` to a point within `radius` of from + d touch the box [lo, hi]?  (See bundle_box_mask.)
+// pad: how far the vectors may be off (0 for world-space boxes, whose bounds are the reference's own floats; the
+// rounding allowance of to_box_space otherwise): the box is grown by it for the clips, and the release rule asks
+// for an origin that much beyond a slab.
+__device__ __forceinline__ bool bundle_reaches(V3 from, V3 d, V3 lo, V3 hi, float radius, float pad) {
+    const float growFull = radius * 1.01f + 0.01f + pad;
+    const V3 inv = mk3(rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z));
+    if (fabsf(d.x) < 1e-6f || fabsf(d.y) < 1e-6f || fabsf(d.z) < 1e-6f) {
+        // the centre segment does not move along some axis (rare): the general clip
+        float sEnd;
+        if (!bundle_clip(from, d, inv, lo, hi, growFull, &sEnd)) return false;
+        const float reach = fminf(fmaxf(sEnd + 1e-3f, 0.0f), 1.0f);
+        float unused;
+        return bundle_clip(from, d, inv, lo, hi, reach * radius * 1.01f + 0.01f + pad, &unused);
+    }
+    // A ray that starts beyond a slab of the box and moves further away along that axis cannot
+    // enter the box (the reference's own slab test gives tmax < 0 for it).  Every ray of the
+    // bundle has a direction within growFull of d, so this holds for all of them at once.  It is
+    // what releases the box a hit lies ON (origin = hit point + normal * 1e-3, just outside it):
+    // without it that box would survive every distance-based clip.
+    if ((from.x > hi.x + pad && d.x > growFull) || (from.x < lo.x - pad && d.x < -growFull) ||
+        (from.y > hi.y + pad && d.y > growFull) || (from.y < lo.y - pad && d.y < -growFull) ||
+        (from.z > hi.z + pad && d.z > growFull) || (from.z < lo.z - pad && d.z < -growFull))
+        return false;
+    // Every axis moves: growing a slab by g widens its parameter interval by g*|1/d| at both ends,
+    // so the slab fractions of the ungrown box are computed once and serve both passes.
+    const V3 ainv = mk3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
+    const V3 g1 = ainv * growFull;
+    const float ax = (lo.x - from.x) * inv.x, bx = (hi.x - from.x) * inv.x;
+    const float ay = (lo.y - from.y) * inv.y, by = (hi.y - from.y) * inv.y;
+    const float az = (lo.z - from.z) * inv.z, bz = (hi.z - from.z) * inv.z;
+    const float nx = fminf(ax, bx), fx = fmaxf(ax, bx);
+    const float ny = fminf(ay, by), fy = fmaxf(ay, by);
+    const float nz = fminf(az, bz), fz = fmaxf(az, bz);
+    const float s0 = fmaxf(fmaxf(nx - g1.x, ny - g1.y), fmaxf(nz - g1.z, 0.0f));
+    const float s1 = fminf(fminf(fx + g1.x, fy + g1.y), fminf(fz + g1.z, 1.0f));
+    if (!(s0 <= s1 + 1e-3f)) return false;
+    const float reach = fminf(fmaxf(s1 + 1e-3f, 0.0f), 1.0f);
+    const V3 g2 = ainv * (reach * radius * 1.01f + 0.01f + pad);
+    const float t0 = fmaxf(fmaxf(nx - g2.x, ny - g2.y), fmaxf(nz - g2.z, 0.0f));
+    const float t1 = fminf(fminf(fx + g2.x, fy + g2.y), fminf(fz + g2.z, 1.0f));
+    return t0 <= t1 + 1e-3f;
+}
+
+// A posed box again in its own space, where it is tight (sc.lo / sc.hi hold loose world-space bounds of it): a
+// rotation keeps distances, so the bundle is the same bundle there.  Above all this releases the box the hit lies on,
+// which its world-space bounds — the hit is inside them — never do: without it every shadow ray of a hit on a posed
+// limb ran the limb's full pose transform and slab test, and its outer layer's.
+// (the shadow origin sits 1e-3 off the face it left, the rounding of the transform is ~1e-5: allow 1e-4)
+__device__ __forceinline__ bool posed_bundle_reaches(const DevBox& pb, V3 from, V3 d, float radius) {
+    return bundle_reaches(to_box_space(pb, from, true), to_box_space(pb, d, false), ld3(pb.lo), ld3(pb.hi), radius, 1e-4f);
+}
+
+__device__ __forceinline__ uint32_t drop_unreached_posed(const SceneView& sc, V3 from, V3 d, float radius, uint32_t mask) {
+    if (!kPosedScenes) return mask;
+    uint32_t todo = mask & sc.rotated_mask;
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        if (!posed_bundle_reaches(sc.boxes[i], from, d, radius)) mask &= ~(1u << i);
+    }
+    return mask;
+}
+
 
 __device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from, V3 to, float radius) {
     const int n = min(32, sc.n_boxes);
@@ -536,7 +671,7 @@ __device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from
             if (!bundle_clip(from, d, inv, lo, hi, reach * radius * 1.01f + 0.01f, &unused)) continue;
             mask |= 1u << i;
         }
-        return mask;
+        return drop_unreached_posed(sc, from, d, radius, mask);
     }
     // Every axis moves: growing a slab by g widens its parameter interval by g*|1/d| at both ends,
     // so the slab fractions of the ungrown box are computed once and serve both passes.
@@ -571,15 +706,16 @@ __device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from
         if (!(t0 <= t1 + 1e-3f)) continue;
         mask |= 1u << i;
     }
-    return mask;
+    return drop_unreached_posed(sc, from, d, radius, mask);
 }
+
 
 // Normal of the winning hit (intersection.cpp:355,366,399-401).
 __device__ __forceinline__ V3 hit_normal(const SceneView& sc, const Hit& h) {
     V3 n = face_normal(h.face);
     if (h.flip) n = n * -1.0f;
     const DevBox& bx = sc.boxes[h.box];
-    if (bx.flags & kBoxRotated) {
+    if (kPosedScenes && (bx.flags & kBoxRotated)) {
         n = rotate_about(n, mk3(0.0f, 0.0f, 0.0f), bx.flags & kBoxRotX, bx.fwd_cx, bx.fwd_sx, bx.flags & kBoxRotZ,
                          bx.fwd_cz, bx.fwd_sz);
         n = normalize3(n);

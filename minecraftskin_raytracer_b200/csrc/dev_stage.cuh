@@ -54,6 +54,7 @@ __device__ __forceinline__ SceneView scene_view(const unsigned char* blob, const
     sc.posed_mask = fr.posed_mask;
     sc.usable_mask = fr.usable_mask;
     sc.opaque_mask = fr.opaque_mask;
+    sc.rotated_mask = fr.rotated_mask;
     return sc;
 }
 

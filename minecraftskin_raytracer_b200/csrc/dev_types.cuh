@@ -9,8 +9,27 @@
 #include <stdint.h>
 #include <cuda_runtime.h>  // int2, __align__, __host__ __device__
 
+// The kernels are built twice: MCSKIN_POSED=1 (kernels.cu, wavefront.cu), the general form, and MCSKIN_POSED=0
+// (kernels_plain.cu, wavefront_plain.cu, into namespace mcskin::plain) for scenes in which no box is posed — the
+// standing figure of every BASELINE config — where the pose transform of the exact box test, the box-space second
+// opinions on posed boxes and what they cost in registers are compiled out.  The host picks the build per scene
+// (DevFrame::any_rotated).
+#ifndef MCSKIN_POSED
+#define MCSKIN_POSED 1
+#endif
+#if MCSKIN_POSED
+#define MCSKIN_VARIANT_BEGIN
+#define MCSKIN_VARIANT_END
+#define MCSKIN_VARIANT_NS ::mcskin
+#else
+#define MCSKIN_VARIANT_BEGIN namespace plain {
+#define MCSKIN_VARIANT_END }
+#define MCSKIN_VARIANT_NS ::mcskin::plain
+#endif
+
 namespace mcskin {
 
+constexpr bool kPosedScenes = MCSKIN_POSED != 0;
 constexpr int kFaceCount = 6;
 
 // One Mesh == one box (intersection.cpp:200-406).  144 bytes, 16-byte aligned so a
@@ -77,6 +96,8 @@ struct DevFrame {
     int n_boxes;
     uint32_t posed_mask, usable_mask;   // over boxes 0..31: posed / has triangles
     uint32_t opaque_mask;               // over boxes 0..31: kBoxOpaque
+    uint32_t rotated_mask;              // over boxes 0..31: kBoxRotated
+    int any_rotated;                    // some box (of any index) is posed: needs the MCSKIN_POSED=1 build of the kernels
     float light_pos[3], light_color[4], light_radius;
     float background[4];
     // integrator

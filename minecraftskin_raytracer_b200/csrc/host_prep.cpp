@@ -240,8 +240,10 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
             d.fwd_cz = std::cos(fz); d.fwd_sz = std::sin(fz);
         }
         d.flags = flags;
+        if ((flags & kBoxRotated) && !(flags & kBoxEmpty)) f.any_rotated = 1;
         if (b < 32) {
             if (!(flags & kBoxEmpty)) f.usable_mask |= 1u << b;
+            if ((flags & kBoxRotated) && !(flags & kBoxEmpty)) f.rotated_mask |= 1u << b;
         }
         bool opaque = true;  // no texel of any face has alpha == 0 (the pass-through rule, intersection.cpp:311)
         for (int k = 0; k < kFaceCount; ++k) {

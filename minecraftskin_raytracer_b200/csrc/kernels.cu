@@ -26,6 +26,7 @@
 #include "dev_sample.cuh"
 
 namespace mcskin {
+MCSKIN_VARIANT_BEGIN
 
 namespace {
 
@@ -1367,4 +1368,5 @@ void launch_aov(const DevFrame& fr, const FramePointers& fp, int* outTriId, cuda
     k_aov<<<grid, block, 0, stream>>>(fr, fp, outTriId);
 }
 
+MCSKIN_VARIANT_END
 }  // namespace mcskin

@@ -100,6 +100,15 @@ struct FramePointers {
     unsigned int blob_bytes;
 };
 
+// ---- launchers that exist in both builds of the kernels (mcskin:: for any scene, mcskin::plain:: for scenes
+//      without posed boxes; dev_types.cuh) ----
+#define MCSKIN_HOT_KERNEL_LAUNCHERS                                                                                      \
+    bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,      \
+                        int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, int heavyTargetTiles, \
+                        cudaStream_t stream);                                                                           \
+    void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,        \
+                      int gridBlocks, unsigned int* groupCounter, unsigned int firstSlot, cudaStream_t stream,          \
+                      int variant = 1);
 // Primary pass: per-tile jitter stream, camera rays, hit/miss classification, background
 // resolve of pixels no sample of which hits, work records for the rest.
 // classify == 0 puts every pixel on the work list (used for spp > 256 and for tests).
@@ -110,16 +119,14 @@ struct FramePointers {
 // Returns true when tileStates holds the seeded engines of the band's tiles afterwards.
 // heavyTargetTiles: the tiles that intersect the figure are split over more blocks while the launch has
 // fewer tiles than this.
-bool launch_primary(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                    int classify, uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, int heavyTargetTiles,
-                    cudaStream_t stream);
+MCSKIN_HOT_KERNEL_LAUNCHERS
+namespace plain {
+MCSKIN_HOT_KERNEL_LAUNCHERS
+}
 // Shading pass: full integrator for every sample of every listed pixel, ordered resolve.
 // Megakernel form of the shading pass over the listed pixels from `firstSlot` on.
 // variant 1: block-synchronous groups; variant 2: warp-autonomous groups with dynamic
 // distribution (groupCounter: a zeroed device counter; spp must be a power of two <= 32).
-void launch_shade(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                  int gridBlocks, unsigned int* groupCounter, unsigned int firstSlot, cudaStream_t stream,
-                  int variant = 1);
 
 // Single-query views of the same device code (all pointers are device memory).
 void launch_intersect(const DevFrame& fr, const FramePointers& fp, int box, const McRay* rays, int n, McHit* out,

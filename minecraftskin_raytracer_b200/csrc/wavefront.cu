@@ -8,6 +8,7 @@
 #include "dev_sample.cuh"
 
 namespace mcskin {
+MCSKIN_VARIANT_BEGIN
 
 namespace {
 
@@ -647,10 +648,11 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
     // pixels the queues could not take: megakernel, starting at the first slot beyond them
     // (never in a batch: its queues are sized for every pixel of a scene)
     if (!batch && wv.slotCapacity < list.capacity) {
-        launch_shade(fr, fp, band, list, grid, groupCounter, wv.slotCapacity, stream);
+        MCSKIN_VARIANT_NS::launch_shade(fr, fp, band, list, grid, groupCounter, wv.slotCapacity, stream);  // (this build's)
         ++n;
     }
     if (launches) *launches += n;
 }
 
+MCSKIN_VARIANT_END
 }  // namespace mcskin

@@ -89,14 +89,20 @@ bool wavefront_carve(const DevFrame& fr, void* base, size_t bytes, unsigned int 
 // megakernel) and writes the band image.  groupCounter: zeroed device counter.
 // batch / nScenes: device array of per-scene slices and its length (launches get gridDim.y = nScenes);
 // every slice must have slotCapacity >= its list's capacity (no megakernel overflow in batches).
-void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
-                      const WaveView& wave, unsigned int* groupCounter, cudaStream_t stream, int* launches,
-                      const BatchSlice* batch = nullptr, int nScenes = 1);
-void launch_batch_reset(const BatchSlice* batch, int nScenes, cudaStream_t stream);
-// The primary pass over the scenes of a batch (pixel-per-lane kernels only): returns false if the
+// launch_primary_batch: the primary pass over the scenes of a batch (pixel-per-lane kernels only): returns false if the
 // frame description needs one of the other primary kernels, which have no batched form.
-bool launch_primary_batch(const DevFrame& fr, const BandView& band, uint32_t* tileStates, bool seedTiles,
-                          const BatchSlice* batch, int nScenes, unsigned int blobBytes, int primaryTargetBlocks,
-                          cudaStream_t stream);
+// (declared for both builds of the kernels: dev_types.cuh)
+#define MCSKIN_HOT_WAVEFRONT_LAUNCHERS                                                                                   \
+    void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,    \
+                          const WaveView& wave, unsigned int* groupCounter, cudaStream_t stream, int* launches,         \
+                          const BatchSlice* batch = nullptr, int nScenes = 1);                                          \
+    void launch_batch_reset(const BatchSlice* batch, int nScenes, cudaStream_t stream);                                 \
+    bool launch_primary_batch(const DevFrame& fr, const BandView& band, uint32_t* tileStates, bool seedTiles,           \
+                              const BatchSlice* batch, int nScenes, unsigned int blobBytes, int primaryTargetBlocks,    \
+                              cudaStream_t stream);
+MCSKIN_HOT_WAVEFRONT_LAUNCHERS
+namespace plain {
+MCSKIN_HOT_WAVEFRONT_LAUNCHERS
+}
 
 }  // namespace mcskin
