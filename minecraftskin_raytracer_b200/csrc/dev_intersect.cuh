@@ -59,6 +59,7 @@ struct SceneView {
     uint32_t usable_mask;  // among boxes 0..31: exist and have triangles
     uint32_t opaque_mask;  // among boxes 0..31: unposed and without see-through texels (kBoxOpaque)
     uint32_t rotated_mask; // among boxes 0..31: posed (kBoxRotated); their lo / hi are loose world-space bounds
+    uint32_t opaque_posed_mask;  // among boxes 0..31: posed and without see-through texels
 };
 
 __device__ __forceinline__ V3 face_normal(int face) {
@@ -224,33 +225,51 @@ __device__ __forceinline__ V3 to_box_space(const DevBox& bx, V3 p, bool isPoint)
 }
 
 // A cheap second opinion on a posed box that survived the test against its (loose) world-space bounds: the slab
-// test again in the box's own space, in approximate arithmetic, against the box grown by 1e-2 (the transform and
-// the approximate reciprocals are good to ~1e-5 here).  true = the ray surely misses the box, or — LIMITED — enters
-// it beyond `limit`; false = the exact evaluation has to decide.
+// test again in the box's own space, in approximate arithmetic (the transform and the approximate reciprocals are
+// good to ~1e-5 here), against the box GROWN by 1e-2 — a ray that misses that surely misses the box — and, for
+// occlusion queries on boxes without see-through texels, against the box SHRUNK by 1e-2: a ray that passes through
+// that, and leaves even the grown box before `limit`, surely hits the box before the light, whatever the exact
+// arithmetic's last bits.  Everything in between is left to the exact evaluation.
+enum : int { kPosedUnknown = 0, kPosedMissed = 1, kPosedHitBeforeLimit = 2 };
 template <bool LIMITED>
-__device__ __forceinline__ bool posed_box_missed(const DevBox& bx, const Ray& ray, float limit) {
+__device__ __forceinline__ int posed_box_verdict(const DevBox& bx, const Ray& ray, float limit, bool opaque) {
     constexpr float kPad = 1e-2f;
     const V3 o = to_box_space(bx, ray.o, true);
     const V3 d = to_box_space(bx, ray.d, false);  // |d| = 1 up to rounding: distances along it are world distances
-    float tmin = -FLT_MAX, tmax = FLT_MAX;
+    float tmin = -FLT_MAX, tmax = FLT_MAX;        // grown box
+    float smin = -FLT_MAX, smax = FLT_MAX;        // shrunk box
+    bool sure = LIMITED && opaque;
     const float os[3] = {o.x, o.y, o.z}, ds[3] = {d.x, d.y, d.z};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float lo = bx.lo[k] - kPad, hi = bx.hi[k] + kPad;
         if (fabsf(ds[k]) < 1e-6f) {
-            if (os[k] < lo || os[k] > hi) return true;
+            if (os[k] < lo || os[k] > hi) return kPosedMissed;
+            sure = sure && os[k] > lo + 2.0f * kPad && os[k] < hi - 2.0f * kPad;
             continue;
         }
         const float inv = rcp_fast(ds[k]);
         const float a = (lo - os[k]) * inv, b = (hi - os[k]) * inv;
         tmin = fmaxf(tmin, fminf(a, b));
         tmax = fminf(tmax, fmaxf(a, b));
+        if (LIMITED) {
+            const float shift = 2.0f * kPad * fabsf(inv);  // the shrunk slab starts that much later and ends that much earlier
+            smin = fmaxf(smin, fminf(a, b) + shift);
+            smax = fminf(smax, fmaxf(a, b) - shift);
+        }
     }
     // relative slack on the distances for the approximate reciprocal (2^-22) and |d| != 1
     const float slack = 1e-4f * (fabsf(tmin) + fabsf(tmax)) + 1e-3f;
-    if (fmaxf(tmin, 0.0f) > tmax + slack) return true;
-    if (LIMITED && !(tmin - slack < limit)) return true;
-    return false;
+    if (fmaxf(tmin, 0.0f) > tmax + slack) return kPosedMissed;
+    if (LIMITED && !(tmin - slack < limit)) return kPosedMissed;
+    // through the shrunk box in front of the origin, and out of the grown one before the light: the hit distance
+    // (entry, or exit when the origin is inside) lies below tmax
+    if (LIMITED && sure && fmaxf(smin, 0.0f) + slack < smax && tmax + slack < limit) return kPosedHitBeforeLimit;
+    return kPosedUnknown;
+}
+template <bool LIMITED>
+__device__ __forceinline__ bool posed_box_missed(const DevBox& bx, const Ray& ray, float limit) {
+    return posed_box_verdict<LIMITED>(bx, ray, limit, false) == kPosedMissed;
 }
 
 // Clears from `mask` (boxes 0..31 that survived the world-space reject pass) the posed boxes the ray surely misses.
@@ -537,7 +556,16 @@ __device__ __forceinline__ bool occluded_among(const SceneView& sc, const Ray& r
                     }
                 }
                 mask &= ~rejected | sc.posed_mask;
-                mask = drop_missed_posed<true>(sc, ray, mask, dist);
+                if (kPosedScenes) {  // posed survivors: missed / surely hit before the light / ask the exact test
+                    uint32_t posedTodo = mask & sc.rotated_mask;
+                    while (posedTodo) {
+                        const int i = __ffs(posedTodo) - 1;
+                        posedTodo &= posedTodo - 1u;
+                        const int verdict = posed_box_verdict<true>(sc.boxes[i], ray, dist, (sc.opaque_posed_mask >> i) & 1u);
+                        if (verdict == kPosedHitBeforeLimit) return true;
+                        if (verdict == kPosedMissed) mask &= ~(1u << i);
+                    }
+                }
             }
         } else {
             mask = candidate_mask<true>(sc, ray, pre, base, dist);

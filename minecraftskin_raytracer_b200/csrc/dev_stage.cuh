@@ -55,6 +55,7 @@ __device__ __forceinline__ SceneView scene_view(const unsigned char* blob, const
     sc.usable_mask = fr.usable_mask;
     sc.opaque_mask = fr.opaque_mask;
     sc.rotated_mask = fr.rotated_mask;
+    sc.opaque_posed_mask = fr.opaque_posed_mask;
     return sc;
 }
 

@@ -97,6 +97,7 @@ struct DevFrame {
     uint32_t posed_mask, usable_mask;   // over boxes 0..31: posed / has triangles
     uint32_t opaque_mask;               // over boxes 0..31: kBoxOpaque
     uint32_t rotated_mask;              // over boxes 0..31: kBoxRotated
+    uint32_t opaque_posed_mask;         // over boxes 0..31: posed, and no texel of any face has alpha == 0
     int any_rotated;                    // some box (of any index) is posed: needs the MCSKIN_POSED=1 build of the kernels
     float light_pos[3], light_color[4], light_radius;
     float background[4];

@@ -281,6 +281,8 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
             d.flags = flags;
             if (b < 32) f.opaque_mask |= 1u << b;
         }
+        // (posed: no exact shortcut, but a ray well inside such a box needs no exact evaluation to be called occluded)
+        if (opaque && src.has_rotation && !(flags & kBoxEmpty) && b < 32) f.opaque_posed_mask |= 1u << b;
         // conservative world bounds of this box (posed boxes: rotate the 8 corners in double)
         double boxLo[3] = {1e300, 1e300, 1e300}, boxHi[3] = {-1e300, -1e300, -1e300};
         if (!(flags & kBoxEmpty)) {
