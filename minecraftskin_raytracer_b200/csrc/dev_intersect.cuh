@@ -60,6 +60,8 @@ struct SceneView {
     uint32_t opaque_mask;  // among boxes 0..31: unposed and without see-through texels (kBoxOpaque)
     uint32_t rotated_mask; // among boxes 0..31: posed (kBoxRotated); their lo / hi are loose world-space bounds
     uint32_t opaque_posed_mask;  // among boxes 0..31: posed and without see-through texels
+    uint32_t root_mask;    // among boxes 0..31: not enclosed by another box (0: no two-level reject pass); hi[i].w of a
+                           // root = the boxes it encloses
 };
 
 __device__ __forceinline__ V3 face_normal(int face) {
@@ -383,6 +385,40 @@ __device__ __forceinline__ uint32_t candidate_mask(const SceneView& sc, const Ra
         }
     }
     if (pre.parallel) return all & usable;
+    if (base == 0 && sc.root_mask != 0u) {
+        // Two levels: a box that lies well inside another one (an inner body part inside its outer layer) can only
+        // be hit by rays that pass the enclosing box's test — the host records for every enclosing box ("root")
+        // which boxes it contains (hi.w) — so the roots are tested first and the enclosed boxes only where their
+        // root survives: 6 + ~1.5 tests per ray on a skin with every outer layer instead of 12.
+        uint32_t survivors = 0u, enclosed = 0u;
+        auto test = [&](int i, uint32_t* children) {
+            const float4 L = sc.lo[i];
+            const float4 H = sc.hi[i];
+            const float ax = (L.x - ray.o.x) * pre.inv.x, bx = (H.x - ray.o.x) * pre.inv.x;
+            const float ay = (L.y - ray.o.y) * pre.inv.y, by = (H.y - ray.o.y) * pre.inv.y;
+            const float az = (L.z - ray.o.z) * pre.inv.z, bz = (H.z - ray.o.z) * pre.inv.z;
+            const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+            const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+            bool reject = fmaxf(tmin, 0.0f) > tmax;
+            if (LIMITED) reject = reject || !(tmin < limit);
+            *children = __float_as_uint(H.w);
+            return !reject;
+        };
+        for (uint32_t m = sc.root_mask & usable & all; m; m &= m - 1u) {
+            const int i = __ffs(m) - 1;
+            uint32_t children;
+            if (test(i, &children) || ((posed >> i) & 1u)) {
+                survivors |= 1u << i;
+                enclosed |= children;
+            }
+        }
+        for (uint32_t m = enclosed & usable & all; m; m &= m - 1u) {
+            const int i = __ffs(m) - 1;
+            uint32_t unused;
+            if (test(i, &unused) || ((posed >> i) & 1u)) survivors |= 1u << i;
+        }
+        return drop_missed_posed<LIMITED>(sc, ray, survivors, limit);
+    }
     uint32_t rejected = 0u;
 #pragma unroll 4
     for (int i = 0; i < n; ++i) {

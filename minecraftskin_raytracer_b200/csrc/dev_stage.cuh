@@ -56,6 +56,7 @@ __device__ __forceinline__ SceneView scene_view(const unsigned char* blob, const
     sc.opaque_mask = fr.opaque_mask;
     sc.rotated_mask = fr.rotated_mask;
     sc.opaque_posed_mask = fr.opaque_posed_mask;
+    sc.root_mask = fr.root_mask;
     return sc;
 }
 

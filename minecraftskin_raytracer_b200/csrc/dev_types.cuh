@@ -61,7 +61,7 @@ enum : uint32_t {
 
 // The scene blob: what a CTA stages into shared memory with one bulk copy.
 //   [ float4 lo[nPad] ][ float4 hi[nPad] ][ int4 rect[nPad] ][ DevBox boxes[n] ]      nPad = n rounded up to 4
-// lo[i] = (bounds_min, flags as bit pattern), hi[i] = (bounds_max, 0): the compact
+// lo[i] = (bounds_min, flags as bit pattern), hi[i] = (bounds_max, bit mask of the boxes box i encloses): the compact
 // operands of the reject pass; rect[i] = (x0, y0, x1, y1), the pixels (inclusive, 2-pixel margin) a pinhole
 // ray must pass through to reach box i (valid when DevFrame::box_rects_valid); the full records serve the
 // exact evaluation.
@@ -98,6 +98,7 @@ struct DevFrame {
     uint32_t opaque_mask;               // over boxes 0..31: kBoxOpaque
     uint32_t rotated_mask;              // over boxes 0..31: kBoxRotated
     uint32_t opaque_posed_mask;         // over boxes 0..31: posed, and no texel of any face has alpha == 0
+    uint32_t root_mask;                 // over boxes 0..31: boxes no other box encloses; 0 = no box encloses another
     int any_rotated;                    // some box (of any index) is posed: needs the MCSKIN_POSED=1 build of the kernels
     float light_pos[3], light_color[4], light_radius;
     float background[4];

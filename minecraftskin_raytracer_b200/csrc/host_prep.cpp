@@ -337,11 +337,48 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
         out.blob.assign(std::max<size_t>(16, lay.bytes()), 0);
         float* lo = reinterpret_cast<float*>(out.blob.data() + lay.loOffset());
         float* hi = reinterpret_cast<float*>(out.blob.data() + lay.hiOffset());
+        // Two-level reject pass: box i is ENCLOSED by box j when its reject bounds lie inside j's with 1e-3 to spare on
+        // every side (an inner body part inside its outer layer: 0.5) — a ray the slab test of j rejects then misses
+        // i in any float arithmetic.  Enclosing boxes ("roots") must not be enclosed themselves; every enclosed box
+        // hangs on one root.  Only among the first 32 boxes, and only when it saves tests.
+        std::vector<uint32_t> children(scene->n_boxes, 0u);
+        if (scene->n_boxes <= 32) {
+            std::vector<int> parent(scene->n_boxes, -1);
+            auto inside = [&](int i, int j) {
+                for (int k = 0; k < 3; ++k)
+                    if (!(rejectLo[i][k] >= rejectLo[j][k] + 1e-3f && rejectHi[i][k] <= rejectHi[j][k] - 1e-3f)) return false;
+                return true;
+            };
+            auto usable = [&](int b) { return !(out.boxes[b].flags & kBoxEmpty); };
+            for (int i = 0; i < scene->n_boxes; ++i) {
+                if (!usable(i)) continue;
+                for (int j = 0; j < scene->n_boxes && parent[i] < 0; ++j)
+                    if (j != i && usable(j) && inside(i, j)) parent[i] = j;
+            }
+            // one level only: a parent that is itself enclosed hands its children to its own root
+            for (int i = 0; i < scene->n_boxes; ++i) {
+                int p = parent[i], guard = 0;
+                while (p >= 0 && parent[p] >= 0 && guard++ < 64) p = parent[p];
+                parent[i] = p;
+            }
+            int nRoots = 0, nEnclosed = 0;
+            for (int i = 0; i < scene->n_boxes; ++i) {
+                if (!usable(i)) continue;
+                if (parent[i] < 0) { f.root_mask |= 1u << i; ++nRoots; }
+                else { children[parent[i]] |= 1u << i; ++nEnclosed; }
+            }
+            if (nEnclosed < 2) {  // nothing to gain
+                f.root_mask = 0u;
+                std::fill(children.begin(), children.end(), 0u);
+            }
+            (void)nRoots;
+        }
         for (int b = 0; b < scene->n_boxes; ++b) {
             const DevBox& d = out.boxes[b];
             std::memcpy(lo + 4 * b, rejectLo[b].data(), 3 * sizeof(float));
             std::memcpy(lo + 4 * b + 3, &d.flags, sizeof(uint32_t));
             std::memcpy(hi + 4 * b, rejectHi[b].data(), 3 * sizeof(float));
+            std::memcpy(hi + 4 * b + 3, &children[b], sizeof(uint32_t));
         }
         if (scene->n_boxes > 0)
             std::memcpy(out.blob.data() + lay.boxOffset(), out.boxes.data(), sizeof(DevBox) * scene->n_boxes);
