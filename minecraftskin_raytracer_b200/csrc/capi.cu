@@ -114,8 +114,8 @@ struct McContext {
     int shadeBlocksPerSm = 8;
     int softBlocksPerSm = 4;                 // persistent blocks of the soft-shadow kernel (its shared memory fits 4 per SM)
     int heavyTilesPerSm = 16;                // the figure's tiles are split over more blocks while a frame (all lanes) has fewer tiles per SM
-    int primaryBlocksPerSm = 2;              // split tiles over blocks only while a launch has fewer than this many per SM
-                                             // (every block of a split tile regenerates the tile's whole jitter stream)
+    int primaryBlocksPerSm = 8;              // split tiles over blocks while a frame (all lanes) has fewer tiles than this per SM
+                                             // (free of extra work: every block starts at its own round of the tile's stream)
     int waveQueuePct = 0;                    // hit-queue entries as a percentage of the paths (0: paths x (bounces + 1),
                                              // which cannot overflow; smaller queues redo overflowing paths in-thread)
     int frameLanes = 2;                      // a frame's tile rows are rendered on this many streams at once
@@ -128,9 +128,11 @@ struct McContext {
         cudaStream_t stream = nullptr;
         const void* map = nullptr;
         unsigned long long mapVersion = 0;
+        int wordsPerPixel = 0, statesPerTile = 0;  // the per-round states of split tiles depend on the sampling pattern
         bool operator==(const TileSeedKey& o) const {
             return width == o.width && tile_size == o.tile_size && first == o.first && stride == o.stride &&
-                   rows == o.rows && buf == o.buf && stream == o.stream && map == o.map && mapVersion == o.mapVersion;
+                   rows == o.rows && buf == o.buf && stream == o.stream && map == o.map && mapVersion == o.mapVersion &&
+                   wordsPerPixel == o.wordsPerPixel && statesPerTile == o.statesPerTile;
         }
     } tileSeedKey;
     bool tileSeedValid = false;
@@ -291,7 +293,17 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
     CU_TRY(ctx->countLog.reserve(sizeof(unsigned int) * 2 * nChunks));  // [active count | group counter] per chunk
     CU_TRY(ctx->slotPixel.reserve(slotCap * sizeof(uint2)));
     CU_TRY(ctx->records.reserve(std::max<size_t>(16, slotCap * recordBytesPerSlot)));
-    CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, unitsPerChunk * tilesPerUnit * 624 * sizeof(uint32_t))));
+    // Splitting the figure's tiles pays only when the frame (all lanes in flight) has too few tiles to
+    // keep every SM busy for as long as its slowest tile takes: below ~10 tiles per SM (B200 sweep:
+    // a whole 1080p frame, 2040 tiles, is best unsplit; half a frame is best split in three).
+    const long long tilesInFlight = nTilesAll * std::max(1, lanesInFlight);
+    const int heavyTarget = tilesInFlight * 3 >= 2ll * ctx->smCount * ctx->heavyTilesPerSm
+                                ? 0 : ctx->smCount * ctx->heavyTilesPerSm / std::max(1, lanesInFlight);
+    const int primaryTarget = ctx->smCount * ctx->primaryBlocksPerSm / std::max(1, lanesInFlight);
+    // engine states per tile: one per round of 256 pixels when tiles are split over blocks (kernels.cu)
+    const size_t statesPerTile = static_cast<size_t>(primary_states_per_tile(
+        f, static_cast<int>(std::min<size_t>(unitsPerChunk * tilesPerUnit, 0x7fffffff)), 1, primaryTarget, heavyTarget));
+    CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, unitsPerChunk * tilesPerUnit * statesPerTile * 624 * sizeof(uint32_t))));
     CU_TRY(cudaMemsetAsync(ctx->countLog.p, 0, sizeof(unsigned int) * 2 * nChunks, stream));
 
     while (ctx->passEvents.size() < static_cast<size_t>(3 * nChunks)) {
@@ -331,17 +343,12 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
     seedKey.width = f.width; seedKey.tile_size = f.tile_size; seedKey.first = first; seedKey.stride = stride;
     seedKey.rows = mapped ? spec.nTiles : nRows; seedKey.buf = ctx->tileStates.p; seedKey.stream = stream;
     seedKey.map = spec.map; seedKey.mapVersion = spec.mapVersion;
+    seedKey.wordsPerPixel = f.spp * f.draws_per_sample; seedKey.statesPerTile = static_cast<int>(statesPerTile);
     const bool seedsCacheable = ctx->cacheTileSeeds && nChunks == 1 && f.draws_per_sample > 0;
     const bool seedTiles = !(seedsCacheable && ctx->tileSeedValid && seedKey == ctx->tileSeedKey);
     ctx->tileSeedKey = seedKey;
     ctx->tileSeedValid = false;
     if (seedTiles) ++ctx->seedGen;
-    // Splitting the figure's tiles pays only when the frame (all lanes in flight) has too few tiles to
-    // keep every SM busy for as long as its slowest tile takes: below ~10 tiles per SM (B200 sweep:
-    // a whole 1080p frame, 2040 tiles, is best unsplit; half a frame is best split in three).
-    const long long tilesInFlight = nTilesAll * std::max(1, lanesInFlight);
-    const int heavyTarget = tilesInFlight * 3 >= 2ll * ctx->smCount * ctx->heavyTilesPerSm
-                                ? 0 : ctx->smCount * ctx->heavyTilesPerSm / std::max(1, lanesInFlight);
     for (int c = 0; c < nChunks; ++c) {
         const size_t unit0 = static_cast<size_t>(c) * unitsPerChunk;
         const size_t units = std::min<size_t>(unitsPerChunk, nUnits - unit0);
@@ -384,9 +391,9 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
         // (two builds of the kernels: the one without pose code for scenes in which no box is posed; dev_types.cuh)
         const bool posed = f.any_rotated != 0;
         const bool seeded = posed ? launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
-                                                   seedTiles, ctx->smCount * ctx->primaryBlocksPerSm, heavyTarget, stream)
+                                                   seedTiles, primaryTarget, heavyTarget, stream)
                                   : plain::launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
-                                                          seedTiles, ctx->smCount * ctx->primaryBlocksPerSm, heavyTarget, stream);
+                                                          seedTiles, primaryTarget, heavyTarget, stream);
         ctx->tileSeedValid = seedsCacheable && seeded;
         // from here on every pixel of the band outside the figure's screen rectangle is final: the host
         // copy of the image may start (render_host).  Inside a capture this must be a real event-record
@@ -903,7 +910,8 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, const SkinBatchS
     CU_TRY(ctx->batchRecords.reserve(static_cast<size_t>(G) * recordBytes));
     CU_TRY(ctx->batchWave.reserve(static_cast<size_t>(G) * waveBytes));
     CU_TRY(ctx->batchCounts.reserve(static_cast<size_t>(G) * sizeof(unsigned int)));
-    CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, static_cast<size_t>(f0.tiles_x) * f0.tiles_y * 624 * sizeof(uint32_t))));
+    CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, static_cast<size_t>(f0.tiles_x) * f0.tiles_y * 624 * sizeof(uint32_t) *
+                                                            static_cast<size_t>(primary_states_per_tile(f0, f0.tiles_x * f0.tiles_y, 1, ctx->smCount * ctx->primaryBlocksPerSm, 0)))));
     for (int i = 0; i < 2; ++i) CU_TRY(ctx->batchStage[i].reserve(static_cast<size_t>(G) * (sceneStride + sizeof(BatchSlice))));
     if (skins) {
         CU_TRY(ctx->batchSkinSrc.reserve(static_cast<size_t>(G) * skinRecord));
@@ -918,6 +926,7 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, const SkinBatchS
     const size_t sliceOffset = static_cast<size_t>(G) * sceneStride;  // slices follow the scene data
     int stageSlot = 0;
     bool seeded = false;
+    int seededStatesPerTile = 0;
     for (int c0 = 0; c0 < nScenes; c0 += G) {
         const int nC = std::min(G, nScenes - c0);
         // (the staging buffers of this slot are free once the copies that last read them are done)
@@ -1032,12 +1041,18 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, const SkinBatchS
             const DevFrame& f = ctx->batchPreps[groups[g][0]].frame;
             launch_batch_reset(gs, nS, stream);
             const bool posed = f.any_rotated != 0;  // (equal frame descriptions: equal for the whole group)
-            const bool launched = posed ? launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), !seeded, gs, nS,
-                                                               first.fp.blob_bytes, ctx->smCount * ctx->primaryBlocksPerSm, stream)
-                                        : plain::launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), !seeded, gs, nS,
-                                                                      first.fp.blob_bytes, ctx->smCount * ctx->primaryBlocksPerSm, stream);
+            // the engines are seeded once per batch — same image geometry for every scene — unless a group is small enough
+            // for its tiles to be split over blocks, which changes what is kept per tile
+            const int primaryTarget = ctx->smCount * ctx->primaryBlocksPerSm;
+            const int statesPerTile = primary_states_per_tile(f, f.tiles_x * f.tiles_y, nS, primaryTarget, 0);
+            const bool seedNow = !seeded || statesPerTile != seededStatesPerTile;
+            const bool launched = posed ? launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), seedNow, gs, nS,
+                                                               first.fp.blob_bytes, primaryTarget, stream)
+                                        : plain::launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), seedNow, gs, nS,
+                                                                      first.fp.blob_bytes, primaryTarget, stream);
             if (!launched) return MC_OK;  // no batched primary kernel for this frame description: frame-by-frame path instead
-            seeded = true;  // same image geometry for every scene of the batch
+            seeded = true;
+            seededStatesPerTile = statesPerTile;
             int launches = 0;
             if (posed) launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
             else plain::launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);

@@ -71,10 +71,12 @@ struct TileOrder {
     int n_heavy;       // hw * hr (0: no reordering)
     int parts_heavy;   // blocks per heavy tile
     int parts_light;   // blocks per other tile
+    int round_states;  // 0: one engine state per tile (its seed); R > 0: R states per tile, one at the start of every
+                       // round of 256 pixels (k_tile_rounds), so that a block of a split tile starts at its own round
 };
 
 static TileOrder make_tile_order(const DevFrame& fr, const BandView& band, int partsHeavy, int partsLight) {
-    TileOrder o{0, 0, 0, 0, 0, partsLight, partsLight};
+    TileOrder o{0, 0, 0, 0, 0, partsLight, partsLight, 0};
     if (band.tile_map) {  // the map lists the heavy tiles first: launch slot == local tile (hw == 0 marks it)
         o.n_heavy = band.n_heavy;
         o.parts_heavy = band.n_heavy > 0 ? partsHeavy : partsLight;
@@ -585,17 +587,42 @@ __device__ __forceinline__ void pix_stream_block(uint32_t (*state)[kMtN], float*
 // Seeding of every tile's engine (state[0] = seed, state[i] = f(state[i-1], i)): 623
 // dependent steps that cannot be shared out inside a tile, so they run one tile per THREAD
 // in a small kernel of their own instead of idling 255 threads of each tile's block.
-__global__ void k_tile_seed(const DevFrame fr, const BandView band, uint32_t* states) {
+__global__ void k_tile_seed(const DevFrame fr, const BandView band, uint32_t* states, const int statesPerTile) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nTiles = band_tile_count(band, fr.tiles_x);
     if (t >= nTiles) return;
     const TileGeom tg = tile_geom(fr, band, t);
     uint32_t x = static_cast<uint32_t>(tg.y * fr.width + tg.x);  // tile_renderer.cpp:78
-    uint32_t* st = states + static_cast<size_t>(t) * kMtN;
+    uint32_t* st = states + static_cast<size_t>(t) * statesPerTile * kMtN;
     st[0] = x;
     for (uint32_t i = 1u; i < static_cast<uint32_t>(kMtN); ++i) {
         x = mt_lcg(x, i);
         st[i] = x;
+    }
+}
+
+// The engine state of every tile at the start of each of its rounds of 256 pixels (round r starts at stream word
+// r * 256 * wordsPerPixel; the state kept is the one after the last whole 624-word block before it).  With these a
+// tile can be split over several blocks at no cost: each block starts at its own round instead of running the
+// generator through the rounds other blocks take (a third of a round's work each).  Like the seeds they depend on the
+// frame geometry and the sampling pattern only, and are kept while those do not change.
+// states: rounds states per tile, state 0 = the seeded engine (k_tile_seed).
+__global__ void __launch_bounds__(kBlockThreads)
+k_tile_rounds(uint32_t* states, const int rounds, const unsigned int wordsPerRound) {
+    __shared__ uint32_t st[2][kMtN];
+    uint32_t* mine = states + static_cast<size_t>(blockIdx.x) * rounds * kMtN;
+    for (int i = threadIdx.x; i < kMtN; i += kBlockThreads) st[0][i] = mine[i];
+    __syncthreads();
+    int which = 0;
+    unsigned int produced = 0u;
+    for (int r = 1; r < rounds; ++r) {
+        const unsigned int first = static_cast<unsigned int>(r) * wordsPerRound;
+        while (produced + kMtN <= first) {
+            pix_stream_block<false>(st, nullptr, which, produced);
+            which ^= 1;
+            produced += kMtN;
+        }
+        for (int i = threadIdx.x; i < kMtN; i += kBlockThreads) mine[static_cast<size_t>(r) * kMtN + i] = st[which][i];
     }
 }
 
@@ -655,9 +682,10 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
     const SceneView sc = scene_view(sceneSmem, fp.texels, fr);
     const BandView out = tileCanHit ? hot_band(band) : band;
 
-    if (dps > 0) {  // this tile's freshly seeded engine (k_tile_seed)
-        const uint32_t* st = tileStates + static_cast<size_t>(tileIndex) * kMtN;
-        for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = st[i];
+    const int statesPerTile = order.round_states > 0 ? order.round_states : 1;
+    const uint32_t* tileState = tileStates + static_cast<size_t>(tileIndex) * statesPerTile * kMtN;
+    if (dps > 0 && order.round_states == 0) {  // this tile's freshly seeded engine (k_tile_seed)
+        for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = tileState[i];
         __syncthreads();
     }
     int which = 0;
@@ -669,6 +697,13 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
         if (dps > 0) {
             const unsigned int first = static_cast<unsigned int>(q0) * wordsPerPixel;
             const unsigned int need = static_cast<unsigned int>(min(nPix, q0 + kBlockThreads)) * wordsPerPixel;
+            if (order.round_states > 0) {  // the engine as it stands at the start of this round (k_tile_rounds)
+                const uint32_t* st = tileState + static_cast<size_t>(q0 / kBlockThreads) * kMtN;
+                for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = st[i];
+                which = 0;
+                produced = first / kMtN * kMtN;
+                __syncthreads();
+            }
             while (produced + kMtN <= first) {  // words of rounds other blocks take: state only
                 pix_stream_block<false>(mt->state, mt->ring, which, produced);
                 which ^= 1;
@@ -782,9 +817,10 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
     if (tileCanHit) stage_bulk(sceneSmem, fp.blob, fp.blob_bytes, &stageBar);
     const SceneView sc = scene_view(sceneSmem, fp.texels, fr);
     const BandView out = tileCanHit ? hot_band(band) : band;
-    {
-        const uint32_t* st = tileStates + static_cast<size_t>(tileIndex) * kMtN;
-        for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = st[i];
+    const int statesPerTile = order.round_states > 0 ? order.round_states : 1;
+    const uint32_t* tileState = tileStates + static_cast<size_t>(tileIndex) * statesPerTile * kMtN;
+    if (order.round_states == 0) {  // this tile's freshly seeded engine (k_tile_seed)
+        for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = tileState[i];
         __syncthreads();
     }
     int which = 0;
@@ -800,6 +836,14 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
         {
             const unsigned int first = static_cast<unsigned int>(q0) * kWords;
             const unsigned int need = static_cast<unsigned int>(min(nPix, q0 + kBlockThreads)) * kWords;
+            if (order.round_states > 0) {  // the engine as it stands at the start of this round (k_tile_rounds)
+                const uint32_t* st = tileState + static_cast<size_t>(q0 / kBlockThreads) * kMtN;
+                for (int i = tid; i < kMtN; i += kBlockThreads) mt->state[0][i] = st[i];
+                which = 0;
+                produced = first / kMtN * kMtN;
+                producedMod = produced % static_cast<unsigned int>(kRing);
+                __syncthreads();
+            }
             while (produced + kMtN <= first) {
                 pix_stream_block<false, kRing>(mt->state, mt->ring, which, producedMod);
                 which ^= 1;
@@ -1198,24 +1242,44 @@ static size_t pix_smem_limit() {
     return optIn.limit(fns, static_cast<int>(sizeof(fns) / sizeof(fns[0])));
 }
 
+// Engine states the pixel-per-lane primary kernels keep per tile for a launch of nTiles tiles x nScenes scenes: 1 (the
+// seed) when no tile is split over blocks, else one per round of 256 pixels.  The host sizes tileStates with it.
+int primary_states_per_tile(const DevFrame& fr, int nTiles, int nScenes, int primaryTargetBlocks, int heavyTargetTiles) {
+    if (nTiles <= 0 || fr.draws_per_sample <= 0) return 1;
+    const int roundsPerTile = (fr.tile_size * fr.tile_size + kBlockThreads - 1) / kBlockThreads;
+    const long long allTiles = static_cast<long long>(nTiles) * std::max(1, nScenes);
+    const bool split = primaryTargetBlocks > allTiles || heavyTargetTiles > allTiles;
+    return split && roundsPerTile > 1 ? roundsPerTile : 1;
+}
+
 // The pixel-per-lane primary kernels over one scene (batch == nullptr) or the scenes of a batch.
 static void launch_primary_pix(const DevFrame& fr, const FramePointers& fp, const BandView& band, const ActiveList& list,
                                uint32_t* tileStates, bool seedTiles, int primaryTargetBlocks, int heavyTargetTiles,
                                const BatchSlice* batch, int nScenes, unsigned int blobBytes, cudaStream_t stream) {
     const int nTiles = band_tile_count(band, fr.tiles_x);
     const size_t pixSmem = ((sizeof(PixStreamSmem) + 15) & ~size_t(15)) + blobBytes;
-    // the seeded engines depend on the tile geometry only: one set serves every scene of a batch
-    if (fr.draws_per_sample > 0 && seedTiles) k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates);
     // enough blocks to fill the machine, at most one block per round of 256 pixels
     const int roundsPerTile = (fr.tile_size * fr.tile_size + kBlockThreads - 1) / kBlockThreads;
     const int allTiles = nTiles * (batch ? nScenes : 1);
     int parts = (primaryTargetBlocks + allTiles - 1) / allTiles;
     parts = parts < 1 ? 1 : (parts > roundsPerTile ? roundsPerTile : parts);
+    while (roundsPerTile % parts) --parts;  // equal shares: every block of a tile takes the same number of rounds
     // the figure's tiles are split further while the launch has few tiles: it should not last as
     // long as its slowest tile (one GPU's share of a frame is 255 tiles at 8 GPUs)
     int partsHeavy = (heavyTargetTiles + allTiles - 1) / allTiles;
     partsHeavy = partsHeavy < parts ? parts : (partsHeavy > roundsPerTile ? roundsPerTile : partsHeavy);
-    const TileOrder order = make_tile_order(fr, band, partsHeavy, parts);
+    while (roundsPerTile % partsHeavy) --partsHeavy;
+    TileOrder order = make_tile_order(fr, band, partsHeavy, parts);
+    // split tiles start every block at its own round of the tile's stream (k_tile_rounds)
+    const int statesPerTile = MCSKIN_VARIANT_NS::primary_states_per_tile(fr, nTiles, batch ? nScenes : 1, primaryTargetBlocks, heavyTargetTiles);
+    order.round_states = statesPerTile > 1 ? statesPerTile : 0;
+    // the seeded engines depend on the tile geometry only: one set serves every scene of a batch
+    if (fr.draws_per_sample > 0 && seedTiles) {
+        k_tile_seed<<<(nTiles + 63) / 64, 64, 0, stream>>>(fr, band, tileStates, statesPerTile);
+        if (statesPerTile > 1)
+            k_tile_rounds<<<nTiles, kBlockThreads, 0, stream>>>(tileStates, statesPerTile,
+                                                                static_cast<unsigned int>(kBlockThreads * fr.spp * fr.draws_per_sample));
+    }
     const dim3 grid(order.n_heavy * order.parts_heavy + (nTiles - order.n_heavy) * order.parts_light, batch ? nScenes : 1);
     // jitter only (no lens draws), 4 or 16 spp, quotients by the host reciprocals: compile-time sample loop
     const bool fixedForm = fr.draws_per_sample == 2 && fr.spp > 1 && !fr.dof_on && fr.uv_recip;

@@ -128,6 +128,13 @@ MCSKIN_HOT_KERNEL_LAUNCHERS
 // variant 1: block-synchronous groups; variant 2: warp-autonomous groups with dynamic
 // distribution (groupCounter: a zeroed device counter; spp must be a power of two <= 32).
 
+// Engine states per tile the primary pass keeps for such a launch (1 = the seed only; more: one per round of 256
+// pixels, for tiles split over blocks): tileStates must hold nTiles * this * 624 words.
+int primary_states_per_tile(const DevFrame& fr, int nTiles, int nScenes, int primaryTargetBlocks, int heavyTargetTiles);
+namespace plain {
+int primary_states_per_tile(const DevFrame& fr, int nTiles, int nScenes, int primaryTargetBlocks, int heavyTargetTiles);
+}
+
 // Single-query views of the same device code (all pointers are device memory).
 void launch_intersect(const DevFrame& fr, const FramePointers& fp, int box, const McRay* rays, int n, McHit* out,
                       cudaStream_t stream);
