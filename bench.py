@@ -227,7 +227,9 @@ class FrameJob:
             self.local_frame = torch.zeros((self.H, self.W, 4), dtype=torch.float32, device=self.dev)
         if self.split > 1 and self.exchange != "gather":
             part = int(os.environ.get("MCSKIN_BENCH_PART", "0")) if emulate > 1 else rank
-            self.tiles = lib.partition_tiles(scene, cfg, self.split, part)
+            # value: rank 0 holds the frame, the others store into it over NVLink (their background tiles count a little more)
+            self.tiles = lib.partition_tiles(scene, cfg, self.split, part, 0 if (self.exchange == "p2p" and not emulate) else -1)
+            self.tiles_host = lib.partition_tiles(scene, cfg, self.split, part, -1)  # e2e: every rank writes to the host frame
         if self.exchange == "p2p":
             self.peer = bands.PeerFrame(lib, self.H, self.W, local_rank)
             self.frame_ptr = self.peer.ptr
@@ -270,6 +272,11 @@ class FrameJob:
             if self.peer is not None:
                 self.peer.fence(self.stream.cuda_stream)  # ranks release a flag in the root's memory; the root's stream acquires them
 
+    def release(self):
+        """After step(): the root has the frame; the peers may overwrite it (PeerFrame.release)."""
+        if self.peer is not None and not self.diag:
+            self.peer.release(self.stream.cuda_stream)
+
     def close(self):
         self.ctx.close()
         if self.peer is not None:
@@ -284,6 +291,7 @@ def time_steps(torch, dist, job, flush, steps, warmup, world, dev):
     for i in range(warmup):
         flush.fill_(1)
         job.step()
+        job.release()
     torch.cuda.synchronize(dev)
     job.ctx.sync()
     if world > 1:
@@ -299,6 +307,7 @@ def time_steps(torch, dist, job, flush, steps, warmup, world, dev):
         starts[i].record(job.stream)
         job.step()
         ends[i].record(job.stream)
+        job.release()  # (untimed) the root is done with the frame: the peers may store the next one
     torch.cuda.synchronize(dev)
     w1 = time.time()
     st = job.ctx.sync()
@@ -435,6 +444,7 @@ def run_own_arm(args):
         # ---- sustained: >= 2 s of back-to-back frames (no flush: a frame's queue traffic alone exceeds the L2)
         for _ in range(3):
             job.step()
+            job.release()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -444,6 +454,7 @@ def run_own_arm(args):
         e0.record(stream)
         for _ in range(n_sus):
             job.step()
+            job.release()  # (the handshake is part of a sustained pipeline: inside this figure)
         e1.record(stream)
         torch.cuda.synchronize(dev)
         s1 = time.time()
@@ -491,7 +502,7 @@ def run_own_arm(args):
         host = bands.HostFrame(lib, H, W)
 
         e2e_dev = [0.0, 0]
-        my_tiles = np.ascontiguousarray(job.tiles, dtype=np.int32)
+        my_tiles = np.ascontiguousarray(job.tiles_host, dtype=np.int32)
         c_scene = scene.as_c()  # the C view of the host scene, built once
 
         def e2e_step():

@@ -200,11 +200,13 @@ int32_t mcskin_cuda_context_render_scene_tiles(McContext* ctx, const McScene* sc
                                                 uint8_t* host_frame_u8, float* ms_device);
 /* Deals the tiles of a frame to n_parts renderers so that every part costs about the same: tiles are weighted
  * by how much of them the figure's screen rectangles cover (covered pixels cost ~50x a background pixel) and
- * dealt greedily, heaviest first, to the least loaded part; deterministic, the parts are disjoint and cover the
- * frame.  Returns the number of tiles of `part` (negative MC_ERR_* on failure) and writes at most `capacity`
+ * dealt greedily, heaviest first, to the least loaded part; the background tiles are then dealt as contiguous runs
+ * in frame order that fill every part to the same level (a part's background is a few rectangles); deterministic, the
+ * parts are disjoint and cover the frame.  root_part: the part whose device holds the frame the others store into over
+ * NVLink (their background tiles count 1.3: remote stores), or -1 when every part writes under the same conditions.  Returns the number of tiles of `part` (negative MC_ERR_* on failure) and writes at most `capacity`
  * of them to out_tiles (may be null to query the count).  Host code only: needs no device. */
 int32_t mcskin_partition_tiles(const McScene* scene, const McConfig* cfg, int32_t n_parts, int32_t part,
-                               int32_t* out_tiles, int32_t capacity);
+                               int32_t root_part, int32_t* out_tiles, int32_t capacity);
 /* Page-locks a host range (e.g. a shared-memory segment every process of the box has mapped) and maps it into
  * the device address space: *d_ptr is what kernels store to (zero-copy over PCIe), so N GPUs can write their
  * tiles of one frame into one host image through N PCIe links at once. */

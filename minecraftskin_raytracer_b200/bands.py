@@ -134,9 +134,10 @@ class PeerFrame:
 
     def fence(self, stream: int = 0):
         """One-way barrier: after this (in the root's stream order) every rank's tiles of the current frame
-        are in the root's image.  Non-root ranks only signal and run ahead: use it only while the root does not
-        consume the frame between steps (else follow it with fence_all).  A rank that never signals makes the
-        root's wait give up after ~2 s; check_timeout() raises then."""
+        are in the root's image.  Non-root ranks only signal.  Follow it with release() once the root is done with
+        the frame: the peers then hold their NEXT frame's stores until the root has said so (they never run more
+        than one frame ahead, and never overwrite a frame the root still reads).  A rank that never signals makes
+        the root's wait give up after ~2 s; check_timeout() raises then."""
         self.epoch += 1
         if self.world == 1:
             return
@@ -144,6 +145,16 @@ class PeerFrame:
             self.lib.peer_wait(self.device, self.flags_ptr + 4, self.world - 1, self.epoch, self._timed_out.data_ptr(), stream)
         else:
             self.lib.peer_signal(self.device, self.flags_ptr + 4 * self.rank, self.epoch, stream)
+
+    def release(self, stream: int = 0):
+        """The other half of the handshake (stream-ordered like fence): the root releases flag 0 of its page when it
+        is done with the frame; every other rank's stream waits for it (polling the root's memory over NVLink)."""
+        if self.world == 1:
+            return
+        if self.rank == 0:
+            self.lib.peer_signal(self.device, self.flags_ptr, self.epoch, stream)
+        else:
+            self.lib.peer_wait(self.device, self.flags_ptr, 1, self.epoch, 0, stream)
 
     def check_timeout(self):
         """Root, after synchronising: raises if a wait of this frame or an earlier one gave up on a rank."""

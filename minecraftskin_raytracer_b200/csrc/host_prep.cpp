@@ -472,9 +472,9 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
 // kCoveredCost times the fraction of it that box rectangles cover (every box counted: overlapping inner and
 // outer layers do mean more work), or that the figure's rectangle covers when the boxes have none.
 extern "C" int32_t mcskin_partition_tiles(const McScene* scene, const McConfig* cfg, int32_t nParts, int32_t part,
-                                          int32_t* outTiles, int32_t capacity) {
+                                          int32_t rootPart, int32_t* outTiles, int32_t capacity) {
     using namespace mcskin;
-    if (!scene || !cfg || nParts <= 0 || part < 0 || part >= nParts || capacity < 0) {
+    if (!scene || !cfg || nParts <= 0 || part < 0 || part >= nParts || capacity < 0 || rootPart >= nParts) {
         set_last_error("partition_tiles: bad argument");
         return MC_ERR_INVALID;
     }
@@ -548,24 +548,33 @@ extern "C" int32_t mcskin_partition_tiles(const McScene* scene, const McConfig* 
             return static_cast<double>(std::min(f.width, (tileX + 1) * ts) - tileX * ts) *
                    (std::min(f.height, (tileY + 1) * ts) - tileY * ts) / (static_cast<double>(ts) * ts);
         };
-        double lightLeft = 0.0;
-        for (int id : light) lightLeft += weight_of(id);
-        // the level part p is filled to: the mean of what is left for parts p.. when its run starts
-        auto level = [&](int p) {
-            double rest = lightLeft;
-            for (int q = p; q < nParts; ++q) rest += load[q];
-            return rest / (nParts - p);
-        };
+        // What a background tile costs a part: 1, or kRemoteLight when its pixels go to ANOTHER device's memory (the
+        // parts other than rootPart, when one device holds the frame and the others store into it over NVLink: a
+        // background tile is little more than its stores, and remote stores measured ~30 % dearer on B200).
+        constexpr double kRemoteLight = 1.3;
+        auto cost_of = [&](int p) { return (rootPart >= 0 && p != rootPart) ? kRemoteLight : 1.0; };
+        double lightTotal = 0.0;
+        for (int id : light) lightTotal += weight_of(id);
+        // the level T every part is filled to: sum over parts of max(0, T - load) / cost = the background tiles
+        double lo = 0.0, hi = 0.0;
+        for (int p = 0; p < nParts; ++p) hi = std::max(hi, load[p]);
+        hi += lightTotal * kRemoteLight + 1.0;
+        for (int it = 0; it < 100; ++it) {
+            const double T = 0.5 * (lo + hi);
+            double fit = 0.0;
+            for (int p = 0; p < nParts; ++p) fit += std::max(0.0, T - load[p]) / cost_of(p);
+            (fit < lightTotal ? lo : hi) = T;
+        }
+        const double T = hi;
         int p = 0;
-        double target = level(0);
+        double room = std::max(0.0, T - load[0]) / cost_of(0);
         for (int id : light) {
             const double w = weight_of(id);
-            while (p < nParts - 1 && load[p] + 0.5 * w > target) {
+            while (p < nParts - 1 && room < 0.5 * w) {  // this part is full: its run ends here
                 ++p;
-                target = level(p);
+                room = std::max(0.0, T - load[p]) / cost_of(p);
             }
-            load[p] += w;
-            lightLeft -= w;
+            room -= w;
             if (p == part) mine.push_back(id);
         }
     }

@@ -1140,17 +1140,22 @@ __global__ void k_peer_wait(const unsigned int* flags, const int n, const unsign
     if (i < n) {
         const long long t0 = clock64();
         for (;;) {
+            // poll with plain (relaxed, system-scope) loads: an acquire load per poll, or a system fence at the end,
+            // cost the root ~0.1 ms per frame while seven peers were streaming their tiles into its memory
             unsigned int v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
-            if (static_cast<int>(v - value) >= 0) break;           // counters wrap: compare as a signed distance
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+            if (static_cast<int>(v - value) >= 0) {                // counters wrap: compare as a signed distance
+                // one acquire on the flag that was seen set: what the peer stored before releasing it is visible now
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+                break;
+            }
             if (clock64() - t0 > 4000000000ll) {                   // ~2 s at 2 GHz: give up rather than hang the device
                 if (timedOut) *timedOut = 1u;
                 break;
             }
-            __nanosleep(200);
+            __nanosleep(100);
         }
     }
-    __threadfence_system();
 }
 
 // Eight independent chains per thread, each step one FMUL and one FADD (this translation unit is built

@@ -263,15 +263,16 @@ def peer_wait(device: int, d_flags: int, n: int, value: int, d_timeout: int = 0,
                                       C.c_void_p(d_timeout or None), C.c_void_p(stream or None)))
 
 
-def partition_tiles(scene: FlatScene, cfg: McConfig, n_parts: int, part: int) -> np.ndarray:
+def partition_tiles(scene: FlatScene, cfg: McConfig, n_parts: int, part: int, root_part: int = -1) -> np.ndarray:
     """Frame tile indices (ty * tiles_x + tx, ascending) of `part` in the cost-balanced deal of the frame's tiles
-    to n_parts renderers (host code, needs no GPU).  The parts are disjoint and cover the frame."""
+    to n_parts renderers (host code, needs no GPU).  The parts are disjoint and cover the frame.  root_part: the part
+    whose device holds the frame the others store into over NVLink (-1: none)."""
     cs = scene.as_c()
-    n = _lib.mcskin_partition_tiles(C.byref(cs), C.byref(cfg), C.c_int32(n_parts), C.c_int32(part), None, C.c_int32(0))
+    n = _lib.mcskin_partition_tiles(C.byref(cs), C.byref(cfg), C.c_int32(n_parts), C.c_int32(part), C.c_int32(root_part), None, C.c_int32(0))
     _check(min(n, 0))
     out = np.zeros(n, dtype=np.int32)
     if n:
-        _check(min(_lib.mcskin_partition_tiles(C.byref(cs), C.byref(cfg), C.c_int32(n_parts), C.c_int32(part),
+        _check(min(_lib.mcskin_partition_tiles(C.byref(cs), C.byref(cfg), C.c_int32(n_parts), C.c_int32(part), C.c_int32(root_part),
                                                _ptr(out, C.c_int32), C.c_int32(n)), 0))
     return out
 
