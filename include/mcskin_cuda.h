@@ -154,8 +154,9 @@ int32_t mcskin_cuda_render(const McScene* scene, const McConfig* cfg, int32_t de
 int32_t mcskin_cuda_render_tile(const McScene* scene, const McConfig* cfg, int32_t device,
                                 const McTile* tile, float* image_rgba_f32, uint8_t* image_rgba_u8);
 
-/* Same frame split over devices 0..n_devices-1 of this process by interleaved
- * tile rows (tile row j -> device j % n_devices) and gathered on the host. */
+/* Same frame split over devices 0..n_devices-1 of this process: every device renders its cost-balanced tile set
+ * (mcskin_partition_tiles) and sends it to the caller's image over its own PCIe link (page-locked, mapped images:
+ * see mcskin_cuda_context_render_scene_tiles). */
 int32_t mcskin_cuda_render_multi(const McScene* scene, const McConfig* cfg, int32_t n_devices,
                                  float* out_rgba_f32, uint8_t* out_rgba_u8, McRenderStats* stats);
 

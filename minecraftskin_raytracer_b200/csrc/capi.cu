@@ -1283,26 +1283,31 @@ int32_t mcskin_cuda_context_render_tiles_into_frame(McContext* ctx, const int32_
 // box shares: upload, this rank's tiles, wait.  The image must be page-locked and mapped (mcskin_cuda_host_register,
 // cudaHostAlloc, torch pin_memory).  Tiles the figure's rectangle touches are stored by the kernels straight into it;
 // the others go to a device image and leave by DMA, in a few rectangles, once the primary pass is done.
-int32_t mcskin_cuda_context_render_scene_tiles(McContext* ctx, const McScene* scene, const McConfig* cfg, const int32_t* tiles,
-                                                int32_t nTiles, float* hostF32, uint8_t* hostU8, float* msDevice) {
-    if (!ctx) return fail(MC_ERR_INVALID, "render_scene_tiles: null context");
-    if (nTiles < 0 || (nTiles > 0 && !tiles)) return fail(MC_ERR_INVALID, "render_scene_tiles: bad tile list");
-    int rc = mcskin_cuda_context_set_scene(ctx, scene, cfg);
-    if (rc != MC_OK) return rc;
-    if (msDevice) *msDevice = 0.0f;
+// Asynchronous part of a tile set rendered to a host image: launches on the context's stream (and its copy stream).
+// Page-locked, mapped host images take the two-destination route (see render_host); any other host memory gets the
+// tiles from a device frame, rectangle by rectangle, after the frame's kernels.
+static int launch_tiles_to_host(McContext* ctx, const int32_t* tiles, int32_t nTiles, float* hostF32, uint8_t* hostU8) {
     const DevFrame& f = ctx->prep.frame;
     void* aliasF32 = device_alias_of_host(hostF32);
     void* aliasU8 = device_alias_of_host(hostU8);
-    if ((hostF32 && !aliasF32) || (hostU8 && !aliasU8))
-        return fail(MC_ERR_INVALID, "render_scene_tiles: the host image must be page-locked and mapped (mcskin_cuda_host_register)");
+    const bool mappedHost = (!hostF32 || aliasF32) && (!hostU8 || aliasU8);
     BandSpec spec;
     bool empty = false;
-    rc = prepare_tile_map(ctx, tiles, nTiles, ctx->stream, &spec, &empty);
+    int rc = prepare_tile_map(ctx, tiles, nTiles, ctx->stream, &spec, &empty);
     if (rc != MC_OK || empty) return rc;
     const bool classified = !ctx->forceAllActive && f.spp <= kBlockThreads;
+    const size_t pixels = static_cast<size_t>(f.width) * f.height;
+    if (!mappedHost) {
+        if (hostF32) CU_TRY(ctx->imgF32.reserve(pixels * sizeof(float4)));
+        if (hostU8) CU_TRY(ctx->imgU8.reserve(pixels * sizeof(uchar4)));
+        rc = render_bands(ctx, 0, 1, hostF32 ? static_cast<float4*>(ctx->imgF32.p) : nullptr,
+                          hostU8 ? static_cast<uchar4*>(ctx->imgU8.p) : nullptr, ctx->stream, true, &spec);
+        if (rc != MC_OK) return rc;
+        const std::vector<PixelRect> all = tile_rects(f, ctx->tileMapOrdered);
+        return copy_rects_to_host(all, f.width, ctx->imgF32.p, hostF32, ctx->imgU8.p, hostU8, ctx->stream);
+    }
     const bool dual = ctx->overlapCopyOut >= 2 && classified && !ctx->tileMapLightRects.empty();
     if (dual) {
-        const size_t pixels = static_cast<size_t>(f.width) * f.height;
         if (hostF32) CU_TRY(ctx->imgF32.reserve(pixels * sizeof(float4)));
         if (hostU8) CU_TRY(ctx->imgU8.reserve(pixels * sizeof(uchar4)));
         rc = render_bands(ctx, 0, 1, hostF32 ? static_cast<float4*>(ctx->imgF32.p) : nullptr,
@@ -1310,17 +1315,36 @@ int32_t mcskin_cuda_context_render_scene_tiles(McContext* ctx, const McScene* sc
                           static_cast<float4*>(aliasF32), static_cast<uchar4*>(aliasU8));
         if (rc != MC_OK) return rc;
         CU_TRY(cudaStreamWaitEvent(ctx->copyStream, ctx->evPrimaryDone, 0));
-        rc = copy_rects_to_host(ctx->tileMapLightRects, f.width, ctx->imgF32.p, hostF32, ctx->imgU8.p, hostU8, ctx->copyStream);
-        if (rc != MC_OK) return rc;
-        CU_TRY(cudaStreamSynchronize(ctx->copyStream));
-    } else {  // every tile straight into the host image
-        rc = render_bands(ctx, 0, 1, static_cast<float4*>(aliasF32), static_cast<uchar4*>(aliasU8), ctx->stream, true, &spec);
-        if (rc != MC_OK) return rc;
+        return copy_rects_to_host(ctx->tileMapLightRects, f.width, ctx->imgF32.p, hostF32, ctx->imgU8.p, hostU8, ctx->copyStream);
     }
+    // every tile straight into the host image
+    return render_bands(ctx, 0, 1, static_cast<float4*>(aliasF32), static_cast<uchar4*>(aliasU8), ctx->stream, true, &spec);
+}
+static int finish_tiles_to_host(McContext* ctx) {
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaStreamSynchronize(ctx->copyStream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     for (McContext* lane : ctx->lanes) CU_TRY(cudaStreamSynchronize(lane->stream));
     CU_TRY(cudaGetLastError());
-    if (msDevice) CU_TRY(cudaEventElapsedTime(msDevice, ctx->ev0, ctx->ev1));
+    return MC_OK;
+}
+
+// The per-frame call of a rank whose scene lives on the CPU and whose result goes to a host image every rank of the
+// box shares: upload, this rank's tiles, wait.  With a page-locked, mapped image (mcskin_cuda_host_register,
+// cudaHostAlloc, torch pin_memory) the tiles the figure's rectangle touches are stored by the kernels straight into
+// it; the others go to a device image and leave by DMA, in a few rectangles, once the primary pass is done.
+int32_t mcskin_cuda_context_render_scene_tiles(McContext* ctx, const McScene* scene, const McConfig* cfg, const int32_t* tiles,
+                                                int32_t nTiles, float* hostF32, uint8_t* hostU8, float* msDevice) {
+    if (!ctx) return fail(MC_ERR_INVALID, "render_scene_tiles: null context");
+    if (nTiles < 0 || (nTiles > 0 && !tiles)) return fail(MC_ERR_INVALID, "render_scene_tiles: bad tile list");
+    int rc = mcskin_cuda_context_set_scene(ctx, scene, cfg);
+    if (rc != MC_OK) return rc;
+    if (msDevice) *msDevice = 0.0f;
+    rc = launch_tiles_to_host(ctx, tiles, nTiles, hostF32, hostU8);
+    if (rc != MC_OK) return rc;
+    rc = finish_tiles_to_host(ctx);
+    if (rc != MC_OK) return rc;
+    if (msDevice && nTiles > 0) CU_TRY(cudaEventElapsedTime(msDevice, ctx->ev0, ctx->ev1));
     return MC_OK;
 }
 
@@ -1601,49 +1625,26 @@ int32_t mcskin_cuda_render_multi(const McScene* scene, const McConfig* cfg, int3
     }
     std::lock_guard<std::mutex> lock(g_ctxMutex);
     std::vector<McContext*> ctxs(nDevices, nullptr);
-    std::string err;
-    const int ts = cfg->tile_size, W = cfg->width, H = cfg->height;
-    const int tilesY = (H + ts - 1) / ts;
-    // launch everywhere first (asynchronous), then gather
+    // every device gets its cost-balanced tile set (mcskin_partition_tiles) and sends it to the caller's image over
+    // its own PCIe link; launch everywhere first (asynchronous), then wait
+    std::vector<int32_t> tiles(static_cast<size_t>(totalTiles));
     for (int d = 0; d < nDevices; ++d) {
         int rc = shared_context(d, &ctxs[d]);
         if (rc != MC_OK) return rc;
         McContext* ctx = ctxs[d];
         rc = mcskin_cuda_context_set_scene(ctx, scene, cfg);
         if (rc != MC_OK) return rc;
-        const int rows = band_pixel_rows(ctx->prep.frame, d, nDevices);
-        const size_t pixels = static_cast<size_t>(rows) * W;
-        if (pixels == 0) continue;
-        if (outF32) CU_TRY(ctx->imgF32.reserve(pixels * sizeof(float4)));
-        if (outU8) CU_TRY(ctx->imgU8.reserve(pixels * sizeof(uchar4)));
-        rc = render_bands(ctx, d, nDevices, outF32 ? static_cast<float4*>(ctx->imgF32.p) : nullptr,
-                          outU8 ? static_cast<uchar4*>(ctx->imgU8.p) : nullptr, ctx->stream);
+        const int32_t n = mcskin_partition_tiles(scene, cfg, nDevices, d, -1, tiles.data(), totalTiles);
+        if (n < 0) return n;
+        rc = launch_tiles_to_host(ctx, tiles.data(), n, outF32, outU8);
         if (rc != MC_OK) return rc;
     }
     McRenderStats total{};
     for (int d = 0; d < nDevices; ++d) {
-        McContext* ctx = ctxs[d];
-        CU_TRY(cudaSetDevice(d));
-        const int nLocal = local_tile_rows(ctx->prep.frame, d, nDevices);
-        for (int r = 0; r < nLocal; ++r) {  // de-interleave tile row by tile row
-            const int tileRow = d + r * nDevices;
-            const int y0 = tileRow * ts;
-            const int h = std::min(ts, H - y0);
-            const size_t src = static_cast<size_t>(r) * ts * W, dst = static_cast<size_t>(y0) * W;
-            if (outF32)
-                CU_TRY(cudaMemcpyAsync(outF32 + dst * 4, static_cast<float4*>(ctx->imgF32.p) + src,
-                                       static_cast<size_t>(h) * W * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-            if (outU8)
-                CU_TRY(cudaMemcpyAsync(outU8 + dst * 4, static_cast<uchar4*>(ctx->imgU8.p) + src,
-                                       static_cast<size_t>(h) * W * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        (void)tilesY;
-    }
-    for (int d = 0; d < nDevices; ++d) {
-        CU_TRY(cudaSetDevice(d));
-        CU_TRY(cudaStreamSynchronize(ctxs[d]->stream));
+        int rc = finish_tiles_to_host(ctxs[d]);
+        if (rc != MC_OK) return rc;
         McRenderStats s{};
-        const int rc = finish_stats(ctxs[d], &s);
+        rc = finish_stats(ctxs[d], &s);
         if (rc != MC_OK) return rc;
         total.n_tiles += s.n_tiles;
         total.n_active_pixels += s.n_active_pixels;
@@ -1652,7 +1653,7 @@ int32_t mcskin_cuda_render_multi(const McScene* scene, const McConfig* cfg, int3
         total.ms_primary = std::max(total.ms_primary, s.ms_primary);
         total.ms_shade = std::max(total.ms_shade, s.ms_shade);
     }
-    total.n_samples = static_cast<int64_t>(W) * H * std::max(1, cfg->samples_per_pixel);
+    total.n_samples = static_cast<int64_t>(cfg->width) * cfg->height * std::max(1, cfg->samples_per_pixel);
     if (stats) *stats = total;
     return MC_OK;
 }
