@@ -1,6 +1,9 @@
 #!/usr/bin/env bash
-# round-end check on one GPU: the GPU test suite, smoke(), the bench line
+# On the GPU box: the GPU test suite, smoke(), both bench arms, then the round's profile capture.
 mkdir -p gpurun_out
-(time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/gpu_tests.log 2>&1; grep -E "passed|failed" gpurun_out/gpu_tests.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -2 gpurun_out/bench.err
+export MCSKIN_SKIP_REF_BUILD=1
+( time python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$? $(tail -4 gpurun_out/pytest_gpu.log | head -1)"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+( time python bench.py --steps 20 --warmup 5 ) > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 300 gpurun_out/bench.err
+( time python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; echo "reference arm rc=$?"; cat gpurun_out/bench_ref.json | cut -c1-400
+bash tools/profile_r2.sh > gpurun_out/profile.log 2>&1; tail -3 gpurun_out/profile.log
