@@ -54,6 +54,9 @@ EXTRA_FRAMES = [
     # SURVEY §8d secondary rows of the headline: pose 1 ("walking", 8 rotated boxes) and hard shadows
     ("headline_walking_1080p_16spp_4b", 0, "64x64", "walking", dict(width=1920, height=1080, samples_per_pixel=16, max_bounces=4)),
     ("headline_hard_shadows_1080p_16spp_4b", 0, "64x64", None, dict(width=1920, height=1080, samples_per_pixel=16, max_bounces=4, soft_shadows=0)),
+    # not the reference's frame: the headline with McConfig.rng_mode 1 (counter-based streams) — equal to
+    # the oracle with the same switch, reported beside the mt19937 number, never in its place
+    ("headline_counter_rng_1080p_16spp_4b", 0, "64x64", None, dict(width=1920, height=1080, samples_per_pixel=16, max_bounces=4, rng_mode=1)),
 ]
 C4_SKINS_PER_GPU = 512
 C4_CONFIG = dict(width=256, height=256, samples_per_pixel=4, max_bounces=2)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MCSKIN_ABI_VERSION 1
+#define MCSKIN_ABI_VERSION 2
 
 enum {
     MC_OK = 0,
@@ -102,7 +102,25 @@ typedef struct McConfig {
     float bg_center[4];
     float bg_edge[4];
     float kd, ks, ambient, shininess;
+    /* Not in the reference's Config.  0: every random stream is the reference's std::mt19937 (frames equal the
+     * reference's bit for bit).  1 (MC_RNG_COUNTER): counter-based streams — draw k of a stream seeded s is
+     * canonical(mc_rng_counter_word(s, k)), no engine state, no 623-step seeding per tile and per shaded hit; the
+     * same seeds, the same number and order of draws, the same float mapping.  Frames then differ from the
+     * reference's in their noise only and equal the CPU oracle's with the same switch. */
+    int32_t rng_mode;
 } McConfig;
+#define MC_RNG_MT19937 0
+#define MC_RNG_COUNTER 1
+
+/* Word k of the counter-based stream seeded `seed` (rng_mode 1): two rounds of the lowbias32 integer hash. */
+static inline uint32_t mc_rng_lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+static inline uint32_t mc_rng_counter_key(uint32_t seed) { return mc_rng_lowbias32(seed ^ 0x9e3779b9u); }
+static inline uint32_t mc_rng_counter_word(uint32_t seed, uint32_t k) { return mc_rng_lowbias32(mc_rng_counter_key(seed) + k); }
+/* The same word from the library (for bindings that restate the hash in their own language and want to check it). */
+uint32_t mcskin_counter_word(uint32_t seed, uint32_t k);
 
 /* Fills *cfg with the reference defaults (raytracer.h:10-38, shading.h:9-14). */
 void mcskin_config_defaults(McConfig* cfg);

@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MC_OK = 0
 MC_ERR_INVALID = -1
@@ -78,6 +78,7 @@ class McConfig(C.Structure):
         ("ks", C.c_float),
         ("ambient", C.c_float),
         ("shininess", C.c_float),
+        ("rng_mode", C.c_int32),
     ]
 
 
@@ -174,6 +175,7 @@ def default_config(**overrides) -> McConfig:
     cfg.bg_center[:] = [0.91, 0.89, 0.86, 1.0]
     cfg.bg_edge[:] = [0.56, 0.63, 0.71, 1.0]
     cfg.kd, cfg.ks, cfg.ambient, cfg.shininess = 0.75, 0.15, 0.20, 16.0
+    cfg.rng_mode = 0
     for k, v in overrides.items():
         if k in ("bg_center", "bg_edge"):
             getattr(cfg, k)[:] = list(v)

@@ -343,7 +343,7 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
     seedKey.width = f.width; seedKey.tile_size = f.tile_size; seedKey.first = first; seedKey.stride = stride;
     seedKey.rows = mapped ? spec.nTiles : nRows; seedKey.buf = ctx->tileStates.p; seedKey.stream = stream;
     seedKey.map = spec.map; seedKey.mapVersion = spec.mapVersion;
-    seedKey.wordsPerPixel = f.spp * f.draws_per_sample; seedKey.statesPerTile = static_cast<int>(statesPerTile);
+    seedKey.wordsPerPixel = f.spp * f.draws_per_sample; seedKey.statesPerTile = static_cast<int>(statesPerTile) | (f.rng_mode << 16);
     const bool seedsCacheable = ctx->cacheTileSeeds && nChunks == 1 && f.draws_per_sample > 0;
     const bool seedTiles = !(seedsCacheable && ctx->tileSeedValid && seedKey == ctx->tileSeedKey);
     ctx->tileSeedKey = seedKey;
@@ -388,12 +388,14 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
             CU_TRY(cudaMemcpyAsync(list.count, &list.capacity, sizeof(unsigned int), cudaMemcpyHostToDevice, stream));
         }
         if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c], stream));
-        // (two builds of the kernels: the one without pose code for scenes in which no box is posed; dev_types.cuh)
-        const bool posed = f.any_rotated != 0;
-        const bool seeded = posed ? launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
-                                                   seedTiles, primaryTarget, heavyTarget, stream)
-                                  : plain::launch_primary(f, fp, band, list, classify ? 1 : 0, static_cast<uint32_t*>(ctx->tileStates.p),
-                                                          seedTiles, primaryTarget, heavyTarget, stream);
+        // (three builds of the kernels — dev_types.cuh: counter-based random streams; no pose code, for scenes in which
+        // no box is posed; the general form)
+        const int build = f.rng_mode ? 2 : (f.any_rotated ? 0 : 1);
+        uint32_t* const states = static_cast<uint32_t*>(ctx->tileStates.p);
+        const bool seeded =
+            build == 2 ? counter::launch_primary(f, fp, band, list, classify ? 1 : 0, states, seedTiles, primaryTarget, heavyTarget, stream)
+            : build == 1 ? plain::launch_primary(f, fp, band, list, classify ? 1 : 0, states, seedTiles, primaryTarget, heavyTarget, stream)
+                         : launch_primary(f, fp, band, list, classify ? 1 : 0, states, seedTiles, primaryTarget, heavyTarget, stream);
         ctx->tileSeedValid = seedsCacheable && seeded;
         // from here on every pixel of the band outside the figure's screen rectangle is final: the host
         // copy of the image may start (render_host).  Inside a capture this must be a real event-record
@@ -404,11 +406,13 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
         unsigned int* groupCounter = static_cast<unsigned int*>(ctx->countLog.p) + nChunks + c;
         const int shadeGrid = ctx->smCount * ctx->shadeBlocksPerSm;
         if (ctx->shadeMode == 0) {
-            if (posed) launch_wavefront(f, fp, band, list, wave, groupCounter, stream, &launches);
-            else plain::launch_wavefront(f, fp, band, list, wave, groupCounter, stream, &launches);
+            if (build == 2) counter::launch_wavefront(f, fp, band, list, wave, groupCounter, stream, &launches);
+            else if (build == 1) plain::launch_wavefront(f, fp, band, list, wave, groupCounter, stream, &launches);
+            else launch_wavefront(f, fp, band, list, wave, groupCounter, stream, &launches);
         } else {
-            if (posed) launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
-            else plain::launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
+            if (build == 2) counter::launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
+            else if (build == 1) plain::launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
+            else launch_shade(f, fp, band, list, shadeGrid, groupCounter, 0u, stream, ctx->shadeMode);
             ++launches;
         }
         if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 2], stream));
@@ -1040,22 +1044,24 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, const SkinBatchS
             const BatchSlice& first = stageSlices[groupFirstSlice[g]];
             const DevFrame& f = ctx->batchPreps[groups[g][0]].frame;
             launch_batch_reset(gs, nS, stream);
-            const bool posed = f.any_rotated != 0;  // (equal frame descriptions: equal for the whole group)
+            const int build = f.rng_mode ? 2 : (f.any_rotated ? 0 : 1);  // (equal frame descriptions: equal for the whole group)
             // the engines are seeded once per batch — same image geometry for every scene — unless a group is small enough
             // for its tiles to be split over blocks, which changes what is kept per tile
             const int primaryTarget = ctx->smCount * ctx->primaryBlocksPerSm;
             const int statesPerTile = primary_states_per_tile(f, f.tiles_x * f.tiles_y, nS, primaryTarget, 0);
             const bool seedNow = !seeded || statesPerTile != seededStatesPerTile;
-            const bool launched = posed ? launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), seedNow, gs, nS,
-                                                               first.fp.blob_bytes, primaryTarget, stream)
-                                        : plain::launch_primary_batch(f, first.band, static_cast<uint32_t*>(ctx->tileStates.p), seedNow, gs, nS,
-                                                                      first.fp.blob_bytes, primaryTarget, stream);
+            uint32_t* const states = static_cast<uint32_t*>(ctx->tileStates.p);
+            const bool launched =
+                build == 2 ? counter::launch_primary_batch(f, first.band, states, seedNow, gs, nS, first.fp.blob_bytes, primaryTarget, stream)
+                : build == 1 ? plain::launch_primary_batch(f, first.band, states, seedNow, gs, nS, first.fp.blob_bytes, primaryTarget, stream)
+                             : launch_primary_batch(f, first.band, states, seedNow, gs, nS, first.fp.blob_bytes, primaryTarget, stream);
             if (!launched) return MC_OK;  // no batched primary kernel for this frame description: frame-by-frame path instead
             seeded = true;
             seededStatesPerTile = statesPerTile;
             int launches = 0;
-            if (posed) launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
-            else plain::launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
+            if (build == 2) counter::launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
+            else if (build == 1) plain::launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
+            else launch_wavefront(f, first.fp, first.band, first.list, first.wave, nullptr, stream, &launches, gs, nS);
         }
         CU_TRY(cudaGetLastError());
     }
@@ -1861,6 +1867,8 @@ int32_t mcskin_cuda_intersect(const McScene* scene, int32_t device, int32_t box,
 int32_t mcskin_cuda_trace(const McScene* scene, const McConfig* cfg, int32_t device, int32_t useConfig, int32_t depth,
                           const McRay* rays, int32_t n, float* out) {
     if (!cfg || n < 0 || (n > 0 && (!rays || !out))) return fail(MC_ERR_INVALID, "trace: bad argument");
+    // the single-query entry points exist to compare against the reference's functions: mt19937 streams only
+    if (cfg->rng_mode != MC_RNG_MT19937) return fail(MC_ERR_INVALID, "trace: rng_mode 1 is a mode of the render entry points only");
     std::lock_guard<std::mutex> lock(g_ctxMutex);
     McContext* ctx = nullptr;
     int rc = query_setup(scene, cfg, device, useConfig, 0.0f, &ctx);

@@ -65,7 +65,10 @@ Image TileRenderer::render(const Scene& scene, const RayTracer::Config& config,
 
     mcskin::FlatScene flat;
     mcskin::flattenScene(scene, flat);
-    const McConfig cfg = mcskin::flattenConfig(config);
+    McConfig cfg = mcskin::flattenConfig(config);
+    // MCSKIN_RNG=counter: counter-based random streams instead of std::mt19937 (not in RayTracer::Config; frames then
+    // differ from the reference's in their noise only)
+    if (const char* v = std::getenv("MCSKIN_RNG")) cfg.rng_mode = std::strcmp(v, "counter") == 0 ? MC_RNG_COUNTER : MC_RNG_MT19937;
     static_assert(sizeof(Color) == 4 * sizeof(float), "Image::pixels is handed to the C ABI as float RGBA");
     const int spread = deviceSpread();
     int rc;

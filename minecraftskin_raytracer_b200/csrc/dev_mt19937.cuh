@@ -47,6 +47,19 @@ __device__ __forceinline__ float mt_canonical(uint32_t u) {
     return fminf(r, __uint_as_float(0x3f7fffffu));  // r <= 1; only r == 1 is replaced
 }
 
+// ---- counter-based streams (McConfig::rng_mode 1; the MCSKIN_COUNTER_RNG build) -----------------
+// Word k of the stream seeded s is lowbias32(lowbias32(s ^ 0x9e3779b9) + k) (mc_rng_counter_word in mcskin_cuda.h):
+// no engine state, no seeding recurrence; seeds, number and order of draws and the float mapping stay the reference's.
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t counter_key(uint32_t seed) { return lowbias32(seed ^ 0x9e3779b9u); }
+
 // ---- (b) fresh engine, first outputs only -------------------------------------
 // Word 397 of the seeding sequence, given word 1: 396 dependent LCG steps.  Kept as a
 // short rolled loop: fully unrolling it (19 KB of straight-line code) measured 20 % slower
@@ -81,6 +94,12 @@ struct FreshStream {
 
     // `one` must be 1 at run time (see mt_seed_word397_balanced)
     __device__ __forceinline__ void seed_balanced(uint32_t s, uint32_t one) {
+        if (kCounterRng) {  // cur = the stream's key, j = the next word
+            cur = counter_key(s);
+            nxt = far = 0u;
+            j = 0u;
+            return;
+        }
         cur = s;
         nxt = mt_lcg(s, 1u);
         far = mt_seed_word397_balanced(nxt, one);
@@ -88,6 +107,12 @@ struct FreshStream {
     }
 
     __device__ __forceinline__ void seed(uint32_t s) {
+        if (kCounterRng) {
+            cur = counter_key(s);
+            nxt = far = 0u;
+            j = 0u;
+            return;
+        }
         cur = s;
         nxt = mt_lcg(s, 1u);
         far = mt_seed_word397(nxt);
@@ -95,6 +120,7 @@ struct FreshStream {
     }
     // valid for the first kMtN - kMtM = 227 calls
     __device__ __forceinline__ float next() {
+        if (kCounterRng) return mt_canonical(lowbias32(cur + j++));
         const uint32_t v = mt_mix(cur, nxt, far);
         cur = nxt;
         nxt = mt_lcg(nxt, j + 2u);
@@ -110,11 +136,17 @@ struct LocalEngine {
     uint32_t s[kMtN];
     int idx;
     __device__ void seed(uint32_t v) {
+        if (kCounterRng) {
+            s[0] = counter_key(v);
+            idx = 0;
+            return;
+        }
         s[0] = v;
         for (int i = 1; i < kMtN; ++i) s[i] = mt_lcg(s[i - 1], static_cast<uint32_t>(i));
         idx = kMtN;
     }
     __device__ float next() {
+        if (kCounterRng) return mt_canonical(lowbias32(s[0] + static_cast<uint32_t>(idx++)));
         if (idx >= kMtN) {
             for (int i = 0; i < kMtN; ++i) {
                 const int i1 = (i + 1 == kMtN) ? 0 : i + 1;
@@ -149,7 +181,7 @@ struct TileStream {
         if (threadIdx.x == 0) {
             uint32_t x = seedValue;
             sm->state[0][0] = x;
-            for (uint32_t i = 1u; i < static_cast<uint32_t>(kMtN); ++i) {
+            for (uint32_t i = 1u; !kCounterRng && i < static_cast<uint32_t>(kMtN); ++i) {
                 x = mt_lcg(x, i);
                 sm->state[0][i] = x;
             }
@@ -159,6 +191,14 @@ struct TileStream {
 
     // Generates the next 624 words into the ring.  Uniform call; ends with a barrier.
     __device__ void produce_block() {
+        if (kCounterRng) {  // word k of the stream needs nothing but the seed and k
+            const uint32_t key = counter_key(sm->state[0][0]);
+            for (int i = threadIdx.x; i < kMtN; i += blockDim.x)
+                sm->ring[static_cast<int>((produced + i) & kRingMask)] = mt_canonical(lowbias32(key + static_cast<uint32_t>(produced + i)));
+            __syncthreads();
+            produced += kMtN;
+            return;
+        }
         const uint32_t* a = sm->state[which];
         uint32_t* b = sm->state[which ^ 1];
         const int base = static_cast<int>(produced & kRingMask);

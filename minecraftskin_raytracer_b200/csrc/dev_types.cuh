@@ -17,7 +17,16 @@
 #ifndef MCSKIN_POSED
 #define MCSKIN_POSED 1
 #endif
-#if MCSKIN_POSED
+// A third build (kernels_counter.cu, wavefront_counter.cu, namespace mcskin::counter; the general, pose-capable form)
+// replaces every std::mt19937 stream by the counter-based streams of McConfig::rng_mode 1 (dev_mt19937.cuh).
+#ifndef MCSKIN_COUNTER_RNG
+#define MCSKIN_COUNTER_RNG 0
+#endif
+#if MCSKIN_COUNTER_RNG
+#define MCSKIN_VARIANT_BEGIN namespace counter {
+#define MCSKIN_VARIANT_END }
+#define MCSKIN_VARIANT_NS ::mcskin::counter
+#elif MCSKIN_POSED
 #define MCSKIN_VARIANT_BEGIN
 #define MCSKIN_VARIANT_END
 #define MCSKIN_VARIANT_NS ::mcskin
@@ -30,6 +39,7 @@
 namespace mcskin {
 
 constexpr bool kPosedScenes = MCSKIN_POSED != 0;
+constexpr bool kCounterRng = MCSKIN_COUNTER_RNG != 0;
 constexpr int kFaceCount = 6;
 
 // One Mesh == one box (intersection.cpp:200-406).  144 bytes, 16-byte aligned so a
@@ -102,6 +112,7 @@ struct DevFrame {
     int any_rotated;                    // some box (of any index) is posed: needs the MCSKIN_POSED=1 build of the kernels
     float light_pos[3], light_color[4], light_radius;
     float background[4];
+    int rng_mode;             // McConfig::rng_mode: 0 std::mt19937, 1 counter-based streams (the MCSKIN_COUNTER_RNG build)
     // integrator
     int use_config;           // traceRay's config pointer non-null (always 1 for render())
     int soft_on;              // softShadows && shadowSamples > 1 (raytracer.cpp:109)

@@ -46,6 +46,7 @@ void set_last_error(const std::string& message) { g_lastError = message; }
 
 extern "C" const char* mcskin_cuda_last_error(void) { return g_lastError.c_str(); }
 extern "C" int32_t mcskin_cuda_abi_version(void) { return MCSKIN_ABI_VERSION; }
+extern "C" uint32_t mcskin_counter_word(uint32_t seed, uint32_t k) { return mc_rng_counter_word(seed, k); }
 
 extern "C" void mcskin_config_defaults(McConfig* c) {
     if (!c) return;
@@ -112,6 +113,10 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
     McConfig cfg;
     if (cfgIn) cfg = *cfgIn;
     else mcskin_config_defaults(&cfg);
+    if (cfg.rng_mode != MC_RNG_MT19937 && cfg.rng_mode != MC_RNG_COUNTER) {
+        error = "config: rng_mode must be 0 (mt19937) or 1 (counter-based)";
+        return MC_ERR_INVALID;
+    }
 
     DevFrame& f = out.frame;
     std::memset(&f, 0, sizeof(f));
@@ -162,6 +167,7 @@ int prepare_frame(const McScene* scene, const McConfig* cfgIn, int useConfig, fl
     f.light_radius = scene->light_radius;
     std::memcpy(f.background, scene->background, sizeof(f.background));
 
+    f.rng_mode = cfg.rng_mode == MC_RNG_COUNTER ? 1 : 0;
     f.use_config = useConfig ? 1 : 0;
     f.soft_on = (cfg.soft_shadows && cfg.shadow_samples > 1) ? 1 : 0;  // raytracer.cpp:109
     f.shadow_samples = cfg.shadow_samples;

@@ -358,7 +358,7 @@ __device__ __forceinline__ void big_stream_seed(BigStreamSmem* sm, uint32_t seed
     if (threadIdx.x == 0) {
         uint32_t x = seedValue;
         sm->state[0][0] = x;
-        for (uint32_t i = 1u; i < static_cast<uint32_t>(kMtN); ++i) {
+        for (uint32_t i = 1u; !kCounterRng && i < static_cast<uint32_t>(kMtN); ++i) {
             x = mt_lcg(x, i);
             sm->state[0][i] = x;
         }
@@ -367,6 +367,13 @@ __device__ __forceinline__ void big_stream_seed(BigStreamSmem* sm, uint32_t seed
 }
 // one 624-word block: state[which] -> state[which^1], canonical floats into the ring
 __device__ __forceinline__ void big_stream_block(BigStreamSmem* sm, int which, long long produced) {
+    if (kCounterRng) {
+        const uint32_t key = counter_key(sm->state[0][0]);
+        for (int i = threadIdx.x; i < kMtN; i += blockDim.x)
+            sm->ring[static_cast<int>((produced + i) & kBigRingMask)] = mt_canonical(lowbias32(key + static_cast<uint32_t>(produced + i)));
+        __syncthreads();
+        return;
+    }
     const uint32_t* a = sm->state[which];
     uint32_t* b = sm->state[which ^ 1];
     const int base = static_cast<int>(produced & kBigRingMask);
@@ -550,8 +557,22 @@ __device__ __forceinline__ int pix_ring_slot_mod(unsigned int pos) {  // pos < 2
 // second phase still read their far operand from the old block.
 // state: the two 624-word engine states; ring: the float ring; produced: words generated so far
 // (RING == 0) or that count modulo RING.
+// producedAbs: words generated so far, not reduced (the counter-based build numbers the words with it).
 template <bool STORE, int RING = 0>
-__device__ __forceinline__ void pix_stream_block(uint32_t (*state)[kMtN], float* ring, int which, unsigned int produced) {
+__device__ __forceinline__ void pix_stream_block(uint32_t (*state)[kMtN], float* ring, int which, unsigned int produced,
+                                                 unsigned int producedAbs) {
+    if (kCounterRng) {  // word k of the stream needs nothing but the tile's seed (state[0][0], never advanced) and k
+        if (STORE) {
+            const uint32_t key = counter_key(state[0][0]);
+            for (int i = threadIdx.x; i < kMtN; i += kBlockThreads) {
+                const unsigned int n = produced + static_cast<unsigned int>(i);
+                ring[RING > 0 ? pix_ring_slot_mod<(RING > 0 ? RING : 32)>(n) : pix_ring_slot(n)] =
+                    mt_canonical(lowbias32(key + producedAbs + static_cast<unsigned int>(i)));
+            }
+            __syncthreads();
+        }
+        return;
+    }
     constexpr int kCut = 224;
     constexpr int kD = kMtN - kMtM;  // 227
     static_assert(kBlockThreads >= kCut && kCut <= kD && 2 * kCut - kD <= kCut && kMtN - 2 * kCut <= kCut,
@@ -595,7 +616,7 @@ __global__ void k_tile_seed(const DevFrame fr, const BandView band, uint32_t* st
     uint32_t x = static_cast<uint32_t>(tg.y * fr.width + tg.x);  // tile_renderer.cpp:78
     uint32_t* st = states + static_cast<size_t>(t) * statesPerTile * kMtN;
     st[0] = x;
-    for (uint32_t i = 1u; i < static_cast<uint32_t>(kMtN); ++i) {
+    for (uint32_t i = 1u; !kCounterRng && i < static_cast<uint32_t>(kMtN); ++i) {  // (counter-based streams: the seed is all there is)
         x = mt_lcg(x, i);
         st[i] = x;
     }
@@ -611,6 +632,10 @@ __global__ void __launch_bounds__(kBlockThreads)
 k_tile_rounds(uint32_t* states, const int rounds, const unsigned int wordsPerRound) {
     __shared__ uint32_t st[2][kMtN];
     uint32_t* mine = states + static_cast<size_t>(blockIdx.x) * rounds * kMtN;
+    if (kCounterRng) {  // the stream has no state: every round starts from the seed
+        if (threadIdx.x < rounds && threadIdx.x > 0) mine[static_cast<size_t>(threadIdx.x) * kMtN] = mine[0];
+        return;
+    }
     for (int i = threadIdx.x; i < kMtN; i += kBlockThreads) st[0][i] = mine[i];
     __syncthreads();
     int which = 0;
@@ -618,7 +643,7 @@ k_tile_rounds(uint32_t* states, const int rounds, const unsigned int wordsPerRou
     for (int r = 1; r < rounds; ++r) {
         const unsigned int first = static_cast<unsigned int>(r) * wordsPerRound;
         while (produced + kMtN <= first) {
-            pix_stream_block<false>(st, nullptr, which, produced);
+            pix_stream_block<false>(st, nullptr, which, produced, produced);
             which ^= 1;
             produced += kMtN;
         }
@@ -705,12 +730,12 @@ k_primary_pix(const DevFrame fr, const FramePointers fp_, const BandView band_, 
                 __syncthreads();
             }
             while (produced + kMtN <= first) {  // words of rounds other blocks take: state only
-                pix_stream_block<false>(mt->state, mt->ring, which, produced);
+                pix_stream_block<false>(mt->state, mt->ring, which, produced, produced);
                 which ^= 1;
                 produced += kMtN;
             }
             while (produced < need) {  // block-uniform
-                pix_stream_block<true>(mt->state, mt->ring, which, produced);
+                pix_stream_block<true>(mt->state, mt->ring, which, produced, produced);
                 which ^= 1;
                 produced += kMtN;
             }
@@ -845,14 +870,14 @@ k_primary_pix_fixed(const DevFrame fr, const FramePointers fp_, const BandView b
                 __syncthreads();
             }
             while (produced + kMtN <= first) {
-                pix_stream_block<false, kRing>(mt->state, mt->ring, which, producedMod);
+                pix_stream_block<false, kRing>(mt->state, mt->ring, which, producedMod, produced);
                 which ^= 1;
                 produced += kMtN;
                 producedMod += kMtN;
                 if (producedMod >= kRing) producedMod -= kRing;
             }
             while (produced < need) {
-                pix_stream_block<true, kRing>(mt->state, mt->ring, which, producedMod);
+                pix_stream_block<true, kRing>(mt->state, mt->ring, which, producedMod, produced);
                 which ^= 1;
                 produced += kMtN;
                 producedMod += kMtN;

@@ -123,6 +123,9 @@ MCSKIN_HOT_KERNEL_LAUNCHERS
 namespace plain {
 MCSKIN_HOT_KERNEL_LAUNCHERS
 }
+namespace counter {
+MCSKIN_HOT_KERNEL_LAUNCHERS
+}
 // Shading pass: full integrator for every sample of every listed pixel, ordered resolve.
 // Megakernel form of the shading pass over the listed pixels from `firstSlot` on.
 // variant 1: block-synchronous groups; variant 2: warp-autonomous groups with dynamic
@@ -132,6 +135,9 @@ MCSKIN_HOT_KERNEL_LAUNCHERS
 // pixels, for tiles split over blocks): tileStates must hold nTiles * this * 624 words.
 int primary_states_per_tile(const DevFrame& fr, int nTiles, int nScenes, int primaryTargetBlocks, int heavyTargetTiles);
 namespace plain {
+int primary_states_per_tile(const DevFrame& fr, int nTiles, int nScenes, int primaryTargetBlocks, int heavyTargetTiles);
+}
+namespace counter {
 int primary_states_per_tile(const DevFrame& fr, int nTiles, int nScenes, int primaryTargetBlocks, int heavyTargetTiles);
 }
 

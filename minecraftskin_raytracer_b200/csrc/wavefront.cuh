@@ -104,5 +104,8 @@ MCSKIN_HOT_WAVEFRONT_LAUNCHERS
 namespace plain {
 MCSKIN_HOT_WAVEFRONT_LAUNCHERS
 }
+namespace counter {
+MCSKIN_HOT_WAVEFRONT_LAUNCHERS
+}
 
 }  // namespace mcskin

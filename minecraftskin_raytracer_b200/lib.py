@@ -25,7 +25,7 @@ DEFAULT_FRAME_LANES = 2
 
 # every symbol include/mcskin_cuda.h declares
 EXPORTS = [
-    "mcskin_config_defaults", "mcskin_generate_tiles", "mcskin_cuda_device_count", "mcskin_cuda_last_error",
+    "mcskin_config_defaults", "mcskin_counter_word", "mcskin_generate_tiles", "mcskin_cuda_device_count", "mcskin_cuda_last_error",
     "mcskin_cuda_abi_version", "mcskin_cuda_abi_sizes", "mcskin_cuda_render", "mcskin_cuda_render_tile",
     "mcskin_cuda_render_multi", "mcskin_cuda_context_create", "mcskin_cuda_context_destroy",
     "mcskin_cuda_context_set_scene", "mcskin_cuda_context_render_bands", "mcskin_cuda_band_rows",
@@ -66,6 +66,8 @@ def _load() -> C.CDLL:
     lib.mcskin_config_defaults.restype = None
     lib.mcskin_cuda_context_destroy.restype = None
     lib.mcskin_cuda_abi_sizes.restype = None
+    lib.mcskin_counter_word.restype = C.c_uint32
+    lib.mcskin_counter_word.argtypes = [C.c_uint32, C.c_uint32]
     return lib
 
 
@@ -108,6 +110,11 @@ def config_defaults() -> McConfig:
     cfg = McConfig()
     _lib.mcskin_config_defaults(C.byref(cfg))
     return cfg
+
+
+def counter_word(seed: int, k: int) -> int:
+    """Word k of the counter-based stream seeded `seed` (McConfig.rng_mode 1; mc_rng_counter_word in mcskin_cuda.h)."""
+    return int(_lib.mcskin_counter_word(seed & 0xFFFFFFFF, k & 0xFFFFFFFF))
 
 
 def generate_tiles(width: int, height: int, tile_size: int) -> np.ndarray:

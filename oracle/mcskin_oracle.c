@@ -65,15 +65,23 @@ static Col cadd(Col a, Col b) { return col(a.r + b.r, a.g + b.g, a.b + b.b, a.a 
 static Col cmul(Col a, Col b) { return col(a.r * b.r, a.g * b.g, a.b * b.b, a.a * b.a); }
 
 /* ------------------------------------------------- std::mt19937 (ISO 26.5.3.2) */
-typedef struct { uint32_t s[624]; int idx; } Mt;
+/* counter != 0: the stream is McConfig::rng_mode 1's — word k = mc_rng_counter_word(seed, k) (mcskin_cuda.h); this is
+ * the "identically patched oracle" the product's counter-based mode is compared with, not the reference's algorithm. */
+typedef struct { uint32_t s[624]; int idx; int counter; uint32_t seed, k; } Mt;
 
-static void mt_seed(Mt* m, uint32_t seed) {
+static void mt_seed_mode(Mt* m, uint32_t seed, int counter) {
+    m->counter = counter;
+    m->seed = seed;
+    m->k = 0;
+    if (counter) return;
     m->s[0] = seed;
     for (int i = 1; i < 624; ++i) m->s[i] = 1812433253u * (m->s[i - 1] ^ (m->s[i - 1] >> 30)) + (uint32_t)i;
     m->idx = 624;
 }
+static void mt_seed(Mt* m, uint32_t seed) { mt_seed_mode(m, seed, 0); }
 
 static uint32_t mt_next(Mt* m) {
+    if (m->counter) return mc_rng_counter_word(m->seed, m->k++);
     if (m->idx >= 624) {
         for (int i = 0; i < 624; ++i) {
             uint32_t y = (m->s[i] & 0x80000000u) | (m->s[(i + 1) % 624] & 0x7fffffffu);
@@ -324,7 +332,7 @@ static float soft_shadow(Ctx* cx, V3 point, V3 normal, int samples, uint32_t see
     else tangent = vnorm(vcross(v3(0, 1, 0), toPoint));
     V3 bitangent = vcross(toPoint, tangent);
     Mt rng;
-    mt_seed(&rng, seed);
+    mt_seed_mode(&rng, seed, cx->cfg != NULL && cx->cfg->rng_mode == MC_RNG_COUNTER);
     int lit = 0;
     for (int i = 0; i < samples; ++i) {
         float angle = 2.0f * PI_F * canonical_float(&rng);
@@ -395,7 +403,7 @@ static float ambient_occlusion(Ctx* cx, V3 point, V3 normal, int samples, float 
     else T = vnorm(vcross(v3(0, 1, 0), N));
     V3 B = vcross(N, T);
     Mt rng;
-    mt_seed(&rng, seed);
+    mt_seed_mode(&rng, seed, cx->cfg != NULL && cx->cfg->rng_mode == MC_RNG_COUNTER);
     int occluded = 0;
     for (int i = 0; i < samples; ++i) {
         float r1 = canonical_float(&rng);
@@ -524,7 +532,7 @@ static void render_tile(Ctx* cx, const McTile* tile, float* image) {
     float aspect = (float)cfg->width / (float)cfg->height;
     int spp = cfg->samples_per_pixel > 1 ? cfg->samples_per_pixel : 1;
     Mt rng;
-    mt_seed(&rng, (uint32_t)(tile->y * cfg->width + tile->x));
+    mt_seed_mode(&rng, (uint32_t)(tile->y * cfg->width + tile->x), cfg->rng_mode == MC_RNG_COUNTER);
     float focusDist = cfg->focus_distance;
     if (focusDist <= 0.0f) {
         V3 pos = v3(sc->cam_pos[0], sc->cam_pos[1], sc->cam_pos[2]);

@@ -102,3 +102,49 @@ def test_render_tile_equals_render(oracle, mclib):
     assert np.array_equal(_bits(img), _bits(full))
     for threads in (1, 3):
         assert np.array_equal(_bits(oracle.render(scene, cfg, threads=threads)), _bits(full))  # test_tile_renderer.cpp:122-145
+
+
+# ---- McConfig.rng_mode 1 (an extension, not the reference's streams): the switch the oracle shares with the product ----
+
+def _lowbias32(x):
+    x &= 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def test_counter_stream_words_and_statistics(mclib):
+    from minecraftskin_raytracer_b200 import lib
+    for seed in (0, 1, 12345, 0xFFFFFFFF, 0x9E3779B9):
+        for k in (0, 1, 2, 411, 0xFFFFFFFF):
+            assert lib.counter_word(seed, k) == _lowbias32(_lowbias32(seed ^ 0x9E3779B9) + k)
+    # uniform and uncorrelated enough for a Monte-Carlo estimator: bucket counts of one stream and of the first
+    # word of consecutive seeds (how the renderer seeds neighbouring hits and tiles)
+    n = 1 << 14
+    for words in ([lib.counter_word(7, k) for k in range(n)], [lib.counter_word(s, 0) for s in range(n)]):
+        u = np.array(words, dtype=np.float64) / 2.0**32
+        counts = np.bincount((u * 16).astype(int), minlength=16)
+        chi2 = ((counts - n / 16) ** 2 / (n / 16)).sum()
+        assert chi2 < 45.0, chi2                      # 15 degrees of freedom: p(chi2 > 45) < 1e-4
+        assert abs(u.mean() - 0.5) < 0.01
+        assert abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 0.03
+
+
+def test_oracle_counter_mode_changes_the_noise_only(oracle, mclib):
+    from minecraftskin_raytracer_b200 import lib
+    scene = lib.build_skin_scene(synth_skin(1, "64x64"), None)
+    base = dict(width=96, height=96, max_bounces=3)
+    # no stream is drawn from: the two modes are the same frame
+    still = dict(samples_per_pixel=1, soft_shadows=0, **base)
+    a, b = oracle.render(scene, make_config(**still)), oracle.render(scene, make_config(rng_mode=1, **still))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # streams in use: other noise, same picture
+    noisy = dict(samples_per_pixel=16, **base)
+    a, b = oracle.render(scene, make_config(**noisy)), oracle.render(scene, make_config(rng_mode=1, **noisy))
+    assert not np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert abs(float(a[..., :3].mean()) - float(b[..., :3].mean())) < 2e-3
+    assert float(np.abs(a - b).mean()) < 0.02
+    # the unmodified reference has no such switch: its wrapper ignores the field

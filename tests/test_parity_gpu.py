@@ -905,3 +905,90 @@ def test_skin_batch_sliced_on_the_device(gpu, oracle, kind, poses):
             ctx.render_skin_batch(np.zeros((1, 48, 64, 4), dtype=np.uint8), cfg, None, b.data_ptr(), 0, 0)
     finally:
         ctx.close()
+
+
+# ---- McConfig.rng_mode 1: counter-based random streams (not the reference's; the oracle carries the same switch) ----
+
+COUNTER_MODES = ["default", "all_active", "megakernel", "megakernel_warp", "tiny_queue", "split_tiles",
+                 "one_lane_no_graph", "two_soft_blocks"]
+
+
+@pytest.mark.parametrize("case", RENDER_CASES, ids=[c[0] for c in RENDER_CASES])
+@pytest.mark.parametrize("mode", COUNTER_MODES)
+def test_render_parity_counter_rng(gpu, oracle, case, mode):
+    """With rng_mode 1 every stream (tile jitter, lens, soft shadows, AO) is the counter-based one; seeds, draw
+    order and the float mapping are unchanged, so the frame equals the oracle's with the same switch bit for bit —
+    through every code path of the library — and differs from the mt19937 frame in its noise only."""
+    name, seed, kind, pose, over = case
+    scene = _scene(gpu, seed, kind, pose)
+    cfg = make_config(rng_mode=1, **over)
+    want = oracle.render(scene, cfg)
+    got = _render_with_options(gpu, scene, cfg, RENDER_MODES[mode])
+    rep = pixel_report(got, want, oracle.quantize)
+    assert rep["within1"] >= 0.999, rep
+    if _flip_budget() == 0.0:
+        assert np.array_equal(_bits(got), _bits(want)), rep
+    if mode == "default":
+        mt = oracle.render(scene, make_config(**over))
+        uses_streams = cfg.samples_per_pixel > 1 or cfg.dof_enabled or cfg.soft_shadows or cfg.ao_enabled
+        if uses_streams:
+            assert not np.array_equal(_bits(want), _bits(mt))
+        # the same estimator: the frame means agree to well within the noise of either
+        assert abs(float(want[..., :3].mean()) - float(mt[..., :3].mean())) < 0.01
+
+
+def test_counter_rng_context_switches_modes_and_shapes(gpu, oracle):
+    """One context alternating between the two stream kinds (the kept tile seeds are per kind), tile sets and
+    the batch entry points with rng_mode 1."""
+    import torch
+    scene = _scene(gpu, 3, "64x64", "walking")
+    base = dict(width=160, height=128, samples_per_pixel=4, max_bounces=3)
+    cfg_mt, cfg_ctr = make_config(**base), make_config(rng_mode=1, **base)
+    want_mt, want_ctr = oracle.render(scene, cfg_mt), oracle.render(scene, cfg_ctr)
+    ctx = gpu.Context(0)
+    try:
+        out = torch.zeros((128, 160, 4), dtype=torch.float32, device="cuda:0")
+
+        def frame(cfg):
+            ctx.set_scene(scene, cfg)
+            out.zero_()
+            torch.cuda.synchronize()
+            ctx.render_bands(0, 1, out.data_ptr(), 0, 0)
+            ctx.sync()
+            return out.cpu().numpy()
+
+        for cfg, want in ((cfg_ctr, want_ctr), (cfg_mt, want_mt), (cfg_ctr, want_ctr), (cfg_ctr, want_ctr), (cfg_mt, want_mt)):
+            got = frame(cfg)
+            assert pixel_report(got, want, oracle.quantize)["within1"] >= 0.999
+            if _flip_budget() == 0.0:
+                assert np.array_equal(_bits(got), _bits(want))
+        # tile sets
+        ctx.set_scene(scene, cfg_ctr)
+        ref_frame = frame(cfg_ctr)
+        out.fill_(-1.0)
+        torch.cuda.synchronize()
+        for r in range(3):
+            ctx.render_tiles_into_frame(gpu.partition_tiles(scene, cfg_ctr, 3, r), out.data_ptr(), 0, 0)
+            ctx.sync()
+        assert np.array_equal(_bits(out.cpu().numpy()), _bits(ref_frame))
+        # batch of scenes, and of skins sliced on the device
+        n = 6
+        skins = [synth_skin(40 + i, "64x64") for i in range(n)]
+        scenes = [gpu.build_skin_scene(s, "walking") for s in skins]
+        cfg_b = make_config(rng_mode=1, width=64, height=64, samples_per_pixel=4, max_bounces=2)
+        outb = torch.zeros((n, 64, 64, 4), dtype=torch.float32, device="cuda:0")
+        torch.cuda.synchronize()
+        ctx.render_batch(scenes, cfg_b, outb.data_ptr(), 0, 0)
+        ctx.sync()
+        got = outb.cpu().numpy()
+        for i in range(n):
+            want = oracle.render(scenes[i], cfg_b)
+            assert pixel_report(got[i], want, oracle.quantize)["within1"] >= 0.999
+            if _flip_budget() == 0.0:
+                assert np.array_equal(_bits(got[i]), _bits(want)), i
+    finally:
+        ctx.close()
+    with pytest.raises(gpu.McSkinError):
+        gpu.render(scene, make_config(rng_mode=2, **base))
+    with pytest.raises(gpu.McSkinError):   # the single-query views restate reference functions: mt19937 only
+        gpu.trace(scene, cfg_ctr, random_rays(np.random.default_rng(1), 8))
