@@ -177,8 +177,11 @@ struct McContext {
     // stats of the last render
     McRenderStats stats{};
     bool statsPending = false;
-    std::vector<unsigned int> hostCounts;  // active-pixel counts read back lazily
+    bool uploadQueued = false;             // evUpload has been recorded at least once
     DevBuf countLog;                       // one counter per chunk of the last render
+    PinnedBuf countHost;                   // ... and where the frame's last kernel (or a copy) leaves them for the statistics
+    unsigned int* countAlias = nullptr;    // countHost as the device addresses it (null: not mapped)
+    PinnedBuf sceneStage;                  // page-locked staging of the scene blob and texels (upload_scene)
     int chunksLastRender = 0;
     // batch rendering
     int batchLanes = 4;
@@ -203,12 +206,20 @@ int upload_scene(McContext* ctx) {
                                       std::to_string(pf.boxes.size()) + " boxes)");
     CU_TRY(ctx->boxes.reserve(pf.blob.size()));
     CU_TRY(ctx->texels.reserve(pf.texels.size() * sizeof(float4h)));
-    CU_TRY(cudaMemcpyAsync(ctx->boxes.p, pf.blob.data(), pf.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(ctx->texels.p, pf.texels.data(), pf.texels.size() * sizeof(float4h),
-                           cudaMemcpyHostToDevice, ctx->stream));
-    // pageable sources: the copies above are staged synchronously by the runtime, so the
-    // host vectors may change afterwards; renders on another stream wait for this event
+    // Through a page-locked staging buffer: two host memcpys (~55 KB) and two copies the runtime only has to queue
+    // (from pageable memory it stages them itself, synchronously: ~30 us per scene).  The host vectors may change
+    // afterwards; the staging buffer is reused once the previous upload has left it; renders on another stream wait
+    // for the event.
+    const size_t blobBytes = (pf.blob.size() + 255) & ~size_t(255), texelBytes = pf.texels.size() * sizeof(float4h);
+    if (ctx->uploadQueued) CU_TRY(cudaEventSynchronize(ctx->evUpload));
+    CU_TRY(ctx->sceneStage.reserve(blobBytes + texelBytes + 256));
+    unsigned char* stage = static_cast<unsigned char*>(ctx->sceneStage.p);
+    std::memcpy(stage, pf.blob.data(), pf.blob.size());
+    if (texelBytes) std::memcpy(stage + blobBytes, pf.texels.data(), texelBytes);
+    CU_TRY(cudaMemcpyAsync(ctx->boxes.p, stage, pf.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (texelBytes) CU_TRY(cudaMemcpyAsync(ctx->texels.p, stage + blobBytes, texelBytes, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaEventRecord(ctx->evUpload, ctx->stream));
+    ctx->uploadQueued = true;
     return MC_OK;
 }
 
@@ -291,6 +302,17 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
     const int nChunks = static_cast<int>((nUnits + unitsPerChunk - 1) / unitsPerChunk);
 
     CU_TRY(ctx->countLog.reserve(sizeof(unsigned int) * 2 * nChunks));  // [active count | group counter] per chunk
+    if (ctx->countHost.cap < sizeof(unsigned int) * nChunks) {
+        g_allocEpoch.fetch_add(1);  // (captured graphs copy to the old address)
+        CU_TRY(ctx->countHost.reserve(sizeof(unsigned int) * std::max(1024, 2 * nChunks)));
+        void* alias = nullptr;
+        if (cudaHostGetDevicePointer(&alias, ctx->countHost.p, 0) != cudaSuccess) {
+            cudaGetLastError();
+            alias = nullptr;
+        }
+        ctx->countAlias = static_cast<unsigned int*>(alias);
+    }
+    unsigned int* const countAlias = ctx->countAlias;
     CU_TRY(ctx->slotPixel.reserve(slotCap * sizeof(uint2)));
     CU_TRY(ctx->records.reserve(std::max<size_t>(16, slotCap * recordBytesPerSlot)));
     // Splitting the figure's tiles pays only when the frame (all lanes in flight) has too few tiles to
@@ -382,6 +404,9 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
         list.slot_pixel = static_cast<uint2*>(ctx->slotPixel.p);
         list.records = static_cast<float*>(ctx->records.p);
         list.capacity = static_cast<unsigned int>(std::min(slotCap, std::max<size_t>(1, listing * slotsPerUnit)));
+        // the wavefront's last kernel leaves the count in page-locked host memory for the statistics (no copy, nothing
+        // more in the stream); the other shading modes copy it below
+        list.count_host = (ctx->shadeMode == 0 && countAlias) ? countAlias + c : nullptr;
         if (!classify) {
             // positional slots: mark all unused, preset the count to the capacity
             CU_TRY(cudaMemsetAsync(list.slot_pixel, 0xff, static_cast<size_t>(list.capacity) * sizeof(uint2), stream));
@@ -418,6 +443,8 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
         if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->passEvents[3 * c + 2], stream));
         ++launches;
     }
+    if (!(ctx->shadeMode == 0 && countAlias))
+        CU_TRY(cudaMemcpyAsync(ctx->countHost.p, ctx->countLog.p, sizeof(unsigned int) * nChunks, cudaMemcpyDeviceToHost, stream));
     if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->ev1, stream));
     CU_TRY(cudaGetLastError());
     ctx->chunksLastRender = nChunks;
@@ -632,12 +659,11 @@ int finish_stats(McContext* ctx, McRenderStats* out) {
             ctx->stats.ms_primary += a;
             ctx->stats.ms_shade += b;
         }
-        ctx->hostCounts.resize(ctx->chunksLastRender);
-        if (ctx->chunksLastRender > 0)
-            CU_TRY(cudaMemcpy(ctx->hostCounts.data(), ctx->countLog.p, sizeof(unsigned int) * ctx->chunksLastRender,
-                              cudaMemcpyDeviceToHost));
+        // (left in countHost by the frame's last kernel or by a copy behind it, before ev1 — for a lane inside its
+        // parent's graph: before the parent's ev1, which the parent has waited for by now)
         long long active = 0;
-        for (unsigned int v : ctx->hostCounts) active += v;
+        const unsigned int* counts = static_cast<const unsigned int*>(ctx->countHost.p);
+        for (int c = 0; c < ctx->chunksLastRender && counts; ++c) active += counts[c];
         ctx->stats.n_active_pixels = static_cast<int32_t>(std::min<long long>(active, 0x7fffffff));
         ctx->statsPending = false;
         // a frame split over lanes: the lanes ran side by side, so counts add and pass times overlap
@@ -1015,6 +1041,7 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, const SkinBatchS
                 sl.list.slot_pixel = static_cast<uint2*>(ctx->batchSlots.p) + static_cast<size_t>(i) * slotCap;
                 sl.list.records = reinterpret_cast<float*>(static_cast<unsigned char*>(ctx->batchRecords.p) + static_cast<size_t>(i) * recordBytes);
                 sl.list.capacity = static_cast<unsigned int>(slotCap);
+                sl.list.count_host = nullptr;
                 // few blocks per scene: a launch has gridDim.y scenes to fill the machine with
                 const int gridX = std::max(2, (ctx->smCount * ctx->shadeBlocksPerSm + nC - 1) / nC);
                 if (!wavefront_carve(pf.frame, static_cast<unsigned char*>(ctx->batchWave.p) + static_cast<size_t>(i) * waveBytes,
@@ -1134,6 +1161,8 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
                       &ctx->blockTimes})
         b->release();
     ctx->pinned.release();
+    ctx->countHost.release();
+    ctx->sceneStage.release();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);

@@ -92,6 +92,7 @@ struct ActiveList {
     uint2* slot_pixel;    // x = index into the band image, y = px | (py << 16); x = 0xffffffff: unused slot
     float* records;       // slot-major, spp * draws_per_sample floats per slot: jx, jy [, lens r1, r2]
     unsigned int capacity;
+    unsigned int* count_host;  // if set (page-locked host memory as the device sees it): the frame's last kernel leaves the count there
 };
 
 struct FramePointers {

@@ -473,6 +473,7 @@ k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list
     __shared__ __align__(16) float stageAll[kWfThreads / 32][kWarpStageFloats];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int count = *list.count;
+    if (!BATCH && list.count_host && blockIdx.x == 0 && threadIdx.x == 0) *list.count_host = count;  // for the statistics
     if (count > list.capacity) count = list.capacity;
     if (count > wv.slotCapacity) count = wv.slotCapacity;
     const int spp = fr.spp;
@@ -510,6 +511,7 @@ k_wf_resolve_pixel(const DevFrame fr, const BandView band_, const ActiveList lis
     const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
     const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     unsigned int count = *list.count;
+    if (!BATCH && list.count_host && blockIdx.x == 0 && threadIdx.x == 0) *list.count_host = count;  // for the statistics
     if (count > list.capacity) count = list.capacity;
     if (count > wv.slotCapacity) count = wv.slotCapacity;
     const int spp = fr.spp;
