@@ -83,11 +83,18 @@ constexpr int kWarpStageFloats = 32 * 4 + 32 * 4;
 // 4p+c (so 4*32/spp lanes run the dependent add chains side by side), scaled by 1/spp and
 // written out.  resolveMask: bit p set = pixel p is resolved here; outIndex: the band-image
 // index held by the first lane of each pixel.
+// outStage != null: the averages are not written to the image but to outStage[p] (p = pixel of the warp), for a caller
+// that collects the pixels of several calls and stores them together (the wavefront resolve: whole runs of
+// neighbouring pixels per store instead of 16 bytes at a time — the image may lie across PCIe or NVLink).
 __device__ __forceinline__ void warp_resolve(const DevFrame& fr, const BandView& band, float* stageW, int lane,
                                              int spp, int lgSpp, float4 colour, unsigned int outIndex,
-                                             unsigned int resolveMask) {
+                                             unsigned int resolveMask, float4* outStage = nullptr) {
     if (spp == 1) {  // nothing to add: every lane writes its own pixel
-        if ((resolveMask >> lane) & 1u) store_pixel(band, outIndex, scale4(add4(make_float4(0.f, 0.f, 0.f, 0.f), colour), fr.inv_spp));
+        if ((resolveMask >> lane) & 1u) {
+            const float4 c = scale4(add4(make_float4(0.f, 0.f, 0.f, 0.f), colour), fr.inv_spp);
+            if (outStage) outStage[lane] = c;
+            else store_pixel(band, outIndex, c);
+        }
         return;
     }
     const int pix = lane >> lgSpp;
@@ -105,6 +112,13 @@ __device__ __forceinline__ void warp_resolve(const DevFrame& fr, const BandView&
             const float* src = stageW + (p << lgSpp) * 4 + p * 4 + ch;
             for (int i = 0; i < spp; ++i) acc += src[i * 4];
             acc *= fr.inv_spp;
+        }
+        if (outStage) {
+            const float a1 = __shfl_down_sync(kFullMask, acc, 1);
+            const float a2 = __shfl_down_sync(kFullMask, acc, 2);
+            const float a3 = __shfl_down_sync(kFullMask, acc, 3);
+            if (on && ch == 0) outStage[p] = make_float4(acc, a1, a2, a3);
+            continue;
         }
         const int leader = (p << lgSpp) & 31;
         const unsigned int idx = __shfl_sync(kFullMask, outIndex, leader);

@@ -471,6 +471,7 @@ k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list
     const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
     const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     __shared__ __align__(16) float stageAll[kWfThreads / 32][kWarpStageFloats];
+    __shared__ __align__(16) float4 outAll[kWfThreads / 32][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int count = *list.count;
     if (!BATCH && list.count_host && blockIdx.x == 0 && threadIdx.x == 0) *list.count_host = count;  // for the statistics
@@ -478,27 +479,45 @@ k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list
     if (count > wv.slotCapacity) count = wv.slotCapacity;
     const int spp = fr.spp;
     const int pixPerGroup = 32 >> lgSpp;
-    const unsigned int nGroups = (count + pixPerGroup - 1) / pixPerGroup;
     const int pix = lane >> lgSpp, s = lane & (spp - 1);
     float* stageW = stageAll[warp];
-    for (unsigned int g = blockIdx.x * (kWfThreads / 32) + warp; g < nGroups; g += gridDim.x * (kWfThreads / 32)) {
-        const unsigned int slot = g * pixPerGroup + pix;
-        uint2 sp = make_uint2(kUnusedSlot, 0u);
-        if (slot < count) sp = list.slot_pixel[slot];
-        const bool on = sp.x != kUnusedSlot;
-        float4 colour = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on) colour = fold_path(wv, static_cast<size_t>(slot) * spp + s);
-        const unsigned int leaders = __ballot_sync(0xffffffffu, on && s == 0);
-        unsigned int resolveMask = 0u;
-        {
-            unsigned int m = leaders;
-            while (m) {
-                const int l = __ffs(m) - 1;
-                m &= m - 1u;
-                resolveMask |= 1u << (l >> lgSpp);
+    float4* outW = outAll[warp];
+    // Every warp takes an equal run of consecutive slots — the primary pass hands out slots in runs of neighbouring
+    // pixels of a tile row — and works through it up to 32 slots at a time: 32 / spp pixels per round are averaged into
+    // shared memory, then lane l stores pixel l, so neighbours leave as one piece of up to 512 bytes instead of 16
+    // bytes at a time (the image may lie across PCIe or NVLink).  Equal runs, because the rounds of a warp are
+    // dependent loads in series and a frame has only some ten of them per resident warp.
+    const unsigned int totalWarps = gridDim.x * (kWfThreads / 32);
+    const unsigned int perWarp = ((count + totalWarps - 1u) / totalWarps + pixPerGroup - 1u) / pixPerGroup * pixPerGroup;
+    const unsigned int first = (blockIdx.x * (kWfThreads / 32) + warp) * perWarp;
+    const unsigned int last = min(count, first + perWarp);
+    for (unsigned int base = first; base < last; base += 32u) {
+        const unsigned int mySlot = base + lane;
+        const unsigned int myPixel = mySlot < last ? list.slot_pixel[mySlot].x : kUnusedSlot;
+        const int rounds = (static_cast<int>(min(32u, last - base)) + pixPerGroup - 1) >> (5 - lgSpp);
+        for (int g = 0; g < rounds; ++g) {
+            const int local = g * pixPerGroup + pix;  // slot of the batch this lane's sample belongs to
+            const unsigned int slot = base + local;
+            const unsigned int pixelIndex = __shfl_sync(0xffffffffu, myPixel, local);
+            const bool on = pixelIndex != kUnusedSlot;
+            if (__ballot_sync(0xffffffffu, on) == 0u) continue;
+            float4 colour = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on) colour = fold_path(wv, static_cast<size_t>(slot) * spp + s);
+            const unsigned int leaders = __ballot_sync(0xffffffffu, on && s == 0);
+            unsigned int resolveMask = 0u;
+            {
+                unsigned int m = leaders;
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1u;
+                    resolveMask |= 1u << (l >> lgSpp);
+                }
             }
+            warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, pixelIndex, resolveMask, outW + g * pixPerGroup);
         }
-        warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, sp.x, resolveMask);
+        __syncwarp();
+        if (myPixel != kUnusedSlot) store_pixel(band, myPixel, outW[lane]);
+        __syncwarp();
     }
 }
 
