@@ -182,6 +182,7 @@ struct McContext {
     PinnedBuf countHost;                   // ... and where the frame's last kernel (or a copy) leaves them for the statistics
     unsigned int* countAlias = nullptr;    // countHost as the device addresses it (null: not mapped)
     PinnedBuf sceneStage;                  // page-locked staging of the scene blob and texels (upload_scene)
+    std::vector<std::pair<const void*, bool>> farCache;  // is_far_memory
     int chunksLastRender = 0;
     // batch rendering
     int batchLanes = 4;
@@ -252,6 +253,21 @@ struct BandSpec {
     float4* hotF32 = nullptr;  // BandView::hot_*: where the tiles the figure's rectangle touches are written instead
     uchar4* hotU8 = nullptr;
 };
+
+// Is p (an output image the kernels store to) anything but this context's device memory: a mapped host range, a
+// peer device's allocation?  The last answers are kept: the pointers of a render loop repeat.
+static bool is_far_memory(McContext* ctx, const void* p) {
+    if (!p) return false;
+    for (const auto& e : ctx->farCache)
+        if (e.first == p) return e.second;
+    cudaPointerAttributes attr{};
+    bool far = false;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) far = attr.type == cudaMemoryTypeHost || (attr.type == cudaMemoryTypeDevice && attr.device != ctx->device);
+    else cudaGetLastError();
+    if (ctx->farCache.size() >= 8) ctx->farCache.erase(ctx->farCache.begin());
+    ctx->farCache.emplace_back(p, far);
+    return far;
+}
 
 // Launches the two passes of a band on one stream; output pointers are device memory.  scn: the context whose
 // scene (prepared frame, box and texel buffers) is rendered.
@@ -371,6 +387,8 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
     ctx->tileSeedKey = seedKey;
     ctx->tileSeedValid = false;
     if (seedTiles) ++ctx->seedGen;
+    // where the shaded pixels go: this device's memory, or across a link (BandView::far_output)
+    const bool farOutput = spec.hotF32 || spec.hotU8 || is_far_memory(ctx, outF32) || is_far_memory(ctx, outU8);
     for (int c = 0; c < nChunks; ++c) {
         const size_t unit0 = static_cast<size_t>(c) * unitsPerChunk;
         const size_t units = std::min<size_t>(unitsPerChunk, nUnits - unit0);
@@ -379,6 +397,7 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
         band.out_u8 = outU8;
         band.hot_f32 = spec.hotF32;
         band.hot_u8 = spec.hotU8;
+        band.far_output = farOutput ? 1 : 0;
         if (ctx->debugPrimaryTiming && nChunks == 1) {  // room for the finest split: one block per 256-pixel round of every tile
             const size_t blocks = static_cast<size_t>(nTilesAll) * ((tilePixels + kBlockThreads - 1) / kBlockThreads);
             CU_TRY(ctx->blockTimes.reserve(blocks * 4 * sizeof(unsigned long long)));

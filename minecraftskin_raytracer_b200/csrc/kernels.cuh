@@ -77,6 +77,9 @@ struct BandView {
     uchar4* hot_u8;
     const int* tile_map;  // device memory, or null
     int n_tiles, n_heavy;
+    // != 0: the shaded pixels land in memory across PCIe or NVLink (a mapped host image, a peer GPU's frame): the
+    // resolve kernel then stores runs of neighbouring pixels together instead of one pixel at a time
+    int far_output;
     // diagnosis ("debug_primary_timing" option): 4 words per block of the pixel-per-lane primary kernels —
     // %globaltimer at entry and exit, the block's frame tile, part | parts << 16; null otherwise
     unsigned long long* block_times;

@@ -482,11 +482,37 @@ k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list
     const int pix = lane >> lgSpp, s = lane & (spp - 1);
     float* stageW = stageAll[warp];
     float4* outW = outAll[warp];
-    // Every warp takes an equal run of consecutive slots — the primary pass hands out slots in runs of neighbouring
-    // pixels of a tile row — and works through it up to 32 slots at a time: 32 / spp pixels per round are averaged into
-    // shared memory, then lane l stores pixel l, so neighbours leave as one piece of up to 512 bytes instead of 16
-    // bytes at a time (the image may lie across PCIe or NVLink).  Equal runs, because the rounds of a warp are
-    // dependent loads in series and a frame has only some ten of them per resident warp.
+    // One round: the 32 samples of 32 / spp listed pixels (slot = firstSlot + pix for this lane), folded and averaged in
+    // sample order; the averages go to the image, or to outStage for the caller to store.
+    auto round = [&](unsigned int slot, unsigned int pixelIndex, float4* outStage) {
+        const bool on = pixelIndex != kUnusedSlot;
+        float4 colour = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) colour = fold_path(wv, static_cast<size_t>(slot) * spp + s);
+        const unsigned int leaders = __ballot_sync(0xffffffffu, on && s == 0);
+        unsigned int resolveMask = 0u;
+        unsigned int m = leaders;
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1u;
+            resolveMask |= 1u << (l >> lgSpp);
+        }
+        warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, pixelIndex, resolveMask, outStage);
+    };
+    if (!band.far_output) {
+        // the image is this device's memory: rounds dealt to the warps of the grid in turn (the grid streams through the
+        // path arrays front to back), every pixel stored as soon as it is averaged
+        const unsigned int nRounds = (count + pixPerGroup - 1) / pixPerGroup;
+        for (unsigned int g = blockIdx.x * (kWfThreads / 32) + warp; g < nRounds; g += gridDim.x * (kWfThreads / 32)) {
+            const unsigned int slot = g * pixPerGroup + pix;
+            round(slot, slot < count ? list.slot_pixel[slot].x : kUnusedSlot, nullptr);
+        }
+        return;
+    }
+    // The image lies across PCIe or NVLink (a mapped host image, a peer's frame): stores of 16 bytes at a time waste the
+    // link.  Every warp takes an equal run of consecutive slots — the primary pass hands out slots in runs of
+    // neighbouring pixels of a tile row — and works through it up to 32 slots at a time: the rounds' averages go to
+    // shared memory, then lane l stores pixel l, so neighbours leave as one piece of up to 512 bytes.  Equal runs,
+    // because the rounds of a warp are dependent loads in series and a frame has only some ten of them per warp.
     const unsigned int totalWarps = gridDim.x * (kWfThreads / 32);
     const unsigned int perWarp = ((count + totalWarps - 1u) / totalWarps + pixPerGroup - 1u) / pixPerGroup * pixPerGroup;
     const unsigned int first = (blockIdx.x * (kWfThreads / 32) + warp) * perWarp;
@@ -497,23 +523,9 @@ k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list
         const int rounds = (static_cast<int>(min(32u, last - base)) + pixPerGroup - 1) >> (5 - lgSpp);
         for (int g = 0; g < rounds; ++g) {
             const int local = g * pixPerGroup + pix;  // slot of the batch this lane's sample belongs to
-            const unsigned int slot = base + local;
             const unsigned int pixelIndex = __shfl_sync(0xffffffffu, myPixel, local);
-            const bool on = pixelIndex != kUnusedSlot;
-            if (__ballot_sync(0xffffffffu, on) == 0u) continue;
-            float4 colour = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (on) colour = fold_path(wv, static_cast<size_t>(slot) * spp + s);
-            const unsigned int leaders = __ballot_sync(0xffffffffu, on && s == 0);
-            unsigned int resolveMask = 0u;
-            {
-                unsigned int m = leaders;
-                while (m) {
-                    const int l = __ffs(m) - 1;
-                    m &= m - 1u;
-                    resolveMask |= 1u << (l >> lgSpp);
-                }
-            }
-            warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, pixelIndex, resolveMask, outW + g * pixPerGroup);
+            if (__ballot_sync(0xffffffffu, pixelIndex != kUnusedSlot) == 0u) continue;
+            round(base + local, pixelIndex, outW + g * pixPerGroup);
         }
         __syncwarp();
         if (myPixel != kUnusedSlot) store_pixel(band, myPixel, outW[lane]);
