@@ -463,7 +463,9 @@ __device__ __forceinline__ float4 fold_path(const WaveView& wv, size_t path) {
     return c;
 }
 
-template <bool BATCH>
+// FAR: the form for images across a link (BandView::far_output); two instantiations, so that the streaming form keeps
+// its 32 registers (8 resident blocks: the kernel lives on loads in flight).
+template <bool BATCH, bool FAR>
 __global__ void __launch_bounds__(kWfThreads)
 k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list_, const WaveView wv_, const int lgSpp,
                   const BatchSlice* __restrict__ batch) {
@@ -471,7 +473,7 @@ k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list
     const ActiveList& list = BATCH ? batch[blockIdx.y].list : list_;
     const WaveView& wv = BATCH ? batch[blockIdx.y].wave : wv_;
     __shared__ __align__(16) float stageAll[kWfThreads / 32][kWarpStageFloats];
-    __shared__ __align__(16) float4 outAll[kWfThreads / 32][32];
+    __shared__ __align__(16) float4 outAll[FAR ? kWfThreads / 32 : 1][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int count = *list.count;
     if (!BATCH && list.count_host && blockIdx.x == 0 && threadIdx.x == 0) *list.count_host = count;  // for the statistics
@@ -481,7 +483,7 @@ k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list
     const int pixPerGroup = 32 >> lgSpp;
     const int pix = lane >> lgSpp, s = lane & (spp - 1);
     float* stageW = stageAll[warp];
-    float4* outW = outAll[warp];
+    float4* outW = outAll[FAR ? warp : 0];
     // One round: the 32 samples of 32 / spp listed pixels (slot = firstSlot + pix for this lane), folded and averaged in
     // sample order; the averages go to the image, or to outStage for the caller to store.
     auto round = [&](unsigned int slot, unsigned int pixelIndex, float4* outStage) {
@@ -498,7 +500,7 @@ k_wf_resolve_warp(const DevFrame fr, const BandView band_, const ActiveList list
         }
         warp_resolve(fr, band, stageW, lane, spp, lgSpp, colour, pixelIndex, resolveMask, outStage);
     };
-    if (!band.far_output) {
+    if (!FAR) {
         // the image is this device's memory: rounds dealt to the warps of the grid in turn (the grid streams through the
         // path arrays front to back), every pixel stored as soon as it is averaged
         const unsigned int nRounds = (count + pixPerGroup - 1) / pixPerGroup;
@@ -675,7 +677,13 @@ void launch_wavefront(const DevFrame& fr, const FramePointers& fp, const BandVie
             MCSKIN_WF_LAUNCH(k_wf_overflow, g, blob, fr, fp, list, wv);
     }
     const int lg = log2_pow2_le32(fr.spp);
-    if (lg >= 0) MCSKIN_WF_LAUNCH(k_wf_resolve_warp, g, 0, fr, band, list, wv, lg);
+    if (lg >= 0) {
+        const bool farImage = !batch && band.far_output != 0;
+        if (batch) k_wf_resolve_warp<true, false><<<g, kWfThreads, 0, stream>>>(fr, band, list, wv, lg, batch);
+        else if (farImage) k_wf_resolve_warp<false, true><<<g, kWfThreads, 0, stream>>>(fr, band, list, wv, lg, batch);
+        else k_wf_resolve_warp<false, false><<<g, kWfThreads, 0, stream>>>(fr, band, list, wv, lg, batch);
+        ++n;
+    }
     else MCSKIN_WF_LAUNCH(k_wf_resolve_pixel, g, 0, fr, band, list, wv);
 #undef MCSKIN_WF_LAUNCH
     // pixels the queues could not take: megakernel, starting at the first slot beyond them
