@@ -992,3 +992,39 @@ def test_counter_rng_context_switches_modes_and_shapes(gpu, oracle):
         gpu.render(scene, make_config(rng_mode=2, **base))
     with pytest.raises(gpu.McSkinError):   # the single-query views restate reference functions: mt19937 only
         gpu.trace(scene, cfg_ctr, random_rays(np.random.default_rng(1), 8))
+
+
+def test_active_pixel_count_through_every_path(gpu, oracle):
+    """McRenderStats.n_active_pixels (the pixels the primary pass hands to the shading pass) reaches the host by
+    different routes — left in mapped host memory by the wavefront's last kernel, copied behind the launches in the
+    other shading modes, per lane and added up, inside a replayed graph: the same number every time, and the number
+    of pixels that are not pure background at least."""
+    import torch
+    scene = _scene(gpu, 2, "64x64", "waving")
+    cfg = make_config(width=224, height=160, samples_per_pixel=4, max_bounces=2)
+    want = oracle.render(scene, cfg)
+    not_background = int((~_background_pixels(oracle, scene, cfg, want)).sum())
+    counts = {}
+    out = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.float32, device="cuda:0")
+    for name, opts in (("wavefront", {}), ("one_lane_no_graph", RENDER_MODES["one_lane_no_graph"]),
+                       ("megakernel", RENDER_MODES["megakernel"]), ("megakernel_warp", RENDER_MODES["megakernel_warp"]),
+                       ("five_lanes", RENDER_MODES["five_lanes"]), ("small_queue", RENDER_MODES["small_queue"])):
+        ctx = gpu.Context(0)
+        try:
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            ctx.set_scene(scene, cfg)
+            seen = []
+            for _ in range(3):  # direct launches, graph capture, replay
+                ctx.render_bands(0, 1, out.data_ptr(), 0, 0)
+                seen.append(ctx.sync()["n_active_pixels"])
+            assert seen[0] == seen[1] == seen[2], (name, seen)
+            counts[name] = seen[0]
+        finally:
+            ctx.close()
+    assert len(set(counts.values())) == 1, counts
+    n = counts["wavefront"]
+    assert not_background <= n <= cfg.width * cfg.height // 2, (n, not_background)
+    # the host call reports the same
+    _, _, stats = gpu.render(scene, cfg)
+    assert stats["n_active_pixels"] == n
