@@ -226,6 +226,11 @@ int32_t mcskin_cuda_context_render_scene_tiles(McContext* ctx, const McScene* sc
  * of them to out_tiles (may be null to query the count).  Host code only: needs no device. */
 int32_t mcskin_partition_tiles(const McScene* scene, const McConfig* cfg, int32_t n_parts, int32_t part,
                                int32_t root_part, int32_t* out_tiles, int32_t capacity);
+/* Host code only: copies `rows` rows of `row_bytes` from src to dst (pitches in bytes), cut into `pieces` jobs for the
+ * library's host copy threads — the ones that carry a frame from the page-locked staging image into a pageable
+ * destination (mcskin_cuda_render into an Image's std::vector<Color>) while the GPU is still shading.  Needs no device. */
+int32_t mcskin_host_copy_rows(void* dst, const void* src, uint64_t dst_pitch, uint64_t src_pitch, uint64_t row_bytes,
+                              uint64_t rows, int32_t pieces);
 /* Page-locks a host range (e.g. a shared-memory segment every process of the box has mapped) and maps it into
  * the device address space: *d_ptr is what kernels store to (zero-copy over PCIe), so N GPUs can write their
  * tiles of one frame into one host image through N PCIe links at once. */

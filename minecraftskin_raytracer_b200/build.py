@@ -19,7 +19,7 @@ LIB_PATH = LIB_DIR / "libmcskin_cuda.so"
 # kernels_counter.cu / wavefront_counter.cu: the general kernels with counter-based random streams (McConfig::rng_mode 1)
 CUDA_SOURCES = ["kernels.cu", "wavefront.cu", "kernels_plain.cu", "wavefront_plain.cu", "kernels_counter.cu",
                 "wavefront_counter.cu", "capi.cu"]
-HOST_SOURCES = ["host_prep.cpp", "skin_scene.cpp"]
+HOST_SOURCES = ["host_prep.cpp", "skin_scene.cpp", "host_copy.cpp"]
 
 # --fmad=false: the geometry chain must round like the x86-64 reference build (no FMA);
 # IEEE division and sqrt are nvcc's defaults and are left alone (no -use_fast_math).

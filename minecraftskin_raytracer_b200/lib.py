@@ -25,7 +25,7 @@ DEFAULT_FRAME_LANES = 2
 
 # every symbol include/mcskin_cuda.h declares
 EXPORTS = [
-    "mcskin_config_defaults", "mcskin_counter_word", "mcskin_generate_tiles", "mcskin_cuda_device_count", "mcskin_cuda_last_error",
+    "mcskin_config_defaults", "mcskin_counter_word", "mcskin_host_copy_rows", "mcskin_generate_tiles", "mcskin_cuda_device_count", "mcskin_cuda_last_error",
     "mcskin_cuda_abi_version", "mcskin_cuda_abi_sizes", "mcskin_cuda_render", "mcskin_cuda_render_tile",
     "mcskin_cuda_render_multi", "mcskin_cuda_context_create", "mcskin_cuda_context_destroy",
     "mcskin_cuda_context_set_scene", "mcskin_cuda_context_render_bands", "mcskin_cuda_band_rows",
@@ -115,6 +115,15 @@ def config_defaults() -> McConfig:
 def counter_word(seed: int, k: int) -> int:
     """Word k of the counter-based stream seeded `seed` (McConfig.rng_mode 1; mc_rng_counter_word in mcskin_cuda.h)."""
     return int(_lib.mcskin_counter_word(seed & 0xFFFFFFFF, k & 0xFFFFFFFF))
+
+
+def host_copy_rows(dst: np.ndarray, src: np.ndarray, row_bytes: int, rows: int, pieces: int = 8,
+                   dst_pitch: int | None = None, src_pitch: int | None = None):
+    """mcskin_host_copy_rows over two byte arrays (the library's host copy threads; no device needed)."""
+    _check(_lib.mcskin_host_copy_rows(C.c_void_p(dst.ctypes.data), C.c_void_p(src.ctypes.data),
+                                      C.c_uint64(row_bytes if dst_pitch is None else dst_pitch),
+                                      C.c_uint64(row_bytes if src_pitch is None else src_pitch),
+                                      C.c_uint64(row_bytes), C.c_uint64(rows), C.c_int32(pieces)))
 
 
 def generate_tiles(width: int, height: int, tile_size: int) -> np.ndarray:

@@ -301,3 +301,31 @@ def test_partition_tiles_covers_the_frame_and_balances(mclib):
     assert sorted(np.concatenate(parts).tolist()) == [0, 1, 2, 3]
     with pytest.raises(mclib.McSkinError):
         mclib.partition_tiles(scene, cfg, 4, 4)
+
+
+def test_host_copy_threads(mclib):
+    """The host threads that carry finished pieces of a frame into pageable images (csrc/host_copy.cpp): pitched rows,
+    aligned (streaming stores) and unaligned (memcpy) ends, more pieces than rows, several callers at once."""
+    import threading
+    rng = np.random.default_rng(3)
+    for row_bytes, rows, dst_off, src_off, pieces in ((30720, 97, 0, 0, 8), (30720, 97, 4, 0, 5), (1000, 13, 0, 16, 64),
+                                                       (64, 1, 0, 0, 3), (4096, 700, 16, 32, 37), (17, 5, 1, 3, 2)):
+        src_pitch, dst_pitch = row_bytes + 48, row_bytes + 80
+        src = rng.integers(0, 256, size=src_off + src_pitch * rows + 64, dtype=np.uint8)
+        dst = np.full(dst_off + dst_pitch * rows + 64, 0xEE, dtype=np.uint8)
+        mclib.host_copy_rows(dst[dst_off:], src[src_off:], row_bytes, rows, pieces, dst_pitch=dst_pitch, src_pitch=src_pitch)
+        want = np.full_like(dst, 0xEE)
+        for r in range(rows):
+            want[dst_off + r * dst_pitch: dst_off + r * dst_pitch + row_bytes] = src[src_off + r * src_pitch: src_off + r * src_pitch + row_bytes]
+        assert np.array_equal(dst, want), (row_bytes, rows, dst_off, src_off, pieces)
+    # concurrent callers share the pool one call at a time
+    src = rng.integers(0, 256, size=(6, 1 << 20), dtype=np.uint8)
+    dst = np.zeros_like(src)
+    threads = [threading.Thread(target=lambda i=i: [mclib.host_copy_rows(dst[i], src[i], 4096, 256, 16) for _ in range(5)]) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert np.array_equal(dst, src)
+    with pytest.raises(mclib.McSkinError):
+        mclib.host_copy_rows(dst[0], src[0], 4096, 4, 2, dst_pitch=100)
