@@ -1543,6 +1543,8 @@ int32_t mcskin_cuda_context_sync(McContext* ctx, McRenderStats* stats) {
 static int render_host_staged(McContext* ctx, float* outF32, uint8_t* outU8, int tx0, int tx1, int ty0, int ty1, McRenderStats* stats) {
     const DevFrame& f = ctx->prep.frame;
     const size_t pixels = static_cast<size_t>(f.width) * f.height;
+    // (page-locked memory is a scarce resource of the host: frames beyond 1 GiB of staging take the plain route)
+    if (pixels * ((outF32 ? sizeof(float4) : 0) + (outU8 ? sizeof(uchar4) : 0)) > (size_t(1) << 30)) return MC_ERR_LIMIT;
     if (outF32) CU_TRY(ctx->stageF32.reserve(pixels * sizeof(float4)));
     if (outU8) CU_TRY(ctx->stageU8.reserve(pixels * sizeof(uchar4)));
     void* aliasF32 = outF32 ? device_alias_of_host(ctx->stageF32.p) : nullptr;
