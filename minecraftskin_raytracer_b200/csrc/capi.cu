@@ -1545,8 +1545,11 @@ static int render_host_staged(McContext* ctx, float* outF32, uint8_t* outU8, int
     const size_t pixels = static_cast<size_t>(f.width) * f.height;
     // (page-locked memory is a scarce resource of the host: frames beyond 1 GiB of staging take the plain route)
     if (pixels * ((outF32 ? sizeof(float4) : 0) + (outU8 ? sizeof(uchar4) : 0)) > (size_t(1) << 30)) return MC_ERR_LIMIT;
-    if (outF32) CU_TRY(ctx->stageF32.reserve(pixels * sizeof(float4)));
-    if (outU8) CU_TRY(ctx->stageU8.reserve(pixels * sizeof(uchar4)));
+    if ((outF32 && ctx->stageF32.reserve(pixels * sizeof(float4)) != cudaSuccess) ||
+        (outU8 && ctx->stageU8.reserve(pixels * sizeof(uchar4)) != cudaSuccess)) {
+        cudaGetLastError();  // (no page-locked memory to be had: the plain route needs none of this size... or fails on its own)
+        return MC_ERR_LIMIT;
+    }
     void* aliasF32 = outF32 ? device_alias_of_host(ctx->stageF32.p) : nullptr;
     void* aliasU8 = outU8 ? device_alias_of_host(ctx->stageU8.p) : nullptr;
     if ((outF32 && !aliasF32) || (outU8 && !aliasU8)) return MC_ERR_LIMIT;  // (not mapped: the caller takes the plain route)
