@@ -741,10 +741,11 @@ __device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from
     // so the slab fractions of the ungrown box are computed once and serve both passes.
     const V3 ainv = mk3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
     const V3 g1 = ainv * growFull;
-    for (int i = 0; i < n; ++i) {
+    auto reaches = [&](int i, uint32_t* children) {
         const float4 L = sc.lo[i];
         const float4 H = sc.hi[i];
-        if (__float_as_uint(L.w) & kBoxEmpty) continue;
+        *children = __float_as_uint(H.w);
+        if (__float_as_uint(L.w) & kBoxEmpty) return false;
         // A ray that starts beyond a slab of the box and moves further away along that axis cannot
         // enter the box (the reference's own slab test gives tmax < 0 for it).  Every ray of the
         // bundle has a direction within growFull of d, so this holds for all of them at once.  It is
@@ -753,7 +754,7 @@ __device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from
         if ((from.x > H.x && d.x > growFull) || (from.x < L.x && d.x < -growFull) ||
             (from.y > H.y && d.y > growFull) || (from.y < L.y && d.y < -growFull) ||
             (from.z > H.z && d.z > growFull) || (from.z < L.z && d.z < -growFull))
-            continue;
+            return false;
         const float ax = (L.x - from.x) * inv.x, bx = (H.x - from.x) * inv.x;
         const float ay = (L.y - from.y) * inv.y, by = (H.y - from.y) * inv.y;
         const float az = (L.z - from.z) * inv.z, bz = (H.z - from.z) * inv.z;
@@ -762,13 +763,37 @@ __device__ __forceinline__ uint32_t bundle_box_mask(const SceneView& sc, V3 from
         const float nz = fminf(az, bz), fz = fmaxf(az, bz);
         const float s0 = fmaxf(fmaxf(nx - g1.x, ny - g1.y), fmaxf(nz - g1.z, 0.0f));
         const float s1 = fminf(fminf(fx + g1.x, fy + g1.y), fminf(fz + g1.z, 1.0f));
-        if (!(s0 <= s1 + 1e-3f)) continue;
+        if (!(s0 <= s1 + 1e-3f)) return false;
         const float reach = fminf(fmaxf(s1 + 1e-3f, 0.0f), 1.0f);
         const V3 g2 = ainv * (reach * radius * 1.01f + 0.01f);
         const float t0 = fmaxf(fmaxf(nx - g2.x, ny - g2.y), fmaxf(nz - g2.z, 0.0f));
         const float t1 = fminf(fminf(fx + g2.x, fy + g2.y), fminf(fz + g2.z, 1.0f));
-        if (!(t0 <= t1 + 1e-3f)) continue;
-        mask |= 1u << i;
+        return t0 <= t1 + 1e-3f;
+    };
+    if (sc.root_mask != 0u) {
+        // Two levels, as in candidate_mask: a box enclosed by another one (an inner body part inside its outer layer, with
+        // room to spare on every side) lies inside everything this test grows the enclosing box to, and beyond every
+        // slab the bundle leaves the enclosing box behind — a bundle that cannot reach the root cannot reach it either.
+        const uint32_t all = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+        uint32_t enclosed = 0u;
+        for (uint32_t m = sc.root_mask & all; m; m &= m - 1u) {
+            const int i = __ffs(m) - 1;
+            uint32_t children;
+            if (reaches(i, &children)) {
+                mask |= 1u << i;
+                enclosed |= children;
+            }
+        }
+        for (uint32_t m = enclosed & all; m; m &= m - 1u) {
+            const int i = __ffs(m) - 1;
+            uint32_t unused;
+            if (reaches(i, &unused)) mask |= 1u << i;
+        }
+        return drop_unreached_posed(sc, from, d, radius, mask);
+    }
+    for (int i = 0; i < n; ++i) {
+        uint32_t unused;
+        if (reaches(i, &unused)) mask |= 1u << i;
     }
     return drop_unreached_posed(sc, from, d, radius, mask);
 }
