@@ -1,5 +1,5 @@
 // host_copy.hpp — a few host threads that move finished pieces of a frame from the library's page-locked staging image to
-// a caller's pageable image (an Image's std::vector<Color>: what TileRenderer::render returns, tile_renderer.cpp:129-143)
+// a caller's pageable image (an Image's std::vector<Color>: what TileRenderer::render returns, tile_renderer.cpp:129-189)
 // while the GPU is still shading the rest of the frame.
 #pragma once
 #include <cuda_runtime.h>
