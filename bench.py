@@ -472,10 +472,16 @@ def run_own_arm(args):
                                "what": "back-to-back frames (CUDA graph replay, no L2 flush between frames), CUDA events around the whole run, max over ranks",
                                "clocks": sampler.window(s0, s1) if rank == 0 else None}
         # ---- the frame with the per-tile engine seeding inside (k_tile_seed; cached across frames of equal geometry otherwise)
+        # (and without the memo of the shadow engines' seeding recurrence, shadow_seed_memo: the frame with nothing kept
+        # from earlier frames but its buffers and the captured graph)
         job.ctx.set_option("cache_tile_seeds", 0)
+        job.ctx.set_option("shadow_seed_memo", 0)
         seed_ms, _, _, _ = time_steps(torch, dist, job, flush, max(3, min(args.steps, 10)), 3, world, dev)
         job.ctx.set_option("cache_tile_seeds", 1)
+        job.ctx.set_option("shadow_seed_memo", 1)
         extras["ms_per_step_with_tile_seed"] = seed_ms
+        extras["ms_per_step_with_tile_seed_what"] = ("the frame with k_tile_seed inside (cache_tile_seeds 0) and every shaded hit's "
+                                                     "engine seeded by the 396-step recurrence (shadow_seed_memo 0)")
 
     # ---- e2e: host scene in, host image out, copies inside the timed region
     h2d_bytes = scene.boxes.nbytes + scene.texels.nbytes + C.sizeof(_abi.McScene) + C.sizeof(_abi.McConfig)

@@ -183,6 +183,8 @@ struct McContext {
     PinnedBuf countHost;                   // ... and where the frame's last kernel (or a copy) leaves them for the statistics
     unsigned int* countAlias = nullptr;    // countHost as the device addresses it (null: not mapped)
     PinnedBuf sceneStage;                  // page-locked staging of the scene blob and texels (upload_scene)
+    DevBuf seedMemo;                       // FreshStream::seed_memo's table (dev_mt19937.cuh), shared with the lanes
+    int shadowSeedMemo = 1;                // option "shadow_seed_memo"
     PinnedBuf stageF32, stageU8;           // page-locked staging images for pageable destinations (render_host_staged)
     std::vector<cudaEvent_t> pieceEvents;  // one per piece of the staging image on its way to the host
     int stagedCopyOut = 1;                 // option "staged_copy_out": pageable destinations are filled piece by piece during the frame
@@ -257,6 +259,24 @@ struct BandSpec {
     float4* hotF32 = nullptr;  // BandView::hot_*: where the tiles the figure's rectangle touches are written instead
     uchar4* hotU8 = nullptr;
 };
+
+// The table of FreshStream::seed_memo, allocated and zeroed the first time a frame with soft shadows comes in (never
+// inside a graph capture: the frame that is captured has been rendered once before).  Null when switched off.
+static uint2* seed_memo_of(McContext* ctx) {
+    if (!ctx->shadowSeedMemo) return nullptr;
+    if (!ctx->seedMemo.p) {
+        if (ctx->capturing) return nullptr;
+        const size_t bytes = static_cast<size_t>(kSeedMemoEntries) * sizeof(uint2);
+        if (ctx->seedMemo.reserve(bytes) != cudaSuccess || cudaMemsetAsync(ctx->seedMemo.p, 0, bytes, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {  // (zeroed before any stream of a frame can read it)
+            cudaGetLastError();
+            ctx->seedMemo.release();
+            ctx->shadowSeedMemo = 0;  // no memory for it: the frames are the same without
+            return nullptr;
+        }
+    }
+    return static_cast<uint2*>(ctx->seedMemo.p);
+}
 
 // Is p (an output image the kernels store to) anything but this context's device memory: a mapped host range, a
 // peer device's allocation?  The last answers are kept: the pointers of a render loop repeat.
@@ -377,6 +397,8 @@ int render_bands_lane(McContext* ctx, const McContext* scn, const BandSpec& spec
                              ctx->smCount * ctx->shadeBlocksPerSm, &wave))
             return fail(MC_ERR_CUDA, "wavefront buffer carve failed");
         wave.softGrid = ctx->smCount * ctx->softBlocksPerSm;
+        wave.seedMemo = static_cast<uint2*>(scn->seedMemo.p);  // (render_bands has seen to it; the lanes of a frame share it)
+        if (!scn->shadowSeedMemo) wave.seedMemo = nullptr;
     }
     if (!ctx->capturing) CU_TRY(cudaEventRecord(ctx->ev0, stream));
     const FramePointers fp = frame_pointers(scn);
@@ -537,7 +559,7 @@ int launch_frame_lanes(McContext* ctx, int first, int stride, int L, float4* out
 
 long long option_bits(const McContext* c, int i) {
     const long long v[12] = {c->forceAllActive, c->recordBudgetBytes, c->shadeBlocksPerSm, c->primaryBlocksPerSm,
-                             c->waveQueuePct, c->shadeMode, c->waveBudgetBytes, 0,
+                             c->waveQueuePct, c->shadeMode, c->waveBudgetBytes, c->shadowSeedMemo,
                              c->softBlocksPerSm, c->cacheTileSeeds, c->heavyTilesPerSm, c->frameLanes};
     return v[i];
 }
@@ -565,6 +587,7 @@ int render_bands(McContext* ctx, int first, int stride, float4* outF32, uchar4* 
     const int L = (ctx->isChild || tiles) ? 1 : std::max(1, std::min(ctx->frameLanes, nRows / 2));
     ctx->splitLastRender = 0;
     ctx->graphLastRender = false;
+    if (!ctx->isChild && f.soft_on) seed_memo_of(ctx);
     if (stream != ctx->stream && ctx->evUpload) CU_TRY(cudaStreamWaitEvent(stream, ctx->evUpload, 0));
     if (L > 1) {
         const int rc = ensure_lanes(ctx, L - 1);
@@ -962,6 +985,7 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, const SkinBatchS
     CU_TRY(ctx->batchSlots.reserve(static_cast<size_t>(G) * slotCap * sizeof(uint2)));
     CU_TRY(ctx->batchRecords.reserve(static_cast<size_t>(G) * recordBytes));
     CU_TRY(ctx->batchWave.reserve(static_cast<size_t>(G) * waveBytes));
+    uint2* const batchSeedMemo = f0.soft_on ? seed_memo_of(ctx) : nullptr;
     CU_TRY(ctx->batchCounts.reserve(static_cast<size_t>(G) * sizeof(unsigned int)));
     CU_TRY(ctx->tileStates.reserve(std::max<size_t>(16, static_cast<size_t>(f0.tiles_x) * f0.tiles_y * 624 * sizeof(uint32_t) *
                                                             static_cast<size_t>(primary_states_per_tile(f0, f0.tiles_x * f0.tiles_y, 1, ctx->smCount * ctx->primaryBlocksPerSm, 0)))));
@@ -1070,6 +1094,7 @@ int render_batch_grouped(McContext* ctx, const McScene* scenes, const SkinBatchS
                 if (!wavefront_carve(pf.frame, static_cast<unsigned char*>(ctx->batchWave.p) + static_cast<size_t>(i) * waveBytes,
                                      waveBytes, static_cast<unsigned int>(paths), static_cast<unsigned int>(entries), gridX, &sl.wave))
                     return MC_OK;  // (cannot happen: the sizes depend on the config only) frame-by-frame path instead
+                sl.wave.seedMemo = batchSeedMemo;
                 stageSlices[sliceAt++] = sl;
             }
         }
@@ -1164,6 +1189,7 @@ int32_t mcskin_cuda_context_create(int32_t device, McContext** out) {
     if (const char* v = std::getenv("MCSKIN_BATCH_MODE")) ctx->batchMode = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_GRAPHS")) ctx->useGraphs = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_STAGED_COPY")) ctx->stagedCopyOut = std::atoi(v) != 0;
+    if (const char* v = std::getenv("MCSKIN_SEED_MEMO")) ctx->shadowSeedMemo = std::atoi(v) != 0;
     if (const char* v = std::getenv("MCSKIN_OVERLAP_COPY")) ctx->overlapCopyOut = std::min(2, std::max(0, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_FRAME_LANES")) ctx->frameLanes = std::min(8, std::max(1, std::atoi(v)));
     if (const char* v = std::getenv("MCSKIN_CACHE_TILE_SEEDS")) ctx->cacheTileSeeds = std::atoi(v) != 0;
@@ -1187,6 +1213,7 @@ void mcskin_cuda_context_destroy(McContext* ctx) {
     ctx->pinned.release();
     ctx->countHost.release();
     ctx->sceneStage.release();
+    ctx->seedMemo.release();
     ctx->stageF32.release();
     ctx->stageU8.release();
     for (cudaEvent_t e : ctx->pieceEvents) cudaEventDestroy(e);
@@ -1232,6 +1259,7 @@ int32_t mcskin_cuda_context_set_option(McContext* ctx, const char* name, int64_t
     else if (k == "overlap_copy_out") ctx->overlapCopyOut = static_cast<int>(std::min<int64_t>(2, std::max<int64_t>(0, value)));
     else if (k == "wave_budget_bytes") ctx->waveBudgetBytes = std::max<int64_t>(1 << 20, value);
     else if (k == "staged_copy_out") ctx->stagedCopyOut = value != 0;
+    else if (k == "shadow_seed_memo") ctx->shadowSeedMemo = value != 0;
     else return fail(MC_ERR_INVALID, "set_option: unknown option " + k);
     return MC_OK;
 }

@@ -106,6 +106,33 @@ struct FreshStream {
         j = 0u;
     }
 
+    // The same with a memo of the seeding recurrence.  Word 397 of the seeded state is a function of the seed alone, and
+    // traceRay's shadow seeds (raytracer.cpp:110-112: a weighted sum of the hit's coordinates cast to unsigned) are
+    // small integers — a figure's hits fall into a few million of them, every one used again and again, by the next
+    // sample, the next frame, the next scene.  cache: kSeedMemoEntries pairs (seed ^ kSeedMemoTag, word 397), zeroed
+    // once (the tag is outside the window, so a zero entry matches no seed); an 8-byte entry is stored and loaded
+    // whole, and every writer of an entry writes the same pair, so no ordering is needed.  Seeds outside the window,
+    // or a null cache: the recurrence.
+    __device__ __forceinline__ void seed_memo(uint32_t s, uint32_t one, uint2* cache) {
+        if (kCounterRng || !cache) {
+            seed_balanced(s, one);
+            return;
+        }
+        const uint32_t idx = s + kSeedMemoOffset;  // (wraps: seeds just below zero come from negative sums)
+        if (idx < kSeedMemoEntries) {
+            const uint2 e = __ldcg(cache + idx);
+            if (e.x == (s ^ kSeedMemoTag)) {
+                cur = s;
+                nxt = mt_lcg(s, 1u);
+                far = e.y;
+                j = 0u;
+                return;
+            }
+        }
+        seed_balanced(s, one);
+        if (idx < kSeedMemoEntries) __stcg(cache + idx, make_uint2(s ^ kSeedMemoTag, far));
+    }
+
     __device__ __forceinline__ void seed(uint32_t s) {
         if (kCounterRng) {
             cur = counter_key(s);

@@ -38,6 +38,12 @@
 
 namespace mcskin {
 
+// memo of the engines' seeding (FreshStream::seed_memo): seeds in [-2^20, 2^23 - 2^20), 64 MB
+constexpr uint32_t kSeedMemoEntries = 1u << 23;
+constexpr uint32_t kSeedMemoOffset = 1u << 20;
+constexpr uint32_t kSeedMemoTag = 0x5bd1e995u;  // not a seed of the window: an all-zero entry is never valid
+
+
 constexpr bool kPosedScenes = MCSKIN_POSED != 0;
 constexpr bool kCounterRng = MCSKIN_COUNTER_RNG != 0;
 constexpr int kFaceCount = 6;

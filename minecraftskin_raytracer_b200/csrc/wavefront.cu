@@ -331,7 +331,7 @@ k_wf_softshadow(const DevFrame fr, const FramePointers fp_, const WaveView wv_, 
                     const V3 P = mk3(eP.x, eP.y, eP.z);
                     FreshStream rng;
                     if (round == 0) {
-                        rng.seed_balanced(__float_as_uint(eP.w), one);
+                        rng.seed_memo(__float_as_uint(eP.w), one, wv.seedMemo);
                     } else {
                         const uint4 e = sm->engine[tid];
                         rng.cur = e.x; rng.nxt = e.y; rng.far = e.z; rng.j = e.w;

@@ -55,6 +55,7 @@ struct WaveView {
     int shadowRays;          // rays per hit cast by the shadow kernel
     int gridBlocks;
     int softGrid;            // blocks of the soft-shadow kernel (persistent: what fits the device at once)
+    uint2* seedMemo;         // FreshStream::seed_memo's table (kSeedMemoEntries entries), or null
 };
 
 enum : int {

@@ -194,6 +194,7 @@ RENDER_MODES = {
     "one_lane_no_graph": {"frame_lanes": 1, "use_graphs": 0, "cache_tile_seeds": 0},
     "five_lanes": {"frame_lanes": 5},
     "two_soft_blocks": {"soft_blocks_per_sm": 1, "shade_blocks_per_sm": 2, "frame_lanes": 2},
+    "no_seed_memo": {"shadow_seed_memo": 0},              # every shaded hit's engine seeded by the recurrence (default: memoized per seed)
 }
 
 
