@@ -443,6 +443,7 @@ def run_own_arm(args):
         dist.barrier()
 
     extras = {}
+    nomemo_ms = None
     if not args.kernel_only:
         # ---- sustained: >= 2 s of back-to-back frames (no flush: a frame's queue traffic alone exceeds the L2)
         for _ in range(3):
@@ -482,6 +483,12 @@ def run_own_arm(args):
         extras["ms_per_step_with_tile_seed"] = seed_ms
         extras["ms_per_step_with_tile_seed_what"] = ("the frame with k_tile_seed inside (cache_tile_seeds 0) and every shaded hit's "
                                                      "engine seeded by the 396-step recurrence (shadow_seed_memo 0)")
+        # ---- the configuration the committed ncu capture was taken in (tile seeds kept, no seed memo): the frame
+        #      time its instruction count is set against (roofline.frac_executed)
+        job.ctx.set_option("shadow_seed_memo", 0)
+        nomemo_ms, _, _, _ = time_steps(torch, dist, job, flush, max(3, min(args.steps, 10)), 3, world, dev)
+        job.ctx.set_option("shadow_seed_memo", 1)
+        extras["ms_per_step_without_seed_memo"] = nomemo_ms
 
     # ---- e2e: host scene in, host image out, copies inside the timed region
     h2d_bytes = scene.boxes.nbytes + scene.texels.nbytes + C.sizeof(_abi.McScene) + C.sizeof(_abi.McConfig)
@@ -578,7 +585,9 @@ def run_own_arm(args):
     if counters and world == 1 and not emulate and device_ms > 0:
         # issue slots used by the frame's warp instructions (ncu smsp__inst_executed.sum over the frame's kernels)
         # / issue slots the chip has in the measured frame time (4 schedulers per SM, one instruction per clock each)
-        frac_executed = counters["warp_instructions_per_frame"] / (sm_count * 4 * sm_hz * device_ms * 1e-3)
+        # (a capture taken without the seed memo is set against the time of such a frame)
+        counted_ms = nomemo_ms if (counters.get("captured_without_seed_memo") and nomemo_ms) else device_ms
+        frac_executed = counters["warp_instructions_per_frame"] / (sm_count * 4 * sm_hz * counted_ms * 1e-3)
     partition = "whole frame"
     if world > 1:
         partition = (f"cost-balanced tile sets over {world} GPUs (mcskin_partition_tiles), stored into rank 0's frame over NVLink peer memory + flag barrier"
@@ -609,7 +618,9 @@ def run_own_arm(args):
             "traffic": counters["dram_bytes_per_frame"] if (counters and world == 1 and not emulate) else None,
             "traffic_source": str(FRAME_COUNTERS.relative_to(ROOT)) if counters else None,
             "frac_executed": frac_executed,
-            "frac_executed_source": "warp instructions of one frame (ncu smsp__inst_executed.sum, same capture) / (SMs x 4 schedulers x sampled SM clock x ms_per_launch)" if frac_executed else None,
+            "frac_executed_source": ("warp instructions of one frame (ncu smsp__inst_executed.sum, same capture) / (SMs x 4 schedulers x sampled SM clock x "
+                                     + ("ms_per_step_without_seed_memo: the capture was taken without the seed memo, whose frame executes fewer instructions)"
+                                        if (counters and counters.get("captured_without_seed_memo") and nomemo_ms) else "ms_per_launch)")) if frac_executed else None,
             "peak_source": f"{sm_count} SMs x 128 FP32 lanes x {peaks['sm_max_mhz']:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json"
                            + (", fallback" if peaks.get("_fallback") else "") + "); non-FMA issue rate, SURVEY.md §8d",
             "peak_measured": fp32_peak_measured,
