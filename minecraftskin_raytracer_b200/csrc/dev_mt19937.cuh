@@ -111,8 +111,8 @@ struct FreshStream {
     // small integers — a figure's hits fall into a few million of them, every one used again and again, by the next
     // sample, the next frame, the next scene.  cache: kSeedMemoEntries pairs (seed ^ kSeedMemoTag, word 397), zeroed
     // once (the tag is outside the window, so a zero entry matches no seed); an 8-byte entry is stored and loaded
-    // whole, and every writer of an entry writes the same pair, so no ordering is needed.  Seeds outside the window,
-    // or a null cache: the recurrence.
+    // whole (one STG.E.64 / LDG.E.64 at L2, checked in the SASS), and every writer of an entry writes the same
+    // pair, so no ordering is needed.  Seeds outside the window, or a null cache: the recurrence.
     __device__ __forceinline__ void seed_memo(uint32_t s, uint32_t one, uint2* cache) {
         if (kCounterRng || !cache) {
             seed_balanced(s, one);
