@@ -148,3 +148,28 @@ def test_oracle_counter_mode_changes_the_noise_only(oracle, mclib):
     assert abs(float(a[..., :3].mean()) - float(b[..., :3].mean())) < 2e-3
     assert float(np.abs(a - b).mean()) < 0.02
     # the unmodified reference has no such switch: its wrapper ignores the field
+
+
+def test_shadow_seeds_of_a_figure_fall_into_the_memo_window(oracle, mclib):
+    """The premise of the product's seed memo (FreshStream::seed_memo, csrc/dev_mt19937.cuh): traceRay's shadow seed,
+    unsigned(x*12345 + y*67890 + z*11111 + depth*99999) (raytracer.cpp:110-112), is a small integer for every point of a
+    skin figure in every built-in pose and at every bounce depth, inside the table's window [-2^20, 2^23 - 2^20) — and
+    many hits share one seed, which is what makes keeping its seeding worth while."""
+    from minecraftskin_raytracer_b200 import lib
+    from minecraftskin_raytracer_b200.scene import BUILTIN_POSE_ORDER
+    offset, entries = 1 << 20, 1 << 23
+    for pose in BUILTIN_POSE_ORDER:
+        scene = lib.build_skin_scene(synth_skin(3, "64x64"), None if pose == "standing" else pose)
+        rays = random_rays(np.random.default_rng(11), 6000)
+        hits = oracle.intersect(scene, rays)
+        p = hits["point"][hits["hit"] == 1].astype(np.float32)
+        assert len(p) > 500
+        for depth in (0, 4, 8):
+            v = (p[:, 0] * np.float32(12345.0) + p[:, 1] * np.float32(67890.0) + p[:, 2] * np.float32(11111.0)
+                 + np.float32(depth) * np.float32(99999.0)).astype(np.float32)
+            seeds = v.astype(np.int64).astype(np.uint32)          # cvttss2si to 64 bits, low half (x86-64 semantics)
+            index = (seeds + np.uint32(offset)).astype(np.uint32)  # wraps like the device's
+            assert (index < entries).all(), (pose, depth, int((index >= entries).sum()))
+    # the headline frame: 2.8 M shaded hits (tests/golden/work_counts.json) over a window of 8.4 M seeds of which a
+    # figure reaches a third at most
+    assert 32 * 67890 + 8 * 12345 + 5 * 11111 + 8 * 99999 < entries - offset
